@@ -1,0 +1,876 @@
+// sm_100a kernels + C ABI of the FlowMap optimisation hot path (see include/flowmap_b200.h).
+//
+// Roofline: everything here is pointwise + reduction work over (frame, H, W) tensors --
+// HBM-bound, no tensor cores.  Per frame pair the algorithmic traffic is 32 B per
+// pair-pixel + 8 B per frame-pixel.
+//
+// Version-1 structure (one launch per phase over all pairs):
+//   k_moments      phase A  weighted moment sums per pair (bilinear gather of the earlier
+//                           frame at xy + backward flow), fp32 per thread -> fp64 block
+//                           reduction -> fp64 atomics                (projection.py:213-249)
+//   k_solve        phase B  16 moments -> C -> Jacobi SVD -> [R|t], saved state
+//                                                                    (procrustes.py:7-51)
+//   k_flow         phase C  per frame: forward term of pair k and backward term of pair
+//                           k-1 share the unprojected point; loss, direct depth gradient
+//                           (plain store), pose / intrinsics partial sums
+//                                                  (loss_flow.py:31-70, projection.py:116-184)
+//   k_adjoint      phase D1 pose gradient -> per-pair adjoint constants
+//   k_distribute   phase D2 per-point adjoints: aligned add into the later frame,
+//                           bilinear scatter into the earlier frame, weight gradient
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/flowmap_b200.h"
+#include "fm_pixel.cuh"
+
+namespace {
+
+using namespace fm;
+
+thread_local char g_err[512] = "";
+
+int fail(const char* what, cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return 1;
+}
+int fail_msg(const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s", what);
+  return 2;
+}
+#define FM_CHECK_LAUNCH(name)                          \
+  do {                                                 \
+    cudaError_t e_ = cudaGetLastError();               \
+    if (e_ != cudaSuccess) return fail(name, e_);      \
+  } while (0)
+
+constexpr int kThreads = 256;
+constexpr int kFlowAcc = 40;  // per-frame accumulator slots of k_flow
+
+// ---------------------------------------------------------------- workspace layout
+struct Workspace {
+  double* moments;   // [BP][16]
+  double* flowacc;   // [BF][kFlowAcc]
+  double* k4acc;     // [BF][4]
+  double* loss;      // [4]
+  PairState* state;  // [BP]
+  PairAdjoint* adj;  // [BP]
+  size_t bytes;
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+Workspace carve(void* base, int B, int F) {
+  const size_t BP = (size_t)B * (F - 1), BF = (size_t)B * F;
+  char* p = (char*)base;
+  size_t off = 0;
+  Workspace w;
+  w.moments = (double*)(p + off); off = align_up(off + BP * kNumMoments * sizeof(double), 256);
+  w.flowacc = (double*)(p + off); off = align_up(off + BF * kFlowAcc * sizeof(double), 256);
+  w.k4acc = (double*)(p + off); off = align_up(off + BF * 4 * sizeof(double), 256);
+  w.loss = (double*)(p + off); off = align_up(off + 4 * sizeof(double), 256);
+  w.state = (PairState*)(p + off); off = align_up(off + BP * sizeof(PairState), 256);
+  w.adj = (PairAdjoint*)(p + off); off = align_up(off + BP * sizeof(PairAdjoint), 256);
+  w.bytes = off;
+  return w;
+}
+
+// ---------------------------------------------------------------- small device helpers
+__device__ __forceinline__ K4 load_k4(const float* k4, int frame) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(k4) + frame);
+  K4 k; k.fx = v.x; k.fy = v.y; k.cx = v.z; k.cy = v.w;
+  return k;
+}
+
+__device__ __forceinline__ Rt load_rt(const float* rt, int pair) {
+  Rt t;
+  const float* s = rt + (size_t)pair * 12;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    t.r[r * 3 + 0] = __ldg(s + r * 4 + 0);
+    t.r[r * 3 + 1] = __ldg(s + r * 4 + 1);
+    t.r[r * 3 + 2] = __ldg(s + r * 4 + 2);
+    t.t[r] = __ldg(s + r * 4 + 3);
+  }
+  return t;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of NV per-thread values, result atomically added (fp64) to dst[0..NV).
+// smem must hold NV * (kThreads / 32) doubles.
+template <int NV>
+__device__ __forceinline__ void block_accumulate(const float* vals, double* dst, double* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kThreads / 32;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = warp_sum((double)vals[i]);
+    if (lane == 0) smem[i * NW + warp] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NV; i += kThreads) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += smem[i * NW + w];
+    if (s != 0.0) atomicAdd(dst + i, s);
+  }
+  __syncthreads();
+}
+
+template <int NV>
+__device__ __forceinline__ void block_accumulate_d(const double* vals, double* dst, double* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kThreads / 32;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = warp_sum(vals[i]);
+    if (lane == 0) smem[i * NW + warp] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NV; i += kThreads) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += smem[i * NW + w];
+    if (s != 0.0) atomicAdd(dst + i, s);
+  }
+  __syncthreads();
+}
+
+// ================================================================== phase A: moments
+__device__ __forceinline__ PairGeom pair_geom(const float* depth, const float* k4, int pair, int F,
+                                              int H, int W) {
+  const int bi = pair / (F - 1), i = pair - bi * (F - 1);
+  const int a = bi * F + i;
+  PairGeom g;
+  g.ka = load_k4(k4, a);
+  g.kb = load_k4(k4, a + 1);
+  g.H = H; g.W = W;
+  g.z0 = __ldg(depth + (size_t)(a + 1) * H * W + (size_t)(H / 2) * W + W / 2);
+  return g;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
+          const float* __restrict__ bflow, const float* __restrict__ weights,
+          const int64_t* __restrict__ indices, int num_indices, double* __restrict__ moments,
+          int F, int H, int W) {
+  __shared__ double smem[kNumMoments * (kThreads / 32)];
+  const int pair = blockIdx.y;
+  const int N = H * W;
+  const PairGeom g = pair_geom(depth, k4, pair, F, H, W);
+  const int frame_a = (pair / (F - 1)) * F + pair % (F - 1);
+  const float* da = depth + (size_t)frame_a * N;
+  const float* db = da + N;
+  const float* fl = bflow + (size_t)pair * N * 2;
+  const float* wt = weights ? weights + (size_t)pair * N : nullptr;
+  auto load_a = [da](int i) { return __ldg(da + i); };
+  double accd[kNumMoments];
+#pragma unroll
+  for (int i = 0; i < kNumMoments; ++i) accd[i] = 0.0;
+
+  if (indices == nullptr) {
+    for (int base = (blockIdx.x * kThreads + threadIdx.x) * VEC; base < N;
+         base += gridDim.x * kThreads * VEC) {
+      float acc[kNumMoments];
+#pragma unroll
+      for (int i = 0; i < kNumMoments; ++i) acc[i] = 0.f;
+      float dv[VEC], wv[VEC], fv[2 * VEC];
+      if (VEC == 4) {
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(db + base));
+        dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
+        if (wt) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wt + base));
+          wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+        } else { wv[0] = wv[1] = wv[2] = wv[3] = 1.f; }
+        const float4 f0 = __ldg(reinterpret_cast<const float4*>(fl + 2 * base));
+        const float4 f1 = __ldg(reinterpret_cast<const float4*>(fl + 2 * base) + 1);
+        fv[0] = f0.x; fv[1] = f0.y; fv[2] = f0.z; fv[3] = f0.w;
+        fv[4] = f1.x; fv[5] = f1.y; fv[6] = f1.z; fv[7] = f1.w;
+      } else {
+        dv[0] = __ldg(db + base);
+        wv[0] = wt ? __ldg(wt + base) : 1.f;
+        fv[0] = __ldg(fl + 2 * base); fv[1] = __ldg(fl + 2 * base + 1);
+      }
+      const int r = base / W, c0 = base - r * W;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float p[3], q[3];
+        Taps taps;
+        point_pq(g, r, c0 + v, dv[v], fv[2 * v], fv[2 * v + 1], load_a, p, q, taps);
+        moments_add(acc, wv[v], p, q);
+      }
+#pragma unroll
+      for (int i = 0; i < kNumMoments; ++i) accd[i] += (double)acc[i];
+    }
+  } else {
+    for (int t = blockIdx.x * kThreads + threadIdx.x; t < num_indices; t += gridDim.x * kThreads) {
+      const int j = (int)indices[t];
+      const int r = j / W, c = j - r * W;
+      float acc[kNumMoments];
+#pragma unroll
+      for (int i = 0; i < kNumMoments; ++i) acc[i] = 0.f;
+      float p[3], q[3];
+      Taps taps;
+      point_pq(g, r, c, __ldg(db + j), __ldg(fl + 2 * j), __ldg(fl + 2 * j + 1), load_a, p, q, taps);
+      moments_add(acc, wt ? __ldg(wt + j) : 1.f, p, q);
+#pragma unroll
+      for (int i = 0; i < kNumMoments; ++i) accd[i] += (double)acc[i];
+    }
+  }
+  block_accumulate_d<kNumMoments>(accd, moments + (size_t)pair * kNumMoments, smem);
+}
+
+// ================================================================== phase B: solve
+__global__ void k_solve(const double* __restrict__ moments, const float* __restrict__ depth,
+                        float* __restrict__ rt, PairState* __restrict__ state, int BP, int F, int H,
+                        int W) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= BP) return;
+  const int bi = pair / (F - 1), i = pair - bi * (F - 1);
+  const int b = bi * F + i + 1;
+  const double z0 = (double)__ldg(depth + (size_t)b * H * W + (size_t)(H / 2) * W + W / 2);
+  double m[kNumMoments];
+  for (int k = 0; k < kNumMoments; ++k) m[k] = moments[(size_t)pair * kNumMoments + k];
+  const double shift[3] = {0.0, 0.0, z0};
+  PairState st;
+  float out[12];
+  procrustes_solve(m, shift, out, st);
+  for (int k = 0; k < 12; ++k) rt[(size_t)pair * 12 + k] = out[k];
+  state[pair] = st;
+}
+
+// ================================================================== phase C: flow loss
+// Accumulator slots per frame k (kFlowAcc doubles):
+//  0        loss numerator (already scaled by weight / mask_sum)
+//  1..9     forward term of pair (k, k+1): A[l][m] = sum (s - t)_l dY_m      (dR)
+//  10..12   forward term: b = sum dY                                        (dt = -R b)
+//  13..21   backward term of pair (k-1, k): sum dX_l s_m                    (dR)
+//  22..24   backward term: sum dX                                           (dt)
+//  25..28   dK_k through the unprojection ray (fx fy cx cy)
+//  29..32   dK_{k+1} through the forward-term projection
+//  33..36   dK_{k-1} through the backward-term projection
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_flow(const float* __restrict__ depth, const float* __restrict__ k4, const float* __restrict__ rt,
+       const float* __restrict__ fflow, const float* __restrict__ bflow,
+       const float* __restrict__ fmask, const float* __restrict__ bmask,
+       const double* __restrict__ mask_sum, int mapping, float delta, float loss_weight,
+       float* __restrict__ g_depth, double* __restrict__ flowacc, int F, int H, int W) {
+  __shared__ double smem[kFlowVals * (kThreads / 32)];
+  const int frame = blockIdx.y;
+  const int bi = frame / F, i = frame - bi * F;
+  const int N = H * W;
+  FlowFrame f;
+  f.hasF = i < F - 1;
+  f.hasB = i > 0;
+  f.kk = load_k4(k4, frame);
+  f.kn = load_k4(k4, f.hasF ? frame + 1 : frame);
+  f.kp = load_k4(k4, f.hasB ? frame - 1 : frame);
+  const int pairF = bi * (F - 1) + i, pairB = pairF - 1;
+  if (f.hasF) f.tf = load_rt(rt, pairF);
+  if (f.hasB) f.tb = load_rt(rt, pairB);
+  double den = mask_sum ? *mask_sum : 1.0;
+  if (den == 0.0) den = 1.0;  // loss_flow.py:70 "valid_sum or 1"
+  const float g = (float)((double)loss_weight / den);
+  const float sc = sqrtf((float)H * (float)W);
+  const float ax = (float)W / sc, ay = (float)H / sc;
+
+  const float* D = depth + (size_t)frame * N;
+  const float* ff = fflow + (size_t)(f.hasF ? pairF : 0) * N * 2;
+  const float* mf = fmask + (size_t)(f.hasF ? pairF : 0) * N;
+  const float* fb = bflow + (size_t)(f.hasB ? pairB : 0) * N * 2;
+  const float* mb = bmask + (size_t)(f.hasB ? pairB : 0) * N;
+  float* gd = g_depth + (size_t)frame * N;
+
+  float acc[kFlowVals];
+#pragma unroll
+  for (int k = 0; k < kFlowVals; ++k) acc[k] = 0.f;
+
+  for (int base = (blockIdx.x * kThreads + threadIdx.x) * VEC; base < N;
+       base += gridDim.x * kThreads * VEC) {
+    float dv[VEC], ffv[2 * VEC], fbv[2 * VEC], mfv[VEC], mbv[VEC], out[VEC];
+    if (VEC == 4) {
+      const float4 d4 = __ldg(reinterpret_cast<const float4*>(D + base));
+      dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
+      if (f.hasF) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(ff + 2 * base));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(ff + 2 * base) + 1);
+        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mf + base));
+        ffv[0] = a0.x; ffv[1] = a0.y; ffv[2] = a0.z; ffv[3] = a0.w;
+        ffv[4] = a1.x; ffv[5] = a1.y; ffv[6] = a1.z; ffv[7] = a1.w;
+        mfv[0] = m4.x; mfv[1] = m4.y; mfv[2] = m4.z; mfv[3] = m4.w;
+      }
+      if (f.hasB) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(fb + 2 * base));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(fb + 2 * base) + 1);
+        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mb + base));
+        fbv[0] = a0.x; fbv[1] = a0.y; fbv[2] = a0.z; fbv[3] = a0.w;
+        fbv[4] = a1.x; fbv[5] = a1.y; fbv[6] = a1.z; fbv[7] = a1.w;
+        mbv[0] = m4.x; mbv[1] = m4.y; mbv[2] = m4.z; mbv[3] = m4.w;
+      }
+    } else {
+      dv[0] = __ldg(D + base);
+      if (f.hasF) { ffv[0] = __ldg(ff + 2 * base); ffv[1] = __ldg(ff + 2 * base + 1); mfv[0] = __ldg(mf + base); }
+      if (f.hasB) { fbv[0] = __ldg(fb + 2 * base); fbv[1] = __ldg(fb + 2 * base + 1); mbv[0] = __ldg(mb + base); }
+    }
+    const int r = base / W, c0 = base - r * W;
+    const float y = pix_y(r, H);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      out[v] = flow_pixel(f, pix_x(c0 + v, W), y, dv[v], f.hasF ? ffv[2 * v] : 0.f,
+                          f.hasF ? ffv[2 * v + 1] : 0.f, f.hasF ? mfv[v] : 0.f,
+                          f.hasB ? fbv[2 * v] : 0.f, f.hasB ? fbv[2 * v + 1] : 0.f,
+                          f.hasB ? mbv[v] : 0.f, g, ax, ay, mapping, delta, acc);
+    }
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(gd + base) = make_float4(out[0], out[1], out[2], out[3]);
+    } else {
+      gd[base] = out[0];
+    }
+  }
+  block_accumulate<kFlowVals>(acc, flowacc + (size_t)frame * kFlowAcc, smem);
+}
+
+// Assemble dL/d[R|t] of pair p (float64, 12 values) from the per-frame accumulators.
+__device__ inline void flow_pose_grad(const double* flowacc, const PairState* st, const float* rt,
+                                      int pair, int F, double* g) {
+  const int bi = pair / (F - 1), i = pair - bi * (F - 1);
+  const int a = bi * F + i;
+  const double* fa = flowacc + (size_t)a * kFlowAcc;        // forward term lives on frame a
+  const double* fb = flowacc + (size_t)(a + 1) * kFlowAcc;  // backward term on frame b
+  double R[9];
+  if (st) { for (int k = 0; k < 9; ++k) R[k] = st[pair].R[k]; }
+  else { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r * 3 + c] = rt[(size_t)pair * 12 + r * 4 + c]; }
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) g[r * 4 + c] = fa[1 + r * 3 + c] + fb[13 + r * 3 + c];
+    g[r * 4 + 3] = fb[22 + r] - (R[r * 3 + 0] * fa[10] + R[r * 3 + 1] * fa[11] + R[r * 3 + 2] * fa[12]);
+  }
+}
+
+// Per-frame dK from the flow loss: own ray term + projection terms of the neighbours.
+__device__ inline void flow_k4_grad(const double* flowacc, int frame, int F, double* g) {
+  const int i = frame % F;
+  const double* f = flowacc + (size_t)frame * kFlowAcc;
+  for (int k = 0; k < 4; ++k) g[k] = f[25 + k];
+  if (i > 0) { const double* p = f - kFlowAcc; for (int k = 0; k < 4; ++k) g[k] += p[29 + k]; }
+  if (i < F - 1) { const double* n = f + kFlowAcc; for (int k = 0; k < 4; ++k) g[k] += n[33 + k]; }
+}
+
+__global__ void k_flow_finalize(const double* __restrict__ flowacc, const float* __restrict__ rt,
+                                float* __restrict__ loss, float* __restrict__ g_rt,
+                                float* __restrict__ g_k4, int B, int F) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int BP = B * (F - 1), BF = B * F;
+  if (t < BP && g_rt) {
+    double g[12];
+    flow_pose_grad(flowacc, nullptr, rt, t, F, g);
+    for (int k = 0; k < 12; ++k) g_rt[(size_t)t * 12 + k] = (float)g[k];
+  }
+  if (t < BF && g_k4) {
+    double g[4];
+    flow_k4_grad(flowacc, t, F, g);
+    for (int k = 0; k < 4; ++k) g_k4[(size_t)t * 4 + k] = (float)g[k];
+  }
+  if (t == 0 && loss) {
+    double s = 0.0;
+    for (int k = 0; k < BF; ++k) s += flowacc[(size_t)k * kFlowAcc];
+    *loss = (float)s;
+  }
+}
+
+// ================================================================== phase D1: adjoint solve
+__global__ void k_adjoint(const double* __restrict__ flowacc, const PairState* __restrict__ state,
+                          const float* __restrict__ g_rt, int include_flow,
+                          const float* __restrict__ flow_scale, PairAdjoint* __restrict__ adj, int BP,
+                          int F) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= BP) return;
+  double g[12];
+  for (int k = 0; k < 12; ++k) g[k] = 0.0;
+  if (include_flow) {
+    flow_pose_grad(flowacc, state, nullptr, pair, F, g);
+    const double s = flow_scale ? (double)*flow_scale : 1.0;
+    for (int k = 0; k < 12; ++k) g[k] *= s;
+  }
+  if (g_rt) for (int k = 0; k < 12; ++k) g[k] += (double)g_rt[(size_t)pair * 12 + k];
+  PairAdjoint out;
+  procrustes_adjoint(state[pair], g, out);
+  adj[pair] = out;
+}
+
+// ================================================================== phase D2: distribute
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
+             const float* __restrict__ bflow, const float* __restrict__ weights,
+             const int64_t* __restrict__ indices, int num_indices,
+             const PairAdjoint* __restrict__ adj, float* __restrict__ g_depth,
+             float* __restrict__ g_weights, double* __restrict__ k4acc, int F, int H, int W) {
+  __shared__ double smem[8 * (kThreads / 32)];
+  __shared__ PairAdjoint s_adj;
+  const int pair = blockIdx.y;
+  const int N = H * W;
+  if (threadIdx.x < sizeof(PairAdjoint) / 4)
+    reinterpret_cast<float*>(&s_adj)[threadIdx.x] = reinterpret_cast<const float*>(adj + pair)[threadIdx.x];
+  __syncthreads();
+  const PairAdjoint ad = s_adj;
+  const PairGeom g = pair_geom(depth, k4, pair, F, H, W);
+  const int bi = pair / (F - 1), i = pair - bi * (F - 1);
+  const int a = bi * F + i;
+  const float* da = depth + (size_t)a * N;
+  const float* db = da + N;
+  const float* fl = bflow + (size_t)pair * N * 2;
+  const float* wt = weights ? weights + (size_t)pair * N : nullptr;
+  float* gda = g_depth + (size_t)a * N;
+  auto load_a = [da](int i) { return __ldg(da + i); };
+  auto scatter = [gda](int i, float v) { atomicAdd(gda + i, v); };
+  float* gdb = gda + N;
+  float* gw = g_weights ? g_weights + (size_t)pair * N : nullptr;
+  float kacc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
+
+  if (indices == nullptr) {
+    for (int base = (blockIdx.x * kThreads + threadIdx.x) * VEC; base < N;
+         base += gridDim.x * kThreads * VEC) {
+      float dv[VEC], wv[VEC], fv[2 * VEC], gwv[VEC], gdv[VEC];
+      if (VEC == 4) {
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(db + base));
+        dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
+        if (wt) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wt + base));
+          wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+        } else { wv[0] = wv[1] = wv[2] = wv[3] = 1.f; }
+        const float4 f0 = __ldg(reinterpret_cast<const float4*>(fl + 2 * base));
+        const float4 f1 = __ldg(reinterpret_cast<const float4*>(fl + 2 * base) + 1);
+        fv[0] = f0.x; fv[1] = f0.y; fv[2] = f0.z; fv[3] = f0.w;
+        fv[4] = f1.x; fv[5] = f1.y; fv[6] = f1.z; fv[7] = f1.w;
+      } else {
+        dv[0] = __ldg(db + base);
+        wv[0] = wt ? __ldg(wt + base) : 1.f;
+        fv[0] = __ldg(fl + 2 * base); fv[1] = __ldg(fl + 2 * base + 1);
+      }
+      const int r = base / W, c0 = base - r * W;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        distribute_point(g, ad, r, c0 + v, dv[v], wv[v], fv[2 * v], fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) atomicAdd(gdb + base + v, gdv[v]);
+      if (gw) {
+        if (VEC == 4) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
+        else gw[base] = gwv[0];
+      }
+    }
+  } else {
+    for (int t = blockIdx.x * kThreads + threadIdx.x; t < num_indices; t += gridDim.x * kThreads) {
+      const int j = (int)indices[t];
+      const int r = j / W, c = j - r * W;
+      float gdj, gwj;
+      distribute_point(g, ad, r, c, __ldg(db + j), wt ? __ldg(wt + j) : 1.f, __ldg(fl + 2 * j),
+                       __ldg(fl + 2 * j + 1), load_a, scatter, gdj, gwj, kacc);
+      atomicAdd(gdb + j, gdj);
+      if (gw) atomicAdd(gw + j, gwj);
+    }
+  }
+  // kacc[0..3] -> frame a, kacc[4..7] -> frame b = a + 1: contiguous in k4acc
+  block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
+}
+
+__global__ void k_k4_finalize(const double* __restrict__ k4acc, const double* __restrict__ flowacc,
+                              int include_flow, const float* __restrict__ flow_scale,
+                              float* __restrict__ g_k4, int B, int F) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * F) return;
+  double g[4] = {0, 0, 0, 0};
+  if (include_flow) {
+    flow_k4_grad(flowacc, t, F, g);
+    const double s = flow_scale ? (double)*flow_scale : 1.0;
+    for (int k = 0; k < 4; ++k) g[k] *= s;
+  }
+  for (int k = 0; k < 4; ++k) g_k4[(size_t)t * 4 + k] = (float)(g[k] + k4acc[(size_t)t * 4 + k]);
+}
+
+__global__ void k_scale_inplace(float* __restrict__ buf, const float* __restrict__ scale, size_t n) {
+  const float s = *scale;
+  if (s == 1.0f) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    buf[i] *= s;
+}
+
+// ================================================================== mask sum
+__global__ void __launch_bounds__(kThreads)
+k_mask_sum(const float* __restrict__ a, const float* __restrict__ b, double* __restrict__ out, size_t n) {
+  __shared__ double smem[kThreads / 32];
+  double acc = 0.0;
+  const size_t n4 = n / 4;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kThreads) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i);
+    const float4 y = __ldg(reinterpret_cast<const float4*>(b) + i);
+    acc += (double)((x.x + x.y) + (x.z + x.w)) + (double)((y.x + y.y) + (y.z + y.w));
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads)
+    acc += (double)a[i] + (double)b[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) s += smem[w];
+    atomicAdd(out, s);
+  }
+}
+
+// ================================================================== utilities
+__global__ void k_unproject(const float* __restrict__ depth, const float* __restrict__ k4,
+                            float* __restrict__ surf, int H, int W) {
+  const int frame = blockIdx.y, N = H * W;
+  const K4 k = load_k4(k4, frame);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+    const int r = j / W, c = j - r * W;
+    float rx, ry;
+    ray_of(pix_x(c, W), pix_y(r, H), k, rx, ry);
+    const float d = __ldg(depth + (size_t)frame * N + j);
+    float* o = surf + ((size_t)frame * N + j) * 3;
+    o[0] = d * rx; o[1] = d * ry; o[2] = d;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_unproject_bwd(const float* __restrict__ depth, const float* __restrict__ k4,
+                const float* __restrict__ gs, float* __restrict__ gd, double* __restrict__ gk, int H, int W) {
+  __shared__ double smem[4 * (kThreads / 32)];
+  const int frame = blockIdx.y, N = H * W;
+  const K4 k = load_k4(k4, frame);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+    const int r = j / W, c = j - r * W;
+    float rx, ry;
+    ray_of(pix_x(c, W), pix_y(r, H), k, rx, ry);
+    const float d = __ldg(depth + (size_t)frame * N + j);
+    const float* g = gs + ((size_t)frame * N + j) * 3;
+    const float g0 = g[0], g1 = g[1], g2 = g[2];
+    gd[(size_t)frame * N + j] = g0 * rx + g1 * ry + g2;
+    acc[0] -= g0 * d * rx / k.fx;
+    acc[1] -= g1 * d * ry / k.fy;
+    acc[2] -= g0 * d / k.fx;
+    acc[3] -= g1 * d / k.fy;
+  }
+  block_accumulate<4>(acc, gk + (size_t)frame * 4, smem);
+}
+
+__global__ void k_d2f(const double* __restrict__ src, float* __restrict__ dst, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = (float)src[t];
+}
+
+__global__ void k_reproject(const float* __restrict__ xyz, const float* __restrict__ rt,
+                            const float* __restrict__ k4, float* __restrict__ xy, int n) {
+  const int item = blockIdx.y;
+  const Rt t = load_rt(rt, item);
+  const K4 k = load_k4(k4, item);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const float* p = xyz + ((size_t)item * n + j) * 3;
+    const float s0 = p[0], s1 = p[1], s2 = p[2];
+    const float X0 = t.r[0] * s0 + t.r[1] * s1 + t.r[2] * s2 + t.t[0];
+    const float X1 = t.r[3] * s0 + t.r[4] * s1 + t.r[5] * s2 + t.t[1];
+    const float X2 = t.r[6] * s0 + t.r[7] * s1 + t.r[8] * s2 + t.t[2];
+    const Proj pr = project_point(X0, X1, X2, k);
+    float* o = xy + ((size_t)item * n + j) * 2;
+    o[0] = pr.uvx; o[1] = pr.uvy;
+  }
+}
+
+// P_0 = I, P_{k+1} = P_k @ T_k in float32, one thread per batch item (projection.py:207-209).
+__global__ void k_pose_chain(const float* __restrict__ rt, float* __restrict__ ext, int B, int F) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float P[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  float* o = ext + (size_t)b * F * 16;
+  for (int k = 0;; ++k) {
+    for (int i = 0; i < 12; ++i) o[(size_t)k * 16 + i] = P[i];
+    o[(size_t)k * 16 + 12] = 0.f; o[(size_t)k * 16 + 13] = 0.f; o[(size_t)k * 16 + 14] = 0.f; o[(size_t)k * 16 + 15] = 1.f;
+    if (k == F - 1) break;
+    const float* T = rt + ((size_t)b * (F - 1) + k) * 12;
+    float Q[12];
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 4; ++c) {
+        float s = P[r * 4 + 0] * T[0 * 4 + c] + P[r * 4 + 1] * T[1 * 4 + c] + P[r * 4 + 2] * T[2 * 4 + c];
+        if (c == 3) s += P[r * 4 + 3];
+        Q[r * 4 + c] = s;
+      }
+    }
+    for (int i = 0; i < 12; ++i) P[i] = Q[i];
+  }
+}
+
+// Adjoint of the chain.  With G_k = dL/dP_k (top 3 rows matter; the bottom row is constant):
+// acc_{F-1} = G_{F-1}; dT_k = P_k^T acc_{k+1} (3x4 part); acc_k = G_k + acc_{k+1} T_k^T.
+__global__ void k_pose_chain_bwd(const float* __restrict__ rt, const float* __restrict__ ext,
+                                 const float* __restrict__ g_ext, float* __restrict__ g_rt, int B, int F) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double acc[12];
+  const float* G = g_ext + ((size_t)b * F + (F - 1)) * 16;
+  for (int i = 0; i < 12; ++i) acc[i] = G[i];
+  for (int k = F - 2; k >= 0; --k) {
+    const float* P = ext + ((size_t)b * F + k) * 16;
+    const float* T = rt + ((size_t)b * (F - 1) + k) * 12;
+    float* o = g_rt + ((size_t)b * (F - 1) + k) * 12;
+    // P_{k+1}[r][c] = sum_m P_k[r][m] T4[m][c] (T4 = [T; 0 0 0 1]); dT[m][c] = sum_r P_k[r][m] acc[r][c], m < 3
+    for (int m = 0; m < 3; ++m)
+      for (int c = 0; c < 4; ++c)
+        o[m * 4 + c] = (float)(P[0 * 4 + m] * acc[0 * 4 + c] + P[1 * 4 + m] * acc[1 * 4 + c] + P[2 * 4 + m] * acc[2 * 4 + c]);
+    // dP_k[r][m] = sum_c acc[r][c] T4[m][c]
+    double nxt[12];
+    const float* Gk = g_ext + ((size_t)b * F + k) * 16;
+    for (int r = 0; r < 3; ++r) {
+      for (int m = 0; m < 3; ++m)
+        nxt[r * 4 + m] = Gk[r * 4 + m] + acc[r * 4 + 0] * T[m * 4 + 0] + acc[r * 4 + 1] * T[m * 4 + 1] +
+                         acc[r * 4 + 2] * T[m * 4 + 2] + acc[r * 4 + 3] * T[m * 4 + 3];
+      nxt[r * 4 + 3] = Gk[r * 4 + 3] + acc[r * 4 + 3];
+    }
+    for (int i = 0; i < 12; ++i) acc[i] = nxt[i];
+  }
+}
+
+// torch.optim.Adam (single-tensor, no amsgrad / weight decay), same operation order.
+__global__ void __launch_bounds__(kThreads)
+k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+       size_t n, float beta1, float beta2, float omb1, float omb2, float eps, float step_size,
+       float bc2_sqrt) {
+  const size_t n4 = n / 4;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kThreads) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define FM_ADAM1(P, G, M, V)                                   \
+    M = M + omb1 * (G - M);                                    \
+    V = V * beta2 + omb2 * G * G;                              \
+    P = P - step_size * (M / (sqrtf(V) / bc2_sqrt + eps));
+    FM_ADAM1(pp.x, gg.x, mm.x, vv.x)
+    FM_ADAM1(pp.y, gg.y, mm.y, vv.y)
+    FM_ADAM1(pp.z, gg.z, mm.z, vv.z)
+    FM_ADAM1(pp.w, gg.w, mm.w, vv.w)
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+    float pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    FM_ADAM1(pp, gg, mm, vv)
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+#undef FM_ADAM1
+}
+
+// ---------------------------------------------------------------- launch geometry
+int blocks_for(int n_items_per_row, int vec) {
+  // ~4096 items per block keeps thousands of blocks in flight at the BASELINE sizes and
+  // still gives every thread a few independent loads.
+  const int per_block = kThreads * vec * 4;
+  int nb = (n_items_per_row + per_block - 1) / per_block;
+  return nb < 1 ? 1 : nb;
+}
+
+bool bad_dims(int B, int F, int H, int W) { return B < 1 || F < 2 || H < 1 || W < 1 || (long long)H * W > (1ll << 30); }
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+int fm_version(void) { return 100; }
+const char* fm_last_error(void) { return g_err; }
+
+size_t fm_workspace_bytes(int B, int F, int H, int W) {
+  (void)H; (void)W;
+  if (B < 1 || F < 2) return 0;
+  return carve(nullptr, B, F).bytes;
+}
+
+int fm_workspace_reset(void* ws, int B, int F, int H, int W, void* stream) {
+  if (!ws || bad_dims(B, F, H, W)) return fail_msg("fm_workspace_reset: bad arguments");
+  Workspace w = carve(ws, B, F);
+  cudaError_t e = cudaMemsetAsync(ws, 0, (char*)w.state - (char*)ws, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail("fm_workspace_reset", e);
+  return 0;
+}
+
+int fm_unproject(const float* depth, const float* k4, float* surfaces, int BF, int H, int W, void* stream) {
+  if (!depth || !k4 || !surfaces || BF < 1) return fail_msg("fm_unproject: bad arguments");
+  dim3 grid(blocks_for(H * W, 4), BF);
+  k_unproject<<<grid, kThreads, 0, (cudaStream_t)stream>>>(depth, k4, surfaces, H, W);
+  FM_CHECK_LAUNCH("fm_unproject");
+  return 0;
+}
+
+int fm_unproject_bwd(const float* depth, const float* k4, const float* g_surfaces, float* g_depth,
+                     float* g_k4, void* ws, int B, int F, int H, int W, void* stream) {
+  if (!depth || !k4 || !g_surfaces || !g_depth || !g_k4 || !ws || bad_dims(B, F, H, W))
+    return fail_msg("fm_unproject_bwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace w = carve(ws, B, F);
+  const int BF = B * F;
+  cudaError_t e = cudaMemsetAsync(w.k4acc, 0, (size_t)BF * 4 * sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_unproject_bwd: memset", e);
+  dim3 grid(blocks_for(H * W, 4), BF);
+  k_unproject_bwd<<<grid, kThreads, 0, s>>>(depth, k4, g_surfaces, g_depth, w.k4acc, H, W);
+  k_d2f<<<(BF * 4 + 127) / 128, 128, 0, s>>>(w.k4acc, g_k4, BF * 4);
+  FM_CHECK_LAUNCH("fm_unproject_bwd");
+  return 0;
+}
+
+int fm_reproject(const float* xyz, const float* rt, const float* k4, float* xy, int items, int n, void* stream) {
+  if (!xyz || !rt || !k4 || !xy || items < 1 || n < 1) return fail_msg("fm_reproject: bad arguments");
+  dim3 grid(blocks_for(n, 1), items);
+  k_reproject<<<grid, kThreads, 0, (cudaStream_t)stream>>>(xyz, rt, k4, xy, n);
+  FM_CHECK_LAUNCH("fm_reproject");
+  return 0;
+}
+
+int fm_procrustes_fwd(const float* depth, const float* k4, const float* backward_flow,
+                      const float* weights, const int64_t* indices, int num_indices, float* rt,
+                      void* ws, int B, int F, int H, int W, void* stream) {
+  if (!depth || !k4 || !backward_flow || !rt || !ws || bad_dims(B, F, H, W))
+    return fail_msg("fm_procrustes_fwd: bad arguments");
+  if (indices && num_indices < 1) return fail_msg("fm_procrustes_fwd: empty index set");
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace w = carve(ws, B, F);
+  const int BP = B * (F - 1);
+  cudaError_t e = cudaMemsetAsync(w.moments, 0, (size_t)BP * kNumMoments * sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_procrustes_fwd: memset", e);
+  if (indices) {
+    dim3 grid(blocks_for(num_indices, 1), BP);
+    k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.moments, F, H, W);
+  } else if (W % 4 == 0) {
+    dim3 grid(blocks_for(H * W, 4), BP);
+    k_moments<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, F, H, W);
+  } else {
+    dim3 grid(blocks_for(H * W, 1), BP);
+    k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, F, H, W);
+  }
+  FM_CHECK_LAUNCH("fm_procrustes_fwd: k_moments");
+  k_solve<<<(BP + 63) / 64, 64, 0, s>>>(w.moments, depth, rt, w.state, BP, F, H, W);
+  FM_CHECK_LAUNCH("fm_procrustes_fwd: k_solve");
+  return 0;
+}
+
+int fm_procrustes_bwd(const float* depth, const float* k4, const float* backward_flow,
+                      const float* weights, const int64_t* indices, int num_indices,
+                      const float* g_rt, int include_flow_loss, const float* flow_scale,
+                      float* g_depth, float* g_weights, float* g_k4, void* ws, int B, int F, int H,
+                      int W, void* stream) {
+  if (!depth || !k4 || !backward_flow || !g_depth || !g_k4 || !ws || bad_dims(B, F, H, W))
+    return fail_msg("fm_procrustes_bwd: bad arguments");
+  if (!g_rt && !include_flow_loss) return fail_msg("fm_procrustes_bwd: no pose gradient given");
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace w = carve(ws, B, F);
+  const int BP = B * (F - 1), BF = B * F;
+  cudaError_t e = cudaMemsetAsync(w.k4acc, 0, (size_t)BF * 4 * sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_procrustes_bwd: memset", e);
+  if (include_flow_loss && flow_scale) {
+    // the direct depth gradient already sitting in g_depth was computed for scale 1
+    k_scale_inplace<<<148 * 4, kThreads, 0, s>>>(g_depth, flow_scale, (size_t)BF * H * W);
+    FM_CHECK_LAUNCH("fm_procrustes_bwd: k_scale_inplace");
+  }
+  k_adjoint<<<(BP + 63) / 64, 64, 0, s>>>(w.flowacc, w.state, g_rt, include_flow_loss, flow_scale, w.adj, BP, F);
+  FM_CHECK_LAUNCH("fm_procrustes_bwd: k_adjoint");
+  if (indices) {
+    dim3 grid(blocks_for(num_indices, 1), BP);
+    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, F, H, W);
+  } else if (W % 4 == 0) {
+    dim3 grid(blocks_for(H * W, 4), BP);
+    k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, F, H, W);
+  } else {
+    dim3 grid(blocks_for(H * W, 1), BP);
+    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, F, H, W);
+  }
+  FM_CHECK_LAUNCH("fm_procrustes_bwd: k_distribute");
+  k_k4_finalize<<<(BF + 127) / 128, 128, 0, s>>>(w.k4acc, w.flowacc, include_flow_loss, flow_scale, g_k4, B, F);
+  FM_CHECK_LAUNCH("fm_procrustes_bwd: k_k4_finalize");
+  return 0;
+}
+
+int fm_mask_sum(const float* forward_mask, const float* backward_mask, double* out, size_t count, void* stream) {
+  if (!forward_mask || !backward_mask || !out) return fail_msg("fm_mask_sum: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_mask_sum: memset", e);
+  if (count == 0) return 0;
+  size_t nb = (count / 4 + kThreads * 8 - 1) / (kThreads * 8);
+  if (nb < 1) nb = 1;
+  if (nb > 148 * 8) nb = 148 * 8;
+  k_mask_sum<<<(unsigned)nb, kThreads, 0, s>>>(forward_mask, backward_mask, out, count);
+  FM_CHECK_LAUNCH("fm_mask_sum");
+  return 0;
+}
+
+int fm_flow_loss_fwd_bwd(const float* depth, const float* k4, const float* rt,
+                         const float* forward_flow, const float* backward_flow,
+                         const float* forward_mask, const float* backward_mask,
+                         const double* mask_sum, int mapping, float delta, float loss_weight,
+                         float* loss, float* g_depth, float* g_rt, float* g_k4, void* ws, int B,
+                         int F, int H, int W, void* stream) {
+  if (!depth || !k4 || !rt || !forward_flow || !backward_flow || !forward_mask || !backward_mask ||
+      !mask_sum || !g_depth || !ws || bad_dims(B, F, H, W))
+    return fail_msg("fm_flow_loss_fwd_bwd: bad arguments");
+  if (mapping < 0 || mapping > 2) return fail_msg("fm_flow_loss_fwd_bwd: unknown mapping");
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace w = carve(ws, B, F);
+  const int BP = B * (F - 1), BF = B * F;
+  cudaError_t e = cudaMemsetAsync(w.flowacc, 0, (size_t)BF * kFlowAcc * sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_flow_loss_fwd_bwd: memset", e);
+  if (W % 4 == 0) {
+    dim3 grid(blocks_for(H * W, 4), BF);
+    k_flow<4><<<grid, kThreads, 0, s>>>(depth, k4, rt, forward_flow, backward_flow, forward_mask, backward_mask, mask_sum, mapping, delta, loss_weight, g_depth, w.flowacc, F, H, W);
+  } else {
+    dim3 grid(blocks_for(H * W, 1), BF);
+    k_flow<1><<<grid, kThreads, 0, s>>>(depth, k4, rt, forward_flow, backward_flow, forward_mask, backward_mask, mask_sum, mapping, delta, loss_weight, g_depth, w.flowacc, F, H, W);
+  }
+  FM_CHECK_LAUNCH("fm_flow_loss_fwd_bwd: k_flow");
+  const int n = BF > BP ? BF : BP;
+  k_flow_finalize<<<(n + 127) / 128, 128, 0, s>>>(w.flowacc, rt, loss, g_rt, g_k4, B, F);
+  FM_CHECK_LAUNCH("fm_flow_loss_fwd_bwd: k_flow_finalize");
+  return 0;
+}
+
+int fm_pose_chain(const float* rt, float* extrinsics, int B, int F, void* stream) {
+  if (!rt || !extrinsics || B < 1 || F < 2) return fail_msg("fm_pose_chain: bad arguments");
+  k_pose_chain<<<(B + 31) / 32, 32, 0, (cudaStream_t)stream>>>(rt, extrinsics, B, F);
+  FM_CHECK_LAUNCH("fm_pose_chain");
+  return 0;
+}
+
+int fm_pose_chain_bwd(const float* rt, const float* extrinsics, const float* g_extrinsics, float* g_rt,
+                      int B, int F, void* stream) {
+  if (!rt || !extrinsics || !g_extrinsics || !g_rt || B < 1 || F < 2) return fail_msg("fm_pose_chain_bwd: bad arguments");
+  k_pose_chain_bwd<<<(B + 31) / 32, 32, 0, (cudaStream_t)stream>>>(rt, extrinsics, g_extrinsics, g_rt, B, F);
+  FM_CHECK_LAUNCH("fm_pose_chain_bwd");
+  return 0;
+}
+
+int fm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count,
+                 double lr, double beta1_d, double beta2_d, double eps_d, int step, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || step < 1) return fail_msg("fm_adam_step: bad arguments");
+  if (count == 0) return 0;
+  const float beta1 = (float)beta1_d, beta2 = (float)beta2_d, eps = (float)eps_d;
+  const double bc1 = 1.0 - pow(beta1_d, (double)step);
+  const double bc2 = 1.0 - pow(beta2_d, (double)step);
+  const float step_size = (float)(lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  size_t nb = (count / 4 + kThreads * 2 - 1) / (kThreads * 2);
+  if (nb < 1) nb = 1;
+  if (nb > 148 * 16) nb = 148 * 16;
+  k_adam<<<(unsigned)nb, kThreads, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, count, beta1, beta2, (float)(1.0 - (double)beta1_d), (float)(1.0 - (double)beta2_d), eps, step_size, bc2_sqrt);
+  FM_CHECK_LAUNCH("fm_adam_step");
+  return 0;
+}
+
+}  // extern "C"

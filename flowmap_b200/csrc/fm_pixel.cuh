@@ -1,0 +1,177 @@
+// Per-pixel bodies of the three pixel-parallel phases, host+device.
+//
+// fm_kernels.cu instantiates these with __ldg loads and red.global atomics;
+// tests/host_emulation instantiates the same code with plain loads/adds on the CPU to
+// check the analytic gradients against the oracle without a GPU (test-only).
+#pragma once
+#include "fm_procrustes.cuh"
+
+namespace fm {
+
+// Geometry of pair (a, b = a + 1).
+struct PairGeom {
+  K4 ka, kb;
+  int H, W;
+  float z0;  // conditioning shift (0, 0, z0) applied to p and q before accumulation
+};
+
+// Later point p (frame b, pixel (r, c)) and earlier point q (frame a sampled at
+// xy + backward flow), both shifted by (0, 0, z0).  projection.py:222-242.
+template <typename LoadA>
+FM_HD void point_pq(const PairGeom& g, int r, int c, float db, float flx, float fly, LoadA load_a,
+                    float* p, float* q, Taps& t) {
+  const float x = pix_x(c, g.W), y = pix_y(r, g.H);
+  float rx, ry;
+  ray_of(x, y, g.kb, rx, ry);
+  p[0] = db * rx;
+  p[1] = db * ry;
+  p[2] = db - g.z0;
+  t = bilinear_taps(x + flx, y + fly, g.H, g.W);
+  float qx, qy, qz;
+  sample_surface(t, g.W, g.H, g.ka, load_a, qx, qy, qz);
+  q[0] = qx;
+  q[1] = qy;
+  q[2] = qz - g.z0;
+}
+
+// acc[16] += (w, w p, w q, w q p^T)   (procrustes.py:23-32 on sufficient statistics)
+FM_HD void moments_add(float* acc, float w, const float* p, const float* q) {
+  acc[0] += w;
+  const float wp0 = w * p[0], wp1 = w * p[1], wp2 = w * p[2];
+  acc[1] += wp0;
+  acc[2] += wp1;
+  acc[3] += wp2;
+  acc[4] += w * q[0];
+  acc[5] += w * q[1];
+  acc[6] += w * q[2];
+  for (int a = 0; a < 3; ++a) {
+    acc[7 + a * 3 + 0] += q[a] * wp0;
+    acc[7 + a * 3 + 1] += q[a] * wp1;
+    acc[7 + a * 3 + 2] += q[a] * wp2;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Phase C.  Accumulator slots per frame k:
+//  0        loss numerator (already scaled by weight / mask_sum)
+//  1..9     forward term of pair (k, k+1): A[l][m] = sum (s - t)_l dY_m      (dR)
+//  10..12   forward term: b = sum dY                                        (dt = -R b)
+//  13..21   backward term of pair (k-1, k): sum dX_l s_m                    (dR)
+//  22..24   backward term: sum dX                                           (dt)
+//  25..28   dK_k through the unprojection ray (fx fy cx cy)
+//  29..32   dK_{k+1} through the forward-term projection
+//  33..36   dK_{k-1} through the backward-term projection
+// ---------------------------------------------------------------------------------
+constexpr int kFlowVals = 37;
+
+struct FlowFrame {
+  K4 kk, kn, kp;  // intrinsics of frames k, k+1, k-1
+  Rt tf, tb;      // [R|t] of pair (k, k+1) and of pair (k-1, k)
+  bool hasF, hasB;
+};
+
+// One pixel of frame k: forward term (loss_flow.py:47-56 with projection.py:143-162) and
+// backward term (loss_flow.py:59-68 with projection.py:165-184) in the pair-local form of
+// SURVEY A.6.  Returns the direct (pose-detached) depth gradient.
+FM_HD float flow_pixel(const FlowFrame& f, float x, float y, float D, float ffx, float ffy, float mf,
+                       float fbx, float fby, float mb, float g, float ax, float ay, int mapping,
+                       float delta, float* acc) {
+  float rx, ry;
+  ray_of(x, y, f.kk, rx, ry);
+  const float s0 = D * rx, s1 = D * ry, s2 = D;
+  float ds0 = 0.f, ds1 = 0.f, ds2 = 0.f;
+  if (f.hasF) {  // Y = R^T (s - t), projected with K_{k+1}
+    const float d0 = s0 - f.tf.t[0], d1 = s1 - f.tf.t[1], d2 = s2 - f.tf.t[2];
+    const float* R = f.tf.r;
+    const float Y0 = R[0] * d0 + R[3] * d1 + R[6] * d2;
+    const float Y1 = R[1] * d0 + R[4] * d1 + R[7] * d2;
+    const float Y2 = R[2] * d0 + R[5] * d1 + R[8] * d2;
+    const Proj pr = project_point(Y0, Y1, Y2, f.kn);
+    float gx, gy;
+    const float l = robust_map((pr.uvx - x) - ffx, (pr.uvy - y) - ffy, ax, ay, mapping, delta, gx, gy);
+    const float wgt = g * mf;
+    acc[0] += wgt * l;
+    float dY0, dY1, dY2;
+    project_point_adj(pr, Y0, Y1, Y2, f.kn, wgt * gx, wgt * gy, dY0, dY1, dY2, acc[29], acc[30],
+                      acc[31], acc[32]);
+    acc[1] += d0 * dY0; acc[2] += d0 * dY1; acc[3] += d0 * dY2;
+    acc[4] += d1 * dY0; acc[5] += d1 * dY1; acc[6] += d1 * dY2;
+    acc[7] += d2 * dY0; acc[8] += d2 * dY1; acc[9] += d2 * dY2;
+    acc[10] += dY0; acc[11] += dY1; acc[12] += dY2;
+    ds0 += R[0] * dY0 + R[1] * dY1 + R[2] * dY2;
+    ds1 += R[3] * dY0 + R[4] * dY1 + R[5] * dY2;
+    ds2 += R[6] * dY0 + R[7] * dY1 + R[8] * dY2;
+  }
+  if (f.hasB) {  // X = R s + t, projected with K_{k-1}
+    const float* R = f.tb.r;
+    const float X0 = R[0] * s0 + R[1] * s1 + R[2] * s2 + f.tb.t[0];
+    const float X1 = R[3] * s0 + R[4] * s1 + R[5] * s2 + f.tb.t[1];
+    const float X2 = R[6] * s0 + R[7] * s1 + R[8] * s2 + f.tb.t[2];
+    const Proj pr = project_point(X0, X1, X2, f.kp);
+    float gx, gy;
+    const float l = robust_map((pr.uvx - x) - fbx, (pr.uvy - y) - fby, ax, ay, mapping, delta, gx, gy);
+    const float wgt = g * mb;
+    acc[0] += wgt * l;
+    float dX0, dX1, dX2;
+    project_point_adj(pr, X0, X1, X2, f.kp, wgt * gx, wgt * gy, dX0, dX1, dX2, acc[33], acc[34],
+                      acc[35], acc[36]);
+    acc[13] += dX0 * s0; acc[14] += dX0 * s1; acc[15] += dX0 * s2;
+    acc[16] += dX1 * s0; acc[17] += dX1 * s1; acc[18] += dX1 * s2;
+    acc[19] += dX2 * s0; acc[20] += dX2 * s1; acc[21] += dX2 * s2;
+    acc[22] += dX0; acc[23] += dX1; acc[24] += dX2;
+    ds0 += R[0] * dX0 + R[3] * dX1 + R[6] * dX2;
+    ds1 += R[1] * dX0 + R[4] * dX1 + R[7] * dX2;
+    ds2 += R[2] * dX0 + R[5] * dX1 + R[8] * dX2;
+  }
+  // s = D * (rx, ry, 1), rx = (x - cx) / fx
+  acc[25] -= ds0 * s0 / f.kk.fx;
+  acc[26] -= ds1 * s1 / f.kk.fy;
+  acc[27] -= ds0 * D / f.kk.fx;
+  acc[28] -= ds1 * D / f.kk.fy;
+  return ds0 * rx + ds1 * ry + ds2;
+}
+
+// ---------------------------------------------------------------------------------
+// Phase D2: per-point adjoints of the Procrustes inputs.  `scatter(index, value)` adds into
+// the earlier frame's depth gradient; returns the aligned later-frame depth gradient and
+// the weight gradient.  kacc[0..3] += dK_a (through q), kacc[4..7] += dK_b (through p).
+// ---------------------------------------------------------------------------------
+template <typename LoadA, typename Scatter>
+FM_HD void distribute_point(const PairGeom& g, const PairAdjoint& ad, int r, int c, float db, float w,
+                            float flx, float fly, LoadA load_a, Scatter scatter, float& g_db,
+                            float& g_w, float* kacc) {
+  float p[3], q[3];
+  Taps t;
+  point_pq(g, r, c, db, flx, fly, load_a, p, q, t);
+  const float dp[3] = {p[0] - ad.pbar[0], p[1] - ad.pbar[1], p[2] - ad.pbar[2]};
+  const float dq[3] = {q[0] - ad.qbar[0], q[1] - ad.qbar[1], q[2] - ad.qbar[2]};
+  float pb[3], qb[3];
+  point_adjoint(ad, w, dp, dq, g_w, pb, qb);
+  // p = db * (rx, ry, 1)
+  float rx, ry;
+  ray_of(pix_x(c, g.W), pix_y(r, g.H), g.kb, rx, ry);
+  g_db = pb[0] * rx + pb[1] * ry + pb[2];
+  kacc[4] -= pb[0] * p[0] / g.kb.fx;
+  kacc[5] -= pb[1] * p[1] / g.kb.fy;
+  kacc[6] -= pb[0] * db / g.kb.fx;
+  kacc[7] -= pb[1] * db / g.kb.fy;
+  // q = sum_n w_n D_n (rx_n, ry_n, 1): scatter into the four taps of the earlier frame
+  float rx0, ry0, rx1, ry1;
+  ray_of(pix_x(t.x0, g.W), pix_y(t.y0, g.H), g.ka, rx0, ry0);
+  ray_of(pix_x(t.x1, g.W), pix_y(t.y1, g.H), g.ka, rx1, ry1);
+  const float b00 = qb[0] * rx0 + qb[1] * ry0 + qb[2];
+  const float b01 = qb[0] * rx1 + qb[1] * ry0 + qb[2];
+  const float b10 = qb[0] * rx0 + qb[1] * ry1 + qb[2];
+  const float b11 = qb[0] * rx1 + qb[1] * ry1 + qb[2];
+  if (t.w00 != 0.f) scatter(t.y0 * g.W + t.x0, t.w00 * b00);
+  if (t.w01 != 0.f) scatter(t.y0 * g.W + t.x1, t.w01 * b01);
+  if (t.w10 != 0.f) scatter(t.y1 * g.W + t.x0, t.w10 * b10);
+  if (t.w11 != 0.f) scatter(t.y1 * g.W + t.x1, t.w11 * b11);
+  const float qz_true = q[2] + g.z0;
+  kacc[0] -= qb[0] * q[0] / g.ka.fx;
+  kacc[1] -= qb[1] * q[1] / g.ka.fy;
+  kacc[2] -= qb[0] * qz_true / g.ka.fx;
+  kacc[3] -= qb[1] * qz_true / g.ka.fy;
+}
+
+}  // namespace fm

@@ -1,0 +1,113 @@
+/* flowmap_b200 -- C ABI of the B200-native FlowMap optimisation hot path.
+ *
+ * The reference (dcharatan/flowmap) has no FFI of its own: its boundary is the Python
+ * surface of flowmap.model.projection / flowmap.model.procrustes / flowmap.loss, every
+ * body being ATen calls.  This header is what those bodies bind to instead.  Each entry
+ * point cites the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless said otherwise; all arrays are contiguous
+ *     float32, row-major, in the reference's layouts: depth (B,F,H,W), flows
+ *     (B,F-1,H,W,2), masks/weights (B,F-1,H,W).  Intrinsics are passed as k4 (B,F,4) =
+ *     (fx, fy, cx, cy) of the normalised matrix of intrinsics/common.py:6-20; relative
+ *     poses as rt (B,F-1,3,4) = [R | t] of procrustes.py:45-51 (maps frame i+1 camera
+ *     coordinates to frame i camera coordinates).
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     allocates or frees device memory, keeps no pointer after returning, is re-entrant
+ *     and may be called from any host thread (autograd runs backward on its own thread).
+ *   - return value 0 = success; otherwise fm_last_error() (thread-local) describes it.
+ *   - `ws` is caller-provided scratch of at least fm_workspace_bytes(...) bytes, 256-byte
+ *     aligned; the same ws must be passed to the forward and backward halves of one step.
+ */
+#ifndef FLOWMAP_B200_H
+#define FLOWMAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FM_MAP_HUBER 0 /* loss/mapping/mapping_huber.py:19-34 */
+#define FM_MAP_L1 1    /* loss/mapping/mapping_l1.py:16-20    */
+#define FM_MAP_L2 2    /* loss/mapping/mapping_l2.py:16-21    */
+
+int fm_version(void);
+const char* fm_last_error(void);
+
+/* Scratch size for one optimisation step on (B, F, H, W). */
+size_t fm_workspace_bytes(int B, int F, int H, int W);
+/* Zero the accumulators in ws; call once at the start of every step. */
+int fm_workspace_reset(void* ws, int B, int F, int H, int W, void* stream);
+
+/* projection.py:76-90 unproject (+ :93-113 sample_image_grid): depth, k4 -> surfaces
+ * (B*F, H, W, 3). */
+int fm_unproject(const float* depth, const float* k4, float* surfaces, int BF, int H, int W,
+                 void* stream);
+/* Adjoint of fm_unproject: g_surfaces -> g_depth (B*F,H,W) and g_k4 (B*F,4). */
+int fm_unproject_bwd(const float* depth, const float* k4, const float* g_surfaces, float* g_depth,
+                     float* g_k4, void* ws, int B, int F, int H, int W, void* stream);
+
+/* projection.py:116-134 reproject_points + :49-58 project_camera_space: n points per
+ * item, one [R|t] (3x4) and one k4 per item -> xy (items, n, 2).  Forward only (used by
+ * the visualiser/export callers; the differentiable uses are the fused ops below). */
+int fm_reproject(const float* xyz, const float* rt, const float* k4, float* xy, int items, int n,
+                 void* stream);
+
+/* projection.py:213-249 align_surfaces up to the chain, + procrustes.py:7-51
+ * align_rigid: per pair, gather later points / bilinear-sample earlier surface at
+ * xy + backward_flow / weights, accumulate weighted moments, 3x3 SVD, det fix.
+ * indices: int64 pixel indices (extrinsics_procrustes.py:33-51) or NULL for all pixels.
+ * Writes rt (B*(F-1), 3, 4); keeps the solver state in ws for fm_procrustes_bwd. */
+int fm_procrustes_fwd(const float* depth, const float* k4, const float* backward_flow,
+                      const float* weights, const int64_t* indices, int num_indices, float* rt,
+                      void* ws, int B, int F, int H, int W, void* stream);
+
+/* Backward of fm_procrustes_fwd (closed-form SVD adjoint).
+ * g_rt: dL/d rt from any consumer, or NULL.  When `include_flow_loss` is non-zero the
+ * pose gradient that fm_flow_loss_fwd_bwd left in ws is added, scaled by *flow_scale
+ * (device scalar, NULL = 1).  g_depth (B,F,H,W) is ACCUMULATED into (atomics; caller
+ * zero-fills or passes the buffer fm_flow_loss_fwd_bwd wrote); g_weights (B,F-1,H,W) is
+ * written (all-pixel mode) or accumulated into (index mode; caller zero-fills);
+ * g_k4 (B,F,4) is written = procrustes part [+ flow-loss part when included]. */
+int fm_procrustes_bwd(const float* depth, const float* k4, const float* backward_flow,
+                      const float* weights, const int64_t* indices, int num_indices,
+                      const float* g_rt, int include_flow_loss, const float* flow_scale,
+                      float* g_depth, float* g_weights, float* g_k4, void* ws, int B, int F, int H,
+                      int W, void* stream);
+
+/* loss_flow.py:55-56,67-68 denominators: *out = sum(forward_mask) + sum(backward_mask)
+ * (device float64 scalar). */
+int fm_mask_sum(const float* forward_mask, const float* backward_mask, double* out, size_t count,
+                void* stream);
+
+/* loss_flow.py:31-70 LossFlow + projection.py:143-184 compute_{forward,backward}_flow +
+ * mapping/*.py, forward and analytic backward in one pass.  Uses the pair-local form of
+ * SURVEY A.6 (inv(P_i) P_{i+1} == rt_i).  loss_weight is cfg.weight (loss.py:46).
+ * mask_sum: device float64 scalar from fm_mask_sum ("or 1" applied inside).
+ * Outputs: loss (device float, = weight * sum / mask_sum); g_depth (B,F,H,W) WRITTEN with
+ * the direct (pose-detached) depth gradient; g_rt (B*(F-1),3,4) written; pose and
+ * intrinsics partials also stay in ws for fm_procrustes_bwd / fm_flow_k4_grad. */
+int fm_flow_loss_fwd_bwd(const float* depth, const float* k4, const float* rt,
+                         const float* forward_flow, const float* backward_flow,
+                         const float* forward_mask, const float* backward_mask,
+                         const double* mask_sum, int mapping, float delta, float loss_weight,
+                         float* loss, float* g_depth, float* g_rt, float* g_k4, void* ws, int B,
+                         int F, int H, int W, void* stream);
+
+/* projection.py:187-210 get_extrinsics: rt (B, F-1, 3, 4) -> camera-to-world (B, F, 4, 4),
+ * P_0 = I, P_{k+1} = P_k @ T_k, and its adjoint. */
+int fm_pose_chain(const float* rt, float* extrinsics, int B, int F, void* stream);
+int fm_pose_chain_bwd(const float* rt, const float* extrinsics, const float* g_extrinsics,
+                      float* g_rt, int B, int F, void* stream);
+
+/* model_wrapper_overfit.py:104-105 optim.Adam(lr): torch's single-tensor Adam update (no
+ * amsgrad, no weight decay), one fused pass; `step` is the 1-based step number. */
+int fm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count,
+                 double lr, double beta1, double beta2, double eps, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWMAP_B200_H */

@@ -1,0 +1,112 @@
+// TEST INFRASTRUCTURE -- never loaded by flowmap_b200.
+//
+// Serial host driver for the per-pixel bodies in flowmap_b200/csrc/fm_pixel.cuh and the
+// float64 solver in fm_procrustes.cuh.  It exists so that the analytic gradients can be
+// checked against the oracle in the build container, which has no GPU; the CUDA kernels
+// instantiate the very same inline functions.  Compiled by tests/test_host_emulation.py
+// with g++ into tests/host_emulation/_build/ (git-ignored).
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../flowmap_b200/csrc/fm_pixel.cuh"
+
+using namespace fm;
+
+static K4 k4_of(const float* k4, int frame) {
+  K4 k; k.fx = k4[frame * 4 + 0]; k.fy = k4[frame * 4 + 1]; k.cx = k4[frame * 4 + 2]; k.cy = k4[frame * 4 + 3];
+  return k;
+}
+
+static PairGeom geom(const float* depth, const float* k4, int pair, int F, int H, int W, int& a) {
+  int bi = pair / (F - 1), i = pair - bi * (F - 1);
+  a = bi * F + i;
+  PairGeom g;
+  g.ka = k4_of(k4, a); g.kb = k4_of(k4, a + 1); g.H = H; g.W = W;
+  g.z0 = depth[(size_t)(a + 1) * H * W + (size_t)(H / 2) * W + W / 2];
+  return g;
+}
+
+extern "C" {
+
+size_t emu_state_bytes() { return sizeof(PairState); }
+
+void emu_procrustes_fwd(const float* depth, const float* k4, const float* bflow, const float* weights,
+                        const int64_t* indices, int n_idx, float* rt, PairState* state, int B, int F,
+                        int H, int W) {
+  const int N = H * W, BP = B * (F - 1);
+  for (int pair = 0; pair < BP; ++pair) {
+    int a;
+    PairGeom g = geom(depth, k4, pair, F, H, W, a);
+    const float* da = depth + (size_t)a * N; const float* db = da + N;
+    double m[kNumMoments] = {0};
+    const int cnt = indices ? n_idx : N;
+    for (int t = 0; t < cnt; ++t) {
+      const int j = indices ? (int)indices[t] : t;
+      float acc[kNumMoments] = {0}; float p[3], q[3]; Taps taps;
+      point_pq(g, j / W, j % W, db[j], bflow[((size_t)pair * N + j) * 2], bflow[((size_t)pair * N + j) * 2 + 1],
+               [da](int i) { return da[i]; }, p, q, taps);
+      moments_add(acc, weights ? weights[(size_t)pair * N + j] : 1.f, p, q);
+      for (int k = 0; k < kNumMoments; ++k) m[k] += acc[k];
+    }
+    double shift[3] = {0, 0, (double)g.z0};
+    procrustes_solve(m, shift, rt + (size_t)pair * 12, state[pair]);
+  }
+}
+
+// flowacc: (B*F, 40) doubles, zero-filled by the caller.
+void emu_flow(const float* depth, const float* k4, const float* rt, const float* ff, const float* fb,
+              const float* mf, const float* mb, double mask_sum, int mapping, float delta, float weight,
+              float* g_depth, double* flowacc, int B, int F, int H, int W) {
+  const int N = H * W;
+  if (mask_sum == 0.0) mask_sum = 1.0;
+  const float g = (float)((double)weight / mask_sum);
+  const float sc = sqrtf((float)H * (float)W), ax = (float)W / sc, ay = (float)H / sc;
+  for (int frame = 0; frame < B * F; ++frame) {
+    int bi = frame / F, i = frame - bi * F;
+    FlowFrame f;
+    f.hasF = i < F - 1; f.hasB = i > 0;
+    f.kk = k4_of(k4, frame); f.kn = k4_of(k4, f.hasF ? frame + 1 : frame); f.kp = k4_of(k4, f.hasB ? frame - 1 : frame);
+    int pairF = bi * (F - 1) + i, pairB = pairF - 1;
+    auto ld = [&](int pair) { Rt t; for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) t.r[r * 3 + c] = rt[(size_t)pair * 12 + r * 4 + c]; t.t[r] = rt[(size_t)pair * 12 + r * 4 + 3]; } return t; };
+    if (f.hasF) f.tf = ld(pairF);
+    if (f.hasB) f.tb = ld(pairB);
+    for (int j = 0; j < N; ++j) {
+      float acc[kFlowVals] = {0};
+      const size_t jf = (size_t)(f.hasF ? pairF : 0) * N + j, jb = (size_t)(f.hasB ? pairB : 0) * N + j;
+      g_depth[(size_t)frame * N + j] = flow_pixel(
+          f, pix_x(j % W, W), pix_y(j / W, H), depth[(size_t)frame * N + j], f.hasF ? ff[jf * 2] : 0.f,
+          f.hasF ? ff[jf * 2 + 1] : 0.f, f.hasF ? mf[jf] : 0.f, f.hasB ? fb[jb * 2] : 0.f,
+          f.hasB ? fb[jb * 2 + 1] : 0.f, f.hasB ? mb[jb] : 0.f, g, ax, ay, mapping, delta, acc);
+      for (int k = 0; k < kFlowVals; ++k) flowacc[(size_t)frame * 40 + k] += acc[k];
+    }
+  }
+}
+
+// g_rt: (BP, 12) doubles = dL/d[R|t]; g_depth accumulated into; g_weights written/accumulated;
+// k4acc: (B*F, 4) doubles accumulated into.
+void emu_procrustes_bwd(const float* depth, const float* k4, const float* bflow, const float* weights,
+                        const int64_t* indices, int n_idx, const PairState* state, const double* g_rt,
+                        float* g_depth, float* g_weights, double* k4acc, int B, int F, int H, int W) {
+  const int N = H * W, BP = B * (F - 1);
+  for (int pair = 0; pair < BP; ++pair) {
+    int a;
+    PairGeom g = geom(depth, k4, pair, F, H, W, a);
+    PairAdjoint ad;
+    procrustes_adjoint(state[pair], g_rt + (size_t)pair * 12, ad);
+    const float* da = depth + (size_t)a * N; const float* db = da + N;
+    float* gda = g_depth + (size_t)a * N; float* gdb = gda + N;
+    const int cnt = indices ? n_idx : N;
+    for (int t = 0; t < cnt; ++t) {
+      const int j = indices ? (int)indices[t] : t;
+      float kacc[8] = {0}; float gdj, gwj;
+      distribute_point(g, ad, j / W, j % W, db[j], weights ? weights[(size_t)pair * N + j] : 1.f,
+                       bflow[((size_t)pair * N + j) * 2], bflow[((size_t)pair * N + j) * 2 + 1],
+                       [da](int i) { return da[i]; }, [gda](int i, float v) { gda[i] += v; }, gdj, gwj, kacc);
+      gdb[j] += gdj;
+      if (g_weights) g_weights[(size_t)pair * N + j] += gwj;
+      for (int k = 0; k < 8; ++k) k4acc[(size_t)a * 4 + k] += kacc[k];
+    }
+  }
+}
+}
