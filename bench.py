@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the FlowMap optimisation hot path on B200 (contract: see DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one full overfit iteration at the BASELINE shape (150 x 360 x 640, explicit
+depth backbone, all-pixel Procrustes): Model.forward -> LossFlow -> backward -> Adam.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+F_, H_, W_ = 150, 360, 640  # BASELINE.json configs[2] ("Tanks&Temples-shape")
+WORKLOAD = ("C3 150x360x640 synthetic (iid N(0,0.01^2) flows, U(0,1) masks), explicit_depth "
+            "backbone, all-pixel Procrustes, regressed focal, flow loss (Huber), full overfit "
+            "step = Model.forward + LossFlow + backward + Adam")
+
+
+# ------------------------------------------------------------------------------ inputs
+def synthetic_inputs(f, h, w, seed=0):
+    """SURVEY 8(d) "throughput set": depth 0.1+0.05 U, weight logits N(0,.01), flows
+    N(0, .01^2) in normalised units, masks U(0,1).  CPU float32 tensors."""
+    g = torch.Generator().manual_seed(seed)
+    p = f - 1
+    d = {
+        "depth": 0.1 + 0.05 * torch.rand(f, h, w, generator=g),
+        "wparam": 0.01 * torch.randn(p, h, w, generator=g),
+        "fwd": 0.01 * torch.randn(1, p, h, w, 2, generator=g),
+        "bwd": 0.01 * torch.randn(1, p, h, w, 2, generator=g),
+        "fmask": torch.rand(1, p, h, w, generator=g),
+        "bmask": torch.rand(1, p, h, w, generator=g),
+    }
+    return d
+
+
+def algorithmic_bytes(f, h, w):
+    """32 B per pair-pixel + 8 B per frame-pixel."""
+    n = h * w
+    return n * (32 * (f - 1) + 8 * f)
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [x.strip() for x in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline(inputs, sample_frames, steps, warmup):
+    """The oracle (CPU restatement of the reference, oracle/flowmap_oracle.py) timed on the
+    host cores on the first `sample_frames` frames of the workload; it/s scaled by pairs."""
+    from oracle import flowmap_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    f, h, w = sample_frames, inputs["depth"].shape[1], inputs["depth"].shape[2]
+    st = O.OverfitOracle(O.OverfitConfig(intrinsics="regressed"), f, h, w)
+    with torch.no_grad():
+        st.depth.copy_(inputs["depth"][:f])
+        st.weights.copy_(inputs["wparam"][:f - 1])
+    flows = O.Flows(inputs["fwd"][:, :f - 1], inputs["bwd"][:, :f - 1], inputs["fmask"][:, :f - 1],
+                    inputs["bmask"][:, :f - 1])
+    for _ in range(warmup):
+        st.training_step(flows)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st.training_step(flows)
+    dt = (time.perf_counter() - t0) / steps
+    pairs_per_s = (f - 1) / dt
+    return {"value": pairs_per_s / (F_ - 1), "unit": "it/s", "cores": cores, "kind": "port",
+            "threads": torch.get_num_threads(), "frame_pairs_per_s": pairs_per_s,
+            "sample": f"first {f} of {F_} frames ({f - 1} pairs) at {h}x{w}, {steps} timed steps "
+                      f"after {warmup} warm-up; it/s = pairs/s / {F_ - 1}",
+            "s_per_sample_step": dt}
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    from flowmap_b200._lib import lib
+    from flowmap_b200 import ops
+    from flowmap_b200.overfit import OverfitCfg, Overfitter
+    from flowmap_b200.types import Batch, Flows
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (flowmap_b200 has no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    inputs = synthetic_inputs(F_, H_, W_, seed=rank)
+    batch_dev = Batch(torch.zeros(1, 1, 1, 1, 1, device=dev).expand(1, F_, 3, H_, W_),
+                      torch.arange(F_, device=dev)[None], ["synthetic"], ["synthetic"])
+    flows_host = Flows(inputs["fwd"].pin_memory(), inputs["bwd"].pin_memory(),
+                       inputs["fmask"].pin_memory(), inputs["bmask"].pin_memory())
+    o = Overfitter.__new__(Overfitter)
+    cfg = OverfitCfg()
+    from flowmap_b200.overfit import FusedAdam, build_model_and_losses
+    o.cfg, o.batch, o.tracks = cfg, batch_dev, None
+    o.flows = Flows(*(t.to(dev, non_blocking=True) for t in
+                      (flows_host.forward, flows_host.backward, flows_host.forward_mask,
+                       flows_host.backward_mask)))
+    o.model, o.losses = build_model_and_losses(cfg, F_, (H_, W_))
+    o.model.to(dev)
+    with torch.no_grad():
+        o.model.backbone.depth.copy_(inputs["depth"])
+        o.model.backbone.weights.copy_(inputs["wparam"])
+    o.optimizer = FusedAdam(o.model.parameters(), cfg.lr)
+    o.global_step = 0
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    for _ in range(args.warmup):
+        o.training_step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = lib().fm_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, _ = o.training_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = lib().fm_launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t)
+    final_loss = float(loss)
+
+    # ---- end-to-end: the step's Flows arrive in pinned host memory every step, the loss is
+    # read back to the host every step (the pretrain-style use of the same API).
+    h2d = sum(x.numel() * 4 for x in (flows_host.forward, flows_host.backward,
+                                      flows_host.forward_mask, flows_host.backward_mask))
+    def e2e_step():
+        o.flows = Flows(flows_host.forward.to(dev, non_blocking=True),
+                        flows_host.backward.to(dev, non_blocking=True),
+                        flows_host.forward_mask.to(dev, non_blocking=True),
+                        flows_host.backward_mask.to(dev, non_blocking=True))
+        l, _ = o.training_step()
+        return float(l)  # D2H read of the step's loss
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    e2e_ms = float(t)
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---- per-op timing for the roofline (rank 0, ops called through the C ABI, CUDA events
+    # on the launching stream)
+    with torch.no_grad():
+        depths = o.model.backbone.depth.detach()[None].contiguous()
+        weights = torch.sigmoid(100.0 * o.model.backbone.weights.detach())[None].contiguous()
+        k3 = o.model.intrinsics.forward(o.batch, o.flows, None, 0)
+        k4 = ops.intrinsics_to_k4(k3).contiguous()
+        msum = ops.mask_sum(o.flows.forward_mask, o.flows.backward_mask)
+        ws = ops.workspace(1, F_, H_, W_, dev)
+        rt = torch.empty(1, F_ - 1, 3, 4, device=dev)
+        g_depth = torch.empty_like(depths)
+        g_w = torch.empty_like(weights)
+        g_k4 = torch.empty_like(k4)
+        g_rt = torch.empty_like(rt)
+        lossb = torch.empty((), device=dev)
+        P = lambda x: x.data_ptr()  # noqa: E731
+        st = torch.cuda.current_stream().cuda_stream
+        L = lib()
+        def op_fwd():
+            L.fm_procrustes_fwd(P(depths), P(k4), P(o.flows.backward), P(weights), None, 0, P(rt),
+                                P(ws), 1, F_, H_, W_, st)
+        def op_flow():
+            L.fm_flow_loss_fwd_bwd(P(depths), P(k4), P(rt), P(o.flows.forward), P(o.flows.backward),
+                                   P(o.flows.forward_mask), P(o.flows.backward_mask), P(msum), 0,
+                                   0.01, 1000.0, P(lossb), P(g_depth), P(g_rt), P(g_k4), P(ws), 1,
+                                   F_, H_, W_, st)
+        def op_bwd():
+            L.fm_procrustes_bwd(P(depths), P(k4), P(o.flows.backward), P(weights), None, 0, None, 1,
+                                None, P(g_depth), P(g_w), P(g_k4), P(ws), 1, F_, H_, W_, st)
+        def timed(fn, n=10):
+            for _ in range(3):
+                op_fwd(); op_flow(); fn()
+            torch.cuda.synchronize()
+            tot = 0.0
+            for _ in range(n):
+                if fn is op_bwd:
+                    op_flow()  # re-create the direct gradient that op_bwd accumulates into
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+            return tot / n
+        t_fwd, t_flow, t_bwd = timed(op_fwd), timed(op_flow), timed(op_bwd)
+
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = json.loads(peaks_path.read_text())["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    n = H_ * W_
+    p_ = F_ - 1
+    ops_bytes = {  # algorithmic bytes per launch of each op: inputs read once, outputs written once
+        "procrustes_fwd(k_moments)": n * (4 * F_ + (8 + 4) * p_),
+        "flow_loss_fwd_bwd(k_flow)": n * (4 * F_ + (8 + 8 + 4 + 4) * p_ + 4 * F_),
+        "procrustes_bwd(k_distribute)": n * (4 * F_ + (8 + 4) * p_ + 4 * p_ + 8 * F_),
+    }
+    times = {"procrustes_fwd(k_moments)": t_fwd, "flow_loss_fwd_bwd(k_flow)": t_flow,
+             "procrustes_bwd(k_distribute)": t_bwd}
+    dom = max(times, key=times.get)
+    path_ms = t_fwd + t_flow + t_bwd
+    path_gbs = algorithmic_bytes(F_, H_, W_) / (path_ms * 1e-3) / 1e9
+    dom_gbs = ops_bytes[dom] / (times[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(dom_gbs, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(dom_gbs / peak, 4), "traffic": None,
+                "peak_source": peak_src,
+                "path": {"what": "unproject->Procrustes->reproject->loss+grad (3 ops, summed)",
+                         "algorithmic_bytes": algorithmic_bytes(F_, H_, W_),
+                         "ms": round(path_ms, 4), "achieved": round(path_gbs, 1),
+                         "frac": round(path_gbs / peak, 4)},
+                "ops_ms": {k: round(v, 4) for k, v in times.items()}}
+
+    cpu = cpu_baseline(inputs, sample_frames=12, steps=2, warmup=1)
+
+    its = world * 1000.0 / ms
+    out = {
+        "metric": "overfit iters/sec at 150x360x640 (149 frame pairs per iteration)",
+        "value": round(its, 3), "unit": "it/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "frame_pairs_per_s": round(its * (F_ - 1), 1),
+        "config": {"workload": WORKLOAD, "frames": F_, "height": H_, "width": W_,
+                   "shards": f"{world} x {F_ - 1} pairs" if world > 1 else "1 x 149 pairs",
+                   "l2": "inputs (1.1 GB) exceed the 126 MB L2, no flush needed",
+                   "mask_sum": "loop-invariant denominator cached on tensor version"},
+        "e2e": {"value": round(world * 1000.0 / e2e_ms, 3), "unit": "it/s",
+                "ms_per_step": round(e2e_ms, 3), "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4,
+                "what": "Flows (flow fwd/bwd + masks) copied from pinned host memory every step, "
+                        "loss read back every step"},
+        "gpu_launches": int(launches), "final_loss": final_loss,
+        "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path.  The reference is pure Python on
+    ATen and cannot travel to the GPU box, so this times the oracle port of it (same op
+    sequence, torch CPU, all host threads) on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    inputs = synthetic_inputs(12, H_, W_, seed=0)
+    cpu = cpu_baseline(inputs, sample_frames=12, steps=max(1, args.steps), warmup=args.warmup)
+    out = {
+        "impl": "reference",
+        "metric": "overfit iters/sec at 150x360x640 (149 frame pairs per iteration)",
+        "value": round(cpu["value"], 6), "unit": "it/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1000.0 / cpu["value"], 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD}, "cpu_baseline": cpu,
+        "e2e": {"value": round(cpu["value"], 6), "unit": "it/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,7 @@ namespace {
 using namespace fm;
 
 thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;  // kernels launched by this library (bench evidence only)
 
 int fail(const char* what, cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
@@ -42,6 +43,7 @@ int fail_msg(const char* what) {
   do {                                                 \
     cudaError_t e_ = cudaGetLastError();               \
     if (e_ != cudaSuccess) return fail(name, e_);      \
+    __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); \
   } while (0)
 
 constexpr int kThreads = 256;
@@ -687,6 +689,7 @@ bool bad_dims(int B, int F, int H, int W) { return B < 1 || F < 2 || H < 1 || W 
 extern "C" {
 
 int fm_version(void) { return 100; }
+unsigned long long fm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 const char* fm_last_error(void) { return g_err; }
 
 size_t fm_workspace_bytes(int B, int F, int H, int W) {
@@ -722,8 +725,9 @@ int fm_unproject_bwd(const float* depth, const float* k4, const float* g_surface
   if (e != cudaSuccess) return fail("fm_unproject_bwd: memset", e);
   dim3 grid(blocks_for(H * W, 4), BF);
   k_unproject_bwd<<<grid, kThreads, 0, s>>>(depth, k4, g_surfaces, g_depth, w.k4acc, H, W);
+  FM_CHECK_LAUNCH("fm_unproject_bwd: k_unproject_bwd");
   k_d2f<<<(BF * 4 + 127) / 128, 128, 0, s>>>(w.k4acc, g_k4, BF * 4);
-  FM_CHECK_LAUNCH("fm_unproject_bwd");
+  FM_CHECK_LAUNCH("fm_unproject_bwd: k_d2f");
   return 0;
 }
 

@@ -1,0 +1,111 @@
+"""Loss side of the hot path.  Mirrors flowmap/loss/loss.py:24-58, loss_flow.py:26-70 and
+the mapping registry of flowmap/loss/mapping/__init__.py (same names / cfg fields)."""
+from __future__ import annotations
+
+import weakref
+from dataclasses import dataclass
+from typing import Literal, Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import ops
+from .types import Batch, Flows, ModelOutput
+
+
+@dataclass
+class MappingHuberCfg:
+    name: Literal["huber"]
+    delta: float
+
+
+@dataclass
+class MappingL1Cfg:
+    name: Literal["l1"]
+
+
+@dataclass
+class MappingL2Cfg:
+    name: Literal["l2"]
+
+
+@dataclass
+class LossCfgCommon:
+    enable_after: int
+    weight: float
+
+
+@dataclass
+class LossFlowCfg(LossCfgCommon):
+    name: Literal["flow"]
+    mapping: object
+
+
+@dataclass
+class LossTrackingCfg(LossCfgCommon):
+    name: Literal["tracking"]
+    mapping: object
+
+
+class Loss(nn.Module):
+    """loss.py:24-58: gate on enable_after, scale by weight."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+
+    def forward(self, batch, flows, tracks, model_output, global_step) -> Tensor:
+        if global_step < self.cfg.enable_after:  # loss.py:40-41
+            return torch.tensor(0, dtype=torch.float32, device=batch.videos.device)
+        return self.compute_weighted_loss(batch, flows, tracks, model_output, global_step)
+
+
+def _relative_from_extrinsics(extrinsics: Tensor) -> Tensor:
+    """inv(P_i) P_{i+1} for callers that hand in extrinsics without the Procrustes output
+    (projection.py:176); rigid inverse [R^T | -R^T t]."""
+    r, t = extrinsics[:, :-1, :3, :3], extrinsics[:, :-1, :3, 3:]
+    rn, tn = extrinsics[:, 1:, :3, :3], extrinsics[:, 1:, :3, 3:]
+    rt_ = r.transpose(-1, -2)
+    return torch.cat((rt_ @ rn, rt_ @ (tn - t)), dim=-1)
+
+
+class LossFlow(Loss):
+    """loss_flow.py:26-70.  The weight (loss.py:46) and the 1/mask-sum normalisation are
+    folded into the kernel so that it emits final gradients in the same pass."""
+
+    def __init__(self, cfg: LossFlowCfg):
+        super().__init__(cfg)
+        self._mask_key = None
+        self._mask_sum = None
+
+    def _mask_total(self, flows: Flows) -> Tensor:
+        # The denominator depends on the (constant) masks only: recompute when the mask
+        # tensors change identity or are written to.
+        fm, bm = flows.forward_mask, flows.backward_mask
+        key = self._mask_key
+        hit = (key is not None and key[0]() is fm and key[1]() is bm and
+               key[2] == (fm._version, bm._version))
+        if not hit:
+            self._mask_sum = ops.mask_sum(fm, bm)
+            self._mask_key = (weakref.ref(fm), weakref.ref(bm), (fm._version, bm._version))
+        return self._mask_sum
+
+    def compute_weighted_loss(self, batch, flows, tracks, model_output, global_step):
+        out = model_output
+        k4 = getattr(out, "k4", None)
+        if k4 is None:
+            k4 = ops.intrinsics_to_k4(out.intrinsics)
+        rt = getattr(out, "relative", None)
+        if rt is None:
+            rt = _relative_from_extrinsics(out.extrinsics)
+        m = self.cfg.mapping
+        return ops.flow_loss(out.depths, rt, k4, flows.forward, flows.backward,
+                             flows.forward_mask, flows.backward_mask, self._mask_total(flows),
+                             m.name, getattr(m, "delta", 0.0), self.cfg.weight)
+
+
+LOSSES = {"flow": LossFlow}
+
+
+def get_losses(cfgs):
+    return [LOSSES[c.name](c) for c in cfgs]

@@ -1,0 +1,208 @@
+"""Model side of the hot path: backbone -> intrinsics -> Procrustes poses.
+
+Mirrors flowmap/model/model.py:41-110 and the registries of flowmap/model/{backbone,
+intrinsics,extrinsics}/__init__.py with the same class names, cfg dataclasses and
+forward signatures; the bodies call the sm_100a kernels through flowmap_b200.ops.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Literal, Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import ops
+from .types import BackboneOutput, Batch, Flows, ModelExports, ModelOutput
+
+
+# --------------------------------------------------------------------------- backbones
+@dataclass
+class BackboneExplicitDepthCfg:
+    """config/model/backbone/explicit_depth.yaml"""
+    name: Literal["explicit_depth"]
+    initial_depth: float
+    weight_sensitivity: float
+
+
+class BackboneExplicitDepth(nn.Module):
+    """flowmap/model/backbone/backbone_explicit_depth.py:19-41: free depth and
+    correspondence-weight tensors; parameter names kept (`depth`, `weights`) so reference
+    checkpoints load."""
+
+    def __init__(self, cfg, num_frames, image_shape):
+        super().__init__()
+        self.cfg, self.num_frames, self.image_shape = cfg, num_frames, image_shape
+        self.depth = nn.Parameter(torch.full((num_frames, *image_shape), cfg.initial_depth,
+                                             dtype=torch.float32))
+        self.weights = nn.Parameter(torch.zeros((num_frames - 1, *image_shape),
+                                                dtype=torch.float32))
+
+    def forward(self, batch: Batch, flows: Flows) -> BackboneOutput:
+        assert batch.videos.shape[0] == 1  # backbone_explicit_depth.py:35-36
+        return BackboneOutput(self.depth[None],
+                              (self.cfg.weight_sensitivity * self.weights).sigmoid()[None])
+
+
+BACKBONES = {"explicit_depth": BackboneExplicitDepth}
+
+
+def get_backbone(cfg, num_frames, image_shape):
+    if cfg.name not in BACKBONES:
+        raise NotImplementedError(
+            f"backbone '{cfg.name}' is outside the hot path (SURVEY 2, row 6): construct the "
+            "reference's backbone and pass its BackboneOutput to the kernels instead")
+    return BACKBONES[cfg.name](cfg, num_frames, image_shape)
+
+
+# --------------------------------------------------------------------------- intrinsics
+def focal_lengths_to_intrinsics(focal_lengths: Tensor, image_shape) -> Tensor:
+    """flowmap/model/intrinsics/common.py:6-20."""
+    h, w = image_shape
+    scaled = focal_lengths * (h * w) ** 0.5
+    k = torch.zeros((*focal_lengths.shape, 3, 3), dtype=torch.float32, device=focal_lengths.device)
+    k[..., 0, 2] = 0.5
+    k[..., 1, 2] = 0.5
+    k[..., 2, 2] = 1.0
+    sel = torch.zeros((2, 3, 3), dtype=torch.float32, device=focal_lengths.device)
+    sel[0, 0, 0] = 1.0
+    sel[1, 1, 1] = 1.0
+    return k + (scaled / w)[..., None, None] * sel[0] + (scaled / h)[..., None, None] * sel[1]
+
+
+@dataclass
+class IntrinsicsRegressedCfg:
+    name: Literal["regressed"]
+    initial_focal_length: float
+
+
+class IntrinsicsRegressed(nn.Module):
+    """flowmap/model/intrinsics/intrinsics_regressed.py:22-41."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.focal_length = nn.Parameter(torch.tensor(cfg.initial_focal_length,
+                                                      dtype=torch.float32))
+
+    def forward(self, batch, flows, backbone_output, global_step) -> Tensor:
+        b, f, _, h, w = batch.videos.shape
+        return focal_lengths_to_intrinsics(self.focal_length, (h, w)).expand(b, f, 3, 3)
+
+
+@dataclass
+class IntrinsicsGroundTruthCfg:
+    name: Literal["ground_truth"]
+
+
+class IntrinsicsGroundTruth(nn.Module):
+    """flowmap/model/intrinsics/intrinsics_ground_truth.py:18-27."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+
+    def forward(self, batch, flows, backbone_output, global_step) -> Tensor:
+        return batch.intrinsics
+
+
+@dataclass
+class RegressionCfg:
+    after_step: int
+    window: int
+
+
+@dataclass
+class IntrinsicsSoftminCfg:
+    name: Literal["softmin"]
+    num_procrustes_points: int
+    min_focal_length: float
+    max_focal_length: float
+    num_candidates: int
+    regression: Optional[RegressionCfg]
+
+
+INTRINSICS = {"ground_truth": IntrinsicsGroundTruth, "regressed": IntrinsicsRegressed}
+
+
+def get_intrinsics(cfg):
+    return INTRINSICS[cfg.name](cfg)
+
+
+# --------------------------------------------------------------------------- extrinsics
+@dataclass
+class ExtrinsicsProcrustesCfg:
+    name: Literal["procrustes"]
+    num_points: Optional[int]
+    randomize_points: bool
+
+
+class ExtrinsicsProcrustes(nn.Module):
+    """flowmap/model/extrinsics/extrinsics_procrustes.py:23-59.  The reference receives
+    the materialised surfaces; here the point cloud is formed inside the moment kernel, so
+    ``forward`` takes depths + k4 and returns (extrinsics, relative poses)."""
+
+    def __init__(self, cfg, num_frames):
+        super().__init__()
+        self.cfg, self.num_frames = cfg, num_frames
+
+    def select_indices(self, h: int, w: int, device) -> Optional[Tensor]:
+        c = self.cfg
+        if c.num_points is None:
+            return None  # all pixels; the kernel's dense path
+        if c.randomize_points:
+            return torch.randint(0, h * w, (c.num_points,), dtype=torch.int64, device=device)
+        return torch.linspace(0, h * w - 1, c.num_points, dtype=torch.int64, device=device)
+
+    def forward(self, batch, flows, backbone_output, k4, indices=None):
+        _, _, h, w = backbone_output.depths.shape
+        if indices is None:
+            indices = self.select_indices(h, w, backbone_output.depths.device)
+        rt = ops.procrustes_poses(backbone_output.depths, backbone_output.weights, k4,
+                                  flows.backward, indices)
+        return ops.pose_chain(rt), rt
+
+
+EXTRINSICS = {"procrustes": ExtrinsicsProcrustes}
+
+
+def get_extrinsics(cfg, num_frames):
+    if cfg.name not in EXTRINSICS:
+        raise NotImplementedError(f"extrinsics '{cfg.name}' is an ablation outside the hot path")
+    return EXTRINSICS[cfg.name](cfg, num_frames)
+
+
+# --------------------------------------------------------------------------- model
+@dataclass
+class ModelCfg:
+    backbone: object
+    intrinsics: object
+    extrinsics: object
+    use_correspondence_weights: bool
+
+
+class Model(nn.Module):
+    """flowmap/model/model.py:41-110."""
+
+    def __init__(self, cfg: ModelCfg, num_frames=None, image_shape=None):
+        super().__init__()
+        self.cfg = cfg
+        self.backbone = get_backbone(cfg.backbone, num_frames, image_shape)
+        self.intrinsics = get_intrinsics(cfg.intrinsics)
+        self.extrinsics = get_extrinsics(cfg.extrinsics, num_frames)
+
+    def forward(self, batch: Batch, flows: Flows, global_step: int) -> ModelOutput:
+        backbone_out = self.backbone.forward(batch, flows)
+        if not self.cfg.use_correspondence_weights:  # model.py:67-68
+            backbone_out.weights = torch.ones_like(backbone_out.weights)
+        intrinsics = self.intrinsics.forward(batch, flows, backbone_out, global_step)
+        k4 = ops.intrinsics_to_k4(intrinsics)
+        extrinsics, rt = self.extrinsics.forward(batch, flows, backbone_out, k4)
+        return ModelOutput(backbone_out.depths, intrinsics, extrinsics, backbone_out.weights,
+                           relative=rt, k4=k4)
+
+    @torch.no_grad()
+    def export(self, batch: Batch, flows: Flows, global_step: int) -> ModelExports:
+        assert batch.videos.shape[0] == 1  # model.py:100-101
+        out = self.forward(batch, flows, global_step)
+        return ModelExports(out.extrinsics, out.intrinsics, batch.videos, out.depths)

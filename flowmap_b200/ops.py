@@ -1,0 +1,232 @@
+"""torch.autograd.Functions over the C ABI (include/flowmap_b200.h).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every number
+is produced by the sm_100a kernels in csrc/.  Inputs must be CUDA float32 tensors in the
+reference's layouts; anything else raises (there is no CPU or eager fallback).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from ._lib import check, lib
+
+MAPPINGS = {"huber": 0, "l1": 1, "l2": 2}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _canon(t: Tensor, name: str, dtype=torch.float32) -> Tensor:
+    if not isinstance(t, Tensor) or not t.is_cuda:
+        raise ValueError(f"flowmap_b200: `{name}` must be a CUDA tensor (no CPU path exists)")
+    if t.dtype != dtype:
+        raise ValueError(f"flowmap_b200: `{name}` must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def workspace(B: int, F: int, H: int, W: int, device) -> Tensor:
+    n = lib().fm_workspace_bytes(B, F, H, W)
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def intrinsics_to_k4(intrinsics: Tensor) -> Tensor:
+    """(..., 3, 3) normalised intrinsics -> (..., 4) = (fx, fy, cx, cy); differentiable."""
+    return torch.stack((intrinsics[..., 0, 0], intrinsics[..., 1, 1], intrinsics[..., 0, 2],
+                        intrinsics[..., 1, 2]), dim=-1)
+
+
+class _Procrustes(torch.autograd.Function):
+    """depths, weights, k4, backward flow [, indices] -> relative poses rt (B, F-1, 3, 4).
+
+    flowmap/model/projection.py:213-249 + flowmap/model/procrustes.py:7-51."""
+
+    @staticmethod
+    def forward(ctx, depths, weights, k4, backward_flows, indices):
+        depths = _canon(depths, "depths")
+        k4 = _canon(k4, "k4")
+        backward_flows = _canon(backward_flows, "backward_flows")
+        weights = None if weights is None else _canon(weights, "weights")
+        indices = None if indices is None else _canon(indices, "indices", torch.int64)
+        B, F, H, W = depths.shape
+        if backward_flows.shape != (B, F - 1, H, W, 2) or k4.shape != (B, F, 4):
+            raise ValueError("flowmap_b200: procrustes shape mismatch")
+        ws = workspace(B, F, H, W, depths.device)
+        rt = torch.empty((B, F - 1, 3, 4), dtype=torch.float32, device=depths.device)
+        with torch.cuda.device(depths.device):
+            check(lib().fm_procrustes_fwd(_ptr(depths), _ptr(k4), _ptr(backward_flows),
+                                          _ptr(weights), _ptr(indices),
+                                          0 if indices is None else indices.numel(), _ptr(rt),
+                                          _ptr(ws), B, F, H, W, _stream()), "fm_procrustes_fwd")
+        ctx.save_for_backward(depths, weights, k4, backward_flows, indices, ws)
+        return rt
+
+    @staticmethod
+    def backward(ctx, g_rt):
+        depths, weights, k4, backward_flows, indices, ws = ctx.saved_tensors
+        B, F, H, W = depths.shape
+        g_rt = _canon(g_rt, "g_rt")
+        g_depth = torch.zeros_like(depths)
+        g_weights = None
+        if weights is not None:
+            g_weights = torch.empty_like(weights) if indices is None else torch.zeros_like(weights)
+        g_k4 = torch.empty_like(k4)
+        with torch.cuda.device(depths.device):
+            check(lib().fm_procrustes_bwd(_ptr(depths), _ptr(k4), _ptr(backward_flows),
+                                          _ptr(weights), _ptr(indices),
+                                          0 if indices is None else indices.numel(), _ptr(g_rt),
+                                          0, None, _ptr(g_depth), _ptr(g_weights), _ptr(g_k4),
+                                          _ptr(ws), B, F, H, W, _stream()), "fm_procrustes_bwd")
+        return g_depth, g_weights, g_k4, None, None
+
+
+def procrustes_poses(depths: Tensor, weights: Optional[Tensor], k4: Tensor,
+                     backward_flows: Tensor, indices: Optional[Tensor] = None) -> Tensor:
+    return _Procrustes.apply(depths, weights, k4, backward_flows, indices)
+
+
+def mask_sum(forward_mask: Tensor, backward_mask: Tensor) -> Tensor:
+    """Device float64 scalar sum(forward_mask) + sum(backward_mask) (loss_flow.py:56,68)."""
+    fm, bm = _canon(forward_mask, "forward_mask"), _canon(backward_mask, "backward_mask")
+    if fm.numel() != bm.numel():
+        raise ValueError("flowmap_b200: mask shapes differ")
+    out = torch.empty((), dtype=torch.float64, device=fm.device)
+    with torch.cuda.device(fm.device):
+        check(lib().fm_mask_sum(_ptr(fm), _ptr(bm), _ptr(out), fm.numel(), _stream()),
+              "fm_mask_sum")
+    return out
+
+
+class _FlowLoss(torch.autograd.Function):
+    """Weighted dense flow loss; forward and analytic backward in one kernel pass.
+
+    flowmap/loss/loss_flow.py:31-70, loss.py:46, projection.py:116-184, loss/mapping/*."""
+
+    @staticmethod
+    def forward(ctx, depths, rt, k4, fflow, bflow, fmask, bmask, msum, mapping, delta, weight):
+        depths, rt, k4 = _canon(depths, "depths"), _canon(rt, "rt"), _canon(k4, "k4")
+        fflow, bflow = _canon(fflow, "flows.forward"), _canon(bflow, "flows.backward")
+        fmask, bmask = _canon(fmask, "flows.forward_mask"), _canon(bmask, "flows.backward_mask")
+        msum = _canon(msum, "mask_sum", torch.float64)
+        B, F, H, W = depths.shape
+        if (rt.shape != (B, F - 1, 3, 4) or k4.shape != (B, F, 4) or
+                fflow.shape != (B, F - 1, H, W, 2) or bflow.shape != fflow.shape or
+                fmask.shape != (B, F - 1, H, W) or bmask.shape != fmask.shape):
+            raise ValueError("flowmap_b200: flow loss shape mismatch")
+        dev = depths.device
+        ws = workspace(B, F, H, W, dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        g_depth = torch.empty_like(depths)
+        g_rt = torch.empty_like(rt)
+        g_k4 = torch.empty_like(k4)
+        with torch.cuda.device(dev):
+            check(lib().fm_flow_loss_fwd_bwd(_ptr(depths), _ptr(k4), _ptr(rt), _ptr(fflow),
+                                             _ptr(bflow), _ptr(fmask), _ptr(bmask), _ptr(msum),
+                                             MAPPINGS[mapping], float(delta), float(weight),
+                                             _ptr(loss), _ptr(g_depth), _ptr(g_rt), _ptr(g_k4),
+                                             _ptr(ws), B, F, H, W, _stream()),
+                  "fm_flow_loss_fwd_bwd")
+        ctx.save_for_backward(g_depth, g_rt, g_k4)
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        g_depth, g_rt, g_k4 = ctx.saved_tensors
+        return (g_depth * go, g_rt * go, g_k4 * go) + (None,) * 8
+
+
+def flow_loss(depths, rt, k4, fflow, bflow, fmask, bmask, msum, mapping="huber", delta=0.01,
+              weight=1.0) -> Tensor:
+    return _FlowLoss.apply(depths, rt, k4, fflow, bflow, fmask, bmask, msum, mapping, delta, weight)
+
+
+class _PoseChain(torch.autograd.Function):
+    """rt (B, F-1, 3, 4) -> camera-to-world extrinsics (B, F, 4, 4); projection.py:187-210."""
+
+    @staticmethod
+    def forward(ctx, rt):
+        rt = _canon(rt, "rt")
+        B, P = rt.shape[:2]
+        ext = torch.empty((B, P + 1, 4, 4), dtype=torch.float32, device=rt.device)
+        with torch.cuda.device(rt.device):
+            check(lib().fm_pose_chain(_ptr(rt), _ptr(ext), B, P + 1, _stream()), "fm_pose_chain")
+        ctx.save_for_backward(rt, ext)
+        return ext
+
+    @staticmethod
+    def backward(ctx, g_ext):
+        rt, ext = ctx.saved_tensors
+        g_ext = _canon(g_ext, "g_extrinsics")
+        g_rt = torch.empty_like(rt)
+        B, P = rt.shape[:2]
+        with torch.cuda.device(rt.device):
+            check(lib().fm_pose_chain_bwd(_ptr(rt), _ptr(ext), _ptr(g_ext), _ptr(g_rt), B, P + 1,
+                                          _stream()), "fm_pose_chain_bwd")
+        return g_rt
+
+
+def pose_chain(rt: Tensor) -> Tensor:
+    return _PoseChain.apply(rt)
+
+
+class _Unproject(torch.autograd.Function):
+    """depths (B, F, H, W), k4 (B, F, 4) -> surfaces (B, F, H, W, 3); projection.py:76-90 on
+    the pixel grid of :93-113."""
+
+    @staticmethod
+    def forward(ctx, depths, k4):
+        depths, k4 = _canon(depths, "depths"), _canon(k4, "k4")
+        B, F, H, W = depths.shape
+        surf = torch.empty((B, F, H, W, 3), dtype=torch.float32, device=depths.device)
+        with torch.cuda.device(depths.device):
+            check(lib().fm_unproject(_ptr(depths), _ptr(k4), _ptr(surf), B * F, H, W, _stream()),
+                  "fm_unproject")
+        ctx.save_for_backward(depths, k4)
+        return surf
+
+    @staticmethod
+    def backward(ctx, g_surf):
+        depths, k4 = ctx.saved_tensors
+        B, F, H, W = depths.shape
+        g_surf = _canon(g_surf, "g_surfaces")
+        g_depth, g_k4 = torch.empty_like(depths), torch.empty_like(k4)
+        ws = workspace(B, F, H, W, depths.device)
+        with torch.cuda.device(depths.device):
+            check(lib().fm_unproject_bwd(_ptr(depths), _ptr(k4), _ptr(g_surf), _ptr(g_depth),
+                                         _ptr(g_k4), _ptr(ws), B, F, H, W, _stream()),
+                  "fm_unproject_bwd")
+        return g_depth, g_k4
+
+
+def unproject_depth(depths: Tensor, k4: Tensor) -> Tensor:
+    return _Unproject.apply(depths, k4)
+
+
+def reproject(xyz: Tensor, rt: Tensor, k4: Tensor) -> Tensor:
+    """Forward-only: xyz (items, n, 3), rt (items, 3, 4), k4 (items, 4) -> xy (items, n, 2)."""
+    xyz, rt, k4 = _canon(xyz, "xyz"), _canon(rt, "rt"), _canon(k4, "k4")
+    items, n = xyz.shape[:2]
+    out = torch.empty((items, n, 2), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        check(lib().fm_reproject(_ptr(xyz), _ptr(rt), _ptr(k4), _ptr(out), items, n, _stream()),
+              "fm_reproject")
+    return out
+
+
+def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, step: int,
+              lr: float, betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+    """In-place torch.optim.Adam update (model_wrapper_overfit.py:104-105)."""
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("flowmap_b200: adam_step needs contiguous CUDA float32 tensors")
+    with torch.cuda.device(param.device):
+        check(lib().fm_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq),
+                                 param.numel(), lr, betas[0], betas[1], eps, step, _stream()),
+              "fm_adam_step")

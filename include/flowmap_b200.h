@@ -35,6 +35,9 @@ extern "C" {
 
 int fm_version(void);
 const char* fm_last_error(void);
+/* Number of kernels this library has launched in this process (evidence for bench.py's
+ * gpu_launches; one count per successful launch). */
+unsigned long long fm_launch_count(void);
 
 /* Scratch size for one optimisation step on (B, F, H, W). */
 size_t fm_workspace_bytes(int B, int F, int H, int W);

@@ -1,0 +1,44 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol the header declares."""
+import ctypes
+import re
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "flowmap_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    from flowmap_b200.build import build
+    from flowmap_b200 import _lib
+    so = build()
+    handle = ctypes.CDLL(str(so))
+    names = declared_symbols()
+    assert len(names) >= 10
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert _lib.lib().fm_version() >= 100
+    # pure host-side query works without a GPU
+    assert _lib.lib().fm_workspace_bytes(1, 150, 360, 640) > 0
+    assert _lib.lib().fm_workspace_bytes(1, 1, 8, 8) == 0
+
+
+def test_product_has_no_cpu_path():
+    import pytest
+    import torch
+    from flowmap_b200 import ops
+    d = torch.zeros(1, 2, 4, 4)
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.procrustes_poses(d, None, torch.zeros(1, 2, 4), torch.zeros(1, 1, 4, 4, 2))
+
+
+def test_package_does_not_import_oracle():
+    import subprocess, sys
+    code = ("import sys, flowmap_b200, flowmap_b200.model, flowmap_b200.loss, flowmap_b200.overfit;"
+            "bad=[m for m in sys.modules if m.startswith('oracle')]; assert not bad, bad")
+    subprocess.check_call([sys.executable, "-c", code], cwd=str(ROOT))
