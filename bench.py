@@ -108,8 +108,22 @@ def cpu_baseline(inputs, sample_frames, steps, warmup):
     host cores on the first `sample_frames` frames of the workload; it/s scaled by pairs."""
     from oracle import flowmap_oracle as O
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     f, h, w = sample_frames, inputs["depth"].shape[1], inputs["depth"].shape[2]
+    # "all the host threads it can use": ATen's elementwise kernels stop scaling (and then
+    # collapse) well below the core count of a 128-core host, so pick the fastest setting.
+    best, best_t = None, None
+    for nt in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}):
+        torch.set_num_threads(nt)
+        st = O.OverfitOracle(O.OverfitConfig(intrinsics="regressed"), 3, h, w)
+        fl = O.Flows(inputs["fwd"][:, :2], inputs["bwd"][:, :2], inputs["fmask"][:, :2],
+                     inputs["bmask"][:, :2])
+        st.training_step(fl)
+        t0 = time.perf_counter()
+        st.training_step(fl)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = nt, dt
+    torch.set_num_threads(best)
     st = O.OverfitOracle(O.OverfitConfig(intrinsics="regressed"), f, h, w)
     with torch.no_grad():
         st.depth.copy_(inputs["depth"][:f])
@@ -297,7 +311,11 @@ def run_gpu(args):
                          "frac": round(path_gbs / peak, 4)},
                 "ops_ms": {k: round(v, 4) for k, v in times.items()}}
 
-    cpu = cpu_baseline(inputs, sample_frames=12, steps=2, warmup=1)
+    if os.environ.get("FM_BENCH_SKIP_CPU") == "1":  # profiling runs (ncu) only
+        cpu = {"value": None, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "skipped (FM_BENCH_SKIP_CPU=1)"}
+    else:
+        cpu = cpu_baseline(inputs, sample_frames=12, steps=2, warmup=1)
 
     its = world * 1000.0 / ms
     out = {

@@ -103,7 +103,15 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Block-wide sum of NV per-thread values, result atomically added (fp64) to dst[0..NV).
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of NV per-thread float values, atomically added (fp64) to dst[0..NV).
+// Per-thread partials cover at most a few dozen pixels, so the float32 warp tree adds no
+// visible error; the cross-warp and cross-block sums run in float64.
 // smem must hold NV * (kThreads / 32) doubles.
 template <int NV>
 __device__ __forceinline__ void block_accumulate(const float* vals, double* dst, double* smem) {
@@ -111,8 +119,8 @@ __device__ __forceinline__ void block_accumulate(const float* vals, double* dst,
   constexpr int NW = kThreads / 32;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    double s = warp_sum((double)vals[i]);
-    if (lane == 0) smem[i * NW + warp] = s;
+    const float s = warp_sum_f(vals[i]);
+    if (lane == 0) smem[i * NW + warp] = (double)s;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < NV; i += kThreads) {
@@ -143,21 +151,49 @@ __device__ __forceinline__ void block_accumulate_d(const double* vals, double* d
   __syncthreads();
 }
 
+// Fire-and-forget float add (RED.E.ADD.F32); no return value, no warp aggregation code.
+__device__ __forceinline__ void red_add(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+// Load the 4 (or 1) values a thread owns.
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* p, float* out) {
+  if (VEC == 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  } else {
+    out[0] = __ldg(p);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void load_vec2(const float* p, float* out) {  // 2 * VEC floats
+  if (VEC == 4) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+    out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+  } else {
+    const float2 a = __ldg(reinterpret_cast<const float2*>(p));
+    out[0] = a.x; out[1] = a.y;
+  }
+}
+
 // ================================================================== phase A: moments
 __device__ __forceinline__ PairGeom pair_geom(const float* depth, const float* k4, int pair, int F,
                                               int H, int W) {
   const int bi = pair / (F - 1), i = pair - bi * (F - 1);
   const int a = bi * F + i;
   PairGeom g;
-  g.ka = load_k4(k4, a);
-  g.kb = load_k4(k4, a + 1);
-  g.H = H; g.W = W;
+  g.ka = make_cam(load_k4(k4, a));
+  g.kb = make_cam(load_k4(k4, a + 1));
+  g.grid = make_grid(H, W);
   g.z0 = __ldg(depth + (size_t)(a + 1) * H * W + (size_t)(H / 2) * W + W / 2);
   return g;
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
           const float* __restrict__ bflow, const float* __restrict__ weights,
           const int64_t* __restrict__ indices, int num_indices, double* __restrict__ moments,
@@ -177,35 +213,33 @@ k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
   for (int i = 0; i < kNumMoments; ++i) accd[i] = 0.0;
 
   if (indices == nullptr) {
-    for (int base = (blockIdx.x * kThreads + threadIdx.x) * VEC; base < N;
-         base += gridDim.x * kThreads * VEC) {
+    constexpr int kFlush = 4;  // float32 partials over at most kFlush * VEC pixels
+    int base = (blockIdx.x * kThreads + threadIdx.x) * VEC;
+    const int stride = gridDim.x * kThreads * VEC;
+    while (base < N) {
       float acc[kNumMoments];
 #pragma unroll
       for (int i = 0; i < kNumMoments; ++i) acc[i] = 0.f;
-      float dv[VEC], wv[VEC], fv[2 * VEC];
-      if (VEC == 4) {
-        const float4 d4 = __ldg(reinterpret_cast<const float4*>(db + base));
-        dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
-        if (wt) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wt + base));
-          wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
-        } else { wv[0] = wv[1] = wv[2] = wv[3] = 1.f; }
-        const float4 f0 = __ldg(reinterpret_cast<const float4*>(fl + 2 * base));
-        const float4 f1 = __ldg(reinterpret_cast<const float4*>(fl + 2 * base) + 1);
-        fv[0] = f0.x; fv[1] = f0.y; fv[2] = f0.z; fv[3] = f0.w;
-        fv[4] = f1.x; fv[5] = f1.y; fv[6] = f1.z; fv[7] = f1.w;
-      } else {
-        dv[0] = __ldg(db + base);
-        wv[0] = wt ? __ldg(wt + base) : 1.f;
-        fv[0] = __ldg(fl + 2 * base); fv[1] = __ldg(fl + 2 * base + 1);
-      }
-      const int r = base / W, c0 = base - r * W;
+#pragma unroll 1
+      for (int it = 0; it < kFlush && base < N; ++it, base += stride) {
+        float dv[VEC], wv[VEC], fv[2 * VEC];
+        load_vec<VEC>(db + base, dv);
+        load_vec2<VEC>(fl + 2 * base, fv);
+        if (wt) load_vec<VEC>(wt + base, wv);
+        else {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        float p[3], q[3];
-        Taps taps;
-        point_pq(g, r, c0 + v, dv[v], fv[2 * v], fv[2 * v + 1], load_a, p, q, taps);
-        moments_add(acc, wv[v], p, q);
+          for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
+        }
+        const int r = base / W, c0 = base - r * W;
+        const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          float p[3], q[3];
+          Taps taps;
+          point_pq(g, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], fv[2 * v], fv[2 * v + 1],
+                   load_a, p, q, taps);
+          moments_add(acc, wv[v], p, q);
+        }
       }
 #pragma unroll
       for (int i = 0; i < kNumMoments; ++i) accd[i] += (double)acc[i];
@@ -219,7 +253,8 @@ k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
       for (int i = 0; i < kNumMoments; ++i) acc[i] = 0.f;
       float p[3], q[3];
       Taps taps;
-      point_pq(g, r, c, __ldg(db + j), __ldg(fl + 2 * j), __ldg(fl + 2 * j + 1), load_a, p, q, taps);
+      point_pq(g, pix_coord(c, g.grid.Wf, g.grid.invW), pix_coord(r, g.grid.Hf, g.grid.invH),
+               __ldg(db + j), __ldg(fl + 2 * j), __ldg(fl + 2 * j + 1), load_a, p, q, taps);
       moments_add(acc, wt ? __ldg(wt + j) : 1.f, p, q);
 #pragma unroll
       for (int i = 0; i < kNumMoments; ++i) accd[i] += (double)acc[i];
@@ -258,7 +293,7 @@ __global__ void k_solve(const double* __restrict__ moments, const float* __restr
 //  29..32   dK_{k+1} through the forward-term projection
 //  33..36   dK_{k-1} through the backward-term projection
 template <int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_flow(const float* __restrict__ depth, const float* __restrict__ k4, const float* __restrict__ rt,
        const float* __restrict__ fflow, const float* __restrict__ bflow,
        const float* __restrict__ fmask, const float* __restrict__ bmask,
@@ -271,17 +306,17 @@ k_flow(const float* __restrict__ depth, const float* __restrict__ k4, const floa
   FlowFrame f;
   f.hasF = i < F - 1;
   f.hasB = i > 0;
-  f.kk = load_k4(k4, frame);
-  f.kn = load_k4(k4, f.hasF ? frame + 1 : frame);
-  f.kp = load_k4(k4, f.hasB ? frame - 1 : frame);
+  f.kk = make_cam(load_k4(k4, frame));
+  f.kn = make_cam(load_k4(k4, f.hasF ? frame + 1 : frame));
+  f.kp = make_cam(load_k4(k4, f.hasB ? frame - 1 : frame));
   const int pairF = bi * (F - 1) + i, pairB = pairF - 1;
   if (f.hasF) f.tf = load_rt(rt, pairF);
   if (f.hasB) f.tb = load_rt(rt, pairB);
   double den = mask_sum ? *mask_sum : 1.0;
   if (den == 0.0) den = 1.0;  // loss_flow.py:70 "valid_sum or 1"
   const float g = (float)((double)loss_weight / den);
-  const float sc = sqrtf((float)H * (float)W);
-  const float ax = (float)W / sc, ay = (float)H / sc;
+  const RobustCfg rc = make_robust(mapping, delta, H, W);
+  const GridDims grid = make_grid(H, W);
 
   const float* D = depth + (size_t)frame * N;
   const float* ff = fflow + (size_t)(f.hasF ? pairF : 0) * N * 2;
@@ -297,38 +332,17 @@ k_flow(const float* __restrict__ depth, const float* __restrict__ k4, const floa
   for (int base = (blockIdx.x * kThreads + threadIdx.x) * VEC; base < N;
        base += gridDim.x * kThreads * VEC) {
     float dv[VEC], ffv[2 * VEC], fbv[2 * VEC], mfv[VEC], mbv[VEC], out[VEC];
-    if (VEC == 4) {
-      const float4 d4 = __ldg(reinterpret_cast<const float4*>(D + base));
-      dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
-      if (f.hasF) {
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(ff + 2 * base));
-        const float4 a1 = __ldg(reinterpret_cast<const float4*>(ff + 2 * base) + 1);
-        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mf + base));
-        ffv[0] = a0.x; ffv[1] = a0.y; ffv[2] = a0.z; ffv[3] = a0.w;
-        ffv[4] = a1.x; ffv[5] = a1.y; ffv[6] = a1.z; ffv[7] = a1.w;
-        mfv[0] = m4.x; mfv[1] = m4.y; mfv[2] = m4.z; mfv[3] = m4.w;
-      }
-      if (f.hasB) {
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(fb + 2 * base));
-        const float4 a1 = __ldg(reinterpret_cast<const float4*>(fb + 2 * base) + 1);
-        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mb + base));
-        fbv[0] = a0.x; fbv[1] = a0.y; fbv[2] = a0.z; fbv[3] = a0.w;
-        fbv[4] = a1.x; fbv[5] = a1.y; fbv[6] = a1.z; fbv[7] = a1.w;
-        mbv[0] = m4.x; mbv[1] = m4.y; mbv[2] = m4.z; mbv[3] = m4.w;
-      }
-    } else {
-      dv[0] = __ldg(D + base);
-      if (f.hasF) { ffv[0] = __ldg(ff + 2 * base); ffv[1] = __ldg(ff + 2 * base + 1); mfv[0] = __ldg(mf + base); }
-      if (f.hasB) { fbv[0] = __ldg(fb + 2 * base); fbv[1] = __ldg(fb + 2 * base + 1); mbv[0] = __ldg(mb + base); }
-    }
+    load_vec<VEC>(D + base, dv);
+    if (f.hasF) { load_vec2<VEC>(ff + 2 * base, ffv); load_vec<VEC>(mf + base, mfv); }
+    if (f.hasB) { load_vec2<VEC>(fb + 2 * base, fbv); load_vec<VEC>(mb + base, mbv); }
     const int r = base / W, c0 = base - r * W;
-    const float y = pix_y(r, H);
+    const float y = pix_coord(r, grid.Hf, grid.invH);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      out[v] = flow_pixel(f, pix_x(c0 + v, W), y, dv[v], f.hasF ? ffv[2 * v] : 0.f,
-                          f.hasF ? ffv[2 * v + 1] : 0.f, f.hasF ? mfv[v] : 0.f,
-                          f.hasB ? fbv[2 * v] : 0.f, f.hasB ? fbv[2 * v + 1] : 0.f,
-                          f.hasB ? mbv[v] : 0.f, g, ax, ay, mapping, delta, acc);
+      out[v] = flow_pixel(f, pix_coord(c0 + v, grid.Wf, grid.invW), y, dv[v],
+                          f.hasF ? ffv[2 * v] : 0.f, f.hasF ? ffv[2 * v + 1] : 0.f,
+                          f.hasF ? mfv[v] : 0.f, f.hasB ? fbv[2 * v] : 0.f,
+                          f.hasB ? fbv[2 * v + 1] : 0.f, f.hasB ? mbv[v] : 0.f, g, rc, acc);
     }
     if (VEC == 4) {
       *reinterpret_cast<float4*>(gd + base) = make_float4(out[0], out[1], out[2], out[3]);
@@ -408,7 +422,7 @@ __global__ void k_adjoint(const double* __restrict__ flowacc, const PairState* _
 
 // ================================================================== phase D2: distribute
 template <int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
              const float* __restrict__ bflow, const float* __restrict__ weights,
              const int64_t* __restrict__ indices, int num_indices,
@@ -431,7 +445,7 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
   const float* wt = weights ? weights + (size_t)pair * N : nullptr;
   float* gda = g_depth + (size_t)a * N;
   auto load_a = [da](int i) { return __ldg(da + i); };
-  auto scatter = [gda](int i, float v) { atomicAdd(gda + i, v); };
+  auto scatter = [gda](int i, float v) { red_add(gda + i, v); };
   float* gdb = gda + N;
   float* gw = g_weights ? g_weights + (size_t)pair * N : nullptr;
   float kacc[8];
@@ -442,28 +456,21 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
     for (int base = (blockIdx.x * kThreads + threadIdx.x) * VEC; base < N;
          base += gridDim.x * kThreads * VEC) {
       float dv[VEC], wv[VEC], fv[2 * VEC], gwv[VEC], gdv[VEC];
-      if (VEC == 4) {
-        const float4 d4 = __ldg(reinterpret_cast<const float4*>(db + base));
-        dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
-        if (wt) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wt + base));
-          wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
-        } else { wv[0] = wv[1] = wv[2] = wv[3] = 1.f; }
-        const float4 f0 = __ldg(reinterpret_cast<const float4*>(fl + 2 * base));
-        const float4 f1 = __ldg(reinterpret_cast<const float4*>(fl + 2 * base) + 1);
-        fv[0] = f0.x; fv[1] = f0.y; fv[2] = f0.z; fv[3] = f0.w;
-        fv[4] = f1.x; fv[5] = f1.y; fv[6] = f1.z; fv[7] = f1.w;
-      } else {
-        dv[0] = __ldg(db + base);
-        wv[0] = wt ? __ldg(wt + base) : 1.f;
-        fv[0] = __ldg(fl + 2 * base); fv[1] = __ldg(fl + 2 * base + 1);
+      load_vec<VEC>(db + base, dv);
+      load_vec2<VEC>(fl + 2 * base, fv);
+      if (wt) load_vec<VEC>(wt + base, wv);
+      else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
       }
       const int r = base / W, c0 = base - r * W;
+      const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
 #pragma unroll
       for (int v = 0; v < VEC; ++v)
-        distribute_point(g, ad, r, c0 + v, dv[v], wv[v], fv[2 * v], fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
+        distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v],
+                         fv[2 * v], fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) atomicAdd(gdb + base + v, gdv[v]);
+      for (int v = 0; v < VEC; ++v) red_add(gdb + base + v, gdv[v]);
       if (gw) {
         if (VEC == 4) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
         else gw[base] = gwv[0];
@@ -474,10 +481,12 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
       const int j = (int)indices[t];
       const int r = j / W, c = j - r * W;
       float gdj, gwj;
-      distribute_point(g, ad, r, c, __ldg(db + j), wt ? __ldg(wt + j) : 1.f, __ldg(fl + 2 * j),
-                       __ldg(fl + 2 * j + 1), load_a, scatter, gdj, gwj, kacc);
-      atomicAdd(gdb + j, gdj);
-      if (gw) atomicAdd(gw + j, gwj);
+      distribute_point(g, ad, pix_coord(c, g.grid.Wf, g.grid.invW),
+                       pix_coord(r, g.grid.Hf, g.grid.invH), __ldg(db + j),
+                       wt ? __ldg(wt + j) : 1.f, __ldg(fl + 2 * j), __ldg(fl + 2 * j + 1), load_a,
+                       scatter, gdj, gwj, kacc);
+      red_add(gdb + j, gdj);
+      if (gw) red_add(gw + j, gwj);
     }
   }
   // kacc[0..3] -> frame a, kacc[4..7] -> frame b = a + 1: contiguous in k4acc
@@ -532,7 +541,7 @@ k_mask_sum(const float* __restrict__ a, const float* __restrict__ b, double* __r
 __global__ void k_unproject(const float* __restrict__ depth, const float* __restrict__ k4,
                             float* __restrict__ surf, int H, int W) {
   const int frame = blockIdx.y, N = H * W;
-  const K4 k = load_k4(k4, frame);
+  const Cam k = make_cam(load_k4(k4, frame));
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
     const int r = j / W, c = j - r * W;
     float rx, ry;
@@ -548,7 +557,7 @@ k_unproject_bwd(const float* __restrict__ depth, const float* __restrict__ k4,
                 const float* __restrict__ gs, float* __restrict__ gd, double* __restrict__ gk, int H, int W) {
   __shared__ double smem[4 * (kThreads / 32)];
   const int frame = blockIdx.y, N = H * W;
-  const K4 k = load_k4(k4, frame);
+  const Cam k = make_cam(load_k4(k4, frame));
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
     const int r = j / W, c = j - r * W;
@@ -558,10 +567,10 @@ k_unproject_bwd(const float* __restrict__ depth, const float* __restrict__ k4,
     const float* g = gs + ((size_t)frame * N + j) * 3;
     const float g0 = g[0], g1 = g[1], g2 = g[2];
     gd[(size_t)frame * N + j] = g0 * rx + g1 * ry + g2;
-    acc[0] -= g0 * d * rx / k.fx;
-    acc[1] -= g1 * d * ry / k.fy;
-    acc[2] -= g0 * d / k.fx;
-    acc[3] -= g1 * d / k.fy;
+    acc[0] -= g0 * d * rx * k.ifx;
+    acc[1] -= g1 * d * ry * k.ify;
+    acc[2] -= g0 * d * k.ifx;
+    acc[3] -= g1 * d * k.ify;
   }
   block_accumulate<4>(acc, gk + (size_t)frame * 4, smem);
 }
@@ -575,7 +584,7 @@ __global__ void k_reproject(const float* __restrict__ xyz, const float* __restri
                             const float* __restrict__ k4, float* __restrict__ xy, int n) {
   const int item = blockIdx.y;
   const Rt t = load_rt(rt, item);
-  const K4 k = load_k4(k4, item);
+  const Cam k = make_cam(load_k4(k4, item));
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const float* p = xyz + ((size_t)item * n + j) * 3;
     const float s0 = p[0], s1 = p[1], s2 = p[2];
@@ -676,7 +685,7 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
 int blocks_for(int n_items_per_row, int vec) {
   // ~4096 items per block keeps thousands of blocks in flight at the BASELINE sizes and
   // still gives every thread a few independent loads.
-  const int per_block = kThreads * vec * 4;
+  const int per_block = kThreads * vec * 16;
   int nb = (n_items_per_row + per_block - 1) / per_block;
   return nb < 1 ? 1 : nb;
 }

@@ -28,6 +28,30 @@ struct Rt {  // rigid 3x4 [R | t], row-major R
 
 enum Mapping : int { MAP_HUBER = 0, MAP_L1 = 1, MAP_L2 = 2 };
 
+// Reciprocal / reciprocal square root: MUFU approximations on the device (<= 1-2 ulp,
+// no IEEE slow path), plain C on the host (tests/host_emulation).
+FM_HD float fm_rcp(float v) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(1.0f, v);
+#else
+  return 1.0f / v;
+#endif
+}
+FM_HD float fm_rsqrt(float v) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(v);
+#else
+  return 1.0f / sqrtf(v);
+#endif
+}
+FM_HD float fm_fma(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, c);
+#else
+  return fmaf(a, b, c);
+#endif
+}
+
 constexpr float kProjEps = 1e-5f;   // projection.py:52
 constexpr float kProjInf = 1e8f;    // projection.py:53
 
@@ -37,10 +61,32 @@ constexpr float kProjInf = 1e8f;    // projection.py:53
 FM_HD float pix_x(int c, int W) { return ((float)c + 0.5f) / (float)W; }
 FM_HD float pix_y(int r, int H) { return ((float)r + 0.5f) / (float)H; }
 
+// Same value as (i + .5) / n, correctly rounded, from a precomputed inv_n = 1 / n: one
+// Newton correction of the quotient with an exact FMA remainder (three instructions
+// instead of an IEEE division).
+FM_HD float pix_coord(int i, float n, float inv_n) {
+  const float a = (float)i + 0.5f;
+  const float q = a * inv_n;
+  const float r = fm_fma(-q, n, a);
+  return fm_fma(r, inv_n, q);
+}
+
+// Per-frame camera constants: K and the reciprocals of the focal lengths.
+struct Cam {
+  float fx, fy, cx, cy, ifx, ify;
+};
+FM_HD Cam make_cam(const K4& k) {
+  Cam c;
+  c.fx = k.fx; c.fy = k.fy; c.cx = k.cx; c.cy = k.cy;
+  c.ifx = 1.0f / k.fx;
+  c.ify = 1.0f / k.fy;
+  return c;
+}
+
 // Ray of K^-1 [x y 1]^T with z = 1 (projection.py:84-87).
-FM_HD void ray_of(float x, float y, const K4& k, float& rx, float& ry) {
-  rx = (x - k.cx) / k.fx;
-  ry = (y - k.cy) / k.fy;
+FM_HD void ray_of(float x, float y, const Cam& k, float& rx, float& ry) {
+  rx = (x - k.cx) * k.ifx;
+  ry = (y - k.cy) * k.ify;
 }
 
 // ---------------------------------------------------------------------------------
@@ -54,24 +100,47 @@ struct Taps {
   float w00, w01, w10, w11;  // weights: w{row}{col}: (y0,x0) (y0,x1) (y1,x0) (y1,x1)
 };
 
-FM_HD Taps bilinear_taps(float ex, float ey, int H, int W) {
-  float gx = ex * 2.0f - 1.0f, gy = ey * 2.0f - 1.0f;
-  float px = ((gx + 1.0f) * (float)W - 1.0f) * 0.5f;
-  float py = ((gy + 1.0f) * (float)H - 1.0f) * 0.5f;
-  px = fminf((float)(W - 1), fmaxf(px, 0.0f));
-  py = fminf((float)(H - 1), fmaxf(py, 0.0f));
-  // NaN locations: fmaxf(NaN, 0) = 0, matching ATen's clip of NaN to 0 is not needed for
-  // finite flows; finite input is a documented precondition.
-  float fx0 = floorf(px), fy0 = floorf(py);
-  float tx = px - fx0, ty = py - fy0;
+struct GridDims {
+  int H, W;
+  float Hf, Wf, invH, invW;
+};
+FM_HD GridDims make_grid(int H, int W) {
+  GridDims g;
+  g.H = H; g.W = W; g.Hf = (float)H; g.Wf = (float)W;
+  g.invH = 1.0f / (float)H; g.invW = 1.0f / (float)W;
+  return g;
+}
+
+// floor() of a value in [0, 2^22) together with its integer, on the FP32 add pipe: adding
+// 1.5 * 2^23 to (v - .5) rounds to the nearest integer; a tie (v an exact integer) may pick
+// v - 1 with fraction 1, which is the same point of the (continuous) bilinear interpolant.
+FM_HD int floor_pos(float v, float& frac) {
+  const float magic = 12582912.0f;  // 1.5 * 2^23
+  const float m = (v - 0.5f) + magic;
+  const float fl = m - magic;
+  frac = v - fl;
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(m) - 0x4B400000;
+#else
+  return (int)fl;
+#endif
+}
+
+FM_HD Taps bilinear_taps(float ex, float ey, const GridDims& g) {
+  // unnormalise (align_corners=False): ((2e - 1 + 1) * n - 1) / 2 = e * n - .5, then clip
+  float px = fm_fma(ex, g.Wf, -0.5f);
+  float py = fm_fma(ey, g.Hf, -0.5f);
+  px = fminf(g.Wf - 1.0f, fmaxf(px, 0.0f));
+  py = fminf(g.Hf - 1.0f, fmaxf(py, 0.0f));
+  float tx, ty;
   Taps t;
-  t.x0 = (int)fx0;
-  t.y0 = (int)fy0;
+  t.x0 = floor_pos(px, tx);
+  t.y0 = floor_pos(py, ty);
   t.x1 = t.x0 + 1;
   t.y1 = t.y0 + 1;
   float wx1 = tx, wx0 = 1.0f - tx, wy1 = ty, wy0 = 1.0f - ty;
-  if (t.x1 > W - 1) { t.x1 = W - 1; wx1 = 0.0f; }
-  if (t.y1 > H - 1) { t.y1 = H - 1; wy1 = 0.0f; }
+  if (t.x1 > g.W - 1) { t.x1 = g.W - 1; wx1 = 0.0f; }
+  if (t.y1 > g.H - 1) { t.y1 = g.H - 1; wy1 = 0.0f; }
   t.w00 = wy0 * wx0;
   t.w01 = wy0 * wx1;
   t.w10 = wy1 * wx0;
@@ -81,16 +150,25 @@ FM_HD Taps bilinear_taps(float ex, float ey, int H, int W) {
 
 // Bilinear sample of the xyz image D*ray(K) of a frame (NOT interp(D)*ray(e)): returns
 // q = (qx, qy, qz).  `D` points at the frame's (H, W) depth.
+// Rays through the tap centres.  (i + .5) * inv_n instead of the exact quotient: the tap
+// rays only enter weighted sums, where one ulp is far below the float32 noise floor.
+FM_HD void tap_rays(const Taps& t, const GridDims& g, const Cam& k, float& rx0, float& ry0,
+                    float& rx1, float& ry1) {
+  rx0 = (((float)t.x0 + 0.5f) * g.invW - k.cx) * k.ifx;
+  rx1 = (((float)t.x1 + 0.5f) * g.invW - k.cx) * k.ifx;
+  ry0 = (((float)t.y0 + 0.5f) * g.invH - k.cy) * k.ify;
+  ry1 = (((float)t.y1 + 0.5f) * g.invH - k.cy) * k.ify;
+}
+
 template <typename Load>
-FM_HD void sample_surface(const Taps& t, int W, int H, const K4& k, Load load, float& qx,
+FM_HD void sample_surface(const Taps& t, const GridDims& g, const Cam& k, Load load, float& qx,
                           float& qy, float& qz) {
+  const int W = g.W;
   float d00 = load(t.y0 * W + t.x0), d01 = load(t.y0 * W + t.x1);
   float d10 = load(t.y1 * W + t.x0), d11 = load(t.y1 * W + t.x1);
   float a00 = t.w00 * d00, a01 = t.w01 * d01, a10 = t.w10 * d10, a11 = t.w11 * d11;
-  float rx0, rx1, ry0, ry1, dummy;
-  ray_of(pix_x(t.x0, W), pix_y(t.y0, H), k, rx0, ry0);
-  ray_of(pix_x(t.x1, W), pix_y(t.y1, H), k, rx1, ry1);
-  (void)dummy;
+  float rx0, rx1, ry0, ry1;
+  tap_rays(t, g, k, rx0, ry0, rx1, ry1);
   qx = (a00 + a10) * rx0 + (a01 + a11) * rx1;
   qy = (a00 + a01) * ry0 + (a10 + a11) * ry1;
   qz = (a00 + a01) + (a10 + a11);
@@ -103,7 +181,8 @@ FM_HD void sample_surface(const Taps& t, int W, int H, const K4& k, Load load, f
 struct Proj {
   float u[3];      // after nan_to_num
   float inv;       // 1 / (z + eps)
-  bool finite[3];  // gradient passes only through finite components
+  bool all_finite; // common case: every component finite, gradient passes everywhere
+  bool finite[3];  // (only meaningful when !all_finite)
   float uvx, uvy;
 };
 
@@ -115,33 +194,46 @@ FM_HD float nan_to_num1(float v, bool& fin) {
   return v;
 }
 
-FM_HD Proj project_point(float X, float Y, float Z, const K4& k) {
+FM_HD Proj project_point(float X, float Y, float Z, const Cam& k) {
   Proj p;
   float den = Z + kProjEps;
-  p.inv = 1.0f / den;
-  p.u[0] = nan_to_num1(X / den, p.finite[0]);
-  p.u[1] = nan_to_num1(Y / den, p.finite[1]);
-  p.u[2] = nan_to_num1(Z / den, p.finite[2]);
+  p.inv = fm_rcp(den);  // den == 0 -> inf, products below -> +-inf / nan as the division would
+  p.u[0] = X * p.inv;
+  p.u[1] = Y * p.inv;
+  p.u[2] = Z * p.inv;
+  // one test for the common case; inf/nan components (z + eps == 0, overflow) take the
+  // nan_to_num branch (projection.py:56)
+  p.all_finite = (fabsf(p.u[0]) <= 3.0e38f) & (fabsf(p.u[1]) <= 3.0e38f) & (fabsf(p.u[2]) <= 3.0e38f);
+  if (!p.all_finite) {
+    p.u[0] = nan_to_num1(p.u[0], p.finite[0]);
+    p.u[1] = nan_to_num1(p.u[1], p.finite[1]);
+    p.u[2] = nan_to_num1(p.u[2], p.finite[2]);
+  }
   p.uvx = k.fx * p.u[0] + k.cx * p.u[2];
   p.uvy = k.fy * p.u[1] + k.cy * p.u[2];
   return p;
 }
 
 // Adjoint of project_point: given d(uv), returns d(X, Y, Z) and accumulates dK.
-FM_HD void project_point_adj(const Proj& p, float X, float Y, float Z, const K4& k, float duvx,
+FM_HD void project_point_adj(const Proj& p, float X, float Y, float Z, const Cam& k, float duvx,
                              float duvy, float& dX, float& dY, float& dZ, float& dfx, float& dfy,
                              float& dcx, float& dcy) {
   dfx += duvx * p.u[0];
   dfy += duvy * p.u[1];
   dcx += duvx * p.u[2];
   dcy += duvy * p.u[2];
-  float du0 = p.finite[0] ? k.fx * duvx : 0.0f;
-  float du1 = p.finite[1] ? k.fy * duvy : 0.0f;
-  float du2 = p.finite[2] ? (k.cx * duvx + k.cy * duvy) : 0.0f;
+  float du0 = k.fx * duvx;
+  float du1 = k.fy * duvy;
+  float du2 = k.cx * duvx + k.cy * duvy;
+  if (!p.all_finite) {
+    if (!p.finite[0]) du0 = 0.0f;
+    if (!p.finite[1]) du1 = 0.0f;
+    if (!p.finite[2]) du2 = 0.0f;
+  }
   dX = du0 * p.inv;
   dY = du1 * p.inv;
-  // d/dZ of (X, Y, Z) / (Z + eps)
-  dZ = du2 * p.inv - (du0 * X + du1 * Y + du2 * Z) * (p.inv * p.inv);
+  // d/dZ of (X, Y, Z) / (Z + eps):  (du2 - du . u) / (Z + eps) on the finite components
+  dZ = (du2 - (du0 * X + du1 * Y + du2 * Z) * p.inv) * p.inv;
 }
 
 // ---------------------------------------------------------------------------------
@@ -150,32 +242,41 @@ FM_HD void project_point_adj(const Proj& p, float X, float Y, float Z, const K4&
 // d(loss)/d(r) for the *uncorrected* residual components (aspect folded in).
 // ax = W / sqrt(HW), ay = H / sqrt(HW).
 // ---------------------------------------------------------------------------------
-FM_HD float robust_map(float rx, float ry, float ax, float ay, int mapping, float delta, float& gx,
-                       float& gy) {
-  float sx = rx * ax, sy = ry * ay;
-  float n2 = sx * sx + sy * sy;
-  if (mapping == MAP_L2) {
-    gx = sx * ax;
-    gy = sy * ay;
+struct RobustCfg {
+  int mapping;
+  float delta, inv_delta, ax, ay;
+};
+FM_HD RobustCfg make_robust(int mapping, float delta, int H, int W) {
+  RobustCfg c;
+  const float sc = sqrtf((float)H * (float)W);
+  c.mapping = mapping;
+  c.delta = delta;
+  c.inv_delta = delta > 0.0f ? 1.0f / delta : 0.0f;
+  c.ax = (float)W / sc;
+  c.ay = (float)H / sc;
+  return c;
+}
+
+FM_HD float robust_map(float rx, float ry, const RobustCfg& c, float& gx, float& gy) {
+  const float sx = rx * c.ax, sy = ry * c.ay;
+  const float n2 = sx * sx + sy * sy;
+  if (c.mapping == MAP_L2) {
+    gx = sx * c.ax;
+    gy = sy * c.ay;
     return 0.5f * n2;
   }
-  float n = sqrtf(n2);
-  float inv_n = n > 0.0f ? 1.0f / n : 0.0f;  // norm has subgradient 0 at the origin
-  if (mapping == MAP_L1) {
-    gx = sx * inv_n * ax;
-    gy = sy * inv_n * ay;
-    return n;
+  // norm has subgradient 0 at the origin; rsqrt(0) = inf is masked out
+  const float inv_n = n2 > 0.0f ? fm_rsqrt(n2) : 0.0f;
+  const float n = n2 * inv_n;
+  float k = inv_n, val = n;                       // l1: n ; d/ds = s / n
+  if (c.mapping == MAP_HUBER) {                   // huber_loss(n, 0, delta) / delta
+    const bool quad = n <= c.delta;
+    k = quad ? c.inv_delta : inv_n;
+    val = quad ? 0.5f * n2 * c.inv_delta : n - 0.5f * c.delta;
   }
-  // huber_loss(n, 0, delta) / delta
-  if (n <= delta) {
-    float id = 1.0f / delta;
-    gx = sx * id * ax;
-    gy = sy * id * ay;
-    return 0.5f * n2 * id;
-  }
-  gx = sx * inv_n * ax;
-  gy = sy * inv_n * ay;
-  return n - 0.5f * delta;
+  gx = sx * k * c.ax;
+  gy = sy * k * c.ay;
+  return val;
 }
 
 }  // namespace fm

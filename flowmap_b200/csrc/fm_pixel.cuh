@@ -10,25 +10,24 @@ namespace fm {
 
 // Geometry of pair (a, b = a + 1).
 struct PairGeom {
-  K4 ka, kb;
-  int H, W;
+  Cam ka, kb;
+  GridDims grid;
   float z0;  // conditioning shift (0, 0, z0) applied to p and q before accumulation
 };
 
 // Later point p (frame b, pixel (r, c)) and earlier point q (frame a sampled at
 // xy + backward flow), both shifted by (0, 0, z0).  projection.py:222-242.
 template <typename LoadA>
-FM_HD void point_pq(const PairGeom& g, int r, int c, float db, float flx, float fly, LoadA load_a,
-                    float* p, float* q, Taps& t) {
-  const float x = pix_x(c, g.W), y = pix_y(r, g.H);
+FM_HD void point_pq(const PairGeom& g, float x, float y, float db, float flx, float fly,
+                    LoadA load_a, float* p, float* q, Taps& t) {
   float rx, ry;
   ray_of(x, y, g.kb, rx, ry);
   p[0] = db * rx;
   p[1] = db * ry;
   p[2] = db - g.z0;
-  t = bilinear_taps(x + flx, y + fly, g.H, g.W);
+  t = bilinear_taps(x + flx, y + fly, g.grid);
   float qx, qy, qz;
-  sample_surface(t, g.W, g.H, g.ka, load_a, qx, qy, qz);
+  sample_surface(t, g.grid, g.ka, load_a, qx, qy, qz);
   q[0] = qx;
   q[1] = qy;
   q[2] = qz - g.z0;
@@ -65,7 +64,7 @@ FM_HD void moments_add(float* acc, float w, const float* p, const float* q) {
 constexpr int kFlowVals = 37;
 
 struct FlowFrame {
-  K4 kk, kn, kp;  // intrinsics of frames k, k+1, k-1
+  Cam kk, kn, kp;  // intrinsics of frames k, k+1, k-1
   Rt tf, tb;      // [R|t] of pair (k, k+1) and of pair (k-1, k)
   bool hasF, hasB;
 };
@@ -74,8 +73,7 @@ struct FlowFrame {
 // backward term (loss_flow.py:59-68 with projection.py:165-184) in the pair-local form of
 // SURVEY A.6.  Returns the direct (pose-detached) depth gradient.
 FM_HD float flow_pixel(const FlowFrame& f, float x, float y, float D, float ffx, float ffy, float mf,
-                       float fbx, float fby, float mb, float g, float ax, float ay, int mapping,
-                       float delta, float* acc) {
+                       float fbx, float fby, float mb, float g, const RobustCfg& rc, float* acc) {
   float rx, ry;
   ray_of(x, y, f.kk, rx, ry);
   const float s0 = D * rx, s1 = D * ry, s2 = D;
@@ -88,7 +86,7 @@ FM_HD float flow_pixel(const FlowFrame& f, float x, float y, float D, float ffx,
     const float Y2 = R[2] * d0 + R[5] * d1 + R[8] * d2;
     const Proj pr = project_point(Y0, Y1, Y2, f.kn);
     float gx, gy;
-    const float l = robust_map((pr.uvx - x) - ffx, (pr.uvy - y) - ffy, ax, ay, mapping, delta, gx, gy);
+    const float l = robust_map((pr.uvx - x) - ffx, (pr.uvy - y) - ffy, rc, gx, gy);
     const float wgt = g * mf;
     acc[0] += wgt * l;
     float dY0, dY1, dY2;
@@ -109,7 +107,7 @@ FM_HD float flow_pixel(const FlowFrame& f, float x, float y, float D, float ffx,
     const float X2 = R[6] * s0 + R[7] * s1 + R[8] * s2 + f.tb.t[2];
     const Proj pr = project_point(X0, X1, X2, f.kp);
     float gx, gy;
-    const float l = robust_map((pr.uvx - x) - fbx, (pr.uvy - y) - fby, ax, ay, mapping, delta, gx, gy);
+    const float l = robust_map((pr.uvx - x) - fbx, (pr.uvy - y) - fby, rc, gx, gy);
     const float wgt = g * mb;
     acc[0] += wgt * l;
     float dX0, dX1, dX2;
@@ -124,10 +122,11 @@ FM_HD float flow_pixel(const FlowFrame& f, float x, float y, float D, float ffx,
     ds2 += R[2] * dX0 + R[5] * dX1 + R[8] * dX2;
   }
   // s = D * (rx, ry, 1), rx = (x - cx) / fx
-  acc[25] -= ds0 * s0 / f.kk.fx;
-  acc[26] -= ds1 * s1 / f.kk.fy;
-  acc[27] -= ds0 * D / f.kk.fx;
-  acc[28] -= ds1 * D / f.kk.fy;
+  const float e0 = ds0 * f.kk.ifx, e1 = ds1 * f.kk.ify;
+  acc[25] -= e0 * s0;
+  acc[26] -= e1 * s1;
+  acc[27] -= e0 * D;
+  acc[28] -= e1 * D;
   return ds0 * rx + ds1 * ry + ds2;
 }
 
@@ -137,41 +136,43 @@ FM_HD float flow_pixel(const FlowFrame& f, float x, float y, float D, float ffx,
 // the weight gradient.  kacc[0..3] += dK_a (through q), kacc[4..7] += dK_b (through p).
 // ---------------------------------------------------------------------------------
 template <typename LoadA, typename Scatter>
-FM_HD void distribute_point(const PairGeom& g, const PairAdjoint& ad, int r, int c, float db, float w,
-                            float flx, float fly, LoadA load_a, Scatter scatter, float& g_db,
-                            float& g_w, float* kacc) {
+FM_HD void distribute_point(const PairGeom& g, const PairAdjoint& ad, float x, float y, float db,
+                            float w, float flx, float fly, LoadA load_a, Scatter scatter,
+                            float& g_db, float& g_w, float* kacc) {
   float p[3], q[3];
   Taps t;
-  point_pq(g, r, c, db, flx, fly, load_a, p, q, t);
+  point_pq(g, x, y, db, flx, fly, load_a, p, q, t);
   const float dp[3] = {p[0] - ad.pbar[0], p[1] - ad.pbar[1], p[2] - ad.pbar[2]};
   const float dq[3] = {q[0] - ad.qbar[0], q[1] - ad.qbar[1], q[2] - ad.qbar[2]};
   float pb[3], qb[3];
   point_adjoint(ad, w, dp, dq, g_w, pb, qb);
   // p = db * (rx, ry, 1)
   float rx, ry;
-  ray_of(pix_x(c, g.W), pix_y(r, g.H), g.kb, rx, ry);
+  ray_of(x, y, g.kb, rx, ry);
   g_db = pb[0] * rx + pb[1] * ry + pb[2];
-  kacc[4] -= pb[0] * p[0] / g.kb.fx;
-  kacc[5] -= pb[1] * p[1] / g.kb.fy;
-  kacc[6] -= pb[0] * db / g.kb.fx;
-  kacc[7] -= pb[1] * db / g.kb.fy;
+  const float eb0 = pb[0] * g.kb.ifx, eb1 = pb[1] * g.kb.ify;
+  kacc[4] -= eb0 * p[0];
+  kacc[5] -= eb1 * p[1];
+  kacc[6] -= eb0 * db;
+  kacc[7] -= eb1 * db;
   // q = sum_n w_n D_n (rx_n, ry_n, 1): scatter into the four taps of the earlier frame
   float rx0, ry0, rx1, ry1;
-  ray_of(pix_x(t.x0, g.W), pix_y(t.y0, g.H), g.ka, rx0, ry0);
-  ray_of(pix_x(t.x1, g.W), pix_y(t.y1, g.H), g.ka, rx1, ry1);
+  tap_rays(t, g.grid, g.ka, rx0, ry0, rx1, ry1);
   const float b00 = qb[0] * rx0 + qb[1] * ry0 + qb[2];
   const float b01 = qb[0] * rx1 + qb[1] * ry0 + qb[2];
   const float b10 = qb[0] * rx0 + qb[1] * ry1 + qb[2];
   const float b11 = qb[0] * rx1 + qb[1] * ry1 + qb[2];
-  if (t.w00 != 0.f) scatter(t.y0 * g.W + t.x0, t.w00 * b00);
-  if (t.w01 != 0.f) scatter(t.y0 * g.W + t.x1, t.w01 * b01);
-  if (t.w10 != 0.f) scatter(t.y1 * g.W + t.x0, t.w10 * b10);
-  if (t.w11 != 0.f) scatter(t.y1 * g.W + t.x1, t.w11 * b11);
+  const int W = g.grid.W;
+  scatter(t.y0 * W + t.x0, t.w00 * b00);
+  scatter(t.y0 * W + t.x1, t.w01 * b01);
+  scatter(t.y1 * W + t.x0, t.w10 * b10);
+  scatter(t.y1 * W + t.x1, t.w11 * b11);
   const float qz_true = q[2] + g.z0;
-  kacc[0] -= qb[0] * q[0] / g.ka.fx;
-  kacc[1] -= qb[1] * q[1] / g.ka.fy;
-  kacc[2] -= qb[0] * qz_true / g.ka.fx;
-  kacc[3] -= qb[1] * qz_true / g.ka.fy;
+  const float ea0 = qb[0] * g.ka.ifx, ea1 = qb[1] * g.ka.ify;
+  kacc[0] -= ea0 * q[0];
+  kacc[1] -= ea1 * q[1];
+  kacc[2] -= ea0 * qz_true;
+  kacc[3] -= ea1 * qz_true;
 }
 
 }  // namespace fm

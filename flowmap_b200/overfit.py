@@ -122,3 +122,37 @@ class Overfitter:
         self.optimizer.step()
         self.global_step += 1
         return total.detach(), out
+
+
+class ShardedOverfitter(Overfitter):
+    """Pair-sharded optimisation (flowmap_b200.parallel): this rank holds the frames and
+    pairs of its ShardPlan; one all-reduce per step carries the loss, the focal-length
+    gradient and the boundary depth-gradient frames."""
+
+    def __init__(self, cfg: OverfitCfg, batch: Batch, flows: Flows, plan, device="cuda",
+                 group=None):
+        from . import parallel
+        if cfg.use_tracking or cfg.intrinsics != "regressed":
+            raise NotImplementedError("pair sharding currently covers the flow loss with a "
+                                      "regressed focal length (BASELINE config 4)")
+        super().__init__(cfg, batch, flows, None, device)
+        self.plan, self.group = plan, group
+        _, _, _, h, w = batch.videos.shape
+        self.reducer = parallel.StepReducer(plan, (h, w), self.flows.forward.device, 2, group)
+        local = ops.mask_sum(self.flows.forward_mask, self.flows.backward_mask)
+        self.losses[0].set_global_mask_sum(parallel.global_mask_sum(local, group))
+
+    def training_step(self):
+        self.optimizer.zero_grad()
+        out = self.model(self.batch, self.flows, self.global_step)
+        total = 0
+        for loss_fn in self.losses:
+            total = total + loss_fn.forward(self.batch, self.flows, None, out, self.global_step)
+        total.backward()
+        focal = self.model.intrinsics.focal_length
+        scalars = torch.stack((total.detach(), focal.grad.reshape(())))
+        red = self.reducer.reduce(scalars, self.model.backbone.depth.grad)
+        focal.grad.copy_(red[1])
+        self.optimizer.step()
+        self.global_step += 1
+        return red[0], out

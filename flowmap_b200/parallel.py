@@ -1,0 +1,128 @@
+"""Multi-GPU execution of the hot path: frame pairs sharded across ranks.
+
+The flow loss is pair-local: pair i needs depth frames i and i+1, its own
+weights/flows/masks and the shared focal length.  Rank g therefore owns a contiguous pair
+range [a_g, b_g) and the frames [a_g, b_g]; flows, masks and weights are sharded and
+never move.  Per optimisation step there is exactly ONE collective, an all-reduce (NCCL
+over NVLink/NVSwitch on the B200 box, gloo in the CPU tests) of a small flat buffer:
+
+    [ loss, d(focal), <world-1 boundary depth-gradient frames> ]
+
+A boundary frame (last frame of rank g == first frame of rank g+1) is "later" for a pair
+on rank g and "earlier" for a pair on rank g+1; each side writes its partial gradient
+into the frame's slot, the all-reduce sums them, and both sides then apply the identical
+Adam update to their replica of that frame, so the replicas stay bit-identical without a
+second message.  The reference has no counterpart (its DDP replicas hold the identical
+problem, flowmap/overfit.py:99-103).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def shard_pairs(num_pairs: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced pair ranges [a, b) per rank (first ranks take the remainder)."""
+    if world < 1 or num_pairs < world:
+        raise ValueError(f"cannot shard {num_pairs} pairs over {world} ranks")
+    base, rem = divmod(num_pairs, world)
+    out, a = [], 0
+    for r in range(world):
+        b = a + base + (1 if r < rem else 0)
+        out.append((a, b))
+        a = b
+    return out
+
+
+@dataclass
+class ShardPlan:
+    rank: int
+    world: int
+    pair_range: Tuple[int, int]  # global [a, b)
+    num_pairs_total: int
+
+    @property
+    def frame_range(self) -> Tuple[int, int]:  # global [a, b] inclusive -> python slice [a, b+1)
+        return self.pair_range[0], self.pair_range[1] + 1
+
+    @property
+    def num_local_frames(self) -> int:
+        return self.pair_range[1] - self.pair_range[0] + 1
+
+    @property
+    def has_left(self) -> bool:
+        return self.rank > 0
+
+    @property
+    def has_right(self) -> bool:
+        return self.rank < self.world - 1
+
+
+def make_plan(num_pairs_total: int, rank: Optional[int] = None,
+              world: Optional[int] = None) -> ShardPlan:
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    return ShardPlan(rank, world, shard_pairs(num_pairs_total, world)[rank], num_pairs_total)
+
+
+def shard_inputs(plan: ShardPlan, depth: Tensor, wparam: Tensor, flows):
+    """Slice a full (unsharded) problem down to this rank's shard.  depth (F,H,W), wparam
+    (F-1,H,W), flows with leading (1, F-1, ...)."""
+    a, b = plan.pair_range
+    sl = slice(a, b)
+    return (depth[a:b + 1].clone(), wparam[sl].clone(),
+            type(flows)(flows.forward[:, sl].clone(), flows.backward[:, sl].clone(),
+                        flows.forward_mask[:, sl].clone(), flows.backward_mask[:, sl].clone()))
+
+
+def global_mask_sum(local_sum: Tensor, group=None) -> Tensor:
+    """The loss normaliser is global (loss_flow.py:70 sums the masks of ALL pairs): all-reduce
+    the local mask sums once; the result is loop-invariant."""
+    total = local_sum.clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return total
+
+
+class StepReducer:
+    """The single per-step collective."""
+
+    def __init__(self, plan: ShardPlan, frame_shape, device, num_scalars: int = 2, group=None):
+        self.plan, self.group = plan, group
+        self.h, self.w = frame_shape
+        self.nscal = num_scalars
+        n_frame = self.h * self.w
+        self.buf = torch.zeros(num_scalars + (plan.world - 1) * n_frame, dtype=torch.float32,
+                               device=device)
+        self.n_frame = n_frame
+
+    def _slot(self, boundary: int) -> Tensor:
+        """View of the slot of boundary `boundary` (between rank boundary and boundary+1)."""
+        o = self.nscal + boundary * self.n_frame
+        return self.buf[o:o + self.n_frame].view(self.h, self.w)
+
+    @torch.no_grad()
+    def reduce(self, scalars: Tensor, depth_grad: Tensor) -> Tensor:
+        """scalars: (num_scalars,) local partials (loss, d focal, ...); depth_grad: this
+        rank's (frames, H, W) gradient, modified in place at the shared boundary frames.
+        Returns the globally summed scalars."""
+        p = self.plan
+        self.buf.zero_()
+        self.buf[:self.nscal] = scalars
+        if p.has_left:
+            self._slot(p.rank - 1).copy_(depth_grad[0])
+        if p.has_right:
+            self._slot(p.rank).copy_(depth_grad[-1])
+        if p.world > 1:
+            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
+        if p.has_left:
+            depth_grad[0].copy_(self._slot(p.rank - 1))
+        if p.has_right:
+            depth_grad[-1].copy_(self._slot(p.rank))
+        return self.buf[:self.nscal].clone()
+
+    def bytes_per_step(self) -> int:
+        return self.buf.numel() * 4

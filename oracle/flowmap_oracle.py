@@ -556,13 +556,12 @@ def synthetic_tracks(f: int, n_points: int = 1225, interval: int = 5, radius: in
 
 def consistent_scene(f: int, h: int, w: int, seed: int = 0, focal: float = 0.85,
                      dtype=torch.float64):
-    """"Parity set": smooth random depth, a small SE(3) motion per frame and the exact
-    flows it induces, so that Procrustes is well conditioned.  Returns
-    (depth (f,h,w), Flows, focal)."""
+    """"Parity set": one static surface (the inside of a sphere) seen by cameras that move by
+    a small SE(3) step per frame; depths are exact ray/sphere intersections and flows the
+    exact induced correspondences, so Procrustes is well conditioned and recovers the
+    motion up to bilinear-interpolation error.  Returns (depth (f,h,w), Flows, focal,
+    extrinsics (1,f,4,4))."""
     g = torch.Generator().manual_seed(seed)
-    lo = torch.rand(f, 1, 4, 5, generator=g, dtype=torch.float64)
-    depth = 1.0 + F.interpolate(lo, size=(h, w), mode="bicubic", align_corners=True)[:, 0]
-    # Small rigid motions.
     rel = torch.eye(4, dtype=torch.float64).repeat(f - 1, 1, 1)
     ang = 0.02 * torch.randn(f - 1, 3, generator=g, dtype=torch.float64)
     for i in range(f - 1):
@@ -570,14 +569,23 @@ def consistent_scene(f: int, h: int, w: int, seed: int = 0, focal: float = 0.85,
         skew = torch.tensor([[0, -az, ay], [az, 0, -ax], [-ay, ax, 0]], dtype=torch.float64)
         rel[i, :3, :3] = torch.linalg.matrix_exp(skew)
     rel[:, :3, 3] = 0.03 * torch.randn(f - 1, 3, generator=g, dtype=torch.float64)
-    ext = pose_chain(rel[None])
-    k = intrinsics_from_focal(torch.tensor(focal, dtype=torch.float64), h, w)
-    k = k.expand(1, f, 3, 3)
+    ext = pose_chain(rel[None])  # camera-to-world
+    k = intrinsics_from_focal(torch.tensor(focal, dtype=torch.float64), h, w).expand(1, f, 3, 3)
     xy = pixel_grid(h, w, torch.float64)
+    rays = unproject(xy, torch.ones(1, f, h, w, dtype=torch.float64), k[:, :, None, None])
+    # ray/sphere: | o + z d - c |^2 = r^2 with o, d the camera centre / ray in world space
+    centre = torch.tensor([0.2, -0.1, 0.5], dtype=torch.float64)
+    radius = 3.0
+    d = matvec(ext[:, :, None, None, :3, :3], rays)
+    o = ext[:, :, None, None, :3, 3] - centre
+    a_ = (d * d).sum(-1)
+    b_ = 2 * (d * o).sum(-1)
+    c_ = (o * o).sum(-1) - radius ** 2
+    depth = ((-b_ + torch.sqrt(b_ * b_ - 4 * a_ * c_)) / (2 * a_))[0]  # far root: inside wall
     surf = unproject(xy, depth[None], k[:, :, None, None])
     fwd = forward_flow_positions(surf, ext, k) - xy
     bwd = backward_flow_positions(surf, ext, k) - xy
     u = lambda *s: 0.5 + 0.5 * torch.rand(*s, generator=g, dtype=torch.float64)  # noqa
     flows = Flows(fwd.to(dtype), bwd.to(dtype), u(1, f - 1, h, w).to(dtype),
                   u(1, f - 1, h, w).to(dtype))
-    return depth.to(dtype), flows, focal
+    return depth.to(dtype), flows, focal, ext

@@ -22,7 +22,7 @@ static PairGeom geom(const float* depth, const float* k4, int pair, int F, int H
   int bi = pair / (F - 1), i = pair - bi * (F - 1);
   a = bi * F + i;
   PairGeom g;
-  g.ka = k4_of(k4, a); g.kb = k4_of(k4, a + 1); g.H = H; g.W = W;
+  g.ka = make_cam(k4_of(k4, a)); g.kb = make_cam(k4_of(k4, a + 1)); g.grid = make_grid(H, W);
   g.z0 = depth[(size_t)(a + 1) * H * W + (size_t)(H / 2) * W + W / 2];
   return g;
 }
@@ -44,7 +44,7 @@ void emu_procrustes_fwd(const float* depth, const float* k4, const float* bflow,
     for (int t = 0; t < cnt; ++t) {
       const int j = indices ? (int)indices[t] : t;
       float acc[kNumMoments] = {0}; float p[3], q[3]; Taps taps;
-      point_pq(g, j / W, j % W, db[j], bflow[((size_t)pair * N + j) * 2], bflow[((size_t)pair * N + j) * 2 + 1],
+      point_pq(g, pix_coord(j % W, g.grid.Wf, g.grid.invW), pix_coord(j / W, g.grid.Hf, g.grid.invH), db[j], bflow[((size_t)pair * N + j) * 2], bflow[((size_t)pair * N + j) * 2 + 1],
                [da](int i) { return da[i]; }, p, q, taps);
       moments_add(acc, weights ? weights[(size_t)pair * N + j] : 1.f, p, q);
       for (int k = 0; k < kNumMoments; ++k) m[k] += acc[k];
@@ -61,12 +61,13 @@ void emu_flow(const float* depth, const float* k4, const float* rt, const float*
   const int N = H * W;
   if (mask_sum == 0.0) mask_sum = 1.0;
   const float g = (float)((double)weight / mask_sum);
-  const float sc = sqrtf((float)H * (float)W), ax = (float)W / sc, ay = (float)H / sc;
+  const RobustCfg rc = make_robust(mapping, delta, H, W);
+  const GridDims grid = make_grid(H, W);
   for (int frame = 0; frame < B * F; ++frame) {
     int bi = frame / F, i = frame - bi * F;
     FlowFrame f;
     f.hasF = i < F - 1; f.hasB = i > 0;
-    f.kk = k4_of(k4, frame); f.kn = k4_of(k4, f.hasF ? frame + 1 : frame); f.kp = k4_of(k4, f.hasB ? frame - 1 : frame);
+    f.kk = make_cam(k4_of(k4, frame)); f.kn = make_cam(k4_of(k4, f.hasF ? frame + 1 : frame)); f.kp = make_cam(k4_of(k4, f.hasB ? frame - 1 : frame));
     int pairF = bi * (F - 1) + i, pairB = pairF - 1;
     auto ld = [&](int pair) { Rt t; for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) t.r[r * 3 + c] = rt[(size_t)pair * 12 + r * 4 + c]; t.t[r] = rt[(size_t)pair * 12 + r * 4 + 3]; } return t; };
     if (f.hasF) f.tf = ld(pairF);
@@ -75,9 +76,9 @@ void emu_flow(const float* depth, const float* k4, const float* rt, const float*
       float acc[kFlowVals] = {0};
       const size_t jf = (size_t)(f.hasF ? pairF : 0) * N + j, jb = (size_t)(f.hasB ? pairB : 0) * N + j;
       g_depth[(size_t)frame * N + j] = flow_pixel(
-          f, pix_x(j % W, W), pix_y(j / W, H), depth[(size_t)frame * N + j], f.hasF ? ff[jf * 2] : 0.f,
+          f, pix_coord(j % W, grid.Wf, grid.invW), pix_coord(j / W, grid.Hf, grid.invH), depth[(size_t)frame * N + j], f.hasF ? ff[jf * 2] : 0.f,
           f.hasF ? ff[jf * 2 + 1] : 0.f, f.hasF ? mf[jf] : 0.f, f.hasB ? fb[jb * 2] : 0.f,
-          f.hasB ? fb[jb * 2 + 1] : 0.f, f.hasB ? mb[jb] : 0.f, g, ax, ay, mapping, delta, acc);
+          f.hasB ? fb[jb * 2 + 1] : 0.f, f.hasB ? mb[jb] : 0.f, g, rc, acc);
       for (int k = 0; k < kFlowVals; ++k) flowacc[(size_t)frame * 40 + k] += acc[k];
     }
   }
@@ -100,7 +101,7 @@ void emu_procrustes_bwd(const float* depth, const float* k4, const float* bflow,
     for (int t = 0; t < cnt; ++t) {
       const int j = indices ? (int)indices[t] : t;
       float kacc[8] = {0}; float gdj, gwj;
-      distribute_point(g, ad, j / W, j % W, db[j], weights ? weights[(size_t)pair * N + j] : 1.f,
+      distribute_point(g, ad, pix_coord(j % W, g.grid.Wf, g.grid.invW), pix_coord(j / W, g.grid.Hf, g.grid.invH), db[j], weights ? weights[(size_t)pair * N + j] : 1.f,
                        bflow[((size_t)pair * N + j) * 2], bflow[((size_t)pair * N + j) * 2 + 1],
                        [da](int i) { return da[i]; }, [gda](int i, float v) { gda[i] += v; }, gdj, gwj, kacc);
       gdb[j] += gdj;
