@@ -34,6 +34,12 @@ SIGNATURES = {
                                      _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "fm_pose_chain": (c_int, [_P, _P, c_int, c_int, _P]),
     "fm_pose_chain_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
+    "fm_track_workspace_bytes": (c_size_t, [c_int, ctypes.c_longlong]),
+    "fm_track_loss_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, ctypes.c_longlong,
+                                  c_int, c_float, c_float, _P, _P, c_int, c_int, c_int, _P]),
+    "fm_track_loss_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, ctypes.c_longlong,
+                                  c_int, c_float, c_float, _P, _P, _P, _P, _P, c_int, c_int, c_int,
+                                  _P]),
     "fm_adam_step": (c_int, [_P, _P, _P, _P, c_size_t, c_double, c_double, c_double, c_double,
                              c_int, _P]),
 }

@@ -681,6 +681,229 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
 #undef FM_ADAM1
 }
 
+// ================================================================== tracking loss
+// projection.py:255-298 (compute_track_flow) + loss_tracking.py:28-61, all segments in one
+// launch.  Samples are packed per segment: sample(s, row, p) = seg.sample_start + row * n + p.
+// seg table (int32 x 4 per segment): sample_start, rows f_s, points n_s, start_frame.
+//   k_track_fwd      block = (segment, source row, point chunk): bilinear-sample xyz at the track
+//                    location, lift to world space (stored), loop over the segment's target rows:
+//                    loss sum + valid count.
+//   k_track_bwd_src  same mapping: gradient w.r.t. the source sample -> depth (bilinear scatter),
+//                    K of the source frame (unprojection), pose of the source frame (twist).
+//   k_track_bwd_tgt  block = (segment, target row, point chunk), loop over source rows: gradient
+//                    w.r.t. the target frame's pose (twist) and K (projection).
+// Pose gradients are accumulated as left-perturbation twists (a = d/d omega, b = d/d v with
+// delta R = [omega]x R, delta t = v) and expanded to an ambient 3x4 gradient in k_track_finalize;
+// only the tangent part survives the rigid chain / Procrustes adjoint.
+constexpr int kTrackAcc = 10;  // per frame: dK (4), a (3), b (3)
+
+struct SegInfo { int sample_start, rows, n, start_frame; };
+
+__device__ __forceinline__ SegInfo load_seg(const int* seg, int s) {
+  const int4 v = __ldg(reinterpret_cast<const int4*>(seg) + s);
+  SegInfo i; i.sample_start = v.x; i.rows = v.y; i.n = v.z; i.start_frame = v.w;
+  return i;
+}
+
+// Segment poses / cameras in shared memory: [row][18] = R(9) t(3) fx fy cx cy ifx ify
+__device__ __forceinline__ void load_segment_frames(float* sm, const float* ext, const float* k4,
+                                                    const SegInfo& si) {
+  for (int i = threadIdx.x; i < si.rows * 18; i += blockDim.x) {
+    const int row = i / 18, e = i - row * 18;
+    const int frame = si.start_frame + row;
+    float v;
+    if (e < 9) v = __ldg(ext + (size_t)frame * 16 + (e / 3) * 4 + (e % 3));
+    else if (e < 12) v = __ldg(ext + (size_t)frame * 16 + (e - 9) * 4 + 3);
+    else if (e < 16) v = __ldg(k4 + (size_t)frame * 4 + (e - 12));
+    else v = 1.0f / __ldg(k4 + (size_t)frame * 4 + (e - 16));
+    sm[i] = v;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ Pose sm_pose(const float* sm, int row) {
+  Pose p;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) p.r[i] = sm[row * 18 + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) p.t[i] = sm[row * 18 + 9 + i];
+  return p;
+}
+__device__ __forceinline__ Cam sm_cam(const float* sm, int row) {
+  Cam c;
+  c.fx = sm[row * 18 + 12]; c.fy = sm[row * 18 + 13]; c.cx = sm[row * 18 + 14];
+  c.cy = sm[row * 18 + 15]; c.ifx = sm[row * 18 + 16]; c.ify = sm[row * 18 + 17];
+  return c;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads)
+k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const float* __restrict__ ext,
+            const int* __restrict__ seg, const float* __restrict__ txy,
+            const unsigned char* __restrict__ tvis, int mapping, float delta, float loss_weight,
+            const float* __restrict__ go, double* __restrict__ sums, float* __restrict__ xw,
+            unsigned char* __restrict__ flag, float* __restrict__ g_depth, double* __restrict__ trackacc,
+            int H, int W) {
+  extern __shared__ float sm[];
+  __shared__ double red[kTrackAcc * (kThreads / 32)];
+  const SegInfo si = load_seg(seg, blockIdx.z);
+  const int row = blockIdx.y;
+  if (row >= si.rows) return;
+  load_segment_frames(sm, ext, k4, si);
+  const int p = blockIdx.x * kThreads + threadIdx.x;
+  const bool active = p < si.n;
+  const GridDims grid = make_grid(H, W);
+  const RobustCfg rc = make_robust(mapping, delta, H, W);
+  const int frame = si.start_frame + row;
+  const float* D = depth + (size_t)frame * H * W;
+  const Pose ps = sm_pose(sm, row);
+  const Cam ks = sm_cam(sm, row);
+  float acc[kTrackAcc];
+#pragma unroll
+  for (int i = 0; i < kTrackAcc; ++i) acc[i] = 0.f;
+  float scale = 0.f;
+  if (BWD) {
+    double cnt = sums[1];
+    if (cnt == 0.0) cnt = 1.0;  // loss_tracking.py:61 "valid_sum or 1"
+    scale = (float)((double)loss_weight * (go ? (double)*go : 1.0) / cnt);
+  }
+  if (active) {
+    const size_t sidx = (size_t)si.sample_start + (size_t)row * si.n + p;
+    const float2 sxy = __ldg(reinterpret_cast<const float2*>(txy) + sidx);
+    const bool src_ok = tvis[sidx] && in_unit_square(sxy.x, sxy.y);
+    const Taps t = bilinear_taps(sxy.x, sxy.y, grid);
+    float q[3];
+    sample_surface(t, grid, ks, [D](int i) { return __ldg(D + i); }, q[0], q[1], q[2]);
+    float Xw[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      Xw[i] = ps.r[i * 3 + 0] * q[0] + ps.r[i * 3 + 1] * q[1] + ps.r[i * 3 + 2] * q[2] + ps.t[i];
+    if (!BWD) {
+      xw[sidx * 3 + 0] = Xw[0]; xw[sidx * 3 + 1] = Xw[1]; xw[sidx * 3 + 2] = Xw[2];
+      flag[sidx] = src_ok ? 1 : 0;
+    }
+    if (src_ok) {
+      float G[3] = {0.f, 0.f, 0.f};
+      for (int ft = 0; ft < si.rows; ++ft) {
+        const size_t tidx = (size_t)si.sample_start + (size_t)ft * si.n + p;
+        if (!tvis[tidx]) continue;
+        const float2 gxy = __ldg(reinterpret_cast<const float2*>(txy) + tidx);
+        const Pose pt = sm_pose(sm, ft);
+        const Cam kt = sm_cam(sm, ft);
+        float l, d[3], Y[3], gux, guy;
+        Proj pr;
+        const bool valid = track_term(pt, kt, Xw, gxy.x, gxy.y, true, rc, l, d, Y, pr, gux, guy);
+        if (!valid) continue;
+        if (!BWD) {
+          acc[0] += l;
+          acc[1] += 1.f;
+        } else {
+          float dY0, dY1, dY2, u0 = 0, u1 = 0, u2 = 0, u3 = 0;
+          project_point_adj(pr, Y[0], Y[1], Y[2], kt, scale * gux, scale * guy, dY0, dY1, dY2, u0, u1, u2, u3);
+          G[0] += pt.r[0] * dY0 + pt.r[1] * dY1 + pt.r[2] * dY2;
+          G[1] += pt.r[3] * dY0 + pt.r[4] * dY1 + pt.r[5] * dY2;
+          G[2] += pt.r[6] * dY0 + pt.r[7] * dY1 + pt.r[8] * dY2;
+        }
+      }
+      if (BWD) {
+        // camera-space adjoint of the sampled point, scatter to the four depth taps
+        const float dq0 = ps.r[0] * G[0] + ps.r[3] * G[1] + ps.r[6] * G[2];
+        const float dq1 = ps.r[1] * G[0] + ps.r[4] * G[1] + ps.r[7] * G[2];
+        const float dq2 = ps.r[2] * G[0] + ps.r[5] * G[1] + ps.r[8] * G[2];
+        float rx0, ry0, rx1, ry1;
+        tap_rays(t, grid, ks, rx0, ry0, rx1, ry1);
+        float* gd = g_depth + (size_t)frame * H * W;
+        red_add(gd + t.y0 * W + t.x0, t.w00 * (dq0 * rx0 + dq1 * ry0 + dq2));
+        red_add(gd + t.y0 * W + t.x1, t.w01 * (dq0 * rx1 + dq1 * ry0 + dq2));
+        red_add(gd + t.y1 * W + t.x0, t.w10 * (dq0 * rx0 + dq1 * ry1 + dq2));
+        red_add(gd + t.y1 * W + t.x1, t.w11 * (dq0 * rx1 + dq1 * ry1 + dq2));
+        const float e0 = dq0 * ks.ifx, e1 = dq1 * ks.ify;
+        acc[0] -= e0 * q[0]; acc[1] -= e1 * q[1]; acc[2] -= e0 * q[2]; acc[3] -= e1 * q[2];
+        const float c0 = Xw[0] - ps.t[0], c1 = Xw[1] - ps.t[1], c2 = Xw[2] - ps.t[2];
+        acc[4] += c1 * G[2] - c2 * G[1];
+        acc[5] += c2 * G[0] - c0 * G[2];
+        acc[6] += c0 * G[1] - c1 * G[0];
+        acc[7] += G[0]; acc[8] += G[1]; acc[9] += G[2];
+      }
+    }
+  }
+  if (!BWD) block_accumulate<2>(acc, sums, red);
+  else block_accumulate<kTrackAcc>(acc, trackacc + (size_t)frame * kTrackAcc, red);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_track_bwd_tgt(const float* __restrict__ k4, const float* __restrict__ ext, const int* __restrict__ seg,
+                const float* __restrict__ txy, const unsigned char* __restrict__ tvis, int mapping,
+                float delta, float loss_weight, const float* __restrict__ go,
+                const double* __restrict__ sums, const float* __restrict__ xw,
+                const unsigned char* __restrict__ flag, double* __restrict__ trackacc, int H, int W) {
+  extern __shared__ float sm[];
+  __shared__ double red[kTrackAcc * (kThreads / 32)];
+  const SegInfo si = load_seg(seg, blockIdx.z);
+  const int ft = blockIdx.y;
+  if (ft >= si.rows) return;
+  load_segment_frames(sm, ext, k4, si);
+  const int p = blockIdx.x * kThreads + threadIdx.x;
+  const RobustCfg rc = make_robust(mapping, delta, H, W);
+  const Pose pt = sm_pose(sm, ft);
+  const Cam kt = sm_cam(sm, ft);
+  double cnt = sums[1];
+  if (cnt == 0.0) cnt = 1.0;
+  const float scale = (float)((double)loss_weight * (go ? (double)*go : 1.0) / cnt);
+  float acc[kTrackAcc];
+#pragma unroll
+  for (int i = 0; i < kTrackAcc; ++i) acc[i] = 0.f;
+  if (p < si.n) {
+    const size_t tidx = (size_t)si.sample_start + (size_t)ft * si.n + p;
+    if (tvis[tidx]) {
+      const float2 gxy = __ldg(reinterpret_cast<const float2*>(txy) + tidx);
+      for (int fs = 0; fs < si.rows; ++fs) {
+        const size_t sidx = (size_t)si.sample_start + (size_t)fs * si.n + p;
+        if (!flag[sidx]) continue;
+        const float Xw[3] = {xw[sidx * 3 + 0], xw[sidx * 3 + 1], xw[sidx * 3 + 2]};
+        float l, d[3], Y[3], gux, guy;
+        Proj pr;
+        if (!track_term(pt, kt, Xw, gxy.x, gxy.y, true, rc, l, d, Y, pr, gux, guy)) continue;
+        float dY0, dY1, dY2;
+        project_point_adj(pr, Y[0], Y[1], Y[2], kt, scale * gux, scale * guy, dY0, dY1, dY2, acc[0],
+                          acc[1], acc[2], acc[3]);
+        const float g0 = pt.r[0] * dY0 + pt.r[1] * dY1 + pt.r[2] * dY2;
+        const float g1 = pt.r[3] * dY0 + pt.r[4] * dY1 + pt.r[5] * dY2;
+        const float g2 = pt.r[6] * dY0 + pt.r[7] * dY1 + pt.r[8] * dY2;
+        acc[4] -= d[1] * g2 - d[2] * g1;
+        acc[5] -= d[2] * g0 - d[0] * g2;
+        acc[6] -= d[0] * g1 - d[1] * g0;
+        acc[7] -= g0; acc[8] -= g1; acc[9] -= g2;
+      }
+    }
+  }
+  block_accumulate<kTrackAcc>(acc, trackacc + (size_t)(si.start_frame + ft) * kTrackAcc, red);
+}
+
+__global__ void k_track_loss(const double* __restrict__ sums, float loss_weight, float* __restrict__ loss) {
+  double cnt = sums[1];
+  if (cnt == 0.0) cnt = 1.0;
+  *loss = (float)((double)loss_weight * sums[0] / cnt);
+}
+
+__global__ void k_track_finalize(const double* __restrict__ trackacc, const float* __restrict__ ext,
+                                 float* __restrict__ g_ext, float* __restrict__ g_k4, int F) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const double* a = trackacc + (size_t)f * kTrackAcc;
+  for (int k = 0; k < 4; ++k) g_k4[(size_t)f * 4 + k] = (float)a[k];
+  const float* P = ext + (size_t)f * 16;
+  const double w0 = 0.5 * a[4], w1 = 0.5 * a[5], w2 = 0.5 * a[6];
+  float* o = g_ext + (size_t)f * 16;
+  for (int c = 0; c < 3; ++c) {  // G_R = 1/2 [a]x R
+    const double r0 = P[0 * 4 + c], r1 = P[1 * 4 + c], r2 = P[2 * 4 + c];
+    o[0 * 4 + c] = (float)(-w2 * r1 + w1 * r2);
+    o[1 * 4 + c] = (float)(w2 * r0 - w0 * r2);
+    o[2 * 4 + c] = (float)(-w1 * r0 + w0 * r1);
+  }
+  o[3] = (float)a[7]; o[7] = (float)a[8]; o[11] = (float)a[9];
+  o[12] = o[13] = o[14] = o[15] = 0.f;
+}
+
 // ---------------------------------------------------------------- launch geometry
 int blocks_for(int n_items_per_row, int vec) {
   // ~4096 items per block keeps thousands of blocks in flight at the BASELINE sizes and
@@ -883,6 +1106,78 @@ int fm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
   if (nb > 148 * 16) nb = 148 * 16;
   k_adam<<<(unsigned)nb, kThreads, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, count, beta1, beta2, (float)(1.0 - (double)beta1_d), (float)(1.0 - (double)beta2_d), eps, step_size, bc2_sqrt);
   FM_CHECK_LAUNCH("fm_adam_step");
+  return 0;
+}
+
+size_t fm_track_workspace_bytes(int F, long long total_samples) {
+  if (F < 1 || total_samples < 0) return 0;
+  size_t off = 0;
+  off = align_up(off + 4 * sizeof(double), 256);                          // sums
+  off = align_up(off + (size_t)F * kTrackAcc * sizeof(double), 256);      // per-frame accumulators
+  off = align_up(off + (size_t)total_samples * 3 * sizeof(float), 256);   // world points
+  off = align_up(off + (size_t)total_samples, 256);                       // source-valid flags
+  return off;
+}
+
+namespace {
+struct TrackWs { double* sums; double* acc; float* xw; unsigned char* flag; };
+TrackWs carve_track(void* base, int F, long long total) {
+  char* p = (char*)base; size_t off = 0; TrackWs w;
+  w.sums = (double*)(p + off); off = align_up(off + 4 * sizeof(double), 256);
+  w.acc = (double*)(p + off); off = align_up(off + (size_t)F * kTrackAcc * sizeof(double), 256);
+  w.xw = (float*)(p + off); off = align_up(off + (size_t)total * 3 * sizeof(float), 256);
+  w.flag = (unsigned char*)(p + off);
+  return w;
+}
+}  // namespace
+
+int fm_track_loss_fwd(const float* depth, const float* k4, const float* extrinsics, const int* segments,
+                      int num_segments, int max_rows, int max_points, const float* track_xy,
+                      const unsigned char* track_vis, long long total_samples, int mapping, float delta,
+                      float loss_weight, float* loss, void* ws, int F, int H, int W, void* stream) {
+  if (!depth || !k4 || !extrinsics || !segments || !track_xy || !track_vis || !loss || !ws ||
+      num_segments < 1 || max_rows < 1 || max_points < 1 || F < 1)
+    return fail_msg("fm_track_loss_fwd: bad arguments");
+  if (mapping < 0 || mapping > 2) return fail_msg("fm_track_loss_fwd: unknown mapping");
+  cudaStream_t s = (cudaStream_t)stream;
+  TrackWs w = carve_track(ws, F, total_samples);
+  cudaError_t e = cudaMemsetAsync(w.sums, 0, 4 * sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_track_loss_fwd: memset", e);
+  dim3 grid((max_points + kThreads - 1) / kThreads, max_rows, num_segments);
+  const size_t smem = (size_t)max_rows * 18 * sizeof(float);
+  k_track_src<false><<<grid, kThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis,
+                                                 mapping, delta, loss_weight, nullptr, w.sums, w.xw,
+                                                 w.flag, nullptr, nullptr, H, W);
+  FM_CHECK_LAUNCH("fm_track_loss_fwd: k_track_src");
+  k_track_loss<<<1, 1, 0, s>>>(w.sums, loss_weight, loss);
+  FM_CHECK_LAUNCH("fm_track_loss_fwd: k_track_loss");
+  return 0;
+}
+
+int fm_track_loss_bwd(const float* depth, const float* k4, const float* extrinsics, const int* segments,
+                      int num_segments, int max_rows, int max_points, const float* track_xy,
+                      const unsigned char* track_vis, long long total_samples, int mapping, float delta,
+                      float loss_weight, const float* grad_out, float* g_depth, float* g_extrinsics,
+                      float* g_k4, void* ws, int F, int H, int W, void* stream) {
+  if (!depth || !k4 || !extrinsics || !segments || !track_xy || !track_vis || !g_depth ||
+      !g_extrinsics || !g_k4 || !ws || num_segments < 1 || max_rows < 1 || max_points < 1 || F < 1)
+    return fail_msg("fm_track_loss_bwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  TrackWs w = carve_track(ws, F, total_samples);
+  cudaError_t e = cudaMemsetAsync(w.acc, 0, (size_t)F * kTrackAcc * sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_track_loss_bwd: memset", e);
+  dim3 grid((max_points + kThreads - 1) / kThreads, max_rows, num_segments);
+  const size_t smem = (size_t)max_rows * 18 * sizeof(float);
+  k_track_src<true><<<grid, kThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis,
+                                                mapping, delta, loss_weight, grad_out, w.sums, w.xw,
+                                                w.flag, g_depth, w.acc, H, W);
+  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_src");
+  k_track_bwd_tgt<<<grid, kThreads, smem, s>>>(k4, extrinsics, segments, track_xy, track_vis, mapping,
+                                               delta, loss_weight, grad_out, w.sums, w.xw, w.flag, w.acc,
+                                               H, W);
+  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_bwd_tgt");
+  k_track_finalize<<<(F + 63) / 64, 64, 0, s>>>(w.acc, extrinsics, g_extrinsics, g_k4, F);
+  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_finalize");
   return 0;
 }
 

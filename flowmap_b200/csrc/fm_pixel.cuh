@@ -176,3 +176,36 @@ FM_HD void distribute_point(const PairGeom& g, const PairAdjoint& ad, float x, f
 }
 
 }  // namespace fm
+
+// ---------------------------------------------------------------------------------
+// Track reprojection (projection.py:255-298 + loss_tracking.py:28-61): one source sample
+// (world point Xw) seen from target frame ft.  Returns validity and the robust loss; on
+// request the adjoint pieces.
+// ---------------------------------------------------------------------------------
+namespace fm {
+
+struct Pose {  // camera-to-world [R | t]
+  float r[9];
+  float t[3];
+};
+
+FM_HD bool in_unit_square(float x, float y) { return x >= 0.f && x < 1.f && y >= 0.f && y < 1.f; }
+
+// Y = R_ft^T (Xw - t_ft); uv = project(K_ft, Y).  valid = base_valid & uv in [0,1)^2
+// (projection.py:294-296: the *predicted* target position decides).
+FM_HD bool track_term(const Pose& pt, const Cam& kt, const float* Xw, float gx_, float gy_,
+                      bool base_valid, const RobustCfg& rc, float& loss, float* dvec, float* Yout,
+                      Proj& pr, float& gux, float& guy) {
+  const float d0 = Xw[0] - pt.t[0], d1 = Xw[1] - pt.t[1], d2 = Xw[2] - pt.t[2];
+  const float Y0 = pt.r[0] * d0 + pt.r[3] * d1 + pt.r[6] * d2;
+  const float Y1 = pt.r[1] * d0 + pt.r[4] * d1 + pt.r[7] * d2;
+  const float Y2 = pt.r[2] * d0 + pt.r[5] * d1 + pt.r[8] * d2;
+  pr = project_point(Y0, Y1, Y2, kt);
+  const bool valid = base_valid && in_unit_square(pr.uvx, pr.uvy);
+  loss = robust_map(pr.uvx - gx_, pr.uvy - gy_, rc, gux, guy);
+  dvec[0] = d0; dvec[1] = d1; dvec[2] = d2;
+  Yout[0] = Y0; Yout[1] = Y1; Yout[2] = Y2;
+  return valid;
+}
+
+}  // namespace fm

@@ -112,7 +112,34 @@ class LossFlow(Loss):
                              m.name, getattr(m, "delta", 0.0), self.cfg.weight)
 
 
-LOSSES = {"flow": LossFlow}
+class LossTracking(Loss):
+    """loss_tracking.py:23-61: all-pairs track reprojection loss over every segment."""
+
+    def __init__(self, cfg: LossTrackingCfg):
+        super().__init__(cfg)
+        self._packed = None
+        self._packed_key = None
+
+    def _pack(self, tracks, device):
+        key = tuple(id(t) for t in tracks)
+        if key != self._packed_key or self._packed is None:
+            self._packed = ops.PackedTracks(tracks, device)  # tracks are constant across steps
+            self._packed_key = key
+            self._keepalive = list(tracks)
+        return self._packed
+
+    def compute_weighted_loss(self, batch, flows, tracks, model_output, global_step):
+        assert tracks is not None  # loss_tracking.py:37
+        out = model_output
+        k4 = getattr(out, "k4", None)
+        if k4 is None:
+            k4 = ops.intrinsics_to_k4(out.intrinsics)
+        m = self.cfg.mapping
+        return ops.track_loss(out.depths, out.extrinsics, k4, self._pack(tracks, out.depths.device),
+                              m.name, getattr(m, "delta", 0.0), self.cfg.weight)
+
+
+LOSSES = {"flow": LossFlow, "tracking": LossTracking}
 
 
 def get_losses(cfgs):

@@ -230,3 +230,78 @@ def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, 
         check(lib().fm_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq),
                                  param.numel(), lr, betas[0], betas[1], eps, step, _stream()),
               "fm_adam_step")
+
+
+class PackedTracks:
+    """All segments of a list[Tracks] in the flat layout fm_track_loss_* expects."""
+
+    def __init__(self, tracks, device):
+        segs, xy, vis, off = [], [], [], 0
+        for t in tracks:
+            b, f, n, _ = t.xy.shape
+            if b != 1:
+                raise ValueError("flowmap_b200: tracking supports batch size 1 "
+                                 "(flowmap/tracking/__init__.py:92-93)")
+            segs.append((off, f, n, int(t.start_frame)))
+            xy.append(t.xy[0].reshape(-1, 2))
+            vis.append(t.visibility[0].reshape(-1))
+            off += f * n
+        self.total = off
+        self.num_segments = len(segs)
+        self.max_rows = max(s[1] for s in segs)
+        self.max_points = max(s[2] for s in segs)
+        self.last_frame = max(s[3] + s[1] for s in segs)
+        self.seg = torch.tensor(segs, dtype=torch.int32).to(device).contiguous()
+        self.xy = torch.cat(xy).to(device=device, dtype=torch.float32).contiguous()
+        self.vis = torch.cat(vis).to(device=device, dtype=torch.uint8).contiguous()
+
+
+class _TrackLoss(torch.autograd.Function):
+    """Weighted track reprojection loss over all segments.
+
+    flowmap/loss/loss_tracking.py:28-61 + flowmap/model/projection.py:255-298."""
+
+    @staticmethod
+    def forward(ctx, depths, extrinsics, k4, packed, mapping, delta, weight):
+        depths, extrinsics, k4 = _canon(depths, "depths"), _canon(extrinsics, "extrinsics"), _canon(k4, "k4")
+        B, F, H, W = depths.shape
+        if B != 1 or extrinsics.shape != (1, F, 4, 4) or k4.shape != (1, F, 4):
+            raise ValueError("flowmap_b200: tracking loss needs batch size 1 and matching shapes")
+        if packed.last_frame > F:
+            raise ValueError("flowmap_b200: a track segment runs past the last frame")
+        dev = depths.device
+        n = lib().fm_track_workspace_bytes(F, packed.total)
+        ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().fm_track_loss_fwd(_ptr(depths), _ptr(k4), _ptr(extrinsics), _ptr(packed.seg),
+                                          packed.num_segments, packed.max_rows, packed.max_points,
+                                          _ptr(packed.xy), _ptr(packed.vis), packed.total,
+                                          MAPPINGS[mapping], float(delta), float(weight), _ptr(loss),
+                                          _ptr(ws), F, H, W, _stream()), "fm_track_loss_fwd")
+        ctx.save_for_backward(depths, extrinsics, k4, ws)
+        ctx.packed, ctx.cfg = packed, (mapping, delta, weight)
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        depths, extrinsics, k4, ws = ctx.saved_tensors
+        packed, (mapping, delta, weight) = ctx.packed, ctx.cfg
+        _, F, H, W = depths.shape
+        go = _canon(go, "grad_output").reshape(())
+        g_depth = torch.zeros_like(depths)
+        g_ext = torch.empty_like(extrinsics)
+        g_k4 = torch.empty_like(k4)
+        with torch.cuda.device(depths.device):
+            check(lib().fm_track_loss_bwd(_ptr(depths), _ptr(k4), _ptr(extrinsics), _ptr(packed.seg),
+                                          packed.num_segments, packed.max_rows, packed.max_points,
+                                          _ptr(packed.xy), _ptr(packed.vis), packed.total,
+                                          MAPPINGS[mapping], float(delta), float(weight), _ptr(go),
+                                          _ptr(g_depth), _ptr(g_ext), _ptr(g_k4), _ptr(ws), F, H, W,
+                                          _stream()), "fm_track_loss_bwd")
+        return g_depth, g_ext, g_k4, None, None, None, None
+
+
+def track_loss(depths, extrinsics, k4, packed: PackedTracks, mapping="huber", delta=0.01,
+               weight=1.0) -> Tensor:
+    return _TrackLoss.apply(depths, extrinsics, k4, packed, mapping, delta, weight)

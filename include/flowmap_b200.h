@@ -105,6 +105,29 @@ int fm_pose_chain(const float* rt, float* extrinsics, int B, int F, void* stream
 int fm_pose_chain_bwd(const float* rt, const float* extrinsics, const float* g_extrinsics,
                       float* g_rt, int B, int F, void* stream);
 
+/* loss_tracking.py:28-61 LossTracking + projection.py:255-298 compute_track_flow, all
+ * segments in one launch (batch size 1, as tracking/__init__.py:92-93 asserts).
+ * Packing: samples of segment s are stored row-major (frame row, point) starting at
+ * segments[s][0]; segments (device int32, num_segments x 4) = (sample_start, rows f_s,
+ * points n_s, start_frame); track_xy (total_samples, 2) float; track_vis (total_samples)
+ * uint8.  extrinsics: camera-to-world (F, 4, 4).  All (source row, target row) pairs of a
+ * segment are evaluated, including source == target; a term is valid when both ends are
+ * visible, the source lies in [0,1)^2 and the PREDICTED target lies in [0,1)^2.
+ * fwd writes loss = weight * sum / (count or 1) and keeps sum / count and the lifted world
+ * points in ws (fm_track_workspace_bytes); bwd accumulates into g_depth (F,H,W; caller
+ * zero-fills) and writes g_extrinsics (F,4,4) and g_k4 (F,4).  grad_out: device float
+ * scalar dL/dloss or NULL (= 1). */
+size_t fm_track_workspace_bytes(int F, long long total_samples);
+int fm_track_loss_fwd(const float* depth, const float* k4, const float* extrinsics, const int* segments,
+                      int num_segments, int max_rows, int max_points, const float* track_xy,
+                      const unsigned char* track_vis, long long total_samples, int mapping, float delta,
+                      float loss_weight, float* loss, void* ws, int F, int H, int W, void* stream);
+int fm_track_loss_bwd(const float* depth, const float* k4, const float* extrinsics, const int* segments,
+                      int num_segments, int max_rows, int max_points, const float* track_xy,
+                      const unsigned char* track_vis, long long total_samples, int mapping, float delta,
+                      float loss_weight, const float* grad_out, float* g_depth, float* g_extrinsics,
+                      float* g_k4, void* ws, int F, int H, int W, void* stream);
+
 /* model_wrapper_overfit.py:104-105 optim.Adam(lr): torch's single-tensor Adam update (no
  * amsgrad, no weight decay), one fused pass; `step` is the 1-based step number. */
 int fm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count,

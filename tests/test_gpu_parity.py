@@ -187,3 +187,53 @@ def test_unproject_and_pose_chain_against_golden():
                        torch.eye(4)[:3].expand(4, 3, 4).contiguous().cuda(),
                        ops.intrinsics_to_k4(T(g["proj_k"]))[None].expand(4, 4).contiguous().cuda())
     assert np.allclose(xy.cpu().numpy(), g["proj_xy"], rtol=1e-5, atol=2e-6)
+
+
+def test_tracking_loss_matches_reference_golden():
+    """loss_tracking.py / compute_track_flow incl. out-of-frame tracks, overlapping segments,
+    the dynamic target-in-frame mask and source == target pairs."""
+    from flowmap_b200.types import Tracks
+    g64, g32 = load_golden("tracking", True), load_golden("tracking", False)
+    o = _setup(g64, cfg_kw=dict(use_tracking=True, tracking_enable_after=0))
+    tracks = [Tracks(T(g64[f"trk{i}_xy"]).float(), T(g64[f"trk{i}_vis"]), int(g64[f"trk{i}_start"]))
+              for i in range(2)]
+    o.tracks = [t.to("cuda") for t in tracks]
+    out = o.model(o.batch, o.flows, 0)
+    lf = o.losses[0].forward(o.batch, o.flows, o.tracks, out, 0)
+    lt = o.losses[1].forward(o.batch, o.flows, o.tracks, out, 0)
+    (lf + lt).backward()
+    assert abs(float(lf) - float(g64["loss_flow"])) <= 1e-4 * abs(float(g64["loss_flow"]))
+    assert abs(float(lt) - float(g64["loss_tracking"])) <= 1e-4 * abs(float(g64["loss_tracking"]))
+    gd, gw = o.model.backbone.depth.grad.cpu(), o.model.backbone.weights.grad.cpu()
+    gf = float(o.model.intrinsics.focal_length.grad)
+    assert rel_l2(gd, g64["g_depth"]) <= max(1e-4, 3 * rel_l2(g32["g_depth"], g64["g_depth"]))
+    assert rel_l2(gw, g64["g_wparam"]) <= max(1e-4, 3 * rel_l2(g32["g_wparam"], g64["g_wparam"]))
+    assert abs(gf - float(g64["g_focal"])) <= 1e-4 * abs(float(g64["g_focal"]))
+
+
+def test_tracking_only_gradients_vs_oracle():
+    """Tracking loss alone (flow loss off) so that its pose/depth/focal gradients are not
+    masked by the larger flow-loss gradients."""
+    from oracle import flowmap_oracle as O
+    from flowmap_b200.types import Tracks
+    g64 = load_golden("tracking", True)
+    f, h, w = g64["in_depth"].shape
+    st = O.OverfitOracle(O.OverfitConfig(intrinsics="regressed", use_tracking=True,
+                                         tracking_enable_after=0, flow_enable_after=10**9),
+                         f, h, w, dtype=torch.float64)
+    with torch.no_grad():
+        st.depth.copy_(T(g64["in_depth"]))
+        st.weights.copy_(T(g64["in_wparam"]))
+    flows64 = O.Flows(*(T(g64[k]) for k in ("in_fwd", "in_bwd", "in_fmask", "in_bmask")))
+    tr64 = [O.Tracks(T(g64[f"trk{i}_xy"]), T(g64[f"trk{i}_vis"]), int(g64[f"trk{i}_start"])) for i in range(2)]
+    ref = st.training_step(flows64, tr64)
+    o = _setup(g64, cfg_kw=dict(use_tracking=True, tracking_enable_after=0, flow_enable_after=10**9))
+    o.tracks = [Tracks(t.xy.float().cuda(), t.visibility.cuda(), t.start_frame) for t in tr64]
+    out = o.model(o.batch, o.flows, 0)
+    lt = o.losses[1].forward(o.batch, o.flows, o.tracks, out, 0)
+    lt.backward()
+    assert abs(float(lt) - ref["parts"]["tracking"]) <= 1e-4 * abs(ref["parts"]["tracking"])
+    assert rel_l2(o.model.backbone.depth.grad.cpu(), ref["grads"]["depth"]) <= 2e-4
+    assert rel_l2(o.model.backbone.weights.grad.cpu(), ref["grads"]["weights"]) <= 2e-4
+    assert abs(float(o.model.intrinsics.focal_length.grad) - float(ref["grads"]["focal"])) <= \
+        2e-4 * abs(float(ref["grads"]["focal"]))
