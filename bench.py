@@ -26,7 +26,7 @@ sys.path.insert(0, str(ROOT))
 F_, H_, W_ = 150, 360, 640  # BASELINE.json configs[2] ("Tanks&Temples-shape")
 WORKLOAD = ("C3 150x360x640 synthetic (iid N(0,0.01^2) flows, U(0,1) masks), explicit_depth "
             "backbone, all-pixel Procrustes, regressed focal, flow loss (Huber), full overfit "
-            "step = Model.forward + LossFlow + backward + Adam")
+            "step = Model.forward + LossFlow + backward + Adam (fm_overfit_step)")
 
 
 # ------------------------------------------------------------------------------ inputs
@@ -54,18 +54,21 @@ def algorithmic_bytes(f, h, w):
 
 # ------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """nvidia-smi sampled every 20 ms in the background; samples are time-stamped so that the
+    ones that fall inside the timed regions can be picked out afterwards."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.samples, self.proc, self.index = [], None, index
+        self.samples, self.proc, self.index, self.windows = [], None, index, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                 "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -73,7 +76,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if self.proc is None:
@@ -83,23 +89,31 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            parts = [x.strip() for x in s.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx = float(parts[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
+
+        def summarise(rows):
+            sm, mx, reasons = [], None, set()
+            for _, s in rows:
+                parts = [x.strip() for x in s.split(",")]
+                if len(parts) < 6:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx = float(parts[1])
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            sm.sort()
+            return sm, mx, reasons
+        inside = [r for r in self.samples if any(a <= r[0] <= b for a, b in self.windows)]
+        which = "timed regions"
+        if len(inside) < 3:  # regions shorter than the sampling period: use everything under load
+            inside, which = self.samples, "warm-up + timed regions + per-op timing (all under load)"
+        sm, mx, reasons = summarise(inside)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": which}
 
 
 # ------------------------------------------------------------------------------ CPU baseline
@@ -167,20 +181,24 @@ def run_gpu(args):
                       torch.arange(F_, device=dev)[None], ["synthetic"], ["synthetic"])
     flows_host = Flows(inputs["fwd"].pin_memory(), inputs["bwd"].pin_memory(),
                        inputs["fmask"].pin_memory(), inputs["bmask"].pin_memory())
-    o = Overfitter.__new__(Overfitter)
+    from flowmap_b200 import parallel
+    from flowmap_b200.overfit import FusedOverfitter, ShardedFusedOverfitter
     cfg = OverfitCfg()
-    from flowmap_b200.overfit import FusedAdam, build_model_and_losses
-    o.cfg, o.batch, o.tracks = cfg, batch_dev, None
-    o.flows = Flows(*(t.to(dev, non_blocking=True) for t in
-                      (flows_host.forward, flows_host.backward, flows_host.forward_mask,
-                       flows_host.backward_mask)))
-    o.model, o.losses = build_model_and_losses(cfg, F_, (H_, W_))
-    o.model.to(dev)
+    flows_dev = Flows(*(t.to(dev, non_blocking=True) for t in
+                        (flows_host.forward, flows_host.backward, flows_host.forward_mask,
+                         flows_host.backward_mask)))
+    if world > 1:
+        # weak scaling: every rank owns 149 pairs of one long video (world * 149 pairs)
+        plan = parallel.ShardPlan(rank, world, (rank * (F_ - 1), (rank + 1) * (F_ - 1)),
+                                  world * (F_ - 1))
+        o = ShardedFusedOverfitter(cfg, batch_dev, flows_dev, plan, device=dev)
+    else:
+        o = FusedOverfitter(cfg, batch_dev, flows_dev, device=dev)
     with torch.no_grad():
         o.model.backbone.depth.copy_(inputs["depth"])
         o.model.backbone.weights.copy_(inputs["wparam"])
-    o.optimizer = FusedAdam(o.model.parameters(), cfg.lr)
-    o.global_step = 0
+    if world > 1:
+        o.sync_boundary_depth()
 
     def barrier():
         if world > 1:
@@ -188,13 +206,14 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing (value)
-    for _ in range(args.warmup):
-        o.training_step()
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        o.training_step()
+    barrier()
     l0 = lib().fm_launch_count()
+    t_w0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -203,7 +222,7 @@ def run_gpu(args):
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
     launches = lib().fm_launch_count() - l0
-    clk = clocks.stop() if rank == 0 else None
+    clocks.window(t_w0, time.time())
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -215,21 +234,29 @@ def run_gpu(args):
     h2d = sum(x.numel() * 4 for x in (flows_host.forward, flows_host.backward,
                                       flows_host.forward_mask, flows_host.backward_mask))
     def e2e_step():
-        o.flows = Flows(flows_host.forward.to(dev, non_blocking=True),
-                        flows_host.backward.to(dev, non_blocking=True),
-                        flows_host.forward_mask.to(dev, non_blocking=True),
-                        flows_host.backward_mask.to(dev, non_blocking=True))
+        # the step's Flows arrive from pinned host memory into the (fixed) device buffers the
+        # step reads; the mask normaliser is recomputed because the masks are "new"
+        o.flows.forward.copy_(flows_host.forward, non_blocking=True)
+        o.flows.backward.copy_(flows_host.backward, non_blocking=True)
+        o.flows.forward_mask.copy_(flows_host.forward_mask, non_blocking=True)
+        o.flows.backward_mask.copy_(flows_host.backward_mask, non_blocking=True)
+        ms_ = ops.mask_sum(o.flows.forward_mask, o.flows.backward_mask)
+        if world > 1:
+            ms_ = parallel.global_mask_sum(ms_)
+        o._msum.copy_(ms_)
         l, _ = o.training_step()
         return float(l)  # D2H read of the step's loss
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
         e2e_step()
     barrier()
+    t_w0 = time.time()
     e0.record()
     for _ in range(e2e_steps):
         e2e_step()
     e1.record()
     barrier()
+    clocks.window(t_w0, time.time())
     t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -237,6 +264,7 @@ def run_gpu(args):
 
     if rank != 0:
         if world > 1:
+            torch.distributed.barrier()  # rank 0 still runs its per-op timing / CPU baseline
             torch.distributed.destroy_process_group()
         return
 
@@ -246,7 +274,7 @@ def run_gpu(args):
         depths = o.model.backbone.depth.detach()[None].contiguous()
         weights = torch.sigmoid(100.0 * o.model.backbone.weights.detach())[None].contiguous()
         k3 = o.model.intrinsics.forward(o.batch, o.flows, None, 0)
-        k4 = ops.intrinsics_to_k4(k3).contiguous()
+        k4 = ops.intrinsics_to_k4(k3).contiguous().clone()
         msum = ops.mask_sum(o.flows.forward_mask, o.flows.backward_mask)
         ws = ops.workspace(1, F_, H_, W_, dev)
         rt = torch.empty(1, F_ - 1, 3, 4, device=dev)
@@ -283,6 +311,7 @@ def run_gpu(args):
                 tot += a.elapsed_time(b)
             return tot / n
         t_fwd, t_flow, t_bwd = timed(op_fwd), timed(op_flow), timed(op_bwd)
+    clk = clocks.stop()
 
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
@@ -327,7 +356,10 @@ def run_gpu(args):
         "config": {"workload": WORKLOAD, "frames": F_, "height": H_, "width": W_,
                    "shards": f"{world} x {F_ - 1} pairs" if world > 1 else "1 x 149 pairs",
                    "l2": "inputs (1.1 GB) exceed the 126 MB L2, no flush needed",
-                   "mask_sum": "loop-invariant denominator cached on tensor version"},
+                   "mask_sum": "loop-invariant denominator hoisted out of the loop (recomputed "
+                               "every step in the e2e leg, where the masks are re-uploaded)",
+                   "collective": ("1 all-reduce/step of %d bytes (loss, d focal, boundary frames)"
+                                  % o.reducer.bytes_per_step()) if world > 1 else "none"},
         "e2e": {"value": round(world * 1000.0 / e2e_ms, 3), "unit": "it/s",
                 "ms_per_step": round(e2e_ms, 3), "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4,
@@ -338,6 +370,7 @@ def run_gpu(args):
     }
     print(json.dumps(out))
     if world > 1:
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 
@@ -369,7 +402,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

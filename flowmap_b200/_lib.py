@@ -45,6 +45,34 @@ SIGNATURES = {
 }
 
 
+class PackedTracksC(ctypes.Structure):
+    """fm_packed_tracks"""
+    _fields_ = [("segments", _P), ("xy", _P), ("vis", _P), ("num_segments", c_int),
+                ("max_rows", c_int), ("max_points", c_int), ("total_samples", ctypes.c_longlong)]
+
+
+class OverfitStepArgs(ctypes.Structure):
+    """fm_overfit_step_args (field order as in include/flowmap_b200.h)"""
+    _fields_ = [("F", c_int), ("H", c_int), ("W", c_int),
+                ("depth", _P), ("weight_logits", _P), ("weight_sensitivity", c_float),
+                ("focal", _P), ("k4", _P), ("indices", _P), ("num_indices", c_int),
+                ("fflow", _P), ("bflow", _P), ("fmask", _P), ("bmask", _P), ("mask_sum", _P),
+                ("mapping", c_int), ("delta", c_float), ("flow_weight", c_float),
+                ("tracks", ctypes.POINTER(PackedTracksC)), ("track_weight", c_float),
+                ("m_depth", _P), ("v_depth", _P), ("m_weights", _P), ("v_weights", _P),
+                ("m_focal", _P), ("v_focal", _P),
+                ("lr", c_double), ("beta1", c_double), ("beta2", c_double), ("eps", c_double),
+                ("step", c_int),
+                ("g_depth", _P), ("g_weights", _P), ("g_focal", _P), ("g_k4", _P),
+                ("rt", _P), ("loss", _P),
+                ("extrinsics", _P), ("g_extrinsics", _P), ("g_rt", _P), ("track_g_k4", _P),
+                ("track_loss", _P),
+                ("ws", _P), ("track_ws", _P)]
+
+
+SIGNATURES["fm_overfit_step"] = (c_int, [ctypes.POINTER(OverfitStepArgs), _P])
+
+
 class FlowmapLibraryError(RuntimeError):
     pass
 

@@ -156,6 +156,33 @@ __device__ __forceinline__ void red_add(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// Adds v0 / v1 at columns x0 / x0 + 1 of a row.  With 16-byte aligned rows (ALIGNED) the pair
+// goes out as ONE vector RED on the aligned group of four floats that contains x0 unless it
+// straddles two groups; measured on B200 (tools/red_bench.cu) the padded vector form is
+// 1.5x faster than four scalar REDs for scattered taps.
+template <bool ALIGNED>
+__device__ __forceinline__ void red_pair(float* row, int x0, int W, float v0, float v1) {
+  const int k = x0 & 3;
+  if (ALIGNED && k != 3) {
+    red_add4(row + (x0 - k), k == 0 ? v0 : 0.f, k == 0 ? v1 : (k == 1 ? v0 : 0.f),
+             k == 1 ? v1 : (k == 2 ? v0 : 0.f), k == 2 ? v1 : 0.f);
+  } else {
+    red_add(row + x0, v0);
+    if (x0 + 1 < W) red_add(row + x0 + 1, v1);
+  }
+}
+
+// Correspondence weight from its stored form: the weight itself (sens == 0) or the logit of
+// BackboneExplicitDepth (backbone_explicit_depth.py:40): w = sigmoid(sens * logit).
+__device__ __forceinline__ float weight_of(float stored, float sens) {
+  return sens == 0.f ? stored : __fdividef(1.0f, 1.0f + __expf(-sens * stored));
+}
+
 // Load the 4 (or 1) values a thread owns.
 template <int VEC>
 __device__ __forceinline__ void load_vec(const float* p, float* out) {
@@ -197,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
           const float* __restrict__ bflow, const float* __restrict__ weights,
           const int64_t* __restrict__ indices, int num_indices, double* __restrict__ moments,
-          int F, int H, int W) {
+          float wsens, int F, int H, int W) {
   __shared__ double smem[kNumMoments * (kThreads / 32)];
   const int pair = blockIdx.y;
   const int N = H * W;
@@ -225,8 +252,11 @@ k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
         float dv[VEC], wv[VEC], fv[2 * VEC];
         load_vec<VEC>(db + base, dv);
         load_vec2<VEC>(fl + 2 * base, fv);
-        if (wt) load_vec<VEC>(wt + base, wv);
-        else {
+        if (wt) {
+          load_vec<VEC>(wt + base, wv);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) wv[v] = weight_of(wv[v], wsens);
+        } else {
 #pragma unroll
           for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
         }
@@ -255,7 +285,7 @@ k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
       Taps taps;
       point_pq(g, pix_coord(c, g.grid.Wf, g.grid.invW), pix_coord(r, g.grid.Hf, g.grid.invH),
                __ldg(db + j), __ldg(fl + 2 * j), __ldg(fl + 2 * j + 1), load_a, p, q, taps);
-      moments_add(acc, wt ? __ldg(wt + j) : 1.f, p, q);
+      moments_add(acc, wt ? weight_of(__ldg(wt + j), wsens) : 1.f, p, q);
 #pragma unroll
       for (int i = 0; i < kNumMoments; ++i) accd[i] += (double)acc[i];
     }
@@ -292,13 +322,47 @@ __global__ void k_solve(const double* __restrict__ moments, const float* __restr
 //  25..28   dK_k through the unprojection ray (fx fy cx cy)
 //  29..32   dK_{k+1} through the forward-term projection
 //  33..36   dK_{k-1} through the backward-term projection
+// Body for one frame with compile-time knowledge of which of its two pairs exist.
+template <int VEC, bool HASF, bool HASB>
+__device__ __forceinline__ void flow_frame_body(const FlowFrame& f, const float* __restrict__ D,
+                                                const float* __restrict__ ff, const float* __restrict__ mf,
+                                                const float* __restrict__ fb, const float* __restrict__ mb,
+                                                float* __restrict__ gd, float g, const RobustCfg& rc,
+                                                const GridDims& grid, int N, float* acc) {
+  const int W = grid.W;
+  const int stride = gridDim.x * kThreads * VEC;
+  int base = (blockIdx.x * kThreads + threadIdx.x) * VEC;
+  int r = base / W, c0 = base - r * W;          // one division, then incremental updates
+  const int dr = stride / W, dc = stride - dr * W;
+#pragma unroll 1
+  for (; base < N; base += stride) {
+    float dv[VEC], ffv[2 * VEC], fbv[2 * VEC], mfv[VEC], mbv[VEC], out[VEC];
+    load_vec<VEC>(D + base, dv);
+    if (HASF) { load_vec2<VEC>(ff + 2 * base, ffv); load_vec<VEC>(mf + base, mfv); }
+    if (HASB) { load_vec2<VEC>(fb + 2 * base, fbv); load_vec<VEC>(mb + base, mbv); }
+    const float y = pix_coord(r, grid.Hf, grid.invH);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      out[v] = flow_pixel<HASF, HASB>(f, pix_coord(c0 + v, grid.Wf, grid.invW), y, dv[v],
+                                      HASF ? ffv[2 * v] : 0.f, HASF ? ffv[2 * v + 1] : 0.f,
+                                      HASF ? mfv[v] : 0.f, HASB ? fbv[2 * v] : 0.f,
+                                      HASB ? fbv[2 * v + 1] : 0.f, HASB ? mbv[v] : 0.f, g, rc, acc);
+    }
+    if (VEC == 4) *reinterpret_cast<float4*>(gd + base) = make_float4(out[0], out[1], out[2], out[3]);
+    else gd[base] = out[0];
+    r += dr; c0 += dc;
+    if (c0 >= W) { c0 -= W; ++r; }
+  }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(kThreads, 2)
 k_flow(const float* __restrict__ depth, const float* __restrict__ k4, const float* __restrict__ rt,
        const float* __restrict__ fflow, const float* __restrict__ bflow,
        const float* __restrict__ fmask, const float* __restrict__ bmask,
-       const double* __restrict__ mask_sum, int mapping, float delta, float loss_weight,
-       float* __restrict__ g_depth, double* __restrict__ flowacc, int F, int H, int W) {
+       const double* __restrict__ mask_sum, const float* __restrict__ grad_scale, int mapping,
+       float delta, float loss_weight, float* __restrict__ g_depth, double* __restrict__ flowacc, int F,
+       int H, int W) {
   __shared__ double smem[kFlowVals * (kThreads / 32)];
   const int frame = blockIdx.y;
   const int bi = frame / F, i = frame - bi * F;
@@ -314,7 +378,7 @@ k_flow(const float* __restrict__ depth, const float* __restrict__ k4, const floa
   if (f.hasB) f.tb = load_rt(rt, pairB);
   double den = mask_sum ? *mask_sum : 1.0;
   if (den == 0.0) den = 1.0;  // loss_flow.py:70 "valid_sum or 1"
-  const float g = (float)((double)loss_weight / den);
+  const float g = (float)((double)loss_weight * (grad_scale ? (double)*grad_scale : 1.0) / den);
   const RobustCfg rc = make_robust(mapping, delta, H, W);
   const GridDims grid = make_grid(H, W);
 
@@ -328,28 +392,9 @@ k_flow(const float* __restrict__ depth, const float* __restrict__ k4, const floa
   float acc[kFlowVals];
 #pragma unroll
   for (int k = 0; k < kFlowVals; ++k) acc[k] = 0.f;
-
-  for (int base = (blockIdx.x * kThreads + threadIdx.x) * VEC; base < N;
-       base += gridDim.x * kThreads * VEC) {
-    float dv[VEC], ffv[2 * VEC], fbv[2 * VEC], mfv[VEC], mbv[VEC], out[VEC];
-    load_vec<VEC>(D + base, dv);
-    if (f.hasF) { load_vec2<VEC>(ff + 2 * base, ffv); load_vec<VEC>(mf + base, mfv); }
-    if (f.hasB) { load_vec2<VEC>(fb + 2 * base, fbv); load_vec<VEC>(mb + base, mbv); }
-    const int r = base / W, c0 = base - r * W;
-    const float y = pix_coord(r, grid.Hf, grid.invH);
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      out[v] = flow_pixel(f, pix_coord(c0 + v, grid.Wf, grid.invW), y, dv[v],
-                          f.hasF ? ffv[2 * v] : 0.f, f.hasF ? ffv[2 * v + 1] : 0.f,
-                          f.hasF ? mfv[v] : 0.f, f.hasB ? fbv[2 * v] : 0.f,
-                          f.hasB ? fbv[2 * v + 1] : 0.f, f.hasB ? mbv[v] : 0.f, g, rc, acc);
-    }
-    if (VEC == 4) {
-      *reinterpret_cast<float4*>(gd + base) = make_float4(out[0], out[1], out[2], out[3]);
-    } else {
-      gd[base] = out[0];
-    }
-  }
+  if (f.hasF && f.hasB) flow_frame_body<VEC, true, true>(f, D, ff, mf, fb, mb, gd, g, rc, grid, N, acc);
+  else if (f.hasF) flow_frame_body<VEC, true, false>(f, D, ff, mf, fb, mb, gd, g, rc, grid, N, acc);
+  else flow_frame_body<VEC, false, true>(f, D, ff, mf, fb, mb, gd, g, rc, grid, N, acc);
   block_accumulate<kFlowVals>(acc, flowacc + (size_t)frame * kFlowAcc, smem);
 }
 
@@ -427,7 +472,8 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
              const float* __restrict__ bflow, const float* __restrict__ weights,
              const int64_t* __restrict__ indices, int num_indices,
              const PairAdjoint* __restrict__ adj, float* __restrict__ g_depth,
-             float* __restrict__ g_weights, double* __restrict__ k4acc, int F, int H, int W) {
+             float* __restrict__ g_weights, double* __restrict__ k4acc, float wsens, int F, int H,
+             int W) {
   __shared__ double smem[8 * (kThreads / 32)];
   __shared__ PairAdjoint s_adj;
   const int pair = blockIdx.y;
@@ -445,7 +491,7 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
   const float* wt = weights ? weights + (size_t)pair * N : nullptr;
   float* gda = g_depth + (size_t)a * N;
   auto load_a = [da](int i) { return __ldg(da + i); };
-  auto scatter = [gda](int i, float v) { red_add(gda + i, v); };
+  auto scatter = [gda, W](int rb, int x0, float v0, float v1) { red_pair<VEC == 4>(gda + rb, x0, W, v0, v1); };
   float* gdb = gda + N;
   float* gw = g_weights ? g_weights + (size_t)pair * N : nullptr;
   float kacc[8];
@@ -458,8 +504,11 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
       float dv[VEC], wv[VEC], fv[2 * VEC], gwv[VEC], gdv[VEC];
       load_vec<VEC>(db + base, dv);
       load_vec2<VEC>(fl + 2 * base, fv);
-      if (wt) load_vec<VEC>(wt + base, wv);
-      else {
+      if (wt) {
+        load_vec<VEC>(wt + base, wv);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) wv[v] = weight_of(wv[v], wsens);
+      } else {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
       }
@@ -469,9 +518,13 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
       for (int v = 0; v < VEC; ++v)
         distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v],
                          fv[2 * v], fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) red_add(gdb + base + v, gdv[v]);
+      if (VEC == 4) red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
+      else red_add(gdb + base, gdv[0]);
       if (gw) {
+        if (wsens != 0.f) {  // chain rule of the sigmoid: d/d logit = sens * w (1 - w) * d/dw
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) gwv[v] *= wsens * wv[v] * (1.0f - wv[v]);
+        }
         if (VEC == 4) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
         else gw[base] = gwv[0];
       }
@@ -481,12 +534,13 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
       const int j = (int)indices[t];
       const int r = j / W, c = j - r * W;
       float gdj, gwj;
+      const float wj = wt ? weight_of(__ldg(wt + j), wsens) : 1.f;
       distribute_point(g, ad, pix_coord(c, g.grid.Wf, g.grid.invW),
                        pix_coord(r, g.grid.Hf, g.grid.invH), __ldg(db + j),
-                       wt ? __ldg(wt + j) : 1.f, __ldg(fl + 2 * j), __ldg(fl + 2 * j + 1), load_a,
+                       wj, __ldg(fl + 2 * j), __ldg(fl + 2 * j + 1), load_a,
                        scatter, gdj, gwj, kacc);
       red_add(gdb + j, gdj);
-      if (gw) red_add(gw + j, gwj);
+      if (gw) red_add(gw + j, wsens != 0.f ? gwj * wsens * wj * (1.0f - wj) : gwj);
     }
   }
   // kacc[0..3] -> frame a, kacc[4..7] -> frame b = a + 1: contiguous in k4acc
@@ -904,6 +958,45 @@ __global__ void k_track_finalize(const double* __restrict__ trackacc, const floa
   o[12] = o[13] = o[14] = o[15] = 0.f;
 }
 
+// ================================================================== fused overfit step helpers
+// focal_lengths_to_intrinsics (intrinsics/common.py:6-20) for a shared focal length, as k4 rows.
+__global__ void k_k4_from_focal(const float* __restrict__ focal, float* __restrict__ k4, int BF, int H, int W) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= BF) return;
+  const float scaled = *focal * sqrtf((float)H * (float)W);  // float32 like the reference
+  k4[t * 4 + 0] = scaled / (float)W;
+  k4[t * 4 + 1] = scaled / (float)H;
+  k4[t * 4 + 2] = 0.5f;
+  k4[t * 4 + 3] = 0.5f;
+}
+
+// d loss / d focal from the per-frame k4 gradients (flow-loss part + Procrustes part).
+__global__ void k_focal_grad(const double* __restrict__ k4acc, const double* __restrict__ flowacc,
+                             const float* __restrict__ extra_g_k4, float* __restrict__ g_focal, int B,
+                             int F, int H, int W) {
+  double sx = 0.0, sy = 0.0;
+  for (int t = threadIdx.x; t < B * F; t += blockDim.x) {
+    double g[4];
+    flow_k4_grad(flowacc, t, F, g);
+    sx += g[0] + k4acc[(size_t)t * 4 + 0] + (extra_g_k4 ? (double)extra_g_k4[t * 4 + 0] : 0.0);
+    sy += g[1] + k4acc[(size_t)t * 4 + 1] + (extra_g_k4 ? (double)extra_g_k4[t * 4 + 1] : 0.0);
+  }
+  __shared__ double sm[2][32];
+  sx = warp_sum(sx); sy = warp_sum(sy);
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = sx; sm[1][threadIdx.x >> 5] = sy; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ax = 0.0, ay = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ax += sm[0][w]; ay += sm[1][w]; }
+    const double sc = sqrt((double)H * (double)W);
+    *g_focal = (float)(ax * sc / W + ay * sc / H);
+  }
+}
+
+__global__ void k_add_scalar(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b) {
+  *dst = *a + (b ? *b : 0.f);
+}
+
 // ---------------------------------------------------------------- launch geometry
 int blocks_for(int n_items_per_row, int vec) {
   // ~4096 items per block keeps thousands of blocks in flight at the BASELINE sizes and
@@ -971,9 +1064,10 @@ int fm_reproject(const float* xyz, const float* rt, const float* k4, float* xy, 
   return 0;
 }
 
-int fm_procrustes_fwd(const float* depth, const float* k4, const float* backward_flow,
-                      const float* weights, const int64_t* indices, int num_indices, float* rt,
-                      void* ws, int B, int F, int H, int W, void* stream) {
+static int procrustes_fwd_impl(const float* depth, const float* k4, const float* backward_flow,
+                               const float* weights, float wsens, const int64_t* indices,
+                               int num_indices, float* rt, void* ws, int B, int F, int H, int W,
+                               void* stream) {
   if (!depth || !k4 || !backward_flow || !rt || !ws || bad_dims(B, F, H, W))
     return fail_msg("fm_procrustes_fwd: bad arguments");
   if (indices && num_indices < 1) return fail_msg("fm_procrustes_fwd: empty index set");
@@ -984,13 +1078,13 @@ int fm_procrustes_fwd(const float* depth, const float* k4, const float* backward
   if (e != cudaSuccess) return fail("fm_procrustes_fwd: memset", e);
   if (indices) {
     dim3 grid(blocks_for(num_indices, 1), BP);
-    k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.moments, F, H, W);
+    k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.moments, wsens, F, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
-    k_moments<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, F, H, W);
+    k_moments<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, F, H, W);
   } else {
     dim3 grid(blocks_for(H * W, 1), BP);
-    k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, F, H, W);
+    k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, F, H, W);
   }
   FM_CHECK_LAUNCH("fm_procrustes_fwd: k_moments");
   k_solve<<<(BP + 63) / 64, 64, 0, s>>>(w.moments, depth, rt, w.state, BP, F, H, W);
@@ -998,11 +1092,18 @@ int fm_procrustes_fwd(const float* depth, const float* k4, const float* backward
   return 0;
 }
 
-int fm_procrustes_bwd(const float* depth, const float* k4, const float* backward_flow,
-                      const float* weights, const int64_t* indices, int num_indices,
-                      const float* g_rt, int include_flow_loss, const float* flow_scale,
-                      float* g_depth, float* g_weights, float* g_k4, void* ws, int B, int F, int H,
-                      int W, void* stream) {
+int fm_procrustes_fwd(const float* depth, const float* k4, const float* backward_flow,
+                      const float* weights, const int64_t* indices, int num_indices, float* rt,
+                      void* ws, int B, int F, int H, int W, void* stream) {
+  return procrustes_fwd_impl(depth, k4, backward_flow, weights, 0.f, indices, num_indices, rt, ws, B, F,
+                             H, W, stream);
+}
+
+static int procrustes_bwd_impl(const float* depth, const float* k4, const float* backward_flow,
+                               const float* weights, float wsens, const int64_t* indices,
+                               int num_indices, const float* g_rt, int include_flow_loss,
+                               const float* flow_scale, float* g_depth, float* g_weights, float* g_k4,
+                               void* ws, int B, int F, int H, int W, void* stream) {
   if (!depth || !k4 || !backward_flow || !g_depth || !g_k4 || !ws || bad_dims(B, F, H, W))
     return fail_msg("fm_procrustes_bwd: bad arguments");
   if (!g_rt && !include_flow_loss) return fail_msg("fm_procrustes_bwd: no pose gradient given");
@@ -1020,18 +1121,28 @@ int fm_procrustes_bwd(const float* depth, const float* k4, const float* backward
   FM_CHECK_LAUNCH("fm_procrustes_bwd: k_adjoint");
   if (indices) {
     dim3 grid(blocks_for(num_indices, 1), BP);
-    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, F, H, W);
+    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, F, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
-    k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, F, H, W);
+    k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, F, H, W);
   } else {
     dim3 grid(blocks_for(H * W, 1), BP);
-    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, F, H, W);
+    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, F, H, W);
   }
   FM_CHECK_LAUNCH("fm_procrustes_bwd: k_distribute");
   k_k4_finalize<<<(BF + 127) / 128, 128, 0, s>>>(w.k4acc, w.flowacc, include_flow_loss, flow_scale, g_k4, B, F);
   FM_CHECK_LAUNCH("fm_procrustes_bwd: k_k4_finalize");
   return 0;
+}
+
+int fm_procrustes_bwd(const float* depth, const float* k4, const float* backward_flow,
+                      const float* weights, const int64_t* indices, int num_indices,
+                      const float* g_rt, int include_flow_loss, const float* flow_scale,
+                      float* g_depth, float* g_weights, float* g_k4, void* ws, int B, int F, int H,
+                      int W, void* stream) {
+  return procrustes_bwd_impl(depth, k4, backward_flow, weights, 0.f, indices, num_indices, g_rt,
+                             include_flow_loss, flow_scale, g_depth, g_weights, g_k4, ws, B, F, H, W,
+                             stream);
 }
 
 int fm_mask_sum(const float* forward_mask, const float* backward_mask, double* out, size_t count, void* stream) {
@@ -1065,10 +1176,10 @@ int fm_flow_loss_fwd_bwd(const float* depth, const float* k4, const float* rt,
   if (e != cudaSuccess) return fail("fm_flow_loss_fwd_bwd: memset", e);
   if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BF);
-    k_flow<4><<<grid, kThreads, 0, s>>>(depth, k4, rt, forward_flow, backward_flow, forward_mask, backward_mask, mask_sum, mapping, delta, loss_weight, g_depth, w.flowacc, F, H, W);
+    k_flow<4><<<grid, kThreads, 0, s>>>(depth, k4, rt, forward_flow, backward_flow, forward_mask, backward_mask, mask_sum, nullptr, mapping, delta, loss_weight, g_depth, w.flowacc, F, H, W);
   } else {
     dim3 grid(blocks_for(H * W, 1), BF);
-    k_flow<1><<<grid, kThreads, 0, s>>>(depth, k4, rt, forward_flow, backward_flow, forward_mask, backward_mask, mask_sum, mapping, delta, loss_weight, g_depth, w.flowacc, F, H, W);
+    k_flow<1><<<grid, kThreads, 0, s>>>(depth, k4, rt, forward_flow, backward_flow, forward_mask, backward_mask, mask_sum, nullptr, mapping, delta, loss_weight, g_depth, w.flowacc, F, H, W);
   }
   FM_CHECK_LAUNCH("fm_flow_loss_fwd_bwd: k_flow");
   const int n = BF > BP ? BF : BP;
@@ -1178,6 +1289,92 @@ int fm_track_loss_bwd(const float* depth, const float* k4, const float* extrinsi
   FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_bwd_tgt");
   k_track_finalize<<<(F + 63) / 64, 64, 0, s>>>(w.acc, extrinsics, g_extrinsics, g_k4, F);
   FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_finalize");
+  return 0;
+}
+
+int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
+  if (!a || !a->depth || !a->fflow || !a->bflow || !a->fmask || !a->bmask || !a->mask_sum ||
+      !a->g_depth || !a->rt || !a->loss || !a->ws || !a->k4 || bad_dims(1, a->F, a->H, a->W))
+    return fail_msg("fm_overfit_step: bad arguments");
+  if (a->weight_logits && !a->g_weights) return fail_msg("fm_overfit_step: g_weights missing");
+  if (a->tracks && (!a->extrinsics || !a->g_extrinsics || !a->track_ws || !a->track_loss))
+    return fail_msg("fm_overfit_step: tracking needs extrinsics / g_extrinsics / track_ws / track_loss");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int F = a->F, H = a->H, W = a->W, BP = F - 1;
+  const size_t N = (size_t)H * W;
+  Workspace w = carve(a->ws, 1, F);
+  int rc;
+  // intrinsics from the focal parameter (regressed stage) or as given
+  float* k4 = a->k4;
+  if (a->focal) {
+    k_k4_from_focal<<<(F + 63) / 64, 64, 0, s>>>(a->focal, k4, F, H, W);
+    FM_CHECK_LAUNCH("fm_overfit_step: k_k4_from_focal");
+  }
+  // Model.forward: Procrustes poses (model.py:54-90)
+  if ((rc = procrustes_fwd_impl(a->depth, k4, a->bflow, a->weight_logits, a->weight_sensitivity,
+                                a->indices, a->num_indices, a->rt, a->ws, 1, F, H, W, stream)))
+    return rc;
+  // LossFlow forward + direct gradients (loss_flow.py:31-70)
+  cudaError_t e = cudaMemsetAsync(w.flowacc, 0, (size_t)F * kFlowAcc * sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_overfit_step: memset", e);
+  if (W % 4 == 0) {
+    dim3 grid(blocks_for(H * W, 4), F);
+    k_flow<4><<<grid, kThreads, 0, s>>>(a->depth, k4, a->rt, a->fflow, a->bflow, a->fmask, a->bmask, a->mask_sum, nullptr, a->mapping, a->delta, a->flow_weight, a->g_depth, w.flowacc, F, H, W);
+  } else {
+    dim3 grid(blocks_for(H * W, 1), F);
+    k_flow<1><<<grid, kThreads, 0, s>>>(a->depth, k4, a->rt, a->fflow, a->bflow, a->fmask, a->bmask, a->mask_sum, nullptr, a->mapping, a->delta, a->flow_weight, a->g_depth, w.flowacc, F, H, W);
+  }
+  FM_CHECK_LAUNCH("fm_overfit_step: k_flow");
+  k_flow_finalize<<<(F + 127) / 128, 128, 0, s>>>(w.flowacc, a->rt, a->loss, nullptr, nullptr, 1, F);
+  FM_CHECK_LAUNCH("fm_overfit_step: k_flow_finalize");
+  // LossTracking (loss_tracking.py:28-61) on the chained poses, gradients into g_depth / g_rt
+  const float* g_rt = nullptr;
+  const float* track_g_k4 = nullptr;
+  if (a->tracks) {
+    const fm_packed_tracks* t = a->tracks;
+    if ((rc = fm_pose_chain(a->rt, a->extrinsics, 1, F, stream))) return rc;
+    if ((rc = fm_track_loss_fwd(a->depth, k4, a->extrinsics, t->segments, t->num_segments, t->max_rows,
+                                t->max_points, t->xy, t->vis, t->total_samples, a->mapping, a->delta,
+                                a->track_weight, a->track_loss, a->track_ws, F, H, W, stream)))
+      return rc;
+    if ((rc = fm_track_loss_bwd(a->depth, k4, a->extrinsics, t->segments, t->num_segments, t->max_rows,
+                                t->max_points, t->xy, t->vis, t->total_samples, a->mapping, a->delta,
+                                a->track_weight, nullptr, a->g_depth, a->g_extrinsics, a->track_g_k4,
+                                a->track_ws, F, H, W, stream)))
+      return rc;
+    if ((rc = fm_pose_chain_bwd(a->rt, a->extrinsics, a->g_extrinsics, a->g_rt, 1, F, stream))) return rc;
+    g_rt = a->g_rt;
+    track_g_k4 = a->track_g_k4;
+  }
+  // backward through Procrustes: adjoint constants, per-point distribution
+  if (a->indices && a->g_weights) {  // subsampled Procrustes: sparse weight gradient, dense buffer
+    e = cudaMemsetAsync(a->g_weights, 0, (size_t)BP * N * sizeof(float), s);
+    if (e != cudaSuccess) return fail("fm_overfit_step: memset g_weights", e);
+  }
+  if ((rc = procrustes_bwd_impl(a->depth, k4, a->bflow, a->weight_logits, a->weight_sensitivity,
+                                a->indices, a->num_indices, g_rt, 1, nullptr, a->g_depth, a->g_weights,
+                                a->g_k4, a->ws, 1, F, H, W, stream)))
+    return rc;
+  // Adam (model_wrapper_overfit.py:104-105)
+  if (a->step > 0) {
+    if ((rc = fm_adam_step(a->depth, a->g_depth, a->m_depth, a->v_depth, (size_t)F * N, a->lr, a->beta1,
+                           a->beta2, a->eps, a->step, stream)))
+      return rc;
+    if (a->weight_logits &&
+        (rc = fm_adam_step(a->weight_logits, a->g_weights, a->m_weights, a->v_weights, (size_t)BP * N,
+                           a->lr, a->beta1, a->beta2, a->eps, a->step, stream)))
+      return rc;
+    if (a->focal) {
+      k_focal_grad<<<1, 256, 0, s>>>(w.k4acc, w.flowacc, track_g_k4, a->g_focal, 1, F, H, W);
+      FM_CHECK_LAUNCH("fm_overfit_step: k_focal_grad");
+      if ((rc = fm_adam_step(a->focal, a->g_focal, a->m_focal, a->v_focal, 1, a->lr, a->beta1, a->beta2,
+                             a->eps, a->step, stream)))
+        return rc;
+    }
+  } else if (a->focal) {
+    k_focal_grad<<<1, 256, 0, s>>>(w.k4acc, w.flowacc, track_g_k4, a->g_focal, 1, F, H, W);
+    FM_CHECK_LAUNCH("fm_overfit_step: k_focal_grad");
+  }
   return 0;
 }
 

@@ -72,13 +72,14 @@ struct FlowFrame {
 // One pixel of frame k: forward term (loss_flow.py:47-56 with projection.py:143-162) and
 // backward term (loss_flow.py:59-68 with projection.py:165-184) in the pair-local form of
 // SURVEY A.6.  Returns the direct (pose-detached) depth gradient.
+template <bool HASF, bool HASB>
 FM_HD float flow_pixel(const FlowFrame& f, float x, float y, float D, float ffx, float ffy, float mf,
                        float fbx, float fby, float mb, float g, const RobustCfg& rc, float* acc) {
   float rx, ry;
   ray_of(x, y, f.kk, rx, ry);
   const float s0 = D * rx, s1 = D * ry, s2 = D;
   float ds0 = 0.f, ds1 = 0.f, ds2 = 0.f;
-  if (f.hasF) {  // Y = R^T (s - t), projected with K_{k+1}
+  if (HASF) {  // Y = R^T (s - t), projected with K_{k+1}
     const float d0 = s0 - f.tf.t[0], d1 = s1 - f.tf.t[1], d2 = s2 - f.tf.t[2];
     const float* R = f.tf.r;
     const float Y0 = R[0] * d0 + R[3] * d1 + R[6] * d2;
@@ -100,7 +101,7 @@ FM_HD float flow_pixel(const FlowFrame& f, float x, float y, float D, float ffx,
     ds1 += R[3] * dY0 + R[4] * dY1 + R[5] * dY2;
     ds2 += R[6] * dY0 + R[7] * dY1 + R[8] * dY2;
   }
-  if (f.hasB) {  // X = R s + t, projected with K_{k-1}
+  if (HASB) {  // X = R s + t, projected with K_{k-1}
     const float* R = f.tb.r;
     const float X0 = R[0] * s0 + R[1] * s1 + R[2] * s2 + f.tb.t[0];
     const float X1 = R[3] * s0 + R[4] * s1 + R[5] * s2 + f.tb.t[1];
@@ -131,8 +132,8 @@ FM_HD float flow_pixel(const FlowFrame& f, float x, float y, float D, float ffx,
 }
 
 // ---------------------------------------------------------------------------------
-// Phase D2: per-point adjoints of the Procrustes inputs.  `scatter(index, value)` adds into
-// the earlier frame's depth gradient; returns the aligned later-frame depth gradient and
+// Phase D2: per-point adjoints of the Procrustes inputs.  `scatter(row_base, x0, v0, v1)` adds
+// v0 / v1 into the earlier frame's depth gradient at columns x0 / x0 + 1 of a row; returns the aligned later-frame depth gradient and
 // the weight gradient.  kacc[0..3] += dK_a (through q), kacc[4..7] += dK_b (through p).
 // ---------------------------------------------------------------------------------
 template <typename LoadA, typename Scatter>
@@ -162,11 +163,10 @@ FM_HD void distribute_point(const PairGeom& g, const PairAdjoint& ad, float x, f
   const float b01 = qb[0] * rx1 + qb[1] * ry0 + qb[2];
   const float b10 = qb[0] * rx0 + qb[1] * ry1 + qb[2];
   const float b11 = qb[0] * rx1 + qb[1] * ry1 + qb[2];
+  // one call per tap row: (row base, x0, value at x0, value at x0 + 1); a clamped x1 has weight 0
   const int W = g.grid.W;
-  scatter(t.y0 * W + t.x0, t.w00 * b00);
-  scatter(t.y0 * W + t.x1, t.w01 * b01);
-  scatter(t.y1 * W + t.x0, t.w10 * b10);
-  scatter(t.y1 * W + t.x1, t.w11 * b11);
+  scatter(t.y0 * W, t.x0, t.w00 * b00, t.w01 * b01);
+  scatter(t.y1 * W, t.x0, t.w10 * b10, t.w11 * b11);
   const float qz_true = q[2] + g.z0;
   const float ea0 = qb[0] * g.ka.ifx, ea1 = qb[1] * g.ka.ify;
   kacc[0] -= ea0 * q[0];

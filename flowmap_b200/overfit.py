@@ -124,6 +124,149 @@ class Overfitter:
         return total.detach(), out
 
 
+class FusedOverfitter(Overfitter):
+    """Same optimisation as :class:`Overfitter` (explicit-depth backbone, Procrustes poses,
+    regressed focal length, flow [+ tracking] loss, Adam) but each step is ONE C-ABI call,
+    fm_overfit_step: no autograd graph, no intermediate tensors, the sigmoid of the weight
+    logits and its chain rule evaluated inside the kernels, gradients accumulated into a
+    single buffer per parameter."""
+
+    def __init__(self, cfg: OverfitCfg, batch: Batch, flows: Flows, tracks=None, device="cuda"):
+        super().__init__(cfg, batch, flows, tracks, device)
+        if cfg.intrinsics != "regressed":
+            raise NotImplementedError("FusedOverfitter: regressed intrinsics only (so far)")
+        from ._lib import OverfitStepArgs, PackedTracksC, lib
+        import ctypes
+        dev = self.flows.forward.device
+        _, f, _, h, w = batch.videos.shape
+        bb = self.model.backbone
+        self._depth, self._wlog = bb.depth.data, bb.weights.data
+        self._focal = self.model.intrinsics.focal_length.data
+        z = lambda t: torch.zeros_like(t)  # noqa: E731
+        self._state = [z(self._depth), z(self._depth), z(self._wlog), z(self._wlog),
+                       z(self._focal), z(self._focal)]
+        self._g_depth, self._g_w = torch.empty_like(self._depth), torch.empty_like(self._wlog)
+        self._g_focal = torch.zeros_like(self._focal)
+        self._k4 = torch.empty(f, 4, device=dev)
+        self._g_k4 = torch.empty(f, 4, device=dev)
+        self.rt = torch.empty(1, f - 1, 3, 4, device=dev)
+        self._loss = torch.zeros((), device=dev)
+        self._track_loss = torch.zeros((), device=dev)
+        self._ws = ops.workspace(1, f, h, w, dev)
+        self._msum = ops.mask_sum(self.flows.forward_mask, self.flows.backward_mask)
+        self._indices = self.model.extrinsics.select_indices(h, w, dev) \
+            if not cfg.procrustes_randomize else None
+        a = OverfitStepArgs()
+        P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        a.F, a.H, a.W = f, h, w
+        a.depth = P(self._depth)
+        a.weight_logits = P(self._wlog) if cfg.use_correspondence_weights else None
+        a.weight_sensitivity = cfg.weight_sensitivity
+        a.focal, a.k4 = P(self._focal), P(self._k4)
+        a.fflow, a.bflow = P(self.flows.forward), P(self.flows.backward)
+        a.fmask, a.bmask = P(self.flows.forward_mask), P(self.flows.backward_mask)
+        a.mask_sum = P(self._msum)
+        a.mapping, a.delta, a.flow_weight = ops.MAPPINGS[cfg.mapping], cfg.delta, cfg.flow_weight
+        (a.m_depth, a.v_depth, a.m_weights, a.v_weights, a.m_focal, a.v_focal) = \
+            [P(t) for t in self._state]
+        a.lr, a.beta1, a.beta2, a.eps = cfg.lr, 0.9, 0.999, 1e-8
+        a.g_depth, a.g_weights, a.g_focal, a.g_k4 = P(self._g_depth), P(self._g_w), \
+            P(self._g_focal), P(self._g_k4)
+        a.rt, a.loss, a.ws = P(self.rt), P(self._loss), P(self._ws)
+        self._packed = None
+        if cfg.use_tracking:
+            assert self.tracks is not None
+            pk = ops.PackedTracks(self.tracks, dev)
+            self._packed = pk
+            self._pk_c = PackedTracksC(P(pk.seg), P(pk.xy), P(pk.vis), pk.num_segments,
+                                       pk.max_rows, pk.max_points, pk.total)
+            self._ext = torch.empty(1, f, 4, 4, device=dev)
+            self._g_ext = torch.empty(1, f, 4, 4, device=dev)
+            self._g_rt = torch.empty(1, f - 1, 3, 4, device=dev)
+            self._tg_k4 = torch.empty(f, 4, device=dev)
+            self._tws = torch.empty(lib().fm_track_workspace_bytes(f, pk.total), dtype=torch.uint8,
+                                    device=dev)
+            a.track_weight = cfg.tracking_weight
+            a.extrinsics, a.g_extrinsics, a.g_rt = P(self._ext), P(self._g_ext), P(self._g_rt)
+            a.track_g_k4, a.track_loss, a.track_ws = P(self._tg_k4), P(self._track_loss), P(self._tws)
+        self._args, self._ctypes = a, ctypes
+        self._lib = lib()
+
+    def training_step(self, update: bool = True):
+        """Returns (total loss (device tensor), relative poses rt (1, F-1, 3, 4))."""
+        from ._lib import check
+        c, a = self.cfg, self._args
+        if c.procrustes_randomize:
+            _, _, _, h, w = self.batch.videos.shape
+            self._indices = self.model.extrinsics.select_indices(h, w, self.rt.device)
+        a.indices = None if self._indices is None else self._indices.data_ptr()
+        a.num_indices = 0 if self._indices is None else self._indices.numel()
+        track_on = c.use_tracking and self.global_step >= c.tracking_enable_after
+        a.tracks = self._ctypes.pointer(self._pk_c) if track_on else None
+        a.flow_weight = c.flow_weight if self.global_step >= c.flow_enable_after else 0.0
+        a.step = self.global_step + 1 if update else 0
+        with torch.cuda.device(self.rt.device):
+            check(self._lib.fm_overfit_step(self._ctypes.byref(a),
+                                            torch.cuda.current_stream().cuda_stream),
+                  "fm_overfit_step")
+        if update:
+            self.global_step += 1
+        total = self._loss + self._track_loss if track_on else self._loss.clone()
+        return total, self.rt
+
+    def extrinsics(self) -> Tensor:
+        """Camera-to-world poses of the last step (projection.py:187-210)."""
+        return ops.pose_chain(self.rt)
+
+    def gradients(self):
+        return {"depth": self._g_depth, "weights": self._g_w, "focal": self._g_focal}
+
+
+class ShardedFusedOverfitter(FusedOverfitter):
+    """Pair-sharded :class:`FusedOverfitter` (flowmap_b200.parallel): every rank runs
+    fm_overfit_step on its own pairs without the Adam part, ONE all-reduce carries the loss,
+    the focal-length gradient and the boundary depth-gradient frames, then each rank applies
+    Adam to its parameters (replicas of a boundary frame see identical gradients)."""
+
+    def __init__(self, cfg: OverfitCfg, batch: Batch, flows: Flows, plan, device="cuda", group=None):
+        from . import parallel
+        if cfg.use_tracking:
+            raise NotImplementedError("pair sharding covers the flow loss (BASELINE config 4)")
+        super().__init__(cfg, batch, flows, None, device)
+        self.plan, self.group = plan, group
+        _, _, _, h, w = batch.videos.shape
+        self.reducer = parallel.StepReducer(plan, (h, w), self.rt.device, 2, group)
+        self._msum.copy_(parallel.global_mask_sum(self._msum, group))  # in place: args hold its address
+
+    def sync_boundary_depth(self):
+        """Make the replicas of every shared boundary frame identical (owner = left rank)."""
+        import torch.distributed as dist
+        p = self.plan
+        if p.world == 1:
+            return
+        buf = torch.zeros(p.world - 1, *self._depth.shape[1:], device=self._depth.device)
+        if p.has_right:
+            buf[p.rank].copy_(self._depth[-1])
+        dist.all_reduce(buf, group=self.group)
+        if p.has_left:
+            self._depth[0].copy_(buf[p.rank - 1])
+
+    def training_step(self, update: bool = True):
+        loss, rt = super().training_step(update=False)
+        scalars = torch.stack((loss.reshape(()), self._g_focal.reshape(())))
+        red = self.reducer.reduce(scalars, self._g_depth)
+        self._g_focal.copy_(red[1])
+        if update:
+            self.global_step += 1
+            st, c = self._state, self.cfg
+            ops.adam_step(self._depth, self._g_depth, st[0], st[1], self.global_step, c.lr)
+            if c.use_correspondence_weights:
+                ops.adam_step(self._wlog, self._g_w, st[2], st[3], self.global_step, c.lr)
+            ops.adam_step(self._focal.reshape(1), self._g_focal.reshape(1), st[4].reshape(1),
+                          st[5].reshape(1), self.global_step, c.lr)
+        return red[0], rt
+
+
 class ShardedOverfitter(Overfitter):
     """Pair-sharded optimisation (flowmap_b200.parallel): this rank holds the frames and
     pairs of its ShardPlan; one all-reduce per step carries the loss, the focal-length

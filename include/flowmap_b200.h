@@ -133,6 +133,52 @@ int fm_track_loss_bwd(const float* depth, const float* k4, const float* extrinsi
 int fm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count,
                  double lr, double beta1, double beta2, double eps, int step, void* stream);
 
+/* Packed tracks (see fm_track_loss_fwd), device pointers. */
+typedef struct {
+  const int* segments;
+  const float* xy;
+  const unsigned char* vis;
+  int num_segments, max_rows, max_points;
+  long long total_samples;
+} fm_packed_tracks;
+
+/* One whole optimisation step of the explicit-depth overfit run (batch size 1) without
+ * leaving the library: what model_wrapper_overfit.py:51-73 (training_step) + :104-105
+ * (Adam) do through autograd, as one sequence of launches on `stream`:
+ *   [k4 from the focal parameter] -> Procrustes poses (model.py:54-90) -> flow loss with its
+ *   direct gradients (loss_flow.py:31-70) -> [track loss fwd/bwd on the chained poses,
+ *   loss_tracking.py:28-61] -> Procrustes backward -> Adam on depth, weight
+ *   logits and focal length.
+ * The correspondence weights are sigmoid(weight_sensitivity * weight_logits)
+ * (backbone_explicit_depth.py:40), evaluated inside the kernels; weight_logits == NULL means
+ * use_correspondence_weights = false (model.py:67-68).  focal == NULL keeps k4 as given
+ * (no intrinsics gradient).  step <= 0 computes loss and gradients but skips Adam.
+ * Gradients of the step are left in g_depth / g_weights / g_focal / g_k4. */
+typedef struct {
+  int F, H, W;
+  float* depth;                 /* (F,H,W) parameter, updated in place            */
+  float* weight_logits;         /* (F-1,H,W) parameter or NULL                    */
+  float weight_sensitivity;
+  float* focal;                 /* device scalar parameter or NULL                */
+  float* k4;                    /* (F,4): written from focal, or read if focal == NULL */
+  const int64_t* indices;       /* Procrustes point subset or NULL (all pixels)   */
+  int num_indices;
+  const float *fflow, *bflow, *fmask, *bmask;
+  const double* mask_sum;
+  int mapping;
+  float delta, flow_weight;
+  const fm_packed_tracks* tracks; /* host struct with device pointers, or NULL    */
+  float track_weight;
+  float *m_depth, *v_depth, *m_weights, *v_weights, *m_focal, *v_focal;
+  double lr, beta1, beta2, eps;
+  int step;                     /* 1-based Adam step number                        */
+  float *g_depth, *g_weights, *g_focal, *g_k4;  /* gradient buffers (written)     */
+  float *rt, *loss;             /* outputs: (F-1,3,4) poses, flow loss             */
+  float *extrinsics, *g_extrinsics, *g_rt, *track_g_k4, *track_loss; /* tracking only */
+  void *ws, *track_ws;
+} fm_overfit_step_args;
+int fm_overfit_step(const fm_overfit_step_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,7 +75,8 @@ void emu_flow(const float* depth, const float* k4, const float* rt, const float*
     for (int j = 0; j < N; ++j) {
       float acc[kFlowVals] = {0};
       const size_t jf = (size_t)(f.hasF ? pairF : 0) * N + j, jb = (size_t)(f.hasB ? pairB : 0) * N + j;
-      g_depth[(size_t)frame * N + j] = flow_pixel(
+      auto fp = f.hasF && f.hasB ? flow_pixel<true, true> : (f.hasF ? flow_pixel<true, false> : flow_pixel<false, true>);
+      g_depth[(size_t)frame * N + j] = fp(
           f, pix_coord(j % W, grid.Wf, grid.invW), pix_coord(j / W, grid.Hf, grid.invH), depth[(size_t)frame * N + j], f.hasF ? ff[jf * 2] : 0.f,
           f.hasF ? ff[jf * 2 + 1] : 0.f, f.hasF ? mf[jf] : 0.f, f.hasB ? fb[jb * 2] : 0.f,
           f.hasB ? fb[jb * 2 + 1] : 0.f, f.hasB ? mb[jb] : 0.f, g, rc, acc);
@@ -103,7 +104,7 @@ void emu_procrustes_bwd(const float* depth, const float* k4, const float* bflow,
       float kacc[8] = {0}; float gdj, gwj;
       distribute_point(g, ad, pix_coord(j % W, g.grid.Wf, g.grid.invW), pix_coord(j / W, g.grid.Hf, g.grid.invH), db[j], weights ? weights[(size_t)pair * N + j] : 1.f,
                        bflow[((size_t)pair * N + j) * 2], bflow[((size_t)pair * N + j) * 2 + 1],
-                       [da](int i) { return da[i]; }, [gda](int i, float v) { gda[i] += v; }, gdj, gwj, kacc);
+                       [da](int i) { return da[i]; }, [gda, W](int rb, int x0, float v0, float v1) { gda[rb + x0] += v0; if (x0 + 1 < W) gda[rb + x0 + 1] += v1; }, gdj, gwj, kacc);
       gdb[j] += gdj;
       if (g_weights) g_weights[(size_t)pair * N + j] += gwj;
       for (int k = 0; k < 8; ++k) k4acc[(size_t)a * 4 + k] += kacc[k];

@@ -237,3 +237,68 @@ def test_tracking_only_gradients_vs_oracle():
     assert rel_l2(o.model.backbone.weights.grad.cpu(), ref["grads"]["weights"]) <= 2e-4
     assert abs(float(o.model.intrinsics.focal_length.grad) - float(ref["grads"]["focal"])) <= \
         2e-4 * abs(float(ref["grads"]["focal"]))
+
+
+@pytest.mark.parametrize("name,mapping,focal,npts", CASES)
+def test_fused_step_matches_reference_golden(name, mapping, focal, npts):
+    """fm_overfit_step (one C-ABI call per optimisation step) against the same golden vectors."""
+    from flowmap_b200.overfit import FusedOverfitter, OverfitCfg
+    from flowmap_b200.types import Batch, Flows
+    g64, g32 = load_golden(name, True), load_golden(name, False)
+    f, h, w = g64["in_depth"].shape
+    cfg = OverfitCfg(mapping=mapping, initial_focal=focal, procrustes_points=npts)
+    batch = Batch(torch.zeros(1, f, 3, h, w), torch.arange(f)[None], ["s"], ["d"])
+    flows = Flows(*(T(g64[k]).float() for k in ("in_fwd", "in_bwd", "in_fmask", "in_bmask")))
+    o = FusedOverfitter(cfg, batch, flows)
+    with torch.no_grad():
+        o.model.backbone.depth.copy_(T(g64["in_depth"]).float())
+        o.model.backbone.weights.copy_(T(g64["in_wparam"]).float())
+    loss, rt = o.training_step(update=False)
+    gr = o.gradients()
+    assert abs(float(loss) - float(g64["loss"])) <= 1e-4 * abs(float(g64["loss"]))
+    assert max_abs(o.extrinsics().cpu(), g64["extrinsics"]) <= 1e-5
+    assert rel_l2(gr["depth"].cpu(), g64["g_depth"]) <= max(1e-4, 3 * rel_l2(g32["g_depth"], g64["g_depth"]))
+    assert rel_l2(gr["weights"].cpu(), g64["g_wparam"]) <= max(1e-4, 3 * rel_l2(g32["g_wparam"], g64["g_wparam"]))
+    assert abs(float(gr["focal"]) - float(g64["g_focal"])) <= 1e-4 * abs(float(g64["g_focal"]))
+
+
+@pytest.mark.parametrize("name", ["traj_generic", "traj_init"])
+def test_fused_adam_trajectory_matches_reference(name):
+    from flowmap_b200.overfit import FusedOverfitter, OverfitCfg
+    from flowmap_b200.types import Batch, Flows
+    g64 = load_golden(name, True)
+    f, h, w = g64["in_depth"].shape
+    batch = Batch(torch.zeros(1, f, 3, h, w), torch.arange(f)[None], ["s"], ["d"])
+    flows = Flows(*(T(g64[k]).float() for k in ("in_fwd", "in_bwd", "in_fmask", "in_bmask")))
+    o = FusedOverfitter(OverfitCfg(), batch, flows)
+    with torch.no_grad():
+        o.model.backbone.depth.copy_(T(g64["in_depth"]).float())
+        o.model.backbone.weights.copy_(T(g64["in_wparam"]).float())
+    for s in range(len(g64["loss"])):
+        total, _ = o.training_step()
+        assert abs(float(total) - g64["loss"][s]) <= 1e-4 * abs(g64["loss"][s]), s
+        assert max_abs(o.extrinsics().cpu(), g64["extrinsics"][s]) <= 1e-4, s
+    assert rel_l2(o.model.backbone.depth.detach().cpu(), g64["depth_final"]) <= 1e-5
+    w0, w1 = T(g64["in_wparam"]), T(g64["wparam_final"])
+    assert rel_l2(o.model.backbone.weights.detach().cpu().double() - w0, w1 - w0) <= 2e-2
+
+
+def test_fused_step_with_tracking_matches_golden():
+    from flowmap_b200.overfit import FusedOverfitter, OverfitCfg
+    from flowmap_b200.types import Batch, Flows, Tracks
+    g64, g32 = load_golden("tracking", True), load_golden("tracking", False)
+    f, h, w = g64["in_depth"].shape
+    batch = Batch(torch.zeros(1, f, 3, h, w), torch.arange(f)[None], ["s"], ["d"])
+    flows = Flows(*(T(g64[k]).float() for k in ("in_fwd", "in_bwd", "in_fmask", "in_bmask")))
+    tracks = [Tracks(T(g64[f"trk{i}_xy"]).float(), T(g64[f"trk{i}_vis"]), int(g64[f"trk{i}_start"]))
+              for i in range(2)]
+    o = FusedOverfitter(OverfitCfg(use_tracking=True, tracking_enable_after=0), batch, flows, tracks)
+    with torch.no_grad():
+        o.model.backbone.depth.copy_(T(g64["in_depth"]).float())
+        o.model.backbone.weights.copy_(T(g64["in_wparam"]).float())
+    loss, _ = o.training_step(update=False)
+    gr = o.gradients()
+    assert abs(float(loss) - float(g64["loss"])) <= 1e-4 * abs(float(g64["loss"]))
+    assert rel_l2(gr["depth"].cpu(), g64["g_depth"]) <= max(1e-4, 3 * rel_l2(g32["g_depth"], g64["g_depth"]))
+    assert rel_l2(gr["weights"].cpu(), g64["g_wparam"]) <= max(1e-4, 3 * rel_l2(g32["g_wparam"], g64["g_wparam"]))
+    assert abs(float(gr["focal"]) - float(g64["g_focal"])) <= 1e-4 * abs(float(g64["g_focal"]))
