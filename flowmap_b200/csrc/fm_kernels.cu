@@ -207,101 +207,120 @@ __device__ __forceinline__ void load_vec2(const float* p, float* out) {  // 2 * 
 }
 
 // ================================================================== phase A: moments
-__device__ __forceinline__ PairGeom pair_geom(const float* depth, const float* k4, int pair, int F,
+// Where the data of (virtual) pair `pair` lives.  Normally item == batch element and the
+// strides are the dense ones; the focal-length sweep (intrinsics_softmin.py:84-109) runs
+// `cand` virtual items per batch element that all read the SAME depth / flow / weights
+// (and accumulate into the same gradients) but have their own intrinsics, poses and moments.
+struct PairLayout {
+  int F;     // frames per item
+  int cand;  // virtual items per batch element (1 = none)
+  long long depth_bs, flow_bs, weight_bs;  // element strides between batch elements
+};
+struct PairAddr {
+  int k4_frame_a;          // row of k4 for the earlier frame (virtual frame index)
+  long long depth_a;       // element offset of the earlier frame's depth
+  long long flow, weight;  // element offsets of the pair's flow / weights
+};
+__host__ __device__ inline PairLayout dense_layout(int F, int H, int W) {
+  PairLayout l;
+  const long long N = (long long)H * W;
+  l.F = F; l.cand = 1; l.depth_bs = F * N; l.flow_bs = (F - 1) * N * 2; l.weight_bs = (F - 1) * N;
+  return l;
+}
+__device__ __forceinline__ PairAddr pair_addr(const PairLayout& l, int pair, int N) {
+  const int item = pair / (l.F - 1), i = pair - item * (l.F - 1);
+  const int rb = item / l.cand;
+  PairAddr a;
+  a.k4_frame_a = item * l.F + i;
+  a.depth_a = rb * l.depth_bs + (long long)i * N;
+  a.flow = rb * l.flow_bs + (long long)i * N * 2;
+  a.weight = rb * l.weight_bs + (long long)i * N;
+  return a;
+}
+__device__ __forceinline__ PairGeom pair_geom(const float* depth, const float* k4, const PairAddr& pa,
                                               int H, int W) {
-  const int bi = pair / (F - 1), i = pair - bi * (F - 1);
-  const int a = bi * F + i;
   PairGeom g;
-  g.ka = make_cam(load_k4(k4, a));
-  g.kb = make_cam(load_k4(k4, a + 1));
+  g.ka = make_cam(load_k4(k4, pa.k4_frame_a));
+  g.kb = make_cam(load_k4(k4, pa.k4_frame_a + 1));
   g.grid = make_grid(H, W);
-  g.z0 = __ldg(depth + (size_t)(a + 1) * H * W + (size_t)(H / 2) * W + W / 2);
+  g.z0 = __ldg(depth + pa.depth_a + (size_t)H * W + (size_t)(H / 2) * W + W / 2);
   return g;
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
           const float* __restrict__ bflow, const float* __restrict__ weights,
           const int64_t* __restrict__ indices, int num_indices, double* __restrict__ moments,
-          float wsens, int F, int H, int W) {
+          float wsens, PairLayout lay, int H, int W) {
   __shared__ double smem[kNumMoments * (kThreads / 32)];
   const int pair = blockIdx.y;
   const int N = H * W;
-  const PairGeom g = pair_geom(depth, k4, pair, F, H, W);
-  const int frame_a = (pair / (F - 1)) * F + pair % (F - 1);
-  const float* da = depth + (size_t)frame_a * N;
+  const PairAddr pa = pair_addr(lay, pair, N);
+  const PairGeom g = pair_geom(depth, k4, pa, H, W);
+  const float* da = depth + pa.depth_a;
   const float* db = da + N;
-  const float* fl = bflow + (size_t)pair * N * 2;
-  const float* wt = weights ? weights + (size_t)pair * N : nullptr;
+  const float* fl = bflow + pa.flow;
+  const float* wt = weights ? weights + pa.weight : nullptr;
   auto load_a = [da](int i) { return __ldg(da + i); };
-  double accd[kNumMoments];
+  // float32 per-thread partials: a thread sees at most a few dozen (shifted, O(1)) terms, the
+  // cross-thread / cross-block sums run in float64.
+  float acc[kNumMoments];
 #pragma unroll
-  for (int i = 0; i < kNumMoments; ++i) accd[i] = 0.0;
+  for (int i = 0; i < kNumMoments; ++i) acc[i] = 0.f;
 
   if (indices == nullptr) {
-    constexpr int kFlush = 4;  // float32 partials over at most kFlush * VEC pixels
-    int base = (blockIdx.x * kThreads + threadIdx.x) * VEC;
     const int stride = gridDim.x * kThreads * VEC;
-    while (base < N) {
-      float acc[kNumMoments];
-#pragma unroll
-      for (int i = 0; i < kNumMoments; ++i) acc[i] = 0.f;
+    int base = (blockIdx.x * kThreads + threadIdx.x) * VEC;
+    int r = base / W, c0 = base - r * W;
+    const int dr = stride / W, dc = stride - dr * W;
 #pragma unroll 1
-      for (int it = 0; it < kFlush && base < N; ++it, base += stride) {
-        float dv[VEC], wv[VEC], fv[2 * VEC];
-        load_vec<VEC>(db + base, dv);
-        load_vec2<VEC>(fl + 2 * base, fv);
-        if (wt) {
-          load_vec<VEC>(wt + base, wv);
+    for (; base < N; base += stride) {
+      float dv[VEC], wv[VEC], fv[2 * VEC];
+      load_vec<VEC>(db + base, dv);
+      load_vec2<VEC>(fl + 2 * base, fv);
+      if (wt) {
+        load_vec<VEC>(wt + base, wv);
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) wv[v] = weight_of(wv[v], wsens);
-        } else {
+        for (int v = 0; v < VEC; ++v) wv[v] = weight_of(wv[v], wsens);
+      } else {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
-        }
-        const int r = base / W, c0 = base - r * W;
-        const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          float p[3], q[3];
-          Taps taps;
-          point_pq(g, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], fv[2 * v], fv[2 * v + 1],
-                   load_a, p, q, taps);
-          moments_add(acc, wv[v], p, q);
-        }
+        for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
       }
+      const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
 #pragma unroll
-      for (int i = 0; i < kNumMoments; ++i) accd[i] += (double)acc[i];
+      for (int v = 0; v < VEC; ++v) {
+        float p[3], q[3];
+        Taps taps;
+        point_pq(g, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], fv[2 * v], fv[2 * v + 1],
+                 load_a, p, q, taps);
+        moments_add(acc, wv[v], p, q);
+      }
+      r += dr; c0 += dc;
+      if (c0 >= W) { c0 -= W; ++r; }
     }
   } else {
     for (int t = blockIdx.x * kThreads + threadIdx.x; t < num_indices; t += gridDim.x * kThreads) {
       const int j = (int)indices[t];
       const int r = j / W, c = j - r * W;
-      float acc[kNumMoments];
-#pragma unroll
-      for (int i = 0; i < kNumMoments; ++i) acc[i] = 0.f;
       float p[3], q[3];
       Taps taps;
       point_pq(g, pix_coord(c, g.grid.Wf, g.grid.invW), pix_coord(r, g.grid.Hf, g.grid.invH),
                __ldg(db + j), __ldg(fl + 2 * j), __ldg(fl + 2 * j + 1), load_a, p, q, taps);
       moments_add(acc, wt ? weight_of(__ldg(wt + j), wsens) : 1.f, p, q);
-#pragma unroll
-      for (int i = 0; i < kNumMoments; ++i) accd[i] += (double)acc[i];
     }
   }
-  block_accumulate_d<kNumMoments>(accd, moments + (size_t)pair * kNumMoments, smem);
+  block_accumulate<kNumMoments>(acc, moments + (size_t)pair * kNumMoments, smem);
 }
 
 // ================================================================== phase B: solve
 __global__ void k_solve(const double* __restrict__ moments, const float* __restrict__ depth,
-                        float* __restrict__ rt, PairState* __restrict__ state, int BP, int F, int H,
-                        int W) {
+                        float* __restrict__ rt, PairState* __restrict__ state, int BP, PairLayout lay,
+                        int H, int W) {
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
   if (pair >= BP) return;
-  const int bi = pair / (F - 1), i = pair - bi * (F - 1);
-  const int b = bi * F + i + 1;
-  const double z0 = (double)__ldg(depth + (size_t)b * H * W + (size_t)(H / 2) * W + W / 2);
+  const PairAddr pa = pair_addr(lay, pair, H * W);
+  const double z0 = (double)__ldg(depth + pa.depth_a + (size_t)H * W + (size_t)(H / 2) * W + W / 2);
   double m[kNumMoments];
   for (int k = 0; k < kNumMoments; ++k) m[k] = moments[(size_t)pair * kNumMoments + k];
   const double shift[3] = {0.0, 0.0, z0};
@@ -467,13 +486,13 @@ __global__ void k_adjoint(const double* __restrict__ flowacc, const PairState* _
 
 // ================================================================== phase D2: distribute
 template <int VEC>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
              const float* __restrict__ bflow, const float* __restrict__ weights,
              const int64_t* __restrict__ indices, int num_indices,
              const PairAdjoint* __restrict__ adj, float* __restrict__ g_depth,
-             float* __restrict__ g_weights, double* __restrict__ k4acc, float wsens, int F, int H,
-             int W) {
+             float* __restrict__ g_weights, double* __restrict__ k4acc, float wsens, PairLayout lay,
+             int H, int W) {
   __shared__ double smem[8 * (kThreads / 32)];
   __shared__ PairAdjoint s_adj;
   const int pair = blockIdx.y;
@@ -482,25 +501,29 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
     reinterpret_cast<float*>(&s_adj)[threadIdx.x] = reinterpret_cast<const float*>(adj + pair)[threadIdx.x];
   __syncthreads();
   const PairAdjoint ad = s_adj;
-  const PairGeom g = pair_geom(depth, k4, pair, F, H, W);
-  const int bi = pair / (F - 1), i = pair - bi * (F - 1);
-  const int a = bi * F + i;
-  const float* da = depth + (size_t)a * N;
+  const PairAddr pa = pair_addr(lay, pair, N);
+  const PairGeom g = pair_geom(depth, k4, pa, H, W);
+  const int a = pa.k4_frame_a;
+  const float* da = depth + pa.depth_a;
   const float* db = da + N;
-  const float* fl = bflow + (size_t)pair * N * 2;
-  const float* wt = weights ? weights + (size_t)pair * N : nullptr;
-  float* gda = g_depth + (size_t)a * N;
+  const float* fl = bflow + pa.flow;
+  const float* wt = weights ? weights + pa.weight : nullptr;
+  float* gda = g_depth + pa.depth_a;
   auto load_a = [da](int i) { return __ldg(da + i); };
   auto scatter = [gda, W](int rb, int x0, float v0, float v1) { red_pair<VEC == 4>(gda + rb, x0, W, v0, v1); };
   float* gdb = gda + N;
-  float* gw = g_weights ? g_weights + (size_t)pair * N : nullptr;
+  float* gw = g_weights ? g_weights + pa.weight : nullptr;
   float kacc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
 
   if (indices == nullptr) {
-    for (int base = (blockIdx.x * kThreads + threadIdx.x) * VEC; base < N;
-         base += gridDim.x * kThreads * VEC) {
+    const int stride = gridDim.x * kThreads * VEC;
+    int base = (blockIdx.x * kThreads + threadIdx.x) * VEC;
+    int r = base / W, c0 = base - r * W;
+    const int dr = stride / W, dc = stride - dr * W;
+#pragma unroll 1
+    for (; base < N; base += stride) {
       float dv[VEC], wv[VEC], fv[2 * VEC], gwv[VEC], gdv[VEC];
       load_vec<VEC>(db + base, dv);
       load_vec2<VEC>(fl + 2 * base, fv);
@@ -512,12 +535,13 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
 #pragma unroll
         for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
       }
-      const int r = base / W, c0 = base - r * W;
       const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
 #pragma unroll
       for (int v = 0; v < VEC; ++v)
         distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v],
                          fv[2 * v], fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
+      r += dr; c0 += dc;
+      if (c0 >= W) { c0 -= W; ++r; }
       if (VEC == 4) red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
       else red_add(gdb + base, gdv[0]);
       if (gw) {
@@ -958,6 +982,113 @@ __global__ void k_track_finalize(const double* __restrict__ trackacc, const floa
   o[12] = o[13] = o[14] = o[15] = 0.f;
 }
 
+// ================================================================== focal-length sweep
+// intrinsics_softmin.py:84-131: for every candidate focal length, Procrustes on the first
+// frame pair at the selected points (k_moments / k_solve with a broadcast PairLayout), then
+// the backward-flow error  err_n = sum_points sum_xy | (uv - xy - flow) * w |.
+// k_sweep<false>: err per candidate.  k_sweep<true>: given d loss / d err_n, the direct
+// depth / weight gradients (REDs) and the pose-gradient sums per candidate.
+constexpr int kSweepAcc = 80;  // doubles reserved per virtual item inside Workspace::flowacc
+
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads)
+k_sweep(const float* __restrict__ depth, const float* __restrict__ k4, const float* __restrict__ rt,
+        const float* __restrict__ bflow, const float* __restrict__ weights, float wsens,
+        const int64_t* __restrict__ indices, int num_indices, const float* __restrict__ g_err,
+        double* __restrict__ acc_out, float* __restrict__ g_depth, float* __restrict__ g_weights,
+        PairLayout lay, int H, int W) {
+  __shared__ double smem[12 * (kThreads / 32)];
+  const int item = blockIdx.y;
+  const int N = H * W;
+  const PairAddr pa = pair_addr(lay, item, N);  // F == 2: one pair per item
+  const Cam ka = make_cam(load_k4(k4, pa.k4_frame_a));
+  const Cam kb = make_cam(load_k4(k4, pa.k4_frame_a + 1));
+  const Rt T = load_rt(rt, item);
+  const GridDims grid = make_grid(H, W);
+  const float* d1 = depth + pa.depth_a + N;
+  const float* fl = bflow + pa.flow;
+  const float* wt = weights ? weights + pa.weight : nullptr;
+  float* gd1 = BWD ? g_depth + pa.depth_a + N : nullptr;
+  float* gw = (BWD && g_weights) ? g_weights + pa.weight : nullptr;
+  const float ge = BWD ? __ldg(g_err + item) : 0.f;
+  float acc[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+  for (int t = blockIdx.x * kThreads + threadIdx.x; t < num_indices; t += gridDim.x * kThreads) {
+    const int j = (int)indices[t];
+    const int r = j / W, c = j - r * W;
+    const float x = pix_coord(c, grid.Wf, grid.invW), y = pix_coord(r, grid.Hf, grid.invH);
+    const float D = __ldg(d1 + j);
+    float rx, ry;
+    ray_of(x, y, kb, rx, ry);
+    const float p0 = D * rx, p1 = D * ry, p2 = D;
+    const float X0 = T.r[0] * p0 + T.r[1] * p1 + T.r[2] * p2 + T.t[0];
+    const float X1 = T.r[3] * p0 + T.r[4] * p1 + T.r[5] * p2 + T.t[1];
+    const float X2 = T.r[6] * p0 + T.r[7] * p1 + T.r[8] * p2 + T.t[2];
+    const Proj pr = project_point(X0, X1, X2, ka);
+    const float ex = (pr.uvx - x) - __ldg(fl + 2 * j), ey = (pr.uvy - y) - __ldg(fl + 2 * j + 1);
+    const float w = wt ? weight_of(__ldg(wt + j), wsens) : 1.f;
+    const float a = ex * w, b = ey * w;
+    if (!BWD) {
+      acc[0] += fabsf(a) + fabsf(b);
+    } else {
+      const float da = (a > 0.f ? ge : (a < 0.f ? -ge : 0.f)), db = (b > 0.f ? ge : (b < 0.f ? -ge : 0.f));
+      float dX0, dX1, dX2, u0 = 0, u1 = 0, u2 = 0, u3 = 0;
+      project_point_adj(pr, X0, X1, X2, ka, da * w, db * w, dX0, dX1, dX2, u0, u1, u2, u3);
+      acc[0] += dX0 * p0; acc[1] += dX0 * p1; acc[2] += dX0 * p2; acc[3] += dX0;
+      acc[4] += dX1 * p0; acc[5] += dX1 * p1; acc[6] += dX1 * p2; acc[7] += dX1;
+      acc[8] += dX2 * p0; acc[9] += dX2 * p1; acc[10] += dX2 * p2; acc[11] += dX2;
+      const float dp0 = T.r[0] * dX0 + T.r[3] * dX1 + T.r[6] * dX2;
+      const float dp1 = T.r[1] * dX0 + T.r[4] * dX1 + T.r[7] * dX2;
+      const float dp2 = T.r[2] * dX0 + T.r[5] * dX1 + T.r[8] * dX2;
+      red_add(gd1 + j, dp0 * rx + dp1 * ry + dp2);
+      if (gw) {
+        float dw = da * ex + db * ey;
+        if (wsens != 0.f) dw *= wsens * w * (1.0f - w);
+        red_add(gw + j, dw);
+      }
+    }
+  }
+  if (!BWD) block_accumulate<1>(acc, acc_out + (size_t)item * kSweepAcc, smem);
+  else block_accumulate<12>(acc, acc_out + (size_t)item * kSweepAcc + 1, smem);
+}
+
+__global__ void k_sweep_out(const double* __restrict__ acc, float* __restrict__ out, int items, int off,
+                            int count) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= items * count) return;
+  const int item = t / count, k = t - item * count;
+  out[t] = (float)acc[(size_t)item * kSweepAcc + off + k];
+}
+
+// softmin((err - min) * 10) over the candidates -> focal estimate (intrinsics_softmin.py:126-139),
+// one block per batch element.  Writes the weights and f_hat = sum_n softmin_n f_n.
+__global__ void k_softmin_focal(const float* __restrict__ err, const float* __restrict__ cand_f, int n,
+                                float* __restrict__ sm_out, float* __restrict__ f_hat) {
+  const int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  float mn = err[b * n];
+  for (int i = 1; i < n; ++i) mn = fminf(mn, err[b * n + i]);
+  double z = 0.0, f = 0.0;
+  for (int i = 0; i < n; ++i) z += exp(-(double)((err[b * n + i] - mn) * 10.0f));
+  for (int i = 0; i < n; ++i) {
+    const double sm = exp(-(double)((err[b * n + i] - mn) * 10.0f)) / z;
+    sm_out[b * n + i] = (float)sm;
+    f += sm * (double)cand_f[i];
+  }
+  f_hat[b] = (float)f;
+}
+
+// d f_hat / d err_m = -10 sm_m (f_m - f_hat)   (softmin is shift invariant: the min drops out)
+__global__ void k_softmin_focal_bwd(const float* __restrict__ sm, const float* __restrict__ cand_f,
+                                    const float* __restrict__ f_hat, const float* __restrict__ g_f_hat, int n,
+                                    int B, float* __restrict__ g_err) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * n) return;
+  const int b = t / n, i = t - b * n;
+  g_err[t] = -10.0f * sm[t] * (cand_f[i] - f_hat[b]) * g_f_hat[b];
+}
+
 // ================================================================== fused overfit step helpers
 // focal_lengths_to_intrinsics (intrinsics/common.py:6-20) for a shared focal length, as k4 rows.
 __global__ void k_k4_from_focal(const float* __restrict__ focal, float* __restrict__ k4, int BF, int H, int W) {
@@ -1013,7 +1144,7 @@ bool bad_dims(int B, int F, int H, int W) { return B < 1 || F < 2 || H < 1 || W 
 // =================================================================== C ABI
 extern "C" {
 
-int fm_version(void) { return 100; }
+int fm_version(void) { return 101; }
 unsigned long long fm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 const char* fm_last_error(void) { return g_err; }
 
@@ -1067,7 +1198,8 @@ int fm_reproject(const float* xyz, const float* rt, const float* k4, float* xy, 
 static int procrustes_fwd_impl(const float* depth, const float* k4, const float* backward_flow,
                                const float* weights, float wsens, const int64_t* indices,
                                int num_indices, float* rt, void* ws, int B, int F, int H, int W,
-                               void* stream) {
+                               void* stream, const PairLayout* layout = nullptr) {
+  const PairLayout lay = layout ? *layout : dense_layout(F, H, W);
   if (!depth || !k4 || !backward_flow || !rt || !ws || bad_dims(B, F, H, W))
     return fail_msg("fm_procrustes_fwd: bad arguments");
   if (indices && num_indices < 1) return fail_msg("fm_procrustes_fwd: empty index set");
@@ -1078,16 +1210,16 @@ static int procrustes_fwd_impl(const float* depth, const float* k4, const float*
   if (e != cudaSuccess) return fail("fm_procrustes_fwd: memset", e);
   if (indices) {
     dim3 grid(blocks_for(num_indices, 1), BP);
-    k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.moments, wsens, F, H, W);
+    k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.moments, wsens, lay, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
-    k_moments<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, F, H, W);
+    k_moments<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, lay, H, W);
   } else {
     dim3 grid(blocks_for(H * W, 1), BP);
-    k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, F, H, W);
+    k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, lay, H, W);
   }
   FM_CHECK_LAUNCH("fm_procrustes_fwd: k_moments");
-  k_solve<<<(BP + 63) / 64, 64, 0, s>>>(w.moments, depth, rt, w.state, BP, F, H, W);
+  k_solve<<<(BP + 63) / 64, 64, 0, s>>>(w.moments, depth, rt, w.state, BP, lay, H, W);
   FM_CHECK_LAUNCH("fm_procrustes_fwd: k_solve");
   return 0;
 }
@@ -1103,7 +1235,9 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
                                const float* weights, float wsens, const int64_t* indices,
                                int num_indices, const float* g_rt, int include_flow_loss,
                                const float* flow_scale, float* g_depth, float* g_weights, float* g_k4,
-                               void* ws, int B, int F, int H, int W, void* stream) {
+                               void* ws, int B, int F, int H, int W, void* stream,
+                               const PairLayout* layout = nullptr) {
+  const PairLayout lay = layout ? *layout : dense_layout(F, H, W);
   if (!depth || !k4 || !backward_flow || !g_depth || !g_k4 || !ws || bad_dims(B, F, H, W))
     return fail_msg("fm_procrustes_bwd: bad arguments");
   if (!g_rt && !include_flow_loss) return fail_msg("fm_procrustes_bwd: no pose gradient given");
@@ -1121,13 +1255,13 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
   FM_CHECK_LAUNCH("fm_procrustes_bwd: k_adjoint");
   if (indices) {
     dim3 grid(blocks_for(num_indices, 1), BP);
-    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, F, H, W);
+    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
-    k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, F, H, W);
+    k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, H, W);
   } else {
     dim3 grid(blocks_for(H * W, 1), BP);
-    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, F, H, W);
+    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, H, W);
   }
   FM_CHECK_LAUNCH("fm_procrustes_bwd: k_distribute");
   k_k4_finalize<<<(BF + 127) / 128, 128, 0, s>>>(w.k4acc, w.flowacc, include_flow_loss, flow_scale, g_k4, B, F);
@@ -1292,6 +1426,96 @@ int fm_track_loss_bwd(const float* depth, const float* k4, const float* extrinsi
   return 0;
 }
 
+size_t fm_softmin_workspace_bytes(int B, int num_candidates) {
+  if (B < 1 || num_candidates < 1) return 0;
+  const size_t items = (size_t)B * num_candidates;
+  return align_up(carve(nullptr, (int)items, 2).bytes, 256) + align_up(items * (12 + 8) * sizeof(float), 256);
+}
+
+namespace {
+PairLayout sweep_layout(int F, int H, int W, int cand) {
+  PairLayout l = dense_layout(F, H, W);  // strides of the REAL tensors
+  l.F = 2;                               // the sweep only sees frames 0 and 1 (pair 0)
+  l.cand = cand;
+  return l;
+}
+}  // namespace
+
+int fm_softmin_sweep_fwd(const float* depth, const float* weights, float weight_sensitivity,
+                         const float* backward_flow, const int64_t* indices, int num_indices,
+                         const float* cand_k4, int num_candidates, float* err, float* rt, void* ws, int B,
+                         int F, int H, int W, void* stream) {
+  if (!depth || !backward_flow || !indices || num_indices < 1 || !cand_k4 || num_candidates < 1 ||
+      !err || !rt || !ws || bad_dims(B, F, H, W))
+    return fail_msg("fm_softmin_sweep_fwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int items = B * num_candidates;
+  const PairLayout lay = sweep_layout(F, H, W, num_candidates);
+  int rc = procrustes_fwd_impl(depth, cand_k4, backward_flow, weights, weight_sensitivity, indices,
+                               num_indices, rt, ws, items, 2, H, W, stream, &lay);
+  if (rc) return rc;
+  Workspace w = carve(ws, items, 2);
+  cudaError_t e = cudaMemsetAsync(w.flowacc, 0, (size_t)items * kSweepAcc * sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_softmin_sweep_fwd: memset", e);
+  dim3 grid(blocks_for(num_indices, 1), items);
+  k_sweep<false><<<grid, kThreads, 0, s>>>(depth, cand_k4, rt, backward_flow, weights, weight_sensitivity,
+                                          indices, num_indices, nullptr, w.flowacc, nullptr, nullptr, lay,
+                                          H, W);
+  FM_CHECK_LAUNCH("fm_softmin_sweep_fwd: k_sweep");
+  k_sweep_out<<<(items + 127) / 128, 128, 0, s>>>(w.flowacc, err, items, 0, 1);
+  FM_CHECK_LAUNCH("fm_softmin_sweep_fwd: k_sweep_out");
+  return 0;
+}
+
+int fm_softmin_sweep_bwd(const float* depth, const float* weights, float weight_sensitivity,
+                         const float* backward_flow, const int64_t* indices, int num_indices,
+                         const float* cand_k4, int num_candidates, const float* rt, const float* g_err,
+                         float* g_depth, float* g_weights, void* ws, int B, int F, int H, int W,
+                         void* stream) {
+  if (!depth || !backward_flow || !indices || num_indices < 1 || !cand_k4 || num_candidates < 1 || !rt ||
+      !g_err || !g_depth || !ws || bad_dims(B, F, H, W))
+    return fail_msg("fm_softmin_sweep_bwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int items = B * num_candidates;
+  const PairLayout lay = sweep_layout(F, H, W, num_candidates);
+  Workspace w = carve(ws, items, 2);
+  float* scratch = (float*)((char*)ws + align_up(w.bytes, 256));
+  float* g_rt = scratch;
+  float* g_k4 = scratch + (size_t)items * 12;
+  cudaError_t e = cudaMemsetAsync(w.flowacc, 0, (size_t)items * kSweepAcc * sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_softmin_sweep_bwd: memset", e);
+  dim3 grid(blocks_for(num_indices, 1), items);
+  k_sweep<true><<<grid, kThreads, 0, s>>>(depth, cand_k4, rt, backward_flow, weights, weight_sensitivity,
+                                         indices, num_indices, g_err, w.flowacc, g_depth, g_weights, lay, H,
+                                         W);
+  FM_CHECK_LAUNCH("fm_softmin_sweep_bwd: k_sweep");
+  k_sweep_out<<<(items * 12 + 127) / 128, 128, 0, s>>>(w.flowacc, g_rt, items, 1, 12);
+  FM_CHECK_LAUNCH("fm_softmin_sweep_bwd: k_sweep_out");
+  return procrustes_bwd_impl(depth, cand_k4, backward_flow, weights, weight_sensitivity, indices,
+                             num_indices, g_rt, 0, nullptr, g_depth, g_weights, g_k4, ws, items, 2, H, W,
+                             stream, &lay);
+}
+
+int fm_softmin_focal(const float* err, const float* cand_focal, int num_candidates, int B, float* softmin,
+                     float* focal, void* stream) {
+  if (!err || !cand_focal || !softmin || !focal || B < 1 || num_candidates < 1)
+    return fail_msg("fm_softmin_focal: bad arguments");
+  k_softmin_focal<<<B, 32, 0, (cudaStream_t)stream>>>(err, cand_focal, num_candidates, softmin, focal);
+  FM_CHECK_LAUNCH("fm_softmin_focal");
+  return 0;
+}
+
+int fm_softmin_focal_bwd(const float* softmin, const float* cand_focal, const float* focal,
+                         const float* g_focal, int num_candidates, int B, float* g_err, void* stream) {
+  if (!softmin || !cand_focal || !focal || !g_focal || !g_err || B < 1 || num_candidates < 1)
+    return fail_msg("fm_softmin_focal_bwd: bad arguments");
+  const int n = B * num_candidates;
+  k_softmin_focal_bwd<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(softmin, cand_focal, focal, g_focal,
+                                                                        num_candidates, B, g_err);
+  FM_CHECK_LAUNCH("fm_softmin_focal_bwd");
+  return 0;
+}
+
 int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
   if (!a || !a->depth || !a->fflow || !a->bflow || !a->fmask || !a->bmask || !a->mask_sum ||
       !a->g_depth || !a->rt || !a->loss || !a->ws || !a->k4 || bad_dims(1, a->F, a->H, a->W))
@@ -1368,7 +1592,7 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
       k_focal_grad<<<1, 256, 0, s>>>(w.k4acc, w.flowacc, track_g_k4, a->g_focal, 1, F, H, W);
       FM_CHECK_LAUNCH("fm_overfit_step: k_focal_grad");
       if ((rc = fm_adam_step(a->focal, a->g_focal, a->m_focal, a->v_focal, 1, a->lr, a->beta1, a->beta2,
-                             a->eps, a->step, stream)))
+                             a->eps, a->focal_step > 0 ? a->focal_step : a->step, stream)))
         return rc;
     }
   } else if (a->focal) {

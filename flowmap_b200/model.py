@@ -122,7 +122,47 @@ class IntrinsicsSoftminCfg:
     regression: Optional[RegressionCfg]
 
 
-INTRINSICS = {"ground_truth": IntrinsicsGroundTruth, "regressed": IntrinsicsRegressed}
+class IntrinsicsSoftmin(nn.Module):
+    """flowmap/model/intrinsics/intrinsics_softmin.py:40-141.  First stage: candidate sweep on
+    the first frame pair -> softmin-weighted focal length (the weighted sum of candidate
+    matrices equals K(sum softmin_n f_n)); after `regression.after_step` steps a
+    regressed focal length seeded with the mean of the last `window` estimates."""
+
+    def __init__(self, cfg: IntrinsicsSoftminCfg):
+        super().__init__()
+        self.cfg = cfg
+        self.register_buffer("focal_length_candidates",
+                             torch.linspace(cfg.min_focal_length, cfg.max_focal_length,
+                                            cfg.num_candidates), persistent=False)
+        if cfg.regression is not None:
+            self.intrinsics_regressed = IntrinsicsRegressed(IntrinsicsRegressedCfg("regressed", 0.0))
+            self.window = []
+        self.injected_indices = None  # tests: same point set as the oracle (SURVEY A.8 item 1)
+
+    def forward(self, batch, flows, backbone_output, global_step) -> Tensor:
+        b, f, _, h, w = batch.videos.shape
+        c = self.cfg
+        if c.regression is not None and global_step >= c.regression.after_step:
+            if global_step == c.regression.after_step:
+                self.intrinsics_regressed.focal_length.data = torch.stack(self.window).mean()
+            return self.intrinsics_regressed(batch, flows, backbone_output, global_step)
+        device = backbone_output.depths.device
+        indices = self.injected_indices
+        if indices is None:
+            indices = torch.randperm(h * w, device=device)[:c.num_procrustes_points]
+        err = ops.softmin_errors(backbone_output.depths, backbone_output.weights, flows.backward,
+                                 indices, self.focal_length_candidates)
+        weights = torch.softmax(-(err - err.min(dim=1, keepdim=True).values) * 10, dim=1)
+        focal = (weights * self.focal_length_candidates).sum(dim=1)  # (b,)
+        if c.regression is not None:
+            start = c.regression.after_step - c.regression.window
+            if global_step >= start and self.training:
+                self.window.append(focal.sum().detach())
+        return focal_lengths_to_intrinsics(focal, (h, w))[:, None].expand(b, f, 3, 3)
+
+
+INTRINSICS = {"ground_truth": IntrinsicsGroundTruth, "regressed": IntrinsicsRegressed,
+              "softmin": IntrinsicsSoftmin}
 
 
 def get_intrinsics(cfg):

@@ -305,3 +305,58 @@ class _TrackLoss(torch.autograd.Function):
 def track_loss(depths, extrinsics, k4, packed: PackedTracks, mapping="huber", delta=0.01,
                weight=1.0) -> Tensor:
     return _TrackLoss.apply(depths, extrinsics, k4, packed, mapping, delta, weight)
+
+
+def candidate_k4(candidates: Tensor, h: int, w: int, batch: int) -> Tensor:
+    """k4 rows (batch * n, 2, 4) of the candidate focal lengths (intrinsics/common.py:6-20)."""
+    scaled = candidates.float() * (h * w) ** 0.5
+    half = torch.full_like(scaled, 0.5)
+    k = torch.stack((scaled / w, scaled / h, half, half), dim=-1)  # (n, 4)
+    return k[None, :, None, :].expand(batch, -1, 2, -1).reshape(-1, 2, 4).contiguous()
+
+
+class _SoftminErrors(torch.autograd.Function):
+    """Per-candidate flow error of the focal-length sweep, (B, n).
+
+    flowmap/model/intrinsics/intrinsics_softmin.py:84-125."""
+
+    @staticmethod
+    def forward(ctx, depths, weights, backward_flows, indices, cand_k4, n):
+        depths, backward_flows = _canon(depths, "depths"), _canon(backward_flows, "backward_flows")
+        weights = None if weights is None else _canon(weights, "weights")
+        indices = _canon(indices, "indices", torch.int64)
+        cand_k4 = _canon(cand_k4, "cand_k4")
+        B, F, H, W = depths.shape
+        dev = depths.device
+        ws = torch.empty(lib().fm_softmin_workspace_bytes(B, n), dtype=torch.uint8, device=dev)
+        err = torch.empty((B, n), dtype=torch.float32, device=dev)
+        rt = torch.empty((B * n, 3, 4), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().fm_softmin_sweep_fwd(_ptr(depths), _ptr(weights), 0.0, _ptr(backward_flows),
+                                             _ptr(indices), indices.numel(), _ptr(cand_k4), n,
+                                             _ptr(err), _ptr(rt), _ptr(ws), B, F, H, W, _stream()),
+                  "fm_softmin_sweep_fwd")
+        ctx.save_for_backward(depths, weights, backward_flows, indices, cand_k4, rt, ws)
+        ctx.n = n
+        return err
+
+    @staticmethod
+    def backward(ctx, g_err):
+        depths, weights, backward_flows, indices, cand_k4, rt, ws = ctx.saved_tensors
+        B, F, H, W = depths.shape
+        g_err = _canon(g_err, "g_err")
+        g_depth = torch.zeros_like(depths)
+        g_weights = None if weights is None else torch.zeros_like(weights)
+        with torch.cuda.device(depths.device):
+            check(lib().fm_softmin_sweep_bwd(_ptr(depths), _ptr(weights), 0.0, _ptr(backward_flows),
+                                             _ptr(indices), indices.numel(), _ptr(cand_k4), ctx.n,
+                                             _ptr(rt), _ptr(g_err), _ptr(g_depth), _ptr(g_weights),
+                                             _ptr(ws), B, F, H, W, _stream()), "fm_softmin_sweep_bwd")
+        return g_depth, g_weights, None, None, None, None
+
+
+def softmin_errors(depths, weights, backward_flows, indices, candidates) -> Tensor:
+    b, _, h, w = depths.shape
+    n = candidates.numel()
+    return _SoftminErrors.apply(depths, weights, backward_flows, indices,
+                                candidate_k4(candidates, h, w, b), n)

@@ -78,7 +78,7 @@ class FusedAdam:
     def __init__(self, params, lr: float, betas=(0.9, 0.999), eps: float = 1e-8):
         self.params = [p for p in params]
         self.lr, self.betas, self.eps = lr, betas, eps
-        self.step_count = 0
+        self.steps = [0 for _ in self.params]  # torch keeps one step counter per parameter
         self.state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in self.params]
 
     def zero_grad(self):
@@ -87,11 +87,11 @@ class FusedAdam:
 
     @torch.no_grad()
     def step(self):
-        self.step_count += 1
-        for p, (m, v) in zip(self.params, self.state):
-            if p.grad is None:
+        for i, (p, (m, v)) in enumerate(zip(self.params, self.state)):
+            if p.grad is None:  # torch.optim skips parameters that did not receive a gradient
                 continue
-            ops.adam_step(p.data, p.grad.contiguous(), m, v, self.step_count, self.lr, self.betas,
+            self.steps[i] += 1
+            ops.adam_step(p.data, p.grad.contiguous(), m, v, self.steps[i], self.lr, self.betas,
                           self.eps)
 
 
@@ -133,15 +133,31 @@ class FusedOverfitter(Overfitter):
 
     def __init__(self, cfg: OverfitCfg, batch: Batch, flows: Flows, tracks=None, device="cuda"):
         super().__init__(cfg, batch, flows, tracks, device)
-        if cfg.intrinsics != "regressed":
-            raise NotImplementedError("FusedOverfitter: regressed intrinsics only (so far)")
         from ._lib import OverfitStepArgs, PackedTracksC, lib
         import ctypes
         dev = self.flows.forward.device
         _, f, _, h, w = batch.videos.shape
         bb = self.model.backbone
         self._depth, self._wlog = bb.depth.data, bb.weights.data
-        self._focal = self.model.intrinsics.focal_length.data
+        self._softmin = cfg.intrinsics == "softmin"
+        if self._softmin:
+            intr = self.model.intrinsics
+            self._focal = (intr.intrinsics_regressed.focal_length.data if cfg.regression_after
+                           is not None else torch.zeros((), device=dev))
+            n = cfg.softmin_candidates
+            self._cand_f = intr.focal_length_candidates.float().contiguous()
+            self._cand_k4 = ops.candidate_k4(self._cand_f, h, w, 1)
+            self._sw_err = torch.empty(1, n, device=dev)
+            self._sw_sm = torch.empty(1, n, device=dev)
+            self._sw_gerr = torch.empty(1, n, device=dev)
+            self._sw_rt = torch.empty(n, 3, 4, device=dev)
+            self._sw_focal = torch.zeros(1, device=dev)
+            self._sw_ws = torch.empty(lib().fm_softmin_workspace_bytes(1, n), dtype=torch.uint8,
+                                      device=dev)
+            self.window = []
+            self.injected_indices = None
+        else:
+            self._focal = self.model.intrinsics.focal_length.data
         z = lambda t: torch.zeros_like(t)  # noqa: E731
         self._state = [z(self._depth), z(self._depth), z(self._wlog), z(self._wlog),
                        z(self._focal), z(self._focal)]
@@ -192,6 +208,53 @@ class FusedOverfitter(Overfitter):
         self._args, self._ctypes = a, ctypes
         self._lib = lib()
 
+    def _softmin_stage(self) -> bool:
+        c = self.cfg
+        return self._softmin and not (c.regression_after is not None and
+                                      self.global_step >= c.regression_after)
+
+    def _step_softmin(self, update: bool):
+        """Sweep stage (intrinsics_softmin.py:84-141): focal estimate from the candidate sweep,
+        the step itself with that focal length, the sweep's backward, then Adam."""
+        from ._lib import check
+        c, a, L = self.cfg, self._args, self._lib
+        _, f, _, h, w = self.batch.videos.shape
+        dev = self.rt.device
+        st = torch.cuda.current_stream().cuda_stream
+        P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        idx = self.injected_indices
+        if idx is None:
+            idx = torch.randperm(h * w, device=dev)[:c.softmin_points]
+        idx = idx.contiguous()
+        n = c.softmin_candidates
+        wl = P(self._wlog) if c.use_correspondence_weights else None
+        sens = c.weight_sensitivity if c.use_correspondence_weights else 0.0
+        with torch.cuda.device(dev):
+            check(L.fm_softmin_sweep_fwd(P(self._depth), wl, sens, P(self.flows.backward), P(idx),
+                                         idx.numel(), P(self._cand_k4), n, P(self._sw_err),
+                                         P(self._sw_rt), P(self._sw_ws), 1, f, h, w, st),
+                  "fm_softmin_sweep_fwd")
+            check(L.fm_softmin_focal(P(self._sw_err), P(self._cand_f), n, 1, P(self._sw_sm),
+                                     P(self._sw_focal), st), "fm_softmin_focal")
+            a.focal, a.step = P(self._sw_focal), 0
+            check(L.fm_overfit_step(self._ctypes.byref(a), st), "fm_overfit_step")
+            check(L.fm_softmin_focal_bwd(P(self._sw_sm), P(self._cand_f), P(self._sw_focal),
+                                         P(self._g_focal), n, 1, P(self._sw_gerr), st),
+                  "fm_softmin_focal_bwd")
+            check(L.fm_softmin_sweep_bwd(P(self._depth), wl, sens, P(self.flows.backward), P(idx),
+                                         idx.numel(), P(self._cand_k4), n, P(self._sw_rt),
+                                         P(self._sw_gerr), P(self._g_depth),
+                                         P(self._g_w) if wl else None, P(self._sw_ws), 1, f, h, w, st),
+                  "fm_softmin_sweep_bwd")
+        if update:
+            s_ = self.global_step + 1
+            ops.adam_step(self._depth, self._g_depth, self._state[0], self._state[1], s_, c.lr)
+            if c.use_correspondence_weights:
+                ops.adam_step(self._wlog, self._g_w, self._state[2], self._state[3], s_, c.lr)
+            if c.regression_after is not None and \
+                    self.global_step >= c.regression_after - c.regression_window:
+                self.window.append(self._sw_focal[0].clone())
+
     def training_step(self, update: bool = True):
         """Returns (total loss (device tensor), relative poses rt (1, F-1, 3, 4))."""
         from ._lib import check
@@ -204,11 +267,19 @@ class FusedOverfitter(Overfitter):
         track_on = c.use_tracking and self.global_step >= c.tracking_enable_after
         a.tracks = self._ctypes.pointer(self._pk_c) if track_on else None
         a.flow_weight = c.flow_weight if self.global_step >= c.flow_enable_after else 0.0
-        a.step = self.global_step + 1 if update else 0
-        with torch.cuda.device(self.rt.device):
-            check(self._lib.fm_overfit_step(self._ctypes.byref(a),
-                                            torch.cuda.current_stream().cuda_stream),
-                  "fm_overfit_step")
+        if self._softmin_stage():
+            self._step_softmin(update)
+        else:
+            a.focal = self._focal.data_ptr()
+            a.step = self.global_step + 1 if update else 0
+            if self._softmin:  # hand-over: seed the regressed focal length once, own Adam clock
+                if self.global_step == c.regression_after and update:
+                    self._focal.copy_(torch.stack(self.window).mean())
+                a.focal_step = self.global_step - c.regression_after + 1 if update else 0
+            with torch.cuda.device(self.rt.device):
+                check(self._lib.fm_overfit_step(self._ctypes.byref(a),
+                                                torch.cuda.current_stream().cuda_stream),
+                      "fm_overfit_step")
         if update:
             self.global_step += 1
         total = self._loss + self._track_loss if track_on else self._loss.clone()
@@ -220,6 +291,10 @@ class FusedOverfitter(Overfitter):
 
     def gradients(self):
         return {"depth": self._g_depth, "weights": self._g_w, "focal": self._g_focal}
+
+    def intrinsics_k4(self) -> Tensor:
+        """(F, 4) = (fx, fy, cx, cy) used by the last step."""
+        return self._k4
 
 
 class ShardedFusedOverfitter(FusedOverfitter):

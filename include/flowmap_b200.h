@@ -133,6 +133,31 @@ int fm_track_loss_bwd(const float* depth, const float* k4, const float* extrinsi
 int fm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count,
                  double lr, double beta1, double beta2, double eps, int step, void* stream);
 
+/* intrinsics_softmin.py:84-131, the candidate sweep on the first frame pair.  For each of
+ * the num_candidates intrinsics in cand_k4 (B*num_candidates, 2, 4: one k4 row per virtual
+ * frame) run Procrustes at the `indices` points (depth frames 0/1, backward flow and weights
+ * of pair 0 are SHARED by all candidates: no (n,2,H,W,3) temporary) and sum the weighted
+ * backward-flow error err (B, num_candidates) = sum |(uv - xy - flow) * w|.  rt (B*n, 3, 4)
+ * receives the per-candidate poses (needed by the backward).  The backward takes d/d err
+ * and ACCUMULATES into g_depth (B,F,H,W) and g_weights (B,F-1,H,W) (frames 0/1, pair 0).
+ * weights may be stored as logits (weight_sensitivity != 0), see fm_overfit_step. */
+size_t fm_softmin_workspace_bytes(int B, int num_candidates);
+int fm_softmin_sweep_fwd(const float* depth, const float* weights, float weight_sensitivity,
+                         const float* backward_flow, const int64_t* indices, int num_indices,
+                         const float* cand_k4, int num_candidates, float* err, float* rt, void* ws, int B,
+                         int F, int H, int W, void* stream);
+int fm_softmin_sweep_bwd(const float* depth, const float* weights, float weight_sensitivity,
+                         const float* backward_flow, const int64_t* indices, int num_indices,
+                         const float* cand_k4, int num_candidates, const float* rt, const float* g_err,
+                         float* g_depth, float* g_weights, void* ws, int B, int F, int H, int W,
+                         void* stream);
+/* intrinsics_softmin.py:126-139: softmin((err - min) * 10) over the candidates and the focal
+ * estimate f_hat (B) = sum softmin_n * cand_focal_n; and d f_hat / d err for the backward. */
+int fm_softmin_focal(const float* err, const float* cand_focal, int num_candidates, int B, float* softmin,
+                     float* focal, void* stream);
+int fm_softmin_focal_bwd(const float* softmin, const float* cand_focal, const float* focal,
+                         const float* g_focal, int num_candidates, int B, float* g_err, void* stream);
+
 /* Packed tracks (see fm_track_loss_fwd), device pointers. */
 typedef struct {
   const int* segments;
@@ -176,6 +201,9 @@ typedef struct {
   float *rt, *loss;             /* outputs: (F-1,3,4) poses, flow loss             */
   float *extrinsics, *g_extrinsics, *g_rt, *track_g_k4, *track_loss; /* tracking only */
   void *ws, *track_ws;
+  int focal_step;               /* Adam step number of the focal parameter (0: same as step);
+                                   differs after the softmin -> regressed hand-over, where the
+                                   focal length first receives a gradient at step after_step */
 } fm_overfit_step_args;
 int fm_overfit_step(const fm_overfit_step_args* args, void* stream);
 

@@ -302,3 +302,82 @@ def test_fused_step_with_tracking_matches_golden():
     assert rel_l2(gr["depth"].cpu(), g64["g_depth"]) <= max(1e-4, 3 * rel_l2(g32["g_depth"], g64["g_depth"]))
     assert rel_l2(gr["weights"].cpu(), g64["g_wparam"]) <= max(1e-4, 3 * rel_l2(g32["g_wparam"], g64["g_wparam"]))
     assert abs(float(gr["focal"]) - float(g64["g_focal"])) <= 1e-4 * abs(float(g64["g_focal"]))
+
+
+def test_softmin_intrinsics_matches_reference_golden():
+    """IntrinsicsSoftmin (60-candidate sweep, injected point indices) + flow loss: loss, K,
+    poses and the gradients that flow through the sweep into depth[:2] / weights[:1]."""
+    g64, g32 = load_golden("softmin", True), load_golden("softmin", False)
+    o = _setup(g64, cfg_kw=dict(intrinsics="softmin", softmin_points=300, regression_after=None))
+    o.model.intrinsics.injected_indices = T(g64["indices"]).cuda()
+    out = o.model(o.batch, o.flows, 0)
+    loss = o.losses[0].forward(o.batch, o.flows, None, out, 0)
+    loss.backward()
+    assert abs(float(loss) - float(g64["loss"])) <= 1e-4 * abs(float(g64["loss"]))
+    assert max_abs(out.intrinsics.cpu(), g64["intrinsics"]) <= 1e-5
+    assert max_abs(out.extrinsics.cpu(), g64["extrinsics"]) <= 1e-5
+    gd, gw = o.model.backbone.depth.grad.cpu(), o.model.backbone.weights.grad.cpu()
+    assert rel_l2(gd, g64["g_depth"]) <= max(1e-4, 3 * rel_l2(g32["g_depth"], g64["g_depth"]))
+    assert rel_l2(gw, g64["g_wparam"]) <= max(1e-4, 3 * rel_l2(g32["g_wparam"], g64["g_wparam"]))
+    # the part that exists only because of the sweep: gradient on pair 0's weights / frames 0-1
+    assert rel_l2(gw[:1], g64["g_wparam"][:1]) <= max(1e-4, 3 * rel_l2(g32["g_wparam"][:1], g64["g_wparam"][:1]))
+    assert rel_l2(gd[:2], g64["g_depth"][:2]) <= max(1e-4, 3 * rel_l2(g32["g_depth"][:2], g64["g_depth"][:2]))
+
+
+def test_fused_softmin_step_matches_reference_golden():
+    from flowmap_b200.overfit import FusedOverfitter, OverfitCfg
+    from flowmap_b200.types import Batch, Flows
+    g64, g32 = load_golden("softmin", True), load_golden("softmin", False)
+    f, h, w = g64["in_depth"].shape
+    batch = Batch(torch.zeros(1, f, 3, h, w), torch.arange(f)[None], ["s"], ["d"])
+    flows = Flows(*(T(g64[k]).float() for k in ("in_fwd", "in_bwd", "in_fmask", "in_bmask")))
+    o = FusedOverfitter(OverfitCfg(intrinsics="softmin", softmin_points=300, regression_after=None),
+                        batch, flows)
+    o.injected_indices = T(g64["indices"]).cuda()
+    with torch.no_grad():
+        o.model.backbone.depth.copy_(T(g64["in_depth"]).float())
+        o.model.backbone.weights.copy_(T(g64["in_wparam"]).float())
+    loss, _ = o.training_step(update=False)
+    gr = o.gradients()
+    assert abs(float(loss) - float(g64["loss"])) <= 1e-4 * abs(float(g64["loss"]))
+    k4 = o.intrinsics_k4().cpu()
+    assert abs(float(k4[0, 0]) - g64["intrinsics"][0, 0, 0, 0]) <= 1e-5
+    assert abs(float(k4[0, 1]) - g64["intrinsics"][0, 0, 1, 1]) <= 1e-5
+    assert max_abs(o.extrinsics().cpu(), g64["extrinsics"]) <= 1e-5
+    assert rel_l2(gr["depth"].cpu(), g64["g_depth"]) <= max(1e-4, 3 * rel_l2(g32["g_depth"], g64["g_depth"]))
+    assert rel_l2(gr["weights"].cpu(), g64["g_wparam"]) <= max(1e-4, 3 * rel_l2(g32["g_wparam"], g64["g_wparam"]))
+
+
+def test_softmin_to_regressed_handover():
+    """intrinsics_softmin.py:75-82,133-139: after `after_step` steps the focal length becomes a
+    parameter seeded with the mean of the last `window` sweep estimates (autograd path vs the
+    fused path vs the oracle, short schedule)."""
+    from oracle import flowmap_oracle as O
+    from flowmap_b200.overfit import FusedOverfitter, OverfitCfg, Overfitter
+    from flowmap_b200.types import Batch, Flows
+    g64 = load_golden("softmin", True)
+    f, h, w = g64["in_depth"].shape
+    kw = dict(intrinsics="softmin", softmin_points=300, regression_after=4, regression_window=2)
+    st = O.OverfitOracle(O.OverfitConfig(**kw), f, h, w, dtype=torch.float64)
+    with torch.no_grad():
+        st.depth.copy_(T(g64["in_depth"]))
+        st.weights.copy_(T(g64["in_wparam"]))
+    flows64 = O.Flows(*(T(g64[k]) for k in ("in_fwd", "in_bwd", "in_fmask", "in_bmask")))
+    idx = T(g64["indices"])
+    ref = [st.training_step(flows64, softmin_indices=idx) for _ in range(7)]
+    batch = Batch(torch.zeros(1, f, 3, h, w), torch.arange(f)[None], ["s"], ["d"])
+    flows = Flows(*(T(g64[k]).float() for k in ("in_fwd", "in_bwd", "in_fmask", "in_bmask")))
+    for cls in (Overfitter, FusedOverfitter):
+        o = cls(OverfitCfg(**kw), batch, flows)
+        if cls is Overfitter:
+            o.model.intrinsics.injected_indices = idx.cuda()
+        else:
+            o.injected_indices = idx.cuda()
+        with torch.no_grad():
+            o.model.backbone.depth.copy_(T(g64["in_depth"]).float())
+            o.model.backbone.weights.copy_(T(g64["in_wparam"]).float())
+        for s in range(7):
+            total, _ = o.training_step()
+            assert abs(float(total) - ref[s]["loss"]) <= 2e-4 * abs(ref[s]["loss"]), (cls.__name__, s)
+        assert abs(float(o.model.intrinsics.intrinsics_regressed.focal_length) - float(st.focal)) <= 1e-5
+        assert rel_l2(o.model.backbone.depth.detach().cpu(), st.depth.detach()) <= 1e-5
