@@ -2,4 +2,39 @@
 optimisation hot path behind the reference's Python surface.  See DESIGN.md."""
 from .types import Batch, Flows, Tracks, BackboneOutput, ModelOutput, ModelExports  # noqa: F401
 
-__all__ = ["Batch", "Flows", "Tracks", "BackboneOutput", "ModelOutput", "ModelExports"]
+__all__ = ["Batch", "Flows", "Tracks", "BackboneOutput", "ModelOutput", "ModelExports", "install"]
+
+
+def install() -> dict:
+    """Swap the hot path of an importable reference checkout (`flowmap` on sys.path) for the
+    CUDA implementation, under the reference's own names:
+
+      * ``flowmap.model.model.Model``      -> flowmap_b200.model.Model (same cfg / forward)
+      * ``flowmap.loss.LOSSES["flow"|"tracking"]`` -> flowmap_b200.loss.LossFlow / LossTracking
+      * ``flowmap.model.intrinsics.INTRINSICS`` / ``...extrinsics.EXTRINSICS["procrustes"]``
+        entries of the pieces that exist here,
+
+    so that ``flowmap/overfit.py`` (Hydra/Lightning harness) runs unchanged.  Call it before
+    ``flowmap.overfit`` is imported.  Backbones that are outside the hot path (MiDaS) keep
+    the reference's class.  Returns what was replaced (for logging / tests)."""
+    import importlib
+
+    from . import loss as my_loss
+    from . import model as my_model
+
+    replaced = {}
+    ref_model = importlib.import_module("flowmap.model.model")
+    replaced["flowmap.model.model.Model"] = ref_model.Model
+    ref_model.Model = my_model.Model
+    ref_loss = importlib.import_module("flowmap.loss")
+    for key, cls in (("flow", my_loss.LossFlow), ("tracking", my_loss.LossTracking)):
+        replaced[f"flowmap.loss.LOSSES[{key}]"] = ref_loss.LOSSES.get(key)
+        ref_loss.LOSSES[key] = cls
+    ref_intr = importlib.import_module("flowmap.model.intrinsics")
+    for key, cls in my_model.INTRINSICS.items():
+        replaced[f"flowmap.model.intrinsics.INTRINSICS[{key}]"] = ref_intr.INTRINSICS.get(key)
+        ref_intr.INTRINSICS[key] = cls
+    ref_back = importlib.import_module("flowmap.model.backbone")
+    for key, cls in ref_back.BACKBONES.items():  # e.g. midas: produced by the reference
+        my_model.BACKBONES.setdefault(key, cls)
+    return replaced

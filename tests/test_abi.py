@@ -42,3 +42,31 @@ def test_package_does_not_import_oracle():
     code = ("import sys, flowmap_b200, flowmap_b200.model, flowmap_b200.loss, flowmap_b200.overfit;"
             "bad=[m for m in sys.modules if m.startswith('oracle')]; assert not bad, bad")
     subprocess.check_call([sys.executable, "-c", code], cwd=str(ROOT))
+
+
+def test_install_patches_reference_registries():
+    """flowmap_b200.install() against the reference checkout (build container only)."""
+    import os, sys
+    import pytest
+    if not os.path.isdir("/root/reference/flowmap"):
+        pytest.skip("reference checkout not present (GPU box)")
+    code = (
+        "import sys; sys.path.insert(0, '/root/reference'); sys.dont_write_bytecode = True\n"
+        "import flowmap_b200, flowmap.model.model as rm, flowmap.loss as rl\n"
+        "rep = flowmap_b200.install()\n"
+        "from flowmap_b200.model import Model\nfrom flowmap_b200.loss import LossFlow, LossTracking\n"
+        "assert rm.Model is Model and rl.LOSSES['flow'] is LossFlow and rl.LOSSES['tracking'] is LossTracking\n"
+        "from flowmap.model.model import ModelCfg\n"
+        "from flowmap.model.backbone.backbone_explicit_depth import BackboneExplicitDepthCfg\n"
+        "from flowmap.model.intrinsics.intrinsics_softmin import IntrinsicsSoftminCfg, RegressionCfg\n"
+        "from flowmap.model.extrinsics.extrinsics_procrustes import ExtrinsicsProcrustesCfg\n"
+        "cfg = ModelCfg(BackboneExplicitDepthCfg('explicit_depth', 0.1, 100.0), IntrinsicsSoftminCfg('softmin', 8192, 0.5, 2.0, 60, RegressionCfg(1000, 100)), ExtrinsicsProcrustesCfg('procrustes', None, False), True)\n"
+        "m = rm.Model(cfg, 4, (8, 12))\n"
+        "names = sorted(n for n, _ in m.named_parameters())\n"
+        "assert names == ['backbone.depth', 'backbone.weights', 'intrinsics.intrinsics_regressed.focal_length'], names\n"
+        "from flowmap.loss import get_losses\nfrom flowmap.loss.loss_flow import LossFlowCfg\nfrom flowmap.loss.mapping.mapping_huber import MappingHuberCfg\n"
+        "l = get_losses([LossFlowCfg(0, 1000.0, 'flow', MappingHuberCfg('huber', 0.01))])\n"
+        "assert type(l[0]) is LossFlow\n")
+    import subprocess
+    from conftest import ROOT
+    subprocess.check_call([sys.executable, "-c", code], cwd=str(ROOT))
