@@ -292,7 +292,7 @@ def run_gpu(args):
         def op_flow():
             L.fm_flow_loss_fwd_bwd(P(depths), P(k4), P(rt), P(o.flows.forward), P(o.flows.backward),
                                    P(o.flows.forward_mask), P(o.flows.backward_mask), P(msum), 0,
-                                   0.01, 1000.0, P(lossb), P(g_depth), P(g_rt), P(g_k4), P(ws), 1,
+                                   0.01, 1000.0, 1, P(lossb), P(g_depth), P(g_rt), P(g_k4), P(ws), 1,
                                    F_, H_, W_, st)
         def op_bwd():
             L.fm_procrustes_bwd(P(depths), P(k4), P(o.flows.backward), P(weights), None, 0, None, 1,

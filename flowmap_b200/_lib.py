@@ -30,7 +30,7 @@ SIGNATURES = {
     "fm_procrustes_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P, _P,
                                   c_int, c_int, c_int, c_int, _P]),
     "fm_mask_sum": (c_int, [_P, _P, _P, c_size_t, _P]),
-    "fm_flow_loss_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_float, c_float,
+    "fm_flow_loss_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_float, c_float, c_int,
                                      _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "fm_pose_chain": (c_int, [_P, _P, c_int, c_int, _P]),
     "fm_pose_chain_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),

@@ -132,7 +132,143 @@ FM_HD float flow_pixel(const FlowFrame& f, float x, float y, float D, float ffx,
 }
 
 // ---------------------------------------------------------------------------------
-// Phase D2: per-point adjoints of the Procrustes inputs.  `scatter(row_base, x0, v0, v1)` adds
+// Phase C, lean form (intrinsics are constant or one shared focal length).  Uses
+//   Y = R^T (s - t) = D * m + c,  m = R^T ray, c = -R^T t      (forward term)
+//   X = R s + t     = D * n + t,  n = R ray                    (backward term)
+// so the direct depth gradient is dY . m (+ dX . n), and the pose gradient is accumulated
+// as 6-DOF twists in the local frames (only the tangent part of dL/d[R|t] survives the
+// Procrustes adjoint): forward term  aF += Y x dY, bF += dY  (world twist =
+// -R aF, -R bF), backward term  aB += (D n) x dX, bB += dX.  With a shared focal length
+// (fx = f W'/..., fy likewise, principal point fixed) d/df needs ONE accumulator:
+//   f * dL/df = sum (du . u)_{xy}  -  D (dY . m - (R dY)_z)  -  D (dX . n - (R^T dX)_z).
+// Slots: 0 loss | 1-3 aF | 4-6 bF | 7-9 aB | 10-12 bB | 13 f * dL/df.
+// ---------------------------------------------------------------------------------
+constexpr int kFlowLeanVals = 14;
+
+struct FlowFrameLean {
+  Cam kk, kn, kp;
+  float rtF[9], cF[3], r2F[3];  // R_F^T (row-major), -R_F^T t_F, row 2 of R_F
+  float rB[9], tB[3], c2B[3];   // R_B, t_B, column 2 of R_B
+};
+
+FM_HD void fill_lean(FlowFrameLean& f, const Rt* tf, const Rt* tb) {
+  if (tf) {
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) f.rtF[i * 3 + j] = tf->r[j * 3 + i];
+      f.cF[i] = -(tf->r[0 * 3 + i] * tf->t[0] + tf->r[1 * 3 + i] * tf->t[1] + tf->r[2 * 3 + i] * tf->t[2]);
+      f.r2F[i] = tf->r[2 * 3 + i];
+    }
+  }
+  if (tb) {
+    for (int i = 0; i < 9; ++i) f.rB[i] = tb->r[i];
+    for (int i = 0; i < 3; ++i) { f.tB[i] = tb->t[i]; f.c2B[i] = tb->r[i * 3 + 2]; }
+  }
+}
+
+// Projection adjoint without the per-component intrinsics gradients; returns du . u over x, y
+// (= fx * dL/dfx + fy * dL/dfy of this projection).
+FM_HD float project_adj_lean(const Proj& p, float P0, float P1, float P2, const Cam& k, float duvx,
+                             float duvy, float& d0, float& d1, float& d2) {
+  float du0 = k.fx * duvx, du1 = k.fy * duvy, du2 = k.cx * duvx + k.cy * duvy;
+  if (!p.all_finite) {
+    if (!p.finite[0]) du0 = 0.0f;
+    if (!p.finite[1]) du1 = 0.0f;
+    if (!p.finite[2]) du2 = 0.0f;
+  }
+  d0 = du0 * p.inv;
+  d1 = du1 * p.inv;
+  d2 = (du2 - (du0 * P0 + du1 * P1 + du2 * P2) * p.inv) * p.inv;
+  return k.fx * duvx * p.u[0] + k.fy * duvy * p.u[1];
+}
+
+template <bool HASF, bool HASB, bool FOCAL>
+FM_HD float flow_pixel_lean(const FlowFrameLean& f, float x, float y, float D, float ffx, float ffy,
+                            float mf, float fbx, float fby, float mb, float g, const RobustCfg& rc,
+                            float* acc) {
+  float rx, ry;
+  ray_of(x, y, f.kk, rx, ry);
+  float gD = 0.f;
+  if (HASF) {
+    const float m0 = f.rtF[0] * rx + f.rtF[1] * ry + f.rtF[2];
+    const float m1 = f.rtF[3] * rx + f.rtF[4] * ry + f.rtF[5];
+    const float m2 = f.rtF[6] * rx + f.rtF[7] * ry + f.rtF[8];
+    const float Y0 = D * m0 + f.cF[0], Y1 = D * m1 + f.cF[1], Y2 = D * m2 + f.cF[2];
+    const Proj pr = project_point(Y0, Y1, Y2, f.kn);
+    float gx, gy;
+    const float l = robust_map((pr.uvx - x) - ffx, (pr.uvy - y) - ffy, rc, gx, gy);
+    const float wgt = g * mf;
+    acc[0] += wgt * l;
+    float d0, d1, d2;
+    const float su = project_adj_lean(pr, Y0, Y1, Y2, f.kn, wgt * gx, wgt * gy, d0, d1, d2);
+    const float gd = d0 * m0 + d1 * m1 + d2 * m2;
+    gD += gd;
+    acc[1] += Y1 * d2 - Y2 * d1;
+    acc[2] += Y2 * d0 - Y0 * d2;
+    acc[3] += Y0 * d1 - Y1 * d0;
+    acc[4] += d0; acc[5] += d1; acc[6] += d2;
+    if (FOCAL) acc[13] += su - D * (gd - (f.r2F[0] * d0 + f.r2F[1] * d1 + f.r2F[2] * d2));
+  }
+  if (HASB) {
+    const float n0 = f.rB[0] * rx + f.rB[1] * ry + f.rB[2];
+    const float n1 = f.rB[3] * rx + f.rB[4] * ry + f.rB[5];
+    const float n2 = f.rB[6] * rx + f.rB[7] * ry + f.rB[8];
+    const float e0 = D * n0, e1 = D * n1, e2 = D * n2;
+    const float X0 = e0 + f.tB[0], X1 = e1 + f.tB[1], X2 = e2 + f.tB[2];
+    const Proj pr = project_point(X0, X1, X2, f.kp);
+    float gx, gy;
+    const float l = robust_map((pr.uvx - x) - fbx, (pr.uvy - y) - fby, rc, gx, gy);
+    const float wgt = g * mb;
+    acc[0] += wgt * l;
+    float d0, d1, d2;
+    const float su = project_adj_lean(pr, X0, X1, X2, f.kp, wgt * gx, wgt * gy, d0, d1, d2);
+    const float gd = d0 * n0 + d1 * n1 + d2 * n2;
+    gD += gd;
+    acc[7] += e1 * d2 - e2 * d1;
+    acc[8] += e2 * d0 - e0 * d2;
+    acc[9] += e0 * d1 - e1 * d0;
+    acc[10] += d0; acc[11] += d1; acc[12] += d2;
+    if (FOCAL) acc[13] += su - D * (gd - (f.c2B[0] * d0 + f.c2B[1] * d1 + f.c2B[2] * d2));
+  }
+  return gD;
+}
+
+// Lean accumulators of frame `frame` -> the standard slot layout (kFlowVals) that the pose /
+// intrinsics reductions read.  rtF / rtB: [R|t] (3x4 row-major, float) of pair (frame, frame+1)
+// / (frame-1, frame) or NULL; f_of_frame: the shared focal length expressed through this
+// frame's fx (f = fx * W / sqrt(HW)); W_over_s = W / sqrt(HW).
+template <typename T>
+FM_HD void lean_to_standard(const T* lean, const float* rtF, const float* rtB, double focal,
+                            double W_over_s, bool focal_mode, T* out) {
+  for (int i = 0; i < kFlowVals; ++i) out[i] = (T)0;
+  out[0] = lean[0];
+  if (rtF) {  // world twist a = -R aF, ambient dR = 1/2 [a]x R ; slots 10-12 feed dt = -R b
+    double a[3];
+    for (int i = 0; i < 3; ++i)
+      a[i] = -((double)rtF[i * 4 + 0] * lean[1] + (double)rtF[i * 4 + 1] * lean[2] + (double)rtF[i * 4 + 2] * lean[3]);
+    for (int c = 0; c < 3; ++c) {
+      const double r0 = rtF[0 * 4 + c], r1 = rtF[1 * 4 + c], r2 = rtF[2 * 4 + c];
+      out[1 + 0 * 3 + c] = (T)(0.5 * (-a[2] * r1 + a[1] * r2));
+      out[1 + 1 * 3 + c] = (T)(0.5 * (a[2] * r0 - a[0] * r2));
+      out[1 + 2 * 3 + c] = (T)(0.5 * (-a[1] * r0 + a[0] * r1));
+    }
+    out[10] = lean[4]; out[11] = lean[5]; out[12] = lean[6];
+  }
+  if (rtB) {
+    const double a[3] = {(double)lean[7], (double)lean[8], (double)lean[9]};
+    for (int c = 0; c < 3; ++c) {
+      const double r0 = rtB[0 * 4 + c], r1 = rtB[1 * 4 + c], r2 = rtB[2 * 4 + c];
+      out[13 + 0 * 3 + c] = (T)(0.5 * (-a[2] * r1 + a[1] * r2));
+      out[13 + 1 * 3 + c] = (T)(0.5 * (a[2] * r0 - a[0] * r2));
+      out[13 + 2 * 3 + c] = (T)(0.5 * (-a[1] * r0 + a[0] * r1));
+    }
+    out[22] = lean[10]; out[23] = lean[11]; out[24] = lean[12];
+  }
+  // dL/df booked as an equivalent dL/dfx (fx = f * sqrt(HW) / W) of this frame
+  if (focal_mode) out[25] = (T)((double)lean[13] / focal * W_over_s);
+}
+
+// ---------------------------------------------------------------------------------
+// Phase D2: per-point adjoints of the Procrustes inputs.  `scatter(row, x0, v0, v1)` adds
 // v0 / v1 into the earlier frame's depth gradient at columns x0 / x0 + 1 of a row; returns the aligned later-frame depth gradient and
 // the weight gradient.  kacc[0..3] += dK_a (through q), kacc[4..7] += dK_b (through p).
 // ---------------------------------------------------------------------------------
@@ -163,10 +299,9 @@ FM_HD void distribute_point(const PairGeom& g, const PairAdjoint& ad, float x, f
   const float b01 = qb[0] * rx1 + qb[1] * ry0 + qb[2];
   const float b10 = qb[0] * rx0 + qb[1] * ry1 + qb[2];
   const float b11 = qb[0] * rx1 + qb[1] * ry1 + qb[2];
-  // one call per tap row: (row base, x0, value at x0, value at x0 + 1); a clamped x1 has weight 0
-  const int W = g.grid.W;
-  scatter(t.y0 * W, t.x0, t.w00 * b00, t.w01 * b01);
-  scatter(t.y1 * W, t.x0, t.w10 * b10, t.w11 * b11);
+  // one call per tap row: (row y, x0, value at x0, value at x0 + 1); a clamped x1 has weight 0
+  scatter(t.y0, t.x0, t.w00 * b00, t.w01 * b01);
+  scatter(t.y1, t.x0, t.w10 * b10, t.w11 * b11);
   const float qz_true = q[2] + g.z0;
   const float ea0 = qb[0] * g.ka.ifx, ea1 = qb[1] * g.ka.ify;
   kacc[0] -= ea0 * q[0];

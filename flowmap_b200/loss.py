@@ -109,7 +109,8 @@ class LossFlow(Loss):
         m = self.cfg.mapping
         return ops.flow_loss(out.depths, rt, k4, flows.forward, flows.backward,
                              flows.forward_mask, flows.backward_mask, self._mask_total(flows),
-                             m.name, getattr(m, "delta", 0.0), self.cfg.weight)
+                             m.name, getattr(m, "delta", 0.0), self.cfg.weight,
+                             getattr(out, "k_mode", "full"))
 
 
 class LossTracking(Loss):

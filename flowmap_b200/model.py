@@ -238,8 +238,10 @@ class Model(nn.Module):
         intrinsics = self.intrinsics.forward(batch, flows, backbone_out, global_step)
         k4 = ops.intrinsics_to_k4(intrinsics)
         extrinsics, rt = self.extrinsics.forward(batch, flows, backbone_out, k4)
+        k_mode = {IntrinsicsRegressed: "shared_focal", IntrinsicsSoftmin: "shared_focal",
+                  IntrinsicsGroundTruth: "const"}.get(type(self.intrinsics), "full")
         return ModelOutput(backbone_out.depths, intrinsics, extrinsics, backbone_out.weights,
-                           relative=rt, k4=k4)
+                           relative=rt, k4=k4, k_mode=k_mode)
 
     @torch.no_grad()
     def export(self, batch: Batch, flows: Flows, global_step: int) -> ModelExports:

@@ -14,6 +14,7 @@ from torch import Tensor
 from ._lib import check, lib
 
 MAPPINGS = {"huber": 0, "l1": 1, "l2": 2}
+K_MODES = {"full": 0, "shared_focal": 1, "const": 2}
 
 
 def _stream() -> int:
@@ -110,7 +111,8 @@ class _FlowLoss(torch.autograd.Function):
     flowmap/loss/loss_flow.py:31-70, loss.py:46, projection.py:116-184, loss/mapping/*."""
 
     @staticmethod
-    def forward(ctx, depths, rt, k4, fflow, bflow, fmask, bmask, msum, mapping, delta, weight):
+    def forward(ctx, depths, rt, k4, fflow, bflow, fmask, bmask, msum, mapping, delta, weight,
+                k_mode):
         depths, rt, k4 = _canon(depths, "depths"), _canon(rt, "rt"), _canon(k4, "k4")
         fflow, bflow = _canon(fflow, "flows.forward"), _canon(bflow, "flows.backward")
         fmask, bmask = _canon(fmask, "flows.forward_mask"), _canon(bmask, "flows.backward_mask")
@@ -130,7 +132,8 @@ class _FlowLoss(torch.autograd.Function):
             check(lib().fm_flow_loss_fwd_bwd(_ptr(depths), _ptr(k4), _ptr(rt), _ptr(fflow),
                                              _ptr(bflow), _ptr(fmask), _ptr(bmask), _ptr(msum),
                                              MAPPINGS[mapping], float(delta), float(weight),
-                                             _ptr(loss), _ptr(g_depth), _ptr(g_rt), _ptr(g_k4),
+                                             K_MODES[k_mode], _ptr(loss), _ptr(g_depth), _ptr(g_rt),
+                                             _ptr(g_k4),
                                              _ptr(ws), B, F, H, W, _stream()),
                   "fm_flow_loss_fwd_bwd")
         ctx.save_for_backward(g_depth, g_rt, g_k4)
@@ -139,12 +142,16 @@ class _FlowLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, go):
         g_depth, g_rt, g_k4 = ctx.saved_tensors
-        return (g_depth * go, g_rt * go, g_k4 * go) + (None,) * 8
+        return (g_depth * go, g_rt * go, g_k4 * go) + (None,) * 9
 
 
 def flow_loss(depths, rt, k4, fflow, bflow, fmask, bmask, msum, mapping="huber", delta=0.01,
-              weight=1.0) -> Tensor:
-    return _FlowLoss.apply(depths, rt, k4, fflow, bflow, fmask, bmask, msum, mapping, delta, weight)
+              weight=1.0, k_mode="full") -> Tensor:
+    """k_mode: "full" (any per-frame intrinsics), "shared_focal" (k4 derives from ONE focal
+    length with a fixed principal point: cheaper kernel, gradient routed through fx only) or
+    "const" (intrinsics receive no gradient)."""
+    return _FlowLoss.apply(depths, rt, k4, fflow, bflow, fmask, bmask, msum, mapping, delta, weight,
+                           k_mode)
 
 
 class _PoseChain(torch.autograd.Function):

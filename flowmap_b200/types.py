@@ -60,7 +60,7 @@ class ModelOutput:
     access only (by the unprojection kernel, differentiable)."""
 
     def __init__(self, depths, intrinsics, extrinsics, backward_correspondence_weights,
-                 surfaces=None, relative=None, k4=None):
+                 surfaces=None, relative=None, k4=None, k_mode="full"):
         self.depths = depths
         self.intrinsics = intrinsics
         self.extrinsics = extrinsics
@@ -68,6 +68,7 @@ class ModelOutput:
         self._surfaces = surfaces
         self.relative = relative  # (b, f-1, 3, 4) Procrustes [R|t], frame i+1 -> frame i
         self.k4 = k4  # (b, f, 4) = (fx, fy, cx, cy)
+        self.k_mode = k_mode  # how the intrinsics were produced (see ops.flow_loss)
 
     @property
     def surfaces(self) -> Tensor:

@@ -33,6 +33,10 @@ extern "C" {
 #define FM_MAP_L1 1    /* loss/mapping/mapping_l1.py:16-20    */
 #define FM_MAP_L2 2    /* loss/mapping/mapping_l2.py:16-21    */
 
+#define FM_K_FULL 0
+#define FM_K_SHARED_FOCAL 1
+#define FM_K_CONST 2
+
 int fm_version(void);
 const char* fm_last_error(void);
 /* Number of kernels this library has launched in this process (evidence for bench.py's
@@ -89,6 +93,11 @@ int fm_mask_sum(const float* forward_mask, const float* backward_mask, double* o
  * mapping/*.py, forward and analytic backward in one pass.  Uses the pair-local form of
  * SURVEY A.6 (inv(P_i) P_{i+1} == rt_i).  loss_weight is cfg.weight (loss.py:46).
  * mask_sum: device float64 scalar from fm_mask_sum ("or 1" applied inside).
+ * intrinsics_mode: FM_K_FULL = per-frame k4, gradient for every entry; FM_K_SHARED_FOCAL =
+ * all frames share one focal length with the principal point fixed (intrinsics_regressed.py,
+ * intrinsics_softmin.py): a cheaper kernel, the gradient is returned as the equivalent
+ * d/dfx of each frame (g_k4[:, 1:] = 0); FM_K_CONST = constant intrinsics (g_k4 = 0).  In the
+ * two cheap modes g_rt is the tangent (rigid) part of the pose gradient.
  * Outputs: loss (device float, = weight * sum / mask_sum); g_depth (B,F,H,W) WRITTEN with
  * the direct (pose-detached) depth gradient; g_rt (B*(F-1),3,4) written; pose and
  * intrinsics partials also stay in ws for fm_procrustes_bwd / fm_flow_k4_grad. */
@@ -96,8 +105,8 @@ int fm_flow_loss_fwd_bwd(const float* depth, const float* k4, const float* rt,
                          const float* forward_flow, const float* backward_flow,
                          const float* forward_mask, const float* backward_mask,
                          const double* mask_sum, int mapping, float delta, float loss_weight,
-                         float* loss, float* g_depth, float* g_rt, float* g_k4, void* ws, int B,
-                         int F, int H, int W, void* stream);
+                         int intrinsics_mode, float* loss, float* g_depth, float* g_rt, float* g_k4,
+                         void* ws, int B, int F, int H, int W, void* stream);
 
 /* projection.py:187-210 get_extrinsics: rt (B, F-1, 3, 4) -> camera-to-world (B, F, 4, 4),
  * P_0 = I, P_{k+1} = P_k @ T_k, and its adjoint. */

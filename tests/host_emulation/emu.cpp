@@ -85,6 +85,48 @@ void emu_flow(const float* depth, const float* k4, const float* rt, const float*
   }
 }
 
+// Lean phase C: writes the STANDARD accumulator layout (after lean_to_standard) into flowacc.
+void emu_flow_lean(const float* depth, const float* k4, const float* rt, const float* ff, const float* fb,
+                   const float* mf, const float* mb, double mask_sum, int mapping, float delta, float weight,
+                   int focal_mode, float* g_depth, double* flowacc, int B, int F, int H, int W) {
+  const int N = H * W;
+  if (mask_sum == 0.0) mask_sum = 1.0;
+  const float g = (float)((double)weight / mask_sum);
+  const RobustCfg rc = make_robust(mapping, delta, H, W);
+  const GridDims grid = make_grid(H, W);
+  for (int frame = 0; frame < B * F; ++frame) {
+    int bi = frame / F, i = frame - bi * F;
+    const bool hasF = i < F - 1, hasB = i > 0;
+    FlowFrameLean f;
+    f.kk = make_cam(k4_of(k4, frame)); f.kn = make_cam(k4_of(k4, hasF ? frame + 1 : frame)); f.kp = make_cam(k4_of(k4, hasB ? frame - 1 : frame));
+    int pairF = bi * (F - 1) + i, pairB = pairF - 1;
+    auto ld = [&](int pair) { Rt t; for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) t.r[r * 3 + c] = rt[(size_t)pair * 12 + r * 4 + c]; t.t[r] = rt[(size_t)pair * 12 + r * 4 + 3]; } return t; };
+    Rt tf, tb;
+    if (hasF) tf = ld(pairF);
+    if (hasB) tb = ld(pairB);
+    fill_lean(f, hasF ? &tf : nullptr, hasB ? &tb : nullptr);
+    double lean[kFlowLeanVals] = {0};
+    for (int j = 0; j < N; ++j) {
+      float acc[kFlowLeanVals] = {0};
+      const size_t jf = (size_t)(hasF ? pairF : 0) * N + j, jb = (size_t)(hasB ? pairB : 0) * N + j;
+      const float x = pix_coord(j % W, grid.Wf, grid.invW), y = pix_coord(j / W, grid.Hf, grid.invH);
+      const float D = depth[(size_t)frame * N + j];
+      float out;
+#define FM_CALL(HF, HB) out = focal_mode ? flow_pixel_lean<HF, HB, true>(f, x, y, D, HF ? ff[jf * 2] : 0.f, HF ? ff[jf * 2 + 1] : 0.f, HF ? mf[jf] : 0.f, HB ? fb[jb * 2] : 0.f, HB ? fb[jb * 2 + 1] : 0.f, HB ? mb[jb] : 0.f, g, rc, acc) \
+                                 : flow_pixel_lean<HF, HB, false>(f, x, y, D, HF ? ff[jf * 2] : 0.f, HF ? ff[jf * 2 + 1] : 0.f, HF ? mf[jf] : 0.f, HB ? fb[jb * 2] : 0.f, HB ? fb[jb * 2 + 1] : 0.f, HB ? mb[jb] : 0.f, g, rc, acc)
+      if (hasF && hasB) { FM_CALL(true, true); } else if (hasF) { FM_CALL(true, false); } else { FM_CALL(false, true); }
+#undef FM_CALL
+      g_depth[(size_t)frame * N + j] = out;
+      for (int k = 0; k < kFlowLeanVals; ++k) lean[k] += acc[k];
+    }
+    const double s = sqrt((double)H * (double)W);
+    const double focal = (double)k4[(size_t)frame * 4] * (double)W / s;
+    double out_std[kFlowVals];
+    lean_to_standard<double>(lean, hasF ? rt + (size_t)pairF * 12 : nullptr, hasB ? rt + (size_t)pairB * 12 : nullptr, focal, (double)W / s, focal_mode != 0, out_std);
+    for (int k = 0; k < kFlowVals; ++k) flowacc[(size_t)frame * 40 + k] = out_std[k];
+  }
+}
+
 // g_rt: (BP, 12) doubles = dL/d[R|t]; g_depth accumulated into; g_weights written/accumulated;
 // k4acc: (B*F, 4) doubles accumulated into.
 void emu_procrustes_bwd(const float* depth, const float* k4, const float* bflow, const float* weights,
@@ -104,7 +146,7 @@ void emu_procrustes_bwd(const float* depth, const float* k4, const float* bflow,
       float kacc[8] = {0}; float gdj, gwj;
       distribute_point(g, ad, pix_coord(j % W, g.grid.Wf, g.grid.invW), pix_coord(j / W, g.grid.Hf, g.grid.invH), db[j], weights ? weights[(size_t)pair * N + j] : 1.f,
                        bflow[((size_t)pair * N + j) * 2], bflow[((size_t)pair * N + j) * 2 + 1],
-                       [da](int i) { return da[i]; }, [gda, W](int rb, int x0, float v0, float v1) { gda[rb + x0] += v0; if (x0 + 1 < W) gda[rb + x0 + 1] += v1; }, gdj, gwj, kacc);
+                       [da](int i) { return da[i]; }, [gda, W](int y0, int x0, float v0, float v1) { gda[y0 * W + x0] += v0; if (x0 + 1 < W) gda[y0 * W + x0 + 1] += v1; }, gdj, gwj, kacc);
       gdb[j] += gdj;
       if (g_weights) g_weights[(size_t)pair * N + j] += gwj;
       for (int k = 0; k < 8; ++k) k4acc[(size_t)a * 4 + k] += kacc[k];

@@ -60,7 +60,8 @@ def flow_k4_grad(flowacc, B, F):
     return g
 
 
-def run_emulated_step(emu, g, mapping=0, focal=0.85, indices=None, delta=0.01, weight=1000.0):
+def run_emulated_step(emu, g, mapping=0, focal=0.85, indices=None, delta=0.01, weight=1000.0,
+                      lean=False):
     depth = np.ascontiguousarray(g["in_depth"], dtype=np.float32)
     F_, H, W = depth.shape
     B = 1
@@ -82,9 +83,14 @@ def run_emulated_step(emu, g, mapping=0, focal=0.85, indices=None, delta=0.01, w
     mask_sum = float(mf.astype(np.float64).sum() + mb.astype(np.float64).sum())
     g_depth = np.zeros_like(depth)
     flowacc = np.zeros((F_, 40), dtype=np.float64)
-    emu.emu_flow(_p(depth), _p(k4), _p(rt), _p(ff), _p(fb), _p(mf), _p(mb),
-                 ctypes.c_double(mask_sum), mapping, ctypes.c_float(delta), ctypes.c_float(weight),
-                 _p(g_depth), _p(flowacc), B, F_, H, W)
+    if lean:  # shared-focal kernel: twist pose accumulators, one focal accumulator
+        emu.emu_flow_lean(_p(depth), _p(k4), _p(rt), _p(ff), _p(fb), _p(mf), _p(mb),
+                          ctypes.c_double(mask_sum), mapping, ctypes.c_float(delta),
+                          ctypes.c_float(weight), 1, _p(g_depth), _p(flowacc), B, F_, H, W)
+    else:
+        emu.emu_flow(_p(depth), _p(k4), _p(rt), _p(ff), _p(fb), _p(mf), _p(mb),
+                     ctypes.c_double(mask_sum), mapping, ctypes.c_float(delta),
+                     ctypes.c_float(weight), _p(g_depth), _p(flowacc), B, F_, H, W)
     loss = flowacc[:, 0].sum()
     g_rt = flow_pose_grad(flowacc, rt, B, F_)
     g_w = np.zeros_like(w)
@@ -110,13 +116,14 @@ CASES = [("flow_huber", 0, 0.85, None), ("flow_l1", 1, 0.85, None), ("flow_l2", 
          ("flow_rough", 0, 1.3, None), ("flow_pts1000", 0, 0.85, 1000)]
 
 
+@pytest.mark.parametrize("lean", [False, True])
 @pytest.mark.parametrize("name,mapping,focal,npts", CASES)
-def test_emulated_step_matches_reference(emu, name, mapping, focal, npts):
+def test_emulated_step_matches_reference(emu, name, mapping, focal, npts, lean):
     g64 = load_golden(name, f64=True)
     g32 = load_golden(name, f64=False)
     _, H, W = g64["in_depth"].shape
     idx = None if npts is None else torch.linspace(0, H * W - 1, npts, dtype=torch.int64).numpy()
-    r = run_emulated_step(emu, g64, mapping=mapping, focal=focal, indices=idx)
+    r = run_emulated_step(emu, g64, mapping=mapping, focal=focal, indices=idx, lean=lean)
     # float32 noise floor of the reference itself (float32 run vs float64 run of the reference)
     ref_noise_d = rel_l2(g32["g_depth"], g64["g_depth"])
     ref_noise_w = rel_l2(g32["g_wparam"], g64["g_wparam"])

@@ -11,6 +11,7 @@ from flowmap_b200._lib import lib  # noqa: E402
 
 F, H, W = (int(x) for x in (sys.argv[1:4] if len(sys.argv) >= 4 else (150, 360, 640)))
 REPS = int(sys.argv[4]) if len(sys.argv) >= 5 else 3
+KMODE = int(sys.argv[5]) if len(sys.argv) >= 6 else 1  # FM_K_SHARED_FOCAL, as the fused step uses
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(0)
 depths = (0.1 + 0.05 * torch.rand(1, F, H, W, device=dev, generator=g))
@@ -33,7 +34,7 @@ L = lib()
 for _ in range(REPS):
     L.fm_procrustes_fwd(P(depths), P(k4), P(bwd), P(weights), None, 0, P(rt), P(ws), 1, F, H, W, st)
     L.fm_flow_loss_fwd_bwd(P(depths), P(k4), P(rt), P(fwd), P(bwd), P(fm), P(bm), P(msum), 0, 0.01,
-                           1000.0, P(loss), P(g_depth), P(g_rt), P(g_k4), P(ws), 1, F, H, W, st)
+                           1000.0, KMODE, P(loss), P(g_depth), P(g_rt), P(g_k4), P(ws), 1, F, H, W, st)
     L.fm_procrustes_bwd(P(depths), P(k4), P(bwd), P(weights), None, 0, None, 1, None, P(g_depth),
                         P(g_w), P(g_k4), P(ws), 1, F, H, W, st)
 torch.cuda.synchronize()
