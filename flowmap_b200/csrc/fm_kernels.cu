@@ -263,7 +263,7 @@ k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
   const float* db = da + N;
   const float* fl = bflow + pa.flow;
   const float* wt = weights ? weights + pa.weight : nullptr;
-  auto load_a = [da](int i) { return __ldg(da + i); };
+  auto load_a = [da, W](int yy, int xx) { return __ldg(da + yy * W + xx); };
   // float32 per-thread partials: a thread sees at most a few dozen (shifted, O(1)) terms, the
   // cross-thread / cross-block sums run in float64.
   float acc[kNumMoments];
@@ -603,7 +603,7 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
   const float* fl = bflow + pa.flow;
   const float* wt = weights ? weights + pa.weight : nullptr;
   float* gda = g_depth + pa.depth_a;
-  auto load_a = [da](int i) { return __ldg(da + i); };
+  auto load_a = [da, W](int yy, int xx) { return __ldg(da + yy * W + xx); };
   auto scatter = [gda, W](int y0, int x0, float v0, float v1) { red_pair<VEC == 4>(gda + y0 * W, x0, W, v0, v1); };
   float* gdb = gda + N;
   float* gw = g_weights ? g_weights + pa.weight : nullptr;
@@ -666,15 +666,16 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
 }
 
 // ------------------------------------------------------------------------------------------
-// Phase D2, tiled: the dense (all-pixel, W % 32 == 0) path.  A block owns 32 x 32 tiles of the
-// LATER frame; the bilinear scatter into the EARLIER frame is privatised in a 64 x 64 float
-// window in shared memory (tile + 16 px halo, shifted by the tile's mean backward flow so
-// that smooth real flows stay inside), accumulated with shared-memory atomics and flushed once
-// with 16-byte vector REDs.  Taps outside the window fall back to global REDs.  Measured
-// (tools/red_bench.cu): 0.275 ms vs 0.40 ms (vector REDs) vs 0.62 ms (scalar REDs) for the
-// scatter of one 150x360x640 step with iid +-12 px jitter.
-// Optionally applies Adam to the weight logits in the same pass (their gradient is final
-// here, and this kernel has HBM headroom): saves the separate 28 B/parameter Adam pass.
+// Tiled variants of the two gather phases (dense path, W % 32 == 0).  A block owns 32 x 32
+// tiles of the LATER frame; the 64 x 64 window of the EARLIER frame's depth around the tile
+// (16 px halo, shifted by the tile's mean backward flow so that smooth real flows stay
+// inside) is staged in shared memory with coalesced 16-byte loads, and the four bilinear taps
+// of every pixel are read from it (a random 4-byte gather costs ~4 shared-memory wavefronts per
+// warp instruction instead of ~25 L1 wavefronts).  Taps outside the window fall back to global
+// loads.  ncu before: l1tex throughput 82 % (k_moments) / 69 % (k_distribute).
+//
+// The scatter of phase D2 stays on global vector REDs: shared-memory float atomics compile to
+// LDS + FADD + ATOMS.CAST.SPIN loops on sm_100a and measured no faster (profiles/README.md).
 struct AdamFuse {
   float* m; float* v;
   float beta1, beta2, omb1, omb2, eps, step_size, bc2_sqrt;
@@ -682,6 +683,105 @@ struct AdamFuse {
 };
 
 constexpr int kTile = 32, kHalo = 16, kWin = kTile + 2 * kHalo;
+
+// Stage the window whose origin is (wx0, wy0) (wx0 % 4 == 0); cells outside the image hold 0
+// and are never read (taps are clamped into the image).
+__device__ __forceinline__ void load_window(const float* __restrict__ da, int wx0, int wy0, int H, int W,
+                                            float* __restrict__ win) {
+  for (int i = threadIdx.x; i < kWin * kWin / 4; i += kThreads) {
+    const int uy = (i * 4) / kWin, ux = (i * 4) - uy * kWin;
+    const int gy = wy0 + uy, gx = wx0 + ux;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < H && gx >= 0 && gx + 3 < W) v = __ldg(reinterpret_cast<const float4*>(da + gy * W + gx));
+    reinterpret_cast<float4*>(win)[i] = v;
+  }
+}
+
+// Mean backward flow of the tile -> window origin.  fv: the thread's 4 flow vectors (zeros if
+// the thread's row is outside the image).
+__device__ __forceinline__ void window_origin(const float* fv, const GridDims& grid, int X0, int Y0,
+                                              float* s_mean, int& wx0, int& wy0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float sx = (fv[0] + fv[2]) + (fv[4] + fv[6]), sy = (fv[1] + fv[3]) + (fv[5] + fv[7]);
+  sx = warp_sum_f(sx); sy = warp_sum_f(sy);
+  __syncthreads();  // previous tile's readers of s_mean / win are done
+  if (lane == 0) { s_mean[warp] = sx; s_mean[kThreads / 32 + warp] = sy; }
+  __syncthreads();
+  float mx = 0.f, my = 0.f;
+#pragma unroll
+  for (int w8 = 0; w8 < kThreads / 32; ++w8) { mx += s_mean[w8]; my += s_mean[kThreads / 32 + w8]; }
+  const int shift_x = ((int)rintf(mx * (1.0f / (kTile * kTile)) * grid.Wf * 0.25f)) * 4;
+  const int shift_y = (int)rintf(my * (1.0f / (kTile * kTile)) * grid.Hf);
+  wx0 = X0 - kHalo + shift_x;
+  wy0 = Y0 - kHalo + shift_y;
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
+k_moments_tiled(const float* __restrict__ depth, const float* __restrict__ k4,
+                const float* __restrict__ bflow, const float* __restrict__ weights,
+                double* __restrict__ moments, float wsens, PairLayout lay, int H, int W) {
+  __shared__ double smem[kNumMoments * (kThreads / 32)];
+  __shared__ __align__(16) float win[kWin * kWin];
+  __shared__ float s_mean[2 * (kThreads / 32)];
+  const int pair = blockIdx.y;
+  const int N = H * W;
+  const PairAddr pa = pair_addr(lay, pair, N);
+  const PairGeom g = pair_geom(depth, k4, pa, H, W);
+  const float* da = depth + pa.depth_a;
+  const float* db = da + N;
+  const float* fl = bflow + pa.flow;
+  const float* wt = weights ? weights + pa.weight : nullptr;
+  float acc[kNumMoments];
+#pragma unroll
+  for (int i = 0; i < kNumMoments; ++i) acc[i] = 0.f;
+  const int tiles_x = W / kTile, tiles_y = (H + kTile - 1) / kTile;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+    const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
+    const int X0 = txi * kTile, Y0 = tyi * kTile;
+    const int r = Y0 + ty, c0 = X0 + 4 * tx;
+    const bool row_ok = r < H;
+    const int base = r * W + c0;
+    float dv[4], wv[4], fv[8];
+    if (row_ok) {
+      load_vec<4>(db + base, dv);
+      load_vec2<4>(fl + 2 * base, fv);
+      if (wt) {
+        load_vec<4>(wt + base, wv);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) wv[v] = weight_of(wv[v], wsens);
+      } else {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) wv[v] = 1.f;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < 8; ++v) fv[v] = 0.f;
+    }
+    int wx0, wy0;
+    window_origin(fv, g.grid, X0, Y0, s_mean, wx0, wy0);
+    load_window(da, wx0, wy0, H, W, win);
+    __syncthreads();
+    auto load_a = [&](int yy, int xx) {
+      const int ux = xx - wx0, uy = yy - wy0;
+      return ((unsigned)ux < (unsigned)kWin && (unsigned)uy < (unsigned)kWin) ? win[uy * kWin + ux]
+                                                                                : __ldg(da + yy * W + xx);
+    };
+    if (row_ok) {
+      const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        float p[3], q[3];
+        Taps taps;
+        point_pq(g, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], fv[2 * v], fv[2 * v + 1], load_a, p,
+                 q, taps);
+        moments_add(acc, wv[v], p, q);
+      }
+    }
+  }
+  __syncthreads();
+  block_accumulate<kNumMoments>(acc, moments + (size_t)pair * kNumMoments, smem);
+}
 
 __global__ void __launch_bounds__(kThreads, 3)
 k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4,
@@ -697,8 +797,6 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
   const int N = H * W;
   if (threadIdx.x < sizeof(PairAdjoint) / 4)
     reinterpret_cast<float*>(&s_adj)[threadIdx.x] = reinterpret_cast<const float*>(adj + pair)[threadIdx.x];
-  for (int i = threadIdx.x; i < kWin * kWin / 4; i += kThreads)
-    reinterpret_cast<float4*>(win)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   const PairAdjoint ad = s_adj;
   const PairAddr pa = pair_addr(lay, pair, N);
@@ -711,13 +809,12 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
   float* gda = g_depth + pa.depth_a;
   float* gdb = gda + N;
   float* gw = g_weights ? g_weights + pa.weight : nullptr;
-  auto load_a = [da](int i) { return __ldg(da + i); };
+  auto scatter = [gda, W](int y0, int x0, float v0, float v1) { red_pair<true>(gda + y0 * W, x0, W, v0, v1); };
   float kacc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
   const int tiles_x = W / kTile, tiles_y = (H + kTile - 1) / kTile;
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
     const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
@@ -742,26 +839,14 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
 #pragma unroll
       for (int v = 0; v < 8; ++v) fv[v] = 0.f;
     }
-    // window origin: tile origin - halo + rounded mean flow of the tile (x to a multiple of 4)
-    float sx = (fv[0] + fv[2]) + (fv[4] + fv[6]), sy = (fv[1] + fv[3]) + (fv[5] + fv[7]);
-    sx = warp_sum_f(sx); sy = warp_sum_f(sy);
-    if (lane == 0) { s_mean[warp] = sx; s_mean[kThreads / 32 + warp] = sy; }
+    int wx0, wy0;
+    window_origin(fv, g.grid, X0, Y0, s_mean, wx0, wy0);
+    load_window(da, wx0, wy0, H, W, win);
     __syncthreads();
-    float mx = 0.f, my = 0.f;
-#pragma unroll
-    for (int w8 = 0; w8 < kThreads / 32; ++w8) { mx += s_mean[w8]; my += s_mean[kThreads / 32 + w8]; }
-    const int shift_x = ((int)rintf(mx * (1.0f / (kTile * kTile)) * g.grid.Wf * 0.25f)) * 4;
-    const int shift_y = (int)rintf(my * (1.0f / (kTile * kTile)) * g.grid.Hf);
-    const int wx0 = X0 - kHalo + shift_x, wy0 = Y0 - kHalo + shift_y;
-    auto scatter = [&](int y0, int x0, float v0, float v1) {
-      const int ux = x0 - wx0, uy = y0 - wy0;
-      if ((unsigned)ux < (unsigned)(kWin - 1) && (unsigned)uy < (unsigned)kWin) {
-        float* q = win + uy * kWin + ux;
-        atomicAdd(q, v0);
-        atomicAdd(q + 1, v1);
-      } else {
-        red_pair<true>(gda + y0 * W, x0, W, v0, v1);
-      }
+    auto load_a = [&](int yy, int xx) {
+      const int ux = xx - wx0, uy = yy - wy0;
+      return ((unsigned)ux < (unsigned)kWin && (unsigned)uy < (unsigned)kWin) ? win[uy * kWin + ux]
+                                                                                : __ldg(da + yy * W + xx);
     };
     if (row_ok) {
       const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
@@ -771,7 +856,7 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
                          fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
       red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
       if (wt) {
-        if (wsens != 0.f) {
+        if (wsens != 0.f) {  // chain rule of the sigmoid: d/d logit = sens * w (1 - w) * d/dw
 #pragma unroll
           for (int v = 0; v < 4; ++v) gwv[v] *= wsens * wv[v] * (1.0f - wv[v]);
         }
@@ -792,19 +877,8 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
         }
       }
     }
-    __syncthreads();
-    // flush the window (and re-zero it for the next tile)
-    for (int i = threadIdx.x; i < kWin * kWin / 4; i += kThreads) {
-      const int uy = (i * 4) / kWin, ux = (i * 4) - uy * kWin;
-      const int gy = wy0 + uy, gx = wx0 + ux;
-      const float4 v = reinterpret_cast<float4*>(win)[i];
-      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
-        if (gy >= 0 && gy < H && gx >= 0 && gx + 3 < W) red_add4(gda + gy * W + gx, v.x, v.y, v.z, v.w);
-        reinterpret_cast<float4*>(win)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    __syncthreads();
   }
+  __syncthreads();
   block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
 }
 
@@ -1087,7 +1161,7 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
     const bool src_ok = tvis[sidx] && in_unit_square(sxy.x, sxy.y);
     const Taps t = bilinear_taps(sxy.x, sxy.y, grid);
     float q[3];
-    sample_surface(t, grid, ks, [D](int i) { return __ldg(D + i); }, q[0], q[1], q[2]);
+    sample_surface(t, grid, ks, [D, W](int yy, int xx) { return __ldg(D + yy * W + xx); }, q[0], q[1], q[2]);
     float Xw[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -1479,6 +1553,10 @@ static int procrustes_fwd_impl(const float* depth, const float* k4, const float*
   if (indices) {
     dim3 grid(blocks_for(num_indices, 1), BP);
     k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.moments, wsens, lay, H, W);
+  } else if (W % kTile == 0 && getenv("FM_NO_TILED_GATHER") == nullptr) {
+    const int tiles = (W / kTile) * ((H + kTile - 1) / kTile);
+    dim3 grid((tiles + 7) / 8, BP);
+    k_moments_tiled<<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
     k_moments<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, lay, H, W);
@@ -1524,7 +1602,7 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
   if (indices) {
     dim3 grid(blocks_for(num_indices, 1), BP);
     k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, H, W);
-  } else if (W % kTile == 0 && lay.cand == 1 && getenv("FM_NO_TILED_SCATTER") == nullptr) {
+  } else if (W % kTile == 0 && getenv("FM_NO_TILED_GATHER") == nullptr) {
     const int tiles = (W / kTile) * ((H + kTile - 1) / kTile);
     dim3 grid((tiles + 7) / 8, BP);
     AdamFuse af;
@@ -1844,7 +1922,7 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
   AdamFuse af;
   memset(&af, 0, sizeof(af));
   const bool fuse_w = a->step > 0 && a->weight_logits && !a->indices && W % kTile == 0 &&
-                      getenv("FM_NO_TILED_SCATTER") == nullptr;
+                      getenv("FM_NO_TILED_GATHER") == nullptr;
   if (fuse_w) {  // the weight gradient is final inside k_distribute_tiled: update the logits there
     af.on = 1; af.m = a->m_weights; af.v = a->v_weights;
     af.beta1 = (float)a->beta1; af.beta2 = (float)a->beta2;

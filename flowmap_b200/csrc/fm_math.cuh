@@ -163,9 +163,8 @@ FM_HD void tap_rays(const Taps& t, const GridDims& g, const Cam& k, float& rx0, 
 template <typename Load>
 FM_HD void sample_surface(const Taps& t, const GridDims& g, const Cam& k, Load load, float& qx,
                           float& qy, float& qz) {
-  const int W = g.W;
-  float d00 = load(t.y0 * W + t.x0), d01 = load(t.y0 * W + t.x1);
-  float d10 = load(t.y1 * W + t.x0), d11 = load(t.y1 * W + t.x1);
+  float d00 = load(t.y0, t.x0), d01 = load(t.y0, t.x1);
+  float d10 = load(t.y1, t.x0), d11 = load(t.y1, t.x1);
   float a00 = t.w00 * d00, a01 = t.w01 * d01, a10 = t.w10 * d10, a11 = t.w11 * d11;
   float rx0, rx1, ry0, ry1;
   tap_rays(t, g, k, rx0, ry0, rx1, ry1);

@@ -165,20 +165,64 @@ FM_HD void fill_lean(FlowFrameLean& f, const Rt* tf, const Rt* tb) {
   }
 }
 
-// Projection adjoint without the per-component intrinsics gradients; returns du . u over x, y
-// (= fx * dL/dfx + fy * dL/dfy of this projection).
-FM_HD float project_adj_lean(const Proj& p, float P0, float P1, float P2, const Cam& k, float duvx,
-                             float duvy, float& d0, float& d1, float& d2) {
-  float du0 = k.fx * duvx, du1 = k.fy * duvy, du2 = k.cx * duvx + k.cy * duvy;
-  if (!p.all_finite) {
-    if (!p.finite[0]) du0 = 0.0f;
-    if (!p.finite[1]) du1 = 0.0f;
-    if (!p.finite[2]) du2 = 0.0f;
+// One reprojection term of the lean kernel, written with explicit FMAs (the compiler only
+// contracts a*b+c patterns, not the sum-of-products / accumulate chains used here).
+//   P = D * dir + off ; uv = K (P / (P_z + eps)) ; residual vs flow ; robust map ; adjoint.
+// Outputs dP (gradient w.r.t. the camera-space point), su = fx duvx u0 + fy duvy u1 and the
+// masked, scaled loss contribution.
+struct LeanTerm {
+  float P0, P1, P2, d0, d1, d2, su, loss;
+};
+
+FM_HD LeanTerm lean_term(float D, float dir0, float dir1, float dir2, float off0, float off1,
+                         float off2, const Cam& k, float x, float y, float flx, float fly, float wgt,
+                         const RobustCfg& rc) {
+  LeanTerm t;
+  t.P0 = fm_fma(D, dir0, off0);
+  t.P1 = fm_fma(D, dir1, off1);
+  t.P2 = fm_fma(D, dir2, off2);
+  const float inv = fm_rcp(t.P2 + kProjEps);
+  float u0 = t.P0 * inv, u1 = t.P1 * inv, u2 = t.P2 * inv;
+  bool f0 = true, f1 = true, f2 = true;
+  // one test for the common all-finite case (a sum that overflows is re-examined per component)
+  if (!((fabsf(u0) + fabsf(u1)) + fabsf(u2) <= 3.0e38f)) {
+    u0 = nan_to_num1(u0, f0);
+    u1 = nan_to_num1(u1, f1);
+    u2 = nan_to_num1(u2, f2);
   }
-  d0 = du0 * p.inv;
-  d1 = du1 * p.inv;
-  d2 = (du2 - (du0 * P0 + du1 * P1 + du2 * P2) * p.inv) * p.inv;
-  return k.fx * duvx * p.u[0] + k.fy * duvy * p.u[1];
+  const float uvx = fm_fma(k.fx, u0, k.cx * u2), uvy = fm_fma(k.fy, u1, k.cy * u2);
+  // robust map of the aspect-corrected residual (mapping.py:35-43)
+  const float sx = ((uvx - x) - flx) * rc.ax, sy = ((uvy - y) - fly) * rc.ay;
+  const float n2 = fm_fma(sx, sx, sy * sy);
+  float kx, ky, val;
+  if (rc.mapping == MAP_L2) {
+    kx = rc.ax; ky = rc.ay; val = 0.5f * n2;
+  } else {
+    const float inv_n = n2 > 0.0f ? fm_rsqrt(n2) : 0.0f;
+    const float n = n2 * inv_n;
+    float kk = inv_n;
+    val = n;
+    if (rc.mapping == MAP_HUBER) {
+      const bool quad = n <= rc.delta;
+      kk = quad ? rc.inv_delta : inv_n;
+      val = quad ? (0.5f * rc.inv_delta) * n2 : n - 0.5f * rc.delta;
+    }
+    kx = kk * rc.ax; ky = kk * rc.ay;
+  }
+  t.loss = wgt * val;
+  const float duvx = (wgt * sx) * kx, duvy = (wgt * sy) * ky;
+  float du0 = k.fx * duvx, du1 = k.fy * duvy, du2 = fm_fma(k.cx, duvx, k.cy * duvy);
+  t.su = fm_fma(du0, u0, du1 * u1);
+  if (!(f0 && f1 && f2)) {  // nan_to_num passes no gradient through replaced components
+    if (!f0) du0 = 0.0f;
+    if (!f1) du1 = 0.0f;
+    if (!f2) du2 = 0.0f;
+  }
+  t.d0 = du0 * inv;
+  t.d1 = du1 * inv;
+  const float dot = fm_fma(du0, t.P0, fm_fma(du1, t.P1, du2 * t.P2));
+  t.d2 = fm_fma(-dot, inv, du2) * inv;
+  return t;
 }
 
 template <bool HASF, bool HASB, bool FOCAL>
@@ -189,45 +233,40 @@ FM_HD float flow_pixel_lean(const FlowFrameLean& f, float x, float y, float D, f
   ray_of(x, y, f.kk, rx, ry);
   float gD = 0.f;
   if (HASF) {
-    const float m0 = f.rtF[0] * rx + f.rtF[1] * ry + f.rtF[2];
-    const float m1 = f.rtF[3] * rx + f.rtF[4] * ry + f.rtF[5];
-    const float m2 = f.rtF[6] * rx + f.rtF[7] * ry + f.rtF[8];
-    const float Y0 = D * m0 + f.cF[0], Y1 = D * m1 + f.cF[1], Y2 = D * m2 + f.cF[2];
-    const Proj pr = project_point(Y0, Y1, Y2, f.kn);
-    float gx, gy;
-    const float l = robust_map((pr.uvx - x) - ffx, (pr.uvy - y) - ffy, rc, gx, gy);
-    const float wgt = g * mf;
-    acc[0] += wgt * l;
-    float d0, d1, d2;
-    const float su = project_adj_lean(pr, Y0, Y1, Y2, f.kn, wgt * gx, wgt * gy, d0, d1, d2);
-    const float gd = d0 * m0 + d1 * m1 + d2 * m2;
-    gD += gd;
-    acc[1] += Y1 * d2 - Y2 * d1;
-    acc[2] += Y2 * d0 - Y0 * d2;
-    acc[3] += Y0 * d1 - Y1 * d0;
-    acc[4] += d0; acc[5] += d1; acc[6] += d2;
-    if (FOCAL) acc[13] += su - D * (gd - (f.r2F[0] * d0 + f.r2F[1] * d1 + f.r2F[2] * d2));
+    const float m0 = fm_fma(f.rtF[0], rx, fm_fma(f.rtF[1], ry, f.rtF[2]));
+    const float m1 = fm_fma(f.rtF[3], rx, fm_fma(f.rtF[4], ry, f.rtF[5]));
+    const float m2 = fm_fma(f.rtF[6], rx, fm_fma(f.rtF[7], ry, f.rtF[8]));
+    const LeanTerm t = lean_term(D, m0, m1, m2, f.cF[0], f.cF[1], f.cF[2], f.kn, x, y, ffx, ffy, g * mf, rc);
+    acc[0] += t.loss;
+    const float gd = fm_fma(t.d0, m0, fm_fma(t.d1, m1, t.d2 * m2));
+    gD = gd;
+    acc[1] = fm_fma(t.P1, t.d2, fm_fma(-t.P2, t.d1, acc[1]));
+    acc[2] = fm_fma(t.P2, t.d0, fm_fma(-t.P0, t.d2, acc[2]));
+    acc[3] = fm_fma(t.P0, t.d1, fm_fma(-t.P1, t.d0, acc[3]));
+    acc[4] += t.d0; acc[5] += t.d1; acc[6] += t.d2;
+    if (FOCAL) {
+      const float dz = fm_fma(f.r2F[0], t.d0, fm_fma(f.r2F[1], t.d1, f.r2F[2] * t.d2));
+      acc[13] += fm_fma(-D, gd - dz, t.su);
+    }
   }
   if (HASB) {
-    const float n0 = f.rB[0] * rx + f.rB[1] * ry + f.rB[2];
-    const float n1 = f.rB[3] * rx + f.rB[4] * ry + f.rB[5];
-    const float n2 = f.rB[6] * rx + f.rB[7] * ry + f.rB[8];
-    const float e0 = D * n0, e1 = D * n1, e2 = D * n2;
-    const float X0 = e0 + f.tB[0], X1 = e1 + f.tB[1], X2 = e2 + f.tB[2];
-    const Proj pr = project_point(X0, X1, X2, f.kp);
-    float gx, gy;
-    const float l = robust_map((pr.uvx - x) - fbx, (pr.uvy - y) - fby, rc, gx, gy);
-    const float wgt = g * mb;
-    acc[0] += wgt * l;
-    float d0, d1, d2;
-    const float su = project_adj_lean(pr, X0, X1, X2, f.kp, wgt * gx, wgt * gy, d0, d1, d2);
-    const float gd = d0 * n0 + d1 * n1 + d2 * n2;
+    const float n0 = fm_fma(f.rB[0], rx, fm_fma(f.rB[1], ry, f.rB[2]));
+    const float n1 = fm_fma(f.rB[3], rx, fm_fma(f.rB[4], ry, f.rB[5]));
+    const float n2 = fm_fma(f.rB[6], rx, fm_fma(f.rB[7], ry, f.rB[8]));
+    const LeanTerm t = lean_term(D, n0, n1, n2, f.tB[0], f.tB[1], f.tB[2], f.kp, x, y, fbx, fby, g * mb, rc);
+    acc[0] += t.loss;
+    const float gd = fm_fma(t.d0, n0, fm_fma(t.d1, n1, t.d2 * n2));
     gD += gd;
-    acc[7] += e1 * d2 - e2 * d1;
-    acc[8] += e2 * d0 - e0 * d2;
-    acc[9] += e0 * d1 - e1 * d0;
-    acc[10] += d0; acc[11] += d1; acc[12] += d2;
-    if (FOCAL) acc[13] += su - D * (gd - (f.c2B[0] * d0 + f.c2B[1] * d1 + f.c2B[2] * d2));
+    // (X - t) x dX with X - t = D n
+    const float e0 = D * n0, e1 = D * n1, e2 = D * n2;
+    acc[7] = fm_fma(e1, t.d2, fm_fma(-e2, t.d1, acc[7]));
+    acc[8] = fm_fma(e2, t.d0, fm_fma(-e0, t.d2, acc[8]));
+    acc[9] = fm_fma(e0, t.d1, fm_fma(-e1, t.d0, acc[9]));
+    acc[10] += t.d0; acc[11] += t.d1; acc[12] += t.d2;
+    if (FOCAL) {
+      const float dz = fm_fma(f.c2B[0], t.d0, fm_fma(f.c2B[1], t.d1, f.c2B[2] * t.d2));
+      acc[13] += fm_fma(-D, gd - dz, t.su);
+    }
   }
   return gD;
 }
