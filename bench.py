@@ -1,11 +1,16 @@
 #!/usr/bin/env python
-"""Benchmark of the FlowMap optimisation hot path on B200 (contract: see DESIGN.md section 6).
+"""Benchmark of the FlowMap optimisation hot path on B200 (contract: DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode scenes|pairs]
 
-One "step" = one full overfit iteration at the BASELINE shape (150 x 360 x 640, explicit
-depth backbone, all-pixel Procrustes): Model.forward -> LossFlow -> backward -> Adam.
-Prints ONE JSON line on rank 0.
+One "step" = one full overfit iteration at BASELINE config 3 (150 x 360 x 640, synthetic):
+explicit-depth backbone, all-pixel Procrustes, softmin intrinsics (60-candidate sweep), flow
+loss + tracking loss (30 segments x 1225 tracks), backward, Adam -- what
+flowmap/model/model_wrapper_overfit.py:51-73,104-105 runs per iteration with the reference's
+default losses/intrinsics and `+experiment=ablation_explicit_depth`.
+N > 1 (default --mode scenes, BASELINE config 5): one independent scene per GPU, no data-path
+collective.  --mode pairs (config 4 style): flow-loss-only run of ONE long video whose frame
+pairs are sharded across ranks, one all-reduce per step.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -24,9 +29,12 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 F_, H_, W_ = 150, 360, 640  # BASELINE.json configs[2] ("Tanks&Temples-shape")
-WORKLOAD = ("C3 150x360x640 synthetic (iid N(0,0.01^2) flows, U(0,1) masks), explicit_depth "
-            "backbone, all-pixel Procrustes, regressed focal, flow loss (Huber), full overfit "
-            "step = Model.forward + LossFlow + backward + Adam (fm_overfit_step)")
+START_STEP = 50             # tracking loss enabled (>= 50), softmin stage (< 1000)
+WORKLOAD = ("C3 150x360x640 synthetic (iid N(0,0.01^2) flows, U(0,1) masks, 30 track segments x "
+            "1225 uniform tracks), explicit_depth backbone, all-pixel Procrustes, softmin "
+            "intrinsics (60 candidates x 8192 points), flow + tracking loss (Huber), full overfit "
+            "step = Model.forward + losses + backward + Adam, global_step >= 50")
+METRIC = "overfit iters/sec at 150x360x640 (149 frame pairs per iteration)"
 
 
 # ------------------------------------------------------------------------------ inputs
@@ -35,7 +43,7 @@ def synthetic_inputs(f, h, w, seed=0):
     N(0, .01^2) in normalised units, masks U(0,1).  CPU float32 tensors."""
     g = torch.Generator().manual_seed(seed)
     p = f - 1
-    d = {
+    return {
         "depth": 0.1 + 0.05 * torch.rand(f, h, w, generator=g),
         "wparam": 0.01 * torch.randn(p, h, w, generator=g),
         "fwd": 0.01 * torch.randn(1, p, h, w, 2, generator=g),
@@ -43,13 +51,24 @@ def synthetic_inputs(f, h, w, seed=0):
         "fmask": torch.rand(1, p, h, w, generator=g),
         "bmask": torch.rand(1, p, h, w, generator=g),
     }
-    return d
+
+
+def synthetic_track_arrays(f, n_points=1225, interval=5, radius=20, seed=0):
+    """Segment layout of flowmap/tracking/__init__.py:49-70 (one segment every `interval`
+    frames covering [mid - radius, mid + radius]); xy ~ U(0,1)^2, visibility ~ Bernoulli(.7).
+    Returns a list of (xy (1, fs, n, 2), vis (1, fs, n) bool, start_frame)."""
+    g = torch.Generator().manual_seed(seed + 1)
+    out = []
+    for mid in range(0, f, interval):
+        lo, hi = max(0, mid - radius), min(f, mid + radius + 1)
+        out.append((torch.rand(1, hi - lo, n_points, 2, generator=g),
+                    torch.rand(1, hi - lo, n_points, generator=g) < 0.7, lo))
+    return out
 
 
 def algorithmic_bytes(f, h, w):
     """32 B per pair-pixel + 8 B per frame-pixel."""
-    n = h * w
-    return n * (32 * (f - 1) + 8 * f)
+    return h * w * (32 * (f - 1) + 8 * f)
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -69,8 +88,7 @@ class ClockSampler:
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                  "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
@@ -90,80 +108,135 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-
-        def summarise(rows):
-            sm, mx, reasons = [], None, set()
-            for _, s in rows:
-                parts = [x.strip() for x in s.split(",")]
-                if len(parts) < 6:
-                    continue
-                try:
-                    sm.append(float(parts[0]))
-                    mx = float(parts[1])
-                except ValueError:
-                    continue
-                for n, v in zip(names, parts[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            sm.sort()
-            return sm, mx, reasons
         inside = [r for r in self.samples if any(a <= r[0] <= b for a, b in self.windows)]
         which = "timed regions"
-        if len(inside) < 3:  # regions shorter than the sampling period: use everything under load
+        if len(inside) < 3:  # regions shorter than the sampling period
             inside, which = self.samples, "warm-up + timed regions + per-op timing (all under load)"
-        sm, mx, reasons = summarise(inside)
+        sm, mx, reasons = [], None, set()
+        for _, s in inside:
+            parts = [x.strip() for x in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
                 "reasons": sorted(reasons), "samples": len(sm), "window": which}
 
 
 # ------------------------------------------------------------------------------ CPU baseline
-def cpu_baseline(inputs, sample_frames, steps, warmup):
-    """The oracle (CPU restatement of the reference, oracle/flowmap_oracle.py) timed on the
-    host cores on the first `sample_frames` frames of the workload; it/s scaled by pairs."""
+def cpu_baseline(sample_frames, steps, warmup, full=True):
+    """The oracle (CPU restatement of the reference, oracle/flowmap_oracle.py: same op
+    sequence on ATen, autograd, torch.optim.Adam) timed on the host cores on the first
+    `sample_frames` frames of the workload; it/s scaled by frame pairs."""
     from oracle import flowmap_oracle as O
+    inputs = synthetic_inputs(sample_frames, H_, W_, seed=0)
     cores = os.cpu_count() or 1
-    f, h, w = sample_frames, inputs["depth"].shape[1], inputs["depth"].shape[2]
+    f, h, w = sample_frames, H_, W_
+    flows = O.Flows(inputs["fwd"], inputs["bwd"], inputs["fmask"], inputs["bmask"])
+    tracks = [O.Tracks(xy, vis, s) for xy, vis, s in synthetic_track_arrays(f)] if full else None
+    kw = dict(intrinsics="softmin", use_tracking=True) if full else dict(intrinsics="regressed")
+
+    def make(nf):
+        st = O.OverfitOracle(O.OverfitConfig(**kw), nf, h, w)
+        with torch.no_grad():
+            st.depth.copy_(inputs["depth"][:nf])
+            st.weights.copy_(inputs["wparam"][:nf - 1])
+        st.global_step = START_STEP
+        return st
+
     # "all the host threads it can use": ATen's elementwise kernels stop scaling (and then
-    # collapse) well below the core count of a 128-core host, so pick the fastest setting.
+    # collapse) far below the core count of a 128-core host, so pick the fastest setting.
     best, best_t = None, None
+    small = O.Flows(*(t[:, :2] for t in (inputs["fwd"], inputs["bwd"], inputs["fmask"], inputs["bmask"])))
     for nt in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}):
         torch.set_num_threads(nt)
         st = O.OverfitOracle(O.OverfitConfig(intrinsics="regressed"), 3, h, w)
-        fl = O.Flows(inputs["fwd"][:, :2], inputs["bwd"][:, :2], inputs["fmask"][:, :2],
-                     inputs["bmask"][:, :2])
-        st.training_step(fl)
+        st.training_step(small)
         t0 = time.perf_counter()
-        st.training_step(fl)
+        st.training_step(small)
         dt = time.perf_counter() - t0
         if best_t is None or dt < best_t:
             best, best_t = nt, dt
     torch.set_num_threads(best)
-    st = O.OverfitOracle(O.OverfitConfig(intrinsics="regressed"), f, h, w)
-    with torch.no_grad():
-        st.depth.copy_(inputs["depth"][:f])
-        st.weights.copy_(inputs["wparam"][:f - 1])
-    flows = O.Flows(inputs["fwd"][:, :f - 1], inputs["bwd"][:, :f - 1], inputs["fmask"][:, :f - 1],
-                    inputs["bmask"][:, :f - 1])
-    for _ in range(warmup):
-        st.training_step(flows)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        st.training_step(flows)
-    dt = (time.perf_counter() - t0) / steps
-    pairs_per_s = (f - 1) / dt
-    return {"value": pairs_per_s / (F_ - 1), "unit": "it/s", "cores": cores, "kind": "port",
-            "threads": torch.get_num_threads(), "frame_pairs_per_s": pairs_per_s,
-            "sample": f"first {f} of {F_} frames ({f - 1} pairs) at {h}x{w}, {steps} timed steps "
-                      f"after {warmup} warm-up; it/s = pairs/s / {F_ - 1}",
-            "s_per_sample_step": dt}
+
+    def timed(kw_, use_tracks, n):
+        st = O.OverfitOracle(O.OverfitConfig(**kw_), f, h, w)
+        with torch.no_grad():
+            st.depth.copy_(inputs["depth"][:f])
+            st.weights.copy_(inputs["wparam"][:f - 1])
+        st.global_step = START_STEP
+        tr = tracks if use_tracks else None
+        for _ in range(warmup):
+            st.training_step(flows, tr)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            st.training_step(flows, tr)
+        return (time.perf_counter() - t0) / n
+
+    pairs = f - 1
+    if not full:
+        dt = timed(dict(intrinsics="regressed"), False, steps)
+        t150 = dt * (F_ - 1) / pairs
+        parts = {"s_per_sample_step": dt}
+        how = f"time scales with frame pairs: t150 = t_sample * {F_ - 1}/{pairs}"
+    else:
+        # Three cost components with different scaling: per frame pair (flow path), per
+        # iteration (the 60-candidate sweep on the first pair) and per (source, target) frame
+        # pair of a track segment.  Time the sample with each switched on in turn, then
+        # assemble the cost of the 150-frame workload.
+        n_aux = max(1, min(steps, 2))
+        t_flow = timed(dict(intrinsics="regressed"), False, n_aux)
+        t_soft = timed(dict(intrinsics="softmin"), False, n_aux)
+        t_full = timed(dict(intrinsics="softmin", use_tracking=True), True, steps)
+        seg_pairs_sample = sum(xy.shape[1] ** 2 for xy, _, _ in synthetic_track_arrays(f))
+        seg_pairs_full = sum(xy.shape[1] ** 2 for xy, _, _ in synthetic_track_arrays(F_))
+        c_sweep = max(t_soft - t_flow, 0.0)
+        # the sample's 3 short segments are too small to time inside a multi-second step: time
+        # the tracking loss (forward + backward) on ONE full-size segment (41 frames x 1225)
+        fs = 41
+        seg = [O.Tracks(xy, vis, 0) for xy, vis, _ in synthetic_track_arrays(fs, interval=10 ** 6, radius=fs)]
+        k = O.intrinsics_from_focal(torch.tensor(0.85), h, w).expand(1, fs, 3, 3)
+        ext = torch.eye(4).expand(1, fs, 4, 4).clone()
+        ext[0, :, 0, 3] = 0.01 * torch.arange(fs)
+        ext.requires_grad_(True)
+        with torch.no_grad():
+            surf = O.unproject(O.pixel_grid(h, w), 0.1 + 0.05 * torch.rand(1, fs, h, w), k[:, :, None, None])
+        surf.requires_grad_(True)  # marginal cost of the tracking loss given the shared surfaces
+
+        def track_once():
+            surf.grad = None
+            O.tracking_loss(surf, ext, k, seg).backward()
+        track_once()
+        t0 = time.perf_counter()
+        for _ in range(n_aux):
+            track_once()
+        c_track = (time.perf_counter() - t0) / n_aux / (fs * fs)
+        t150 = t_flow * (F_ - 1) / pairs + c_sweep + c_track * seg_pairs_full
+        parts = {"s_flow_path_sample": t_flow, "s_softmin_sweep": c_sweep,
+                 "s_tracking_per_frame_pair": c_track, "s_full_sample_step": t_full,
+                 "track_frame_pairs_sample": seg_pairs_sample, "track_frame_pairs_150": seg_pairs_full}
+        how = (f"t150 = t_flow_path * {F_ - 1}/{pairs} + t_sweep + t_track_per_frame_pair * "
+               f"{seg_pairs_full} (tracking timed on one 41-frame x 1225-track segment)")
+    return {"value": 1.0 / t150, "unit": "it/s", "cores": cores, "kind": "port", "threads": best,
+            "frame_pairs_per_s": (F_ - 1) / t150, "estimated_s_per_iteration_150_frames": t150,
+            "sample": f"first {f} of {F_} frames ({pairs} pairs, {len(tracks) if tracks else 0} track "
+                      f"segments) at {h}x{w}, {steps} timed steps after {warmup} warm-up; {how}",
+            **parts}
 
 
 # ------------------------------------------------------------------------------ GPU arm
 def run_gpu(args):
+    from flowmap_b200 import ops, parallel
     from flowmap_b200._lib import lib
-    from flowmap_b200 import ops
-    from flowmap_b200.overfit import OverfitCfg, Overfitter
-    from flowmap_b200.types import Batch, Flows
+    from flowmap_b200.overfit import FusedOverfitter, OverfitCfg, ShardedFusedOverfitter
+    from flowmap_b200.types import Batch, Flows, Tracks
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -175,35 +248,58 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    pairs_mode = args.mode == "pairs"
 
     inputs = synthetic_inputs(F_, H_, W_, seed=rank)
-    batch_dev = Batch(torch.zeros(1, 1, 1, 1, 1, device=dev).expand(1, F_, 3, H_, W_),
-                      torch.arange(F_, device=dev)[None], ["synthetic"], ["synthetic"])
+    batch = Batch(torch.zeros(1, 1, 1, 1, 1, device=dev).expand(1, F_, 3, H_, W_),
+                  torch.arange(F_, device=dev)[None], ["synthetic"], ["synthetic"])
     flows_host = Flows(inputs["fwd"].pin_memory(), inputs["bwd"].pin_memory(),
                        inputs["fmask"].pin_memory(), inputs["bmask"].pin_memory())
-    from flowmap_b200 import parallel
-    from flowmap_b200.overfit import FusedOverfitter, ShardedFusedOverfitter
-    cfg = OverfitCfg()
-    flows_dev = Flows(*(t.to(dev, non_blocking=True) for t in
-                        (flows_host.forward, flows_host.backward, flows_host.forward_mask,
-                         flows_host.backward_mask)))
-    if world > 1:
-        # weak scaling: every rank owns 149 pairs of one long video (world * 149 pairs)
-        plan = parallel.ShardPlan(rank, world, (rank * (F_ - 1), (rank + 1) * (F_ - 1)),
-                                  world * (F_ - 1))
-        o = ShardedFusedOverfitter(cfg, batch_dev, flows_dev, plan, device=dev)
-    else:
-        o = FusedOverfitter(cfg, batch_dev, flows_dev, device=dev)
-    with torch.no_grad():
-        o.model.backbone.depth.copy_(inputs["depth"])
-        o.model.backbone.weights.copy_(inputs["wparam"])
-    if world > 1:
+
+    def device_flows():
+        return Flows(*(t.to(dev, non_blocking=True) for t in
+                       (flows_host.forward, flows_host.backward, flows_host.forward_mask,
+                        flows_host.backward_mask)))
+
+    def init_params(o):
+        with torch.no_grad():
+            o.model.backbone.depth.copy_(inputs["depth"])
+            o.model.backbone.weights.copy_(inputs["wparam"])
+        o.global_step = START_STEP
+        return o
+
+    flows_dev = device_flows()
+    if pairs_mode:
+        plan = parallel.ShardPlan(rank, world, (rank * (F_ - 1), (rank + 1) * (F_ - 1)), world * (F_ - 1))
+        o = init_params(ShardedFusedOverfitter(OverfitCfg(), batch, flows_dev, plan, device=dev))
         o.sync_boundary_depth()
+    else:
+        tracks = [Tracks(xy, vis, s) for xy, vis, s in synthetic_track_arrays(F_, seed=rank)]
+        o = init_params(FusedOverfitter(OverfitCfg(intrinsics="softmin", use_tracking=True), batch,
+                                        flows_dev, tracks, device=dev))
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t)
+
+    def time_steps(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        clocks.window(t0, time.time())
+        return max_over_ranks(e0.elapsed_time(e1) / steps), out
 
     # ---- device-resident timing (value)
     clocks = ClockSampler(local)
@@ -211,56 +307,40 @@ def run_gpu(args):
         clocks.start()
     for _ in range(args.warmup):
         o.training_step()
-    barrier()
     l0 = lib().fm_launch_count()
-    t_w0 = time.time()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss, _ = o.training_step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / args.steps
+    ms, last = time_steps(o.training_step, args.steps)
     launches = lib().fm_launch_count() - l0
-    clocks.window(t_w0, time.time())
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms = float(t)
-    final_loss = float(loss)
+    final_loss = float(last[0])
 
-    # ---- end-to-end: the step's Flows arrive in pinned host memory every step, the loss is
-    # read back to the host every step (the pretrain-style use of the same API).
+    # ---- end-to-end: the step's Flows arrive in pinned host memory every step (the
+    # pretrain-style use of the same API), the loss is read back to the host every step.
     h2d = sum(x.numel() * 4 for x in (flows_host.forward, flows_host.backward,
                                       flows_host.forward_mask, flows_host.backward_mask))
+
     def e2e_step():
-        # the step's Flows arrive from pinned host memory into the (fixed) device buffers the
-        # step reads; the mask normaliser is recomputed because the masks are "new"
         o.flows.forward.copy_(flows_host.forward, non_blocking=True)
         o.flows.backward.copy_(flows_host.backward, non_blocking=True)
         o.flows.forward_mask.copy_(flows_host.forward_mask, non_blocking=True)
         o.flows.backward_mask.copy_(flows_host.backward_mask, non_blocking=True)
-        ms_ = ops.mask_sum(o.flows.forward_mask, o.flows.backward_mask)
-        if world > 1:
+        ms_ = ops.mask_sum(o.flows.forward_mask, o.flows.backward_mask)  # masks are "new"
+        if pairs_mode:
             ms_ = parallel.global_mask_sum(ms_)
         o._msum.copy_(ms_)
-        l, _ = o.training_step()
-        return float(l)  # D2H read of the step's loss
-    e2e_steps = max(3, min(args.steps, 10))
+        return float(o.training_step()[0])  # D2H read of the step's loss
+
     for _ in range(2):
         e2e_step()
-    barrier()
-    t_w0 = time.time()
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    clocks.window(t_w0, time.time())
-    t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], device=dev, dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    e2e_ms = float(t)
+    e2e_ms, _ = time_steps(e2e_step, max(3, min(args.steps, 10)))
+
+    # ---- flow-loss-only variant of the same step (regressed focal): the path the roofline
+    # accounting below describes
+    flow_only_ms = None
+    if not pairs_mode:
+        o2 = init_params(FusedOverfitter(OverfitCfg(), batch, flows_dev, device=dev))
+        for _ in range(3):
+            o2.training_step()
+        flow_only_ms, _ = time_steps(o2.training_step, min(args.steps, 30))
+        del o2
 
     if rank != 0:
         if world > 1:
@@ -268,35 +348,37 @@ def run_gpu(args):
             torch.distributed.destroy_process_group()
         return
 
-    # ---- per-op timing for the roofline (rank 0, ops called through the C ABI, CUDA events
-    # on the launching stream)
+    # ---- per-op timing for the roofline (rank 0; ops called through the C ABI, CUDA events on
+    # the launching stream)
     with torch.no_grad():
         depths = o.model.backbone.depth.detach()[None].contiguous()
         weights = torch.sigmoid(100.0 * o.model.backbone.weights.detach())[None].contiguous()
-        k3 = o.model.intrinsics.forward(o.batch, o.flows, None, 0)
-        k4 = ops.intrinsics_to_k4(k3).contiguous().clone()
+        s_ = (H_ * W_) ** 0.5
+        k4 = torch.tensor([0.85 * s_ / W_, 0.85 * s_ / H_, 0.5, 0.5], device=dev).expand(1, F_, 4).contiguous()
         msum = ops.mask_sum(o.flows.forward_mask, o.flows.backward_mask)
         ws = ops.workspace(1, F_, H_, W_, dev)
         rt = torch.empty(1, F_ - 1, 3, 4, device=dev)
-        g_depth = torch.empty_like(depths)
-        g_w = torch.empty_like(weights)
-        g_k4 = torch.empty_like(k4)
-        g_rt = torch.empty_like(rt)
+        g_depth, g_w = torch.empty_like(depths), torch.empty_like(weights)
+        g_k4, g_rt = torch.empty_like(k4), torch.empty_like(rt)
         lossb = torch.empty((), device=dev)
         P = lambda x: x.data_ptr()  # noqa: E731
         st = torch.cuda.current_stream().cuda_stream
         L = lib()
+        fl = o.flows
+
         def op_fwd():
-            L.fm_procrustes_fwd(P(depths), P(k4), P(o.flows.backward), P(weights), None, 0, P(rt),
-                                P(ws), 1, F_, H_, W_, st)
+            L.fm_procrustes_fwd(P(depths), P(k4), P(fl.backward), P(weights), None, 0, P(rt), P(ws),
+                                1, F_, H_, W_, st)
+
         def op_flow():
-            L.fm_flow_loss_fwd_bwd(P(depths), P(k4), P(rt), P(o.flows.forward), P(o.flows.backward),
-                                   P(o.flows.forward_mask), P(o.flows.backward_mask), P(msum), 0,
-                                   0.01, 1000.0, 1, P(lossb), P(g_depth), P(g_rt), P(g_k4), P(ws), 1,
-                                   F_, H_, W_, st)
+            L.fm_flow_loss_fwd_bwd(P(depths), P(k4), P(rt), P(fl.forward), P(fl.backward),
+                                   P(fl.forward_mask), P(fl.backward_mask), P(msum), 0, 0.01, 1000.0,
+                                   1, P(lossb), P(g_depth), P(g_rt), P(g_k4), P(ws), 1, F_, H_, W_, st)
+
         def op_bwd():
-            L.fm_procrustes_bwd(P(depths), P(k4), P(o.flows.backward), P(weights), None, 0, None, 1,
-                                None, P(g_depth), P(g_w), P(g_k4), P(ws), 1, F_, H_, W_, st)
+            L.fm_procrustes_bwd(P(depths), P(k4), P(fl.backward), P(weights), None, 0, None, 1, None,
+                                P(g_depth), P(g_w), P(g_k4), P(ws), 1, F_, H_, W_, st)
+
         def timed(fn, n=10):
             for _ in range(3):
                 op_fwd(); op_flow(); fn()
@@ -318,14 +400,13 @@ def run_gpu(args):
         peak, peak_src = json.loads(peaks_path.read_text())["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    n = H_ * W_
-    p_ = F_ - 1
-    ops_bytes = {  # algorithmic bytes per launch of each op: inputs read once, outputs written once
+    n, p_ = H_ * W_, F_ - 1
+    ops_bytes = {  # algorithmic bytes per launch: inputs read once, outputs written once
         "procrustes_fwd(k_moments)": n * (4 * F_ + (8 + 4) * p_),
-        "flow_loss_fwd_bwd(k_flow)": n * (4 * F_ + (8 + 8 + 4 + 4) * p_ + 4 * F_),
+        "flow_loss_fwd_bwd(k_flow_lean)": n * (4 * F_ + (8 + 8 + 4 + 4) * p_ + 4 * F_),
         "procrustes_bwd(k_distribute)": n * (4 * F_ + (8 + 4) * p_ + 4 * p_ + 8 * F_),
     }
-    times = {"procrustes_fwd(k_moments)": t_fwd, "flow_loss_fwd_bwd(k_flow)": t_flow,
+    times = {"procrustes_fwd(k_moments)": t_fwd, "flow_loss_fwd_bwd(k_flow_lean)": t_flow,
              "procrustes_bwd(k_distribute)": t_bwd}
     dom = max(times, key=times.get)
     path_ms = t_fwd + t_flow + t_bwd
@@ -338,34 +419,42 @@ def run_gpu(args):
                          "algorithmic_bytes": algorithmic_bytes(F_, H_, W_),
                          "ms": round(path_ms, 4), "achieved": round(path_gbs, 1),
                          "frac": round(path_gbs / peak, 4)},
-                "ops_ms": {k: round(v, 4) for k, v in times.items()}}
+                "ops_ms": {k: round(v, 4) for k, v in times.items()},
+                "note": "k_distribute is bound by L2 RED (atomic add) throughput, k_flow_lean by FP32 "
+                        "issue, k_moments by L1 gather wavefronts (profiles/README.md); HBM is the "
+                        "denominator the task names"}
 
     if os.environ.get("FM_BENCH_SKIP_CPU") == "1":  # profiling runs (ncu) only
         cpu = {"value": None, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
                "sample": "skipped (FM_BENCH_SKIP_CPU=1)"}
     else:
-        cpu = cpu_baseline(inputs, sample_frames=12, steps=2, warmup=1)
+        cpu = cpu_baseline(sample_frames=12, steps=2, warmup=1, full=not pairs_mode)
 
     its = world * 1000.0 / ms
     out = {
-        "metric": "overfit iters/sec at 150x360x640 (149 frame pairs per iteration)",
-        "value": round(its, 3), "unit": "it/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "frame_pairs_per_s": round(its * (F_ - 1), 1),
-        "config": {"workload": WORKLOAD, "frames": F_, "height": H_, "width": W_,
-                   "shards": f"{world} x {F_ - 1} pairs" if world > 1 else "1 x 149 pairs",
+        "metric": METRIC, "value": round(its, 3), "unit": "it/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "frame_pairs_per_s": round(its * (F_ - 1), 1),
+        "config": {"workload": WORKLOAD if not pairs_mode else
+                   WORKLOAD.replace("softmin intrinsics (60 candidates x 8192 points), flow + tracking loss",
+                                    "regressed focal, flow loss only"),
+                   "frames": F_, "height": H_, "width": W_,
+                   "parallelism": ("%d independent scenes, one per GPU (BASELINE config 5), no "
+                                   "collective" % world) if not pairs_mode else
+                                  ("%d x %d pairs of one video, 1 all-reduce/step of %d bytes"
+                                   % (world, F_ - 1, o.reducer.bytes_per_step())),
                    "l2": "inputs (1.1 GB) exceed the 126 MB L2, no flush needed",
-                   "mask_sum": "loop-invariant denominator hoisted out of the loop (recomputed "
-                               "every step in the e2e leg, where the masks are re-uploaded)",
-                   "collective": ("1 all-reduce/step of %d bytes (loss, d focal, boundary frames)"
-                                  % o.reducer.bytes_per_step()) if world > 1 else "none"},
+                   "mask_sum": "loop-invariant flow-loss denominator hoisted out of the loop "
+                               "(recomputed every step in the e2e leg, where the masks are re-uploaded)"},
         "e2e": {"value": round(world * 1000.0 / e2e_ms, 3), "unit": "it/s",
-                "ms_per_step": round(e2e_ms, 3), "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4,
+                "ms_per_step": round(e2e_ms, 3), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "what": "Flows (flow fwd/bwd + masks) copied from pinned host memory every step, "
                         "loss read back every step"},
         "gpu_launches": int(launches), "final_loss": final_loss,
+        "flow_only": None if flow_only_ms is None else
+        {"ms_per_step": round(flow_only_ms, 4), "it_per_s": round(world * 1000.0 / flow_only_ms, 2),
+         "what": "same step without tracking loss / softmin sweep (regressed focal)"},
         "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(out))
@@ -377,26 +466,24 @@ def run_gpu(args):
 # ------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     """The reference's own CPU implementation of the path.  The reference is pure Python on
-    ATen and cannot travel to the GPU box, so this times the oracle port of it (same op
-    sequence, torch CPU, all host threads) on a bounded sample of the same workload."""
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
+    ATen (no compiled path, cannot travel to the GPU box), so this times the oracle port of it
+    (same op sequence, torch CPU autograd + Adam, the fastest host thread count) on a bounded
+    sample of the same workload."""
+    if int(os.environ.get("RANK", 0)) != 0:
         return
-    inputs = synthetic_inputs(12, H_, W_, seed=0)
-    cpu = cpu_baseline(inputs, sample_frames=12, steps=max(1, args.steps), warmup=args.warmup)
-    out = {
-        "impl": "reference",
-        "metric": "overfit iters/sec at 150x360x640 (149 frame pairs per iteration)",
-        "value": round(cpu["value"], 6), "unit": "it/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
-        "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(1000.0 / cpu["value"], 1), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD}, "cpu_baseline": cpu,
+    # exactly K timed steps; the sample shrinks with K so that the run stays within minutes
+    frames = max(3, min(12, 60 // max(1, args.steps) + 2))
+    cpu = cpu_baseline(sample_frames=frames, steps=max(1, args.steps),
+                       warmup=max(1, min(args.warmup, 2)), full=args.mode != "pairs")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(cpu["value"], 6), "unit": "it/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1000.0 / cpu["value"], 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+        "cpu_baseline": cpu,
         "e2e": {"value": round(cpu["value"], 6), "unit": "it/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(out))
+        "gpu_launches": 0}))
 
 
 def main():
@@ -405,11 +492,12 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="scenes", choices=["scenes", "pairs"])
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
+        args.warmup = max(args.warmup, 3)
         run_gpu(args)
 
 

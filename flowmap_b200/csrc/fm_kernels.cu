@@ -579,14 +579,23 @@ __global__ void k_adjoint(const double* __restrict__ flowacc, const PairState* _
 }
 
 // ================================================================== phase D2: distribute
+// Optional Adam update of the weight logits inside phase D2 (dense path): their gradient is
+// final there and the kernel is bound by L2 REDs, not HBM, so the 28 B/parameter of a separate
+// Adam pass over the weights disappear into it.
+struct AdamFuse {
+  float* m; float* v;
+  float beta1, beta2, omb1, omb2, eps, step_size, bc2_sqrt;
+  int on;
+};
+
 template <int VEC>
 __global__ void __launch_bounds__(kThreads, 3)
 k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
-             const float* __restrict__ bflow, const float* __restrict__ weights,
+             const float* __restrict__ bflow, float* weights,
              const int64_t* __restrict__ indices, int num_indices,
              const PairAdjoint* __restrict__ adj, float* __restrict__ g_depth,
              float* __restrict__ g_weights, double* __restrict__ k4acc, float wsens, PairLayout lay,
-             int H, int W) {
+             AdamFuse adam, int H, int W) {
   __shared__ double smem[8 * (kThreads / 32)];
   __shared__ PairAdjoint s_adj;
   const int pair = blockIdx.y;
@@ -601,7 +610,7 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
   const float* da = depth + pa.depth_a;
   const float* db = da + N;
   const float* fl = bflow + pa.flow;
-  const float* wt = weights ? weights + pa.weight : nullptr;
+  float* wt = weights ? weights + pa.weight : nullptr;
   float* gda = g_depth + pa.depth_a;
   auto load_a = [da, W](int yy, int xx) { return __ldg(da + yy * W + xx); };
   auto scatter = [gda, W](int y0, int x0, float v0, float v1) { red_pair<VEC == 4>(gda + y0 * W, x0, W, v0, v1); };
@@ -618,13 +627,18 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
     const int dr = stride / W, dc = stride - dr * W;
 #pragma unroll 1
     for (; base < N; base += stride) {
-      float dv[VEC], wv[VEC], fv[2 * VEC], gwv[VEC], gdv[VEC];
+      float dv[VEC], wv[VEC], wraw[VEC], fv[2 * VEC], gwv[VEC], gdv[VEC];
       load_vec<VEC>(db + base, dv);
       load_vec2<VEC>(fl + 2 * base, fv);
       if (wt) {
-        load_vec<VEC>(wt + base, wv);
+        if (VEC == 4) {  // plain (coherent) load: the logits may be updated in place below
+          const float4 w4 = *reinterpret_cast<const float4*>(wt + base);
+          wraw[0] = w4.x; wraw[1] = w4.y; wraw[2] = w4.z; wraw[3] = w4.w;
+        } else {
+          wraw[0] = wt[base];
+        }
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) wv[v] = weight_of(wv[v], wsens);
+        for (int v = 0; v < VEC; ++v) wv[v] = weight_of(wraw[v], wsens);
       } else {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
@@ -638,13 +652,29 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
       if (c0 >= W) { c0 -= W; ++r; }
       if (VEC == 4) red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
       else red_add(gdb + base, gdv[0]);
-      if (gw) {
+      if (wt) {
         if (wsens != 0.f) {  // chain rule of the sigmoid: d/d logit = sens * w (1 - w) * d/dw
 #pragma unroll
           for (int v = 0; v < VEC; ++v) gwv[v] *= wsens * wv[v] * (1.0f - wv[v]);
         }
-        if (VEC == 4) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
-        else gw[base] = gwv[0];
+        if (gw) {
+          if (VEC == 4) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
+          else gw[base] = gwv[0];
+        }
+        if (VEC == 4 && adam.on) {  // torch.optim.Adam on the logits, same operation order as k_adam
+          float4 mm = *reinterpret_cast<float4*>(adam.m + pa.weight + base);
+          float4 vv = *reinterpret_cast<float4*>(adam.v + pa.weight + base);
+          float* mp = &mm.x; float* vp = &vv.x;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            mp[v] = mp[v] + adam.omb1 * (gwv[v] - mp[v]);
+            vp[v] = vp[v] * adam.beta2 + adam.omb2 * gwv[v] * gwv[v];
+            wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
+          }
+          *reinterpret_cast<float4*>(adam.m + pa.weight + base) = mm;
+          *reinterpret_cast<float4*>(adam.v + pa.weight + base) = vv;
+          *reinterpret_cast<float4*>(wt + base) = make_float4(wraw[0], wraw[1], wraw[2], wraw[3]);
+        }
       }
     }
   } else {
@@ -662,223 +692,6 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
     }
   }
   // kacc[0..3] -> frame a, kacc[4..7] -> frame b = a + 1: contiguous in k4acc
-  block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
-}
-
-// ------------------------------------------------------------------------------------------
-// Tiled variants of the two gather phases (dense path, W % 32 == 0).  A block owns 32 x 32
-// tiles of the LATER frame; the 64 x 64 window of the EARLIER frame's depth around the tile
-// (16 px halo, shifted by the tile's mean backward flow so that smooth real flows stay
-// inside) is staged in shared memory with coalesced 16-byte loads, and the four bilinear taps
-// of every pixel are read from it (a random 4-byte gather costs ~4 shared-memory wavefronts per
-// warp instruction instead of ~25 L1 wavefronts).  Taps outside the window fall back to global
-// loads.  ncu before: l1tex throughput 82 % (k_moments) / 69 % (k_distribute).
-//
-// The scatter of phase D2 stays on global vector REDs: shared-memory float atomics compile to
-// LDS + FADD + ATOMS.CAST.SPIN loops on sm_100a and measured no faster (profiles/README.md).
-struct AdamFuse {
-  float* m; float* v;
-  float beta1, beta2, omb1, omb2, eps, step_size, bc2_sqrt;
-  int on;
-};
-
-constexpr int kTile = 32, kHalo = 16, kWin = kTile + 2 * kHalo;
-
-// Stage the window whose origin is (wx0, wy0) (wx0 % 4 == 0); cells outside the image hold 0
-// and are never read (taps are clamped into the image).
-__device__ __forceinline__ void load_window(const float* __restrict__ da, int wx0, int wy0, int H, int W,
-                                            float* __restrict__ win) {
-  for (int i = threadIdx.x; i < kWin * kWin / 4; i += kThreads) {
-    const int uy = (i * 4) / kWin, ux = (i * 4) - uy * kWin;
-    const int gy = wy0 + uy, gx = wx0 + ux;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gy >= 0 && gy < H && gx >= 0 && gx + 3 < W) v = __ldg(reinterpret_cast<const float4*>(da + gy * W + gx));
-    reinterpret_cast<float4*>(win)[i] = v;
-  }
-}
-
-// Mean backward flow of the tile -> window origin.  fv: the thread's 4 flow vectors (zeros if
-// the thread's row is outside the image).
-__device__ __forceinline__ void window_origin(const float* fv, const GridDims& grid, int X0, int Y0,
-                                              float* s_mean, int& wx0, int& wy0) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float sx = (fv[0] + fv[2]) + (fv[4] + fv[6]), sy = (fv[1] + fv[3]) + (fv[5] + fv[7]);
-  sx = warp_sum_f(sx); sy = warp_sum_f(sy);
-  __syncthreads();  // previous tile's readers of s_mean / win are done
-  if (lane == 0) { s_mean[warp] = sx; s_mean[kThreads / 32 + warp] = sy; }
-  __syncthreads();
-  float mx = 0.f, my = 0.f;
-#pragma unroll
-  for (int w8 = 0; w8 < kThreads / 32; ++w8) { mx += s_mean[w8]; my += s_mean[kThreads / 32 + w8]; }
-  const int shift_x = ((int)rintf(mx * (1.0f / (kTile * kTile)) * grid.Wf * 0.25f)) * 4;
-  const int shift_y = (int)rintf(my * (1.0f / (kTile * kTile)) * grid.Hf);
-  wx0 = X0 - kHalo + shift_x;
-  wy0 = Y0 - kHalo + shift_y;
-}
-
-__global__ void __launch_bounds__(kThreads, 3)
-k_moments_tiled(const float* __restrict__ depth, const float* __restrict__ k4,
-                const float* __restrict__ bflow, const float* __restrict__ weights,
-                double* __restrict__ moments, float wsens, PairLayout lay, int H, int W) {
-  __shared__ double smem[kNumMoments * (kThreads / 32)];
-  __shared__ __align__(16) float win[kWin * kWin];
-  __shared__ float s_mean[2 * (kThreads / 32)];
-  const int pair = blockIdx.y;
-  const int N = H * W;
-  const PairAddr pa = pair_addr(lay, pair, N);
-  const PairGeom g = pair_geom(depth, k4, pa, H, W);
-  const float* da = depth + pa.depth_a;
-  const float* db = da + N;
-  const float* fl = bflow + pa.flow;
-  const float* wt = weights ? weights + pa.weight : nullptr;
-  float acc[kNumMoments];
-#pragma unroll
-  for (int i = 0; i < kNumMoments; ++i) acc[i] = 0.f;
-  const int tiles_x = W / kTile, tiles_y = (H + kTile - 1) / kTile;
-  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
-    const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
-    const int X0 = txi * kTile, Y0 = tyi * kTile;
-    const int r = Y0 + ty, c0 = X0 + 4 * tx;
-    const bool row_ok = r < H;
-    const int base = r * W + c0;
-    float dv[4], wv[4], fv[8];
-    if (row_ok) {
-      load_vec<4>(db + base, dv);
-      load_vec2<4>(fl + 2 * base, fv);
-      if (wt) {
-        load_vec<4>(wt + base, wv);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) wv[v] = weight_of(wv[v], wsens);
-      } else {
-#pragma unroll
-        for (int v = 0; v < 4; ++v) wv[v] = 1.f;
-      }
-    } else {
-#pragma unroll
-      for (int v = 0; v < 8; ++v) fv[v] = 0.f;
-    }
-    int wx0, wy0;
-    window_origin(fv, g.grid, X0, Y0, s_mean, wx0, wy0);
-    load_window(da, wx0, wy0, H, W, win);
-    __syncthreads();
-    auto load_a = [&](int yy, int xx) {
-      const int ux = xx - wx0, uy = yy - wy0;
-      return ((unsigned)ux < (unsigned)kWin && (unsigned)uy < (unsigned)kWin) ? win[uy * kWin + ux]
-                                                                                : __ldg(da + yy * W + xx);
-    };
-    if (row_ok) {
-      const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        float p[3], q[3];
-        Taps taps;
-        point_pq(g, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], fv[2 * v], fv[2 * v + 1], load_a, p,
-                 q, taps);
-        moments_add(acc, wv[v], p, q);
-      }
-    }
-  }
-  __syncthreads();
-  block_accumulate<kNumMoments>(acc, moments + (size_t)pair * kNumMoments, smem);
-}
-
-__global__ void __launch_bounds__(kThreads, 3)
-k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4,
-                   const float* __restrict__ bflow, float* weights_rw,
-                   const PairAdjoint* __restrict__ adj, float* __restrict__ g_depth,
-                   float* __restrict__ g_weights, double* __restrict__ k4acc, float wsens,
-                   PairLayout lay, AdamFuse adam, int H, int W) {
-  __shared__ double smem[8 * (kThreads / 32)];
-  __shared__ PairAdjoint s_adj;
-  __shared__ __align__(16) float win[kWin * kWin];
-  __shared__ float s_mean[2 * (kThreads / 32)];
-  const int pair = blockIdx.y;
-  const int N = H * W;
-  if (threadIdx.x < sizeof(PairAdjoint) / 4)
-    reinterpret_cast<float*>(&s_adj)[threadIdx.x] = reinterpret_cast<const float*>(adj + pair)[threadIdx.x];
-  __syncthreads();
-  const PairAdjoint ad = s_adj;
-  const PairAddr pa = pair_addr(lay, pair, N);
-  const PairGeom g = pair_geom(depth, k4, pa, H, W);
-  const int a = pa.k4_frame_a;
-  const float* da = depth + pa.depth_a;
-  const float* db = da + N;
-  const float* fl = bflow + pa.flow;
-  float* wt = weights_rw ? weights_rw + pa.weight : nullptr;
-  float* gda = g_depth + pa.depth_a;
-  float* gdb = gda + N;
-  float* gw = g_weights ? g_weights + pa.weight : nullptr;
-  auto scatter = [gda, W](int y0, int x0, float v0, float v1) { red_pair<true>(gda + y0 * W, x0, W, v0, v1); };
-  float kacc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
-  const int tiles_x = W / kTile, tiles_y = (H + kTile - 1) / kTile;
-  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-
-  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
-    const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
-    const int X0 = txi * kTile, Y0 = tyi * kTile;
-    const int r = Y0 + ty, c0 = X0 + 4 * tx;
-    const bool row_ok = r < H;
-    const int base = r * W + c0;
-    float dv[4], wv[4], wraw[4], fv[8], gwv[4], gdv[4];
-    if (row_ok) {
-      load_vec<4>(db + base, dv);
-      load_vec2<4>(fl + 2 * base, fv);
-      if (wt) {
-        const float4 w4 = *reinterpret_cast<const float4*>(wt + base);
-        wraw[0] = w4.x; wraw[1] = w4.y; wraw[2] = w4.z; wraw[3] = w4.w;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) wv[v] = weight_of(wraw[v], wsens);
-      } else {
-#pragma unroll
-        for (int v = 0; v < 4; ++v) wv[v] = 1.f;
-      }
-    } else {
-#pragma unroll
-      for (int v = 0; v < 8; ++v) fv[v] = 0.f;
-    }
-    int wx0, wy0;
-    window_origin(fv, g.grid, X0, Y0, s_mean, wx0, wy0);
-    load_window(da, wx0, wy0, H, W, win);
-    __syncthreads();
-    auto load_a = [&](int yy, int xx) {
-      const int ux = xx - wx0, uy = yy - wy0;
-      return ((unsigned)ux < (unsigned)kWin && (unsigned)uy < (unsigned)kWin) ? win[uy * kWin + ux]
-                                                                                : __ldg(da + yy * W + xx);
-    };
-    if (row_ok) {
-      const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
-#pragma unroll
-      for (int v = 0; v < 4; ++v)
-        distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v], fv[2 * v],
-                         fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
-      red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
-      if (wt) {
-        if (wsens != 0.f) {  // chain rule of the sigmoid: d/d logit = sens * w (1 - w) * d/dw
-#pragma unroll
-          for (int v = 0; v < 4; ++v) gwv[v] *= wsens * wv[v] * (1.0f - wv[v]);
-        }
-        if (gw) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
-        if (adam.on) {  // torch.optim.Adam update of the logits (same operation order as k_adam)
-          float4 mm = *reinterpret_cast<float4*>(adam.m + pa.weight + base);
-          float4 vv = *reinterpret_cast<float4*>(adam.v + pa.weight + base);
-          float* mp = &mm.x; float* vp = &vv.x;
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            mp[v] = mp[v] + adam.omb1 * (gwv[v] - mp[v]);
-            vp[v] = vp[v] * adam.beta2 + adam.omb2 * gwv[v] * gwv[v];
-            wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
-          }
-          *reinterpret_cast<float4*>(adam.m + pa.weight + base) = mm;
-          *reinterpret_cast<float4*>(adam.v + pa.weight + base) = vv;
-          *reinterpret_cast<float4*>(wt + base) = make_float4(wraw[0], wraw[1], wraw[2], wraw[3]);
-        }
-      }
-    }
-  }
-  __syncthreads();
   block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
 }
 
@@ -1553,10 +1366,6 @@ static int procrustes_fwd_impl(const float* depth, const float* k4, const float*
   if (indices) {
     dim3 grid(blocks_for(num_indices, 1), BP);
     k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.moments, wsens, lay, H, W);
-  } else if (W % kTile == 0 && getenv("FM_NO_TILED_GATHER") == nullptr) {
-    const int tiles = (W / kTile) * ((H + kTile - 1) / kTile);
-    dim3 grid((tiles + 7) / 8, BP);
-    k_moments_tiled<<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
     k_moments<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, lay, H, W);
@@ -1592,6 +1401,9 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
   const int BP = B * (F - 1), BF = B * F;
   cudaError_t e = cudaMemsetAsync(w.k4acc, 0, (size_t)BF * 4 * sizeof(double), s);
   if (e != cudaSuccess) return fail("fm_procrustes_bwd: memset", e);
+  AdamFuse af;
+  if (adam) af = *adam; else memset(&af, 0, sizeof(af));
+  float* weights_rw = const_cast<float*>(weights);
   if (include_flow_loss && flow_scale) {
     // the direct depth gradient already sitting in g_depth was computed for scale 1
     k_scale_inplace<<<148 * 4, kThreads, 0, s>>>(g_depth, flow_scale, (size_t)BF * H * W);
@@ -1601,19 +1413,13 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
   FM_CHECK_LAUNCH("fm_procrustes_bwd: k_adjoint");
   if (indices) {
     dim3 grid(blocks_for(num_indices, 1), BP);
-    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, H, W);
-  } else if (W % kTile == 0 && getenv("FM_NO_TILED_GATHER") == nullptr) {
-    const int tiles = (W / kTile) * ((H + kTile - 1) / kTile);
-    dim3 grid((tiles + 7) / 8, BP);
-    AdamFuse af;
-    if (adam) af = *adam; else { memset(&af, 0, sizeof(af)); }
-    k_distribute_tiled<<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, const_cast<float*>(weights), w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
+    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
-    k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, H, W);
+    k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   } else {
     dim3 grid(blocks_for(H * W, 1), BP);
-    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, H, W);
+    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   }
   FM_CHECK_LAUNCH("fm_procrustes_bwd: k_distribute");
   k_k4_finalize<<<(BF + 127) / 128, 128, 0, s>>>(w.k4acc, w.flowacc, include_flow_loss, flow_scale, g_k4, B, F);
@@ -1921,9 +1727,8 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
   }
   AdamFuse af;
   memset(&af, 0, sizeof(af));
-  const bool fuse_w = a->step > 0 && a->weight_logits && !a->indices && W % kTile == 0 &&
-                      getenv("FM_NO_TILED_GATHER") == nullptr;
-  if (fuse_w) {  // the weight gradient is final inside k_distribute_tiled: update the logits there
+  const bool fuse_w = a->step > 0 && a->weight_logits && !a->indices && W % 4 == 0;
+  if (fuse_w) {  // the weight gradient is final inside k_distribute: update the logits there
     af.on = 1; af.m = a->m_weights; af.v = a->v_weights;
     af.beta1 = (float)a->beta1; af.beta2 = (float)a->beta2;
     af.omb1 = (float)(1.0 - a->beta1); af.omb2 = (float)(1.0 - a->beta2); af.eps = (float)a->eps;
