@@ -25,7 +25,12 @@ SIGNATURES = {
     "fm_workspace_reset": (c_int, [_P, c_int, c_int, c_int, c_int, _P]),
     "fm_unproject": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "fm_unproject_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
-    "fm_reproject": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
+    "fm_reproject": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "fm_unproject_points": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "fm_unproject_points_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "fm_points_workspace_bytes": (c_size_t, [c_int]),
+    "fm_align_rigid_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "fm_align_rigid_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
     "fm_procrustes_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "fm_procrustes_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P, _P,
                                   c_int, c_int, c_int, c_int, _P]),
@@ -40,6 +45,7 @@ SIGNATURES = {
     "fm_track_loss_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, ctypes.c_longlong,
                                   c_int, c_float, c_float, _P, _P, _P, _P, _P, c_int, c_int, c_int,
                                   _P]),
+    "fm_random_subset": (c_int, [ctypes.c_ulonglong, ctypes.c_longlong, c_int, _P, _P]),
     "fm_softmin_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fm_softmin_sweep_fwd": (c_int, [_P, _P, c_float, _P, _P, c_int, _P, c_int, _P, _P, _P, c_int, c_int,
                                      c_int, c_int, _P]),

@@ -783,7 +783,8 @@ __global__ void k_d2f(const double* __restrict__ src, float* __restrict__ dst, i
 }
 
 __global__ void k_reproject(const float* __restrict__ xyz, const float* __restrict__ rt,
-                            const float* __restrict__ k4, float* __restrict__ xy, int n) {
+                            const float* __restrict__ k4, float* __restrict__ xy,
+                            unsigned char* __restrict__ in_front, int n) {
   const int item = blockIdx.y;
   const Rt t = load_rt(rt, item);
   const Cam k = make_cam(load_k4(k4, item));
@@ -796,60 +797,93 @@ __global__ void k_reproject(const float* __restrict__ xyz, const float* __restri
     const Proj pr = project_point(X0, X1, X2, k);
     float* o = xy + ((size_t)item * n + j) * 2;
     o[0] = pr.uvx; o[1] = pr.uvy;
+    if (in_front) in_front[(size_t)item * n + j] = X2 >= 0.f ? 1 : 0;  // projection.py:72
   }
 }
 
-// P_0 = I, P_{k+1} = P_k @ T_k in float32, one thread per batch item (projection.py:207-209).
+// P_0 = I, P_{k+1} = P_k @ T_k in float32 (projection.py:207-209).  One block per batch item:
+// the block stages all [R|t] in shared memory with coalesced loads, thread 0 runs the
+// (inherently sequential) product out of shared memory, then the block writes the result.
+// (The first version walked global memory from a single thread: 50 us for 149 pairs.)
 __global__ void k_pose_chain(const float* __restrict__ rt, float* __restrict__ ext, int B, int F) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  float P[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-  float* o = ext + (size_t)b * F * 16;
-  for (int k = 0;; ++k) {
-    for (int i = 0; i < 12; ++i) o[(size_t)k * 16 + i] = P[i];
-    o[(size_t)k * 16 + 12] = 0.f; o[(size_t)k * 16 + 13] = 0.f; o[(size_t)k * 16 + 14] = 0.f; o[(size_t)k * 16 + 15] = 1.f;
-    if (k == F - 1) break;
-    const float* T = rt + ((size_t)b * (F - 1) + k) * 12;
-    float Q[12];
-    for (int r = 0; r < 3; ++r) {
-      for (int c = 0; c < 4; ++c) {
-        float s = P[r * 4 + 0] * T[0 * 4 + c] + P[r * 4 + 1] * T[1 * 4 + c] + P[r * 4 + 2] * T[2 * 4 + c];
-        if (c == 3) s += P[r * 4 + 3];
-        Q[r * 4 + c] = s;
+  extern __shared__ float sm[];  // [F-1][12] inputs, then [F][12] outputs
+  const int b = blockIdx.x;
+  const int P = F - 1;
+  float* tin = sm;
+  float* pout = sm + (size_t)P * 12;
+  for (int i = threadIdx.x; i < P * 12; i += blockDim.x) tin[i] = __ldg(rt + (size_t)b * P * 12 + i);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float Pm[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    for (int k = 0;; ++k) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) pout[k * 12 + i] = Pm[i];
+      if (k == P) break;
+      const float* T = tin + k * 12;
+      float Q[12];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float v = Pm[r * 4 + 0] * T[0 * 4 + c] + Pm[r * 4 + 1] * T[1 * 4 + c] + Pm[r * 4 + 2] * T[2 * 4 + c];
+          if (c == 3) v += Pm[r * 4 + 3];
+          Q[r * 4 + c] = v;
+        }
       }
+#pragma unroll
+      for (int i = 0; i < 12; ++i) Pm[i] = Q[i];
     }
-    for (int i = 0; i < 12; ++i) P[i] = Q[i];
+  }
+  __syncthreads();
+  float* o = ext + (size_t)b * F * 16;
+  for (int i = threadIdx.x; i < F * 16; i += blockDim.x) {
+    const int k = i >> 4, e = i & 15;
+    o[i] = e < 12 ? pout[k * 12 + e] : (e == 15 ? 1.f : 0.f);
   }
 }
 
 // Adjoint of the chain.  With G_k = dL/dP_k (top 3 rows matter; the bottom row is constant):
 // acc_{F-1} = G_{F-1}; dT_k = P_k^T acc_{k+1} (3x4 part); acc_k = G_k + acc_{k+1} T_k^T.
+// Same staging: inputs in shared memory, thread 0 runs the reverse recursion.
 __global__ void k_pose_chain_bwd(const float* __restrict__ rt, const float* __restrict__ ext,
                                  const float* __restrict__ g_ext, float* __restrict__ g_rt, int B, int F) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  double acc[12];
-  const float* G = g_ext + ((size_t)b * F + (F - 1)) * 16;
-  for (int i = 0; i < 12; ++i) acc[i] = G[i];
-  for (int k = F - 2; k >= 0; --k) {
-    const float* P = ext + ((size_t)b * F + k) * 16;
-    const float* T = rt + ((size_t)b * (F - 1) + k) * 12;
-    float* o = g_rt + ((size_t)b * (F - 1) + k) * 12;
-    // P_{k+1}[r][c] = sum_m P_k[r][m] T4[m][c] (T4 = [T; 0 0 0 1]); dT[m][c] = sum_r P_k[r][m] acc[r][c], m < 3
-    for (int m = 0; m < 3; ++m)
-      for (int c = 0; c < 4; ++c)
-        o[m * 4 + c] = (float)(P[0 * 4 + m] * acc[0 * 4 + c] + P[1 * 4 + m] * acc[1 * 4 + c] + P[2 * 4 + m] * acc[2 * 4 + c]);
-    // dP_k[r][m] = sum_c acc[r][c] T4[m][c]
-    double nxt[12];
-    const float* Gk = g_ext + ((size_t)b * F + k) * 16;
-    for (int r = 0; r < 3; ++r) {
-      for (int m = 0; m < 3; ++m)
-        nxt[r * 4 + m] = Gk[r * 4 + m] + acc[r * 4 + 0] * T[m * 4 + 0] + acc[r * 4 + 1] * T[m * 4 + 1] +
-                         acc[r * 4 + 2] * T[m * 4 + 2] + acc[r * 4 + 3] * T[m * 4 + 3];
-      nxt[r * 4 + 3] = Gk[r * 4 + 3] + acc[r * 4 + 3];
-    }
-    for (int i = 0; i < 12; ++i) acc[i] = nxt[i];
+  extern __shared__ float sm[];  // T [P][12], P [F][12], G [F][12], out [P][12]
+  const int b = blockIdx.x;
+  const int Pn = F - 1;
+  float* tin = sm;
+  float* pin = tin + (size_t)Pn * 12;
+  float* gin = pin + (size_t)F * 12;
+  float* out = gin + (size_t)F * 12;
+  for (int i = threadIdx.x; i < Pn * 12; i += blockDim.x) tin[i] = __ldg(rt + (size_t)b * Pn * 12 + i);
+  for (int i = threadIdx.x; i < F * 12; i += blockDim.x) {
+    const int k = i / 12, e = i - k * 12;
+    pin[i] = __ldg(ext + ((size_t)b * F + k) * 16 + e);
+    gin[i] = __ldg(g_ext + ((size_t)b * F + k) * 16 + e);
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double acc[12];
+    for (int i = 0; i < 12; ++i) acc[i] = gin[(F - 1) * 12 + i];
+    for (int k = F - 2; k >= 0; --k) {
+      const float* Pm = pin + k * 12;
+      const float* T = tin + k * 12;
+      float* o = out + k * 12;
+      for (int m = 0; m < 3; ++m)
+        for (int c = 0; c < 4; ++c)
+          o[m * 4 + c] = (float)(Pm[0 * 4 + m] * acc[0 * 4 + c] + Pm[1 * 4 + m] * acc[1 * 4 + c] + Pm[2 * 4 + m] * acc[2 * 4 + c]);
+      double nxt[12];
+      const float* Gk = gin + k * 12;
+      for (int r = 0; r < 3; ++r) {
+        for (int m = 0; m < 3; ++m)
+          nxt[r * 4 + m] = Gk[r * 4 + m] + acc[r * 4 + 0] * T[m * 4 + 0] + acc[r * 4 + 1] * T[m * 4 + 1] +
+                           acc[r * 4 + 2] * T[m * 4 + 2] + acc[r * 4 + 3] * T[m * 4 + 3];
+        nxt[r * 4 + 3] = Gk[r * 4 + 3] + acc[r * 4 + 3];
+      }
+      for (int i = 0; i < 12; ++i) acc[i] = nxt[i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Pn * 12; i += blockDim.x) g_rt[(size_t)b * Pn * 12 + i] = out[i];
 }
 
 // torch.optim.Adam (single-tensor, no amsgrad / weight decay), same operation order.
@@ -887,17 +921,24 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
 // projection.py:255-298 (compute_track_flow) + loss_tracking.py:28-61, all segments in one
 // launch.  Samples are packed per segment: sample(s, row, p) = seg.sample_start + row * n + p.
 // seg table (int32 x 4 per segment): sample_start, rows f_s, points n_s, start_frame.
-//   k_track_fwd      block = (segment, source row, point chunk): bilinear-sample xyz at the track
-//                    location, lift to world space (stored), loop over the segment's target rows:
-//                    loss sum + valid count.
-//   k_track_bwd_src  same mapping: gradient w.r.t. the source sample -> depth (bilinear scatter),
-//                    K of the source frame (unprojection), pose of the source frame (twist).
-//   k_track_bwd_tgt  block = (segment, target row, point chunk), loop over source rows: gradient
-//                    w.r.t. the target frame's pose (twist) and K (projection).
-// Pose gradients are accumulated as left-perturbation twists (a = d/d omega, b = d/d v with
-// delta R = [omega]x R, delta t = v) and expanded to an ambient 3x4 gradient in k_track_finalize;
-// only the tangent part survives the rigid chain / Procrustes adjoint.
-constexpr int kTrackAcc = 10;  // per frame: dK (4), a (3), b (3)
+//
+// The loss is sum / count with a count that depends on the PREDICTED positions, so the
+// gradient scale is only known after a full pass.  Everything is therefore accumulated
+// unscaled in ONE sweep over the (source, target, point) triples per direction and scaled at
+// the end:
+//   k_track_src     block = (segment, source row, point chunk): bilinear-sample xyz at the track
+//                   location, lift to world space (stored), loop over the segment's target rows:
+//                   loss sum + valid count, the unscaled camera-space adjoint of the sampled
+//                   point (stored per sample), source-frame K / pose-twist sums.
+//   k_track_tgt     block = (segment, target row, point chunk), loop over source rows (world
+//                   points from scratch): target-frame pose-twist and K sums.
+//   k_track_apply   (backward) per sample: scale * adjoint -> bilinear scatter into the depth
+//                   gradient (4 REDs).
+//   k_track_finalize  scale the per-frame sums, expand twists to ambient 3x4 gradients.
+// Pose gradients are left-perturbation twists (a = d/d omega, b = d/d v with delta R = [omega]x R,
+// delta t = v); only the tangent part survives the rigid chain / Procrustes adjoint.
+constexpr int kTrackAcc = 10;   // per frame: dK (4), a (3), b (3)
+constexpr int kTrackRec = 24;   // per-frame record in shared memory, see load_segment_frames
 
 struct SegInfo { int sample_start, rows, n, start_frame; };
 
@@ -907,44 +948,59 @@ __device__ __forceinline__ SegInfo load_seg(const int* seg, int s) {
   return i;
 }
 
-// Segment poses / cameras in shared memory: [row][18] = R(9) t(3) fx fy cx cy ifx ify
+// Per-frame record: R (9, row-major, camera-to-world), t (3), c = -R^T t (3), fx fy cx cy ifx ify,
+// 3 pad.
 __device__ __forceinline__ void load_segment_frames(float* sm, const float* ext, const float* k4,
                                                     const SegInfo& si) {
-  for (int i = threadIdx.x; i < si.rows * 18; i += blockDim.x) {
-    const int row = i / 18, e = i - row * 18;
-    const int frame = si.start_frame + row;
-    float v;
-    if (e < 9) v = __ldg(ext + (size_t)frame * 16 + (e / 3) * 4 + (e % 3));
-    else if (e < 12) v = __ldg(ext + (size_t)frame * 16 + (e - 9) * 4 + 3);
-    else if (e < 16) v = __ldg(k4 + (size_t)frame * 4 + (e - 12));
-    else v = 1.0f / __ldg(k4 + (size_t)frame * 4 + (e - 16));
-    sm[i] = v;
+  for (int row = threadIdx.x; row < si.rows; row += blockDim.x) {
+    const float* P = ext + (size_t)(si.start_frame + row) * 16;
+    float* o = sm + row * kTrackRec;
+    float R[9], t[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      R[i * 3 + 0] = __ldg(P + i * 4 + 0); R[i * 3 + 1] = __ldg(P + i * 4 + 1); R[i * 3 + 2] = __ldg(P + i * 4 + 2);
+      t[i] = __ldg(P + i * 4 + 3);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[i] = R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      o[9 + i] = t[i];
+      o[12 + i] = -(R[0 * 3 + i] * t[0] + R[1 * 3 + i] * t[1] + R[2 * 3 + i] * t[2]);
+    }
+    const float4 k = __ldg(reinterpret_cast<const float4*>(k4) + si.start_frame + row);
+    o[15] = k.x; o[16] = k.y; o[17] = k.z; o[18] = k.w; o[19] = 1.0f / k.x; o[20] = 1.0f / k.y;
   }
   __syncthreads();
 }
-__device__ __forceinline__ Pose sm_pose(const float* sm, int row) {
-  Pose p;
-#pragma unroll
-  for (int i = 0; i < 9; ++i) p.r[i] = sm[row * 18 + i];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) p.t[i] = sm[row * 18 + 9 + i];
-  return p;
-}
-__device__ __forceinline__ Cam sm_cam(const float* sm, int row) {
+__device__ __forceinline__ Cam sm_cam(const float* rec) {
   Cam c;
-  c.fx = sm[row * 18 + 12]; c.fy = sm[row * 18 + 13]; c.cx = sm[row * 18 + 14];
-  c.cy = sm[row * 18 + 15]; c.ifx = sm[row * 18 + 16]; c.ify = sm[row * 18 + 17];
+  c.fx = rec[15]; c.fy = rec[16]; c.cx = rec[17]; c.cy = rec[18]; c.ifx = rec[19]; c.ify = rec[20];
   return c;
 }
 
-template <bool BWD>
+// One (world point, target frame) term: Y = R_t^T Xw + c_t, project, validity, robust loss and
+// the unscaled adjoint.  Returns false (and leaves outputs unspecified) when invalid.
+__device__ __forceinline__ bool track_term_lean(const float* rec, const float* Xw, float gtx, float gty,
+                                                const RobustCfg& rc, LeanTerm& t, float* g) {
+  const float dir0 = fm_fma(rec[0], Xw[0], fm_fma(rec[3], Xw[1], rec[6] * Xw[2]));
+  const float dir1 = fm_fma(rec[1], Xw[0], fm_fma(rec[4], Xw[1], rec[7] * Xw[2]));
+  const float dir2 = fm_fma(rec[2], Xw[0], fm_fma(rec[5], Xw[1], rec[8] * Xw[2]));
+  t = lean_term(1.0f, dir0, dir1, dir2, rec[12], rec[13], rec[14], sm_cam(rec), gtx, gty, 0.f, 0.f, 1.0f, rc);
+  if (!in_unit_square(t.uvx, t.uvy)) return false;  // projection.py:294-296 (predicted target)
+  // world-space gradient g = R_t dY
+  g[0] = fm_fma(rec[0], t.d0, fm_fma(rec[1], t.d1, rec[2] * t.d2));
+  g[1] = fm_fma(rec[3], t.d0, fm_fma(rec[4], t.d1, rec[5] * t.d2));
+  g[2] = fm_fma(rec[6], t.d0, fm_fma(rec[7], t.d1, rec[8] * t.d2));
+  return true;
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const float* __restrict__ ext,
             const int* __restrict__ seg, const float* __restrict__ txy,
-            const unsigned char* __restrict__ tvis, int mapping, float delta, float loss_weight,
-            const float* __restrict__ go, double* __restrict__ sums, float* __restrict__ xw,
-            unsigned char* __restrict__ flag, float* __restrict__ g_depth, double* __restrict__ trackacc,
-            int H, int W) {
+            const unsigned char* __restrict__ tvis, int mapping, float delta, double* __restrict__ sums,
+            float* __restrict__ xw, unsigned char* __restrict__ flag, float* __restrict__ dq_out,
+            double* __restrict__ trackacc, int H, int W) {
   extern __shared__ float sm[];
   __shared__ double red[kTrackAcc * (kThreads / 32)];
   const SegInfo si = load_seg(seg, blockIdx.z);
@@ -952,23 +1008,16 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
   if (row >= si.rows) return;
   load_segment_frames(sm, ext, k4, si);
   const int p = blockIdx.x * kThreads + threadIdx.x;
-  const bool active = p < si.n;
   const GridDims grid = make_grid(H, W);
   const RobustCfg rc = make_robust(mapping, delta, H, W);
   const int frame = si.start_frame + row;
   const float* D = depth + (size_t)frame * H * W;
-  const Pose ps = sm_pose(sm, row);
-  const Cam ks = sm_cam(sm, row);
-  float acc[kTrackAcc];
+  const float* rs = sm + row * kTrackRec;
+  const Cam ks = sm_cam(rs);
+  float acc[kTrackAcc], lc[2] = {0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < kTrackAcc; ++i) acc[i] = 0.f;
-  float scale = 0.f;
-  if (BWD) {
-    double cnt = sums[1];
-    if (cnt == 0.0) cnt = 1.0;  // loss_tracking.py:61 "valid_sum or 1"
-    scale = (float)((double)loss_weight * (go ? (double)*go : 1.0) / cnt);
-  }
-  if (active) {
+  if (p < si.n) {
     const size_t sidx = (size_t)si.sample_start + (size_t)row * si.n + p;
     const float2 sxy = __ldg(reinterpret_cast<const float2*>(txy) + sidx);
     const bool src_ok = tvis[sidx] && in_unit_square(sxy.x, sxy.y);
@@ -978,66 +1027,45 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
     float Xw[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
-      Xw[i] = ps.r[i * 3 + 0] * q[0] + ps.r[i * 3 + 1] * q[1] + ps.r[i * 3 + 2] * q[2] + ps.t[i];
-    if (!BWD) {
-      xw[sidx * 3 + 0] = Xw[0]; xw[sidx * 3 + 1] = Xw[1]; xw[sidx * 3 + 2] = Xw[2];
-      flag[sidx] = src_ok ? 1 : 0;
-    }
+      Xw[i] = fm_fma(rs[i * 3 + 0], q[0], fm_fma(rs[i * 3 + 1], q[1], fm_fma(rs[i * 3 + 2], q[2], rs[9 + i])));
+    xw[sidx * 3 + 0] = Xw[0]; xw[sidx * 3 + 1] = Xw[1]; xw[sidx * 3 + 2] = Xw[2];
+    flag[sidx] = src_ok ? 1 : 0;
+    float G[3] = {0.f, 0.f, 0.f};
     if (src_ok) {
-      float G[3] = {0.f, 0.f, 0.f};
       for (int ft = 0; ft < si.rows; ++ft) {
         const size_t tidx = (size_t)si.sample_start + (size_t)ft * si.n + p;
         if (!tvis[tidx]) continue;
         const float2 gxy = __ldg(reinterpret_cast<const float2*>(txy) + tidx);
-        const Pose pt = sm_pose(sm, ft);
-        const Cam kt = sm_cam(sm, ft);
-        float l, d[3], Y[3], gux, guy;
-        Proj pr;
-        const bool valid = track_term(pt, kt, Xw, gxy.x, gxy.y, true, rc, l, d, Y, pr, gux, guy);
-        if (!valid) continue;
-        if (!BWD) {
-          acc[0] += l;
-          acc[1] += 1.f;
-        } else {
-          float dY0, dY1, dY2, u0 = 0, u1 = 0, u2 = 0, u3 = 0;
-          project_point_adj(pr, Y[0], Y[1], Y[2], kt, scale * gux, scale * guy, dY0, dY1, dY2, u0, u1, u2, u3);
-          G[0] += pt.r[0] * dY0 + pt.r[1] * dY1 + pt.r[2] * dY2;
-          G[1] += pt.r[3] * dY0 + pt.r[4] * dY1 + pt.r[5] * dY2;
-          G[2] += pt.r[6] * dY0 + pt.r[7] * dY1 + pt.r[8] * dY2;
-        }
-      }
-      if (BWD) {
-        // camera-space adjoint of the sampled point, scatter to the four depth taps
-        const float dq0 = ps.r[0] * G[0] + ps.r[3] * G[1] + ps.r[6] * G[2];
-        const float dq1 = ps.r[1] * G[0] + ps.r[4] * G[1] + ps.r[7] * G[2];
-        const float dq2 = ps.r[2] * G[0] + ps.r[5] * G[1] + ps.r[8] * G[2];
-        float rx0, ry0, rx1, ry1;
-        tap_rays(t, grid, ks, rx0, ry0, rx1, ry1);
-        float* gd = g_depth + (size_t)frame * H * W;
-        red_add(gd + t.y0 * W + t.x0, t.w00 * (dq0 * rx0 + dq1 * ry0 + dq2));
-        red_add(gd + t.y0 * W + t.x1, t.w01 * (dq0 * rx1 + dq1 * ry0 + dq2));
-        red_add(gd + t.y1 * W + t.x0, t.w10 * (dq0 * rx0 + dq1 * ry1 + dq2));
-        red_add(gd + t.y1 * W + t.x1, t.w11 * (dq0 * rx1 + dq1 * ry1 + dq2));
-        const float e0 = dq0 * ks.ifx, e1 = dq1 * ks.ify;
-        acc[0] -= e0 * q[0]; acc[1] -= e1 * q[1]; acc[2] -= e0 * q[2]; acc[3] -= e1 * q[2];
-        const float c0 = Xw[0] - ps.t[0], c1 = Xw[1] - ps.t[1], c2 = Xw[2] - ps.t[2];
-        acc[4] += c1 * G[2] - c2 * G[1];
-        acc[5] += c2 * G[0] - c0 * G[2];
-        acc[6] += c0 * G[1] - c1 * G[0];
-        acc[7] += G[0]; acc[8] += G[1]; acc[9] += G[2];
+        LeanTerm lt;
+        float g[3];
+        if (!track_term_lean(sm + ft * kTrackRec, Xw, gxy.x, gxy.y, rc, lt, g)) continue;
+        lc[0] += lt.loss;
+        lc[1] += 1.f;
+        G[0] += g[0]; G[1] += g[1]; G[2] += g[2];
       }
     }
+    // camera-space adjoint of the sampled point (unscaled), source K / twist sums
+    const float dq0 = fm_fma(rs[0], G[0], fm_fma(rs[3], G[1], rs[6] * G[2]));
+    const float dq1 = fm_fma(rs[1], G[0], fm_fma(rs[4], G[1], rs[7] * G[2]));
+    const float dq2 = fm_fma(rs[2], G[0], fm_fma(rs[5], G[1], rs[8] * G[2]));
+    dq_out[sidx * 3 + 0] = dq0; dq_out[sidx * 3 + 1] = dq1; dq_out[sidx * 3 + 2] = dq2;
+    const float e0 = dq0 * ks.ifx, e1 = dq1 * ks.ify;
+    acc[0] = -e0 * q[0]; acc[1] = -e1 * q[1]; acc[2] = -e0 * q[2]; acc[3] = -e1 * q[2];
+    const float c0 = Xw[0] - rs[9], c1 = Xw[1] - rs[10], c2 = Xw[2] - rs[11];
+    acc[4] = c1 * G[2] - c2 * G[1];
+    acc[5] = c2 * G[0] - c0 * G[2];
+    acc[6] = c0 * G[1] - c1 * G[0];
+    acc[7] = G[0]; acc[8] = G[1]; acc[9] = G[2];
   }
-  if (!BWD) block_accumulate<2>(acc, sums, red);
-  else block_accumulate<kTrackAcc>(acc, trackacc + (size_t)frame * kTrackAcc, red);
+  block_accumulate<2>(lc, sums, red);
+  block_accumulate<kTrackAcc>(acc, trackacc + (size_t)frame * kTrackAcc, red);
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_track_bwd_tgt(const float* __restrict__ k4, const float* __restrict__ ext, const int* __restrict__ seg,
-                const float* __restrict__ txy, const unsigned char* __restrict__ tvis, int mapping,
-                float delta, float loss_weight, const float* __restrict__ go,
-                const double* __restrict__ sums, const float* __restrict__ xw,
-                const unsigned char* __restrict__ flag, double* __restrict__ trackacc, int H, int W) {
+k_track_tgt(const float* __restrict__ k4, const float* __restrict__ ext, const int* __restrict__ seg,
+            const float* __restrict__ txy, const unsigned char* __restrict__ tvis, int mapping, float delta,
+            const float* __restrict__ xw, const unsigned char* __restrict__ flag,
+            double* __restrict__ trackacc, int H, int W) {
   extern __shared__ float sm[];
   __shared__ double red[kTrackAcc * (kThreads / 32)];
   const SegInfo si = load_seg(seg, blockIdx.z);
@@ -1046,11 +1074,7 @@ k_track_bwd_tgt(const float* __restrict__ k4, const float* __restrict__ ext, con
   load_segment_frames(sm, ext, k4, si);
   const int p = blockIdx.x * kThreads + threadIdx.x;
   const RobustCfg rc = make_robust(mapping, delta, H, W);
-  const Pose pt = sm_pose(sm, ft);
-  const Cam kt = sm_cam(sm, ft);
-  double cnt = sums[1];
-  if (cnt == 0.0) cnt = 1.0;
-  const float scale = (float)((double)loss_weight * (go ? (double)*go : 1.0) / cnt);
+  const float* rec = sm + ft * kTrackRec;
   float acc[kTrackAcc];
 #pragma unroll
   for (int i = 0; i < kTrackAcc; ++i) acc[i] = 0.f;
@@ -1062,39 +1086,80 @@ k_track_bwd_tgt(const float* __restrict__ k4, const float* __restrict__ ext, con
         const size_t sidx = (size_t)si.sample_start + (size_t)fs * si.n + p;
         if (!flag[sidx]) continue;
         const float Xw[3] = {xw[sidx * 3 + 0], xw[sidx * 3 + 1], xw[sidx * 3 + 2]};
-        float l, d[3], Y[3], gux, guy;
-        Proj pr;
-        if (!track_term(pt, kt, Xw, gxy.x, gxy.y, true, rc, l, d, Y, pr, gux, guy)) continue;
-        float dY0, dY1, dY2;
-        project_point_adj(pr, Y[0], Y[1], Y[2], kt, scale * gux, scale * guy, dY0, dY1, dY2, acc[0],
-                          acc[1], acc[2], acc[3]);
-        const float g0 = pt.r[0] * dY0 + pt.r[1] * dY1 + pt.r[2] * dY2;
-        const float g1 = pt.r[3] * dY0 + pt.r[4] * dY1 + pt.r[5] * dY2;
-        const float g2 = pt.r[6] * dY0 + pt.r[7] * dY1 + pt.r[8] * dY2;
-        acc[4] -= d[1] * g2 - d[2] * g1;
-        acc[5] -= d[2] * g0 - d[0] * g2;
-        acc[6] -= d[0] * g1 - d[1] * g0;
-        acc[7] -= g0; acc[8] -= g1; acc[9] -= g2;
+        LeanTerm lt;
+        float g[3];
+        if (!track_term_lean(rec, Xw, gxy.x, gxy.y, rc, lt, g)) continue;
+        // projection K gradient of the target frame: d/dfx = duvx u0 etc. -> recover from su parts
+        // (lean_term folds them; recompute the four terms from the adjoint pieces)
+        const float inv = fm_rcp(lt.P2 + kProjEps);
+        const float u0 = lt.P0 * inv, u1 = lt.P1 * inv, u2 = lt.P2 * inv;
+        const Cam kt = sm_cam(rec);
+        // du0 = fx duvx = d0 / inv  =>  duvx = d0 / (inv fx)
+        const float duvx = lt.d0 * (lt.P2 + kProjEps) * kt.ifx, duvy = lt.d1 * (lt.P2 + kProjEps) * kt.ify;
+        acc[0] = fm_fma(duvx, u0, acc[0]);
+        acc[1] = fm_fma(duvy, u1, acc[1]);
+        acc[2] = fm_fma(duvx, u2, acc[2]);
+        acc[3] = fm_fma(duvy, u2, acc[3]);
+        const float d0 = Xw[0] - rec[9], d1 = Xw[1] - rec[10], d2 = Xw[2] - rec[11];
+        acc[4] -= d1 * g[2] - d2 * g[1];
+        acc[5] -= d2 * g[0] - d0 * g[2];
+        acc[6] -= d0 * g[1] - d1 * g[0];
+        acc[7] -= g[0]; acc[8] -= g[1]; acc[9] -= g[2];
       }
     }
   }
   block_accumulate<kTrackAcc>(acc, trackacc + (size_t)(si.start_frame + ft) * kTrackAcc, red);
 }
 
-__global__ void k_track_loss(const double* __restrict__ sums, float loss_weight, float* __restrict__ loss) {
+__device__ __forceinline__ double track_scale(const double* sums, float loss_weight, const float* go) {
   double cnt = sums[1];
-  if (cnt == 0.0) cnt = 1.0;
-  *loss = (float)((double)loss_weight * sums[0] / cnt);
+  if (cnt == 0.0) cnt = 1.0;  // loss_tracking.py:61 "valid_sum or 1"
+  return (double)loss_weight * (go ? (double)*go : 1.0) / cnt;
 }
 
-__global__ void k_track_finalize(const double* __restrict__ trackacc, const float* __restrict__ ext,
-                                 float* __restrict__ g_ext, float* __restrict__ g_k4, int F) {
+__global__ void k_track_loss(const double* __restrict__ sums, float loss_weight, float* __restrict__ loss) {
+  *loss = (float)(track_scale(sums, loss_weight, nullptr) * sums[0]);
+}
+
+// scale * (stored camera-space adjoint) -> the four depth taps of every source sample.
+__global__ void __launch_bounds__(kThreads)
+k_track_apply(const float* __restrict__ k4, const int* __restrict__ seg, const float* __restrict__ txy,
+              const unsigned char* __restrict__ flag, const float* __restrict__ dq,
+              const double* __restrict__ sums, float loss_weight, const float* __restrict__ go,
+              float* __restrict__ g_depth, int H, int W) {
+  const SegInfo si = load_seg(seg, blockIdx.z);
+  const int row = blockIdx.y;
+  const int p = blockIdx.x * kThreads + threadIdx.x;
+  if (row >= si.rows || p >= si.n) return;
+  const size_t sidx = (size_t)si.sample_start + (size_t)row * si.n + p;
+  if (!flag[sidx]) return;
+  const float scale = (float)track_scale(sums, loss_weight, go);
+  const int frame = si.start_frame + row;
+  const GridDims grid = make_grid(H, W);
+  const Cam ks = make_cam(load_k4(k4, frame));
+  const float2 sxy = __ldg(reinterpret_cast<const float2*>(txy) + sidx);
+  const Taps t = bilinear_taps(sxy.x, sxy.y, grid);
+  const float dq0 = scale * dq[sidx * 3 + 0], dq1 = scale * dq[sidx * 3 + 1], dq2 = scale * dq[sidx * 3 + 2];
+  float rx0, ry0, rx1, ry1;
+  tap_rays(t, grid, ks, rx0, ry0, rx1, ry1);
+  float* gd = g_depth + (size_t)frame * H * W;
+  red_add(gd + t.y0 * W + t.x0, t.w00 * (dq0 * rx0 + dq1 * ry0 + dq2));
+  red_add(gd + t.y0 * W + t.x1, t.w01 * (dq0 * rx1 + dq1 * ry0 + dq2));
+  red_add(gd + t.y1 * W + t.x0, t.w10 * (dq0 * rx0 + dq1 * ry1 + dq2));
+  red_add(gd + t.y1 * W + t.x1, t.w11 * (dq0 * rx1 + dq1 * ry1 + dq2));
+}
+
+__global__ void k_track_finalize(const double* __restrict__ trackacc, const double* __restrict__ sums,
+                                 float loss_weight, const float* __restrict__ go,
+                                 const float* __restrict__ ext, float* __restrict__ g_ext,
+                                 float* __restrict__ g_k4, int F) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
+  const double sc = track_scale(sums, loss_weight, go);
   const double* a = trackacc + (size_t)f * kTrackAcc;
-  for (int k = 0; k < 4; ++k) g_k4[(size_t)f * 4 + k] = (float)a[k];
+  for (int k = 0; k < 4; ++k) g_k4[(size_t)f * 4 + k] = (float)(sc * a[k]);
   const float* P = ext + (size_t)f * 16;
-  const double w0 = 0.5 * a[4], w1 = 0.5 * a[5], w2 = 0.5 * a[6];
+  const double w0 = 0.5 * sc * a[4], w1 = 0.5 * sc * a[5], w2 = 0.5 * sc * a[6];
   float* o = g_ext + (size_t)f * 16;
   for (int c = 0; c < 3; ++c) {  // G_R = 1/2 [a]x R
     const double r0 = P[0 * 4 + c], r1 = P[1 * 4 + c], r2 = P[2 * 4 + c];
@@ -1102,7 +1167,7 @@ __global__ void k_track_finalize(const double* __restrict__ trackacc, const floa
     o[1 * 4 + c] = (float)(w2 * r0 - w0 * r2);
     o[2 * 4 + c] = (float)(-w1 * r0 + w0 * r1);
   }
-  o[3] = (float)a[7]; o[7] = (float)a[8]; o[11] = (float)a[9];
+  o[3] = (float)(sc * a[7]); o[7] = (float)(sc * a[8]); o[11] = (float)(sc * a[9]);
   o[12] = o[13] = o[14] = o[15] = 0.f;
 }
 
@@ -1211,6 +1276,127 @@ __global__ void k_softmin_focal_bwd(const float* __restrict__ sm, const float* _
   if (t >= B * n) return;
   const int b = t / n, i = t - b * n;
   g_err[t] = -10.0f * sm[t] * (cand_f[i] - f_hat[b]) * g_f_hat[b];
+}
+
+// ================================================================== standalone API kernels
+// flowmap/model/procrustes.py:7-51 on explicit point sets (*batch, n, 3): moments -> solve ->
+// [R|t]; backward: closed-form per-point adjoints.  One item per blockIdx.y.
+__global__ void __launch_bounds__(kThreads)
+k_points_moments(const float* __restrict__ p, const float* __restrict__ q, const float* __restrict__ w,
+                 double* __restrict__ moments, int n) {
+  __shared__ double smem[kNumMoments * (kThreads / 32)];
+  const int item = blockIdx.y;
+  float acc[kNumMoments];
+#pragma unroll
+  for (int i = 0; i < kNumMoments; ++i) acc[i] = 0.f;
+  for (int j = blockIdx.x * kThreads + threadIdx.x; j < n; j += gridDim.x * kThreads) {
+    const size_t o = ((size_t)item * n + j) * 3;
+    const float pp[3] = {__ldg(p + o), __ldg(p + o + 1), __ldg(p + o + 2)};
+    const float qq[3] = {__ldg(q + o), __ldg(q + o + 1), __ldg(q + o + 2)};
+    moments_add(acc, __ldg(w + (size_t)item * n + j), pp, qq);
+  }
+  block_accumulate<kNumMoments>(acc, moments + (size_t)item * kNumMoments, smem);
+}
+
+__global__ void k_points_solve(const double* __restrict__ moments, float* __restrict__ rt,
+                               PairState* __restrict__ state, int items) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= items) return;
+  double m[kNumMoments];
+  for (int k = 0; k < kNumMoments; ++k) m[k] = moments[(size_t)item * kNumMoments + k];
+  const double shift[3] = {0.0, 0.0, 0.0};
+  PairState st;
+  float out[12];
+  procrustes_solve(m, shift, out, st);
+  for (int k = 0; k < 12; ++k) rt[(size_t)item * 12 + k] = out[k];
+  state[item] = st;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_points_distribute(const float* __restrict__ p, const float* __restrict__ q, const float* __restrict__ w,
+                    const PairAdjoint* __restrict__ adj, float* __restrict__ gp, float* __restrict__ gq,
+                    float* __restrict__ gw, int n) {
+  const int item = blockIdx.y;
+  const PairAdjoint ad = adj[item];
+  for (int j = blockIdx.x * kThreads + threadIdx.x; j < n; j += gridDim.x * kThreads) {
+    const size_t o = ((size_t)item * n + j) * 3;
+    const float dp[3] = {__ldg(p + o) - ad.pbar[0], __ldg(p + o + 1) - ad.pbar[1], __ldg(p + o + 2) - ad.pbar[2]};
+    const float dq[3] = {__ldg(q + o) - ad.qbar[0], __ldg(q + o + 1) - ad.qbar[1], __ldg(q + o + 2) - ad.qbar[2]};
+    float wb, pb[3], qb[3];
+    point_adjoint(ad, __ldg(w + (size_t)item * n + j), dp, dq, wb, pb, qb);
+    gp[o] = pb[0]; gp[o + 1] = pb[1]; gp[o + 2] = pb[2];
+    gq[o] = qb[0]; gq[o + 1] = qb[1]; gq[o + 2] = qb[2];
+    gw[(size_t)item * n + j] = wb;
+  }
+}
+
+// flowmap/model/projection.py:76-90 on explicit coordinates: out = z * K^-1 [x y 1]^T.
+// xy: (xy_items, n, 2) with xy_items == items or 1 (shared grid).
+__global__ void k_unproject_points(const float* __restrict__ xy, const float* __restrict__ z,
+                                   const float* __restrict__ k4, float* __restrict__ out, int n, int xy_shared) {
+  const int item = blockIdx.y;
+  const Cam k = make_cam(load_k4(k4, item));
+  const float* c = xy + (xy_shared ? 0 : (size_t)item * n * 2);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    float rx, ry;
+    ray_of(__ldg(c + 2 * j), __ldg(c + 2 * j + 1), k, rx, ry);
+    const float d = __ldg(z + (size_t)item * n + j);
+    float* o = out + ((size_t)item * n + j) * 3;
+    o[0] = d * rx; o[1] = d * ry; o[2] = d;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_unproject_points_bwd(const float* __restrict__ xy, const float* __restrict__ z, const float* __restrict__ k4,
+                       const float* __restrict__ g_out, float* __restrict__ g_z, double* __restrict__ g_k,
+                       int n, int xy_shared) {
+  __shared__ double smem[4 * (kThreads / 32)];
+  const int item = blockIdx.y;
+  const Cam k = make_cam(load_k4(k4, item));
+  const float* c = xy + (xy_shared ? 0 : (size_t)item * n * 2);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    float rx, ry;
+    ray_of(__ldg(c + 2 * j), __ldg(c + 2 * j + 1), k, rx, ry);
+    const float d = __ldg(z + (size_t)item * n + j);
+    const float* g = g_out + ((size_t)item * n + j) * 3;
+    const float g0 = g[0], g1 = g[1], g2 = g[2];
+    g_z[(size_t)item * n + j] = g0 * rx + g1 * ry + g2;
+    acc[0] -= g0 * d * rx * k.ifx;
+    acc[1] -= g1 * d * ry * k.ify;
+    acc[2] -= g0 * d * k.ifx;
+    acc[3] -= g1 * d * k.ify;
+  }
+  block_accumulate<4>(acc, g_k + (size_t)item * 4, smem);
+}
+
+// n distinct pseudo-random indices in [0, N): the first n outputs of a keyed random PERMUTATION
+// of [0, N) (4-round Feistel network on the next even power of two, cycle-walking back into
+// range).  Stands in for `torch.randperm(N)[:n]` (intrinsics_softmin.py:90) without sorting N
+// keys every step; like randperm it yields a uniform sample without replacement in random order.
+__device__ __forceinline__ unsigned feistel_hash(unsigned v, unsigned key) {
+  v ^= key; v *= 0x9E3779B1u; v ^= v >> 15; v *= 0x85EBCA77u; v ^= v >> 13; v *= 0xC2B2AE3Du; v ^= v >> 16;
+  return v;
+}
+__global__ void k_random_subset(unsigned long long seed, long long N, int n, int64_t* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int bits = 2;
+  while ((1ll << bits) < N) bits += 2;  // even number of bits: two equal halves
+  const int half = bits / 2;
+  const unsigned mask = (1u << half) - 1u;
+  unsigned long long x = (unsigned long long)t;
+  do {
+    unsigned l = (unsigned)(x >> half) & mask, r = (unsigned)x & mask;
+#pragma unroll
+    for (int round = 0; round < 4; ++round) {
+      const unsigned f = feistel_hash(r, (unsigned)(seed >> (16 * round)) ^ (0xA511E9B3u * (round + 1))) & mask;
+      const unsigned nl = r, nr = l ^ f;
+      l = nl; r = nr;
+    }
+    x = ((unsigned long long)l << half) | r;
+  } while ((long long)x >= N);
+  out[t] = (int64_t)x;
 }
 
 // ================================================================== fused overfit step helpers
@@ -1342,10 +1528,11 @@ int fm_unproject_bwd(const float* depth, const float* k4, const float* g_surface
   return 0;
 }
 
-int fm_reproject(const float* xyz, const float* rt, const float* k4, float* xy, int items, int n, void* stream) {
+int fm_reproject(const float* xyz, const float* rt, const float* k4, float* xy, unsigned char* in_front,
+                 int items, int n, void* stream) {
   if (!xyz || !rt || !k4 || !xy || items < 1 || n < 1) return fail_msg("fm_reproject: bad arguments");
   dim3 grid(blocks_for(n, 1), items);
-  k_reproject<<<grid, kThreads, 0, (cudaStream_t)stream>>>(xyz, rt, k4, xy, n);
+  k_reproject<<<grid, kThreads, 0, (cudaStream_t)stream>>>(xyz, rt, k4, xy, in_front, n);
   FM_CHECK_LAUNCH("fm_reproject");
   return 0;
 }
@@ -1478,7 +1665,10 @@ int fm_flow_loss_fwd_bwd(const float* depth, const float* k4, const float* rt,
 
 int fm_pose_chain(const float* rt, float* extrinsics, int B, int F, void* stream) {
   if (!rt || !extrinsics || B < 1 || F < 2) return fail_msg("fm_pose_chain: bad arguments");
-  k_pose_chain<<<(B + 31) / 32, 32, 0, (cudaStream_t)stream>>>(rt, extrinsics, B, F);
+  const size_t smem = ((size_t)(F - 1) * 12 + (size_t)F * 12) * sizeof(float);
+  if (smem > 200 * 1024) return fail_msg("fm_pose_chain: too many frames for the shared-memory chain");
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_pose_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_pose_chain<<<B, 128, smem, (cudaStream_t)stream>>>(rt, extrinsics, B, F);
   FM_CHECK_LAUNCH("fm_pose_chain");
   return 0;
 }
@@ -1486,7 +1676,10 @@ int fm_pose_chain(const float* rt, float* extrinsics, int B, int F, void* stream
 int fm_pose_chain_bwd(const float* rt, const float* extrinsics, const float* g_extrinsics, float* g_rt,
                       int B, int F, void* stream) {
   if (!rt || !extrinsics || !g_extrinsics || !g_rt || B < 1 || F < 2) return fail_msg("fm_pose_chain_bwd: bad arguments");
-  k_pose_chain_bwd<<<(B + 31) / 32, 32, 0, (cudaStream_t)stream>>>(rt, extrinsics, g_extrinsics, g_rt, B, F);
+  const size_t smem = ((size_t)(F - 1) * 24 + (size_t)F * 24) * sizeof(float);
+  if (smem > 200 * 1024) return fail_msg("fm_pose_chain_bwd: too many frames for the shared-memory chain");
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_pose_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_pose_chain_bwd<<<B, 128, smem, (cudaStream_t)stream>>>(rt, extrinsics, g_extrinsics, g_rt, B, F);
   FM_CHECK_LAUNCH("fm_pose_chain_bwd");
   return 0;
 }
@@ -1514,17 +1707,19 @@ size_t fm_track_workspace_bytes(int F, long long total_samples) {
   off = align_up(off + 4 * sizeof(double), 256);                          // sums
   off = align_up(off + (size_t)F * kTrackAcc * sizeof(double), 256);      // per-frame accumulators
   off = align_up(off + (size_t)total_samples * 3 * sizeof(float), 256);   // world points
+  off = align_up(off + (size_t)total_samples * 3 * sizeof(float), 256);   // unscaled point adjoints
   off = align_up(off + (size_t)total_samples, 256);                       // source-valid flags
   return off;
 }
 
 namespace {
-struct TrackWs { double* sums; double* acc; float* xw; unsigned char* flag; };
+struct TrackWs { double* sums; double* acc; float* xw; float* dq; unsigned char* flag; };
 TrackWs carve_track(void* base, int F, long long total) {
   char* p = (char*)base; size_t off = 0; TrackWs w;
   w.sums = (double*)(p + off); off = align_up(off + 4 * sizeof(double), 256);
   w.acc = (double*)(p + off); off = align_up(off + (size_t)F * kTrackAcc * sizeof(double), 256);
   w.xw = (float*)(p + off); off = align_up(off + (size_t)total * 3 * sizeof(float), 256);
+  w.dq = (float*)(p + off); off = align_up(off + (size_t)total * 3 * sizeof(float), 256);
   w.flag = (unsigned char*)(p + off);
   return w;
 }
@@ -1540,14 +1735,16 @@ int fm_track_loss_fwd(const float* depth, const float* k4, const float* extrinsi
   if (mapping < 0 || mapping > 2) return fail_msg("fm_track_loss_fwd: unknown mapping");
   cudaStream_t s = (cudaStream_t)stream;
   TrackWs w = carve_track(ws, F, total_samples);
-  cudaError_t e = cudaMemsetAsync(w.sums, 0, 4 * sizeof(double), s);
+  cudaError_t e = cudaMemsetAsync(w.sums, 0, (char*)w.xw - (char*)w.sums, s);  // sums + accumulators
   if (e != cudaSuccess) return fail("fm_track_loss_fwd: memset", e);
   dim3 grid((max_points + kThreads - 1) / kThreads, max_rows, num_segments);
-  const size_t smem = (size_t)max_rows * 18 * sizeof(float);
-  k_track_src<false><<<grid, kThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis,
-                                                 mapping, delta, loss_weight, nullptr, w.sums, w.xw,
-                                                 w.flag, nullptr, nullptr, H, W);
+  const size_t smem = (size_t)max_rows * kTrackRec * sizeof(float);
+  k_track_src<<<grid, kThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis, mapping,
+                                          delta, w.sums, w.xw, w.flag, w.dq, w.acc, H, W);
   FM_CHECK_LAUNCH("fm_track_loss_fwd: k_track_src");
+  k_track_tgt<<<grid, kThreads, smem, s>>>(k4, extrinsics, segments, track_xy, track_vis, mapping, delta,
+                                          w.xw, w.flag, w.acc, H, W);
+  FM_CHECK_LAUNCH("fm_track_loss_fwd: k_track_tgt");
   k_track_loss<<<1, 1, 0, s>>>(w.sums, loss_weight, loss);
   FM_CHECK_LAUNCH("fm_track_loss_fwd: k_track_loss");
   return 0;
@@ -1558,25 +1755,86 @@ int fm_track_loss_bwd(const float* depth, const float* k4, const float* extrinsi
                       const unsigned char* track_vis, long long total_samples, int mapping, float delta,
                       float loss_weight, const float* grad_out, float* g_depth, float* g_extrinsics,
                       float* g_k4, void* ws, int F, int H, int W, void* stream) {
-  if (!depth || !k4 || !extrinsics || !segments || !track_xy || !track_vis || !g_depth ||
-      !g_extrinsics || !g_k4 || !ws || num_segments < 1 || max_rows < 1 || max_points < 1 || F < 1)
+  (void)depth; (void)track_vis; (void)mapping; (void)delta;
+  if (!k4 || !extrinsics || !segments || !track_xy || !g_depth || !g_extrinsics || !g_k4 || !ws ||
+      num_segments < 1 || max_rows < 1 || max_points < 1 || F < 1)
     return fail_msg("fm_track_loss_bwd: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   TrackWs w = carve_track(ws, F, total_samples);
-  cudaError_t e = cudaMemsetAsync(w.acc, 0, (size_t)F * kTrackAcc * sizeof(double), s);
-  if (e != cudaSuccess) return fail("fm_track_loss_bwd: memset", e);
   dim3 grid((max_points + kThreads - 1) / kThreads, max_rows, num_segments);
-  const size_t smem = (size_t)max_rows * 18 * sizeof(float);
-  k_track_src<true><<<grid, kThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis,
-                                                mapping, delta, loss_weight, grad_out, w.sums, w.xw,
-                                                w.flag, g_depth, w.acc, H, W);
-  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_src");
-  k_track_bwd_tgt<<<grid, kThreads, smem, s>>>(k4, extrinsics, segments, track_xy, track_vis, mapping,
-                                               delta, loss_weight, grad_out, w.sums, w.xw, w.flag, w.acc,
-                                               H, W);
-  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_bwd_tgt");
-  k_track_finalize<<<(F + 63) / 64, 64, 0, s>>>(w.acc, extrinsics, g_extrinsics, g_k4, F);
+  k_track_apply<<<grid, kThreads, 0, s>>>(k4, segments, track_xy, w.flag, w.dq, w.sums, loss_weight, grad_out,
+                                         g_depth, H, W);
+  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_apply");
+  k_track_finalize<<<(F + 63) / 64, 64, 0, s>>>(w.acc, w.sums, loss_weight, grad_out, extrinsics, g_extrinsics,
+                                               g_k4, F);
   FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_finalize");
+  return 0;
+}
+
+size_t fm_points_workspace_bytes(int items) {
+  if (items < 1) return 0;
+  return carve(nullptr, items, 2).bytes;
+}
+
+int fm_align_rigid_fwd(const float* p, const float* q, const float* weights, float* rt, void* ws, int items,
+                       int n, void* stream) {
+  if (!p || !q || !weights || !rt || !ws || items < 1 || n < 1) return fail_msg("fm_align_rigid_fwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace w = carve(ws, items, 2);
+  cudaError_t e = cudaMemsetAsync(w.moments, 0, (size_t)items * kNumMoments * sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_align_rigid_fwd: memset", e);
+  dim3 grid(blocks_for(n, 1), items);
+  k_points_moments<<<grid, kThreads, 0, s>>>(p, q, weights, w.moments, n);
+  FM_CHECK_LAUNCH("fm_align_rigid_fwd: k_points_moments");
+  k_points_solve<<<(items + 63) / 64, 64, 0, s>>>(w.moments, rt, w.state, items);
+  FM_CHECK_LAUNCH("fm_align_rigid_fwd: k_points_solve");
+  return 0;
+}
+
+int fm_align_rigid_bwd(const float* p, const float* q, const float* weights, const float* g_rt, float* g_p,
+                       float* g_q, float* g_w, void* ws, int items, int n, void* stream) {
+  if (!p || !q || !weights || !g_rt || !g_p || !g_q || !g_w || !ws || items < 1 || n < 1)
+    return fail_msg("fm_align_rigid_bwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace w = carve(ws, items, 2);
+  // items "pairs" of a 2-frame layout: k_adjoint indexes state / adj by pair
+  k_adjoint<<<(items + 63) / 64, 64, 0, s>>>(w.flowacc, w.state, g_rt, 0, nullptr, w.adj, items, 2);
+  FM_CHECK_LAUNCH("fm_align_rigid_bwd: k_adjoint");
+  dim3 grid(blocks_for(n, 1), items);
+  k_points_distribute<<<grid, kThreads, 0, s>>>(p, q, weights, w.adj, g_p, g_q, g_w, n);
+  FM_CHECK_LAUNCH("fm_align_rigid_bwd: k_points_distribute");
+  return 0;
+}
+
+int fm_unproject_points(const float* xy, const float* z, const float* k4, float* out, int items, int n,
+                        int xy_shared, void* stream) {
+  if (!xy || !z || !k4 || !out || items < 1 || n < 1) return fail_msg("fm_unproject_points: bad arguments");
+  dim3 grid(blocks_for(n, 1), items);
+  k_unproject_points<<<grid, kThreads, 0, (cudaStream_t)stream>>>(xy, z, k4, out, n, xy_shared);
+  FM_CHECK_LAUNCH("fm_unproject_points");
+  return 0;
+}
+
+int fm_unproject_points_bwd(const float* xy, const float* z, const float* k4, const float* g_out, float* g_z,
+                            float* g_k4, void* ws, int items, int n, int xy_shared, void* stream) {
+  if (!xy || !z || !k4 || !g_out || !g_z || !g_k4 || !ws || items < 1 || n < 1)
+    return fail_msg("fm_unproject_points_bwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace w = carve(ws, items, 2);  // k4acc has 2 * items rows; the first `items` are used
+  cudaError_t e = cudaMemsetAsync(w.k4acc, 0, (size_t)items * 4 * sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_unproject_points_bwd: memset", e);
+  dim3 grid(blocks_for(n, 1), items);
+  k_unproject_points_bwd<<<grid, kThreads, 0, s>>>(xy, z, k4, g_out, g_z, w.k4acc, n, xy_shared);
+  FM_CHECK_LAUNCH("fm_unproject_points_bwd: k_unproject_points_bwd");
+  k_d2f<<<(items * 4 + 127) / 128, 128, 0, s>>>(w.k4acc, g_k4, items * 4);
+  FM_CHECK_LAUNCH("fm_unproject_points_bwd: k_d2f");
+  return 0;
+}
+
+int fm_random_subset(unsigned long long seed, long long N, int n, int64_t* out, void* stream) {
+  if (!out || N < 1 || n < 1 || n > N || N > (1ll << 40)) return fail_msg("fm_random_subset: bad arguments");
+  k_random_subset<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, N, n, out);
+  FM_CHECK_LAUNCH("fm_random_subset");
   return 0;
 }
 

@@ -171,7 +171,7 @@ FM_HD void fill_lean(FlowFrameLean& f, const Rt* tf, const Rt* tb) {
 // Outputs dP (gradient w.r.t. the camera-space point), su = fx duvx u0 + fy duvy u1 and the
 // masked, scaled loss contribution.
 struct LeanTerm {
-  float P0, P1, P2, d0, d1, d2, su, loss;
+  float P0, P1, P2, d0, d1, d2, su, loss, uvx, uvy;
 };
 
 FM_HD LeanTerm lean_term(float D, float dir0, float dir1, float dir2, float off0, float off1,
@@ -191,6 +191,8 @@ FM_HD LeanTerm lean_term(float D, float dir0, float dir1, float dir2, float off0
     u2 = nan_to_num1(u2, f2);
   }
   const float uvx = fm_fma(k.fx, u0, k.cx * u2), uvy = fm_fma(k.fy, u1, k.cy * u2);
+  t.uvx = uvx;
+  t.uvy = uvy;
   // robust map of the aspect-corrected residual (mapping.py:35-43)
   const float sx = ((uvx - x) - flx) * rc.ax, sy = ((uvy - y) - fly) * rc.ay;
   const float n2 = fm_fma(sx, sx, sy * sy);

@@ -149,7 +149,7 @@ class IntrinsicsSoftmin(nn.Module):
         device = backbone_output.depths.device
         indices = self.injected_indices
         if indices is None:
-            indices = torch.randperm(h * w, device=device)[:c.num_procrustes_points]
+            indices = ops.random_subset(h * w, min(c.num_procrustes_points, h * w), device)
         err = ops.softmin_errors(backbone_output.depths, backbone_output.weights, flows.backward,
                                  indices, self.focal_length_candidates)
         weights = torch.softmax(-(err - err.min(dim=1, keepdim=True).values) * 10, dim=1)

@@ -216,15 +216,83 @@ def unproject_depth(depths: Tensor, k4: Tensor) -> Tensor:
     return _Unproject.apply(depths, k4)
 
 
-def reproject(xyz: Tensor, rt: Tensor, k4: Tensor) -> Tensor:
-    """Forward-only: xyz (items, n, 3), rt (items, 3, 4), k4 (items, 4) -> xy (items, n, 2)."""
+def reproject(xyz: Tensor, rt: Tensor, k4: Tensor, with_in_front: bool = False):
+    """Forward-only: xyz (items, n, 3), rt (items, 3, 4), k4 (items, 4) -> xy (items, n, 2)
+    [, in_front (items, n) bool]."""
     xyz, rt, k4 = _canon(xyz, "xyz"), _canon(rt, "rt"), _canon(k4, "k4")
     items, n = xyz.shape[:2]
     out = torch.empty((items, n, 2), dtype=torch.float32, device=xyz.device)
+    front = torch.empty((items, n), dtype=torch.uint8, device=xyz.device) if with_in_front else None
     with torch.cuda.device(xyz.device):
-        check(lib().fm_reproject(_ptr(xyz), _ptr(rt), _ptr(k4), _ptr(out), items, n, _stream()),
-              "fm_reproject")
-    return out
+        check(lib().fm_reproject(_ptr(xyz), _ptr(rt), _ptr(k4), _ptr(out), _ptr(front), items, n,
+                                 _stream()), "fm_reproject")
+    return (out, front.bool()) if with_in_front else out
+
+
+class _UnprojectPoints(torch.autograd.Function):
+    """projection.py:76-90 on explicit coordinates."""
+
+    @staticmethod
+    def forward(ctx, xy, z, k4):
+        xy, z, k4 = _canon(xy, "coordinates"), _canon(z, "z"), _canon(k4, "k4")
+        items, n = z.shape
+        shared = 1 if xy.shape[0] == 1 and items > 1 else 0
+        out = torch.empty((items, n, 3), dtype=torch.float32, device=z.device)
+        with torch.cuda.device(z.device):
+            check(lib().fm_unproject_points(_ptr(xy), _ptr(z), _ptr(k4), _ptr(out), items, n, shared,
+                                            _stream()), "fm_unproject_points")
+        ctx.save_for_backward(xy, z, k4)
+        ctx.shared = shared
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        xy, z, k4 = ctx.saved_tensors
+        items, n = z.shape
+        g_out = _canon(g_out, "g_out")
+        g_z, g_k4 = torch.empty_like(z), torch.empty_like(k4)
+        ws = torch.empty(lib().fm_points_workspace_bytes(items), dtype=torch.uint8, device=z.device)
+        with torch.cuda.device(z.device):
+            check(lib().fm_unproject_points_bwd(_ptr(xy), _ptr(z), _ptr(k4), _ptr(g_out), _ptr(g_z),
+                                                _ptr(g_k4), _ptr(ws), items, n, ctx.shared, _stream()),
+                  "fm_unproject_points_bwd")
+        return None, g_z, g_k4
+
+
+def unproject_points(xy: Tensor, z: Tensor, k4: Tensor) -> Tensor:
+    """xy (items or 1, n, 2), z (items, n), k4 (items, 4) -> (items, n, 3)."""
+    return _UnprojectPoints.apply(xy, z, k4)
+
+
+class _AlignRigid(torch.autograd.Function):
+    """flowmap/model/procrustes.py:7-51 on explicit points; returns rt (items, 3, 4)."""
+
+    @staticmethod
+    def forward(ctx, p, q, w):
+        p, q, w = _canon(p, "p"), _canon(q, "q"), _canon(w, "weights")
+        items, n = w.shape
+        ws = torch.empty(lib().fm_points_workspace_bytes(items), dtype=torch.uint8, device=p.device)
+        rt = torch.empty((items, 3, 4), dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            check(lib().fm_align_rigid_fwd(_ptr(p), _ptr(q), _ptr(w), _ptr(rt), _ptr(ws), items, n,
+                                           _stream()), "fm_align_rigid_fwd")
+        ctx.save_for_backward(p, q, w, ws)
+        return rt
+
+    @staticmethod
+    def backward(ctx, g_rt):
+        p, q, w, ws = ctx.saved_tensors
+        items, n = w.shape
+        g_rt = _canon(g_rt, "g_rt")
+        gp, gq, gw = torch.empty_like(p), torch.empty_like(q), torch.empty_like(w)
+        with torch.cuda.device(p.device):
+            check(lib().fm_align_rigid_bwd(_ptr(p), _ptr(q), _ptr(w), _ptr(g_rt), _ptr(gp), _ptr(gq),
+                                           _ptr(gw), _ptr(ws), items, n, _stream()), "fm_align_rigid_bwd")
+        return gp, gq, gw
+
+
+def align_rigid_rt(p: Tensor, q: Tensor, w: Tensor) -> Tensor:
+    return _AlignRigid.apply(p, q, w)
 
 
 def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, step: int,
@@ -367,3 +435,15 @@ def softmin_errors(depths, weights, backward_flows, indices, candidates) -> Tens
     n = candidates.numel()
     return _SoftminErrors.apply(depths, weights, backward_flows, indices,
                                 candidate_k4(candidates, h, w, b), n)
+
+
+def random_subset(num_items: int, n: int, device, seed: int | None = None) -> Tensor:
+    """n distinct uniformly random indices of range(num_items) (int64, random order): what
+    `torch.randperm(num_items)[:n]` samples, without sorting num_items keys.  The seed is drawn
+    from torch's CPU generator (so torch.manual_seed controls it) unless given."""
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    out = torch.empty(n, dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        check(lib().fm_random_subset(seed, num_items, n, _ptr(out), _stream()), "fm_random_subset")
+    return out

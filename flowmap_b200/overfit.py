@@ -224,7 +224,7 @@ class FusedOverfitter(Overfitter):
         P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         idx = self.injected_indices
         if idx is None:
-            idx = torch.randperm(h * w, device=dev)[:c.softmin_points]
+            idx = ops.random_subset(h * w, min(c.softmin_points, h * w), dev)
         idx = idx.contiguous()
         n = c.softmin_candidates
         wl = P(self._wlog) if c.use_correspondence_weights else None

@@ -59,8 +59,25 @@ int fm_unproject_bwd(const float* depth, const float* k4, const float* g_surface
 /* projection.py:116-134 reproject_points + :49-58 project_camera_space: n points per
  * item, one [R|t] (3x4) and one k4 per item -> xy (items, n, 2).  Forward only (used by
  * the visualiser/export callers; the differentiable uses are the fused ops below). */
-int fm_reproject(const float* xyz, const float* rt, const float* k4, float* xy, int items, int n,
-                 void* stream);
+int fm_reproject(const float* xyz, const float* rt, const float* k4, float* xy,
+                 unsigned char* in_front /* optional: z >= 0 after the transform, projection.py:72 */,
+                 int items, int n, void* stream);
+
+/* projection.py:76-90 unproject on explicit coordinates: xy (items or 1, n, 2), z (items, n),
+ * k4 (items, 4) -> (items, n, 3); xy_shared != 0 means one coordinate set for all items.  The
+ * backward returns g_z and g_k4 (coordinates are constants). */
+int fm_unproject_points(const float* xy, const float* z, const float* k4, float* out, int items, int n,
+                        int xy_shared, void* stream);
+int fm_unproject_points_bwd(const float* xy, const float* z, const float* k4, const float* g_out, float* g_z,
+                            float* g_k4, void* ws, int items, int n, int xy_shared, void* stream);
+
+/* procrustes.py:7-51 align_rigid on explicit point sets p, q (items, n, 3), weights (items, n)
+ * -> rt (items, 3, 4), and its backward (closed-form SVD adjoint).  ws: fm_points_workspace_bytes. */
+size_t fm_points_workspace_bytes(int items);
+int fm_align_rigid_fwd(const float* p, const float* q, const float* weights, float* rt, void* ws, int items,
+                       int n, void* stream);
+int fm_align_rigid_bwd(const float* p, const float* q, const float* weights, const float* g_rt, float* g_p,
+                       float* g_q, float* g_w, void* ws, int items, int n, void* stream);
 
 /* projection.py:213-249 align_surfaces up to the chain, + procrustes.py:7-51
  * align_rigid: per pair, gather later points / bilinear-sample earlier surface at
@@ -122,10 +139,12 @@ int fm_pose_chain_bwd(const float* rt, const float* extrinsics, const float* g_e
  * uint8.  extrinsics: camera-to-world (F, 4, 4).  All (source row, target row) pairs of a
  * segment are evaluated, including source == target; a term is valid when both ends are
  * visible, the source lies in [0,1)^2 and the PREDICTED target lies in [0,1)^2.
- * fwd writes loss = weight * sum / (count or 1) and keeps sum / count and the lifted world
- * points in ws (fm_track_workspace_bytes); bwd accumulates into g_depth (F,H,W; caller
- * zero-fills) and writes g_extrinsics (F,4,4) and g_k4 (F,4).  grad_out: device float
- * scalar dL/dloss or NULL (= 1). */
+ * The count depends on the predicted positions, so fwd makes the single sweep over all
+ * (source, target, point) triples, accumulating loss, count AND the unscaled gradient pieces
+ * into ws (fm_track_workspace_bytes); bwd only scales them by weight * grad_out / count:
+ * it accumulates into g_depth (F,H,W; caller zero-fills or passes the flow-loss gradient)
+ * and writes g_extrinsics (F,4,4; tangent part) and g_k4 (F,4).  grad_out: device float
+ * scalar dL/dloss or NULL (= 1).  bwd must follow fwd with the same ws and inputs. */
 size_t fm_track_workspace_bytes(int F, long long total_samples);
 int fm_track_loss_fwd(const float* depth, const float* k4, const float* extrinsics, const int* segments,
                       int num_segments, int max_rows, int max_points, const float* track_xy,
@@ -160,6 +179,10 @@ int fm_softmin_sweep_bwd(const float* depth, const float* weights, float weight_
                          const float* cand_k4, int num_candidates, const float* rt, const float* g_err,
                          float* g_depth, float* g_weights, void* ws, int B, int F, int H, int W,
                          void* stream);
+/* intrinsics_softmin.py:90 `torch.randperm(h * w)[:n]`: n distinct uniformly random pixel indices
+ * (int64) as the head of a keyed pseudo-random permutation of [0, N), O(n) work. */
+int fm_random_subset(unsigned long long seed, long long N, int n, int64_t* out, void* stream);
+
 /* intrinsics_softmin.py:126-139: softmin((err - min) * 10) over the candidates and the focal
  * estimate f_hat (B) = sum softmin_n * cand_focal_n; and d f_hat / d err for the backward. */
 int fm_softmin_focal(const float* err, const float* cand_focal, int num_candidates, int B, float* softmin,

@@ -381,3 +381,67 @@ def test_softmin_to_regressed_handover():
             assert abs(float(total) - ref[s]["loss"]) <= 2e-4 * abs(ref[s]["loss"]), (cls.__name__, s)
         assert abs(float(o.model.intrinsics.intrinsics_regressed.focal_length) - float(st.focal)) <= 1e-5
         assert rel_l2(o.model.backbone.depth.detach().cpu(), st.depth.detach()) <= 1e-5
+
+
+def test_projection_api_against_golden_units():
+    """flowmap_b200.projection / procrustes (function-level mirror) vs the reference's unit vectors."""
+    from flowmap_b200 import projection as P
+    from flowmap_b200.procrustes import align_rigid
+    g = load_golden("units")
+    h, w = g["grid_xy"].shape[:2]
+    xy, ij = P.sample_image_grid((h, w), device="cuda")
+    assert max_abs(xy.cpu(), g["grid_xy"]) <= 1e-7 and bool((ij.cpu().numpy() == g["grid_ij"]).all())
+    k3 = T(g["k3"]).cuda()
+    surf = P.unproject(xy, T(g["z"]).cuda(), k3[:, None, None])
+    assert max_abs(surf.cpu(), g["surfaces"]) <= 2e-6
+    proj = P.reproject_points(T(g["proj_pts"]).cuda(), torch.eye(4, device="cuda").expand(4, 1, 4, 4),
+                              T(g["proj_k"]).cuda())
+    assert np.allclose(proj.cpu().numpy(), g["proj_xy"], rtol=1e-5, atol=2e-6)
+    rig = align_rigid(T(g["rigid_p"]).cuda(), T(g["rigid_q"]).cuda(), T(g["rigid_w"]).cuda())
+    assert max_abs(rig.cpu(), g["rigid_t"]) <= 5e-6
+    assert max_abs(P.get_extrinsics(T(g["rigid_t"]).cuda()[None]).cpu(), g["chain"]) <= 2e-6
+
+
+def test_align_rigid_gradients_vs_oracle():
+    from oracle import flowmap_oracle as O
+    from flowmap_b200.procrustes import align_rigid
+    gen = torch.Generator().manual_seed(0)
+    p = torch.randn(3, 200, 3, generator=gen, dtype=torch.float64)
+    q = torch.randn(3, 200, 3, generator=gen, dtype=torch.float64) * 0.3 + p
+    q[2] = -q[2]  # reflection branch
+    w = torch.rand(3, 200, generator=gen, dtype=torch.float64)
+    coef = torch.randn(3, 4, 4, generator=gen, dtype=torch.float64)
+    pr, qr, wr = (t.clone().requires_grad_(True) for t in (p, q, w))
+    (O.align_rigid(pr, qr, wr) * coef).sum().backward()
+    pc, qc, wc = (t.float().cuda().requires_grad_(True) for t in (p, q, w))
+    (align_rigid(pc, qc, wc) * coef.float().cuda()).sum().backward()
+    assert rel_l2(pc.grad.cpu(), pr.grad) <= 1e-4
+    assert rel_l2(qc.grad.cpu(), qr.grad) <= 1e-4
+    assert rel_l2(wc.grad.cpu(), wr.grad) <= 1e-4
+
+
+def test_induced_flow_positions_vs_golden():
+    """compute_forward_flow / compute_backward_flow on the lazy surfaces of a ModelOutput."""
+    from flowmap_b200 import projection as P
+    g = load_golden("flow_huber")
+    o = _setup(g)
+    with torch.no_grad():
+        out = o.model(o.batch, o.flows, 0)
+        fwd = P.compute_forward_flow(out.surfaces, out.extrinsics, out.intrinsics)
+        bwd = P.compute_backward_flow(out.surfaces, out.extrinsics, out.intrinsics)
+    assert max_abs(fwd[:, :2].cpu(), g["fwd_xy"]) <= 2e-5
+    assert max_abs(bwd[:, :2].cpu(), g["bwd_xy"]) <= 2e-5
+
+
+def test_random_subset_is_a_uniform_sample_without_replacement():
+    from flowmap_b200 import ops
+    n_items, n = 360 * 640, 8192
+    a = ops.random_subset(n_items, n, "cuda", seed=1).cpu()
+    b = ops.random_subset(n_items, n, "cuda", seed=2).cpu()
+    assert a.min() >= 0 and a.max() < n_items and a.unique().numel() == n
+    assert not torch.equal(a, b)
+    # a full-length draw is a permutation
+    perm = ops.random_subset(1000, 1000, "cuda", seed=3).cpu()
+    assert torch.equal(perm.sort().values, torch.arange(1000))
+    # roughly uniform over the range (mean of U[0, N) is N/2, std N/sqrt(12 n))
+    assert abs(float(a.double().mean()) - n_items / 2) < 5 * n_items / (12 * n) ** 0.5
