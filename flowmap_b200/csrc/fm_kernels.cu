@@ -451,8 +451,8 @@ __device__ __forceinline__ void flow_frame_body_lean(const FlowFrameLean& f, con
   }
 }
 
-template <int VEC, bool FOCAL>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int VEC, bool FOCAL, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 k_flow_lean(const float* __restrict__ depth, const float* __restrict__ k4, const float* __restrict__ rt,
             const float* __restrict__ fflow, const float* __restrict__ bflow,
             const float* __restrict__ fmask, const float* __restrict__ bmask,
@@ -1468,12 +1468,14 @@ int launch_flow(const float* depth, const float* k4, const float* rt, const floa
     return 0;
   }
   const bool focal = intrinsics_mode == 1;
+  static const bool exp3 = getenv("FM_FLOW_MINB3") != nullptr;  // experiment switch (profiles/README.md)
   if (vec == 4) {
-    if (focal) k_flow_lean<4, true><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
-    else k_flow_lean<4, false><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
+    if (focal && exp3) k_flow_lean<4, true, 3><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
+    else if (focal) k_flow_lean<4, true, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
+    else k_flow_lean<4, false, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
   } else {
-    if (focal) k_flow_lean<1, true><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
-    else k_flow_lean<1, false><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
+    if (focal) k_flow_lean<1, true, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
+    else k_flow_lean<1, false, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
   }
   FM_CHECK_LAUNCH("k_flow_lean");
   k_flow_lean_convert<<<(BF + 63) / 64, 64, 0, s>>>(flowacc, rt, k4, focal ? 1 : 0, B, F, H, W);
