@@ -445,3 +445,84 @@ def test_random_subset_is_a_uniform_sample_without_replacement():
     assert torch.equal(perm.sort().values, torch.arange(1000))
     # roughly uniform over the range (mean of U[0, N) is N/2, std N/sqrt(12 n))
     assert abs(float(a.double().mean()) - n_items / 2) < 5 * n_items / (12 * n) ** 0.5
+
+
+def _oracle_flow_step(depth, wparam, flows64, focal=0.85, **kw):
+    """float64 oracle: loss, extrinsics and gradients for batched inputs (b, f, h, w)."""
+    from oracle import flowmap_oracle as O
+    b, f, h, w = depth.shape
+    d = depth.clone().requires_grad_(True)
+    wp = wparam.clone().requires_grad_(True)
+    foc = torch.tensor(focal, dtype=torch.float64, requires_grad=True)
+    weights = torch.sigmoid(100.0 * wp) if kw.get("use_weights", True) else torch.ones_like(wp)
+    k = O.intrinsics_from_focal(foc, h, w).expand(b, f, 3, 3)
+    surf = O.unproject(O.pixel_grid(h, w, torch.float64), d, k[:, :, None, None])
+    idx = torch.arange(h * w)
+    ext = O.align_surfaces(surf, flows64.backward, weights, idx)
+    loss = 1000.0 * O.flow_loss(surf, ext, k, flows64, kw.get("mapping", "huber"), 0.01)
+    loss.backward()
+    return loss.detach(), ext.detach(), d.grad, wp.grad, foc.grad
+
+
+@pytest.mark.parametrize("b,f,h,w", [(2, 4, 16, 24), (1, 2, 12, 20), (1, 3, 18, 22), (3, 3, 7, 9)])
+def test_batched_and_odd_shapes_vs_oracle(b, f, h, w):
+    """b > 1 (the pretraining use), a single frame pair, and widths that are not a multiple of 4
+    (scalar instantiation of every kernel), through the autograd ops."""
+    from oracle import flowmap_oracle as O
+    from flowmap_b200 import ops
+    gen = torch.Generator().manual_seed(b * 100 + f * 10 + w)
+    depth = 1.0 + torch.rand(b, f, h, w, generator=gen, dtype=torch.float64)
+    wparam = 0.01 * torch.randn(b, f - 1, h, w, generator=gen, dtype=torch.float64)
+    fl = O.synthetic_flows(f, h, w, seed=w, dtype=torch.float64, b=b)
+    loss_r, ext_r, gd_r, gw_r, gf_r = _oracle_flow_step(depth, wparam, fl)
+    d = depth.float().cuda().requires_grad_(True)
+    wp = wparam.float().cuda().requires_grad_(True)
+    foc = torch.tensor(0.85, device="cuda", requires_grad=True)
+    s = (h * w) ** 0.5
+    k4 = torch.stack((foc * s / w, foc * s / h, torch.tensor(0.5, device="cuda"), torch.tensor(0.5, device="cuda")))
+    k4 = k4.expand(b, f, 4)
+    flc = [t.float().cuda() for t in (fl.forward, fl.backward, fl.forward_mask, fl.backward_mask)]
+    rt = ops.procrustes_poses(d, torch.sigmoid(100.0 * wp), k4, flc[1], None)
+    for mode in ("full", "shared_focal"):
+        d.grad = wp.grad = foc.grad = None
+        loss = ops.flow_loss(d, rt, k4, *flc, ops.mask_sum(flc[2], flc[3]), "huber", 0.01, 1000.0, mode)
+        loss.backward(retain_graph=True)
+        assert abs(float(loss) - float(loss_r)) <= 1e-4 * abs(float(loss_r)), mode
+        assert rel_l2(d.grad.cpu(), gd_r) <= 1e-4, mode
+        assert rel_l2(wp.grad.cpu(), gw_r) <= 1e-4, mode
+        assert abs(float(foc.grad) - float(gf_r)) <= 1e-4 * abs(float(gf_r)), mode
+    assert max_abs(ops.pose_chain(rt).cpu(), ext_r) <= 1e-5
+
+
+def test_constant_intrinsics_mode_and_no_weights():
+    """k_mode="const" (ground-truth intrinsics: no K gradient) and use_correspondence_weights=False."""
+    from oracle import flowmap_oracle as O
+    from flowmap_b200 import ops
+    b, f, h, w = 1, 4, 16, 24
+    gen = torch.Generator().manual_seed(5)
+    depth = 1.0 + torch.rand(b, f, h, w, generator=gen, dtype=torch.float64)
+    wparam = torch.zeros(b, f - 1, h, w, dtype=torch.float64)
+    fl = O.synthetic_flows(f, h, w, seed=2, dtype=torch.float64)
+    loss_r, ext_r, gd_r, _, _ = _oracle_flow_step(depth, wparam, fl, use_weights=False)
+    d = depth.float().cuda().requires_grad_(True)
+    s = (h * w) ** 0.5
+    k4 = torch.tensor([0.85 * s / w, 0.85 * s / h, 0.5, 0.5], device="cuda").expand(b, f, 4).contiguous()
+    flc = [t.float().cuda() for t in (fl.forward, fl.backward, fl.forward_mask, fl.backward_mask)]
+    rt = ops.procrustes_poses(d, None, k4, flc[1], None)
+    loss = ops.flow_loss(d, rt, k4, *flc, ops.mask_sum(flc[2], flc[3]), "huber", 0.01, 1000.0, "const")
+    loss.backward()
+    assert abs(float(loss) - float(loss_r)) <= 1e-4 * abs(float(loss_r))
+    assert rel_l2(d.grad.cpu(), gd_r) <= 1e-4
+
+
+def test_zero_masks_use_denominator_one():
+    """loss_flow.py:70 `valid_sum or 1`: all-zero masks give loss 0 and zero gradients, no NaN."""
+    from flowmap_b200 import ops
+    b, f, h, w = 1, 3, 8, 12
+    d = (1.0 + torch.rand(b, f, h, w)).cuda().requires_grad_(True)
+    k4 = torch.tensor([0.9, 1.2, 0.5, 0.5], device="cuda").expand(b, f, 4).contiguous()
+    z2, z1 = torch.zeros(b, f - 1, h, w, 2, device="cuda"), torch.zeros(b, f - 1, h, w, device="cuda")
+    rt = ops.procrustes_poses(d, torch.ones_like(z1), k4, z2, None)
+    loss = ops.flow_loss(d, rt, k4, z2, z2, z1, z1, ops.mask_sum(z1, z1), "huber", 0.01, 1000.0)
+    loss.backward()
+    assert float(loss) == 0.0 and bool(torch.isfinite(d.grad).all()) and float(d.grad.abs().max()) == 0.0
