@@ -80,7 +80,7 @@ class OverfitStepArgs(ctypes.Structure):
                 ("rt", _P), ("loss", _P),
                 ("extrinsics", _P), ("g_extrinsics", _P), ("g_rt", _P), ("track_g_k4", _P),
                 ("track_loss", _P),
-                ("ws", _P), ("track_ws", _P), ("focal_step", c_int)]
+                ("ws", _P), ("track_ws", _P), ("focal_step", c_int), ("defer_adam", c_int)]
 
 
 SIGNATURES["fm_overfit_step"] = (c_int, [ctypes.POINTER(OverfitStepArgs), _P])

@@ -586,6 +586,7 @@ struct AdamFuse {
   float* m; float* v;
   float beta1, beta2, omb1, omb2, eps, step_size, bc2_sqrt;
   int on;
+  int first_pair;  // pairs below this index are left to a later, separate Adam call
 };
 
 template <int VEC>
@@ -661,7 +662,7 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
           if (VEC == 4) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
           else gw[base] = gwv[0];
         }
-        if (VEC == 4 && adam.on) {  // torch.optim.Adam on the logits, same operation order as k_adam
+        if (VEC == 4 && adam.on && pair >= adam.first_pair) {  // torch.optim.Adam on the logits (k_adam's order)
           float4 mm = *reinterpret_cast<float4*>(adam.m + pa.weight + base);
           float4 vv = *reinterpret_cast<float4*>(adam.v + pa.weight + base);
           float* mp = &mm.x; float* vp = &vv.x;
@@ -1203,6 +1204,76 @@ __global__ void k_track_finalize(const double* __restrict__ trackacc, const doub
 // depth / weight gradients (REDs) and the pose-gradient sums per candidate.
 constexpr int kSweepAcc = 80;  // doubles reserved per virtual item inside Workspace::flowacc
 
+// The candidates of the sweep differ only by S_n = diag(fx_0/fx_n, fy_0/fy_n, 1) applied to the
+// points: p_n = S_n p_0, q_n = S_n q_0 (same principal point, bilinear sampling is linear in the
+// rays).  So the 16 moment sums are accumulated ONCE (candidate 0) and scaled per candidate, and
+// the per-point adjoints of all candidates collapse into ONE PairAdjoint in candidate-0
+// coordinates:  A = sum S C_n S,  pb = sum S (pb_n - C_n^T qbar_n),  qb = sum S (qb_n - C_n pbar_n),
+// wconst = sum (qbar_n^T C_n pbar_n - pb_n . pbar_n - qb_n . qbar_n),  centroids 0.
+__global__ void k_sweep_base_k4(const float* __restrict__ cand_k4, float* __restrict__ base_k4, int B, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * 8) return;
+  const int b = t >> 3, e = t & 7;
+  base_k4[t] = cand_k4[(size_t)b * n * 8 + e];  // frames 0/1 of candidate 0
+}
+
+__global__ void k_sweep_scale_solve(const double* __restrict__ base_moments, const float* __restrict__ depth,
+                                    const float* __restrict__ cand_k4, float* __restrict__ rt,
+                                    PairState* __restrict__ state, int B, int n, PairLayout lay, int H, int W) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= B * n) return;
+  const int b = item / n;
+  const PairAddr pa = pair_addr(lay, item, H * W);
+  const double z0 = (double)__ldg(depth + pa.depth_a + (size_t)H * W + (size_t)(H / 2) * W + W / 2);
+  const double sx = (double)cand_k4[(size_t)b * n * 8 + 0] / (double)cand_k4[(size_t)item * 8 + 0];
+  const double sy = (double)cand_k4[(size_t)b * n * 8 + 1] / (double)cand_k4[(size_t)item * 8 + 1];
+  const double sc[3] = {sx, sy, 1.0};
+  double m[kNumMoments];
+  const double* bm = base_moments + (size_t)b * kNumMoments;
+  m[0] = bm[0];
+  for (int i = 0; i < 3; ++i) { m[1 + i] = bm[1 + i] * sc[i]; m[4 + i] = bm[4 + i] * sc[i]; }
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c) m[7 + a * 3 + c] = bm[7 + a * 3 + c] * sc[a] * sc[c];
+  const double shift[3] = {0.0, 0.0, z0};
+  PairState st;
+  float out[12];
+  procrustes_solve(m, shift, out, st);
+  for (int k = 0; k < 12; ++k) rt[(size_t)item * 12 + k] = out[k];
+  state[item] = st;
+}
+
+__global__ void k_sweep_aggregate(const PairAdjoint* __restrict__ adj, const float* __restrict__ cand_k4,
+                                  PairAdjoint* __restrict__ out, int B, int n) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double A[9] = {0}, pb[3] = {0}, qb[3] = {0}, wc = 0.0;
+  for (int c = 0; c < n; ++c) {
+    const int item = b * n + c;
+    const PairAdjoint a = adj[item];
+    const double s[3] = {(double)cand_k4[(size_t)b * n * 8 + 0] / (double)cand_k4[(size_t)item * 8 + 0],
+                         (double)cand_k4[(size_t)b * n * 8 + 1] / (double)cand_k4[(size_t)item * 8 + 1], 1.0};
+    for (int r = 0; r < 3; ++r) {
+      double cq = 0.0, cp = 0.0;  // (C^T qbar)_r, (C pbar)_r
+      for (int k = 0; k < 3; ++k) {
+        A[r * 3 + k] += s[r] * (double)a.cbar[r * 3 + k] * s[k];
+        cq += (double)a.cbar[k * 3 + r] * (double)a.qbar[k];
+        cp += (double)a.cbar[r * 3 + k] * (double)a.pbar[k];
+      }
+      pb[r] += s[r] * ((double)a.pb[r] - cq);
+      qb[r] += s[r] * ((double)a.qb[r] - cp);
+      wc += (double)a.qbar[r] * cp - (double)a.pb[r] * (double)a.pbar[r] - (double)a.qb[r] * (double)a.qbar[r];
+    }
+  }
+  PairAdjoint o;
+  for (int i = 0; i < 9; ++i) o.cbar[i] = (float)A[i];
+  for (int i = 0; i < 3; ++i) {
+    o.pb[i] = (float)pb[i]; o.qb[i] = (float)qb[i]; o.pbar[i] = 0.f; o.qbar[i] = 0.f;
+    o.shift[i] = adj[b * n].shift[i];
+  }
+  o.wconst = (float)wc;
+  out[b] = o;
+}
+
 template <bool BWD>
 __global__ void __launch_bounds__(kThreads)
 k_sweep(const float* __restrict__ depth, const float* __restrict__ k4, const float* __restrict__ rt,
@@ -1278,18 +1349,22 @@ __global__ void k_sweep_out(const double* __restrict__ acc, float* __restrict__ 
 // one block per batch element.  Writes the weights and f_hat = sum_n softmin_n f_n.
 __global__ void k_softmin_focal(const float* __restrict__ err, const float* __restrict__ cand_f, int n,
                                 float* __restrict__ sm_out, float* __restrict__ f_hat) {
-  const int b = blockIdx.x;
-  if (threadIdx.x != 0) return;
-  float mn = err[b * n];
-  for (int i = 1; i < n; ++i) mn = fminf(mn, err[b * n + i]);
-  double z = 0.0, f = 0.0;
-  for (int i = 0; i < n; ++i) z += exp(-(double)((err[b * n + i] - mn) * 10.0f));
-  for (int i = 0; i < n; ++i) {
+  const int b = blockIdx.x, lane = threadIdx.x;  // one warp per batch element
+  float mn = 3.0e38f;
+  for (int i = lane; i < n; i += 32) mn = fminf(mn, err[b * n + i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  double z = 0.0;
+  for (int i = lane; i < n; i += 32) z += exp(-(double)((err[b * n + i] - mn) * 10.0f));
+  z = warp_sum(z);
+  double f = 0.0;
+  for (int i = lane; i < n; i += 32) {
     const double sm = exp(-(double)((err[b * n + i] - mn) * 10.0f)) / z;
     sm_out[b * n + i] = (float)sm;
     f += sm * (double)cand_f[i];
   }
-  f_hat[b] = (float)f;
+  f = warp_sum(f);
+  if (lane == 0) f_hat[b] = (float)f;
 }
 
 // d f_hat / d err_m = -10 sm_m (f_m - f_hat)   (softmin is shift invariant: the min drops out)
@@ -1866,8 +1941,9 @@ int fm_random_subset(unsigned long long seed, long long N, int n, int64_t* out, 
 
 size_t fm_softmin_workspace_bytes(int B, int num_candidates) {
   if (B < 1 || num_candidates < 1) return 0;
-  const size_t items = (size_t)B * num_candidates;
-  return align_up(carve(nullptr, (int)items, 2).bytes, 256) + align_up(items * (12 + 8) * sizeof(float), 256);
+  const size_t items = (size_t)B * num_candidates;  // + B rows for the shared (candidate-0) quantities
+  return align_up(carve(nullptr, (int)(items + B), 2).bytes, 256) +
+         align_up((items * 12 + (items + B) * 8) * sizeof(float), 256);
 }
 
 namespace {
@@ -1889,11 +1965,25 @@ int fm_softmin_sweep_fwd(const float* depth, const float* weights, float weight_
   cudaStream_t s = (cudaStream_t)stream;
   const int items = B * num_candidates;
   const PairLayout lay = sweep_layout(F, H, W, num_candidates);
-  int rc = procrustes_fwd_impl(depth, cand_k4, backward_flow, weights, weight_sensitivity, indices,
-                               num_indices, rt, ws, items, 2, H, W, stream, &lay);
-  if (rc) return rc;
-  Workspace w = carve(ws, items, 2);
-  cudaError_t e = cudaMemsetAsync(w.flowacc, 0, (size_t)items * kSweepAcc * sizeof(double), s);
+  const PairLayout lay1 = sweep_layout(F, H, W, 1);
+  Workspace w = carve(ws, items + B, 2);
+  float* scratch = (float*)((char*)ws + align_up(w.bytes, 256));
+  float* base_k4 = scratch + (size_t)items * 12 + (size_t)items * 8;  // after g_rt and g_k4 of the bwd
+  double* base_moments = w.moments + (size_t)items * kNumMoments;
+  cudaError_t e = cudaMemsetAsync(base_moments, 0, (size_t)B * kNumMoments * sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_softmin_sweep_fwd: memset", e);
+  k_sweep_base_k4<<<(B * 8 + 127) / 128, 128, 0, s>>>(cand_k4, base_k4, B, num_candidates);
+  FM_CHECK_LAUNCH("fm_softmin_sweep_fwd: k_sweep_base_k4");
+  {  // ONE moment pass (candidate 0); every candidate's moments are a rescaling of it
+    dim3 grid(blocks_for(num_indices, 1), B);
+    k_moments<1><<<grid, kThreads, 0, s>>>(depth, base_k4, backward_flow, weights, indices, num_indices,
+                                          base_moments, weight_sensitivity, lay1, H, W);
+    FM_CHECK_LAUNCH("fm_softmin_sweep_fwd: k_moments");
+  }
+  k_sweep_scale_solve<<<(items + 63) / 64, 64, 0, s>>>(base_moments, depth, cand_k4, rt, w.state, B,
+                                                      num_candidates, lay, H, W);
+  FM_CHECK_LAUNCH("fm_softmin_sweep_fwd: k_sweep_scale_solve");
+  e = cudaMemsetAsync(w.flowacc, 0, (size_t)items * kSweepAcc * sizeof(double), s);
   if (e != cudaSuccess) return fail("fm_softmin_sweep_fwd: memset", e);
   dim3 grid(blocks_for(num_indices, 1), items);
   k_sweep<false><<<grid, kThreads, 0, s>>>(depth, cand_k4, rt, backward_flow, weights, weight_sensitivity,
@@ -1916,11 +2006,14 @@ int fm_softmin_sweep_bwd(const float* depth, const float* weights, float weight_
   cudaStream_t s = (cudaStream_t)stream;
   const int items = B * num_candidates;
   const PairLayout lay = sweep_layout(F, H, W, num_candidates);
-  Workspace w = carve(ws, items, 2);
+  const PairLayout lay1 = sweep_layout(F, H, W, 1);
+  Workspace w = carve(ws, items + B, 2);
   float* scratch = (float*)((char*)ws + align_up(w.bytes, 256));
   float* g_rt = scratch;
-  float* g_k4 = scratch + (size_t)items * 12;
+  float* base_k4 = scratch + (size_t)items * 12 + (size_t)items * 8;
   cudaError_t e = cudaMemsetAsync(w.flowacc, 0, (size_t)items * kSweepAcc * sizeof(double), s);
+  if (e != cudaSuccess) return fail("fm_softmin_sweep_bwd: memset", e);
+  e = cudaMemsetAsync(w.k4acc, 0, (size_t)(items + B) * 2 * 4 * sizeof(double), s);
   if (e != cudaSuccess) return fail("fm_softmin_sweep_bwd: memset", e);
   dim3 grid(blocks_for(num_indices, 1), items);
   k_sweep<true><<<grid, kThreads, 0, s>>>(depth, cand_k4, rt, backward_flow, weights, weight_sensitivity,
@@ -1929,9 +2022,19 @@ int fm_softmin_sweep_bwd(const float* depth, const float* weights, float weight_
   FM_CHECK_LAUNCH("fm_softmin_sweep_bwd: k_sweep");
   k_sweep_out<<<(items * 12 + 127) / 128, 128, 0, s>>>(w.flowacc, g_rt, items, 1, 12);
   FM_CHECK_LAUNCH("fm_softmin_sweep_bwd: k_sweep_out");
-  return procrustes_bwd_impl(depth, cand_k4, backward_flow, weights, weight_sensitivity, indices,
-                             num_indices, g_rt, 0, nullptr, g_depth, g_weights, g_k4, ws, items, 2, H, W,
-                             stream, &lay);
+  // per-candidate adjoint constants, collapsed into one per batch element, then ONE distribution pass
+  k_adjoint<<<(items + 63) / 64, 64, 0, s>>>(w.flowacc, w.state, g_rt, 0, nullptr, w.adj, items, 2);
+  FM_CHECK_LAUNCH("fm_softmin_sweep_bwd: k_adjoint");
+  k_sweep_aggregate<<<(B + 31) / 32, 32, 0, s>>>(w.adj, cand_k4, w.adj + items, B, num_candidates);
+  FM_CHECK_LAUNCH("fm_softmin_sweep_bwd: k_sweep_aggregate");
+  AdamFuse af;
+  memset(&af, 0, sizeof(af));
+  dim3 grid1(blocks_for(num_indices, 1), B);
+  k_distribute<1><<<grid1, kThreads, 0, s>>>(depth, base_k4, backward_flow, const_cast<float*>(weights), indices,
+                                            num_indices, w.adj + items, g_depth, g_weights, w.k4acc,
+                                            weight_sensitivity, lay1, af, H, W);
+  FM_CHECK_LAUNCH("fm_softmin_sweep_bwd: k_distribute");
+  return 0;
 }
 
 int fm_softmin_focal(const float* err, const float* cand_focal, int num_candidates, int B, float* softmin,
@@ -2011,9 +2114,11 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
   }
   AdamFuse af;
   memset(&af, 0, sizeof(af));
+  const bool defer = a->defer_adam != 0;  // softmin stage: the sweep's backward still adds gradients
   const bool fuse_w = a->step > 0 && a->weight_logits && !a->indices && W % 4 == 0;
   if (fuse_w) {  // the weight gradient is final inside k_distribute: update the logits there
     af.on = 1; af.m = a->m_weights; af.v = a->v_weights;
+    af.first_pair = defer ? 1 : 0;  // the sweep touches pair 0 only
     af.beta1 = (float)a->beta1; af.beta2 = (float)a->beta2;
     af.omb1 = (float)(1.0 - a->beta1); af.omb2 = (float)(1.0 - a->beta2); af.eps = (float)a->eps;
     af.step_size = (float)(a->lr / (1.0 - pow(a->beta1, (double)a->step)));
@@ -2024,7 +2129,7 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
                                 a->g_k4, a->ws, 1, F, H, W, stream, nullptr, fuse_w ? &af : nullptr)))
     return rc;
   // Adam (model_wrapper_overfit.py:104-105)
-  if (a->step > 0) {
+  if (a->step > 0 && !defer) {
     if ((rc = fm_adam_step(a->depth, a->g_depth, a->m_depth, a->v_depth, (size_t)F * N, a->lr, a->beta1,
                            a->beta2, a->eps, a->step, stream)))
       return rc;
@@ -2043,6 +2148,7 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
     k_focal_grad<<<1, 256, 0, s>>>(w.k4acc, w.flowacc, track_g_k4, a->g_focal, 1, F, H, W);
     FM_CHECK_LAUNCH("fm_overfit_step: k_focal_grad");
   }
+  if (defer && a->step > 0 && a->weight_logits && !fuse_w) return fail_msg("fm_overfit_step: defer_adam needs the fused weight update");
   return 0;
 }
 

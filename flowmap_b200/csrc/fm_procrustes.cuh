@@ -36,7 +36,7 @@ struct PairAdjoint {
   float pbar[3];   // shifted centroids (so the kernel forms p' - pbar, q' - qbar)
   float qbar[3];
   float shift[3];
-  float pad;
+  float wconst;    // constant added to every point's weight adjoint (aggregated sweeps only)
 };
 
 FM_HD void cross3(const double* a, const double* b, double* c) {
@@ -218,7 +218,7 @@ FM_HD void procrustes_adjoint(const PairState& st, const double* g_rt, PairAdjoi
     out.qbar[i] = (float)st.qbar[i];
     out.shift[i] = (float)st.shift[i];
   }
-  out.pad = 0.0f;
+  out.wconst = 0.0f;
 }
 
 // Per-point adjoints given the pair constants: dp' = p' - pbar', dq' = q' - qbar'.
@@ -231,7 +231,7 @@ FM_HD void point_adjoint(const PairAdjoint& a, float w, const float* dp, const f
     cq[r] = a.cbar[0 * 3 + r] * dq[0] + a.cbar[1 * 3 + r] * dq[1] + a.cbar[2 * 3 + r] * dq[2];
   }
   wbar = dq[0] * cp[0] + dq[1] * cp[1] + dq[2] * cp[2] + a.pb[0] * dp[0] + a.pb[1] * dp[1] +
-         a.pb[2] * dp[2] + a.qb[0] * dq[0] + a.qb[1] * dq[1] + a.qb[2] * dq[2];
+         a.pb[2] * dp[2] + a.qb[0] * dq[0] + a.qb[1] * dq[1] + a.qb[2] * dq[2] + a.wconst;
   for (int r = 0; r < 3; ++r) {
     pbar[r] = w * (cq[r] + a.pb[r]);
     qbar[r] = w * (cp[r] + a.qb[r]);

@@ -236,8 +236,14 @@ class FusedOverfitter(Overfitter):
                   "fm_softmin_sweep_fwd")
             check(L.fm_softmin_focal(P(self._sw_err), P(self._cand_f), n, 1, P(self._sw_sm),
                                      P(self._sw_focal), st), "fm_softmin_focal")
-            a.focal, a.step = P(self._sw_focal), 0
+            # all-pixel dense path: the logits of pairs >= 1 are updated inside the step (their
+            # gradient is final there); depth and pair 0 wait for the sweep's backward
+            fuse = update and c.use_correspondence_weights and self._indices is None and w % 4 == 0
+            a.focal = P(self._sw_focal)
+            a.step = self.global_step + 1 if fuse else 0
+            a.defer_adam = 1 if fuse else 0
             check(L.fm_overfit_step(self._ctypes.byref(a), st), "fm_overfit_step")
+            a.defer_adam = 0
             check(L.fm_softmin_focal_bwd(P(self._sw_sm), P(self._cand_f), P(self._sw_focal),
                                          P(self._g_focal), n, 1, P(self._sw_gerr), st),
                   "fm_softmin_focal_bwd")
@@ -250,7 +256,9 @@ class FusedOverfitter(Overfitter):
             s_ = self.global_step + 1
             ops.adam_step(self._depth, self._g_depth, self._state[0], self._state[1], s_, c.lr)
             if c.use_correspondence_weights:
-                ops.adam_step(self._wlog, self._g_w, self._state[2], self._state[3], s_, c.lr)
+                k = 1 if fuse else self._wlog.shape[0]  # pair 0 only when the rest was fused
+                ops.adam_step(self._wlog[:k], self._g_w[:k], self._state[2][:k], self._state[3][:k],
+                              s_, c.lr)
             if c.regression_after is not None and \
                     self.global_step >= c.regression_after - c.regression_window:
                 self.window.append(self._sw_focal[0].clone())

@@ -236,6 +236,10 @@ typedef struct {
   int focal_step;               /* Adam step number of the focal parameter (0: same as step);
                                    differs after the softmin -> regressed hand-over, where the
                                    focal length first receives a gradient at step after_step */
+  int defer_adam;               /* softmin stage: the sweep's backward (fm_softmin_sweep_bwd) still has to
+                                   add its gradients to depth frames 0/1 and to the weights of pair 0, so
+                                   only the weight logits of pairs >= 1 are updated here (with `step`);
+                                   the caller runs Adam on depth and on pair 0's logits afterwards */
 } fm_overfit_step_args;
 int fm_overfit_step(const fm_overfit_step_args* args, void* stream);
 
