@@ -333,14 +333,25 @@ def run_gpu(args):
     e2e_ms, _ = time_steps(e2e_step, max(3, min(args.steps, 10)))
 
     # ---- flow-loss-only variant of the same step (regressed focal): the path the roofline
-    # accounting below describes
-    flow_only_ms = None
+    # accounting below describes; and the same on spatially smooth flows (real optical flow is
+    # piecewise smooth; the iid flows above are the worst case for the bilinear gather/scatter)
+    flow_only_ms = smooth_ms = None
     if not pairs_mode:
         o2 = init_params(FusedOverfitter(OverfitCfg(), batch, flows_dev, device=dev))
         for _ in range(3):
             o2.training_step()
         flow_only_ms, _ = time_steps(o2.training_step, min(args.steps, 30))
+        g = torch.Generator(device=dev).manual_seed(rank)
+        for t in (o2.flows.forward, o2.flows.backward):
+            lo = 0.01 * torch.randn(F_ - 1, 2, H_ // 16 + 1, W_ // 16 + 1, device=dev, generator=g)
+            up = torch.nn.functional.interpolate(lo, size=(H_, W_), mode="bilinear", align_corners=True)
+            t.copy_(up.permute(0, 2, 3, 1)[None])
+        for _ in range(3):
+            o2.training_step()
+        smooth_ms, _ = time_steps(o2.training_step, min(args.steps, 30))
         del o2
+        flows_dev.forward.copy_(flows_host.forward, non_blocking=True)   # o.flows shares these buffers
+        flows_dev.backward.copy_(flows_host.backward, non_blocking=True)
 
     if rank != 0:
         if world > 1:
@@ -454,7 +465,9 @@ def run_gpu(args):
         "gpu_launches": int(launches), "final_loss": final_loss,
         "flow_only": None if flow_only_ms is None else
         {"ms_per_step": round(flow_only_ms, 4), "it_per_s": round(world * 1000.0 / flow_only_ms, 2),
-         "what": "same step without tracking loss / softmin sweep (regressed focal)"},
+         "what": "same step without tracking loss / softmin sweep (regressed focal)",
+         "ms_per_step_smooth_flows": None if smooth_ms is None else round(smooth_ms, 4),
+         "smooth_flows": "N(0, 0.01^2) flow on a 16x coarser grid, bilinearly upsampled"},
         "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(out))

@@ -1057,10 +1057,19 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
       Xw[i] = fm_fma(rs[i * 3 + 0], q[0], fm_fma(rs[i * 3 + 1], q[1], fm_fma(rs[i * 3 + 2], q[2], rs[9 + i])));
     xw[sidx * 3 + 0] = Xw[0]; xw[sidx * 3 + 1] = Xw[1]; xw[sidx * 3 + 2] = Xw[2];
     float G[3] = {0.f, 0.f, 0.f};
+    // the next target row's visibility / position is fetched while the current one is processed
+    size_t tidx_n = (size_t)si.sample_start + p;
+    unsigned char vis_n = tvis[tidx_n];
+    float2 gxy_n = __ldg(reinterpret_cast<const float2*>(txy) + tidx_n);
     for (int ft = 0; ft < si.rows; ++ft) {
-      const size_t tidx = (size_t)si.sample_start + (size_t)ft * si.n + p;
-      if (!tvis[tidx]) continue;
-      const float2 gxy = __ldg(reinterpret_cast<const float2*>(txy) + tidx);
+      const unsigned char vis_t = vis_n;
+      const float2 gxy = gxy_n;
+      if (ft + 1 < si.rows) {
+        tidx_n += si.n;
+        vis_n = tvis[tidx_n];
+        gxy_n = __ldg(reinterpret_cast<const float2*>(txy) + tidx_n);
+      }
+      if (!vis_t) continue;
       LeanTerm lt;
       float g[3];
       if (!track_term_lean(sm + ft * kTrackRec, Xw, gxy.x, gxy.y, rc, lt, g)) continue;
@@ -1111,10 +1120,19 @@ k_track_tgt(const float* __restrict__ k4, const float* __restrict__ ext, const i
     const size_t tidx = (size_t)si.sample_start + (size_t)ft * si.n + p;
     const float2 gxy = __ldg(reinterpret_cast<const float2*>(txy) + tidx);
     const Cam kt = sm_cam(rec);
+    // the next row's world point is fetched while the current one is processed
+    size_t sidx_n = (size_t)si.sample_start + p;
+    unsigned char fl_n = flag[sidx_n];
+    float xn0 = xw[sidx_n * 3 + 0], xn1 = xw[sidx_n * 3 + 1], xn2 = xw[sidx_n * 3 + 2];
     for (int fs = 0; fs < si.rows; ++fs) {
-      const size_t sidx = (size_t)si.sample_start + (size_t)fs * si.n + p;
-      if (!flag[sidx]) continue;
-      const float Xw[3] = {xw[sidx * 3 + 0], xw[sidx * 3 + 1], xw[sidx * 3 + 2]};
+      const unsigned char fl = fl_n;
+      const float Xw[3] = {xn0, xn1, xn2};
+      if (fs + 1 < si.rows) {
+        sidx_n += si.n;
+        fl_n = flag[sidx_n];
+        xn0 = xw[sidx_n * 3 + 0]; xn1 = xw[sidx_n * 3 + 1]; xn2 = xw[sidx_n * 3 + 2];
+      }
+      if (!fl) continue;
       LeanTerm lt;
       float g[3];
       if (!track_term_lean(rec, Xw, gxy.x, gxy.y, rc, lt, g)) continue;
@@ -1244,34 +1262,41 @@ __global__ void k_sweep_scale_solve(const double* __restrict__ base_moments, con
 
 __global__ void k_sweep_aggregate(const PairAdjoint* __restrict__ adj, const float* __restrict__ cand_k4,
                                   PairAdjoint* __restrict__ out, int B, int n) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  double A[9] = {0}, pb[3] = {0}, qb[3] = {0}, wc = 0.0;
-  for (int c = 0; c < n; ++c) {
+  const int b = blockIdx.x, lane = threadIdx.x;  // one warp per batch element, lanes stride the candidates
+  double acc[16];  // A (9), pb (3), qb (3), wconst
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+  for (int c = lane; c < n; c += 32) {
     const int item = b * n + c;
     const PairAdjoint a = adj[item];
     const double s[3] = {(double)cand_k4[(size_t)b * n * 8 + 0] / (double)cand_k4[(size_t)item * 8 + 0],
                          (double)cand_k4[(size_t)b * n * 8 + 1] / (double)cand_k4[(size_t)item * 8 + 1], 1.0};
+#pragma unroll
     for (int r = 0; r < 3; ++r) {
       double cq = 0.0, cp = 0.0;  // (C^T qbar)_r, (C pbar)_r
+#pragma unroll
       for (int k = 0; k < 3; ++k) {
-        A[r * 3 + k] += s[r] * (double)a.cbar[r * 3 + k] * s[k];
+        acc[r * 3 + k] += s[r] * (double)a.cbar[r * 3 + k] * s[k];
         cq += (double)a.cbar[k * 3 + r] * (double)a.qbar[k];
         cp += (double)a.cbar[r * 3 + k] * (double)a.pbar[k];
       }
-      pb[r] += s[r] * ((double)a.pb[r] - cq);
-      qb[r] += s[r] * ((double)a.qb[r] - cp);
-      wc += (double)a.qbar[r] * cp - (double)a.pb[r] * (double)a.pbar[r] - (double)a.qb[r] * (double)a.qbar[r];
+      acc[9 + r] += s[r] * ((double)a.pb[r] - cq);
+      acc[12 + r] += s[r] * ((double)a.qb[r] - cp);
+      acc[15] += (double)a.qbar[r] * cp - (double)a.pb[r] * (double)a.pbar[r] - (double)a.qb[r] * (double)a.qbar[r];
     }
   }
-  PairAdjoint o;
-  for (int i = 0; i < 9; ++i) o.cbar[i] = (float)A[i];
-  for (int i = 0; i < 3; ++i) {
-    o.pb[i] = (float)pb[i]; o.qb[i] = (float)qb[i]; o.pbar[i] = 0.f; o.qbar[i] = 0.f;
-    o.shift[i] = adj[b * n].shift[i];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+    PairAdjoint o;
+    for (int i = 0; i < 9; ++i) o.cbar[i] = (float)acc[i];
+    for (int i = 0; i < 3; ++i) {
+      o.pb[i] = (float)acc[9 + i]; o.qb[i] = (float)acc[12 + i]; o.pbar[i] = 0.f; o.qbar[i] = 0.f;
+      o.shift[i] = adj[b * n].shift[i];
+    }
+    o.wconst = (float)acc[15];
+    out[b] = o;
   }
-  o.wconst = (float)wc;
-  out[b] = o;
 }
 
 template <bool BWD>
@@ -1546,6 +1571,13 @@ int blocks_for(int n_items_per_row, int vec) {
   return nb < 1 ? 1 : nb;
 }
 
+// Index-mode launches (subsampled Procrustes, the focal sweep): few points, dependent gathers ->
+// one point per thread so that the latency is covered by parallelism, not by a per-thread loop.
+int blocks_for_points(int n) {
+  int nb = (n + kThreads - 1) / kThreads;
+  return nb < 1 ? 1 : nb;
+}
+
 bool bad_dims(int B, int F, int H, int W) { return B < 1 || F < 2 || H < 1 || W < 1 || (long long)H * W > (1ll << 30); }
 
 }  // namespace
@@ -1652,7 +1684,7 @@ static int procrustes_fwd_impl(const float* depth, const float* k4, const float*
   cudaError_t e = cudaMemsetAsync(w.moments, 0, (size_t)BP * kNumMoments * sizeof(double), s);
   if (e != cudaSuccess) return fail("fm_procrustes_fwd: memset", e);
   if (indices) {
-    dim3 grid(blocks_for(num_indices, 1), BP);
+    dim3 grid(blocks_for_points(num_indices), BP);
     k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.moments, wsens, lay, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
@@ -1700,7 +1732,7 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
   k_adjoint<<<(BP + 63) / 64, 64, 0, s>>>(w.flowacc, w.state, g_rt, include_flow_loss, flow_scale, w.adj, BP, F);
   FM_CHECK_LAUNCH("fm_procrustes_bwd: k_adjoint");
   if (indices) {
-    dim3 grid(blocks_for(num_indices, 1), BP);
+    dim3 grid(blocks_for_points(num_indices), BP);
     k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
@@ -1975,7 +2007,7 @@ int fm_softmin_sweep_fwd(const float* depth, const float* weights, float weight_
   k_sweep_base_k4<<<(B * 8 + 127) / 128, 128, 0, s>>>(cand_k4, base_k4, B, num_candidates);
   FM_CHECK_LAUNCH("fm_softmin_sweep_fwd: k_sweep_base_k4");
   {  // ONE moment pass (candidate 0); every candidate's moments are a rescaling of it
-    dim3 grid(blocks_for(num_indices, 1), B);
+    dim3 grid(blocks_for_points(num_indices), B);
     k_moments<1><<<grid, kThreads, 0, s>>>(depth, base_k4, backward_flow, weights, indices, num_indices,
                                           base_moments, weight_sensitivity, lay1, H, W);
     FM_CHECK_LAUNCH("fm_softmin_sweep_fwd: k_moments");
@@ -1985,7 +2017,7 @@ int fm_softmin_sweep_fwd(const float* depth, const float* weights, float weight_
   FM_CHECK_LAUNCH("fm_softmin_sweep_fwd: k_sweep_scale_solve");
   e = cudaMemsetAsync(w.flowacc, 0, (size_t)items * kSweepAcc * sizeof(double), s);
   if (e != cudaSuccess) return fail("fm_softmin_sweep_fwd: memset", e);
-  dim3 grid(blocks_for(num_indices, 1), items);
+  dim3 grid(blocks_for_points(num_indices), items);
   k_sweep<false><<<grid, kThreads, 0, s>>>(depth, cand_k4, rt, backward_flow, weights, weight_sensitivity,
                                           indices, num_indices, nullptr, w.flowacc, nullptr, nullptr, lay,
                                           H, W);
@@ -2015,7 +2047,7 @@ int fm_softmin_sweep_bwd(const float* depth, const float* weights, float weight_
   if (e != cudaSuccess) return fail("fm_softmin_sweep_bwd: memset", e);
   e = cudaMemsetAsync(w.k4acc, 0, (size_t)(items + B) * 2 * 4 * sizeof(double), s);
   if (e != cudaSuccess) return fail("fm_softmin_sweep_bwd: memset", e);
-  dim3 grid(blocks_for(num_indices, 1), items);
+  dim3 grid(blocks_for_points(num_indices), items);
   k_sweep<true><<<grid, kThreads, 0, s>>>(depth, cand_k4, rt, backward_flow, weights, weight_sensitivity,
                                          indices, num_indices, g_err, w.flowacc, g_depth, g_weights, lay, H,
                                          W);
@@ -2025,11 +2057,11 @@ int fm_softmin_sweep_bwd(const float* depth, const float* weights, float weight_
   // per-candidate adjoint constants, collapsed into one per batch element, then ONE distribution pass
   k_adjoint<<<(items + 63) / 64, 64, 0, s>>>(w.flowacc, w.state, g_rt, 0, nullptr, w.adj, items, 2);
   FM_CHECK_LAUNCH("fm_softmin_sweep_bwd: k_adjoint");
-  k_sweep_aggregate<<<(B + 31) / 32, 32, 0, s>>>(w.adj, cand_k4, w.adj + items, B, num_candidates);
+  k_sweep_aggregate<<<B, 32, 0, s>>>(w.adj, cand_k4, w.adj + items, B, num_candidates);
   FM_CHECK_LAUNCH("fm_softmin_sweep_bwd: k_sweep_aggregate");
   AdamFuse af;
   memset(&af, 0, sizeof(af));
-  dim3 grid1(blocks_for(num_indices, 1), B);
+  dim3 grid1(blocks_for_points(num_indices), B);
   k_distribute<1><<<grid1, kThreads, 0, s>>>(depth, base_k4, backward_flow, const_cast<float*>(weights), indices,
                                             num_indices, w.adj + items, g_depth, g_weights, w.k4acc,
                                             weight_sensitivity, lay1, af, H, W);
