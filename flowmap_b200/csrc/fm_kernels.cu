@@ -418,7 +418,8 @@ k_flow(const float* __restrict__ depth, const float* __restrict__ k4, const floa
   block_accumulate<kFlowVals>(acc, flowacc + (size_t)frame * kFlowAcc, smem);
 }
 
-// Lean phase C (constant intrinsics or one shared focal length): see fm_pixel.cuh.
+// Lean phase C (constant intrinsics or one shared focal length): see fm_pixel.cuh.  The vector
+// instantiation processes its 4 pixels as two packed float32x2 pairs (FFMA2 / FMUL2 / FADD2).
 template <int VEC, bool HASF, bool HASB, bool FOCAL>
 __device__ __forceinline__ void flow_frame_body_lean(const FlowFrameLean& f, const float* __restrict__ D,
                                                      const float* __restrict__ ff, const float* __restrict__ mf,
@@ -430,6 +431,11 @@ __device__ __forceinline__ void flow_frame_body_lean(const FlowFrameLean& f, con
   int base = (blockIdx.x * kThreads + threadIdx.x) * VEC;
   int r = base / W, c0 = base - r * W;
   const int dr = stride / W, dc = stride - dr * W;
+  F2 acc2[kFlowLeanVals];
+  if (VEC == 4) {
+#pragma unroll
+    for (int k = 0; k < kFlowLeanVals; ++k) acc2[k] = f2s(0.f);
+  }
 #pragma unroll 1
   for (; base < N; base += stride) {
     float dv[VEC], ffv[2 * VEC], fbv[2 * VEC], mfv[VEC], mbv[VEC], out[VEC];
@@ -437,17 +443,32 @@ __device__ __forceinline__ void flow_frame_body_lean(const FlowFrameLean& f, con
     if (HASF) { load_vec2<VEC>(ff + 2 * base, ffv); load_vec<VEC>(mf + base, mfv); }
     if (HASB) { load_vec2<VEC>(fb + 2 * base, fbv); load_vec<VEC>(mb + base, mbv); }
     const float y = pix_coord(r, grid.Hf, grid.invH);
+    if (VEC == 4) {
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      out[v] = flow_pixel_lean<HASF, HASB, FOCAL>(
-          f, pix_coord(c0 + v, grid.Wf, grid.invW), y, dv[v], HASF ? ffv[2 * v] : 0.f,
-          HASF ? ffv[2 * v + 1] : 0.f, HASF ? mfv[v] : 0.f, HASB ? fbv[2 * v] : 0.f,
-          HASB ? fbv[2 * v + 1] : 0.f, HASB ? mbv[v] : 0.f, g, rc, acc);
+      for (int h = 0; h < 2; ++h) {
+        const int v = 2 * h;
+        const F2 x = f2(pix_coord(c0 + v, grid.Wf, grid.invW), pix_coord(c0 + v + 1, grid.Wf, grid.invW));
+        const F2 z = f2s(0.f);
+        const F2 o = flow_pixel_lean2<HASF, HASB, FOCAL>(
+            f, x, y, f2(dv[v], dv[v + 1]), HASF ? f2(ffv[2 * v], ffv[2 * v + 2]) : z,
+            HASF ? f2(ffv[2 * v + 1], ffv[2 * v + 3]) : z, HASF ? f2(mfv[v], mfv[v + 1]) : z,
+            HASB ? f2(fbv[2 * v], fbv[2 * v + 2]) : z, HASB ? f2(fbv[2 * v + 1], fbv[2 * v + 3]) : z,
+            HASB ? f2(mbv[v], mbv[v + 1]) : z, g, rc, acc2);
+        out[v] = o.x; out[v + 1] = o.y;
+      }
+      *reinterpret_cast<float4*>(gd + base) = make_float4(out[0], out[1], out[2], out[3]);
+    } else {
+      out[0] = flow_pixel_lean<HASF, HASB, FOCAL>(
+          f, pix_coord(c0, grid.Wf, grid.invW), y, dv[0], HASF ? ffv[0] : 0.f, HASF ? ffv[1] : 0.f,
+          HASF ? mfv[0] : 0.f, HASB ? fbv[0] : 0.f, HASB ? fbv[1] : 0.f, HASB ? mbv[0] : 0.f, g, rc, acc);
+      gd[base] = out[0];
     }
-    if (VEC == 4) *reinterpret_cast<float4*>(gd + base) = make_float4(out[0], out[1], out[2], out[3]);
-    else gd[base] = out[0];
     r += dr; c0 += dc;
     if (c0 >= W) { c0 -= W; ++r; }
+  }
+  if (VEC == 4) {
+#pragma unroll
+    for (int k = 0; k < kFlowLeanVals; ++k) acc[k] += acc2[k].x + acc2[k].y;
   }
 }
 

@@ -52,6 +52,41 @@ FM_HD float fm_fma(float a, float b, float c) {
 #endif
 }
 
+// Packed pairs of float32.  sm_100 issues add / mul / fma on two packed float32 per instruction
+// (FADD2 / FMUL2 / FFMA2, `fma.rn.f32x2`): the lean flow kernel processes two neighbouring pixels
+// per lane-pair with these.  On the host (tests/host_emulation) the same code runs component-wise.
+struct F2 {
+  float x, y;
+};
+FM_HD F2 f2(float a, float b) { F2 r; r.x = a; r.y = b; return r; }
+FM_HD F2 f2s(float a) { F2 r; r.x = a; r.y = a; return r; }
+FM_HD F2 f2_fma(F2 a, F2 b, F2 c) {
+#if defined(__CUDA_ARCH__)
+  const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+  return f2(r.x, r.y);
+#else
+  return f2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+FM_HD F2 f2_mul(F2 a, F2 b) {
+#if defined(__CUDA_ARCH__)
+  const float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  return f2(r.x, r.y);
+#else
+  return f2(a.x * b.x, a.y * b.y);
+#endif
+}
+FM_HD F2 f2_add(F2 a, F2 b) {
+#if defined(__CUDA_ARCH__)
+  const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  return f2(r.x, r.y);
+#else
+  return f2(a.x + b.x, a.y + b.y);
+#endif
+}
+FM_HD F2 f2_sub(F2 a, F2 b) { return f2_add(a, f2(-b.x, -b.y)); }
+FM_HD F2 f2_neg(F2 a) { return f2(-a.x, -a.y); }
+
 constexpr float kProjEps = 1e-5f;   // projection.py:52
 constexpr float kProjInf = 1e8f;    // projection.py:53
 

@@ -273,6 +273,121 @@ FM_HD float flow_pixel_lean(const FlowFrameLean& f, float x, float y, float D, f
   return gD;
 }
 
+// ---------------------------------------------------------------------------------
+// Two-pixel (packed float32x2) form of lean_term / flow_pixel_lean: the two pixels are
+// neighbours in a row, so they share y, the per-frame constants and every control decision
+// except the per-pixel selects (finite test, Huber branch).
+// ---------------------------------------------------------------------------------
+struct LeanTerm2 {
+  F2 P0, P1, P2, d0, d1, d2, su, loss;
+};
+
+FM_HD LeanTerm2 lean_term2(F2 D, F2 dir0, F2 dir1, F2 dir2, float off0, float off1, float off2,
+                           const Cam& k, F2 x, float y, F2 flx, F2 fly, F2 wgt, const RobustCfg& rc) {
+  LeanTerm2 t;
+  t.P0 = f2_fma(D, dir0, f2s(off0));
+  t.P1 = f2_fma(D, dir1, f2s(off1));
+  t.P2 = f2_fma(D, dir2, f2s(off2));
+  const F2 den = f2_add(t.P2, f2s(kProjEps));
+  const F2 inv = f2(fm_rcp(den.x), fm_rcp(den.y));
+  F2 u0 = f2_mul(t.P0, inv), u1 = f2_mul(t.P1, inv), u2 = f2_mul(t.P2, inv);
+  bool fx0 = true, fx1 = true, fx2 = true, fy0 = true, fy1 = true, fy2 = true;
+  const bool okx = (fabsf(u0.x) + fabsf(u1.x)) + fabsf(u2.x) <= 3.0e38f;
+  const bool oky = (fabsf(u0.y) + fabsf(u1.y)) + fabsf(u2.y) <= 3.0e38f;
+  if (!(okx && oky)) {  // rare: nan_to_num branch (projection.py:56), per component
+    u0.x = nan_to_num1(u0.x, fx0); u1.x = nan_to_num1(u1.x, fx1); u2.x = nan_to_num1(u2.x, fx2);
+    u0.y = nan_to_num1(u0.y, fy0); u1.y = nan_to_num1(u1.y, fy1); u2.y = nan_to_num1(u2.y, fy2);
+  }
+  const F2 uvx = f2_fma(f2s(k.fx), u0, f2_mul(f2s(k.cx), u2));
+  const F2 uvy = f2_fma(f2s(k.fy), u1, f2_mul(f2s(k.cy), u2));
+  const F2 sx = f2_mul(f2_sub(f2_sub(uvx, x), flx), f2s(rc.ax));
+  const F2 sy = f2_mul(f2_sub(f2_sub(uvy, f2s(y)), fly), f2s(rc.ay));
+  const F2 n2 = f2_fma(sx, sx, f2_mul(sy, sy));
+  F2 kx, ky, val;
+  if (rc.mapping == MAP_L2) {
+    kx = f2s(rc.ax); ky = f2s(rc.ay); val = f2_mul(f2s(0.5f), n2);
+  } else {
+    const F2 inv_n = f2(n2.x > 0.0f ? fm_rsqrt(n2.x) : 0.0f, n2.y > 0.0f ? fm_rsqrt(n2.y) : 0.0f);
+    const F2 n = f2_mul(n2, inv_n);
+    F2 kk = inv_n;
+    val = n;
+    if (rc.mapping == MAP_HUBER) {
+      const F2 vq = f2_mul(f2s(0.5f * rc.inv_delta), n2), vl = f2_sub(n, f2s(0.5f * rc.delta));
+      const bool qx = n.x <= rc.delta, qy = n.y <= rc.delta;
+      kk = f2(qx ? rc.inv_delta : inv_n.x, qy ? rc.inv_delta : inv_n.y);
+      val = f2(qx ? vq.x : vl.x, qy ? vq.y : vl.y);
+    }
+    kx = f2_mul(kk, f2s(rc.ax)); ky = f2_mul(kk, f2s(rc.ay));
+  }
+  t.loss = f2_mul(wgt, val);
+  const F2 duvx = f2_mul(f2_mul(wgt, sx), kx), duvy = f2_mul(f2_mul(wgt, sy), ky);
+  F2 du0 = f2_mul(f2s(k.fx), duvx), du1 = f2_mul(f2s(k.fy), duvy);
+  F2 du2 = f2_fma(f2s(k.cx), duvx, f2_mul(f2s(k.cy), duvy));
+  t.su = f2_fma(du0, u0, f2_mul(du1, u1));
+  if (!(okx && oky)) {
+    if (!fx0) du0.x = 0.0f;
+    if (!fx1) du1.x = 0.0f;
+    if (!fx2) du2.x = 0.0f;
+    if (!fy0) du0.y = 0.0f;
+    if (!fy1) du1.y = 0.0f;
+    if (!fy2) du2.y = 0.0f;
+  }
+  t.d0 = f2_mul(du0, inv);
+  t.d1 = f2_mul(du1, inv);
+  const F2 dot = f2_fma(du0, t.P0, f2_fma(du1, t.P1, f2_mul(du2, t.P2)));
+  t.d2 = f2_mul(f2_fma(f2_neg(dot), inv, du2), inv);
+  return t;
+}
+
+// Two neighbouring pixels (x.x, x.y) of one row; acc holds kFlowLeanVals packed accumulators
+// (the two lanes are added together when the thread is done).  Returns the two depth gradients.
+template <bool HASF, bool HASB, bool FOCAL>
+FM_HD F2 flow_pixel_lean2(const FlowFrameLean& f, F2 x, float y, F2 D, F2 ffx, F2 ffy, F2 mf, F2 fbx,
+                          F2 fby, F2 mb, float g, const RobustCfg& rc, F2* acc) {
+  const F2 rx = f2_mul(f2_sub(x, f2s(f.kk.cx)), f2s(f.kk.ifx));
+  const float ry = (y - f.kk.cy) * f.kk.ify;
+  F2 gD = f2s(0.f);
+  if (HASF) {
+    // m = R^T ray: the y / constant part is shared by the two pixels
+    const F2 m0 = f2_fma(f2s(f.rtF[0]), rx, f2s(fm_fma(f.rtF[1], ry, f.rtF[2])));
+    const F2 m1 = f2_fma(f2s(f.rtF[3]), rx, f2s(fm_fma(f.rtF[4], ry, f.rtF[5])));
+    const F2 m2 = f2_fma(f2s(f.rtF[6]), rx, f2s(fm_fma(f.rtF[7], ry, f.rtF[8])));
+    const LeanTerm2 t = lean_term2(D, m0, m1, m2, f.cF[0], f.cF[1], f.cF[2], f.kn, x, y, ffx, ffy,
+                                   f2_mul(f2s(g), mf), rc);
+    acc[0] = f2_add(acc[0], t.loss);
+    const F2 gd = f2_fma(t.d0, m0, f2_fma(t.d1, m1, f2_mul(t.d2, m2)));
+    gD = gd;
+    acc[1] = f2_fma(t.P1, t.d2, f2_fma(f2_neg(t.P2), t.d1, acc[1]));
+    acc[2] = f2_fma(t.P2, t.d0, f2_fma(f2_neg(t.P0), t.d2, acc[2]));
+    acc[3] = f2_fma(t.P0, t.d1, f2_fma(f2_neg(t.P1), t.d0, acc[3]));
+    acc[4] = f2_add(acc[4], t.d0); acc[5] = f2_add(acc[5], t.d1); acc[6] = f2_add(acc[6], t.d2);
+    if (FOCAL) {
+      const F2 dz = f2_fma(f2s(f.r2F[0]), t.d0, f2_fma(f2s(f.r2F[1]), t.d1, f2_mul(f2s(f.r2F[2]), t.d2)));
+      acc[13] = f2_add(acc[13], f2_fma(f2_neg(D), f2_sub(gd, dz), t.su));
+    }
+  }
+  if (HASB) {
+    const F2 n0 = f2_fma(f2s(f.rB[0]), rx, f2s(fm_fma(f.rB[1], ry, f.rB[2])));
+    const F2 n1 = f2_fma(f2s(f.rB[3]), rx, f2s(fm_fma(f.rB[4], ry, f.rB[5])));
+    const F2 n2 = f2_fma(f2s(f.rB[6]), rx, f2s(fm_fma(f.rB[7], ry, f.rB[8])));
+    const LeanTerm2 t = lean_term2(D, n0, n1, n2, f.tB[0], f.tB[1], f.tB[2], f.kp, x, y, fbx, fby,
+                                   f2_mul(f2s(g), mb), rc);
+    acc[0] = f2_add(acc[0], t.loss);
+    const F2 gd = f2_fma(t.d0, n0, f2_fma(t.d1, n1, f2_mul(t.d2, n2)));
+    gD = f2_add(gD, gd);
+    const F2 e0 = f2_mul(D, n0), e1 = f2_mul(D, n1), e2 = f2_mul(D, n2);
+    acc[7] = f2_fma(e1, t.d2, f2_fma(f2_neg(e2), t.d1, acc[7]));
+    acc[8] = f2_fma(e2, t.d0, f2_fma(f2_neg(e0), t.d2, acc[8]));
+    acc[9] = f2_fma(e0, t.d1, f2_fma(f2_neg(e1), t.d0, acc[9]));
+    acc[10] = f2_add(acc[10], t.d0); acc[11] = f2_add(acc[11], t.d1); acc[12] = f2_add(acc[12], t.d2);
+    if (FOCAL) {
+      const F2 dz = f2_fma(f2s(f.c2B[0]), t.d0, f2_fma(f2s(f.c2B[1]), t.d1, f2_mul(f2s(f.c2B[2]), t.d2)));
+      acc[13] = f2_add(acc[13], f2_fma(f2_neg(D), f2_sub(gd, dz), t.su));
+    }
+  }
+  return gD;
+}
+
 // Lean accumulators of frame `frame` -> the standard slot layout (kFlowVals) that the pose /
 // intrinsics reductions read.  rtF / rtB: [R|t] (3x4 row-major, float) of pair (frame, frame+1)
 // / (frame-1, frame) or NULL; f_of_frame: the shared focal length expressed through this

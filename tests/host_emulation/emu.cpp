@@ -106,6 +106,26 @@ void emu_flow_lean(const float* depth, const float* k4, const float* rt, const f
     if (hasB) tb = ld(pairB);
     fill_lean(f, hasF ? &tf : nullptr, hasB ? &tb : nullptr);
     double lean[kFlowLeanVals] = {0};
+    // even widths: the packed two-pixel code path (what the vector kernel instantiation runs)
+    if (W % 2 == 0) {
+      for (int j = 0; j < N; j += 2) {
+        F2 acc2[kFlowLeanVals];
+        for (int k = 0; k < kFlowLeanVals; ++k) acc2[k] = f2s(0.f);
+        const size_t jf = (size_t)(hasF ? pairF : 0) * N + j, jb = (size_t)(hasB ? pairB : 0) * N + j;
+        const F2 x = f2(pix_coord(j % W, grid.Wf, grid.invW), pix_coord(j % W + 1, grid.Wf, grid.invW));
+        const float y = pix_coord(j / W, grid.Hf, grid.invH);
+        const F2 D = f2(depth[(size_t)frame * N + j], depth[(size_t)frame * N + j + 1]);
+        const F2 z = f2s(0.f);
+        F2 o;
+#define FM_CALL2(HF, HB) o = focal_mode ? flow_pixel_lean2<HF, HB, true>(f, x, y, D, HF ? f2(ff[jf * 2], ff[jf * 2 + 2]) : z, HF ? f2(ff[jf * 2 + 1], ff[jf * 2 + 3]) : z, HF ? f2(mf[jf], mf[jf + 1]) : z, HB ? f2(fb[jb * 2], fb[jb * 2 + 2]) : z, HB ? f2(fb[jb * 2 + 1], fb[jb * 2 + 3]) : z, HB ? f2(mb[jb], mb[jb + 1]) : z, g, rc, acc2) \
+                                   : flow_pixel_lean2<HF, HB, false>(f, x, y, D, HF ? f2(ff[jf * 2], ff[jf * 2 + 2]) : z, HF ? f2(ff[jf * 2 + 1], ff[jf * 2 + 3]) : z, HF ? f2(mf[jf], mf[jf + 1]) : z, HB ? f2(fb[jb * 2], fb[jb * 2 + 2]) : z, HB ? f2(fb[jb * 2 + 1], fb[jb * 2 + 3]) : z, HB ? f2(mb[jb], mb[jb + 1]) : z, g, rc, acc2)
+        if (hasF && hasB) { FM_CALL2(true, true); } else if (hasF) { FM_CALL2(true, false); } else { FM_CALL2(false, true); }
+#undef FM_CALL2
+        g_depth[(size_t)frame * N + j] = o.x;
+        g_depth[(size_t)frame * N + j + 1] = o.y;
+        for (int k = 0; k < kFlowLeanVals; ++k) lean[k] += (double)acc2[k].x + (double)acc2[k].y;
+      }
+    } else
     for (int j = 0; j < N; ++j) {
       float acc[kFlowLeanVals] = {0};
       const size_t jf = (size_t)(hasF ? pairF : 0) * N + j, jb = (size_t)(hasB ? pairB : 0) * N + j;
