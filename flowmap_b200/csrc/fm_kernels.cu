@@ -184,22 +184,6 @@ __device__ __forceinline__ float weight_of(float stored, float sens) {
   return sens == 0.f ? stored : __fdividef(1.0f, 1.0f + __expf(-sens * stored));
 }
 
-// The two horizontally adjacent bilinear taps (x0, x0 + 1) of a row.  With 16-byte aligned rows
-// both usually sit in one aligned group of four floats: ONE 128-bit load instead of two 32-bit
-// ones (the gather kernels are bound by L1 wavefronts, one per load instruction and sector).
-template <bool ALIGNED>
-__device__ __forceinline__ void load_pair(const float* __restrict__ row, int x0, int x1, float& v0, float& v1) {
-  const int k = x0 & 3;
-  if (ALIGNED && k != 3) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(row + (x0 - k)));
-    v0 = k == 0 ? g.x : (k == 1 ? g.y : g.z);
-    v1 = k == 0 ? g.y : (k == 1 ? g.z : g.w);
-  } else {
-    v0 = __ldg(row + x0);
-    v1 = __ldg(row + x1);
-  }
-}
-
 // Load the 4 (or 1) values a thread owns.
 template <int VEC>
 __device__ __forceinline__ void load_vec(const float* p, float* out) {
@@ -279,7 +263,7 @@ k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
   const float* db = da + N;
   const float* fl = bflow + pa.flow;
   const float* wt = weights ? weights + pa.weight : nullptr;
-  auto load_a = [da, W](int yy, int x0, int x1, float& v0, float& v1) { load_pair<VEC == 4>(da + yy * W, x0, x1, v0, v1); };
+  auto load_a = [da, W](int yy, int xx) { return __ldg(da + yy * W + xx); };
   // float32 per-thread partials: a thread sees at most a few dozen (shifted, O(1)) terms, the
   // cross-thread / cross-block sums run in float64.
   float acc[kNumMoments];
@@ -650,7 +634,7 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
   const float* fl = bflow + pa.flow;
   float* wt = weights ? weights + pa.weight : nullptr;
   float* gda = g_depth + pa.depth_a;
-  auto load_a = [da, W](int yy, int x0, int x1, float& v0, float& v1) { load_pair<VEC == 4>(da + yy * W, x0, x1, v0, v1); };
+  auto load_a = [da, W](int yy, int xx) { return __ldg(da + yy * W + xx); };
   auto scatter = [gda, W](int y0, int x0, float v0, float v1) { red_pair<VEC == 4>(gda + y0 * W, x0, W, v0, v1); };
   float* gdb = gda + N;
   float* gw = g_weights ? g_weights + pa.weight : nullptr;
@@ -1087,7 +1071,7 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
     const float2 sxy = __ldg(reinterpret_cast<const float2*>(txy) + sidx);
     const Taps t = bilinear_taps(sxy.x, sxy.y, grid);
     float q[3];
-    sample_surface(t, grid, ks, [D, W](int yy, int x0, int x1, float& v0, float& v1) { v0 = __ldg(D + yy * W + x0); v1 = __ldg(D + yy * W + x1); }, q[0], q[1], q[2]);
+    sample_surface(t, grid, ks, [D, W](int yy, int xx) { return __ldg(D + yy * W + xx); }, q[0], q[1], q[2]);
     float Xw[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)

@@ -198,10 +198,8 @@ FM_HD void tap_rays(const Taps& t, const GridDims& g, const Cam& k, float& rx0, 
 template <typename Load>
 FM_HD void sample_surface(const Taps& t, const GridDims& g, const Cam& k, Load load, float& qx,
                           float& qy, float& qz) {
-  // load(row, x0, x1, v0, v1): the two taps of a row (x1 == x0 + 1, or x1 == x0 at the border)
-  float d00, d01, d10, d11;
-  load(t.y0, t.x0, t.x1, d00, d01);
-  load(t.y1, t.x0, t.x1, d10, d11);
+  float d00 = load(t.y0, t.x0), d01 = load(t.y0, t.x1);
+  float d10 = load(t.y1, t.x0), d11 = load(t.y1, t.x1);
   float a00 = t.w00 * d00, a01 = t.w01 * d01, a10 = t.w10 * d10, a11 = t.w11 * d11;
   float rx0, rx1, ry0, ry1;
   tap_rays(t, g, k, rx0, ry0, rx1, ry1);
