@@ -279,15 +279,23 @@ FM_HD float flow_pixel_lean(const FlowFrameLean& f, float x, float y, float D, f
 // except the per-pixel selects (finite test, Huber branch).
 // ---------------------------------------------------------------------------------
 struct LeanTerm2 {
-  F2 P0, P1, P2, d0, d1, d2, su, loss;
+  F2 P0, P1, P2, d0, d1, d2, su, loss, uvx, uvy;
 };
+struct Cam2 {  // two cameras side by side (the same one twice for two pixels of one frame)
+  F2 fx, fy, cx, cy;
+};
+FM_HD Cam2 cam2(const Cam& a, const Cam& b) {
+  Cam2 c;
+  c.fx = f2(a.fx, b.fx); c.fy = f2(a.fy, b.fy); c.cx = f2(a.cx, b.cx); c.cy = f2(a.cy, b.cy);
+  return c;
+}
 
-FM_HD LeanTerm2 lean_term2(F2 D, F2 dir0, F2 dir1, F2 dir2, float off0, float off1, float off2,
-                           const Cam& k, F2 x, float y, F2 flx, F2 fly, F2 wgt, const RobustCfg& rc) {
+FM_HD LeanTerm2 lean_term2(F2 D, F2 dir0, F2 dir1, F2 dir2, F2 off0, F2 off1, F2 off2, const Cam2& k,
+                           F2 x, F2 y, F2 flx, F2 fly, F2 wgt, const RobustCfg& rc) {
   LeanTerm2 t;
-  t.P0 = f2_fma(D, dir0, f2s(off0));
-  t.P1 = f2_fma(D, dir1, f2s(off1));
-  t.P2 = f2_fma(D, dir2, f2s(off2));
+  t.P0 = f2_fma(D, dir0, off0);
+  t.P1 = f2_fma(D, dir1, off1);
+  t.P2 = f2_fma(D, dir2, off2);
   const F2 den = f2_add(t.P2, f2s(kProjEps));
   const F2 inv = f2(fm_rcp(den.x), fm_rcp(den.y));
   F2 u0 = f2_mul(t.P0, inv), u1 = f2_mul(t.P1, inv), u2 = f2_mul(t.P2, inv);
@@ -298,10 +306,12 @@ FM_HD LeanTerm2 lean_term2(F2 D, F2 dir0, F2 dir1, F2 dir2, float off0, float of
     u0.x = nan_to_num1(u0.x, fx0); u1.x = nan_to_num1(u1.x, fx1); u2.x = nan_to_num1(u2.x, fx2);
     u0.y = nan_to_num1(u0.y, fy0); u1.y = nan_to_num1(u1.y, fy1); u2.y = nan_to_num1(u2.y, fy2);
   }
-  const F2 uvx = f2_fma(f2s(k.fx), u0, f2_mul(f2s(k.cx), u2));
-  const F2 uvy = f2_fma(f2s(k.fy), u1, f2_mul(f2s(k.cy), u2));
+  const F2 uvx = f2_fma(k.fx, u0, f2_mul(k.cx, u2));
+  const F2 uvy = f2_fma(k.fy, u1, f2_mul(k.cy, u2));
+  t.uvx = uvx;
+  t.uvy = uvy;
   const F2 sx = f2_mul(f2_sub(f2_sub(uvx, x), flx), f2s(rc.ax));
-  const F2 sy = f2_mul(f2_sub(f2_sub(uvy, f2s(y)), fly), f2s(rc.ay));
+  const F2 sy = f2_mul(f2_sub(f2_sub(uvy, y), fly), f2s(rc.ay));
   const F2 n2 = f2_fma(sx, sx, f2_mul(sy, sy));
   F2 kx, ky, val;
   if (rc.mapping == MAP_L2) {
@@ -321,8 +331,8 @@ FM_HD LeanTerm2 lean_term2(F2 D, F2 dir0, F2 dir1, F2 dir2, float off0, float of
   }
   t.loss = f2_mul(wgt, val);
   const F2 duvx = f2_mul(f2_mul(wgt, sx), kx), duvy = f2_mul(f2_mul(wgt, sy), ky);
-  F2 du0 = f2_mul(f2s(k.fx), duvx), du1 = f2_mul(f2s(k.fy), duvy);
-  F2 du2 = f2_fma(f2s(k.cx), duvx, f2_mul(f2s(k.cy), duvy));
+  F2 du0 = f2_mul(k.fx, duvx), du1 = f2_mul(k.fy, duvy);
+  F2 du2 = f2_fma(k.cx, duvx, f2_mul(k.cy, duvy));
   t.su = f2_fma(du0, u0, f2_mul(du1, u1));
   if (!(okx && oky)) {
     if (!fx0) du0.x = 0.0f;
@@ -352,8 +362,8 @@ FM_HD F2 flow_pixel_lean2(const FlowFrameLean& f, F2 x, float y, F2 D, F2 ffx, F
     const F2 m0 = f2_fma(f2s(f.rtF[0]), rx, f2s(fm_fma(f.rtF[1], ry, f.rtF[2])));
     const F2 m1 = f2_fma(f2s(f.rtF[3]), rx, f2s(fm_fma(f.rtF[4], ry, f.rtF[5])));
     const F2 m2 = f2_fma(f2s(f.rtF[6]), rx, f2s(fm_fma(f.rtF[7], ry, f.rtF[8])));
-    const LeanTerm2 t = lean_term2(D, m0, m1, m2, f.cF[0], f.cF[1], f.cF[2], f.kn, x, y, ffx, ffy,
-                                   f2_mul(f2s(g), mf), rc);
+    const LeanTerm2 t = lean_term2(D, m0, m1, m2, f2s(f.cF[0]), f2s(f.cF[1]), f2s(f.cF[2]),
+                                   cam2(f.kn, f.kn), x, f2s(y), ffx, ffy, f2_mul(f2s(g), mf), rc);
     acc[0] = f2_add(acc[0], t.loss);
     const F2 gd = f2_fma(t.d0, m0, f2_fma(t.d1, m1, f2_mul(t.d2, m2)));
     gD = gd;
@@ -370,8 +380,8 @@ FM_HD F2 flow_pixel_lean2(const FlowFrameLean& f, F2 x, float y, F2 D, F2 ffx, F
     const F2 n0 = f2_fma(f2s(f.rB[0]), rx, f2s(fm_fma(f.rB[1], ry, f.rB[2])));
     const F2 n1 = f2_fma(f2s(f.rB[3]), rx, f2s(fm_fma(f.rB[4], ry, f.rB[5])));
     const F2 n2 = f2_fma(f2s(f.rB[6]), rx, f2s(fm_fma(f.rB[7], ry, f.rB[8])));
-    const LeanTerm2 t = lean_term2(D, n0, n1, n2, f.tB[0], f.tB[1], f.tB[2], f.kp, x, y, fbx, fby,
-                                   f2_mul(f2s(g), mb), rc);
+    const LeanTerm2 t = lean_term2(D, n0, n1, n2, f2s(f.tB[0]), f2s(f.tB[1]), f2s(f.tB[2]),
+                                   cam2(f.kp, f.kp), x, f2s(y), fbx, fby, f2_mul(f2s(g), mb), rc);
     acc[0] = f2_add(acc[0], t.loss);
     const F2 gd = f2_fma(t.d0, n0, f2_fma(t.d1, n1, f2_mul(t.d2, n2)));
     gD = f2_add(gD, gd);
