@@ -1032,34 +1032,6 @@ __device__ __forceinline__ bool track_term_lean(const float* rec, const float* X
   return true;
 }
 
-// Packed form: two (world point, target frame) terms at once.  Xw0/1/2 hold the x/y/z of the
-// two world points, rec_a / rec_b the two target-frame records, (gtx, gty) the two target
-// positions.  mask lanes that must not contribute are passed in `ok` and updated with the
-// in-frame test; the adjoint d and the world gradient g come back already masked.
-__device__ __forceinline__ void track_term_lean2(const float* rec_a, const float* rec_b, F2 Xw0, F2 Xw1, F2 Xw2,
-                                                 F2 gtx, F2 gty, const RobustCfg& rc, bool& ok_a, bool& ok_b,
-                                                 LeanTerm2& t, F2* g) {
-  auto R = [&](int i) { return f2(rec_a[i], rec_b[i]); };
-  const F2 dir0 = f2_fma(R(0), Xw0, f2_fma(R(3), Xw1, f2_mul(R(6), Xw2)));
-  const F2 dir1 = f2_fma(R(1), Xw0, f2_fma(R(4), Xw1, f2_mul(R(7), Xw2)));
-  const F2 dir2 = f2_fma(R(2), Xw0, f2_fma(R(5), Xw1, f2_mul(R(8), Xw2)));
-  Cam2 k;
-  k.fx = R(15); k.fy = R(16); k.cx = R(17); k.cy = R(18);
-  t = lean_term2(f2s(1.0f), dir0, dir1, dir2, R(12), R(13), R(14), k, gtx, gty, f2s(0.f), f2s(0.f), f2s(1.0f), rc);
-  ok_a = ok_a && in_unit_square(t.uvx.x, t.uvy.x);  // projection.py:294-296 (predicted target)
-  ok_b = ok_b && in_unit_square(t.uvx.y, t.uvy.y);
-  const F2 m = f2(ok_a ? 1.0f : 0.0f, ok_b ? 1.0f : 0.0f);
-  // masked with a select, not a multiply: an excluded lane may hold inf / nan
-  t.d0 = f2(ok_a ? t.d0.x : 0.f, ok_b ? t.d0.y : 0.f);
-  t.d1 = f2(ok_a ? t.d1.x : 0.f, ok_b ? t.d1.y : 0.f);
-  t.d2 = f2(ok_a ? t.d2.x : 0.f, ok_b ? t.d2.y : 0.f);
-  t.loss = f2(ok_a ? t.loss.x : 0.f, ok_b ? t.loss.y : 0.f);
-  (void)m;
-  g[0] = f2_fma(R(0), t.d0, f2_fma(R(1), t.d1, f2_mul(R(2), t.d2)));
-  g[1] = f2_fma(R(3), t.d0, f2_fma(R(4), t.d1, f2_mul(R(5), t.d2)));
-  g[2] = f2_fma(R(6), t.d0, f2_fma(R(7), t.d1, f2_mul(R(8), t.d2)));
-}
-
 __global__ void __launch_bounds__(kThreads)
 k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const float* __restrict__ ext,
             const int* __restrict__ seg, const float* __restrict__ txy,
@@ -1105,28 +1077,27 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
     for (int i = 0; i < 3; ++i)
       Xw[i] = fm_fma(rs[i * 3 + 0], q[0], fm_fma(rs[i * 3 + 1], q[1], fm_fma(rs[i * 3 + 2], q[2], rs[9 + i])));
     xw[sidx * 3 + 0] = Xw[0]; xw[sidx * 3 + 1] = Xw[1]; xw[sidx * 3 + 2] = Xw[2];
-    // two target rows per iteration, packed float32x2 (FFMA2): lane a = row ft, lane b = row ft + 1
-    F2 G2[3] = {f2s(0.f), f2s(0.f), f2s(0.f)}, lc2[2] = {f2s(0.f), f2s(0.f)};
-    const F2 X0 = f2s(Xw[0]), X1 = f2s(Xw[1]), X2 = f2s(Xw[2]);
-    for (int ft = 0; ft < si.rows; ft += 2) {
-      const bool has_b = ft + 1 < si.rows;
-      const size_t ta = (size_t)si.sample_start + (size_t)ft * si.n + p;
-      const size_t tb = has_b ? ta + si.n : ta;
-      bool ok_a = tvis[ta] != 0, ok_b = has_b && tvis[tb] != 0;
-      if (!(ok_a || ok_b)) continue;
-      const float2 ga = __ldg(reinterpret_cast<const float2*>(txy) + ta);
-      const float2 gb = __ldg(reinterpret_cast<const float2*>(txy) + tb);
-      LeanTerm2 lt;
-      F2 g[3];
-      track_term_lean2(sm + ft * kTrackRec, sm + (has_b ? ft + 1 : ft) * kTrackRec, X0, X1, X2,
-                       f2(ga.x, gb.x), f2(ga.y, gb.y), rc, ok_a, ok_b, lt, g);
-      lc2[0] = f2_add(lc2[0], lt.loss);
-      lc2[1] = f2_add(lc2[1], f2(ok_a ? 1.f : 0.f, ok_b ? 1.f : 0.f));
-      G2[0] = f2_add(G2[0], g[0]); G2[1] = f2_add(G2[1], g[1]); G2[2] = f2_add(G2[2], g[2]);
+    float G[3] = {0.f, 0.f, 0.f};
+    // the next target row's visibility / position is fetched while the current one is processed
+    size_t tidx_n = (size_t)si.sample_start + p;
+    unsigned char vis_n = tvis[tidx_n];
+    float2 gxy_n = __ldg(reinterpret_cast<const float2*>(txy) + tidx_n);
+    for (int ft = 0; ft < si.rows; ++ft) {
+      const unsigned char vis_t = vis_n;
+      const float2 gxy = gxy_n;
+      if (ft + 1 < si.rows) {
+        tidx_n += si.n;
+        vis_n = tvis[tidx_n];
+        gxy_n = __ldg(reinterpret_cast<const float2*>(txy) + tidx_n);
+      }
+      if (!vis_t) continue;
+      LeanTerm lt;
+      float g[3];
+      if (!track_term_lean(sm + ft * kTrackRec, Xw, gxy.x, gxy.y, rc, lt, g)) continue;
+      lc[0] += lt.loss;
+      lc[1] += 1.f;
+      G[0] += g[0]; G[1] += g[1]; G[2] += g[2];
     }
-    const float G[3] = {G2[0].x + G2[0].y, G2[1].x + G2[1].y, G2[2].x + G2[2].y};
-    lc[0] = lc2[0].x + lc2[0].y;
-    lc[1] = lc2[1].x + lc2[1].y;
     // camera-space adjoint of the sampled point (unscaled), source K / twist sums
     const float dq0 = fm_fma(rs[0], G[0], fm_fma(rs[3], G[1], rs[6] * G[2]));
     const float dq1 = fm_fma(rs[1], G[0], fm_fma(rs[4], G[1], rs[7] * G[2]));
@@ -1170,42 +1141,36 @@ k_track_tgt(const float* __restrict__ k4, const float* __restrict__ ext, const i
     const size_t tidx = (size_t)si.sample_start + (size_t)ft * si.n + p;
     const float2 gxy = __ldg(reinterpret_cast<const float2*>(txy) + tidx);
     const Cam kt = sm_cam(rec);
-    // two source rows per iteration, packed float32x2: lane a = row fs, lane b = row fs + 1
-    F2 acc2[kTrackAcc];
-#pragma unroll
-    for (int i = 0; i < kTrackAcc; ++i) acc2[i] = f2s(0.f);
-    const F2 gx2 = f2s(gxy.x), gy2 = f2s(gxy.y);
-    for (int fs = 0; fs < si.rows; fs += 2) {
-      const bool has_b = fs + 1 < si.rows;
-      const size_t sa = (size_t)si.sample_start + (size_t)fs * si.n + p;
-      const size_t sb = has_b ? sa + si.n : sa;
-      bool ok_a = flag[sa] != 0, ok_b = has_b && flag[sb] != 0;
-      if (!(ok_a || ok_b)) continue;
-      // an excluded lane reuses the other lane's (valid) point so that no garbage is computed on
-      const size_t la = ok_a ? sa : sb, lb = ok_b ? sb : sa;
-      const F2 X0 = f2(xw[la * 3 + 0], xw[lb * 3 + 0]), X1 = f2(xw[la * 3 + 1], xw[lb * 3 + 1]);
-      const F2 X2 = f2(xw[la * 3 + 2], xw[lb * 3 + 2]);
-      LeanTerm2 lt;
-      F2 g[3];
-      track_term_lean2(rec, rec, X0, X1, X2, gx2, gy2, rc, ok_a, ok_b, lt, g);
-      if (!(ok_a || ok_b)) continue;
+    // the next row's world point is fetched while the current one is processed
+    size_t sidx_n = (size_t)si.sample_start + p;
+    unsigned char fl_n = flag[sidx_n];
+    float xn0 = xw[sidx_n * 3 + 0], xn1 = xw[sidx_n * 3 + 1], xn2 = xw[sidx_n * 3 + 2];
+    for (int fs = 0; fs < si.rows; ++fs) {
+      const unsigned char fl = fl_n;
+      const float Xw[3] = {xn0, xn1, xn2};
+      if (fs + 1 < si.rows) {
+        sidx_n += si.n;
+        fl_n = flag[sidx_n];
+        xn0 = xw[sidx_n * 3 + 0]; xn1 = xw[sidx_n * 3 + 1]; xn2 = xw[sidx_n * 3 + 2];
+      }
+      if (!fl) continue;
+      LeanTerm lt;
+      float g[3];
+      if (!track_term_lean(rec, Xw, gxy.x, gxy.y, rc, lt, g)) continue;
       // K gradient of the projection: du0 = fx duvx = d0 / inv  =>  duvx = d0 (P_z + eps) / fx
-      const F2 den = f2_add(lt.P2, f2s(kProjEps));
-      const F2 inv = f2(fm_rcp(den.x), fm_rcp(den.y));
-      const F2 u0 = f2_mul(lt.P0, inv), u1 = f2_mul(lt.P1, inv), u2 = f2_mul(lt.P2, inv);
-      const F2 duvx = f2_mul(f2_mul(lt.d0, den), f2s(kt.ifx)), duvy = f2_mul(f2_mul(lt.d1, den), f2s(kt.ify));
-      acc2[0] = f2_fma(duvx, u0, acc2[0]);
-      acc2[1] = f2_fma(duvy, u1, acc2[1]);
-      acc2[2] = f2_fma(duvx, u2, acc2[2]);
-      acc2[3] = f2_fma(duvy, u2, acc2[3]);
-      const F2 d0 = f2_sub(X0, f2s(rec[9])), d1 = f2_sub(X1, f2s(rec[10])), d2 = f2_sub(X2, f2s(rec[11]));
-      acc2[4] = f2_fma(f2_neg(d1), g[2], f2_fma(d2, g[1], acc2[4]));
-      acc2[5] = f2_fma(f2_neg(d2), g[0], f2_fma(d0, g[2], acc2[5]));
-      acc2[6] = f2_fma(f2_neg(d0), g[1], f2_fma(d1, g[0], acc2[6]));
-      acc2[7] = f2_sub(acc2[7], g[0]); acc2[8] = f2_sub(acc2[8], g[1]); acc2[9] = f2_sub(acc2[9], g[2]);
+      const float den = lt.P2 + kProjEps, inv = fm_rcp(den);
+      const float u0 = lt.P0 * inv, u1 = lt.P1 * inv, u2 = lt.P2 * inv;
+      const float duvx = lt.d0 * den * kt.ifx, duvy = lt.d1 * den * kt.ify;
+      acc[0] = fm_fma(duvx, u0, acc[0]);
+      acc[1] = fm_fma(duvy, u1, acc[1]);
+      acc[2] = fm_fma(duvx, u2, acc[2]);
+      acc[3] = fm_fma(duvy, u2, acc[3]);
+      const float d0 = Xw[0] - rec[9], d1 = Xw[1] - rec[10], d2 = Xw[2] - rec[11];
+      acc[4] -= d1 * g[2] - d2 * g[1];
+      acc[5] -= d2 * g[0] - d0 * g[2];
+      acc[6] -= d0 * g[1] - d1 * g[0];
+      acc[7] -= g[0]; acc[8] -= g[1]; acc[9] -= g[2];
     }
-#pragma unroll
-    for (int i = 0; i < kTrackAcc; ++i) acc[i] = acc2[i].x + acc2[i].y;
   }
   block_accumulate<kTrackAcc>(acc, trackacc + (size_t)(si.start_frame + ft) * kTrackAcc, red);
 }
