@@ -526,3 +526,78 @@ def test_zero_masks_use_denominator_one():
     loss = ops.flow_loss(d, rt, k4, z2, z2, z1, z1, ops.mask_sum(z1, z1), "huber", 0.01, 1000.0)
     loss.backward()
     assert float(loss) == 0.0 and bool(torch.isfinite(d.grad).all()) and float(d.grad.abs().max()) == 0.0
+
+
+def test_c2_shape_full_step_vs_oracle():
+    """BASELINE configs[1] (LLFF shape: 30 x 360 x 480, flow + tracks): one fused step with
+    tracking against the float64 oracle (loss parts, poses, gradients)."""
+    from oracle import flowmap_oracle as O
+    from flowmap_b200.overfit import FusedOverfitter, OverfitCfg
+    from flowmap_b200.types import Batch, Flows, Tracks
+    f, h, w = 30, 360, 480
+    fl = O.synthetic_flows(f, h, w, seed=1, dtype=torch.float32)
+    gen = torch.Generator().manual_seed(2)
+    depth = 1.0 + 0.5 * torch.rand(f, h, w, generator=gen)
+    wparam = 0.01 * torch.randn(f - 1, h, w, generator=gen)
+    trk = O.synthetic_tracks(f, n_points=400, seed=3)
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    st = O.OverfitOracle(O.OverfitConfig(intrinsics="regressed", use_tracking=True,
+                                         tracking_enable_after=0), f, h, w, dtype=torch.float64)
+    with torch.no_grad():
+        st.depth.copy_(depth.double())
+        st.weights.copy_(wparam.double())
+    fl64 = O.Flows(*(t.double() for t in (fl.forward, fl.backward, fl.forward_mask, fl.backward_mask)))
+    trk64 = [O.Tracks(t.xy.double(), t.visibility, t.start_frame) for t in trk]
+    ref = st.training_step(fl64, trk64)
+    batch = Batch(torch.zeros(1, 1, 1, 1, 1).expand(1, f, 3, h, w), torch.arange(f)[None], ["s"], ["d"])
+    o = FusedOverfitter(OverfitCfg(use_tracking=True, tracking_enable_after=0), batch,
+                        Flows(fl.forward, fl.backward, fl.forward_mask, fl.backward_mask),
+                        [Tracks(t.xy, t.visibility, t.start_frame) for t in trk])
+    with torch.no_grad():
+        o.model.backbone.depth.copy_(depth)
+        o.model.backbone.weights.copy_(wparam)
+    loss, _ = o.training_step(update=False)
+    gr = o.gradients()
+    assert abs(float(loss) - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert max_abs(o.extrinsics().cpu(), ref["extrinsics"]) <= 2e-5
+    assert rel_l2(gr["depth"].cpu(), ref["grads"]["depth"]) <= 1e-4
+    assert rel_l2(gr["weights"].cpu(), ref["grads"]["weights"]) <= 1e-4
+    assert abs(float(gr["focal"]) - float(ref["grads"]["focal"])) <= 1e-4 * abs(float(ref["grads"]["focal"]))
+
+
+def test_c4_shape_properties():
+    """BASELINE configs[3] shape (720 x 1280 frames; 24 of the 150 frames to bound the test):
+    finite loss, proper rotations, and pair locality against a 3-frame slice."""
+    from flowmap_b200.overfit import FusedOverfitter, OverfitCfg
+    from flowmap_b200.types import Batch, Flows
+    f, h, w = 24, 720, 1280
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    depth = 0.1 + 0.05 * torch.rand(f, h, w, device="cuda", generator=gen)
+    wparam = 0.01 * torch.randn(f - 1, h, w, device="cuda", generator=gen)
+    mk = lambda *s: 0.01 * torch.randn(*s, device="cuda", generator=gen)  # noqa: E731
+    un = lambda *s: torch.rand(*s, device="cuda", generator=gen)  # noqa: E731
+    flows = Flows(mk(1, f - 1, h, w, 2), mk(1, f - 1, h, w, 2), un(1, f - 1, h, w), un(1, f - 1, h, w))
+
+    def run(sl_f, sl_p):
+        nf = sl_f.stop - sl_f.start
+        batch = Batch(torch.zeros(1, 1, 1, 1, 1, device="cuda").expand(1, nf, 3, h, w),
+                      torch.arange(nf, device="cuda")[None], ["s"], ["d"])
+        fl = Flows(*(t[:, sl_p].contiguous() for t in (flows.forward, flows.backward, flows.forward_mask,
+                                                       flows.backward_mask)))
+        o = FusedOverfitter(OverfitCfg(), batch, fl)
+        with torch.no_grad():
+            o.model.backbone.depth.copy_(depth[sl_f])
+            o.model.backbone.weights.copy_(wparam[sl_p])
+        loss, rt = o.training_step(update=False)
+        den = float(fl.forward_mask.double().sum() + fl.backward_mask.double().sum())
+        return float(loss), rt.clone(), o.gradients()["depth"].double() * den, o.gradients()["weights"].double() * den
+
+    loss, rt, gd, gw = run(slice(0, f), slice(0, f - 1))
+    assert np.isfinite(loss)
+    r = rt[0, :, :, :3].double().cpu()
+    assert max_abs(r @ r.transpose(-1, -2), torch.eye(3, dtype=torch.float64).expand_as(r)) < 1e-5
+    s0 = 10
+    _, rt2, gd2, gw2 = run(slice(s0, s0 + 3), slice(s0, s0 + 2))
+    assert max_abs(rt2.cpu(), rt[:, s0:s0 + 2].cpu()) <= 1e-6
+    assert rel_l2(gd2[1].cpu(), gd[s0 + 1].cpu()) <= 1e-4
+    assert rel_l2(gw2.cpu(), gw[s0:s0 + 2].cpu()) <= 1e-4
