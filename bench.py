@@ -423,8 +423,14 @@ def run_gpu(args):
     path_ms = t_fwd + t_flow + t_bwd
     path_gbs = algorithmic_bytes(F_, H_, W_) / (path_ms * 1e-3) / 1e9
     dom_gbs = ops_bytes[dom] / (times[dom] * 1e-3) / 1e9
+    # DRAM bytes per launch from the committed ncu --set full captures (dram__bytes_read.sum +
+    # dram__bytes_write.sum; profiles/r1_v2_ncu_summary.txt, r1_v3_ncu_summary.txt)
+    ncu_traffic = {"procrustes_fwd(k_moments)": 555.9e6, "flow_loss_fwd_bwd(k_flow_lean)": 1118.2e6,
+                   "procrustes_bwd(k_distribute)": 939.1e6}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(dom_gbs, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(dom_gbs / peak, 4), "traffic": None,
+                "unit": "GB/s", "frac": round(dom_gbs / peak, 4), "traffic": ncu_traffic[dom],
+                "algorithmic_bytes": ops_bytes[dom],
+                "traffic_source": "ncu --set full capture of this kernel at this shape (profiles/)",
                 "peak_source": peak_src,
                 "path": {"what": "unproject->Procrustes->reproject->loss+grad (3 ops, summed)",
                          "algorithmic_bytes": algorithmic_bytes(F_, H_, W_),
