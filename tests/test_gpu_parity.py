@@ -541,14 +541,28 @@ def test_c2_shape_full_step_vs_oracle():
     wparam = 0.01 * torch.randn(f - 1, h, w, generator=gen)
     trk = O.synthetic_tracks(f, n_points=400, seed=3)
     torch.set_num_threads(min(16, torch.get_num_threads()))
-    st = O.OverfitOracle(O.OverfitConfig(intrinsics="regressed", use_tracking=True,
-                                         tracking_enable_after=0), f, h, w, dtype=torch.float64)
-    with torch.no_grad():
-        st.depth.copy_(depth.double())
-        st.weights.copy_(wparam.double())
-    fl64 = O.Flows(*(t.double() for t in (fl.forward, fl.backward, fl.forward_mask, fl.backward_mask)))
-    trk64 = [O.Tracks(t.xy.double(), t.visibility, t.start_frame) for t in trk]
-    ref = st.training_step(fl64, trk64)
+
+    def oracle_step(dtype):
+        st = O.OverfitOracle(O.OverfitConfig(intrinsics="regressed", use_tracking=True,
+                                             tracking_enable_after=0), f, h, w, dtype=dtype)
+        with torch.no_grad():
+            st.depth.copy_(depth.to(dtype))
+            st.weights.copy_(wparam.to(dtype))
+        flows = O.Flows(*(t.to(dtype) for t in (fl.forward, fl.backward, fl.forward_mask, fl.backward_mask)))
+        return st.training_step(flows, [O.Tracks(t.xy.to(dtype), t.visibility, t.start_frame) for t in trk])
+
+    def errors(loss, ext, gd, gw, gf, ref):
+        return dict(loss=abs(float(loss) - ref["loss"]) / abs(ref["loss"]),
+                    pose=max_abs(ext.double(), ref["extrinsics"]),
+                    depth=rel_l2(gd.double(), ref["grads"]["depth"]),
+                    weights=rel_l2(gw.double(), ref["grads"]["weights"]),
+                    focal=abs(float(gf) - float(ref["grads"]["focal"])) / abs(float(ref["grads"]["focal"])))
+
+    # The reference's own float32 run is 1.9e-4 / 2.8e-4 / 2.3e-4 (depth / weights / focal
+    # gradients) away from float64 at this shape: the tolerance is max(1e-4, that noise).
+    ref, ref32 = oracle_step(torch.float64), oracle_step(torch.float32)
+    noise = errors(ref32["loss"], ref32["extrinsics"], ref32["grads"]["depth"], ref32["grads"]["weights"],
+                   ref32["grads"]["focal"], ref)
     batch = Batch(torch.zeros(1, 1, 1, 1, 1).expand(1, f, 3, h, w), torch.arange(f)[None], ["s"], ["d"])
     o = FusedOverfitter(OverfitCfg(use_tracking=True, tracking_enable_after=0), batch,
                         Flows(fl.forward, fl.backward, fl.forward_mask, fl.backward_mask),
@@ -558,14 +572,11 @@ def test_c2_shape_full_step_vs_oracle():
         o.model.backbone.weights.copy_(wparam)
     loss, _ = o.training_step(update=False)
     gr = o.gradients()
-    errs = dict(loss=abs(float(loss) - ref["loss"]) / abs(ref["loss"]),
-                pose=max_abs(o.extrinsics().cpu(), ref["extrinsics"]),
-                depth=rel_l2(gr["depth"].cpu(), ref["grads"]["depth"]),
-                weights=rel_l2(gr["weights"].cpu(), ref["grads"]["weights"]),
-                focal=abs(float(gr["focal"]) - float(ref["grads"]["focal"])) / abs(float(ref["grads"]["focal"])))
-    print("C2 errors vs float64 oracle:", errs)
+    errs = errors(loss, o.extrinsics().cpu(), gr["depth"].cpu(), gr["weights"].cpu(), gr["focal"], ref)
+    print("C2 errors vs float64 oracle:", errs, "reference float32 noise:", noise)
     assert errs["loss"] <= 1e-4 and errs["pose"] <= 2e-5, errs
-    assert errs["depth"] <= 1e-4 and errs["weights"] <= 1e-4 and errs["focal"] <= 1e-4, errs
+    for key in ("depth", "weights", "focal"):
+        assert errs[key] <= max(1e-4, noise[key]), (key, errs, noise)
 
 
 def test_c4_shape_properties():

@@ -130,6 +130,20 @@ template <int MODE> float run(float* buf, int H, int W, int J, int frames) {
   float ms; cudaEventElapsedTime(&ms, a, b); return ms;
 }
 
+// SM-count sweep: one 1024-thread CTA per SM (dynamic shared memory forces exclusivity), S CTAs.
+// Tells whether the RED floor is on the SM side (time ~ 1/S) or in the L2 (time flat until S is small).
+template <int MODE> float run_sms(float* buf, int H, int W, int J, int frames, int sms) {
+  cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  dim3 grid(sms, 1);
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  k<MODE><<<grid, 1024, 200 * 1024>>>(buf, H, W, J, frames);
+  cudaDeviceSynchronize();
+  cudaEventRecord(a);
+  k<MODE><<<grid, 1024, 200 * 1024>>>(buf, H, W, J, frames);
+  cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b); return ms;
+}
+
 int main() {
   const int H = 360, W = 640, frames = 149, J = 12;
   float* buf; cudaMalloc(&buf, (size_t)frames * H * W * 4); cudaMemset(buf, 0, (size_t)frames * H * W * 4);
@@ -140,6 +154,10 @@ int main() {
   const char* n2[] = {"2D patch: 4 scalar reds", "2D patch: v4 padded", "2D patch: smem window + v4 flush"};
   float m2[3] = {run2d<0>(buf, H, W, J, frames), run2d<1>(buf, H, W, J, frames), run2d<2>(buf, H, W, J, frames)};
   for (int i = 0; i < 3; ++i) printf("%-32s %8.3f ms  %7.2f Gpx/s\n", n2[i], m2[i], px / m2[i] / 1e6);
+  const int sweep[] = {148, 111, 74, 56, 37, 18};
+  for (int sms : sweep)
+    printf("SMs %3d: scalar jittered %8.3f ms   v4 padded %8.3f ms   aligned v4 %8.3f ms\n", sms,
+           run_sms<0>(buf, H, W, J, frames, sms), run_sms<2>(buf, H, W, J, frames, sms), run_sms<4>(buf, H, W, J, frames, sms));
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));
   return 0;
