@@ -53,6 +53,9 @@ SIGNATURES = {
                                      c_int, c_int, c_int, c_int, _P]),
     "fm_softmin_focal": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "fm_softmin_focal_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P]),
+    "fm_consistency_mask": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "fm_resize_bilinear": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "fm_world_points": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "fm_adam_step": (c_int, [_P, _P, _P, _P, c_size_t, c_double, c_double, c_double, c_double,
                              c_int, _P]),
 }

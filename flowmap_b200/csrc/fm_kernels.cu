@@ -23,15 +23,14 @@
 #include <stdlib.h>
 
 #include "../../include/flowmap_b200.h"
+#include "fm_host.h"
 #include "fm_pixel.cuh"
 
+namespace fm_host {
 namespace {
-
-using namespace fm;
-
 thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;  // kernels launched by this library (bench evidence only)
-
+}  // namespace
 int fail(const char* what, cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
   return 1;
@@ -40,12 +39,17 @@ int fail_msg(const char* what) {
   snprintf(g_err, sizeof(g_err), "%s", what);
   return 2;
 }
-#define FM_CHECK_LAUNCH(name)                          \
-  do {                                                 \
-    cudaError_t e_ = cudaGetLastError();               \
-    if (e_ != cudaSuccess) return fail(name, e_);      \
-    __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); \
-  } while (0)
+void count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+const char* last_error() { return g_err; }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+}  // namespace fm_host
+
+namespace {
+
+using namespace fm;
+
+using fm_host::fail;
+using fm_host::fail_msg;
 
 constexpr int kThreads = 256;
 constexpr int kFlowAcc = 40;  // per-frame accumulator slots of k_flow
@@ -941,14 +945,12 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
 //
 // The loss is sum / count with a count that depends on the PREDICTED positions, so the
 // gradient scale is only known after a full pass.  Everything is therefore accumulated
-// unscaled in ONE sweep over the (source, target, point) triples per direction and scaled at
-// the end:
+// unscaled in ONE sweep over the (source, target, point) triples and scaled at the end:
 //   k_track_src     block = (segment, source row, point chunk): bilinear-sample xyz at the track
-//                   location, lift to world space (stored), loop over the segment's target rows:
+//                   location, lift to world space, loop over the segment's target rows:
 //                   loss sum + valid count, the unscaled camera-space adjoint of the sampled
-//                   point (stored per sample), source-frame K / pose-twist sums.
-//   k_track_tgt     block = (segment, target row, point chunk), loop over source rows (world
-//                   points from scratch): target-frame pose-twist and K sums.
+//                   point (stored per sample), source-frame K / pose-twist sums in registers,
+//                   target-frame K / pose-twist sums by a 12-shuffle warp reduction per row.
 //   k_track_apply   (backward) per sample: scale * adjoint -> bilinear scatter into the depth
 //                   gradient (4 REDs).
 //   k_track_finalize  scale the per-frame sums, expand twists to ambient 3x4 gradients.
@@ -1032,11 +1034,47 @@ __device__ __forceinline__ bool track_term_lean(const float* rec, const float* X
   return true;
 }
 
+// Warp sum of 10 per-lane values by recursive halving: 12 shuffles instead of 50.  Afterwards
+// lane l holds the total of value track_slot(l) (lanes 2k and 2k+1 hold the same total).
+struct TrackSlot { int slot; bool owner; };
+__device__ __forceinline__ TrackSlot track_slot(int lane) {
+  const int i4 = (lane >> 1) & 1;
+  const int i3 = ((lane >> 2) & 1) * 2 + i4;
+  const int i2 = ((lane >> 3) & 1) * 3 + i3;
+  TrackSlot t;
+  t.slot = ((lane >> 4) & 1) * 5 + i2;
+  t.owner = i3 < 3 && i2 < 5 && (lane & 1) == 0;
+  return t;
+}
+template <int N, int OFF>
+__device__ __forceinline__ void halve_exchange(float* v, bool upper) {
+  constexpr int HALF = (N + 1) / 2;
+#pragma unroll
+  for (int j = 0; j < HALF; ++j) {
+    const float hi = (j + HALF < N) ? v[j + HALF] : 0.f;
+    const float send = upper ? v[j] : hi;
+    const float keep = upper ? hi : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+__device__ __forceinline__ float warp_sum10(float* v, int lane) {
+  halve_exchange<10, 16>(v, lane & 16);
+  halve_exchange<5, 8>(v, lane & 8);
+  halve_exchange<3, 4>(v, lane & 4);
+  halve_exchange<2, 2>(v, lane & 2);
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// One sweep over the (source row, target row, point) triples.  A block owns (segment, source
+// row, 256 points): every thread keeps the source-side sums of its point in registers; the
+// target-side sums (pose twist and K of the TARGET frame) of one loop iteration belong to one
+// frame for the whole block, so each warp reduces them with warp_sum10 into its own
+// [target row][10] slice of shared memory, folded into the per-frame accumulators at the end.
 __global__ void __launch_bounds__(kThreads)
 k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const float* __restrict__ ext,
             const int* __restrict__ seg, const float* __restrict__ txy,
             const unsigned char* __restrict__ tvis, int mapping, float delta, double* __restrict__ sums,
-            float* __restrict__ xw, unsigned char* __restrict__ flag, float* __restrict__ dq_out,
+            unsigned char* __restrict__ flag, float* __restrict__ dq_out,
             double* __restrict__ trackacc, int H, int W) {
   extern __shared__ float sm[];
   __shared__ double red[kTrackAcc * (kThreads / 32)];
@@ -1044,6 +1082,7 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
   const int row = blockIdx.y;
   if (row >= si.rows) return;
   load_segment_frames(sm, ext, k4, si);
+  float* s_tgt = sm + (size_t)gridDim.y * kTrackRec;  // [warp][target row][kTrackAcc]
   __shared__ int s_list[kThreads];
   __shared__ int s_wbase[kThreads / 32];
   const GridDims grid = make_grid(H, W);
@@ -1052,6 +1091,7 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
   const float* D = depth + (size_t)frame * H * W;
   const float* rs = sm + row * kTrackRec;
   const Cam ks = sm_cam(rs);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float acc[kTrackAcc], lc[2] = {0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < kTrackAcc; ++i) acc[i] = 0.f;
@@ -1065,114 +1105,86 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
     flag[sidx] = ok_own ? 1 : 0;
   }
   const int count = block_compact(ok_own, p_own, s_list, s_wbase);
-  if ((int)threadIdx.x < count) {
-    const int p = s_list[threadIdx.x];
+  const bool live = (int)threadIdx.x < count;
+  if (warp * 32 < count) {  // warp-uniform: the shuffles below need all 32 lanes
+    const int p = live ? s_list[threadIdx.x] : 0;
     const size_t sidx = (size_t)si.sample_start + (size_t)row * si.n + p;
-    const float2 sxy = __ldg(reinterpret_cast<const float2*>(txy) + sidx);
-    const Taps t = bilinear_taps(sxy.x, sxy.y, grid);
-    float q[3];
-    sample_surface(t, grid, ks, [D, W](int yy, int xx) { return __ldg(D + yy * W + xx); }, q[0], q[1], q[2]);
-    float Xw[3];
+    float q[3] = {0.f, 0.f, 0.f}, Xw[3] = {0.f, 0.f, 0.f};
+    if (live) {
+      const float2 sxy = __ldg(reinterpret_cast<const float2*>(txy) + sidx);
+      const Taps t = bilinear_taps(sxy.x, sxy.y, grid);
+      sample_surface(t, grid, ks, [D, W](int yy, int xx) { return __ldg(D + yy * W + xx); }, q[0], q[1], q[2]);
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-      Xw[i] = fm_fma(rs[i * 3 + 0], q[0], fm_fma(rs[i * 3 + 1], q[1], fm_fma(rs[i * 3 + 2], q[2], rs[9 + i])));
-    xw[sidx * 3 + 0] = Xw[0]; xw[sidx * 3 + 1] = Xw[1]; xw[sidx * 3 + 2] = Xw[2];
+      for (int i = 0; i < 3; ++i)
+        Xw[i] = fm_fma(rs[i * 3 + 0], q[0], fm_fma(rs[i * 3 + 1], q[1], fm_fma(rs[i * 3 + 2], q[2], rs[9 + i])));
+    }
     float G[3] = {0.f, 0.f, 0.f};
+    const TrackSlot slot = track_slot(lane);
+    float* tgt = s_tgt + (size_t)warp * si.rows * kTrackAcc;
     // the next target row's visibility / position is fetched while the current one is processed
     size_t tidx_n = (size_t)si.sample_start + p;
-    unsigned char vis_n = tvis[tidx_n];
-    float2 gxy_n = __ldg(reinterpret_cast<const float2*>(txy) + tidx_n);
+    unsigned char vis_n = live ? tvis[tidx_n] : 0;
+    float2 gxy_n = live ? __ldg(reinterpret_cast<const float2*>(txy) + tidx_n) : make_float2(0.f, 0.f);
     for (int ft = 0; ft < si.rows; ++ft) {
       const unsigned char vis_t = vis_n;
       const float2 gxy = gxy_n;
-      if (ft + 1 < si.rows) {
+      if (ft + 1 < si.rows && live) {
         tidx_n += si.n;
         vis_n = tvis[tidx_n];
         gxy_n = __ldg(reinterpret_cast<const float2*>(txy) + tidx_n);
       }
-      if (!vis_t) continue;
-      LeanTerm lt;
-      float g[3];
-      if (!track_term_lean(sm + ft * kTrackRec, Xw, gxy.x, gxy.y, rc, lt, g)) continue;
-      lc[0] += lt.loss;
-      lc[1] += 1.f;
-      G[0] += g[0]; G[1] += g[1]; G[2] += g[2];
+      float c[kTrackAcc];
+#pragma unroll
+      for (int i = 0; i < kTrackAcc; ++i) c[i] = 0.f;
+      bool ok = false;
+      if (vis_t) {
+        const float* rec = sm + ft * kTrackRec;
+        LeanTerm lt;
+        float g[3];
+        if (track_term_lean(rec, Xw, gxy.x, gxy.y, rc, lt, g)) {
+          ok = true;
+          lc[0] += lt.loss;
+          lc[1] += 1.f;
+          G[0] += g[0]; G[1] += g[1]; G[2] += g[2];
+          // target-frame K gradient: duv = d (P_z + eps) / f and uv - c = f P / (P_z + eps)
+          const float ex = lt.d0 * rec[19], ey = lt.d1 * rec[20];
+          c[0] = ex * lt.P0; c[1] = ey * lt.P1; c[2] = ex * lt.P2; c[3] = ey * lt.P2;
+          const float d0 = Xw[0] - rec[9], d1 = Xw[1] - rec[10], d2 = Xw[2] - rec[11];
+          c[4] = d2 * g[1] - d1 * g[2];
+          c[5] = d0 * g[2] - d2 * g[0];
+          c[6] = d1 * g[0] - d0 * g[1];
+          c[7] = -g[0]; c[8] = -g[1]; c[9] = -g[2];
+        }
+      }
+      float total = 0.f;
+      if (__ballot_sync(0xffffffffu, ok)) total = warp_sum10(c, lane);
+      if (slot.owner) tgt[ft * kTrackAcc + slot.slot] = total;
     }
-    // camera-space adjoint of the sampled point (unscaled), source K / twist sums
-    const float dq0 = fm_fma(rs[0], G[0], fm_fma(rs[3], G[1], rs[6] * G[2]));
-    const float dq1 = fm_fma(rs[1], G[0], fm_fma(rs[4], G[1], rs[7] * G[2]));
-    const float dq2 = fm_fma(rs[2], G[0], fm_fma(rs[5], G[1], rs[8] * G[2]));
-    dq_out[sidx * 3 + 0] = dq0; dq_out[sidx * 3 + 1] = dq1; dq_out[sidx * 3 + 2] = dq2;
-    const float e0 = dq0 * ks.ifx, e1 = dq1 * ks.ify;
-    acc[0] = -e0 * q[0]; acc[1] = -e1 * q[1]; acc[2] = -e0 * q[2]; acc[3] = -e1 * q[2];
-    const float c0 = Xw[0] - rs[9], c1 = Xw[1] - rs[10], c2 = Xw[2] - rs[11];
-    acc[4] = c1 * G[2] - c2 * G[1];
-    acc[5] = c2 * G[0] - c0 * G[2];
-    acc[6] = c0 * G[1] - c1 * G[0];
-    acc[7] = G[0]; acc[8] = G[1]; acc[9] = G[2];
+    if (live) {
+      // camera-space adjoint of the sampled point (unscaled), source K / twist sums
+      const float dq0 = fm_fma(rs[0], G[0], fm_fma(rs[3], G[1], rs[6] * G[2]));
+      const float dq1 = fm_fma(rs[1], G[0], fm_fma(rs[4], G[1], rs[7] * G[2]));
+      const float dq2 = fm_fma(rs[2], G[0], fm_fma(rs[5], G[1], rs[8] * G[2]));
+      dq_out[sidx * 3 + 0] = dq0; dq_out[sidx * 3 + 1] = dq1; dq_out[sidx * 3 + 2] = dq2;
+      const float e0 = dq0 * ks.ifx, e1 = dq1 * ks.ify;
+      acc[0] = -e0 * q[0]; acc[1] = -e1 * q[1]; acc[2] = -e0 * q[2]; acc[3] = -e1 * q[2];
+      const float c0 = Xw[0] - rs[9], c1 = Xw[1] - rs[10], c2 = Xw[2] - rs[11];
+      acc[4] = c1 * G[2] - c2 * G[1];
+      acc[5] = c2 * G[0] - c0 * G[2];
+      acc[6] = c0 * G[1] - c1 * G[0];
+      acc[7] = G[0]; acc[8] = G[1]; acc[9] = G[2];
+    }
   }
   block_accumulate<2>(lc, sums, red);
   block_accumulate<kTrackAcc>(acc, trackacc + (size_t)frame * kTrackAcc, red);
-}
-
-__global__ void __launch_bounds__(kThreads)
-k_track_tgt(const float* __restrict__ k4, const float* __restrict__ ext, const int* __restrict__ seg,
-            const float* __restrict__ txy, const unsigned char* __restrict__ tvis, int mapping, float delta,
-            const float* __restrict__ xw, const unsigned char* __restrict__ flag,
-            double* __restrict__ trackacc, int H, int W) {
-  extern __shared__ float sm[];
-  __shared__ double red[kTrackAcc * (kThreads / 32)];
-  const SegInfo si = load_seg(seg, blockIdx.z);
-  const int ft = blockIdx.y;
-  if (ft >= si.rows) return;
-  load_segment_frames(sm, ext, k4, si);
-  __shared__ int s_list[kThreads];
-  __shared__ int s_wbase[kThreads / 32];
-  const RobustCfg rc = make_robust(mapping, delta, H, W);
-  const float* rec = sm + ft * kTrackRec;
-  float acc[kTrackAcc];
-#pragma unroll
-  for (int i = 0; i < kTrackAcc; ++i) acc[i] = 0.f;
-  const int p_own = blockIdx.x * kThreads + threadIdx.x;
-  const bool ok_own = p_own < si.n && tvis[(size_t)si.sample_start + (size_t)ft * si.n + p_own];
-  const int count = block_compact(ok_own, p_own, s_list, s_wbase);
-  if ((int)threadIdx.x < count) {
-    const int p = s_list[threadIdx.x];
-    const size_t tidx = (size_t)si.sample_start + (size_t)ft * si.n + p;
-    const float2 gxy = __ldg(reinterpret_cast<const float2*>(txy) + tidx);
-    const Cam kt = sm_cam(rec);
-    // the next row's world point is fetched while the current one is processed
-    size_t sidx_n = (size_t)si.sample_start + p;
-    unsigned char fl_n = flag[sidx_n];
-    float xn0 = xw[sidx_n * 3 + 0], xn1 = xw[sidx_n * 3 + 1], xn2 = xw[sidx_n * 3 + 2];
-    for (int fs = 0; fs < si.rows; ++fs) {
-      const unsigned char fl = fl_n;
-      const float Xw[3] = {xn0, xn1, xn2};
-      if (fs + 1 < si.rows) {
-        sidx_n += si.n;
-        fl_n = flag[sidx_n];
-        xn0 = xw[sidx_n * 3 + 0]; xn1 = xw[sidx_n * 3 + 1]; xn2 = xw[sidx_n * 3 + 2];
-      }
-      if (!fl) continue;
-      LeanTerm lt;
-      float g[3];
-      if (!track_term_lean(rec, Xw, gxy.x, gxy.y, rc, lt, g)) continue;
-      // K gradient of the projection: du0 = fx duvx = d0 / inv  =>  duvx = d0 (P_z + eps) / fx
-      const float den = lt.P2 + kProjEps, inv = fm_rcp(den);
-      const float u0 = lt.P0 * inv, u1 = lt.P1 * inv, u2 = lt.P2 * inv;
-      const float duvx = lt.d0 * den * kt.ifx, duvy = lt.d1 * den * kt.ify;
-      acc[0] = fm_fma(duvx, u0, acc[0]);
-      acc[1] = fm_fma(duvy, u1, acc[1]);
-      acc[2] = fm_fma(duvx, u2, acc[2]);
-      acc[3] = fm_fma(duvy, u2, acc[3]);
-      const float d0 = Xw[0] - rec[9], d1 = Xw[1] - rec[10], d2 = Xw[2] - rec[11];
-      acc[4] -= d1 * g[2] - d2 * g[1];
-      acc[5] -= d2 * g[0] - d0 * g[2];
-      acc[6] -= d0 * g[1] - d1 * g[0];
-      acc[7] -= g[0]; acc[8] -= g[1]; acc[9] -= g[2];
-    }
+  // fold the warps' target-side slices into the per-frame accumulators (block_accumulate ended
+  // with a barrier, so every slice is complete)
+  const int live_warps = (count + 31) >> 5;
+  for (int i = threadIdx.x; i < si.rows * kTrackAcc; i += kThreads) {
+    double t = 0.0;
+    for (int w = 0; w < live_warps; ++w) t += (double)s_tgt[(size_t)w * si.rows * kTrackAcc + i];
+    if (t != 0.0) atomicAdd(trackacc + (size_t)si.start_frame * kTrackAcc + i, t);
   }
-  block_accumulate<kTrackAcc>(acc, trackacc + (size_t)(si.start_frame + ft) * kTrackAcc, red);
 }
 
 __device__ __forceinline__ double track_scale(const double* sums, float loss_weight, const float* go) {
@@ -1640,8 +1652,8 @@ int launch_flow(const float* depth, const float* k4, const float* rt, const floa
 extern "C" {
 
 int fm_version(void) { return 101; }
-unsigned long long fm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
-const char* fm_last_error(void) { return g_err; }
+unsigned long long fm_launch_count(void) { return fm_host::launches(); }
+const char* fm_last_error(void) { return fm_host::last_error(); }
 
 size_t fm_workspace_bytes(int B, int F, int H, int W) {
   (void)H; (void)W;
@@ -1860,19 +1872,17 @@ size_t fm_track_workspace_bytes(int F, long long total_samples) {
   size_t off = 0;
   off = align_up(off + 4 * sizeof(double), 256);                          // sums
   off = align_up(off + (size_t)F * kTrackAcc * sizeof(double), 256);      // per-frame accumulators
-  off = align_up(off + (size_t)total_samples * 3 * sizeof(float), 256);   // world points
   off = align_up(off + (size_t)total_samples * 3 * sizeof(float), 256);   // unscaled point adjoints
   off = align_up(off + (size_t)total_samples, 256);                       // source-valid flags
   return off;
 }
 
 namespace {
-struct TrackWs { double* sums; double* acc; float* xw; float* dq; unsigned char* flag; };
+struct TrackWs { double* sums; double* acc; float* dq; unsigned char* flag; };
 TrackWs carve_track(void* base, int F, long long total) {
   char* p = (char*)base; size_t off = 0; TrackWs w;
   w.sums = (double*)(p + off); off = align_up(off + 4 * sizeof(double), 256);
   w.acc = (double*)(p + off); off = align_up(off + (size_t)F * kTrackAcc * sizeof(double), 256);
-  w.xw = (float*)(p + off); off = align_up(off + (size_t)total * 3 * sizeof(float), 256);
   w.dq = (float*)(p + off); off = align_up(off + (size_t)total * 3 * sizeof(float), 256);
   w.flag = (unsigned char*)(p + off);
   return w;
@@ -1889,16 +1899,18 @@ int fm_track_loss_fwd(const float* depth, const float* k4, const float* extrinsi
   if (mapping < 0 || mapping > 2) return fail_msg("fm_track_loss_fwd: unknown mapping");
   cudaStream_t s = (cudaStream_t)stream;
   TrackWs w = carve_track(ws, F, total_samples);
-  cudaError_t e = cudaMemsetAsync(w.sums, 0, (char*)w.xw - (char*)w.sums, s);  // sums + accumulators
+  cudaError_t e = cudaMemsetAsync(w.sums, 0, (char*)w.dq - (char*)w.sums, s);  // sums + accumulators
   if (e != cudaSuccess) return fail("fm_track_loss_fwd: memset", e);
   dim3 grid((max_points + kThreads - 1) / kThreads, max_rows, num_segments);
-  const size_t smem = (size_t)max_rows * kTrackRec * sizeof(float);
+  const size_t smem = (size_t)max_rows * (kTrackRec + (kThreads / 32) * kTrackAcc) * sizeof(float);
+  if (smem > 200 * 1024) return fail_msg("fm_track_loss_fwd: segment too long for shared memory");
+  if (smem > 48 * 1024) {
+    cudaError_t ea = cudaFuncSetAttribute(k_track_src, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ea != cudaSuccess) return fail("fm_track_loss_fwd: shared memory", ea);
+  }
   k_track_src<<<grid, kThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis, mapping,
-                                          delta, w.sums, w.xw, w.flag, w.dq, w.acc, H, W);
+                                          delta, w.sums, w.flag, w.dq, w.acc, H, W);
   FM_CHECK_LAUNCH("fm_track_loss_fwd: k_track_src");
-  k_track_tgt<<<grid, kThreads, smem, s>>>(k4, extrinsics, segments, track_xy, track_vis, mapping, delta,
-                                          w.xw, w.flag, w.acc, H, W);
-  FM_CHECK_LAUNCH("fm_track_loss_fwd: k_track_tgt");
   k_track_loss<<<1, 1, 0, s>>>(w.sums, loss_weight, loss);
   FM_CHECK_LAUNCH("fm_track_loss_fwd: k_track_loss");
   return 0;

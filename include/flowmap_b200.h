@@ -243,6 +243,26 @@ typedef struct {
 } fm_overfit_step_args;
 int fm_overfit_step(const fm_overfit_step_args* args, void* stream);
 
+/* ---- stages either side of the hot path ---------------------------- */
+
+/* flow/flow_predictor.py:60-82 compute_consistency_mask: videos (B,F,3,H,W) planar frames, flow
+ * (B,F-1,H,W,2) in normalised units -> mask (B,F-1,H,W) = (1 - max_c |I_src - bilinear_zero_pad(
+ * I_tgt, xy + flow)|)^8.  reverse = 0: src frame i, tgt frame i+1 (forward flow); reverse = 1:
+ * src i+1, tgt i (the backward flow as stored in Flows.backward, :92-99). */
+int fm_consistency_mask(const float* videos, const float* flow, float* mask, int B, int F, int H, int W,
+                        int reverse, void* stream);
+
+/* flow/flow_predictor.py:40-58 rescale_flow / rescale_mask and misc/cropping.py:19-27
+ * resize_batch: F.interpolate(mode="bilinear", align_corners=False) of channels-last images
+ * in (items,Hin,Win,C) -> out (items,Hout,Wout,C), C in {1,2,3}. */
+int fm_resize_bilinear(const float* in, float* out, int items, int Hin, int Win, int Hout, int Wout,
+                       int channels, void* stream);
+
+/* export/colmap.py:84-101 (the point cloud of export_to_colmap): depth (F,H,W), k4 (F,4),
+ * camera-to-world extrinsics (F,4,4) -> xyz (F*H*W,3), frames concatenated, row-major pixels. */
+int fm_world_points(const float* depth, const float* k4, const float* extrinsics, float* xyz, int F, int H,
+                    int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

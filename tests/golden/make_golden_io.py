@@ -96,7 +96,22 @@ def main():
         xyz = homogenize_points(unproject(xy, d, kk))
         xyz = einsum(e, xyz, "i j, ... j -> ... i")[..., :3]
         points.append(rearrange(xyz, "h w xyz -> (h w) xyz").numpy())
-    np.savez_compressed(OUT / "io_export.npz", extrinsics=ext.numpy(), intrinsics=k.numpy(),
+    # checkpoint layout: parameter / buffer names and shapes of the reference Model (the Lightning
+    # wrapper prefixes them with "model.", model_wrapper_overfit.py:40-49)
+    from flowmap.model.backbone.backbone_explicit_depth import BackboneExplicitDepthCfg
+    from flowmap.model.extrinsics.extrinsics_procrustes import ExtrinsicsProcrustesCfg
+    from flowmap.model.intrinsics.intrinsics_regressed import IntrinsicsRegressedCfg
+    from flowmap.model.intrinsics.intrinsics_softmin import IntrinsicsSoftminCfg, RegressionCfg
+    from flowmap.model.model import Model, ModelCfg
+    state = {}
+    for tag, icfg in (("regressed", IntrinsicsRegressedCfg("regressed", 0.85)),
+                      ("softmin", IntrinsicsSoftminCfg("softmin", 64, 0.5, 2.0, 60, RegressionCfg(1000, 100)))):
+        model = Model(ModelCfg(BackboneExplicitDepthCfg("explicit_depth", 0.1, 100.0), icfg,
+                               ExtrinsicsProcrustesCfg("procrustes", None, False), True), 5, (12, 16))
+        sd = model.state_dict()
+        state[f"state_{tag}_names"] = np.array(list(sd.keys()))
+        state[f"state_{tag}_shapes"] = np.array([",".join(map(str, v.shape)) for v in sd.values()])
+    np.savez_compressed(OUT / "io_export.npz", **state, extrinsics=ext.numpy(), intrinsics=k.numpy(),
                         depths=depths.numpy(), cropped=cropped.numpy(), cameras_bin=cams, images_bin=imgs,
                         points=np.concatenate(points), read_extrinsics=back_ext.numpy(),
                         read_intrinsics=back_k.numpy(), names=np.array(names), read_names=np.array(back_names))
