@@ -63,7 +63,8 @@ k_consistency_mask(const float* __restrict__ videos, const float* __restrict__ f
 // source index = (dst + .5) * (in / out) - .5, clamped below at 0 (flow_predictor.py:40-58).
 struct AxisTap { int i0, i1; float t; };
 __device__ __forceinline__ AxisTap axis_tap(int dst, float scale, int n_in) {
-  float s = scale * ((float)dst + 0.5f) - 0.5f;
+  // separate multiply / subtract (no FMA contraction): the same roundings as ATen's CPU kernel
+  float s = __fsub_rn(__fmul_rn(scale, (float)dst + 0.5f), 0.5f);
   s = s < 0.f ? 0.f : s;
   AxisTap a;
   a.i0 = min((int)s, n_in - 1);

@@ -59,6 +59,8 @@ def write_colmap_model(path: Path, extrinsics: Tensor, intrinsics: Tensor, image
                        image_shape) -> None:
     """export/colmap.py:171-213: cameras.bin + images.bin (no points3D, as the reference)."""
     h, w = image_shape
+    # on the host, so that the files do not depend on which device held the tensors
+    extrinsics, intrinsics = extrinsics.detach().cpu(), intrinsics.detach().cpu()
     cams = struct.pack("<Q", len(intrinsics))
     for index, k in enumerate(intrinsics):
         k = k.detach().clone()
@@ -68,7 +70,7 @@ def write_colmap_model(path: Path, extrinsics: Tensor, intrinsics: Tensor, image
         cams += struct.pack("<dddd", float(k[0, 0]), float(k[1, 1]), float(k[0, 2]), float(k[1, 2]))
     imgs = struct.pack("<Q", len(extrinsics))
     for index, (c2w, name) in enumerate(zip(extrinsics, image_names)):
-        w2c = c2w.inverse().detach().cpu().numpy()
+        w2c = c2w.inverse().numpy()
         imgs += struct.pack("<i", index + 1)
         imgs += struct.pack("<dddd", *_rotation_to_qvec(w2c[:3, :3]).tolist())
         imgs += struct.pack("<ddd", *w2c[:3, 3].tolist())
