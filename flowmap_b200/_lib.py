@@ -45,6 +45,14 @@ SIGNATURES = {
     "fm_track_loss_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, ctypes.c_longlong,
                                   c_int, c_float, c_float, _P, _P, _P, _P, _P, c_int, c_int, c_int,
                                   _P]),
+    "fm_track_reduce_bytes": (c_size_t, [c_int]),
+    "fm_track_loss_fwd_sharded": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, ctypes.c_longlong,
+                                          c_int, c_float, c_float, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                          c_int, _P]),
+    "fm_track_loss_value": (c_int, [_P, c_float, _P, _P]),
+    "fm_track_loss_bwd_sharded": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, ctypes.c_longlong,
+                                          c_int, c_float, c_float, _P, _P, _P, _P, _P, c_int, c_int, c_int,
+                                          c_int, c_int, c_int, _P]),
     "fm_random_subset": (c_int, [ctypes.c_ulonglong, ctypes.c_longlong, c_int, _P, _P]),
     "fm_softmin_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fm_softmin_sweep_fwd": (c_int, [_P, _P, c_float, _P, _P, c_int, _P, c_int, _P, _P, _P, c_int, c_int,
@@ -83,7 +91,8 @@ class OverfitStepArgs(ctypes.Structure):
                 ("rt", _P), ("loss", _P),
                 ("extrinsics", _P), ("g_extrinsics", _P), ("g_rt", _P), ("track_g_k4", _P),
                 ("track_loss", _P),
-                ("ws", _P), ("track_ws", _P), ("focal_step", c_int), ("defer_adam", c_int)]
+                ("ws", _P), ("track_ws", _P), ("focal_step", c_int), ("defer_adam", c_int),
+                ("phase", c_int)]
 
 
 SIGNATURES["fm_overfit_step"] = (c_int, [ctypes.POINTER(OverfitStepArgs), _P])

@@ -961,6 +961,13 @@ constexpr int kTrackRec = 24;   // per-frame record in shared memory, see load_s
 
 struct SegInfo { int sample_start, rows, n, start_frame; };
 
+// Source-frame sharding (multi-GPU): this call samples depth only at source frames
+// [src_lo, src_hi); depth / g_depth point at frame depth_frame0.  Targets are never restricted.
+struct TrackShard {
+  int depth_frame0, src_lo, src_hi;
+  __device__ __forceinline__ bool owns(int frame) const { return frame >= src_lo && frame < src_hi; }
+};
+
 __device__ __forceinline__ SegInfo load_seg(const int* seg, int s) {
   const int4 v = __ldg(reinterpret_cast<const int4*>(seg) + s);
   SegInfo i; i.sample_start = v.x; i.rows = v.y; i.n = v.z; i.start_frame = v.w;
@@ -1075,12 +1082,12 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
             const int* __restrict__ seg, const float* __restrict__ txy,
             const unsigned char* __restrict__ tvis, int mapping, float delta, double* __restrict__ sums,
             unsigned char* __restrict__ flag, float* __restrict__ dq_out,
-            double* __restrict__ trackacc, int H, int W) {
+            double* __restrict__ trackacc, int H, int W, TrackShard sh) {
   extern __shared__ float sm[];
   __shared__ double red[kTrackAcc * (kThreads / 32)];
   const SegInfo si = load_seg(seg, blockIdx.z);
   const int row = blockIdx.y;
-  if (row >= si.rows) return;
+  if (row >= si.rows || !sh.owns(si.start_frame + row)) return;
   load_segment_frames(sm, ext, k4, si);
   float* s_tgt = sm + (size_t)gridDim.y * kTrackRec;  // [warp][target row][kTrackAcc]
   __shared__ int s_list[kThreads];
@@ -1088,7 +1095,7 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
   const GridDims grid = make_grid(H, W);
   const RobustCfg rc = make_robust(mapping, delta, H, W);
   const int frame = si.start_frame + row;
-  const float* D = depth + (size_t)frame * H * W;
+  const float* D = depth + (size_t)(frame - sh.depth_frame0) * H * W;
   const float* rs = sm + row * kTrackRec;
   const Cam ks = sm_cam(rs);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1202,11 +1209,11 @@ __global__ void __launch_bounds__(kThreads)
 k_track_apply(const float* __restrict__ k4, const int* __restrict__ seg, const float* __restrict__ txy,
               const unsigned char* __restrict__ flag, const float* __restrict__ dq,
               const double* __restrict__ sums, float loss_weight, const float* __restrict__ go,
-              float* __restrict__ g_depth, int H, int W) {
+              float* __restrict__ g_depth, int H, int W, TrackShard sh) {
   const SegInfo si = load_seg(seg, blockIdx.z);
   const int row = blockIdx.y;
   const int p = blockIdx.x * kThreads + threadIdx.x;
-  if (row >= si.rows || p >= si.n) return;
+  if (row >= si.rows || p >= si.n || !sh.owns(si.start_frame + row)) return;
   const size_t sidx = (size_t)si.sample_start + (size_t)row * si.n + p;
   if (!flag[sidx]) return;
   const float scale = (float)track_scale(sums, loss_weight, go);
@@ -1218,7 +1225,7 @@ k_track_apply(const float* __restrict__ k4, const int* __restrict__ seg, const f
   const float dq0 = scale * dq[sidx * 3 + 0], dq1 = scale * dq[sidx * 3 + 1], dq2 = scale * dq[sidx * 3 + 2];
   float rx0, ry0, rx1, ry1;
   tap_rays(t, grid, ks, rx0, ry0, rx1, ry1);
-  float* gd = g_depth + (size_t)frame * H * W;
+  float* gd = g_depth + (size_t)(frame - sh.depth_frame0) * H * W;
   red_add(gd + t.y0 * W + t.x0, t.w00 * (dq0 * rx0 + dq1 * ry0 + dq2));
   red_add(gd + t.y0 * W + t.x1, t.w01 * (dq0 * rx1 + dq1 * ry0 + dq2));
   red_add(gd + t.y1 * W + t.x0, t.w10 * (dq0 * rx0 + dq1 * ry1 + dq2));
@@ -1889,14 +1896,22 @@ TrackWs carve_track(void* base, int F, long long total) {
 }
 }  // namespace
 
-int fm_track_loss_fwd(const float* depth, const float* k4, const float* extrinsics, const int* segments,
-                      int num_segments, int max_rows, int max_points, const float* track_xy,
-                      const unsigned char* track_vis, long long total_samples, int mapping, float delta,
-                      float loss_weight, float* loss, void* ws, int F, int H, int W, void* stream) {
-  if (!depth || !k4 || !extrinsics || !segments || !track_xy || !track_vis || !loss || !ws ||
+size_t fm_track_reduce_bytes(int F) {
+  if (F < 1) return 0;
+  return align_up(4 * sizeof(double), 256) + align_up((size_t)F * kTrackAcc * sizeof(double), 256);
+}
+
+int fm_track_loss_fwd_sharded(const float* depth, const float* k4, const float* extrinsics, const int* segments,
+                              int num_segments, int max_rows, int max_points, const float* track_xy,
+                              const unsigned char* track_vis, long long total_samples, int mapping, float delta,
+                              float loss_weight, float* loss, void* ws, int F, int H, int W, int depth_frame0,
+                              int src_frame_lo, int src_frame_hi, void* stream) {
+  if (!depth || !k4 || !extrinsics || !segments || !track_xy || !track_vis || !ws ||
       num_segments < 1 || max_rows < 1 || max_points < 1 || F < 1)
     return fail_msg("fm_track_loss_fwd: bad arguments");
   if (mapping < 0 || mapping > 2) return fail_msg("fm_track_loss_fwd: unknown mapping");
+  if (depth_frame0 < 0 || src_frame_lo < depth_frame0 || src_frame_hi > F || src_frame_lo > src_frame_hi)
+    return fail_msg("fm_track_loss_fwd: bad source-frame range");
   cudaStream_t s = (cudaStream_t)stream;
   TrackWs w = carve_track(ws, F, total_samples);
   cudaError_t e = cudaMemsetAsync(w.sums, 0, (char*)w.dq - (char*)w.sums, s);  // sums + accumulators
@@ -1908,11 +1923,56 @@ int fm_track_loss_fwd(const float* depth, const float* k4, const float* extrinsi
     cudaError_t ea = cudaFuncSetAttribute(k_track_src, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ea != cudaSuccess) return fail("fm_track_loss_fwd: shared memory", ea);
   }
+  const TrackShard sh = {depth_frame0, src_frame_lo, src_frame_hi};
   k_track_src<<<grid, kThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis, mapping,
-                                          delta, w.sums, w.flag, w.dq, w.acc, H, W);
+                                          delta, w.sums, w.flag, w.dq, w.acc, H, W, sh);
   FM_CHECK_LAUNCH("fm_track_loss_fwd: k_track_src");
-  k_track_loss<<<1, 1, 0, s>>>(w.sums, loss_weight, loss);
-  FM_CHECK_LAUNCH("fm_track_loss_fwd: k_track_loss");
+  if (loss) {
+    k_track_loss<<<1, 1, 0, s>>>(w.sums, loss_weight, loss);
+    FM_CHECK_LAUNCH("fm_track_loss_fwd: k_track_loss");
+  }
+  return 0;
+}
+
+int fm_track_loss_fwd(const float* depth, const float* k4, const float* extrinsics, const int* segments,
+                      int num_segments, int max_rows, int max_points, const float* track_xy,
+                      const unsigned char* track_vis, long long total_samples, int mapping, float delta,
+                      float loss_weight, float* loss, void* ws, int F, int H, int W, void* stream) {
+  if (!loss) return fail_msg("fm_track_loss_fwd: bad arguments");
+  return fm_track_loss_fwd_sharded(depth, k4, extrinsics, segments, num_segments, max_rows, max_points, track_xy,
+                                   track_vis, total_samples, mapping, delta, loss_weight, loss, ws, F, H, W, 0,
+                                   0, F, stream);
+}
+
+int fm_track_loss_value(const void* ws, float loss_weight, float* loss, void* stream) {
+  if (!ws || !loss) return fail_msg("fm_track_loss_value: bad arguments");
+  k_track_loss<<<1, 1, 0, (cudaStream_t)stream>>>((const double*)ws, loss_weight, loss);
+  FM_CHECK_LAUNCH("fm_track_loss_value");
+  return 0;
+}
+
+int fm_track_loss_bwd_sharded(const float* depth, const float* k4, const float* extrinsics, const int* segments,
+                              int num_segments, int max_rows, int max_points, const float* track_xy,
+                              const unsigned char* track_vis, long long total_samples, int mapping, float delta,
+                              float loss_weight, const float* grad_out, float* g_depth, float* g_extrinsics,
+                              float* g_k4, void* ws, int F, int H, int W, int depth_frame0, int src_frame_lo,
+                              int src_frame_hi, void* stream) {
+  (void)depth; (void)track_vis; (void)mapping; (void)delta;
+  if (!k4 || !extrinsics || !segments || !track_xy || !g_depth || !g_extrinsics || !g_k4 || !ws ||
+      num_segments < 1 || max_rows < 1 || max_points < 1 || F < 1)
+    return fail_msg("fm_track_loss_bwd: bad arguments");
+  if (depth_frame0 < 0 || src_frame_lo < depth_frame0 || src_frame_hi > F || src_frame_lo > src_frame_hi)
+    return fail_msg("fm_track_loss_bwd: bad source-frame range");
+  cudaStream_t s = (cudaStream_t)stream;
+  TrackWs w = carve_track(ws, F, total_samples);
+  dim3 grid((max_points + kThreads - 1) / kThreads, max_rows, num_segments);
+  const TrackShard sh = {depth_frame0, src_frame_lo, src_frame_hi};
+  k_track_apply<<<grid, kThreads, 0, s>>>(k4, segments, track_xy, w.flag, w.dq, w.sums, loss_weight, grad_out,
+                                         g_depth, H, W, sh);
+  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_apply");
+  k_track_finalize<<<(F + 63) / 64, 64, 0, s>>>(w.acc, w.sums, loss_weight, grad_out, extrinsics, g_extrinsics,
+                                               g_k4, F);
+  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_finalize");
   return 0;
 }
 
@@ -1921,20 +1981,9 @@ int fm_track_loss_bwd(const float* depth, const float* k4, const float* extrinsi
                       const unsigned char* track_vis, long long total_samples, int mapping, float delta,
                       float loss_weight, const float* grad_out, float* g_depth, float* g_extrinsics,
                       float* g_k4, void* ws, int F, int H, int W, void* stream) {
-  (void)depth; (void)track_vis; (void)mapping; (void)delta;
-  if (!k4 || !extrinsics || !segments || !track_xy || !g_depth || !g_extrinsics || !g_k4 || !ws ||
-      num_segments < 1 || max_rows < 1 || max_points < 1 || F < 1)
-    return fail_msg("fm_track_loss_bwd: bad arguments");
-  cudaStream_t s = (cudaStream_t)stream;
-  TrackWs w = carve_track(ws, F, total_samples);
-  dim3 grid((max_points + kThreads - 1) / kThreads, max_rows, num_segments);
-  k_track_apply<<<grid, kThreads, 0, s>>>(k4, segments, track_xy, w.flag, w.dq, w.sums, loss_weight, grad_out,
-                                         g_depth, H, W);
-  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_apply");
-  k_track_finalize<<<(F + 63) / 64, 64, 0, s>>>(w.acc, w.sums, loss_weight, grad_out, extrinsics, g_extrinsics,
-                                               g_k4, F);
-  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_finalize");
-  return 0;
+  return fm_track_loss_bwd_sharded(depth, k4, extrinsics, segments, num_segments, max_rows, max_points, track_xy,
+                                   track_vis, total_samples, mapping, delta, loss_weight, grad_out, g_depth,
+                                   g_extrinsics, g_k4, ws, F, H, W, 0, 0, F, stream);
 }
 
 size_t fm_points_workspace_bytes(int items) {
@@ -2134,28 +2183,35 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
   const size_t N = (size_t)H * W;
   Workspace w = carve(a->ws, 1, F);
   int rc;
+  cudaError_t e;
+  if (a->phase < FM_STEP_ALL || a->phase > FM_STEP_BACKWARD) return fail_msg("fm_overfit_step: unknown phase");
+  if (a->phase != FM_STEP_ALL && a->tracks)
+    return fail_msg("fm_overfit_step: a split step takes the tracking gradient through g_rt / track_g_k4");
   // intrinsics from the focal parameter (regressed stage) or as given
   float* k4 = a->k4;
-  if (a->focal) {
-    k_k4_from_focal<<<(F + 63) / 64, 64, 0, s>>>(a->focal, k4, F, H, W);
-    FM_CHECK_LAUNCH("fm_overfit_step: k_k4_from_focal");
+  if (a->phase != FM_STEP_BACKWARD) {
+    if (a->focal) {
+      k_k4_from_focal<<<(F + 63) / 64, 64, 0, s>>>(a->focal, k4, F, H, W);
+      FM_CHECK_LAUNCH("fm_overfit_step: k_k4_from_focal");
+    }
+    // Model.forward: Procrustes poses (model.py:54-90)
+    if ((rc = procrustes_fwd_impl(a->depth, k4, a->bflow, a->weight_logits, a->weight_sensitivity,
+                                  a->indices, a->num_indices, a->rt, a->ws, 1, F, H, W, stream)))
+      return rc;
+    // LossFlow forward + direct gradients (loss_flow.py:31-70)
+    e = cudaMemsetAsync(w.flowacc, 0, (size_t)F * kFlowAcc * sizeof(double), s);
+    if (e != cudaSuccess) return fail("fm_overfit_step: memset", e);
+    if ((rc = launch_flow(a->depth, k4, a->rt, a->fflow, a->bflow, a->fmask, a->bmask, a->mask_sum,
+                          a->mapping, a->delta, a->flow_weight, a->focal ? 1 : 2, a->g_depth, w.flowacc, 1, F,
+                          H, W, s)))
+      return rc;
+    k_flow_finalize<<<(F + 127) / 128, 128, 0, s>>>(w.flowacc, a->rt, a->loss, nullptr, nullptr, 1, F);
+    FM_CHECK_LAUNCH("fm_overfit_step: k_flow_finalize");
+    if (a->phase == FM_STEP_FORWARD) return 0;
   }
-  // Model.forward: Procrustes poses (model.py:54-90)
-  if ((rc = procrustes_fwd_impl(a->depth, k4, a->bflow, a->weight_logits, a->weight_sensitivity,
-                                a->indices, a->num_indices, a->rt, a->ws, 1, F, H, W, stream)))
-    return rc;
-  // LossFlow forward + direct gradients (loss_flow.py:31-70)
-  cudaError_t e = cudaMemsetAsync(w.flowacc, 0, (size_t)F * kFlowAcc * sizeof(double), s);
-  if (e != cudaSuccess) return fail("fm_overfit_step: memset", e);
-  if ((rc = launch_flow(a->depth, k4, a->rt, a->fflow, a->bflow, a->fmask, a->bmask, a->mask_sum,
-                        a->mapping, a->delta, a->flow_weight, a->focal ? 1 : 2, a->g_depth, w.flowacc, 1, F,
-                        H, W, s)))
-    return rc;
-  k_flow_finalize<<<(F + 127) / 128, 128, 0, s>>>(w.flowacc, a->rt, a->loss, nullptr, nullptr, 1, F);
-  FM_CHECK_LAUNCH("fm_overfit_step: k_flow_finalize");
   // LossTracking (loss_tracking.py:28-61) on the chained poses, gradients into g_depth / g_rt
-  const float* g_rt = nullptr;
-  const float* track_g_k4 = nullptr;
+  const float* g_rt = a->phase == FM_STEP_BACKWARD ? a->g_rt : nullptr;           // the caller's
+  const float* track_g_k4 = a->phase == FM_STEP_BACKWARD ? a->track_g_k4 : nullptr;  // tracking part
   if (a->tracks) {
     const fm_packed_tracks* t = a->tracks;
     if ((rc = fm_pose_chain(a->rt, a->extrinsics, 1, F, stream))) return rc;

@@ -306,20 +306,54 @@ class FusedOverfitter(Overfitter):
 
 
 class ShardedFusedOverfitter(FusedOverfitter):
-    """Pair-sharded :class:`FusedOverfitter` (flowmap_b200.parallel): every rank runs
-    fm_overfit_step on its own pairs without the Adam part, ONE all-reduce carries the loss,
-    the focal-length gradient and the boundary depth-gradient frames, then each rank applies
-    Adam to its parameters (replicas of a boundary frame see identical gradients)."""
+    """Pair-sharded :class:`FusedOverfitter` (flowmap_b200.parallel).
 
-    def __init__(self, cfg: OverfitCfg, batch: Batch, flows: Flows, plan, device="cuda", group=None):
+    Every rank holds the frames / pairs of its ShardPlan and runs fm_overfit_step on them
+    without the Adam part; ONE all-reduce carries the loss, the focal-length gradient and the
+    boundary depth-gradient frames, then each rank applies Adam to its parameters (replicas of
+    a boundary frame see identical gradients).
+
+    Tracking loss (not pair-local: a track segment spans up to 41 frames): the step is split
+    (FM_STEP_FORWARD / FM_STEP_BACKWARD).  In between, the relative poses are gathered (149 x 12
+    floats), every rank chains them, evaluates the tracking loss for the SOURCE frames it owns
+    against all target frames, the loss sum / valid count / per-frame pose and intrinsics sums
+    (F x 10 doubles) are all-reduced, and every rank backpropagates the (now global) pose
+    gradient through the chain to its own pairs.  `tracks` are the global segments.
+
+    Softmin intrinsics: the candidate sweep lives on the rank that owns pair 0; its focal
+    estimate is broadcast before the step and its backward runs after the step's all-reduce
+    (the summed d loss / d focal), so the sweep adds two one-float collectives."""
+
+    def __init__(self, cfg: OverfitCfg, batch: Batch, flows: Flows, plan, tracks=None, device="cuda",
+                 group=None):
+        from dataclasses import replace
         from . import parallel
-        if cfg.use_tracking:
-            raise NotImplementedError("pair sharding covers the flow loss (BASELINE config 4)")
-        super().__init__(cfg, batch, flows, None, device)
+        from ._lib import lib
+        super().__init__(replace(cfg, use_tracking=False), batch, flows, None, device)
+        self.cfg = cfg
         self.plan, self.group = plan, group
-        _, _, _, h, w = batch.videos.shape
-        self.reducer = parallel.StepReducer(plan, (h, w), self.rt.device, 2, group)
+        _, f_local, _, h, w = batch.videos.shape
+        if f_local != plan.num_local_frames:
+            raise ValueError("flowmap_b200: batch does not match the shard plan")
+        dev = self.rt.device
+        self.reducer = parallel.StepReducer(plan, (h, w), dev, 2, group)
         self._msum.copy_(parallel.global_mask_sum(self._msum, group))  # in place: args hold its address
+        if self._softmin and plan.world > 1 and plan.pair_range[1] - plan.pair_range[0] < 2 and plan.rank == 0:
+            raise ValueError("flowmap_b200: the rank owning pair 0 needs >= 2 pairs in the softmin stage")
+        if cfg.use_tracking:
+            if tracks is None:
+                raise ValueError("flowmap_b200: use_tracking needs the (global) track segments")
+            F = plan.num_pairs_total + 1
+            pk = ops.PackedTracks([t.to(dev) for t in tracks], dev)
+            self._packed, self._F = pk, F
+            z = lambda *shape: torch.zeros(*shape, device=dev)  # noqa: E731
+            self._rt_all, self._g_rt_all = z(1, F - 1, 3, 4), z(1, F - 1, 3, 4)
+            self._ext_all, self._g_ext_all = z(1, F, 4, 4), z(1, F, 4, 4)
+            self._tg_k4_all = z(F, 4)
+            self._g_rt_local = z(1, f_local - 1, 3, 4)
+            self._tws = torch.empty(lib().fm_track_workspace_bytes(F, pk.total), dtype=torch.uint8, device=dev)
+            self._treduce = self._tws[:lib().fm_track_reduce_bytes(F)].view(torch.float64)
+            self._src_range = parallel.source_frame_range(plan)
 
     def sync_boundary_depth(self):
         """Make the replicas of every shared boundary frame identical (owner = left rank)."""
@@ -334,20 +368,126 @@ class ShardedFusedOverfitter(FusedOverfitter):
         if p.has_left:
             self._depth[0].copy_(buf[p.rank - 1])
 
+    def _first_rank(self) -> int:
+        import torch.distributed as dist
+        return 0 if self.group is None else dist.get_global_rank(self.group, 0)
+
+    def _tracking_exchange(self, h: int, w: int):
+        """Between the two halves of a split step; returns tracking's d loss / d focal (global)."""
+        import torch.distributed as dist
+        from . import parallel
+        from ._lib import check
+        c, L, pk, F = self.cfg, self._lib, self._packed, self._F
+        a0, b0 = self.plan.pair_range
+        P = lambda t: t.data_ptr()  # noqa: E731
+        st = torch.cuda.current_stream().cuda_stream
+        parallel.gather_pairs(self.plan, self.rt, self._rt_all, self.group)
+        k4_all = self._k4[0].expand(F, 4).contiguous()  # one shared focal length
+        args = (P(k4_all), P(self._ext_all), P(pk.seg), pk.num_segments, pk.max_rows, pk.max_points, P(pk.xy),
+                P(pk.vis), pk.total, ops.MAPPINGS[c.mapping], c.delta, c.tracking_weight)
+        tail = (F, h, w, a0, self._src_range[0], self._src_range[1], st)
+        with torch.cuda.device(self.rt.device):
+            check(L.fm_pose_chain(P(self._rt_all), P(self._ext_all), 1, F, st), "fm_pose_chain")
+            check(L.fm_track_loss_fwd_sharded(P(self._depth), *args, None, P(self._tws), *tail),
+                  "fm_track_loss_fwd_sharded")
+            if self.plan.world > 1:
+                dist.all_reduce(self._treduce, group=self.group)
+            check(L.fm_track_loss_value(P(self._tws), c.tracking_weight, P(self._track_loss), st),
+                  "fm_track_loss_value")
+            check(L.fm_track_loss_bwd_sharded(P(self._depth), *args, None, P(self._g_depth), P(self._g_ext_all),
+                                              P(self._tg_k4_all), P(self._tws), *tail),
+                  "fm_track_loss_bwd_sharded")
+            check(L.fm_pose_chain_bwd(P(self._rt_all), P(self._ext_all), P(self._g_ext_all),
+                                      P(self._g_rt_all), 1, F, st), "fm_pose_chain_bwd")
+        self._g_rt_local.copy_(self._g_rt_all[:, a0:b0])
+        scale = (h * w) ** 0.5
+        return (self._tg_k4_all[:, 0].double().sum() * (scale / w) +
+                self._tg_k4_all[:, 1].double().sum() * (scale / h)).float()
+
     def training_step(self, update: bool = True):
-        loss, rt = super().training_step(update=False)
-        scalars = torch.stack((loss.reshape(()), self._g_focal.reshape(())))
-        red = self.reducer.reduce(scalars, self._g_depth)
+        import torch.distributed as dist
+        from ._lib import check
+        c, a, p, L = self.cfg, self._args, self.plan, self._lib
+        _, _, _, h, w = self.batch.videos.shape
+        P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        st = torch.cuda.current_stream().cuda_stream
+        dev = self.rt.device
+        if c.procrustes_randomize:
+            self._indices = self.model.extrinsics.select_indices(h, w, dev)
+        a.indices = None if self._indices is None else self._indices.data_ptr()
+        a.num_indices = 0 if self._indices is None else self._indices.numel()
+        a.flow_weight = c.flow_weight if self.global_step >= c.flow_enable_after else 0.0
+        a.tracks, a.step, a.defer_adam = None, 0, 0
+        track_on = c.use_tracking and self.global_step >= c.tracking_enable_after
+        sweep = self._softmin_stage()
+        own_sweep = sweep and p.rank == 0
+        if sweep:
+            n = c.softmin_candidates
+            wl = P(self._wlog) if c.use_correspondence_weights else None
+            sens = c.weight_sensitivity if c.use_correspondence_weights else 0.0
+            if own_sweep:
+                idx = self.injected_indices
+                if idx is None:
+                    idx = ops.random_subset(h * w, min(c.softmin_points, h * w), dev)
+                idx = idx.contiguous()
+                f_local = self._depth.shape[0]
+                with torch.cuda.device(dev):
+                    check(L.fm_softmin_sweep_fwd(P(self._depth), wl, sens, P(self.flows.backward), P(idx),
+                                                 idx.numel(), P(self._cand_k4), n, P(self._sw_err),
+                                                 P(self._sw_rt), P(self._sw_ws), 1, f_local, h, w, st),
+                          "fm_softmin_sweep_fwd")
+                    check(L.fm_softmin_focal(P(self._sw_err), P(self._cand_f), n, 1, P(self._sw_sm),
+                                             P(self._sw_focal), st), "fm_softmin_focal")
+            if p.world > 1:
+                dist.broadcast(self._sw_focal, src=self._first_rank(), group=self.group)
+            a.focal = P(self._sw_focal)
+        else:
+            a.focal = P(self._focal)
+            if self._softmin and self.global_step == c.regression_after and update:
+                self._focal.copy_(torch.stack(self.window).mean())  # hand-over, identical on all ranks
+        extra_focal = None
+        with torch.cuda.device(dev):
+            if track_on:
+                a.phase = 1  # FM_STEP_FORWARD
+                check(L.fm_overfit_step(self._ctypes.byref(a), st), "fm_overfit_step (forward)")
+                extra_focal = self._tracking_exchange(h, w)
+                a.phase, a.g_rt, a.track_g_k4 = 2, P(self._g_rt_local), None  # FM_STEP_BACKWARD
+                check(L.fm_overfit_step(self._ctypes.byref(a), st), "fm_overfit_step (backward)")
+                a.phase, a.g_rt = 0, None
+            else:
+                check(L.fm_overfit_step(self._ctypes.byref(a), st), "fm_overfit_step")
+        g_focal = self._g_focal.reshape(())
+        if extra_focal is not None and p.rank == 0:  # global value, counted once
+            g_focal = g_focal + extra_focal
+        red = self.reducer.reduce(torch.stack((self._loss.reshape(()), g_focal)), self._g_depth)
         self._g_focal.copy_(red[1])
+        if own_sweep:  # backward of the sweep with the summed focal gradient: frames 0/1, pair 0
+            f_local = self._depth.shape[0]
+            with torch.cuda.device(dev):
+                check(L.fm_softmin_focal_bwd(P(self._sw_sm), P(self._cand_f), P(self._sw_focal),
+                                             P(self._g_focal), n, 1, P(self._sw_gerr), st),
+                      "fm_softmin_focal_bwd")
+                check(L.fm_softmin_sweep_bwd(P(self._depth), wl, sens, P(self.flows.backward), P(idx),
+                                             idx.numel(), P(self._cand_k4), n, P(self._sw_rt),
+                                             P(self._sw_gerr), P(self._g_depth),
+                                             P(self._g_w) if wl else None, P(self._sw_ws), 1, f_local, h, w, st),
+                      "fm_softmin_sweep_bwd")
         if update:
-            self.global_step += 1
-            st, c = self._state, self.cfg
-            ops.adam_step(self._depth, self._g_depth, st[0], st[1], self.global_step, c.lr)
+            s_ = self.global_step + 1
+            stt = self._state
+            ops.adam_step(self._depth, self._g_depth, stt[0], stt[1], s_, c.lr)
             if c.use_correspondence_weights:
-                ops.adam_step(self._wlog, self._g_w, st[2], st[3], self.global_step, c.lr)
-            ops.adam_step(self._focal.reshape(1), self._g_focal.reshape(1), st[4].reshape(1),
-                          st[5].reshape(1), self.global_step, c.lr)
-        return red[0], rt
+                ops.adam_step(self._wlog, self._g_w, stt[2], stt[3], s_, c.lr)
+            if sweep:
+                if c.regression_after is not None and self.global_step >= c.regression_after - c.regression_window:
+                    self.window.append(self._sw_focal[0].clone())
+            else:
+                fstep = s_ - c.regression_after if self._softmin else s_
+                ops.adam_step(self._focal.reshape(1), self._g_focal.reshape(1), stt[4].reshape(1),
+                              stt[5].reshape(1), fstep, c.lr)
+            self.global_step += 1
+        total = red[0] + self._track_loss if track_on else red[0]
+        return total, self.rt
 
 
 class ShardedOverfitter(Overfitter):

@@ -14,6 +14,14 @@ into the frame's slot, the all-reduce sums them, and both sides then apply the i
 Adam update to their replica of that frame, so the replicas stay bit-identical without a
 second message.  The reference has no counterpart (its DDP replicas hold the identical
 problem, flowmap/overfit.py:99-103).
+
+The tracking loss couples frames up to 40 apart, so it is sharded by SOURCE frame instead
+(`source_frame_range`): the relative poses are gathered (`gather_pairs`, 149 x 12 floats), every
+rank chains them and evaluates its source frames against all targets; the loss sum, the valid
+count and the per-frame pose / intrinsics sums (F x 10 doubles) are all-reduced, after which the
+pose gradient is global on every rank and flows back through the chain into the rank's own pairs
+(overfit.ShardedFusedOverfitter).  The softmin sweep lives on the rank that owns pair 0: one
+broadcast of its focal estimate before the step.
 """
 from __future__ import annotations
 
@@ -85,6 +93,30 @@ def global_mask_sum(local_sum: Tensor, group=None) -> Tensor:
     total = local_sum.clone()
     dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     return total
+
+
+def source_frame_range(plan: ShardPlan) -> Tuple[int, int]:
+    """Tracking loss (not pair-local): rank g evaluates the SOURCE frames [lo, hi) of
+    every track segment against all target frames.  A boundary frame is held by two ranks; the
+    right one owns it as a source, the last rank also owns the last frame."""
+    a, b = plan.pair_range
+    return a, (b + 1 if plan.rank == plan.world - 1 else b)
+
+
+def gather_pairs(plan: ShardPlan, local: Tensor, out: Optional[Tensor] = None, group=None) -> Tensor:
+    """Per-pair quantities (1, local pairs, ...) of every rank -> (1, all pairs, ...) on every rank.
+    The slices are disjoint, so a sum all-reduce of a zero-filled buffer is a gather with one
+    collective and no size bookkeeping (149 x 12 floats for the relative poses)."""
+    a, b = plan.pair_range
+    if out is None:
+        out = torch.zeros((local.shape[0], plan.num_pairs_total, *local.shape[2:]), dtype=local.dtype,
+                          device=local.device)
+    else:
+        out.zero_()
+    out[:, a:b].copy_(local)
+    if plan.world > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
 
 
 class StepReducer:

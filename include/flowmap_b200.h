@@ -156,6 +156,29 @@ int fm_track_loss_bwd(const float* depth, const float* k4, const float* extrinsi
                       float loss_weight, const float* grad_out, float* g_depth, float* g_extrinsics,
                       float* g_k4, void* ws, int F, int H, int W, void* stream);
 
+/* Multi-GPU form ("shard by source frame"): the reference has no counterpart (its
+ * DDP replicas hold the whole problem, overfit.py:99-103).  This rank holds the depth frames
+ * starting at global frame `depth_frame0` (depth and g_depth point at that frame) and evaluates
+ * only the source frames [src_frame_lo, src_frame_hi); k4 / extrinsics / g_extrinsics / g_k4 and
+ * the track arrays are global (F frames).  Between fwd and bwd the caller all-reduces (sum, as
+ * float64) the first fm_track_reduce_bytes(F) bytes of `ws` (loss sum, valid count, per-frame
+ * pose / intrinsics sums); fm_track_loss_value then gives the global loss, and the backward's
+ * g_extrinsics / g_k4 are the global gradients on every rank while g_depth receives this rank's
+ * source frames.  loss may be NULL in the sharded forward. */
+size_t fm_track_reduce_bytes(int F);
+int fm_track_loss_fwd_sharded(const float* depth, const float* k4, const float* extrinsics, const int* segments,
+                              int num_segments, int max_rows, int max_points, const float* track_xy,
+                              const unsigned char* track_vis, long long total_samples, int mapping, float delta,
+                              float loss_weight, float* loss, void* ws, int F, int H, int W, int depth_frame0,
+                              int src_frame_lo, int src_frame_hi, void* stream);
+int fm_track_loss_value(const void* ws, float loss_weight, float* loss, void* stream);
+int fm_track_loss_bwd_sharded(const float* depth, const float* k4, const float* extrinsics, const int* segments,
+                              int num_segments, int max_rows, int max_points, const float* track_xy,
+                              const unsigned char* track_vis, long long total_samples, int mapping, float delta,
+                              float loss_weight, const float* grad_out, float* g_depth, float* g_extrinsics,
+                              float* g_k4, void* ws, int F, int H, int W, int depth_frame0, int src_frame_lo,
+                              int src_frame_hi, void* stream);
+
 /* model_wrapper_overfit.py:104-105 optim.Adam(lr): torch's single-tensor Adam update (no
  * amsgrad, no weight decay), one fused pass; `step` is the 1-based step number. */
 int fm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count,
@@ -240,7 +263,16 @@ typedef struct {
                                    add its gradients to depth frames 0/1 and to the weights of pair 0, so
                                    only the weight logits of pairs >= 1 are updated here (with `step`);
                                    the caller runs Adam on depth and on pair 0's logits afterwards */
+  int phase;                    /* FM_STEP_ALL, or a split step for pair sharding with a tracking loss:
+                                   FM_STEP_FORWARD stops after the flow loss (rt, loss, direct depth
+                                   gradient, pose-gradient sums in ws); FM_STEP_BACKWARD resumes at the
+                                   Procrustes backward with the caller's extra pose gradient g_rt (F-1,3,4)
+                                   and intrinsics gradient track_g_k4 (F,4) (either may be NULL); tracks
+                                   must be NULL in both */
 } fm_overfit_step_args;
+#define FM_STEP_ALL 0
+#define FM_STEP_FORWARD 1
+#define FM_STEP_BACKWARD 2
 int fm_overfit_step(const fm_overfit_step_args* args, void* stream);
 
 /* ---- stages either side of the hot path ---------------------------- */

@@ -615,3 +615,52 @@ def test_c4_shape_properties():
     assert max_abs(rt2.cpu(), rt[:, s0:s0 + 2].cpu()) <= 1e-6
     assert rel_l2(gd2[1].cpu(), gd[s0 + 1].cpu()) <= 1e-4
     assert rel_l2(gw2.cpu(), gw[s0:s0 + 2].cpu()) <= 1e-4
+
+
+@pytest.mark.parametrize("intrinsics", ["regressed", "softmin"])
+def test_split_step_with_tracking_equals_fused(intrinsics):
+    """The pair-sharded driver (split step, gathered poses, source-sharded tracking, sweep on the
+    first rank) on a one-rank group must reproduce the unsharded fused optimisation."""
+    import socket
+    import torch.distributed as dist
+    from oracle import flowmap_oracle as O
+    from flowmap_b200 import parallel
+    from flowmap_b200.overfit import FusedOverfitter, OverfitCfg, ShardedFusedOverfitter
+    from flowmap_b200.types import Batch, Flows, Tracks
+    f, h, w = 12, 48, 64
+    fl = O.synthetic_flows(f, h, w, seed=5)
+    trk = [Tracks(t.xy, t.visibility, t.start_frame)
+           for t in O.synthetic_tracks(f, n_points=96, interval=4, radius=5, seed=6)]
+    gen = torch.Generator().manual_seed(7)
+    depth = 1.0 + 0.5 * torch.rand(f, h, w, generator=gen)
+    wparam = 0.01 * torch.randn(f - 1, h, w, generator=gen)
+    cfg = OverfitCfg(intrinsics=intrinsics, use_tracking=True, tracking_enable_after=1, softmin_points=256,
+                     regression_after=3, regression_window=2, lr=1e-3)
+    idx = torch.randperm(h * w, generator=gen)[:256].cuda()
+
+    def make(cls, *extra, **kw):
+        batch = Batch(torch.zeros(1, 1, 1, 1, 1).expand(1, f, 3, h, w), torch.arange(f)[None], ["s"], ["d"])
+        o = cls(cfg, batch, Flows(fl.forward, fl.backward, fl.forward_mask, fl.backward_mask), *extra, **kw)
+        with torch.no_grad():
+            o.model.backbone.depth.copy_(depth)
+            o.model.backbone.weights.copy_(wparam)
+        o.injected_indices = idx
+        return o
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        sh = make(ShardedFusedOverfitter, parallel.make_plan(f - 1), tracks=trk)
+        ref = make(FusedOverfitter, trk)
+        for step in range(5):   # sweep stage (0-2) incl. tracking from step 1, hand-over at 3, regressed
+            l_sh, _ = sh.training_step()
+            l_ref, _ = ref.training_step()
+            assert abs(float(l_sh) - float(l_ref)) <= 2e-5 * abs(float(l_ref)), step
+        assert rel_l2(sh.model.backbone.depth.detach().cpu(), ref.model.backbone.depth.detach().cpu()) <= 1e-6
+        upd = lambda o: (o.model.backbone.weights.detach().cpu() - wparam)  # noqa: E731
+        assert rel_l2(upd(sh), upd(ref)) <= 1e-3
+        assert abs(float(sh._focal) - float(ref._focal)) <= 1e-6
+    finally:
+        dist.destroy_process_group()

@@ -27,32 +27,50 @@ flows = Flows(0.01 * torch.randn(1, F - 1, H, W, 2, generator=g), 0.01 * torch.r
               torch.rand(1, F - 1, H, W, generator=g), torch.rand(1, F - 1, H, W, generator=g))
 
 
-def make(cls, d, wp, fl, *extra):
+from oracle import flowmap_oracle as O  # noqa: E402  (synthetic tracks only)
+from flowmap_b200.types import Tracks  # noqa: E402
+
+tracks = [Tracks(t.xy, t.visibility, t.start_frame) for t in O.synthetic_tracks(F, n_points=128, interval=4, radius=6, seed=2)]
+idx = torch.randperm(H * W, generator=g)[:512].to(dev)
+
+
+def make(cls, cfg, d, wp, fl, *extra, **kw):
     f = d.shape[0]
     batch = Batch(torch.zeros(1, 1, 1, 1, 1, device=dev).expand(1, f, 3, H, W), torch.arange(f, device=dev)[None], ["s"], ["d"])
-    o = cls(OverfitCfg(), batch, fl.to(dev), *extra, device=dev)
+    o = cls(cfg, batch, fl.to(dev), *extra, device=dev, **kw)
     with torch.no_grad():
         o.model.backbone.depth.copy_(d)
         o.model.backbone.weights.copy_(wp)
+    o.injected_indices = idx
     return o
 
 
 plan = parallel.make_plan(F - 1)
 d_l, w_l, fl_l = parallel.shard_inputs(plan, depth, wparam, flows)
-sh = make(ShardedFusedOverfitter, d_l, w_l, fl_l, plan)
-losses = [float(sh.training_step()[0]) for _ in range(STEPS)]
-full = make(FusedOverfitter, depth, wparam, flows)
-ref_losses = [float(full.training_step()[0]) for _ in range(STEPS)]
 a, b = plan.pair_range
 rel = lambda x, y: float((x - y).norm() / y.norm())  # noqa: E731
-e_d = rel(sh.model.backbone.depth.detach(), full.model.backbone.depth.detach()[a:b + 1])
-upd_ref = full.model.backbone.weights.detach()[a:b] - wparam[a:b].to(dev)
-upd = sh.model.backbone.weights.detach() - w_l.to(dev)
-e_w = rel(upd, upd_ref)
-e_f = abs(float(sh.model.intrinsics.focal_length) - float(full.model.intrinsics.focal_length))
-e_l = max(abs(x - y) / abs(y) for x, y in zip(losses, ref_losses))
-print(f"rank {rank}/{world} pairs {plan.pair_range}: loss rel err {e_l:.2e}, depth {e_d:.2e}, "
-      f"weight-update {e_w:.2e}, focal {e_f:.2e}, collective {sh.reducer.bytes_per_step()} B/step", flush=True)
-assert e_l < 1e-4 and e_d < 1e-5 and e_w < 2e-2 and e_f < 1e-5
-dist.barrier()
+CASES = {
+    "flow only, regressed focal": OverfitCfg(lr=1e-3),
+    "flow + tracking, regressed focal": OverfitCfg(lr=1e-3, use_tracking=True, tracking_enable_after=1),
+    "flow + tracking, softmin sweep then hand-over": OverfitCfg(lr=1e-3, use_tracking=True, tracking_enable_after=1,
+                                                              intrinsics="softmin", softmin_points=512,
+                                                              regression_after=3, regression_window=2),
+}
+for name, cfg in CASES.items():
+    steps = 5 if cfg.intrinsics == "softmin" else STEPS
+    trk = tracks if cfg.use_tracking else None
+    sh = make(ShardedFusedOverfitter, cfg, d_l, w_l, fl_l, plan, tracks=trk)
+    losses = [float(sh.training_step()[0]) for _ in range(steps)]
+    full = make(FusedOverfitter, cfg, depth, wparam, flows, trk)
+    ref_losses = [float(full.training_step()[0]) for _ in range(steps)]
+    e_d = rel(sh.model.backbone.depth.detach(), full.model.backbone.depth.detach()[a:b + 1])
+    upd_ref = full.model.backbone.weights.detach()[a:b] - wparam[a:b].to(dev)
+    upd = sh.model.backbone.weights.detach() - w_l.to(dev)
+    e_w = rel(upd, upd_ref)
+    e_f = abs(float(sh._focal) - float(full._focal))
+    e_l = max(abs(x - y) / abs(y) for x, y in zip(losses, ref_losses))
+    print(f"[{name}] rank {rank}/{world} pairs {plan.pair_range}: loss rel err {e_l:.2e}, depth {e_d:.2e}, "
+          f"weight-update {e_w:.2e}, focal {e_f:.2e}, collective {sh.reducer.bytes_per_step()} B/step", flush=True)
+    assert e_l < 1e-4 and e_d < 1e-5 and e_w < 2e-2 and e_f < 1e-5, name
+    dist.barrier()
 dist.destroy_process_group()
