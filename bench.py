@@ -248,7 +248,8 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    pairs_mode = args.mode == "pairs"
+    pairs_mode = args.mode in ("pairs", "pairs-full")
+    pairs_full = args.mode == "pairs-full"
 
     inputs = synthetic_inputs(F_, H_, W_, seed=rank)
     batch = Batch(torch.zeros(1, 1, 1, 1, 1, device=dev).expand(1, F_, 3, H_, W_),
@@ -271,7 +272,12 @@ def run_gpu(args):
     flows_dev = device_flows()
     if pairs_mode:
         plan = parallel.ShardPlan(rank, world, (rank * (F_ - 1), (rank + 1) * (F_ - 1)), world * (F_ - 1))
-        o = init_params(ShardedFusedOverfitter(OverfitCfg(), batch, flows_dev, plan, device=dev))
+        if pairs_full:  # one long video, full loop: global track segments, sweep on rank 0
+            tracks = [Tracks(xy, vis, s) for xy, vis, s in synthetic_track_arrays(world * (F_ - 1) + 1, seed=0)]
+            o = init_params(ShardedFusedOverfitter(OverfitCfg(intrinsics="softmin", use_tracking=True), batch,
+                                                   flows_dev, plan, tracks=tracks, device=dev))
+        else:
+            o = init_params(ShardedFusedOverfitter(OverfitCfg(), batch, flows_dev, plan, device=dev))
         o.sync_boundary_depth()
     else:
         tracks = [Tracks(xy, vis, s) for xy, vis, s in synthetic_track_arrays(F_, seed=rank)]
@@ -445,7 +451,7 @@ def run_gpu(args):
         cpu = {"value": None, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
                "sample": "skipped (FM_BENCH_SKIP_CPU=1)"}
     else:
-        cpu = cpu_baseline(sample_frames=12, steps=2, warmup=1, full=not pairs_mode)
+        cpu = cpu_baseline(sample_frames=12, steps=2, warmup=1, full=not pairs_mode or pairs_full)
 
     its = world * 1000.0 / ms
     out = {
@@ -453,14 +459,16 @@ def run_gpu(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "frame_pairs_per_s": round(its * (F_ - 1), 1),
-        "config": {"workload": WORKLOAD if not pairs_mode else
+        "config": {"workload": WORKLOAD if (not pairs_mode or pairs_full) else
                    WORKLOAD.replace("softmin intrinsics (60 candidates x 8192 points), flow + tracking loss",
                                     "regressed focal, flow loss only"),
                    "frames": F_, "height": H_, "width": W_,
                    "parallelism": ("%d independent scenes, one per GPU (BASELINE config 5), no "
                                    "collective" % world) if not pairs_mode else
                                   ("%d x %d pairs of one video, 1 all-reduce/step of %d bytes"
-                                   % (world, F_ - 1, o.reducer.bytes_per_step())),
+                                   % (world, F_ - 1, o.reducer.bytes_per_step())) +
+                                  (" + pose gather, tracking-sum all-reduce (F x 10 doubles), focal broadcast"
+                                   if pairs_full else ""),
                    "l2": "inputs (1.1 GB) exceed the 126 MB L2, no flush needed",
                    "mask_sum": "loop-invariant flow-loss denominator hoisted out of the loop "
                                "(recomputed every step in the e2e leg, where the masks are re-uploaded)"},
@@ -511,7 +519,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="scenes", choices=["scenes", "pairs"])
+    ap.add_argument("--mode", default="scenes", choices=["scenes", "pairs", "pairs-full"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
