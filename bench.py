@@ -341,7 +341,7 @@ def run_gpu(args):
     # ---- flow-loss-only variant of the same step (regressed focal): the path the roofline
     # accounting below describes; and the same on spatially smooth flows (real optical flow is
     # piecewise smooth; the iid flows above are the worst case for the bilinear gather/scatter)
-    flow_only_ms = smooth_ms = None
+    flow_only_ms = smooth_ms = sparse_ms = None
     if not pairs_mode:
         o2 = init_params(FusedOverfitter(OverfitCfg(), batch, flows_dev, device=dev))
         for _ in range(3):
@@ -356,6 +356,15 @@ def run_gpu(args):
             o2.training_step()
         smooth_ms, _ = time_steps(o2.training_step, min(args.steps, 30))
         del o2
+        flows_dev.forward.copy_(flows_host.forward, non_blocking=True)
+        flows_dev.backward.copy_(flows_host.backward, non_blocking=True)
+        # the reference's DEFAULT pose solve uses 1000 evenly spaced points per pair
+        # (config/model/extrinsics/procrustes.yaml:3-4) instead of all pixels
+        o3 = init_params(FusedOverfitter(OverfitCfg(procrustes_points=1000), batch, flows_dev, device=dev))
+        for _ in range(3):
+            o3.training_step()
+        sparse_ms, _ = time_steps(o3.training_step, min(args.steps, 30))
+        del o3
         flows_dev.forward.copy_(flows_host.forward, non_blocking=True)   # o.flows shares these buffers
         flows_dev.backward.copy_(flows_host.backward, non_blocking=True)
 
@@ -450,6 +459,9 @@ def run_gpu(args):
     if os.environ.get("FM_BENCH_SKIP_CPU") == "1":  # profiling runs (ncu) only
         cpu = {"value": None, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
                "sample": "skipped (FM_BENCH_SKIP_CPU=1)"}
+    elif world > 1:  # the CPU baseline is a property of the host, timed in the N=1 run
+        cpu = {"value": None, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "timed on rank 0 at N=1 only (see the --gpus 1 line)"}
     else:
         cpu = cpu_baseline(sample_frames=12, steps=2, warmup=1, full=not pairs_mode or pairs_full)
 
@@ -481,6 +493,7 @@ def run_gpu(args):
         {"ms_per_step": round(flow_only_ms, 4), "it_per_s": round(world * 1000.0 / flow_only_ms, 2),
          "what": "same step without tracking loss / softmin sweep (regressed focal)",
          "ms_per_step_smooth_flows": None if smooth_ms is None else round(smooth_ms, 4),
+         "ms_per_step_1000_point_procrustes": None if sparse_ms is None else round(sparse_ms, 4),
          "smooth_flows": "N(0, 0.01^2) flow on a 16x coarser grid, bilinearly upsampled"},
         "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
     }

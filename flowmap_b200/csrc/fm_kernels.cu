@@ -576,10 +576,18 @@ __global__ void k_flow_finalize(const double* __restrict__ flowacc, const float*
     flow_k4_grad(flowacc, t, F, g);
     for (int k = 0; k < 4; ++k) g_k4[(size_t)t * 4 + k] = (float)g[k];
   }
-  if (t == 0 && loss) {
+  if (blockIdx.x == 0 && loss) {  // block 0: the per-frame loss terms, summed in parallel
+    __shared__ double part[32];
     double s = 0.0;
-    for (int k = 0; k < BF; ++k) s += flowacc[(size_t)k * kFlowAcc];
-    *loss = (float)s;
+    for (int k = threadIdx.x; k < BF; k += blockDim.x) s += flowacc[(size_t)k * kFlowAcc];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) tot += part[w];
+      *loss = (float)tot;
+    }
   }
 }
 
