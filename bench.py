@@ -341,7 +341,7 @@ def run_gpu(args):
     # ---- flow-loss-only variant of the same step (regressed focal): the path the roofline
     # accounting below describes; and the same on spatially smooth flows (real optical flow is
     # piecewise smooth; the iid flows above are the worst case for the bilinear gather/scatter)
-    flow_only_ms = smooth_ms = sparse_ms = None
+    flow_only_ms = smooth_ms = sparse_ms = dropin_ms = None
     if not pairs_mode:
         o2 = init_params(FusedOverfitter(OverfitCfg(), batch, flows_dev, device=dev))
         for _ in range(3):
@@ -365,6 +365,16 @@ def run_gpu(args):
             o3.training_step()
         sparse_ms, _ = time_steps(o3.training_step, min(args.steps, 30))
         del o3
+        # the SAME full workload through the per-module drop-in surface (Model.forward, LossFlow /
+        # LossTracking.forward as autograd Functions, Adam on the kernel): what install() gives the
+        # reference's own training loop, one C-ABI call per op instead of one per step
+        from flowmap_b200.overfit import Overfitter
+        o4 = init_params(Overfitter(OverfitCfg(intrinsics="softmin", use_tracking=True), batch, flows_dev,
+                                    tracks, device=dev))
+        for _ in range(3):
+            o4.training_step()
+        dropin_ms, _ = time_steps(o4.training_step, min(args.steps, 20))
+        del o4
         flows_dev.forward.copy_(flows_host.forward, non_blocking=True)   # o.flows shares these buffers
         flows_dev.backward.copy_(flows_host.backward, non_blocking=True)
 
@@ -495,6 +505,10 @@ def run_gpu(args):
          "ms_per_step_smooth_flows": None if smooth_ms is None else round(smooth_ms, 4),
          "ms_per_step_1000_point_procrustes": None if sparse_ms is None else round(sparse_ms, 4),
          "smooth_flows": "N(0, 0.01^2) flow on a 16x coarser grid, bilinearly upsampled"},
+        "dropin_autograd": None if dropin_ms is None else
+        {"ms_per_step": round(dropin_ms, 4), "it_per_s": round(world * 1000.0 / dropin_ms, 2),
+         "what": "same full workload through Model.forward + LossFlow/LossTracking autograd Functions + "
+                 "kernel Adam (the install() drop-in surface) instead of the one-call fused step"},
         "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(out))
