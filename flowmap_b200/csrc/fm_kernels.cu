@@ -1606,10 +1606,6 @@ __global__ void k_focal_grad(const double* __restrict__ k4acc, const double* __r
   }
 }
 
-__global__ void k_add_scalar(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b) {
-  *dst = *a + (b ? *b : 0.f);
-}
-
 // ---------------------------------------------------------------- launch geometry
 int blocks_for(int n_items_per_row, int vec) {
   // ~4096 items per block keeps thousands of blocks in flight at the BASELINE sizes and
@@ -1647,10 +1643,8 @@ int launch_flow(const float* depth, const float* k4, const float* rt, const floa
     return 0;
   }
   const bool focal = intrinsics_mode == 1;
-  static const bool exp3 = getenv("FM_FLOW_MINB3") != nullptr;  // experiment switch (profiles/README.md)
   if (vec == 4) {
-    if (focal && exp3) k_flow_lean<4, true, 3><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
-    else if (focal) k_flow_lean<4, true, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
+    if (focal) k_flow_lean<4, true, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
     else k_flow_lean<4, false, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
   } else {
     if (focal) k_flow_lean<1, true, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
