@@ -13,6 +13,11 @@ def install() -> dict:
       * ``flowmap.loss.LOSSES["flow"|"tracking"]`` -> flowmap_b200.loss.LossFlow / LossTracking
       * ``flowmap.model.intrinsics.INTRINSICS`` / ``...extrinsics.EXTRINSICS["procrustes"]``
         entries of the pieces that exist here,
+      * ``flowmap.flow.flow_predictor.FlowPredictor.rescale_flow / rescale_mask /
+        compute_consistency_mask`` (static methods; the RAFT / GMFlow subclasses inherit them,
+        so ``compute_bidirectional_flow`` runs on the kernels with the reference's predictor),
+      * ``flowmap.export.colmap.export_to_colmap / write_colmap_model / read_colmap_model``
+        (when that module imports; it needs ``plyfile``),
 
     so that ``flowmap/overfit.py`` (Hydra/Lightning harness) runs unchanged.  Call it before
     ``flowmap.overfit`` is imported.  Backbones that are outside the hot path (MiDaS) keep
@@ -34,6 +39,22 @@ def install() -> dict:
     for key, cls in my_model.INTRINSICS.items():
         replaced[f"flowmap.model.intrinsics.INTRINSICS[{key}]"] = ref_intr.INTRINSICS.get(key)
         ref_intr.INTRINSICS[key] = cls
+    from . import export as my_export
+    from . import flow as my_flow
+    try:
+        ref_flow = importlib.import_module("flowmap.flow.flow_predictor")
+        for name in ("rescale_flow", "rescale_mask", "compute_consistency_mask"):
+            replaced[f"flowmap.flow.flow_predictor.FlowPredictor.{name}"] = getattr(ref_flow.FlowPredictor, name)
+            setattr(ref_flow.FlowPredictor, name, staticmethod(getattr(my_flow, name)))
+    except ImportError:  # torchvision-less environments: the flow side stays with the caller
+        pass
+    try:
+        ref_colmap = importlib.import_module("flowmap.export.colmap")
+        for name in ("export_to_colmap", "write_colmap_model", "read_colmap_model"):
+            replaced[f"flowmap.export.colmap.{name}"] = getattr(ref_colmap, name)
+            setattr(ref_colmap, name, getattr(my_export, name))
+    except ImportError:
+        pass
     ref_back = importlib.import_module("flowmap.model.backbone")
     for key, cls in ref_back.BACKBONES.items():  # e.g. midas: produced by the reference
         my_model.BACKBONES.setdefault(key, cls)

@@ -66,7 +66,10 @@ def test_install_patches_reference_registries():
         "assert names == ['backbone.depth', 'backbone.weights', 'intrinsics.intrinsics_regressed.focal_length'], names\n"
         "from flowmap.loss import get_losses\nfrom flowmap.loss.loss_flow import LossFlowCfg\nfrom flowmap.loss.mapping.mapping_huber import MappingHuberCfg\n"
         "l = get_losses([LossFlowCfg(0, 1000.0, 'flow', MappingHuberCfg('huber', 0.01))])\n"
-        "assert type(l[0]) is LossFlow\n")
+        "assert type(l[0]) is LossFlow\n"
+        "from flowmap.flow.flow_predictor import FlowPredictor\nfrom flowmap_b200 import flow as fl\n"
+        "assert FlowPredictor.rescale_flow is fl.rescale_flow and FlowPredictor.compute_consistency_mask is fl.compute_consistency_mask\n"
+        "assert 'flowmap.flow.flow_predictor.FlowPredictor.rescale_mask' in rep\n")
     import subprocess
     from conftest import ROOT
     subprocess.check_call([sys.executable, "-c", code], cwd=str(ROOT))
