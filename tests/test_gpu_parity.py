@@ -664,3 +664,89 @@ def test_split_step_with_tracking_equals_fused(intrinsics):
         assert abs(float(sh._focal) - float(ref._focal)) <= 1e-6
     finally:
         dist.destroy_process_group()
+
+
+def _tracking_case(tracks64, f=6, h=20, w=28, seed=21):
+    """Fused step (flow + tracking) on `tracks64` against the float64 oracle."""
+    from oracle import flowmap_oracle as O
+    from flowmap_b200.overfit import FusedOverfitter, OverfitCfg
+    from flowmap_b200.types import Batch, Flows, Tracks
+    fl = O.synthetic_flows(f, h, w, seed=seed, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(seed + 1)
+    depth = 1.0 + 0.5 * torch.rand(f, h, w, generator=gen, dtype=torch.float64)
+    wparam = 0.01 * torch.randn(f - 1, h, w, generator=gen, dtype=torch.float64)
+    st = O.OverfitOracle(O.OverfitConfig(intrinsics="regressed", use_tracking=True, tracking_enable_after=0),
+                         f, h, w, dtype=torch.float64)
+    with torch.no_grad():
+        st.depth.copy_(depth)
+        st.weights.copy_(wparam)
+    ref = st.training_step(fl, tracks64)
+    batch = Batch(torch.zeros(1, f, 3, h, w), torch.arange(f)[None], ["s"], ["d"])
+    o = FusedOverfitter(OverfitCfg(use_tracking=True, tracking_enable_after=0), batch,
+                        Flows(*(t.float() for t in (fl.forward, fl.backward, fl.forward_mask, fl.backward_mask))),
+                        [Tracks(t.xy.float(), t.visibility, t.start_frame) for t in tracks64])
+    with torch.no_grad():
+        o.model.backbone.depth.copy_(depth.float())
+        o.model.backbone.weights.copy_(wparam.float())
+    loss, _ = o.training_step(update=False)
+    return float(loss), o.gradients(), float(o._track_loss), ref
+
+
+def test_tracking_edge_cases_vs_oracle():
+    """Ragged / degenerate track segments: a one-frame segment, a point count that is not a multiple
+    of the block size, a segment longer than the usual 41 frames, tracks entirely outside the image
+    or entirely invisible (`valid_sum or 1`, loss_tracking.py:61)."""
+    from oracle import flowmap_oracle as O
+    f = 6
+    gen = torch.Generator().manual_seed(3)
+    mk = lambda rows, n, start, vis_p=0.7, lo=0.0, hi=1.0: O.Tracks(  # noqa: E731
+        lo + (hi - lo) * torch.rand(1, rows, n, 2, generator=gen, dtype=torch.float64),
+        torch.rand(1, rows, n, generator=gen) < vis_p, start)
+    ragged = [mk(1, 37, 2), mk(6, 301, 0), mk(3, 5, 3), mk(2, 1, 4)]
+    loss, gr, _, ref = _tracking_case(ragged)
+    assert abs(loss - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert rel_l2(gr["depth"].cpu(), ref["grads"]["depth"]) <= 2e-4
+    assert rel_l2(gr["weights"].cpu(), ref["grads"]["weights"]) <= 2e-4
+    # nothing valid: every source is outside [0,1)^2, or nothing is visible
+    for dead in ([mk(4, 50, 1, lo=1.5, hi=2.5)], [mk(4, 50, 1, vis_p=-1.0)]):
+        loss, gr, track_loss, ref = _tracking_case(dead)
+        assert track_loss == 0.0 and ref["parts"]["tracking"] == 0.0
+        assert abs(loss - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+        assert bool(torch.isfinite(gr["depth"]).all())
+        assert rel_l2(gr["depth"].cpu(), ref["grads"]["depth"]) <= 1e-4
+
+
+def test_long_track_segment_uses_more_shared_memory():
+    """A 70-frame segment (the default radius gives 41): per-block shared memory grows with the
+    segment length; parity with the oracle must hold."""
+    from oracle import flowmap_oracle as O
+    f = 70
+    gen = torch.Generator().manual_seed(9)
+    seg = O.Tracks(torch.rand(1, f, 64, 2, generator=gen, dtype=torch.float64),
+                   torch.rand(1, f, 64, generator=gen) < 0.7, 0)
+    loss, gr, _, ref = _tracking_case([seg], f=f, h=12, w=16)
+    assert abs(loss - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert rel_l2(gr["depth"].cpu(), ref["grads"]["depth"]) <= 3e-4
+
+
+def test_vanishing_weights_give_identity_poses():
+    """All correspondence weights exactly 0 (float32 sigmoid(100 * -2) underflows): centroids use
+    sum + 1e-8 (procrustes.py:24), the covariance is the zero matrix and the reference's SVD returns
+    U = V = I, i.e. the identity pose; the Jacobi solve must not produce NaN there."""
+    from oracle import flowmap_oracle as O
+    from flowmap_b200 import ops
+    b, f, h, w = 1, 3, 8, 12
+    gen = torch.Generator().manual_seed(1)
+    depth = 1.0 + torch.rand(b, f, h, w, generator=gen)
+    fl = O.synthetic_flows(f, h, w, seed=4)
+    weights = torch.sigmoid(torch.full((b, f - 1, h, w), -200.0))
+    assert float(weights.max()) == 0.0
+    k = O.intrinsics_from_focal(torch.tensor(0.85), h, w).expand(b, f, 3, 3)
+    surf = O.unproject(O.pixel_grid(h, w, torch.float32), depth, k[:, :, None, None])
+    ref = O.relative_poses(surf, fl.backward, weights, torch.arange(h * w))
+    assert max_abs(ref, torch.eye(4).expand_as(ref)) == 0.0
+    s = (h * w) ** 0.5
+    k4 = torch.tensor([0.85 * s / w, 0.85 * s / h, 0.5, 0.5], device="cuda").expand(b, f, 4).contiguous()
+    rt = ops.procrustes_poses(depth.cuda(), weights.cuda(), k4, fl.backward.cuda(), None)
+    assert bool(torch.isfinite(rt).all())
+    assert max_abs(rt.cpu(), ref[..., :3, :]) <= 1e-6
