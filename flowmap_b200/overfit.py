@@ -208,6 +208,24 @@ class FusedOverfitter(Overfitter):
         self._args, self._ctypes = a, ctypes
         self._lib = lib()
 
+    def set_flows(self, flows: Flows, mask_sum: Optional[Tensor] = None):
+        """Point the step at another device-resident Flows of the same shape (the next batch of a
+        prefetching loader) without rebuilding parameters or optimiser state.  `mask_sum` is the
+        flow-loss normaliser (loss_flow.py:70) if the caller already has it."""
+        old = self.flows
+        for name in ("forward", "backward", "forward_mask", "backward_mask"):
+            t = ops._canon(getattr(flows, name), name)
+            if t.shape != getattr(old, name).shape or t.device != getattr(old, name).device:
+                raise ValueError(f"flowmap_b200: `{name}` does not match the optimiser's shapes / device")
+        self.flows = flows
+        a = self._args
+        a.fflow, a.bflow = flows.forward.data_ptr(), flows.backward.data_ptr()
+        a.fmask, a.bmask = flows.forward_mask.data_ptr(), flows.backward_mask.data_ptr()
+        self._msum.copy_(self._mask_sum(flows) if mask_sum is None else mask_sum)
+
+    def _mask_sum(self, flows: Flows) -> Tensor:
+        return ops.mask_sum(flows.forward_mask, flows.backward_mask)
+
     def _softmin_stage(self) -> bool:
         c = self.cfg
         return self._softmin and not (c.regression_after is not None and
@@ -354,6 +372,10 @@ class ShardedFusedOverfitter(FusedOverfitter):
             self._tws = torch.empty(lib().fm_track_workspace_bytes(F, pk.total), dtype=torch.uint8, device=dev)
             self._treduce = self._tws[:lib().fm_track_reduce_bytes(F)].view(torch.float64)
             self._src_range = parallel.source_frame_range(plan)
+
+    def _mask_sum(self, flows: Flows) -> Tensor:
+        from . import parallel
+        return parallel.global_mask_sum(ops.mask_sum(flows.forward_mask, flows.backward_mask), self.group)
 
     def sync_boundary_depth(self):
         """Make the replicas of every shared boundary frame identical (owner = left rank)."""

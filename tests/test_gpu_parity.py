@@ -750,3 +750,24 @@ def test_vanishing_weights_give_identity_poses():
     rt = ops.procrustes_poses(depth.cuda(), weights.cuda(), k4, fl.backward.cuda(), None)
     assert bool(torch.isfinite(rt).all())
     assert max_abs(rt.cpu(), ref[..., :3, :]) <= 1e-6
+
+
+def test_set_flows_switches_the_batch():
+    """FusedOverfitter.set_flows (the next batch of a prefetching loader): same result as an
+    optimiser built on those flows; shape mismatches are rejected."""
+    from oracle import flowmap_oracle as O
+    from flowmap_b200.overfit import FusedOverfitter, OverfitCfg
+    from flowmap_b200.types import Batch, Flows
+    f, h, w = 5, 16, 24
+    mk = lambda seed: Flows(*(t.cuda() for t in (lambda fl: (fl.forward, fl.backward, fl.forward_mask,  # noqa: E731
+                                                             fl.backward_mask))(O.synthetic_flows(f, h, w, seed=seed))))
+    batch = Batch(torch.zeros(1, f, 3, h, w), torch.arange(f)[None], ["s"], ["d"])
+    a, b = mk(1), mk(2)
+    o = FusedOverfitter(OverfitCfg(), batch, a)
+    ref = FusedOverfitter(OverfitCfg(), batch, b)
+    first = float(o.training_step(update=False)[0])
+    o.set_flows(b)
+    assert float(o.training_step(update=False)[0]) == float(ref.training_step(update=False)[0]) != first
+    assert torch.equal(o.gradients()["depth"], ref.gradients()["depth"])
+    with pytest.raises(ValueError):
+        o.set_flows(Flows(b.forward[:, :-1], b.backward[:, :-1], b.forward_mask[:, :-1], b.backward_mask[:, :-1]))
