@@ -767,7 +767,8 @@ def test_set_flows_switches_the_batch():
     ref = FusedOverfitter(OverfitCfg(), batch, b)
     first = float(o.training_step(update=False)[0])
     o.set_flows(b)
-    assert float(o.training_step(update=False)[0]) == float(ref.training_step(update=False)[0]) != first
-    assert torch.equal(o.gradients()["depth"], ref.gradients()["depth"])
+    second, want = float(o.training_step(update=False)[0]), float(ref.training_step(update=False)[0])
+    assert abs(second - want) <= 1e-6 * abs(want) and abs(second - first) > 1e-3 * abs(want)
+    assert rel_l2(o.gradients()["depth"].cpu(), ref.gradients()["depth"].cpu()) <= 1e-6  # atomics: order varies
     with pytest.raises(ValueError):
         o.set_flows(Flows(b.forward[:, :-1], b.backward[:, :-1], b.forward_mask[:, :-1], b.backward_mask[:, :-1]))
