@@ -835,84 +835,176 @@ __global__ void k_reproject(const float* __restrict__ xyz, const float* __restri
   }
 }
 
-// P_0 = I, P_{k+1} = P_k @ T_k in float32 (projection.py:207-209).  One block per batch item:
-// the block stages all [R|t] in shared memory with coalesced loads; the (inherently sequential)
-// recursion runs on 12 lanes of warp 0, lane (r, c) owning element (r, c) of the running 3x4
-// product and fetching the row it needs with warp shuffles (4 FMAs per step per lane instead of
-// 48 serial ones on one thread); then the block writes the result.
-__global__ void k_pose_chain(const float* __restrict__ rt, float* __restrict__ ext, int B, int F) {
-  extern __shared__ float sm[];  // [F-1][12] inputs, then [F][12] outputs
-  const int b = blockIdx.x;
-  const int P = F - 1;
-  float* tin = sm;
-  float* pout = sm + (size_t)P * 12;
-  for (int i = threadIdx.x; i < P * 12; i += blockDim.x) tin[i] = __ldg(rt + (size_t)b * P * 12 + i);
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    const int e = lane < 12 ? lane : 0, r = e >> 2, c = e & 3;
-    float v = (r == c) ? 1.f : 0.f;  // P_0 = I
-    for (int k = 0;; ++k) {
-      if (lane < 12) pout[k * 12 + e] = v;
-      if (k == P) break;
-      const float* T = tin + k * 12;
-      // new[r][c] = sum_m P[r][m] T[m][c] (+ P[r][3] for c == 3)
-      const float p0 = __shfl_sync(0xffffffffu, v, r * 4 + 0), p1 = __shfl_sync(0xffffffffu, v, r * 4 + 1);
-      const float p2 = __shfl_sync(0xffffffffu, v, r * 4 + 2), p3 = __shfl_sync(0xffffffffu, v, r * 4 + 3);
-      float nv = p0 * T[0 * 4 + c] + p1 * T[1 * 4 + c] + p2 * T[2 * 4 + c];
-      if (c == 3) nv += p3;
-      v = nv;
+// ---- pose chain as a parallel scan
+// P_0 = I, P_{k+1} = P_k @ T_k (projection.py:207-209) is a prefix product of rigid [R|t]
+// transforms, an associative operation: one block per batch item, every thread owns a contiguous
+// chunk of pairs, a Hillis-Steele scan over the 256 chunk aggregates in shared memory (8 steps),
+// then each thread walks its chunk from its exclusive prefix.  O(log F) dependent steps instead of
+// F - 1, no limit on F.  (Rounding differs from the sequential product at the 1e-7 level.)
+constexpr int kChainThreads = 256;
+
+struct Rigid { float m[12]; };  // [R | t] row-major 3x4
+
+__device__ __forceinline__ Rigid rigid_identity() {
+  Rigid r;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) r.m[i] = (i == 0 || i == 5 || i == 10) ? 1.f : 0.f;
+  return r;
+}
+__device__ __forceinline__ Rigid rigid_load(const float* p) {  // 48 bytes, 16-byte aligned
+  Rigid r;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1),
+               c = __ldg(reinterpret_cast<const float4*>(p) + 2);
+  r.m[0] = a.x; r.m[1] = a.y; r.m[2] = a.z; r.m[3] = a.w; r.m[4] = b.x; r.m[5] = b.y; r.m[6] = b.z; r.m[7] = b.w;
+  r.m[8] = c.x; r.m[9] = c.y; r.m[10] = c.z; r.m[11] = c.w;
+  return r;
+}
+// A o B = [A_R B_R | A_R B_t + A_t]
+__device__ __forceinline__ Rigid rigid_mul(const Rigid& A, const Rigid& B) {
+  Rigid C;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v = A.m[r * 4 + 0] * B.m[0 * 4 + c] + A.m[r * 4 + 1] * B.m[1 * 4 + c] + A.m[r * 4 + 2] * B.m[2 * 4 + c];
+      if (c == 3) v += A.m[r * 4 + 3];
+      C.m[r * 4 + c] = v;
     }
   }
+  return C;
+}
+// X (3x4, general) times T4^T:  out[r][m] = sum_c X[r][c] T4[m][c], T4 row 3 = (0, 0, 0, 1)
+__device__ __forceinline__ Rigid mul_transposed(const Rigid& X, const Rigid& T) {
+  Rigid o;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+      o.m[r * 4 + m] = X.m[r * 4 + 0] * T.m[m * 4 + 0] + X.m[r * 4 + 1] * T.m[m * 4 + 1] +
+                       X.m[r * 4 + 2] * T.m[m * 4 + 2] + X.m[r * 4 + 3] * T.m[m * 4 + 3];
+    o.m[r * 4 + 3] = X.m[r * 4 + 3];
+  }
+  return o;
+}
+__device__ __forceinline__ void rigid_to_smem(float* dst, const Rigid& r) {
+#pragma unroll
+  for (int i = 0; i < 12; ++i) dst[i * kChainThreads] = r.m[i];  // element-major: conflict-free
+}
+__device__ __forceinline__ Rigid rigid_from_smem(const float* src) {
+  Rigid r;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) r.m[i] = src[i * kChainThreads];
+  return r;
+}
+
+__global__ void __launch_bounds__(kChainThreads)
+k_pose_chain(const float* __restrict__ rt, float* __restrict__ ext, int B, int F) {
+  __shared__ float s_agg[12 * kChainThreads];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int P = F - 1;
+  const int chunk = (P + kChainThreads - 1) / kChainThreads;
+  const int lo = min(t * chunk, P), hi = min(lo + chunk, P);
+  const float* T = rt + (size_t)b * P * 12;
+  Rigid agg = rigid_identity();
+  for (int k = lo; k < hi; ++k) agg = rigid_mul(agg, rigid_load(T + (size_t)k * 12));
+  rigid_to_smem(s_agg + t, agg);
   __syncthreads();
+  for (int off = 1; off < kChainThreads; off <<= 1) {
+    Rigid left;
+    if (t >= off) left = rigid_from_smem(s_agg + t - off);
+    __syncthreads();
+    if (t >= off) { agg = rigid_mul(left, agg); rigid_to_smem(s_agg + t, agg); }
+    __syncthreads();
+  }
+  Rigid run = t > 0 ? rigid_from_smem(s_agg + t - 1) : rigid_identity();  // exclusive prefix = P_lo
   float* o = ext + (size_t)b * F * 16;
-  for (int i = threadIdx.x; i < F * 16; i += blockDim.x) {
-    const int k = i >> 4, e = i & 15;
-    o[i] = e < 12 ? pout[k * 12 + e] : (e == 15 ? 1.f : 0.f);
+  auto store = [o](int k, const Rigid& r) {
+    float4* d = reinterpret_cast<float4*>(o + (size_t)k * 16);
+    d[0] = make_float4(r.m[0], r.m[1], r.m[2], r.m[3]);
+    d[1] = make_float4(r.m[4], r.m[5], r.m[6], r.m[7]);
+    d[2] = make_float4(r.m[8], r.m[9], r.m[10], r.m[11]);
+    d[3] = make_float4(0.f, 0.f, 0.f, 1.f);
+  };
+  if (t == 0) store(0, run);  // P_0 = I
+  for (int k = lo; k < hi; ++k) {
+    run = rigid_mul(run, rigid_load(T + (size_t)k * 12));
+    store(k + 1, run);
   }
 }
 
-// Adjoint of the chain.  With G_k = dL/dP_k (top 3 rows matter; the bottom row is constant):
-// acc_{F-1} = G_{F-1}; dT_k = P_k^T acc_{k+1} (3x4 part); acc_k = G_k + acc_{k+1} T4_k^T.
-// Same staging and lane layout: lane (r, c) owns acc[r][c].
-__global__ void k_pose_chain_bwd(const float* __restrict__ rt, const float* __restrict__ ext,
-                                 const float* __restrict__ g_ext, float* __restrict__ g_rt, int B, int F) {
-  extern __shared__ float sm[];  // T [P][12], P [F][12], G [F][12], out [P][12]
-  const int b = blockIdx.x;
-  const int Pn = F - 1;
-  float* tin = sm;
-  float* pin = tin + (size_t)Pn * 12;
-  float* gin = pin + (size_t)F * 12;
-  float* out = gin + (size_t)F * 12;
-  for (int i = threadIdx.x; i < Pn * 12; i += blockDim.x) tin[i] = __ldg(rt + (size_t)b * Pn * 12 + i);
-  for (int i = threadIdx.x; i < F * 12; i += blockDim.x) {
-    const int k = i / 12, e = i - k * 12;
-    pin[i] = __ldg(ext + ((size_t)b * F + k) * 16 + e);
-    gin[i] = __ldg(g_ext + ((size_t)b * F + k) * 16 + e);
+// Adjoint of the chain.  With G_a = dL/dP_a (top 3 rows; the bottom row is constant):
+//   S_{F-1} = G_{F-1},  S_a = G_a + S_{a+1} T4_a^T,  dT_k = P_k^T S_{k+1} (3x4 part).
+// S_a = f_a(S_{a+1}) with the affine maps f_a(X) = G_a + X T4_a^T, whose composition
+// f_a o f_b (a < b) is the pair (T_a o T_b, G_a + G_b T4_a^T): a reverse (suffix) scan over the
+// elements a = 1 .. F-1, same block layout as the forward chain.
+__global__ void __launch_bounds__(kChainThreads)
+k_pose_chain_bwd(const float* __restrict__ rt, const float* __restrict__ ext,
+                 const float* __restrict__ g_ext, float* __restrict__ g_rt, int B, int F) {
+  __shared__ float s_t[12 * kChainThreads];
+  __shared__ float s_b[12 * kChainThreads];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int n = F - 1;                       // elements j = a - 1 for a = 1 .. F-1
+  const int chunk = (n + kChainThreads - 1) / kChainThreads;
+  const int lo = min(t * chunk, n), hi = min(lo + chunk, n);
+  const float* T = rt + (size_t)b * n * 12;
+  const float* G = g_ext + (size_t)b * F * 16;
+  const float* Pm = ext + (size_t)b * F * 16;
+  // element j: (T_a, G_a) with a = j + 1; the last one (a = F-1) has no T: identity
+  auto elem_t = [T, n](int j) { return j + 1 < n + 0 ? rigid_load(T + (size_t)(j + 1) * 12) : rigid_identity(); };
+  Rigid aggT = rigid_identity(), aggB;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) aggB.m[i] = 0.f;
+  // chunk aggregate: f_lo o ... o f_{hi-1}, built right to left
+  for (int j = hi - 1; j >= lo; --j) {
+    const Rigid tj = elem_t(j), gj = rigid_load(G + (size_t)(j + 1) * 16);
+    const Rigid moved = mul_transposed(aggB, tj);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) aggB.m[i] = gj.m[i] + moved.m[i];
+    aggT = rigid_mul(tj, aggT);
   }
+  rigid_to_smem(s_t + t, aggT);
+  rigid_to_smem(s_b + t, aggB);
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    const int e = lane < 12 ? lane : 0, r = e >> 2, c = e & 3;
-    float acc = gin[(F - 1) * 12 + e];
-    for (int k = F - 2; k >= 0; --k) {
-      const float* Pm = pin + k * 12;
-      const float* T = tin + k * 12;
-      // dT[m][c] = sum_r P_k[r][m] acc[r][c]   (this lane: m = r index of its element, column c)
-      const float a0 = __shfl_sync(0xffffffffu, acc, 0 * 4 + c), a1 = __shfl_sync(0xffffffffu, acc, 1 * 4 + c);
-      const float a2 = __shfl_sync(0xffffffffu, acc, 2 * 4 + c);
-      if (lane < 12) out[k * 12 + e] = Pm[0 * 4 + r] * a0 + Pm[1 * 4 + r] * a1 + Pm[2 * 4 + r] * a2;
-      // acc_k[r][m] = G_k[r][m] + sum_c acc[r][c] T4[m][c], this lane: m = c index of its element
-      const float b0 = __shfl_sync(0xffffffffu, acc, r * 4 + 0), b1 = __shfl_sync(0xffffffffu, acc, r * 4 + 1);
-      const float b2 = __shfl_sync(0xffffffffu, acc, r * 4 + 2), b3 = __shfl_sync(0xffffffffu, acc, r * 4 + 3);
-      float nv = gin[k * 12 + e];
-      if (c < 3) nv += b0 * T[c * 4 + 0] + b1 * T[c * 4 + 1] + b2 * T[c * 4 + 2] + b3 * T[c * 4 + 3];
-      else nv += b3;  // T4 row 3 = (0, 0, 0, 1)
-      acc = nv;
+  for (int off = 1; off < kChainThreads; off <<= 1) {
+    Rigid rT, rB;
+    const bool has = t + off < kChainThreads;
+    if (has) { rT = rigid_from_smem(s_t + t + off); rB = rigid_from_smem(s_b + t + off); }
+    __syncthreads();
+    if (has) {  // (aggT, aggB) o (rT, rB) = (aggT o rT, aggB + rB aggT4^T)
+      const Rigid moved = mul_transposed(rB, aggT);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) aggB.m[i] += moved.m[i];
+      aggT = rigid_mul(aggT, rT);
+      rigid_to_smem(s_t + t, aggT);
+      rigid_to_smem(s_b + t, aggB);
     }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < Pn * 12; i += blockDim.x) g_rt[(size_t)b * Pn * 12 + i] = out[i];
+  // exclusive suffix: S of the first element of the next chunk (0 past the end)
+  Rigid S;
+  if (t + 1 < kChainThreads) S = rigid_from_smem(s_b + t + 1);
+  else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) S.m[i] = 0.f;
+  }
+  float* out = g_rt + (size_t)b * n * 12;
+  for (int j = hi - 1; j >= lo; --j) {
+    const Rigid tj = elem_t(j), gj = rigid_load(G + (size_t)(j + 1) * 16);
+    const Rigid moved = mul_transposed(S, tj);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) S.m[i] = gj.m[i] + moved.m[i];       // S_{j+1}
+    const Rigid Pk = rigid_load(Pm + (size_t)j * 16);                  // P_j, dT_j = P_j^T S_{j+1}
+    float4* d = reinterpret_cast<float4*>(out + (size_t)j * 12);
+    float v[12];
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        v[m * 4 + c] = Pk.m[0 * 4 + m] * S.m[0 * 4 + c] + Pk.m[1 * 4 + m] * S.m[1 * 4 + c] + Pk.m[2 * 4 + m] * S.m[2 * 4 + c];
+    d[0] = make_float4(v[0], v[1], v[2], v[3]);
+    d[1] = make_float4(v[4], v[5], v[6], v[7]);
+    d[2] = make_float4(v[8], v[9], v[10], v[11]);
+  }
 }
 
 // torch.optim.Adam (single-tensor, no amsgrad / weight decay), same operation order.
@@ -1840,10 +1932,7 @@ int fm_flow_loss_fwd_bwd(const float* depth, const float* k4, const float* rt,
 
 int fm_pose_chain(const float* rt, float* extrinsics, int B, int F, void* stream) {
   if (!rt || !extrinsics || B < 1 || F < 2) return fail_msg("fm_pose_chain: bad arguments");
-  const size_t smem = ((size_t)(F - 1) * 12 + (size_t)F * 12) * sizeof(float);
-  if (smem > 200 * 1024) return fail_msg("fm_pose_chain: too many frames for the shared-memory chain");
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_pose_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_pose_chain<<<B, 128, smem, (cudaStream_t)stream>>>(rt, extrinsics, B, F);
+  k_pose_chain<<<B, kChainThreads, 0, (cudaStream_t)stream>>>(rt, extrinsics, B, F);
   FM_CHECK_LAUNCH("fm_pose_chain");
   return 0;
 }
@@ -1851,10 +1940,7 @@ int fm_pose_chain(const float* rt, float* extrinsics, int B, int F, void* stream
 int fm_pose_chain_bwd(const float* rt, const float* extrinsics, const float* g_extrinsics, float* g_rt,
                       int B, int F, void* stream) {
   if (!rt || !extrinsics || !g_extrinsics || !g_rt || B < 1 || F < 2) return fail_msg("fm_pose_chain_bwd: bad arguments");
-  const size_t smem = ((size_t)(F - 1) * 24 + (size_t)F * 24) * sizeof(float);
-  if (smem > 200 * 1024) return fail_msg("fm_pose_chain_bwd: too many frames for the shared-memory chain");
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_pose_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_pose_chain_bwd<<<B, 128, smem, (cudaStream_t)stream>>>(rt, extrinsics, g_extrinsics, g_rt, B, F);
+  k_pose_chain_bwd<<<B, kChainThreads, 0, (cudaStream_t)stream>>>(rt, extrinsics, g_extrinsics, g_rt, B, F);
   FM_CHECK_LAUNCH("fm_pose_chain_bwd");
   return 0;
 }

@@ -772,3 +772,31 @@ def test_set_flows_switches_the_batch():
     assert rel_l2(o.gradients()["depth"].cpu(), ref.gradients()["depth"].cpu()) <= 1e-6  # atomics: order varies
     with pytest.raises(ValueError):
         o.set_flows(Flows(b.forward[:, :-1], b.backward[:, :-1], b.forward_mask[:, :-1], b.backward_mask[:, :-1]))
+
+
+@pytest.mark.parametrize("b,f", [(1, 2), (1, 3), (2, 150), (1, 257), (1, 258), (3, 1200)])
+def test_pose_chain_scan_vs_sequential_float64(b, f):
+    """The chain P_{k+1} = P_k T_k (projection.py:187-210) runs as a parallel scan: values and the
+    adjoint against the sequential float64 product, incl. chunked (> 256 pairs) and batched cases."""
+    from oracle import flowmap_oracle as O
+    from flowmap_b200 import ops
+    gen = torch.Generator().manual_seed(f)
+    # small random rigid motions
+    w = 0.05 * torch.randn(b, f - 1, 3, generator=gen, dtype=torch.float64)
+    K = torch.zeros(b, f - 1, 3, 3, dtype=torch.float64)
+    K[..., 0, 1], K[..., 0, 2], K[..., 1, 0] = -w[..., 2], w[..., 1], w[..., 2]
+    K[..., 1, 2], K[..., 2, 0], K[..., 2, 1] = -w[..., 0], -w[..., 1], w[..., 0]
+    T = torch.eye(4, dtype=torch.float64).repeat(b, f - 1, 1, 1)
+    T[..., :3, :3] = torch.linalg.matrix_exp(K)
+    T[..., :3, 3] = 0.1 * torch.randn(b, f - 1, 3, generator=gen, dtype=torch.float64)
+    T.requires_grad_(True)
+    ref = O.pose_chain(T)
+    gout = torch.randn(b, f, 4, 4, generator=gen, dtype=torch.float64)
+    gout[..., 3, :] = 0
+    ref.backward(gout)
+    rt = T.detach()[..., :3, :].float().cuda().requires_grad_(True)
+    ext = ops.pose_chain(rt)
+    ext.backward(gout.float().cuda())
+    scale = float(ref.detach().abs().max())
+    assert max_abs(ext.detach().cpu(), ref.detach()) <= 2e-6 * max(1.0, scale) * (1 + f / 150)
+    assert rel_l2(rt.grad.cpu(), T.grad[..., :3, :]) <= 1e-5
