@@ -508,7 +508,8 @@ def run_gpu(args):
                    "frames": F_, "height": H_, "width": W_,
                    "parallelism": ("%d independent scenes, one per GPU (BASELINE config 5), no "
                                    "collective" % world) if not pairs_mode else
-                                  ("%d x %d pairs of one video, 1 all-reduce/step of %d bytes"
+                                  ("%d x %d pairs of one video; per step a 2-float all-reduce and one boundary "
+                                   "frame swapped with each neighbour (%d bytes sent per rank)"
                                    % (world, F_ - 1, o.reducer.bytes_per_step())) +
                                   (" + pose gather, tracking-sum all-reduce (F x 10 doubles), focal broadcast"
                                    if pairs_full else ""),

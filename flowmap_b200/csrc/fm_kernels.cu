@@ -2327,7 +2327,7 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
   const bool fuse_w = a->step > 0 && a->weight_logits && !a->indices && W % 4 == 0;
   if (fuse_w) {  // the weight gradient is final inside k_distribute: update the logits there
     af.on = 1; af.m = a->m_weights; af.v = a->v_weights;
-    af.first_pair = defer ? 1 : 0;  // the sweep touches pair 0 only
+    af.first_pair = a->defer_adam == 1 ? 1 : 0;  // 1: the sweep still touches pair 0; 2: every pair is final
     af.beta1 = (float)a->beta1; af.beta2 = (float)a->beta2;
     af.omb1 = (float)(1.0 - a->beta1); af.omb2 = (float)(1.0 - a->beta2); af.eps = (float)a->eps;
     af.step_size = (float)(a->lr / (1.0 - pow(a->beta1, (double)a->step)));

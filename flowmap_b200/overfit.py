@@ -439,10 +439,16 @@ class ShardedFusedOverfitter(FusedOverfitter):
         a.indices = None if self._indices is None else self._indices.data_ptr()
         a.num_indices = 0 if self._indices is None else self._indices.numel()
         a.flow_weight = c.flow_weight if self.global_step >= c.flow_enable_after else 0.0
-        a.tracks, a.step, a.defer_adam = None, 0, 0
         track_on = c.use_tracking and self.global_step >= c.tracking_enable_after
         sweep = self._softmin_stage()
         own_sweep = sweep and p.rank == 0
+        # the weight logits' gradient is rank-local and final inside the step: update them there
+        # (all pairs, or pairs >= 1 on the rank whose sweep still touches pair 0); depth and the
+        # focal length wait for the exchange below
+        fuse_w = update and c.use_correspondence_weights and self._indices is None and w % 4 == 0
+        a.tracks = None
+        a.step = self.global_step + 1 if fuse_w else 0
+        a.defer_adam = (1 if own_sweep else 2) if fuse_w else 0
         if sweep:
             n = c.softmin_candidates
             wl = P(self._wlog) if c.use_correspondence_weights else None
@@ -478,6 +484,7 @@ class ShardedFusedOverfitter(FusedOverfitter):
                 a.phase, a.g_rt = 0, None
             else:
                 check(L.fm_overfit_step(self._ctypes.byref(a), st), "fm_overfit_step")
+        a.step, a.defer_adam = 0, 0
         g_focal = self._g_focal.reshape(())
         if extra_focal is not None and p.rank == 0:  # global value, counted once
             g_focal = g_focal + extra_focal
@@ -498,8 +505,9 @@ class ShardedFusedOverfitter(FusedOverfitter):
             s_ = self.global_step + 1
             stt = self._state
             ops.adam_step(self._depth, self._g_depth, stt[0], stt[1], s_, c.lr)
-            if c.use_correspondence_weights:
-                ops.adam_step(self._wlog, self._g_w, stt[2], stt[3], s_, c.lr)
+            if c.use_correspondence_weights and (not fuse_w or own_sweep):
+                k = 1 if fuse_w else self._wlog.shape[0]  # pair 0 only when the rest was fused
+                ops.adam_step(self._wlog[:k], self._g_w[:k], stt[2][:k], stt[3][:k], s_, c.lr)
             if sweep:
                 if c.regression_after is not None and self.global_step >= c.regression_after - c.regression_window:
                     self.window.append(self._sw_focal[0].clone())

@@ -3,15 +3,15 @@
 The flow loss is pair-local: pair i needs depth frames i and i+1, its own
 weights/flows/masks and the shared focal length.  Rank g therefore owns a contiguous pair
 range [a_g, b_g) and the frames [a_g, b_g]; flows, masks and weights are sharded and
-never move.  Per optimisation step there is exactly ONE collective, an all-reduce (NCCL
-over NVLink/NVSwitch on the B200 box, gloo in the CPU tests) of a small flat buffer:
-
-    [ loss, d(focal), <world-1 boundary depth-gradient frames> ]
+never move.  Per optimisation step there is one exchange (NCCL over NVLink/NVSwitch on the
+B200 box, gloo in the CPU tests): an all-reduce of [loss, d(focal)] and, grouped with it, a
+send/recv of ONE boundary depth-gradient frame with each neighbour (its size does not grow
+with the number of ranks).
 
 A boundary frame (last frame of rank g == first frame of rank g+1) is "later" for a pair
-on rank g and "earlier" for a pair on rank g+1; each side writes its partial gradient
-into the frame's slot, the all-reduce sums them, and both sides then apply the identical
-Adam update to their replica of that frame, so the replicas stay bit-identical without a
+on rank g and "earlier" for a pair on rank g+1; the two ranks swap their partial gradients
+of that frame, each adds the other's to its own (a + b == b + a bit for bit), and both then
+apply the identical Adam update to their replica, so the replicas stay bit-identical without a
 second message.  The reference has no counterpart (its DDP replicas hold the identical
 problem, flowmap/overfit.py:99-103).
 
@@ -120,41 +120,54 @@ def gather_pairs(plan: ShardPlan, local: Tensor, out: Optional[Tensor] = None, g
 
 
 class StepReducer:
-    """The single per-step collective."""
+    """The per-step exchange: one all-reduce of the scalars (loss, d focal) and one grouped
+    send/recv of a boundary depth-gradient frame with each neighbour (0.9 MB at 360x640 per
+    boundary, independent of the world size)."""
 
     def __init__(self, plan: ShardPlan, frame_shape, device, num_scalars: int = 2, group=None):
         self.plan, self.group = plan, group
         self.h, self.w = frame_shape
         self.nscal = num_scalars
-        n_frame = self.h * self.w
-        self.buf = torch.zeros(num_scalars + (plan.world - 1) * n_frame, dtype=torch.float32,
-                               device=device)
-        self.n_frame = n_frame
+        self.scal = torch.zeros(num_scalars, dtype=torch.float32, device=device)
+        mk = lambda: torch.zeros(self.h, self.w, dtype=torch.float32, device=device)  # noqa: E731
+        self.from_left = mk() if plan.has_left else None
+        self.from_right = mk() if plan.has_right else None
+        self.to_left = mk() if plan.has_left else None
+        self.to_right = mk() if plan.has_right else None
 
-    def _slot(self, boundary: int) -> Tensor:
-        """View of the slot of boundary `boundary` (between rank boundary and boundary+1)."""
-        o = self.nscal + boundary * self.n_frame
-        return self.buf[o:o + self.n_frame].view(self.h, self.w)
+    def _peer(self, offset: int) -> int:
+        r = self.plan.rank + offset
+        return r if self.group is None else dist.get_global_rank(self.group, r)
 
     @torch.no_grad()
     def reduce(self, scalars: Tensor, depth_grad: Tensor) -> Tensor:
         """scalars: (num_scalars,) local partials (loss, d focal, ...); depth_grad: this
-        rank's (frames, H, W) gradient, modified in place at the shared boundary frames.
+        rank's (frames, H, W) gradient, modified in place at the shared boundary frames (both
+        owners end up with the same sum: a + b is commutative, the replicas stay bit-identical).
         Returns the globally summed scalars."""
         p = self.plan
-        self.buf.zero_()
-        self.buf[:self.nscal] = scalars
+        self.scal.copy_(scalars)
+        if p.world == 1:
+            return self.scal.clone()
+        ops = []
         if p.has_left:
-            self._slot(p.rank - 1).copy_(depth_grad[0])
+            self.to_left.copy_(depth_grad[0])
+            ops += [dist.P2POp(dist.isend, self.to_left, self._peer(-1), self.group),
+                    dist.P2POp(dist.irecv, self.from_left, self._peer(-1), self.group)]
         if p.has_right:
-            self._slot(p.rank).copy_(depth_grad[-1])
-        if p.world > 1:
-            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
+            self.to_right.copy_(depth_grad[-1])
+            ops += [dist.P2POp(dist.isend, self.to_right, self._peer(+1), self.group),
+                    dist.P2POp(dist.irecv, self.from_right, self._peer(+1), self.group)]
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        dist.all_reduce(self.scal, op=dist.ReduceOp.SUM, group=self.group)
+        for r in reqs:
+            r.wait()
         if p.has_left:
-            depth_grad[0].copy_(self._slot(p.rank - 1))
+            depth_grad[0].add_(self.from_left)
         if p.has_right:
-            depth_grad[-1].copy_(self._slot(p.rank))
-        return self.buf[:self.nscal].clone()
+            depth_grad[-1].add_(self.from_right)
+        return self.scal.clone()
 
     def bytes_per_step(self) -> int:
-        return self.buf.numel() * 4
+        """Bytes this rank sends per step (scalars + one frame per neighbour)."""
+        return 4 * self.nscal + 4 * self.h * self.w * (int(self.plan.has_left) + int(self.plan.has_right))

@@ -259,10 +259,13 @@ typedef struct {
   int focal_step;               /* Adam step number of the focal parameter (0: same as step);
                                    differs after the softmin -> regressed hand-over, where the
                                    focal length first receives a gradient at step after_step */
-  int defer_adam;               /* softmin stage: the sweep's backward (fm_softmin_sweep_bwd) still has to
-                                   add its gradients to depth frames 0/1 and to the weights of pair 0, so
-                                   only the weight logits of pairs >= 1 are updated here (with `step`);
-                                   the caller runs Adam on depth and on pair 0's logits afterwards */
+  int defer_adam;               /* 0: Adam on everything inside the step.  1 (softmin stage): the sweep's
+                                   backward (fm_softmin_sweep_bwd) still has to add its gradients to depth
+                                   frames 0/1 and to the weights of pair 0, so only the weight logits of
+                                   pairs >= 1 are updated here (with `step`); the caller runs Adam on depth
+                                   and on pair 0's logits afterwards.  2 (pair sharding): the weight logits
+                                   of ALL pairs are updated here (their gradient is rank-local and final),
+                                   depth and focal length wait for the caller's collective */
   int phase;                    /* FM_STEP_ALL, or a split step for pair sharding with a tracking loss:
                                    FM_STEP_FORWARD stops after the flow loss (rt, loss, direct depth
                                    gradient, pose-gradient sums in ws); FM_STEP_BACKWARD resumes at the
