@@ -27,10 +27,14 @@ flows = Flows(0.01 * torch.randn(1, F - 1, H, W, 2, generator=g), 0.01 * torch.r
               torch.rand(1, F - 1, H, W, generator=g), torch.rand(1, F - 1, H, W, generator=g))
 
 
-from oracle import flowmap_oracle as O  # noqa: E402  (synthetic tracks only)
 from flowmap_b200.types import Tracks  # noqa: E402
 
-tracks = [Tracks(t.xy, t.visibility, t.start_frame) for t in O.synthetic_tracks(F, n_points=128, interval=4, radius=6, seed=2)]
+# segment layout of flowmap/tracking/__init__.py:49-70 (a segment every 4 frames, radius 6)
+tracks = []
+for mid in range(0, F, 4):
+    lo_f, hi_f = max(0, mid - 6), min(F, mid + 7)
+    tracks.append(Tracks(torch.rand(1, hi_f - lo_f, 128, 2, generator=g),
+                         torch.rand(1, hi_f - lo_f, 128, generator=g) < 0.7, lo_f))
 idx = torch.randperm(H * W, generator=g)[:512].to(dev)
 
 
