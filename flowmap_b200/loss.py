@@ -4,13 +4,13 @@ from __future__ import annotations
 
 import weakref
 from dataclasses import dataclass
-from typing import Literal, Optional
+from typing import Literal
 
 import torch
 from torch import Tensor, nn
 
 from . import ops
-from .types import Batch, Flows, ModelOutput
+from .types import Flows
 
 
 @dataclass

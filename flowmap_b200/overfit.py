@@ -4,8 +4,8 @@ sum of losses -> backward -> Adam), without the Lightning/Hydra shell.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import Optional, Sequence
+from dataclasses import dataclass
+from typing import Optional
 
 import torch
 from torch import Tensor

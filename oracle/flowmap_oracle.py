@@ -26,7 +26,7 @@ softmin (intrinsics_softmin.py:129) and optim.Adam (model_wrapper_overfit.py:105
 
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional, Sequence
 
 import torch
