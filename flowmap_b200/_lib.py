@@ -48,7 +48,7 @@ SIGNATURES = {
     "fm_track_reduce_bytes": (c_size_t, [c_int]),
     "fm_track_loss_fwd_sharded": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, ctypes.c_longlong,
                                           c_int, c_float, c_float, _P, _P, c_int, c_int, c_int, c_int, c_int,
-                                          c_int, _P]),
+                                          c_int, c_int, _P]),
     "fm_track_loss_value": (c_int, [_P, c_float, _P, _P]),
     "fm_track_loss_bwd_sharded": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, ctypes.c_longlong,
                                           c_int, c_float, c_float, _P, _P, _P, _P, _P, c_int, c_int, c_int,

@@ -1141,16 +1141,32 @@ __device__ __forceinline__ bool track_term_lean(const float* rec, const float* X
   return true;
 }
 
-// Warp sum of 10 per-lane values by recursive halving: 12 shuffles instead of 50.  Afterwards
-// lane l holds the total of value track_slot(l) (lanes 2k and 2k+1 hold the same total).
+// Warp sum of N per-lane values by recursive halving (N = 10: 12 shuffles instead of 50; N = 6:
+// 8 instead of 30).  Afterwards lane l holds the total of value track_slot<N>(l).slot in v[0];
+// `owner` marks one lane per value.
 struct TrackSlot { int slot; bool owner; };
+template <int N, int OFF>
+struct SlotWalk {
+  __device__ __forceinline__ static void run(int lane, int& pos, bool& ok) {
+    if (N == 1) {
+      SlotWalk<1, OFF / 2>::run(lane, pos, ok);
+      ok = ok && (lane & OFF) == 0;
+    } else {
+      constexpr int HALF = (N + 1) / 2;
+      SlotWalk<HALF, OFF / 2>::run(lane, pos, ok);  // position among the HALF survivors
+      if (lane & OFF) pos += HALF;
+      ok = ok && pos < N;
+    }
+  }
+};
+template <int N>
+struct SlotWalk<N, 0> {
+  __device__ __forceinline__ static void run(int, int& pos, bool& ok) { pos = 0; ok = true; }
+};
+template <int N>
 __device__ __forceinline__ TrackSlot track_slot(int lane) {
-  const int i4 = (lane >> 1) & 1;
-  const int i3 = ((lane >> 2) & 1) * 2 + i4;
-  const int i2 = ((lane >> 3) & 1) * 3 + i3;
   TrackSlot t;
-  t.slot = ((lane >> 4) & 1) * 5 + i2;
-  t.owner = i3 < 3 && i2 < 5 && (lane & 1) == 0;
+  SlotWalk<N, 16>::run(lane, t.slot, t.owner);
   return t;
 }
 template <int N, int OFF>
@@ -1164,12 +1180,26 @@ __device__ __forceinline__ void halve_exchange(float* v, bool upper) {
     v[j] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
   }
 }
-__device__ __forceinline__ float warp_sum10(float* v, int lane) {
-  halve_exchange<10, 16>(v, lane & 16);
-  halve_exchange<5, 8>(v, lane & 8);
-  halve_exchange<3, 4>(v, lane & 4);
-  halve_exchange<2, 2>(v, lane & 2);
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+template <int N, int OFF>
+struct WarpSumN {
+  __device__ __forceinline__ static void run(float* v, int lane) {
+    if (N == 1) {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], OFF);
+      WarpSumN<1, OFF / 2>::run(v, lane);
+    } else {
+      halve_exchange<N, OFF>(v, lane & OFF);
+      WarpSumN<(N + 1) / 2, OFF / 2>::run(v, lane);
+    }
+  }
+};
+template <int N>
+struct WarpSumN<N, 0> {
+  __device__ __forceinline__ static void run(float*, int) {}
+};
+template <int N>
+__device__ __forceinline__ float warp_sum_n(float* v, int lane) {
+  WarpSumN<N, 16>::run(v, lane);
+  return v[0];
 }
 
 // One sweep over the (source row, target row, point) triples.  A block owns (segment, source
@@ -1177,6 +1207,10 @@ __device__ __forceinline__ float warp_sum10(float* v, int lane) {
 // target-side sums (pose twist and K of the TARGET frame) of one loop iteration belong to one
 // frame for the whole block, so each warp reduces them with warp_sum10 into its own
 // [target row][10] slice of shared memory, folded into the per-frame accumulators at the end.
+// SHARED_K: every frame has the same intrinsics (one focal length, or constants), so only the SUM
+// over frames of the intrinsics gradient matters: the target-frame terms are then added to the
+// thread's own (source-frame) accumulators and only the 6 pose values go through the reduction.
+template <bool SHARED_K>
 __global__ void __launch_bounds__(kThreads)
 k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const float* __restrict__ ext,
             const int* __restrict__ seg, const float* __restrict__ txy,
@@ -1226,7 +1260,10 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
         Xw[i] = fm_fma(rs[i * 3 + 0], q[0], fm_fma(rs[i * 3 + 1], q[1], fm_fma(rs[i * 3 + 2], q[2], rs[9 + i])));
     }
     float G[3] = {0.f, 0.f, 0.f};
-    const TrackSlot slot = track_slot(lane);
+    float kt[4] = {0.f, 0.f, 0.f, 0.f};  // SHARED_K: intrinsics terms of the targets
+    constexpr int NRED = SHARED_K ? 6 : kTrackAcc;
+    constexpr int SLOT0 = kTrackAcc - NRED;  // twist values live in slots 4..9 either way
+    const TrackSlot slot = track_slot<NRED>(lane);
     float* tgt = s_tgt + (size_t)warp * si.rows * kTrackAcc;
     // the next target row's visibility / position is fetched while the current one is processed
     size_t tidx_n = (size_t)si.sample_start + p;
@@ -1240,9 +1277,9 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
         vis_n = tvis[tidx_n];
         gxy_n = __ldg(reinterpret_cast<const float2*>(txy) + tidx_n);
       }
-      float c[kTrackAcc];
+      float c[NRED];
 #pragma unroll
-      for (int i = 0; i < kTrackAcc; ++i) c[i] = 0.f;
+      for (int i = 0; i < NRED; ++i) c[i] = 0.f;
       bool ok = false;
       if (vis_t) {
         const float* rec = sm + ft * kTrackRec;
@@ -1255,17 +1292,20 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
           G[0] += g[0]; G[1] += g[1]; G[2] += g[2];
           // target-frame K gradient: duv = d (P_z + eps) / f and uv - c = f P / (P_z + eps)
           const float ex = lt.d0 * rec[19], ey = lt.d1 * rec[20];
-          c[0] = ex * lt.P0; c[1] = ey * lt.P1; c[2] = ex * lt.P2; c[3] = ey * lt.P2;
+          float* kd = SHARED_K ? kt : c;
+          if (SHARED_K) { kd[0] = fm_fma(ex, lt.P0, kd[0]); kd[1] = fm_fma(ey, lt.P1, kd[1]); kd[2] = fm_fma(ex, lt.P2, kd[2]); kd[3] = fm_fma(ey, lt.P2, kd[3]); }
+          else { kd[0] = ex * lt.P0; kd[1] = ey * lt.P1; kd[2] = ex * lt.P2; kd[3] = ey * lt.P2; }
+          float* tw = c + (SHARED_K ? 0 : 4);
           const float d0 = Xw[0] - rec[9], d1 = Xw[1] - rec[10], d2 = Xw[2] - rec[11];
-          c[4] = d2 * g[1] - d1 * g[2];
-          c[5] = d0 * g[2] - d2 * g[0];
-          c[6] = d1 * g[0] - d0 * g[1];
-          c[7] = -g[0]; c[8] = -g[1]; c[9] = -g[2];
+          tw[0] = d2 * g[1] - d1 * g[2];
+          tw[1] = d0 * g[2] - d2 * g[0];
+          tw[2] = d1 * g[0] - d0 * g[1];
+          tw[3] = -g[0]; tw[4] = -g[1]; tw[5] = -g[2];
         }
       }
       float total = 0.f;
-      if (__ballot_sync(0xffffffffu, ok)) total = warp_sum10(c, lane);
-      if (slot.owner) tgt[ft * kTrackAcc + slot.slot] = total;
+      if (__ballot_sync(0xffffffffu, ok)) total = warp_sum_n<NRED>(c, lane);
+      if (slot.owner) tgt[ft * kTrackAcc + SLOT0 + slot.slot] = total;
     }
     if (live) {
       // camera-space adjoint of the sampled point (unscaled), source K / twist sums
@@ -1274,7 +1314,7 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
       const float dq2 = fm_fma(rs[2], G[0], fm_fma(rs[5], G[1], rs[8] * G[2]));
       dq_out[sidx * 3 + 0] = dq0; dq_out[sidx * 3 + 1] = dq1; dq_out[sidx * 3 + 2] = dq2;
       const float e0 = dq0 * ks.ifx, e1 = dq1 * ks.ify;
-      acc[0] = -e0 * q[0]; acc[1] = -e1 * q[1]; acc[2] = -e0 * q[2]; acc[3] = -e1 * q[2];
+      acc[0] = kt[0] - e0 * q[0]; acc[1] = kt[1] - e1 * q[1]; acc[2] = kt[2] - e0 * q[2]; acc[3] = kt[3] - e1 * q[2];
       const float c0 = Xw[0] - rs[9], c1 = Xw[1] - rs[10], c2 = Xw[2] - rs[11];
       acc[4] = c1 * G[2] - c2 * G[1];
       acc[5] = c2 * G[0] - c0 * G[2];
@@ -1288,6 +1328,7 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
   // with a barrier, so every slice is complete)
   const int live_warps = (count + 31) >> 5;
   for (int i = threadIdx.x; i < si.rows * kTrackAcc; i += kThreads) {
+    if (SHARED_K && i % kTrackAcc < 4) continue;  // those slots are not written in this mode
     double t = 0.0;
     for (int w = 0; w < live_warps; ++w) t += (double)s_tgt[(size_t)w * si.rows * kTrackAcc + i];
     if (t != 0.0) atomicAdd(trackacc + (size_t)si.start_frame * kTrackAcc + i, t);
@@ -1993,7 +2034,7 @@ int fm_track_loss_fwd_sharded(const float* depth, const float* k4, const float* 
                               int num_segments, int max_rows, int max_points, const float* track_xy,
                               const unsigned char* track_vis, long long total_samples, int mapping, float delta,
                               float loss_weight, float* loss, void* ws, int F, int H, int W, int depth_frame0,
-                              int src_frame_lo, int src_frame_hi, void* stream) {
+                              int src_frame_lo, int src_frame_hi, int shared_intrinsics, void* stream) {
   if (!depth || !k4 || !extrinsics || !segments || !track_xy || !track_vis || !ws ||
       num_segments < 1 || max_rows < 1 || max_points < 1 || F < 1)
     return fail_msg("fm_track_loss_fwd: bad arguments");
@@ -2008,12 +2049,18 @@ int fm_track_loss_fwd_sharded(const float* depth, const float* k4, const float* 
   const size_t smem = (size_t)max_rows * (kTrackRec + (kThreads / 32) * kTrackAcc) * sizeof(float);
   if (smem > 200 * 1024) return fail_msg("fm_track_loss_fwd: segment too long for shared memory");
   if (smem > 48 * 1024) {
-    cudaError_t ea = cudaFuncSetAttribute(k_track_src, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ea = shared_intrinsics
+        ? cudaFuncSetAttribute(k_track_src<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        : cudaFuncSetAttribute(k_track_src<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ea != cudaSuccess) return fail("fm_track_loss_fwd: shared memory", ea);
   }
   const TrackShard sh = {depth_frame0, src_frame_lo, src_frame_hi};
-  k_track_src<<<grid, kThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis, mapping,
-                                          delta, w.sums, w.flag, w.dq, w.acc, H, W, sh);
+  if (shared_intrinsics)
+    k_track_src<true><<<grid, kThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis, mapping,
+                                                  delta, w.sums, w.flag, w.dq, w.acc, H, W, sh);
+  else
+    k_track_src<false><<<grid, kThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis, mapping,
+                                                   delta, w.sums, w.flag, w.dq, w.acc, H, W, sh);
   FM_CHECK_LAUNCH("fm_track_loss_fwd: k_track_src");
   if (loss) {
     k_track_loss<<<1, 1, 0, s>>>(w.sums, loss_weight, loss);
@@ -2029,7 +2076,7 @@ int fm_track_loss_fwd(const float* depth, const float* k4, const float* extrinsi
   if (!loss) return fail_msg("fm_track_loss_fwd: bad arguments");
   return fm_track_loss_fwd_sharded(depth, k4, extrinsics, segments, num_segments, max_rows, max_points, track_xy,
                                    track_vis, total_samples, mapping, delta, loss_weight, loss, ws, F, H, W, 0,
-                                   0, F, stream);
+                                   0, F, 0, stream);
 }
 
 int fm_track_loss_value(const void* ws, float loss_weight, float* loss, void* stream) {
@@ -2303,9 +2350,11 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
   if (a->tracks) {
     const fm_packed_tracks* t = a->tracks;
     if ((rc = fm_pose_chain(a->rt, a->extrinsics, 1, F, stream))) return rc;
-    if ((rc = fm_track_loss_fwd(a->depth, k4, a->extrinsics, t->segments, t->num_segments, t->max_rows,
-                                t->max_points, t->xy, t->vis, t->total_samples, a->mapping, a->delta,
-                                a->track_weight, a->track_loss, a->track_ws, F, H, W, stream)))
+    // one focal length (or constant intrinsics) for all frames: only the summed K gradient is used
+    if ((rc = fm_track_loss_fwd_sharded(a->depth, k4, a->extrinsics, t->segments, t->num_segments, t->max_rows,
+                                        t->max_points, t->xy, t->vis, t->total_samples, a->mapping, a->delta,
+                                        a->track_weight, a->track_loss, a->track_ws, F, H, W, 0, 0, F, 1,
+                                        stream)))
       return rc;
     if ((rc = fm_track_loss_bwd(a->depth, k4, a->extrinsics, t->segments, t->num_segments, t->max_rows,
                                 t->max_points, t->xy, t->vis, t->total_samples, a->mapping, a->delta,

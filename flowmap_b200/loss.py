@@ -136,8 +136,11 @@ class LossTracking(Loss):
         if k4 is None:
             k4 = ops.intrinsics_to_k4(out.intrinsics)
         m = self.cfg.mapping
+        # one focal length behind all frames (or constant K): autograd sums d/dk4 over the frames
+        # anyway, so the kernel may book the intrinsics terms on any frame
+        shared_k = getattr(out, "k_mode", "full") in ("shared_focal", "const")
         return ops.track_loss(out.depths, out.extrinsics, k4, self._pack(tracks, out.depths.device),
-                              m.name, getattr(m, "delta", 0.0), self.cfg.weight)
+                              m.name, getattr(m, "delta", 0.0), self.cfg.weight, shared_k)
 
 
 LOSSES = {"flow": LossFlow, "tracking": LossTracking}

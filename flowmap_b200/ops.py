@@ -337,7 +337,7 @@ class _TrackLoss(torch.autograd.Function):
     flowmap/loss/loss_tracking.py:28-61 + flowmap/model/projection.py:255-298."""
 
     @staticmethod
-    def forward(ctx, depths, extrinsics, k4, packed, mapping, delta, weight):
+    def forward(ctx, depths, extrinsics, k4, packed, mapping, delta, weight, shared_k=False):
         depths, extrinsics, k4 = _canon(depths, "depths"), _canon(extrinsics, "extrinsics"), _canon(k4, "k4")
         B, F, H, W = depths.shape
         if B != 1 or extrinsics.shape != (1, F, 4, 4) or k4.shape != (1, F, 4):
@@ -349,11 +349,12 @@ class _TrackLoss(torch.autograd.Function):
         ws = torch.empty(n, dtype=torch.uint8, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            check(lib().fm_track_loss_fwd(_ptr(depths), _ptr(k4), _ptr(extrinsics), _ptr(packed.seg),
-                                          packed.num_segments, packed.max_rows, packed.max_points,
-                                          _ptr(packed.xy), _ptr(packed.vis), packed.total,
-                                          MAPPINGS[mapping], float(delta), float(weight), _ptr(loss),
-                                          _ptr(ws), F, H, W, _stream()), "fm_track_loss_fwd")
+            check(lib().fm_track_loss_fwd_sharded(_ptr(depths), _ptr(k4), _ptr(extrinsics), _ptr(packed.seg),
+                                                  packed.num_segments, packed.max_rows, packed.max_points,
+                                                  _ptr(packed.xy), _ptr(packed.vis), packed.total,
+                                                  MAPPINGS[mapping], float(delta), float(weight), _ptr(loss),
+                                                  _ptr(ws), F, H, W, 0, 0, F, int(bool(shared_k)), _stream()),
+                  "fm_track_loss_fwd")
         ctx.save_for_backward(depths, extrinsics, k4, ws)
         ctx.packed, ctx.cfg = packed, (mapping, delta, weight)
         return loss
@@ -374,12 +375,15 @@ class _TrackLoss(torch.autograd.Function):
                                           MAPPINGS[mapping], float(delta), float(weight), _ptr(go),
                                           _ptr(g_depth), _ptr(g_ext), _ptr(g_k4), _ptr(ws), F, H, W,
                                           _stream()), "fm_track_loss_bwd")
-        return g_depth, g_ext, g_k4, None, None, None, None
+        return g_depth, g_ext, g_k4, None, None, None, None, None
 
 
 def track_loss(depths, extrinsics, k4, packed: PackedTracks, mapping="huber", delta=0.01,
-               weight=1.0) -> Tensor:
-    return _TrackLoss.apply(depths, extrinsics, k4, packed, mapping, delta, weight)
+               weight=1.0, shared_k: bool = False) -> Tensor:
+    """shared_k: all frames share their intrinsics (k4 derives from one focal length or is constant)
+    and the caller only uses the sum over frames of d loss / d k4 (true when k4 is an expand of one
+    row): lets the kernel skip the per-target-frame reduction of the intrinsics terms."""
+    return _TrackLoss.apply(depths, extrinsics, k4, packed, mapping, delta, weight, shared_k)
 
 
 def candidate_k4(candidates: Tensor, h: int, w: int, batch: int) -> Tensor:

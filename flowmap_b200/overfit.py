@@ -407,17 +407,17 @@ class ShardedFusedOverfitter(FusedOverfitter):
         k4_all = self._k4[0].expand(F, 4).contiguous()  # one shared focal length
         args = (P(k4_all), P(self._ext_all), P(pk.seg), pk.num_segments, pk.max_rows, pk.max_points, P(pk.xy),
                 P(pk.vis), pk.total, ops.MAPPINGS[c.mapping], c.delta, c.tracking_weight)
-        tail = (F, h, w, a0, self._src_range[0], self._src_range[1], st)
+        tail = (F, h, w, a0, self._src_range[0], self._src_range[1])
         with torch.cuda.device(self.rt.device):
             check(L.fm_pose_chain(P(self._rt_all), P(self._ext_all), 1, F, st), "fm_pose_chain")
-            check(L.fm_track_loss_fwd_sharded(P(self._depth), *args, None, P(self._tws), *tail),
-                  "fm_track_loss_fwd_sharded")
+            check(L.fm_track_loss_fwd_sharded(P(self._depth), *args, None, P(self._tws), *tail, 1, st),
+                  "fm_track_loss_fwd_sharded")  # shared focal: only the summed K gradient is used
             if self.plan.world > 1:
                 dist.all_reduce(self._treduce, group=self.group)
             check(L.fm_track_loss_value(P(self._tws), c.tracking_weight, P(self._track_loss), st),
                   "fm_track_loss_value")
             check(L.fm_track_loss_bwd_sharded(P(self._depth), *args, None, P(self._g_depth), P(self._g_ext_all),
-                                              P(self._tg_k4_all), P(self._tws), *tail),
+                                              P(self._tg_k4_all), P(self._tws), *tail, st),
                   "fm_track_loss_bwd_sharded")
             check(L.fm_pose_chain_bwd(P(self._rt_all), P(self._ext_all), P(self._g_ext_all),
                                       P(self._g_rt_all), 1, F, st), "fm_pose_chain_bwd")

@@ -164,13 +164,18 @@ int fm_track_loss_bwd(const float* depth, const float* k4, const float* extrinsi
  * float64) the first fm_track_reduce_bytes(F) bytes of `ws` (loss sum, valid count, per-frame
  * pose / intrinsics sums); fm_track_loss_value then gives the global loss, and the backward's
  * g_extrinsics / g_k4 are the global gradients on every rank while g_depth receives this rank's
- * source frames.  loss may be NULL in the sharded forward. */
+ * source frames.  loss may be NULL in the sharded forward.
+ * shared_intrinsics != 0: the caller guarantees that all frames share one set of intrinsics (one
+ * focal length parameter, or constants) and only uses the SUM over frames of g_k4; the per-frame
+ * split of g_k4 is then unspecified (the target-frame terms are booked on the source frame, which
+ * takes 4 of the 10 values out of the per-row warp reduction).  depth_frame0 = 0, range [0, F) and
+ * shared_intrinsics = 0 is exactly fm_track_loss_fwd. */
 size_t fm_track_reduce_bytes(int F);
 int fm_track_loss_fwd_sharded(const float* depth, const float* k4, const float* extrinsics, const int* segments,
                               int num_segments, int max_rows, int max_points, const float* track_xy,
                               const unsigned char* track_vis, long long total_samples, int mapping, float delta,
                               float loss_weight, float* loss, void* ws, int F, int H, int W, int depth_frame0,
-                              int src_frame_lo, int src_frame_hi, void* stream);
+                              int src_frame_lo, int src_frame_hi, int shared_intrinsics, void* stream);
 int fm_track_loss_value(const void* ws, float loss_weight, float* loss, void* stream);
 int fm_track_loss_bwd_sharded(const float* depth, const float* k4, const float* extrinsics, const int* segments,
                               int num_segments, int max_rows, int max_points, const float* track_xy,

@@ -800,3 +800,65 @@ def test_pose_chain_scan_vs_sequential_float64(b, f):
     scale = float(ref.detach().abs().max())
     assert max_abs(ext.detach().cpu(), ref.detach()) <= 2e-6 * max(1.0, scale) * (1 + f / 150)
     assert rel_l2(rt.grad.cpu(), T.grad[..., :3, :]) <= 1e-5
+
+
+def test_tracking_per_frame_intrinsics_gradient_and_shared_mode():
+    """Tracking loss with PER-FRAME intrinsics (different k4 rows): d loss / d k4 per frame against the
+    float64 oracle (general kernel variant); and the shared-intrinsics variant must give the same
+    depth / pose gradients and the same SUM over frames of the intrinsics gradient."""
+    from oracle import flowmap_oracle as O
+    from flowmap_b200 import ops
+    f, h, w = 6, 20, 28
+    gen = torch.Generator().manual_seed(13)
+    depth = (1.0 + 0.5 * torch.rand(1, f, h, w, generator=gen, dtype=torch.float64)).requires_grad_(True)
+    # poses: small motions; intrinsics: a different focal per frame
+    wv = 0.03 * torch.randn(f, 3, generator=gen, dtype=torch.float64)
+    K = torch.zeros(f, 3, 3, dtype=torch.float64)
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -wv[:, 2], wv[:, 1], wv[:, 2], -wv[:, 0], -wv[:, 1], wv[:, 0]
+    ext = torch.eye(4, dtype=torch.float64).repeat(1, f, 1, 1)
+    ext[0, :, :3, :3] = torch.linalg.matrix_exp(K)
+    ext[0, :, :3, 3] = 0.05 * torch.randn(f, 3, generator=gen, dtype=torch.float64)
+    ext.requires_grad_(True)
+    focal = (0.8 + 0.1 * torch.rand(f, generator=gen, dtype=torch.float64)).requires_grad_(True)
+    s = (h * w) ** 0.5
+    half = torch.full_like(focal, 0.5)
+    k4 = torch.stack((focal * s / w, focal * s / h, half, half), dim=-1)[None]
+    kmat_rows = []
+    for i in range(f):
+        kmat_rows.append(torch.stack((torch.stack((k4[0, i, 0], torch.zeros((), dtype=torch.float64), k4[0, i, 2])),
+                                      torch.stack((torch.zeros((), dtype=torch.float64), k4[0, i, 1], k4[0, i, 3])),
+                                      torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64))))
+    kmat = torch.stack(kmat_rows)[None]
+    tracks = [O.Tracks(torch.rand(1, f, 90, 2, generator=gen, dtype=torch.float64),
+                       torch.rand(1, f, 90, generator=gen) < 0.8, 0),
+              O.Tracks(torch.rand(1, 3, 33, 2, generator=gen, dtype=torch.float64),
+                       torch.rand(1, 3, 33, generator=gen) < 0.8, 2)]
+    surf = O.unproject(O.pixel_grid(h, w, torch.float64), depth, kmat[:, :, None, None])
+    ref = 100.0 * O.tracking_loss(surf, ext, kmat, tracks)
+    ref.backward()
+    from flowmap_b200.types import Tracks
+    packed = ops.PackedTracks([Tracks(t.xy.float().cuda(), t.visibility.cuda(), t.start_frame) for t in tracks], "cuda")
+    out = {}
+    for shared in (False, True):
+        d = depth.detach().float().cuda().requires_grad_(True)
+        e = ext.detach().float().cuda().requires_grad_(True)
+        k = k4.detach().float().cuda().requires_grad_(True)
+        loss = ops.track_loss(d, e, k, packed, "huber", 0.01, 100.0, shared)
+        loss.backward()
+        out[shared] = (float(loss), d.grad.cpu(), e.grad.cpu(), k.grad.cpu())
+    g_focal_frames = focal.grad  # per-frame d loss / d focal_i
+    rot = ext.detach()[0, :, :3, :3]
+
+    def twist(g):  # left-perturbation twist of an ambient pose gradient: omega = sum_c R_c x G_c, v = G_t
+        om = torch.linalg.cross(rot.transpose(-1, -2), g[0, :, :3, :3].transpose(-1, -2), dim=-1).sum(dim=-2)
+        return torch.cat((om, g[0, :, :3, 3]), dim=-1)
+
+    for shared in (False, True):
+        loss, gd, ge, gk = out[shared]
+        assert abs(loss - float(ref)) <= 1e-4 * abs(float(ref))
+        assert rel_l2(gd, depth.grad) <= 2e-4
+        assert rel_l2(twist(ge.double()), twist(ext.grad)) <= 2e-4   # only the tangent part is defined
+    per_frame = out[False][3][0, :, 0].double() * s / w + out[False][3][0, :, 1].double() * s / h
+    assert rel_l2(per_frame, g_focal_frames) <= 2e-4
+    total = lambda gk: float((gk[0, :, 0].double() * s / w + gk[0, :, 1].double() * s / h).sum())  # noqa: E731
+    assert abs(total(out[True][3]) - float(g_focal_frames.sum())) <= 2e-4 * float(g_focal_frames.abs().sum())
