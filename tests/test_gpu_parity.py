@@ -862,3 +862,39 @@ def test_tracking_per_frame_intrinsics_gradient_and_shared_mode():
     assert rel_l2(per_frame, g_focal_frames) <= 2e-4
     total = lambda gk: float((gk[0, :, 0].double() * s / w + gk[0, :, 1].double() * s / h).sum())  # noqa: E731
     assert abs(total(out[True][3]) - float(g_focal_frames.sum())) <= 2e-4 * float(g_focal_frames.abs().sum())
+
+
+@pytest.mark.parametrize("w,npts", [(22, None), (26, 100), (24, 100)])
+def test_fused_trajectory_odd_width_and_subsampled_procrustes(w, npts):
+    """Fused step with Adam on the code paths the BASELINE shape never takes: a width that is not a
+    multiple of 4 (scalar kernel instantiations, separate weight Adam) and / or subsampled Procrustes
+    points (sparse weight gradient), with the tracking loss, over 4 Adam steps against the float64
+    oracle trajectory."""
+    from oracle import flowmap_oracle as O
+    from flowmap_b200.overfit import FusedOverfitter, OverfitCfg
+    from flowmap_b200.types import Batch, Flows, Tracks
+    f, h = 5, 18
+    fl = O.synthetic_flows(f, h, w, seed=w, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(w + 1)
+    depth = 1.0 + 0.5 * torch.rand(f, h, w, generator=gen, dtype=torch.float64)
+    wparam = 0.01 * torch.randn(f - 1, h, w, generator=gen, dtype=torch.float64)
+    trk = O.synthetic_tracks(f, n_points=70, interval=2, radius=2, seed=5, dtype=torch.float64)
+    kw = dict(use_tracking=True, tracking_enable_after=1, procrustes_points=npts)
+    st = O.OverfitOracle(O.OverfitConfig(intrinsics="regressed", lr=1e-3, **kw), f, h, w, dtype=torch.float64)
+    with torch.no_grad():
+        st.depth.copy_(depth)
+        st.weights.copy_(wparam)
+    batch = Batch(torch.zeros(1, f, 3, h, w), torch.arange(f)[None], ["s"], ["d"])
+    o = FusedOverfitter(OverfitCfg(lr=1e-3, **kw), batch,
+                        Flows(*(t.float() for t in (fl.forward, fl.backward, fl.forward_mask, fl.backward_mask))),
+                        [Tracks(t.xy.float(), t.visibility, t.start_frame) for t in trk])
+    with torch.no_grad():
+        o.model.backbone.depth.copy_(depth.float())
+        o.model.backbone.weights.copy_(wparam.float())
+    for step in range(4):
+        ref = st.training_step(fl, trk)
+        loss, _ = o.training_step()
+        assert abs(float(loss) - ref["loss"]) <= 2e-4 * abs(ref["loss"]), step
+    assert rel_l2(o.model.backbone.depth.detach().cpu(), st.depth.detach()) <= 1e-5
+    assert rel_l2(o.model.backbone.weights.detach().cpu().double() - wparam, st.weights.detach() - wparam) <= 2e-2
+    assert abs(float(o._focal) - float(st.focal)) <= 1e-5
