@@ -1050,7 +1050,8 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
 //                   location, lift to world space, loop over the segment's target rows:
 //                   loss sum + valid count, the unscaled camera-space adjoint of the sampled
 //                   point (stored per sample), source-frame K / pose-twist sums in registers,
-//                   target-frame K / pose-twist sums by a 12-shuffle warp reduction per row.
+//                   target-frame K / pose-twist sums by a recursive-halving warp reduction per
+//                   row (10 values / 12 shuffles; 6 / 8 when all frames share their intrinsics).
 //   k_track_apply   (backward) per sample: scale * adjoint -> bilinear scatter into the depth
 //                   gradient (4 REDs).
 //   k_track_finalize  scale the per-frame sums, expand twists to ambient 3x4 gradients.
@@ -1205,7 +1206,7 @@ __device__ __forceinline__ float warp_sum_n(float* v, int lane) {
 // One sweep over the (source row, target row, point) triples.  A block owns (segment, source
 // row, 256 points): every thread keeps the source-side sums of its point in registers; the
 // target-side sums (pose twist and K of the TARGET frame) of one loop iteration belong to one
-// frame for the whole block, so each warp reduces them with warp_sum10 into its own
+// frame for the whole block, so each warp reduces them with warp_sum_n into its own
 // [target row][10] slice of shared memory, folded into the per-frame accumulators at the end.
 // SHARED_K: every frame has the same intrinsics (one focal length, or constants), so only the SUM
 // over frames of the intrinsics gradient matters: the target-frame terms are then added to the
