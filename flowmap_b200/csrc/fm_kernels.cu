@@ -729,6 +729,164 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
   block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
 }
 
+// ------------------------------------------------------------------------------------------
+// Phase D2, tiled (dense path, W % 32 == 0): the bilinear scatter into the EARLIER frame's depth
+// gradient is privatised in shared memory.  A block owns 32 x 32 tiles of the LATER frame; the
+// taps of a tile land in a 64 x 64 window (tile + 16 px halo, shifted by the tile's mean backward
+// flow so that smooth real flows stay inside); taps outside fall back to global vector REDs.
+//
+// Shared-memory float atomics are CAS loops on sm_100a (measured slower than the global REDs,
+// profiles/README.md), so the window accumulates in fixed point on the native 32-bit integer
+// ATOMS.ADD: an exact (high, low) 64-bit integer per cell with a per-tile power-of-two scale
+// derived from a bound of the tile's contributions (fm_pixel.cuh: fix_add, fix_scale_for,
+// scatter_bound_consts).  Values too large for the fixed-point range (raw weights > 1,
+// non-finite input) take the global float RED, so correctness never depends on the bound.  The
+// flush converts each touched cell once and adds four cells with one aligned 16-byte RED.
+__global__ void __launch_bounds__(kThreads, 3)
+k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4,
+                   const float* __restrict__ bflow, float* weights,
+                   const PairAdjoint* __restrict__ adj, float* __restrict__ g_depth,
+                   float* __restrict__ g_weights, double* __restrict__ k4acc, float wsens,
+                   PairLayout lay, AdamFuse adam, int H, int W) {
+  __shared__ double smem[8 * (kThreads / 32)];
+  __shared__ PairAdjoint s_adj;
+  __shared__ __align__(16) unsigned win_lo[kWin * kWin];
+  __shared__ __align__(16) int win_hi[kWin * kWin];
+  __shared__ float s_red[4 * (kThreads / 32)];
+  const int pair = blockIdx.y;
+  const int N = H * W;
+  if (threadIdx.x < sizeof(PairAdjoint) / 4)
+    reinterpret_cast<float*>(&s_adj)[threadIdx.x] = reinterpret_cast<const float*>(adj + pair)[threadIdx.x];
+  for (int i = threadIdx.x; i < kWin * kWin / 4; i += kThreads) {
+    reinterpret_cast<uint4*>(win_lo)[i] = make_uint4(kFixBias, kFixBias, kFixBias, kFixBias);
+    reinterpret_cast<int4*>(win_hi)[i] = make_int4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  const PairAdjoint ad = s_adj;
+  const PairAddr pa = pair_addr(lay, pair, N);
+  const PairGeom g = pair_geom(depth, k4, pa, H, W);
+  const int a = pa.k4_frame_a;
+  const float* da = depth + pa.depth_a;
+  const float* db = da + N;
+  const float* fl = bflow + pa.flow;
+  float* wt = weights ? weights + pa.weight : nullptr;
+  float* gda = g_depth + pa.depth_a;
+  float* gdb = gda + N;
+  float* gw = g_weights ? g_weights + pa.weight : nullptr;
+  auto load_a = [da, W](int yy, int xx) { return __ldg(da + yy * W + xx); };
+  float kacc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
+  float bnd_z, bnd_c;  // bound of a tile's contributions = wmax * (bnd_z * max|depth_b| + bnd_c)
+  scatter_bound_consts(g, ad, bnd_z, bnd_c);
+  auto add_u = [](unsigned* p, unsigned v) { return atomicAdd(p, v); };
+  auto add_i = [](int* p, int v) { atomicAdd(p, v); };
+  const int tiles_x = W / kTile, tiles_y = (H + kTile - 1) / kTile;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kThreads / 32;
+
+  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+    const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
+    const int X0 = txi * kTile, Y0 = tyi * kTile;
+    const int r = Y0 + ty, c0 = X0 + 4 * tx;
+    const bool row_ok = r < H;
+    const int base = r * W + c0;
+    float dv[4], wv[4], wraw[4], fv[8], gwv[4], gdv[4];
+    float zm = 0.f, wm = 1.f;
+    if (row_ok) {
+      load_vec<4>(db + base, dv);
+      load_vec2<4>(fl + 2 * base, fv);
+      if (wt) {  // plain (coherent) load: the logits may be updated in place below
+        const float4 w4 = *reinterpret_cast<const float4*>(wt + base);
+        wraw[0] = w4.x; wraw[1] = w4.y; wraw[2] = w4.z; wraw[3] = w4.w;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) wv[v] = weight_of(wraw[v], wsens);
+      } else {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) wv[v] = 1.f;
+      }
+      zm = fmaxf(fmaxf(fabsf(dv[0]), fabsf(dv[1])), fmaxf(fabsf(dv[2]), fabsf(dv[3])));
+      wm = fmaxf(fmaxf(fabsf(wv[0]), fabsf(wv[1])), fmaxf(fabsf(wv[2]), fabsf(wv[3])));
+    } else {
+#pragma unroll
+      for (int v = 0; v < 8; ++v) fv[v] = 0.f;
+    }
+    // tile statistics: mean flow (window origin) and max |depth| (fixed-point scale)
+    float sx = (fv[0] + fv[2]) + (fv[4] + fv[6]), sy = (fv[1] + fv[3]) + (fv[5] + fv[7]);
+    sx = warp_sum_f(sx); sy = warp_sum_f(sy);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o));
+      wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+    }
+    if (lane == 0) { s_red[warp] = sx; s_red[NW + warp] = sy; s_red[2 * NW + warp] = zm; s_red[3 * NW + warp] = wm; }
+    __syncthreads();
+    float mx = 0.f, my = 0.f, zmax = 0.f, wmax = 1.f;
+#pragma unroll
+    for (int w8 = 0; w8 < NW; ++w8) {
+      mx += s_red[w8]; my += s_red[NW + w8];
+      zmax = fmaxf(zmax, s_red[2 * NW + w8]); wmax = fmaxf(wmax, s_red[3 * NW + w8]);
+    }
+    int wx0, wy0;
+    tile_window_origin(mx, my, min(kTile, H - Y0) * kTile, X0, Y0, g.grid, wx0, wy0);
+    const FixScale fs = fix_scale_for(wmax * fmaf(bnd_z, zmax, bnd_c));
+    const float inv_scale = fs.inv_scale;
+    auto scatter = [&](int y0, int x0, float v0, float v1) {
+      if (!window_add(win_lo, win_hi, wx0, wy0, fs.scale, y0, x0, v0, v1, add_u, add_i))
+        red_pair<true>(gda + y0 * W, x0, W, v0, v1);
+    };
+    if (row_ok) {
+      const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v], fv[2 * v],
+                         fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
+      red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
+      if (wt) {
+        if (wsens != 0.f) {  // chain rule of the sigmoid: d/d logit = sens * w (1 - w) * d/dw
+#pragma unroll
+          for (int v = 0; v < 4; ++v) gwv[v] *= wsens * wv[v] * (1.0f - wv[v]);
+        }
+        if (gw) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
+        if (adam.on && pair >= adam.first_pair) {  // torch.optim.Adam on the logits (k_adam's order)
+          float4 mm = *reinterpret_cast<float4*>(adam.m + pa.weight + base);
+          float4 vv = *reinterpret_cast<float4*>(adam.v + pa.weight + base);
+          float* mp = &mm.x; float* vp = &vv.x;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            mp[v] = mp[v] + adam.omb1 * (gwv[v] - mp[v]);
+            vp[v] = vp[v] * adam.beta2 + adam.omb2 * gwv[v] * gwv[v];
+            wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
+          }
+          *reinterpret_cast<float4*>(adam.m + pa.weight + base) = mm;
+          *reinterpret_cast<float4*>(adam.v + pa.weight + base) = vv;
+          *reinterpret_cast<float4*>(wt + base) = make_float4(wraw[0], wraw[1], wraw[2], wraw[3]);
+        }
+      }
+    }
+    __syncthreads();
+    // flush the touched cells (one aligned 16-byte RED per four cells) and reset them
+    for (int i = threadIdx.x; i < kWin * kWin / 4; i += kThreads) {
+      const uint4 l4 = reinterpret_cast<uint4*>(win_lo)[i];
+      const int4 h4 = reinterpret_cast<int4*>(win_hi)[i];
+      const bool lo_clean = l4.x == kFixBias && l4.y == kFixBias && l4.z == kFixBias && l4.w == kFixBias;
+      const bool hi_clean = (h4.x | h4.y | h4.z | h4.w) == 0;
+      if (lo_clean && hi_clean) continue;
+      const int uy = (i * 4) / kWin, ux = (i * 4) - uy * kWin;
+      const int gy = wy0 + uy, gx = wx0 + ux;
+      // taps are clamped into the image, so a touched cell is always inside it
+      if (gy >= 0 && gy < H && gx >= 0 && gx + 3 < W)
+        red_add4(gda + gy * W + gx, fix_value(l4.x, h4.x) * inv_scale, fix_value(l4.y, h4.y) * inv_scale,
+                 fix_value(l4.z, h4.z) * inv_scale, fix_value(l4.w, h4.w) * inv_scale);
+      reinterpret_cast<uint4*>(win_lo)[i] = make_uint4(kFixBias, kFixBias, kFixBias, kFixBias);
+      if (!hi_clean) reinterpret_cast<int4*>(win_hi)[i] = make_int4(0, 0, 0, 0);
+    }
+    __syncthreads();
+  }
+  block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
+}
+
 __global__ void k_k4_finalize(const double* __restrict__ k4acc, const double* __restrict__ flowacc,
                               int include_flow, const float* __restrict__ flow_scale,
                               float* __restrict__ g_k4, int B, int F) {
@@ -1756,6 +1914,13 @@ int blocks_for_points(int n) {
   return nb < 1 ? 1 : nb;
 }
 
+// Procrustes-adjoint scatter: FM_SCATTER=tiled selects the shared-memory fixed-point window
+// (k_distribute_tiled), FM_SCATTER=red the global vector REDs (k_distribute).
+bool tiled_scatter_enabled() {  // read per call (a getenv): tests and tools flip it inside one process
+  const char* v = getenv("FM_SCATTER");
+  return v && !strcmp(v, "tiled");
+}
+
 bool bad_dims(int B, int F, int H, int W) { return B < 1 || F < 2 || H < 1 || W < 1 || (long long)H * W > (1ll << 30); }
 
 }  // namespace
@@ -1910,6 +2075,10 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
   if (indices) {
     dim3 grid(blocks_for_points(num_indices), BP);
     k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
+  } else if (W % kTile == 0 && lay.cand == 1 && tiled_scatter_enabled()) {
+    const int tiles = (W / kTile) * ((H + kTile - 1) / kTile);
+    dim3 grid((tiles + 7) / 8, BP);
+    k_distribute_tiled<<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
     k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);

@@ -1,0 +1,178 @@
+"""A/B of the two Procrustes-adjoint scatters on a B200: global vector REDs (k_distribute,
+FM_SCATTER=red) vs the shared-memory fixed-point window (k_distribute_tiled, FM_SCATTER=tiled).
+
+1. same inputs through fm_procrustes_fwd -> fm_flow_loss_fwd_bwd -> fm_procrustes_bwd in both
+   modes at several shapes / flow fields: depth, weight and intrinsics gradients must agree;
+2. per-launch time of fm_procrustes_bwd and of the fused step (full / flow-only) in both modes.
+
+Usage: python tools/ab_scatter.py [--quick]    (writes gpurun_out/ab_scatter.json)"""
+import json
+import os
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+from flowmap_b200 import ops  # noqa: E402
+from flowmap_b200._lib import lib  # noqa: E402
+from flowmap_b200.overfit import FusedOverfitter, OverfitCfg  # noqa: E402
+from flowmap_b200.types import Batch, Flows, Tracks  # noqa: E402
+
+dev = torch.device("cuda:0")
+P = lambda x: x.data_ptr()  # noqa: E731
+MODES = ("red", "tiled")
+
+
+def set_mode(m):
+    os.environ["FM_SCATTER"] = m
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def make_case(f, h, w, kind, seed=0):
+    inp = bench.synthetic_inputs(f, h, w, seed=seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    if kind == "shift":      # large coherent motion
+        inp["bwd"] = inp["bwd"] + torch.tensor([0.2, -0.1])
+    elif kind == "leave":    # most taps leave the frame: border pile-up
+        inp["bwd"] = inp["bwd"] + torch.tensor([1.5, 0.0])
+    elif kind == "outliers":
+        m = torch.rand(1, f - 1, h, w, generator=g) < 0.05
+        inp["bwd"][m] = 0.5 * torch.randn(int(m.sum()), 2, generator=g)
+    elif kind == "smooth":
+        coarse = 0.01 * torch.randn(f - 1, 2, (h + 15) // 16 + 1, (w + 15) // 16 + 1, generator=g)
+        up = torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True)
+        inp["bwd"] = up.permute(0, 2, 3, 1)[None].contiguous()
+    return {k: v.to(dev).contiguous() for k, v in inp.items()}
+
+
+def run_ops(c, f, h, w, raw_weights=False):
+    L = lib()
+    st = torch.cuda.current_stream().cuda_stream
+    depths = c["depth"][None].contiguous()
+    weights = (5.0 * torch.rand_like(c["wparam"]) if raw_weights else torch.sigmoid(100.0 * c["wparam"]))[None].contiguous()
+    s_ = (h * w) ** 0.5
+    k4 = torch.tensor([0.85 * s_ / w, 0.85 * s_ / h, 0.5, 0.5], device=dev).expand(1, f, 4).contiguous()
+    msum = ops.mask_sum(c["fmask"], c["bmask"])
+    ws = ops.workspace(1, f, h, w, dev)
+    rt = torch.empty(1, f - 1, 3, 4, device=dev)
+    g_depth, g_w = torch.zeros_like(depths), torch.zeros_like(weights)
+    g_k4, g_rt = torch.zeros_like(k4), torch.zeros_like(rt)
+    lossb = torch.empty((), device=dev)
+
+    def fwd():
+        assert L.fm_procrustes_fwd(P(depths), P(k4), P(c["bwd"]), P(weights), None, 0, P(rt), P(ws), 1, f, h, w, st) == 0
+        assert L.fm_flow_loss_fwd_bwd(P(depths), P(k4), P(rt), P(c["fwd"]), P(c["bwd"]), P(c["fmask"]), P(c["bmask"]),
+                                      P(msum), 0, 0.01, 1000.0, 1, P(lossb), P(g_depth), P(g_rt), P(g_k4), P(ws),
+                                      1, f, h, w, st) == 0
+
+    def bwd():
+        assert L.fm_procrustes_bwd(P(depths), P(k4), P(c["bwd"]), P(weights), None, 0, None, 1, None, P(g_depth),
+                                   P(g_w), P(g_k4), P(ws), 1, f, h, w, st) == 0, L.fm_last_error()
+    return fwd, bwd, (g_depth, g_w, g_k4)
+
+
+def compare(f, h, w, kind, raw_weights=False):
+    c = make_case(f, h, w, kind)
+    res = {}
+    for m in MODES:
+        set_mode(m)
+        fwd, bwd, outs = run_ops(c, f, h, w, raw_weights)
+        fwd(); bwd()
+        torch.cuda.synchronize()
+        res[m] = [o.clone() for o in outs]
+    r = {"shape": [f, h, w], "flows": kind, "raw_weights": raw_weights,
+         "g_depth_rel": rel(res["tiled"][0], res["red"][0]),
+         "g_weights_equal": bool(torch.equal(res["tiled"][1], res["red"][1])),
+         "g_weights_rel": rel(res["tiled"][1], res["red"][1]),
+         "g_k4_rel": rel(res["tiled"][2], res["red"][2]),
+         "finite": bool(torch.isfinite(res["tiled"][0]).all())}
+    r["ok"] = r["g_depth_rel"] <= 2e-6 and r["g_weights_rel"] <= 1e-7 and r["g_k4_rel"] <= 1e-6 and r["finite"]
+    print("compare", json.dumps(r), flush=True)
+    return r
+
+
+def time_bwd(f, h, w, kind, n=20):
+    c = make_case(f, h, w, kind)
+    out = {}
+    for m in MODES:
+        set_mode(m)
+        fwd, bwd, _ = run_ops(c, f, h, w)
+        for _ in range(3):
+            fwd(); bwd()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(n):
+            fwd()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); bwd(); b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        out[m] = tot / n
+    print(f"fm_procrustes_bwd {f}x{h}x{w} {kind:8s} " + "  ".join(f"{m} {out[m]:.4f} ms" for m in MODES), flush=True)
+    return out
+
+
+def time_steps(steps=40):
+    F, H, W = bench.F_, bench.H_, bench.W_
+    inp = bench.synthetic_inputs(F, H, W, seed=0)
+    batch = Batch(torch.zeros(1, 1, 1, 1, 1, device=dev).expand(1, F, 3, H, W), torch.arange(F, device=dev)[None], ["s"], ["d"])
+    flows = Flows(*(inp[k].to(dev) for k in ("fwd", "bwd", "fmask", "bmask")))
+    tracks = [Tracks(xy, vis, s) for xy, vis, s in bench.synthetic_track_arrays(F, seed=0)]
+
+    def timed(o):
+        with torch.no_grad():
+            o.model.backbone.depth.copy_(inp["depth"])
+            o.model.backbone.weights.copy_(inp["wparam"])
+        o.global_step = bench.START_STEP
+        for _ in range(5):
+            o.training_step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            out = o.training_step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, float(out[0]), o.model.backbone.depth.detach().clone()
+    out = {}
+    for m in MODES:
+        set_mode(m)
+        full, loss, depth = timed(FusedOverfitter(OverfitCfg(intrinsics="softmin", use_tracking=True), batch, flows, tracks, device=dev))
+        flow_only, _, _ = timed(FusedOverfitter(OverfitCfg(), batch, flows, device=dev))
+        out[m] = {"full_ms": full, "flow_only_ms": flow_only, "loss": loss}
+        out[m + "_depth"] = depth
+        print(f"fused step {m:6s} full {full:.4f} ms  flow-only {flow_only:.4f} ms  loss after {steps + 5} steps {loss:.6f}", flush=True)
+    out["depth_after_steps_rel"] = rel(out.pop("tiled_depth"), out.pop("red_depth"))
+    print("depth after the optimisation steps, tiled vs red: rel", out["depth_after_steps_rel"], flush=True)
+    return out
+
+
+def main():
+    quick = "--quick" in sys.argv
+    report = {"compare": [], "bwd_ms": {}, "steps": None}
+    shapes = [(3, 24, 32), (4, 40, 64), (5, 72, 96), (3, 128, 128), (3, 360, 640)]
+    for f, h, w in shapes:
+        for kind in ("iid", "smooth", "shift", "leave", "outliers"):
+            report["compare"].append(compare(f, h, w, kind))
+    report["compare"].append(compare(5, 72, 96, "iid", raw_weights=True))
+    report["compare"].append(compare(2, 720, 1280, "iid"))
+    report["all_ok"] = all(r["ok"] for r in report["compare"])
+    print("ALL_OK" if report["all_ok"] else "MISMATCH", flush=True)
+    for kind in ("iid", "smooth"):
+        report["bwd_ms"][kind] = time_bwd(bench.F_, bench.H_, bench.W_, kind)
+    if not quick:
+        report["steps"] = time_steps()
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "ab_scatter.json").write_text(json.dumps(report, indent=1))
+
+
+if __name__ == "__main__":
+    main()
