@@ -185,7 +185,20 @@ __device__ __forceinline__ void red_pair(float* row, int x0, int W, float v0, fl
 // Correspondence weight from its stored form: the weight itself (sens == 0) or the logit of
 // BackboneExplicitDepth (backbone_explicit_depth.py:40): w = sigmoid(sens * logit).
 __device__ __forceinline__ float weight_of(float stored, float sens) {
-  return sens == 0.f ? stored : __fdividef(1.0f, 1.0f + __expf(-sens * stored));
+  if (sens == 0.f) return stored;
+  // exp(-sens * stored) as ONE MUFU.EX2 (flush-to-zero form: no denormal range fix-up around it;
+  // an underflowing exponential gives w = 1, as it should)
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * sens * stored));
+  return fm_rcp(1.0f + e);
+}
+
+// Keeps a frame's base pointer as ONE 64-bit value: without this the compiler re-associates
+// depth + (frame offset + tap offset) and spends a 64-bit add + two LEAs on every gathered tap
+// instead of one IMAD.WIDE on the finished pointer.
+__device__ __forceinline__ const float* opaque_ptr(const float* p) {
+  asm volatile("" : "+l"(p));
+  return p;
 }
 
 // Load the 4 (or 1) values a thread owns.
@@ -263,11 +276,11 @@ k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
   const int N = H * W;
   const PairAddr pa = pair_addr(lay, pair, N);
   const PairGeom g = pair_geom(depth, k4, pa, H, W);
-  const float* da = depth + pa.depth_a;
+  const float* da = opaque_ptr(depth + pa.depth_a);
   const float* db = da + N;
   const float* fl = bflow + pa.flow;
   const float* wt = weights ? weights + pa.weight : nullptr;
-  auto load_a = [da, W](int yy, int xx) { return __ldg(da + yy * W + xx); };
+  auto load_a = [da](int o) { return __ldg(da + o); };
   // float32 per-thread partials: a thread sees at most a few dozen (shifted, O(1)) terms, the
   // cross-thread / cross-block sums run in float64.
   float acc[kNumMoments];
@@ -641,12 +654,12 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
   const PairAddr pa = pair_addr(lay, pair, N);
   const PairGeom g = pair_geom(depth, k4, pa, H, W);
   const int a = pa.k4_frame_a;
-  const float* da = depth + pa.depth_a;
+  const float* da = opaque_ptr(depth + pa.depth_a);
   const float* db = da + N;
   const float* fl = bflow + pa.flow;
   float* wt = weights ? weights + pa.weight : nullptr;
   float* gda = g_depth + pa.depth_a;
-  auto load_a = [da, W](int yy, int xx) { return __ldg(da + yy * W + xx); };
+  auto load_a = [da](int o) { return __ldg(da + o); };
   auto scatter = [gda, W](int y0, int x0, float v0, float v1) { red_pair<VEC == 4>(gda + y0 * W, x0, W, v0, v1); };
   float* gdb = gda + N;
   float* gw = g_weights ? g_weights + pa.weight : nullptr;
@@ -748,11 +761,13 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
                    const PairAdjoint* __restrict__ adj, float* __restrict__ g_depth,
                    float* __restrict__ g_weights, double* __restrict__ k4acc, float wsens,
                    PairLayout lay, AdamFuse adam, int H, int W) {
-  __shared__ double smem[8 * (kThreads / 32)];
+  constexpr int NW = kThreads / 32;
+  __shared__ double smem[8 * NW];
   __shared__ PairAdjoint s_adj;
   __shared__ __align__(16) unsigned win_lo[kWin * kWin];
   __shared__ __align__(16) int win_hi[kWin * kWin];
-  __shared__ float s_red[4 * (kThreads / 32)];
+  __shared__ __align__(16) float s_red[4 * NW];  // per-warp tile statistics: sum flx, sum fly, max |depth|, max weight
+  __shared__ int s_hi_used[2];                   // did any add of this tile (parity) touch a high word?
   const int pair = blockIdx.y;
   const int N = H * W;
   if (threadIdx.x < sizeof(PairAdjoint) / 4)
@@ -761,32 +776,31 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
     reinterpret_cast<uint4*>(win_lo)[i] = make_uint4(kFixBias, kFixBias, kFixBias, kFixBias);
     reinterpret_cast<int4*>(win_hi)[i] = make_int4(0, 0, 0, 0);
   }
+  if (threadIdx.x < 2) s_hi_used[threadIdx.x] = 0;
   __syncthreads();
   const PairAdjoint ad = s_adj;
   const PairAddr pa = pair_addr(lay, pair, N);
   const PairGeom g = pair_geom(depth, k4, pa, H, W);
   const int a = pa.k4_frame_a;
-  const float* da = depth + pa.depth_a;
+  const float* da = opaque_ptr(depth + pa.depth_a);
   const float* db = da + N;
   const float* fl = bflow + pa.flow;
   float* wt = weights ? weights + pa.weight : nullptr;
   float* gda = g_depth + pa.depth_a;
   float* gdb = gda + N;
   float* gw = g_weights ? g_weights + pa.weight : nullptr;
-  auto load_a = [da, W](int yy, int xx) { return __ldg(da + yy * W + xx); };
+  auto load_a = [da](int o) { return __ldg(da + o); };
   float kacc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
   float bnd_z, bnd_c;  // bound of a tile's contributions = wmax * (bnd_z * max|depth_b| + bnd_c)
   scatter_bound_consts(g, ad, bnd_z, bnd_c);
-  auto add_u = [](unsigned* p, unsigned v) { return atomicAdd(p, v); };
-  auto add_i = [](int* p, int v) { atomicAdd(p, v); };
   const int tiles_x = W / kTile, tiles_y = (H + kTile - 1) / kTile;
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = kThreads / 32;
+  int parity = 0;
 
-  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x, parity ^= 1) {
     const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
     const int X0 = txi * kTile, Y0 = tyi * kTile;
     const int r = Y0 + ty, c0 = X0 + 4 * tx;
@@ -802,36 +816,48 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
         wraw[0] = w4.x; wraw[1] = w4.y; wraw[2] = w4.z; wraw[3] = w4.w;
 #pragma unroll
         for (int v = 0; v < 4; ++v) wv[v] = weight_of(wraw[v], wsens);
+        // a sigmoid never exceeds 1; raw weights (wsens == 0) may
+        if (wsens == 0.f) wm = fmaxf(fmaxf(fabsf(wv[0]), fabsf(wv[1])), fmaxf(fabsf(wv[2]), fabsf(wv[3])));
       } else {
 #pragma unroll
         for (int v = 0; v < 4; ++v) wv[v] = 1.f;
       }
       zm = fmaxf(fmaxf(fabsf(dv[0]), fabsf(dv[1])), fmaxf(fabsf(dv[2]), fabsf(dv[3])));
-      wm = fmaxf(fmaxf(fabsf(wv[0]), fabsf(wv[1])), fmaxf(fabsf(wv[2]), fabsf(wv[3])));
     } else {
 #pragma unroll
       for (int v = 0; v < 8; ++v) fv[v] = 0.f;
     }
-    // tile statistics: mean flow (window origin) and max |depth| (fixed-point scale)
+    // tile statistics: mean flow (window origin), max |depth| and max weight (fixed-point scale)
     float sx = (fv[0] + fv[2]) + (fv[4] + fv[6]), sy = (fv[1] + fv[3]) + (fv[5] + fv[7]);
-    sx = warp_sum_f(sx); sy = warp_sum_f(sy);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
       zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o));
-      wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+    }
+    if (wsens == 0.f && wt) {  // block-uniform
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
     }
     if (lane == 0) { s_red[warp] = sx; s_red[NW + warp] = sy; s_red[2 * NW + warp] = zm; s_red[3 * NW + warp] = wm; }
     __syncthreads();
-    float mx = 0.f, my = 0.f, zmax = 0.f, wmax = 1.f;
-#pragma unroll
-    for (int w8 = 0; w8 < NW; ++w8) {
-      mx += s_red[w8]; my += s_red[NW + w8];
-      zmax = fmaxf(zmax, s_red[2 * NW + w8]); wmax = fmaxf(wmax, s_red[3 * NW + w8]);
+    float mx, my, zmax, wmax;
+    {
+      static_assert(kThreads / 32 == 8, "two float4 per statistic");
+      const float4* r4 = reinterpret_cast<const float4*>(s_red);
+      const float4 a0 = r4[0], a1 = r4[1], b0 = r4[2], b1 = r4[3], c0_ = r4[4], c1 = r4[5], d0 = r4[6], d1 = r4[7];
+      mx = ((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w));
+      my = ((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w));
+      zmax = fmaxf(fmaxf(fmaxf(c0_.x, c0_.y), fmaxf(c0_.z, c0_.w)), fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w)));
+      wmax = fmaxf(fmaxf(fmaxf(d0.x, d0.y), fmaxf(d0.z, d0.w)), fmaxf(fmaxf(d1.x, d1.y), fmaxf(d1.z, d1.w)));
     }
     int wx0, wy0;
     tile_window_origin(mx, my, min(kTile, H - Y0) * kTile, X0, Y0, g.grid, wx0, wy0);
     const FixScale fs = fix_scale_for(wmax * fmaf(bnd_z, zmax, bnd_c));
     const float inv_scale = fs.inv_scale;
+    int* hi_flag = s_hi_used + parity;
+    auto add_u = [](unsigned* p, unsigned v) { return atomicAdd(p, v); };
+    auto add_i = [hi_flag](int* p, int v) { atomicAdd(p, v); *hi_flag = 1; };
     auto scatter = [&](int y0, int x0, float v0, float v1) {
       if (!window_add(win_lo, win_hi, wx0, wy0, fs.scale, y0, x0, v0, v1, add_u, add_i))
         red_pair<true>(gda + y0 * W, x0, W, v0, v1);
@@ -866,21 +892,27 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
       }
     }
     __syncthreads();
-    // flush the touched cells (one aligned 16-byte RED per four cells) and reset them
+    // Flush the touched cells (one aligned 16-byte RED per four cells) and reset them.  The high
+    // words are only looked at when some add of this tile touched one (rare).  The other parity's
+    // flag is cleared here: its last readers passed the previous trailing barrier, its next
+    // writers start after this tile's.
+    const bool any_hi = *hi_flag != 0;
+    if (threadIdx.x == 0) s_hi_used[parity ^ 1] = 0;
     for (int i = threadIdx.x; i < kWin * kWin / 4; i += kThreads) {
       const uint4 l4 = reinterpret_cast<uint4*>(win_lo)[i];
-      const int4 h4 = reinterpret_cast<int4*>(win_hi)[i];
-      const bool lo_clean = l4.x == kFixBias && l4.y == kFixBias && l4.z == kFixBias && l4.w == kFixBias;
-      const bool hi_clean = (h4.x | h4.y | h4.z | h4.w) == 0;
-      if (lo_clean && hi_clean) continue;
-      const int uy = (i * 4) / kWin, ux = (i * 4) - uy * kWin;
+      int4 h4 = make_int4(0, 0, 0, 0);
+      if (any_hi) h4 = reinterpret_cast<int4*>(win_hi)[i];
+      const unsigned dirty = ((l4.x ^ kFixBias) | (l4.y ^ kFixBias)) | ((l4.z ^ kFixBias) | (l4.w ^ kFixBias)) |
+                             (unsigned)((h4.x | h4.y) | (h4.z | h4.w));
+      if (dirty == 0) continue;
+      const int uy = i >> 4, ux = (i & 15) << 2;  // kWin / 4 == 16 groups per window row
       const int gy = wy0 + uy, gx = wx0 + ux;
       // taps are clamped into the image, so a touched cell is always inside it
       if (gy >= 0 && gy < H && gx >= 0 && gx + 3 < W)
         red_add4(gda + gy * W + gx, fix_value(l4.x, h4.x) * inv_scale, fix_value(l4.y, h4.y) * inv_scale,
                  fix_value(l4.z, h4.z) * inv_scale, fix_value(l4.w, h4.w) * inv_scale);
       reinterpret_cast<uint4*>(win_lo)[i] = make_uint4(kFixBias, kFixBias, kFixBias, kFixBias);
-      if (!hi_clean) reinterpret_cast<int4*>(win_hi)[i] = make_int4(0, 0, 0, 0);
+      if (any_hi) reinterpret_cast<int4*>(win_hi)[i] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();
   }
@@ -1413,7 +1445,7 @@ k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const
     if (live) {
       const float2 sxy = __ldg(reinterpret_cast<const float2*>(txy) + sidx);
       const Taps t = bilinear_taps(sxy.x, sxy.y, grid);
-      sample_surface(t, grid, ks, [D, W](int yy, int xx) { return __ldg(D + yy * W + xx); }, q[0], q[1], q[2]);
+      sample_surface(t, grid, ks, [D](int o) { return __ldg(D + o); }, q[0], q[1], q[2]);
 #pragma unroll
       for (int i = 0; i < 3; ++i)
         Xw[i] = fm_fma(rs[i * 3 + 0], q[0], fm_fma(rs[i * 3 + 1], q[1], fm_fma(rs[i * 3 + 2], q[2], rs[9 + i])));
@@ -1921,6 +1953,12 @@ bool tiled_scatter_enabled() {  // read per call (a getenv): tests and tools fli
   return v && !strcmp(v, "tiled");
 }
 
+int tiles_per_cta() {  // tuning knob of tools/ab_scatter.py (a block walks this many 32 x 32 tiles)
+  const char* v = getenv("FM_TILED_TILES_PER_CTA");
+  const int n = v ? atoi(v) : 0;
+  return n >= 1 && n <= 1024 ? n : 8;
+}
+
 bool bad_dims(int B, int F, int H, int W) { return B < 1 || F < 2 || H < 1 || W < 1 || (long long)H * W > (1ll << 30); }
 
 }  // namespace
@@ -2077,7 +2115,8 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
     k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   } else if (W % kTile == 0 && lay.cand == 1 && tiled_scatter_enabled()) {
     const int tiles = (W / kTile) * ((H + kTile - 1) / kTile);
-    dim3 grid((tiles + 7) / 8, BP);
+    const int per_cta = tiles_per_cta();
+    dim3 grid((tiles + per_cta - 1) / per_cta, BP);
     k_distribute_tiled<<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);

@@ -28,18 +28,27 @@ struct Rt {  // rigid 3x4 [R | t], row-major R
 
 enum Mapping : int { MAP_HUBER = 0, MAP_L1 = 1, MAP_L2 = 2 };
 
-// Reciprocal / reciprocal square root: MUFU approximations on the device (<= 1-2 ulp,
-// no IEEE slow path), plain C on the host (tests/host_emulation).
+// Reciprocal / reciprocal square root: ONE MUFU instruction on the device (<= 1-2 ulp), plain C on
+// the host (tests/host_emulation).  The flush-to-zero forms are used on purpose: the default
+// forms wrap the MUFU in a denormal range fix-up (compare, select, two scalings) that costs more
+// issue slots than the operation itself.  Consequences: a denormal argument counts as 0
+// (rcp -> inf, which the callers' nan_to_num path handles like the division by zero it is), and
+// fm_rsqrt callers compare against kTinyNorm2 instead of 0.
+constexpr float kTinyNorm2 = 1e-30f;  // squared residual norms below this are treated as exactly 0
 FM_HD float fm_rcp(float v) {
 #if defined(__CUDA_ARCH__)
-  return __fdividef(1.0f, v);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
 #else
   return 1.0f / v;
 #endif
 }
 FM_HD float fm_rsqrt(float v) {
 #if defined(__CUDA_ARCH__)
-  return rsqrtf(v);
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
 #else
   return 1.0f / sqrtf(v);
 #endif
@@ -132,6 +141,7 @@ FM_HD void ray_of(float x, float y, const Cam& k, float& rx, float& ry) {
 // ---------------------------------------------------------------------------------
 struct Taps {
   int x0, y0, x1, y1;      // clamped tap coordinates
+  float fx0, fy0;          // x0 / y0 as floats (they fall out of the floor computation)
   float w00, w01, w10, w11;  // weights: w{row}{col}: (y0,x0) (y0,x1) (y1,x0) (y1,x1)
 };
 
@@ -149,10 +159,10 @@ FM_HD GridDims make_grid(int H, int W) {
 // floor() of a value in [0, 2^22) together with its integer, on the FP32 add pipe: adding
 // 1.5 * 2^23 to (v - .5) rounds to the nearest integer; a tie (v an exact integer) may pick
 // v - 1 with fraction 1, which is the same point of the (continuous) bilinear interpolant.
-FM_HD int floor_pos(float v, float& frac) {
+FM_HD int floor_pos(float v, float& frac, float& fl) {
   const float magic = 12582912.0f;  // 1.5 * 2^23
   const float m = (v - 0.5f) + magic;
-  const float fl = m - magic;
+  fl = m - magic;
   frac = v - fl;
 #if defined(__CUDA_ARCH__)
   return __float_as_int(m) - 0x4B400000;
@@ -169,8 +179,8 @@ FM_HD Taps bilinear_taps(float ex, float ey, const GridDims& g) {
   py = fminf(g.Hf - 1.0f, fmaxf(py, 0.0f));
   float tx, ty;
   Taps t;
-  t.x0 = floor_pos(px, tx);
-  t.y0 = floor_pos(py, ty);
+  t.x0 = floor_pos(px, tx, t.fx0);
+  t.y0 = floor_pos(py, ty, t.fy0);
   t.x1 = t.x0 + 1;
   t.y1 = t.y0 + 1;
   float wx1 = tx, wx0 = 1.0f - tx, wy1 = ty, wy0 = 1.0f - ty;
@@ -185,21 +195,27 @@ FM_HD Taps bilinear_taps(float ex, float ey, const GridDims& g) {
 
 // Bilinear sample of the xyz image D*ray(K) of a frame (NOT interp(D)*ray(e)): returns
 // q = (qx, qy, qz).  `D` points at the frame's (H, W) depth.
-// Rays through the tap centres.  (i + .5) * inv_n instead of the exact quotient: the tap
+// Rays through the tap centres: ((i + .5) / n - c) / f as ONE fma per axis on the float tap index
+// with per-frame constants (the compiler hoists them out of the pixel loop), the second tap one
+// step further.  A clamped second tap (x1 == x0) carries weight 0, so its ray never matters.  The
 // rays only enter weighted sums, where one ulp is far below the float32 noise floor.
 FM_HD void tap_rays(const Taps& t, const GridDims& g, const Cam& k, float& rx0, float& ry0,
                     float& rx1, float& ry1) {
-  rx0 = (((float)t.x0 + 0.5f) * g.invW - k.cx) * k.ifx;
-  rx1 = (((float)t.x1 + 0.5f) * g.invW - k.cx) * k.ifx;
-  ry0 = (((float)t.y0 + 0.5f) * g.invH - k.cy) * k.ify;
-  ry1 = (((float)t.y1 + 0.5f) * g.invH - k.cy) * k.ify;
+  const float ax = g.invW * k.ifx, bx = (0.5f * g.invW - k.cx) * k.ifx;
+  const float ay = g.invH * k.ify, by = (0.5f * g.invH - k.cy) * k.ify;
+  rx0 = fm_fma(t.fx0, ax, bx);
+  ry0 = fm_fma(t.fy0, ay, by);
+  rx1 = rx0 + ax;
+  ry1 = ry0 + ay;
 }
 
+// `load(o)` returns the frame's depth at linear offset o = row * W + col.
 template <typename Load>
 FM_HD void sample_surface(const Taps& t, const GridDims& g, const Cam& k, Load load, float& qx,
                           float& qy, float& qz) {
-  float d00 = load(t.y0, t.x0), d01 = load(t.y0, t.x1);
-  float d10 = load(t.y1, t.x0), d11 = load(t.y1, t.x1);
+  const int r0 = t.y0 * g.W, r1 = t.y1 * g.W;
+  float d00 = load(r0 + t.x0), d01 = load(r0 + t.x1);
+  float d10 = load(r1 + t.x0), d11 = load(r1 + t.x1);
   float a00 = t.w00 * d00, a01 = t.w01 * d01, a10 = t.w10 * d10, a11 = t.w11 * d11;
   float rx0, rx1, ry0, ry1;
   tap_rays(t, g, k, rx0, ry0, rx1, ry1);
@@ -300,7 +316,7 @@ FM_HD float robust_map(float rx, float ry, const RobustCfg& c, float& gx, float&
     return 0.5f * n2;
   }
   // norm has subgradient 0 at the origin; rsqrt(0) = inf is masked out
-  const float inv_n = n2 > 0.0f ? fm_rsqrt(n2) : 0.0f;
+  const float inv_n = n2 > kTinyNorm2 ? fm_rsqrt(n2) : 0.0f;
   const float n = n2 * inv_n;
   float k = inv_n, val = n;                       // l1: n ; d/ds = s / n
   if (c.mapping == MAP_HUBER) {                   // huber_loss(n, 0, delta) / delta

@@ -176,18 +176,15 @@ struct LeanTerm {
   float P0, P1, P2, d0, d1, d2, su, loss, uvx, uvy;
 };
 
-FM_HD LeanTerm lean_term(float D, float dir0, float dir1, float dir2, float off0, float off1,
-                         float off2, const Cam& k, float x, float y, float flx, float fly, float wgt,
-                         const RobustCfg& rc) {
-  LeanTerm t;
-  t.P0 = fm_fma(D, dir0, off0);
-  t.P1 = fm_fma(D, dir1, off1);
-  t.P2 = fm_fma(D, dir2, off2);
-  const float inv = fm_rcp(t.P2 + kProjEps);
-  float u0 = t.P0 * inv, u1 = t.P1 * inv, u2 = t.P2 * inv;
+// Everything after the projection quotients u = P / (P_z + eps).  ALLFIN: all three are finite
+// (the common case): no nan_to_num, no per-component flags; the rare case runs its own copy of
+// the tail (keeping three rarely-used flags alive through this code costs more instructions
+// than the arithmetic they guard).
+template <bool ALLFIN>
+FM_HD void lean_term_tail(LeanTerm& t, float u0, float u1, float u2, float inv, const Cam& k, float x,
+                          float y, float flx, float fly, float wgt, const RobustCfg& rc) {
   bool f0 = true, f1 = true, f2 = true;
-  // one test for the common all-finite case (a sum that overflows is re-examined per component)
-  if (!((fabsf(u0) + fabsf(u1)) + fabsf(u2) <= 3.0e38f)) {
+  if (!ALLFIN) {
     u0 = nan_to_num1(u0, f0);
     u1 = nan_to_num1(u1, f1);
     u2 = nan_to_num1(u2, f2);
@@ -202,7 +199,7 @@ FM_HD LeanTerm lean_term(float D, float dir0, float dir1, float dir2, float off0
   if (rc.mapping == MAP_L2) {
     kx = rc.ax; ky = rc.ay; val = 0.5f * n2;
   } else {
-    const float inv_n = n2 > 0.0f ? fm_rsqrt(n2) : 0.0f;
+    const float inv_n = n2 > kTinyNorm2 ? fm_rsqrt(n2) : 0.0f;
     const float n = n2 * inv_n;
     float kk = inv_n;
     val = n;
@@ -217,7 +214,7 @@ FM_HD LeanTerm lean_term(float D, float dir0, float dir1, float dir2, float off0
   const float duvx = (wgt * sx) * kx, duvy = (wgt * sy) * ky;
   float du0 = k.fx * duvx, du1 = k.fy * duvy, du2 = fm_fma(k.cx, duvx, k.cy * duvy);
   t.su = fm_fma(du0, u0, du1 * u1);
-  if (!(f0 && f1 && f2)) {  // nan_to_num passes no gradient through replaced components
+  if (!ALLFIN) {  // nan_to_num passes no gradient through replaced components
     if (!f0) du0 = 0.0f;
     if (!f1) du1 = 0.0f;
     if (!f2) du2 = 0.0f;
@@ -226,6 +223,20 @@ FM_HD LeanTerm lean_term(float D, float dir0, float dir1, float dir2, float off0
   t.d1 = du1 * inv;
   const float dot = fm_fma(du0, t.P0, fm_fma(du1, t.P1, du2 * t.P2));
   t.d2 = fm_fma(-dot, inv, du2) * inv;
+}
+
+FM_HD LeanTerm lean_term(float D, float dir0, float dir1, float dir2, float off0, float off1,
+                         float off2, const Cam& k, float x, float y, float flx, float fly, float wgt,
+                         const RobustCfg& rc) {
+  LeanTerm t;
+  t.P0 = fm_fma(D, dir0, off0);
+  t.P1 = fm_fma(D, dir1, off1);
+  t.P2 = fm_fma(D, dir2, off2);
+  const float inv = fm_rcp(t.P2 + kProjEps);
+  const float u0 = t.P0 * inv, u1 = t.P1 * inv, u2 = t.P2 * inv;
+  // one test for the common all-finite case: a NaN or an infinity anywhere fails the comparison
+  if ((fabsf(u0) + fabsf(u1)) + fabsf(u2) <= 3.0e38f) lean_term_tail<true>(t, u0, u1, u2, inv, k, x, y, flx, fly, wgt, rc);
+  else lean_term_tail<false>(t, u0, u1, u2, inv, k, x, y, flx, fly, wgt, rc);
   return t;
 }
 
@@ -292,19 +303,15 @@ FM_HD Cam2 cam2(const Cam& a, const Cam& b) {
   return c;
 }
 
-FM_HD LeanTerm2 lean_term2(F2 D, F2 dir0, F2 dir1, F2 dir2, F2 off0, F2 off1, F2 off2, const Cam2& k,
-                           F2 x, F2 y, F2 flx, F2 fly, F2 wgt, const RobustCfg& rc) {
-  LeanTerm2 t;
-  t.P0 = f2_fma(D, dir0, off0);
-  t.P1 = f2_fma(D, dir1, off1);
-  t.P2 = f2_fma(D, dir2, off2);
-  const F2 den = f2_add(t.P2, f2s(kProjEps));
-  const F2 inv = f2(fm_rcp(den.x), fm_rcp(den.y));
-  F2 u0 = f2_mul(t.P0, inv), u1 = f2_mul(t.P1, inv), u2 = f2_mul(t.P2, inv);
+// Everything after the projection quotients u = P / (P_z + eps).  ALLFIN: all six quotients are
+// finite (the common case): no nan_to_num, no per-component flags -- keeping six rarely-used
+// predicates alive through this code costs more instructions than the arithmetic they guard, so
+// the rare case gets its own copy of the tail instead.
+template <bool ALLFIN>
+FM_HD void lean_term2_tail(LeanTerm2& t, F2 u0, F2 u1, F2 u2, F2 inv, const Cam2& k, F2 x, F2 y, F2 flx,
+                           F2 fly, F2 wgt, const RobustCfg& rc) {
   bool fx0 = true, fx1 = true, fx2 = true, fy0 = true, fy1 = true, fy2 = true;
-  const bool okx = (fabsf(u0.x) + fabsf(u1.x)) + fabsf(u2.x) <= 3.0e38f;
-  const bool oky = (fabsf(u0.y) + fabsf(u1.y)) + fabsf(u2.y) <= 3.0e38f;
-  if (!(okx && oky)) {  // rare: nan_to_num branch (projection.py:56), per component
+  if (!ALLFIN) {  // nan_to_num branch (projection.py:56), per component
     u0.x = nan_to_num1(u0.x, fx0); u1.x = nan_to_num1(u1.x, fx1); u2.x = nan_to_num1(u2.x, fx2);
     u0.y = nan_to_num1(u0.y, fy0); u1.y = nan_to_num1(u1.y, fy1); u2.y = nan_to_num1(u2.y, fy2);
   }
@@ -319,7 +326,7 @@ FM_HD LeanTerm2 lean_term2(F2 D, F2 dir0, F2 dir1, F2 dir2, F2 off0, F2 off1, F2
   if (rc.mapping == MAP_L2) {
     kx = f2s(rc.ax); ky = f2s(rc.ay); val = f2_mul(f2s(0.5f), n2);
   } else {
-    const F2 inv_n = f2(n2.x > 0.0f ? fm_rsqrt(n2.x) : 0.0f, n2.y > 0.0f ? fm_rsqrt(n2.y) : 0.0f);
+    const F2 inv_n = f2(n2.x > kTinyNorm2 ? fm_rsqrt(n2.x) : 0.0f, n2.y > kTinyNorm2 ? fm_rsqrt(n2.y) : 0.0f);
     const F2 n = f2_mul(n2, inv_n);
     F2 kk = inv_n;
     val = n;
@@ -336,7 +343,7 @@ FM_HD LeanTerm2 lean_term2(F2 D, F2 dir0, F2 dir1, F2 dir2, F2 off0, F2 off1, F2
   F2 du0 = f2_mul(k.fx, duvx), du1 = f2_mul(k.fy, duvy);
   F2 du2 = f2_fma(k.cx, duvx, f2_mul(k.cy, duvy));
   t.su = f2_fma(du0, u0, f2_mul(du1, u1));
-  if (!(okx && oky)) {
+  if (!ALLFIN) {
     if (!fx0) du0.x = 0.0f;
     if (!fx1) du1.x = 0.0f;
     if (!fx2) du2.x = 0.0f;
@@ -348,6 +355,22 @@ FM_HD LeanTerm2 lean_term2(F2 D, F2 dir0, F2 dir1, F2 dir2, F2 off0, F2 off1, F2
   t.d1 = f2_mul(du1, inv);
   const F2 dot = f2_fma(du0, t.P0, f2_fma(du1, t.P1, f2_mul(du2, t.P2)));
   t.d2 = f2_mul(f2_fma(f2_neg(dot), inv, du2), inv);
+}
+
+FM_HD LeanTerm2 lean_term2(F2 D, F2 dir0, F2 dir1, F2 dir2, F2 off0, F2 off1, F2 off2, const Cam2& k,
+                           F2 x, F2 y, F2 flx, F2 fly, F2 wgt, const RobustCfg& rc) {
+  LeanTerm2 t;
+  t.P0 = f2_fma(D, dir0, off0);
+  t.P1 = f2_fma(D, dir1, off1);
+  t.P2 = f2_fma(D, dir2, off2);
+  const F2 den = f2_add(t.P2, f2s(kProjEps));
+  const F2 inv = f2(fm_rcp(den.x), fm_rcp(den.y));
+  const F2 u0 = f2_mul(t.P0, inv), u1 = f2_mul(t.P1, inv), u2 = f2_mul(t.P2, inv);
+  // one test per pixel: a NaN or an infinity anywhere makes the sum fail the comparison
+  const bool okx = (fabsf(u0.x) + fabsf(u1.x)) + fabsf(u2.x) <= 3.0e38f;
+  const bool oky = (fabsf(u0.y) + fabsf(u1.y)) + fabsf(u2.y) <= 3.0e38f;
+  if (okx && oky) lean_term2_tail<true>(t, u0, u1, u2, inv, k, x, y, flx, fly, wgt, rc);
+  else lean_term2_tail<false>(t, u0, u1, u2, inv, k, x, y, flx, fly, wgt, rc);
   return t;
 }
 

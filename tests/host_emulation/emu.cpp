@@ -46,7 +46,7 @@ void emu_procrustes_fwd(const float* depth, const float* k4, const float* bflow,
       const int j = indices ? (int)indices[t] : t;
       float acc[kNumMoments] = {0}; float p[3], q[3]; Taps taps;
       point_pq(g, pix_coord(j % W, g.grid.Wf, g.grid.invW), pix_coord(j / W, g.grid.Hf, g.grid.invH), db[j], bflow[((size_t)pair * N + j) * 2], bflow[((size_t)pair * N + j) * 2 + 1],
-               [da, W](int yy, int xx) { return da[yy * W + xx]; }, p, q, taps);
+               [da](int o) { return da[o]; }, p, q, taps);
       moments_add(acc, weights ? weights[(size_t)pair * N + j] : 1.f, p, q);
       for (int k = 0; k < kNumMoments; ++k) m[k] += acc[k];
     }
@@ -167,7 +167,7 @@ void emu_procrustes_bwd(const float* depth, const float* k4, const float* bflow,
       float kacc[8] = {0}; float gdj, gwj;
       distribute_point(g, ad, pix_coord(j % W, g.grid.Wf, g.grid.invW), pix_coord(j / W, g.grid.Hf, g.grid.invH), db[j], weights ? weights[(size_t)pair * N + j] : 1.f,
                        bflow[((size_t)pair * N + j) * 2], bflow[((size_t)pair * N + j) * 2 + 1],
-                       [da, W](int yy, int xx) { return da[yy * W + xx]; }, [gda, W](int y0, int x0, float v0, float v1) { gda[y0 * W + x0] += v0; if (x0 + 1 < W) gda[y0 * W + x0 + 1] += v1; }, gdj, gwj, kacc);
+                       [da](int o) { return da[o]; }, [gda, W](int y0, int x0, float v0, float v1) { gda[y0 * W + x0] += v0; if (x0 + 1 < W) gda[y0 * W + x0 + 1] += v1; }, gdj, gwj, kacc);
       gdb[j] += gdj;
       if (g_weights) g_weights[(size_t)pair * N + j] += gwj;
       for (int k = 0; k < 8; ++k) k4acc[(size_t)a * 4 + k] += kacc[k];
@@ -231,7 +231,7 @@ void emu_procrustes_bwd_tiled(const float* depth, const float* k4, const float* 
           float kacc[8] = {0}; float gdj, gwj;
           distribute_point(g, ad, pix_coord(c, g.grid.Wf, g.grid.invW), pix_coord(r, g.grid.Hf, g.grid.invH), db[j],
                            wt ? wt[j] : 1.f, fl[2 * j], fl[2 * j + 1],
-                           [da, W](int yy, int xx) { return da[yy * W + xx]; }, scatter, gdj, gwj, kacc);
+                           [da](int o) { return da[o]; }, scatter, gdj, gwj, kacc);
           gdb[j] += gdj;
           if (g_weights) g_weights[(size_t)pair * N + j] += gwj;
           for (int k = 0; k < 8; ++k) k4acc[(size_t)a * 4 + k] += kacc[k];
