@@ -469,10 +469,10 @@ def run_gpu(args):
     path_ms = t_fwd + t_flow + t_bwd
     path_gbs = algorithmic_bytes(F_, H_, W_) / (path_ms * 1e-3) / 1e9
     dom_gbs = ops_bytes[dom] / (times[dom] * 1e-3) / 1e9
-    # DRAM bytes per launch from the committed ncu --set full captures (dram__bytes_read.sum +
-    # dram__bytes_write.sum; profiles/r1_v2_ncu_summary.txt, r1_v3_ncu_summary.txt)
-    ncu_traffic = {"procrustes_fwd(k_moments)": 555.9e6, "flow_loss_fwd_bwd(k_flow_lean)": 1118.2e6,
-                   "procrustes_bwd(k_distribute)": 939.1e6}
+    # DRAM bytes per launch from the committed ncu --set full capture of these kernels at this
+    # shape (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1_v12_ncu_summary.txt)
+    ncu_traffic = {"procrustes_fwd(k_moments)": 557.4e6, "flow_loss_fwd_bwd(k_flow_lean)": 1118.0e6,
+                   "procrustes_bwd(k_distribute)": 943.9e6}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(dom_gbs, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(dom_gbs / peak, 4), "traffic": ncu_traffic[dom],
                 "algorithmic_bytes": ops_bytes[dom],
@@ -483,9 +483,9 @@ def run_gpu(args):
                          "ms": round(path_ms, 4), "achieved": round(path_gbs, 1),
                          "frac": round(path_gbs / peak, 4)},
                 "ops_ms": {k: round(v, 4) for k, v in times.items()},
-                "note": "k_distribute is bound by L2 RED (atomic add) throughput, k_flow_lean by FP32 "
-                        "issue, k_moments by L1 gather wavefronts (profiles/README.md); HBM is the "
-                        "denominator the task names"}
+                "note": "k_distribute is bound by L2 RED (atomic add) throughput, k_flow_lean by exposed "
+                        "load latency at 2 CTAs/SM (128 registers), k_moments by L1 gather wavefronts "
+                        "(profiles/README.md); HBM is the denominator the task names"}
 
     if os.environ.get("FM_BENCH_SKIP_CPU") == "1":  # profiling runs (ncu) only
         cpu = {"value": None, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
