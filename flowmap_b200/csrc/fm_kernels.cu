@@ -1054,6 +1054,194 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
   block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
 }
 
+// ------------------------------------------------------------------------------------------
+// Phase D2, tiled, 32 x 64 tiles (opt-in, FM_SCATTER=tiled64): k_distribute_tiled spends a third
+// of its 392 instructions per pixel on per-tile work (statistics, two barriers, the flush of 4
+// window cells per pixel).  Here a block owns 32 x 64 tiles -- every thread processes two groups of
+// four pixels, 32 rows apart, against ONE 64 x 96 window (3 cells per pixel): the tile statistics
+// (window origin, fixed-point scale) come from the upper 32 rows only -- they are only a
+// placement / scaling heuristic, correctness never depends on them (fm_pixel.cuh) -- and the
+// flush reads the high words only if some add of the tile touched one.  48 KB of dynamic shared
+// memory for the window.
+constexpr int kTile64H = 64, kWin64H = kTile64H + 2 * kHalo;
+constexpr size_t kTiled64Smem = (size_t)kWin * kWin64H * (sizeof(unsigned) + sizeof(int));
+
+__global__ void __launch_bounds__(kThreads, 3)
+k_distribute_tiled64(const float* __restrict__ depth, const float* __restrict__ k4,
+                     const float* __restrict__ bflow, float* weights,
+                     const PairAdjoint* __restrict__ adj, float* __restrict__ g_depth,
+                     float* __restrict__ g_weights, double* __restrict__ k4acc, float wsens,
+                     PairLayout lay, AdamFuse adam, int H, int W) {
+  constexpr int NW = kThreads / 32;
+  constexpr int kCells = kWin * kWin64H;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  unsigned* win_lo = reinterpret_cast<unsigned*>(dyn_smem);
+  int* win_hi = reinterpret_cast<int*>(dyn_smem + (size_t)kCells * sizeof(unsigned));
+  __shared__ double smem[8 * NW];
+  __shared__ PairAdjoint s_adj;
+  __shared__ __align__(16) float s_red[4 * NW];
+  __shared__ int s_hi_used[2];
+  const int pair = blockIdx.y;
+  const int N = H * W;
+  if (threadIdx.x < sizeof(PairAdjoint) / 4)
+    reinterpret_cast<float*>(&s_adj)[threadIdx.x] = reinterpret_cast<const float*>(adj + pair)[threadIdx.x];
+  for (int i = threadIdx.x; i < kCells / 4; i += kThreads) {
+    reinterpret_cast<uint4*>(win_lo)[i] = make_uint4(kFixBias, kFixBias, kFixBias, kFixBias);
+    reinterpret_cast<int4*>(win_hi)[i] = make_int4(0, 0, 0, 0);
+  }
+  if (threadIdx.x < 2) s_hi_used[threadIdx.x] = 0;
+  __syncthreads();
+  const PairAdjoint ad = s_adj;
+  const PairAddr pa = pair_addr(lay, pair, N);
+  const PairGeom g = pair_geom(depth, k4, pa, H, W);
+  const int a = pa.k4_frame_a;
+  const float* da = opaque_ptr(depth + pa.depth_a);
+  const float* db = da + N;
+  const float* fl = bflow + pa.flow;
+  float* wt = weights ? weights + pa.weight : nullptr;
+  float* gda = g_depth + pa.depth_a;
+  float* gdb = gda + N;
+  float* gw = g_weights ? g_weights + pa.weight : nullptr;
+  auto load_a = [da](int o) { return __ldg(da + o); };
+  float kacc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
+  float bnd_z, bnd_c;
+  scatter_bound_consts(g, ad, bnd_z, bnd_c);
+  const int tiles_x = W / kTile, tiles_y = (H + kTile64H - 1) / kTile64H;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int parity = 0;
+
+  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x, parity ^= 1) {
+    const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
+    const int X0 = txi * kTile, Y0 = tyi * kTile64H;
+    const int c0 = X0 + 4 * tx;
+    int wx0 = 0, wy0 = 0;
+    float scale = 0.f, inv_scale = 0.f;
+    int* hi_flag = s_hi_used + parity;
+    auto add_u = [](unsigned* p, unsigned v) { return atomicAdd(p, v); };
+    auto add_i = [hi_flag](int* p, int v) { atomicAdd(p, v); *hi_flag = 1; };
+    auto scatter = [&](int y0, int x0, float v0, float v1) {
+      if (!window_add_t<kWin64H>(win_lo, win_hi, wx0, wy0, scale, y0, x0, v0, v1, add_u, add_i))
+        red_pair<true>(gda + y0 * W, x0, W, v0, v1);
+    };
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int r = Y0 + ty + 32 * half;
+      const bool row_ok = r < H;
+      const int base = r * W + c0;
+      float dv[4], wv[4], wraw[4], fv[8], gwv[4], gdv[4];
+      if (row_ok) {
+        load_vec<4>(db + base, dv);
+        load_vec2<4>(fl + 2 * base, fv);
+        if (wt) {  // plain (coherent) load: the logits may be updated in place below
+          const float4 w4 = *reinterpret_cast<const float4*>(wt + base);
+          wraw[0] = w4.x; wraw[1] = w4.y; wraw[2] = w4.z; wraw[3] = w4.w;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) wv[v] = weight_of(wraw[v], wsens);
+        } else {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) wv[v] = 1.f;
+        }
+      }
+      if (half == 0) {  // block-uniform: tile statistics from the upper 32 rows
+        float zm = 0.f, wm = 1.f, sx = 0.f, sy = 0.f;
+        if (row_ok) {
+          zm = fmaxf(fmaxf(fabsf(dv[0]), fabsf(dv[1])), fmaxf(fabsf(dv[2]), fabsf(dv[3])));
+          if (wt && wsens == 0.f) wm = fmaxf(fmaxf(fabsf(wv[0]), fabsf(wv[1])), fmaxf(fabsf(wv[2]), fabsf(wv[3])));
+          sx = (fv[0] + fv[2]) + (fv[4] + fv[6]);
+          sy = (fv[1] + fv[3]) + (fv[5] + fv[7]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sx += __shfl_xor_sync(0xffffffffu, sx, o);
+          sy += __shfl_xor_sync(0xffffffffu, sy, o);
+          zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o));
+        }
+        if (wsens == 0.f && wt) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+        }
+        if (lane == 0) { s_red[warp] = sx; s_red[NW + warp] = sy; s_red[2 * NW + warp] = zm; s_red[3 * NW + warp] = wm; }
+        __syncthreads();
+        static_assert(kThreads / 32 == 8, "two float4 per statistic");
+        const float4* r4 = reinterpret_cast<const float4*>(s_red);
+        const float4 a0 = r4[0], a1 = r4[1], b0 = r4[2], b1 = r4[3], z0 = r4[4], z1 = r4[5], w0 = r4[6], w1 = r4[7];
+        const float mx = ((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w));
+        const float my = ((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w));
+        const float zmax = fmaxf(fmaxf(fmaxf(z0.x, z0.y), fmaxf(z0.z, z0.w)), fmaxf(fmaxf(z1.x, z1.y), fmaxf(z1.z, z1.w)));
+        const float wmax = fmaxf(fmaxf(fmaxf(w0.x, w0.y), fmaxf(w0.z, w0.w)), fmaxf(fmaxf(w1.x, w1.y), fmaxf(w1.z, w1.w)));
+        tile_window_origin_t<kWin64H>(mx, my, min(kTile, H - Y0) * kTile, X0, Y0, g.grid, wx0, wy0);
+        const FixScale fs = fix_scale_for(wmax * fmaf(bnd_z, zmax, bnd_c));
+        scale = fs.scale; inv_scale = fs.inv_scale;
+      }
+      if (row_ok) {
+        const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v], fv[2 * v],
+                           fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
+        red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
+        if (wt) {
+          if (wsens != 0.f) {  // chain rule of the sigmoid: d/d logit = sens * w (1 - w) * d/dw
+#pragma unroll
+            for (int v = 0; v < 4; ++v) gwv[v] *= wsens * wv[v] * (1.0f - wv[v]);
+          }
+          if (gw) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
+          if (adam.on && pair >= adam.first_pair) {  // torch.optim.Adam on the logits (k_adam's order)
+            float4 mm = *reinterpret_cast<float4*>(adam.m + pa.weight + base);
+            float4 vv = *reinterpret_cast<float4*>(adam.v + pa.weight + base);
+            float* mp = &mm.x; float* vp = &vv.x;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              mp[v] = mp[v] + adam.omb1 * (gwv[v] - mp[v]);
+              vp[v] = vp[v] * adam.beta2 + adam.omb2 * gwv[v] * gwv[v];
+              wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
+            }
+            *reinterpret_cast<float4*>(adam.m + pa.weight + base) = mm;
+            *reinterpret_cast<float4*>(adam.v + pa.weight + base) = vv;
+            *reinterpret_cast<float4*>(wt + base) = make_float4(wraw[0], wraw[1], wraw[2], wraw[3]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // flush (see k_distribute_tiled); the two cases of the block-uniform any_hi are separate loops
+    // so that the common one carries no 64-bit conversion code at all
+    const bool any_hi = *hi_flag != 0;
+    if (threadIdx.x == 0) s_hi_used[parity ^ 1] = 0;
+    if (!any_hi) {
+      for (int i = threadIdx.x; i < kCells / 4; i += kThreads) {
+        const uint4 l4 = reinterpret_cast<uint4*>(win_lo)[i];
+        const unsigned dx = l4.x ^ kFixBias, dy = l4.y ^ kFixBias, dz = l4.z ^ kFixBias, dw = l4.w ^ kFixBias;
+        if (((dx | dy) | (dz | dw)) == 0) continue;
+        const int gy = wy0 + (i >> 4), gx = wx0 + ((i & 15) << 2);
+        if (gy < H && gx + 3 < W)  // wx0, wy0 >= 0: the window was clamped onto the image
+          red_add4(gda + gy * W + gx, (float)(int)dx * inv_scale, (float)(int)dy * inv_scale,
+                   (float)(int)dz * inv_scale, (float)(int)dw * inv_scale);
+        reinterpret_cast<uint4*>(win_lo)[i] = make_uint4(kFixBias, kFixBias, kFixBias, kFixBias);
+      }
+    } else {
+      for (int i = threadIdx.x; i < kCells / 4; i += kThreads) {
+        const uint4 l4 = reinterpret_cast<uint4*>(win_lo)[i];
+        const int4 h4 = reinterpret_cast<int4*>(win_hi)[i];
+        const unsigned dirty = ((l4.x ^ kFixBias) | (l4.y ^ kFixBias)) | ((l4.z ^ kFixBias) | (l4.w ^ kFixBias)) |
+                               (unsigned)((h4.x | h4.y) | (h4.z | h4.w));
+        if (dirty == 0) continue;
+        const int gy = wy0 + (i >> 4), gx = wx0 + ((i & 15) << 2);
+        if (gy < H && gx + 3 < W)
+          red_add4(gda + gy * W + gx, fix_value(l4.x, h4.x) * inv_scale, fix_value(l4.y, h4.y) * inv_scale,
+                   fix_value(l4.z, h4.z) * inv_scale, fix_value(l4.w, h4.w) * inv_scale);
+        reinterpret_cast<uint4*>(win_lo)[i] = make_uint4(kFixBias, kFixBias, kFixBias, kFixBias);
+        reinterpret_cast<int4*>(win_hi)[i] = make_int4(0, 0, 0, 0);
+      }
+    }
+    __syncthreads();
+  }
+  block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
+}
+
 __global__ void k_k4_finalize(const double* __restrict__ k4acc, const double* __restrict__ flowacc,
                               int include_flow, const float* __restrict__ flow_scale,
                               float* __restrict__ g_k4, int B, int F) {
@@ -2081,16 +2269,26 @@ int blocks_for_points(int n) {
   return nb < 1 ? 1 : nb;
 }
 
-// Procrustes-adjoint scatter: FM_SCATTER=tiled selects the shared-memory fixed-point window
-// (k_distribute_tiled), FM_SCATTER=red the global vector REDs (k_distribute).
-bool tiled_scatter_enabled() {  // read per call (a getenv): tests and tools flip it inside one process
+// Procrustes-adjoint scatter: FM_SCATTER=tiled / tiled64 select the shared-memory fixed-point
+// windows (k_distribute_tiled / k_distribute_tiled64), anything else the global vector REDs
+// (k_distribute).  Read per call (a getenv): tests and tools flip it inside one process.
+int scatter_mode() {
   const char* v = getenv("FM_SCATTER");
-  return v && !strcmp(v, "tiled");
+  if (!v) return 0;
+  if (!strcmp(v, "tiled")) return 1;
+  if (!strcmp(v, "tiled64")) return 2;
+  return 0;
 }
 
 bool flow_staged_enabled() {  // read per call, like FM_SCATTER
   const char* v = getenv("FM_FLOW_STAGED");
   return v && !strcmp(v, "1");
+}
+
+int tiles_per_cta64() {  // 32 x 64 tiles: half as many per block for the same pixels per block
+  const char* v = getenv("FM_TILED_TILES_PER_CTA");
+  const int n = v ? atoi(v) : 0;
+  return n >= 1 && n <= 1024 ? n : 4;
 }
 
 int tiles_per_cta() {  // tuning knob of tools/ab_scatter.py (a block walks this many 32 x 32 tiles)
@@ -2262,7 +2460,14 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
   if (indices) {
     dim3 grid(blocks_for_points(num_indices), BP);
     k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
-  } else if (W % kTile == 0 && lay.cand == 1 && tiled_scatter_enabled()) {
+  } else if (W % kTile == 0 && lay.cand == 1 && scatter_mode() == 2) {  // opt-in experiment, 32 x 64 tiles
+    static const cudaError_t attr = cudaFuncSetAttribute(k_distribute_tiled64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiled64Smem);
+    if (attr != cudaSuccess) return fail("k_distribute_tiled64: shared memory attribute", attr);
+    const int tiles = (W / kTile) * ((H + kTile64H - 1) / kTile64H);
+    const int per_cta = tiles_per_cta64();
+    dim3 grid((tiles + per_cta - 1) / per_cta, BP);
+    k_distribute_tiled64<<<grid, kThreads, kTiled64Smem, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
+  } else if (W % kTile == 0 && lay.cand == 1 && scatter_mode() == 1) {
     const int tiles = (W / kTile) * ((H + kTile - 1) / kTile);
     const int per_cta = tiles_per_cta();
     dim3 grid((tiles + per_cta - 1) / per_cta, BP);

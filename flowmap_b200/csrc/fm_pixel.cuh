@@ -594,10 +594,13 @@ FM_HD FixScale fix_scale_for(float bound) {
 }
 
 // Window origin of a tile: tile origin - halo, shifted by the tile's mean backward flow (x to a
-// multiple of 4 so that the flush stays 16-byte aligned; W is a multiple of kTile).  fmaxf / fminf also map a NaN mean to a
-// finite origin: any origin is correct, taps are clamped into the image and far ones fall back.
-FM_HD void tile_window_origin(float sum_flx, float sum_fly, int valid_pixels, int X0, int Y0,
-                              const GridDims& grid, int& wx0, int& wy0) {
+// multiple of 4 so that the flush stays 16-byte aligned; W is a multiple of kTile).  fmaxf / fminf
+// also map a NaN mean to a finite origin: any origin is correct, taps are clamped into the image
+// and far ones fall back.  WINH: rows of the window (kWin for 32-row tiles, kWin + 32 for the
+// 64-row tiles of k_distribute_tiled64); the window is always kWin columns wide.
+template <int WINH>
+FM_HD void tile_window_origin_t(float sum_flx, float sum_fly, int valid_pixels, int X0, int Y0,
+                                const GridDims& grid, int& wx0, int& wy0) {
   const float inv_cnt = 1.0f / (float)valid_pixels;
   const float mx = fminf(fmaxf(sum_flx * inv_cnt, -4.0f), 4.0f);
   const float my = fminf(fmaxf(sum_fly * inv_cnt, -4.0f), 4.0f);
@@ -606,24 +609,33 @@ FM_HD void tile_window_origin(float sum_flx, float sum_fly, int valid_pixels, in
   // keep the window on the image (taps are clamped into it: flows that leave the frame pile up
   // on the border rows / columns, which a window hanging over the edge would miss)
   wx0 = max_i(min_i(wx0, grid.W - kWin), 0);
-  wy0 = max_i(min_i(wy0, grid.H - kWin), 0);
+  wy0 = max_i(min_i(wy0, grid.H - WINH), 0);
+}
+FM_HD void tile_window_origin(float sum_flx, float sum_fly, int valid_pixels, int X0, int Y0,
+                              const GridDims& grid, int& wx0, int& wy0) {
+  tile_window_origin_t<kWin>(sum_flx, sum_fly, valid_pixels, X0, Y0, grid, wx0, wy0);
 }
 
 // One tap row of a pixel into the window; false = outside the window or too large for the
 // fixed-point range (the caller then adds v0 / v1 to global memory as floats).
-template <typename AtomicAddU, typename AtomicAddI>
-FM_HD bool window_add(unsigned* lo, int* hi, int wx0, int wy0, float scale, int y0, int x0, float v0,
-                      float v1, AtomicAddU add_u, AtomicAddI add_i) {
+template <int WINH, typename AtomicAddU, typename AtomicAddI>
+FM_HD bool window_add_t(unsigned* lo, int* hi, int wx0, int wy0, float scale, int y0, int x0, float v0,
+                        float v1, AtomicAddU add_u, AtomicAddI add_i) {
   const int ux = x0 - wx0, uy = y0 - wy0;
   const float s0 = v0 * scale, s1 = v1 * scale;
   // NaN compares false: non-finite values take the fallback and propagate like in the float path
-  if (!((unsigned)ux < (unsigned)(kWin - 1) && (unsigned)uy < (unsigned)kWin && fabsf(s0) < kFixLimit &&
+  if (!((unsigned)ux < (unsigned)(kWin - 1) && (unsigned)uy < (unsigned)WINH && fabsf(s0) < kFixLimit &&
         fabsf(s1) < kFixLimit))
     return false;
   const int cell = uy * kWin + ux;
   fix_add(lo, hi, cell, s0, add_u, add_i);
   fix_add(lo, hi, cell + 1, s1, add_u, add_i);
   return true;
+}
+template <typename AtomicAddU, typename AtomicAddI>
+FM_HD bool window_add(unsigned* lo, int* hi, int wx0, int wy0, float scale, int y0, int x0, float v0,
+                      float v1, AtomicAddU add_u, AtomicAddI add_i) {
+  return window_add_t<kWin>(lo, hi, wx0, wy0, scale, y0, x0, v0, v1, add_u, add_i);
 }
 
 }  // namespace fm

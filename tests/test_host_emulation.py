@@ -169,7 +169,7 @@ def test_fixed_point_scale_maps_the_bound_below_2_pow_29(emu):
 
 
 def _tiled_case(emu, F_, H, W, seed=0, sigma=0.01, outliers=0.0, wscale=1.0, shift=(0.0, 0.0),
-                depth_scale=1.0, grt_scale=1.0):
+                depth_scale=1.0, grt_scale=1.0, tall=False):
     rng = np.random.default_rng(seed)
     _, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
     depth = (depth_scale * (1.0 + 0.5 * rng.random((F_, H, W)) + 0.3 * np.sin(xx / 17.0)[None])).astype(np.float32)
@@ -192,7 +192,7 @@ def _tiled_case(emu, F_, H, W, seed=0, sigma=0.01, outliers=0.0, wscale=1.0, shi
         gd, gw, k4acc = np.zeros_like(depth), np.zeros_like(w), np.zeros((F_, 4))
         stats = np.zeros(8, dtype=np.int64)
         if tiled:
-            emu.emu_procrustes_bwd_tiled(_p(depth), _p(k4), _p(fb), _p(w), _p(state), _p(g_rt), _p(gd), _p(gw),
+            (emu.emu_procrustes_bwd_tiled64 if tall else emu.emu_procrustes_bwd_tiled)(_p(depth), _p(k4), _p(fb), _p(w), _p(state), _p(g_rt), _p(gd), _p(gw),
                                          _p(k4acc), _p(stats), 1, F_, H, W)
         else:
             emu.emu_procrustes_bwd(_p(depth), _p(k4), _p(fb), _p(w), None, 0, _p(state), _p(g_rt), _p(gd),
@@ -205,6 +205,8 @@ TILED_CASES = [
     dict(F_=3, H=72, W=96),                                  # iid +-6 px jitter (the bench's flows)
     dict(F_=3, H=40, W=64),                                  # partial last tile row
     dict(F_=3, H=24, W=32),                                  # image smaller than the window
+    dict(F_=3, H=100, W=64),                                 # second half of the last 64-row tile partly outside
+    dict(F_=2, H=136, W=96, shift=(0.0, 0.08)),              # vertical motion across several tile rows
     dict(F_=3, H=72, W=96, outliers=0.05),                   # far taps: float fallback
     dict(F_=3, H=72, W=96, wscale=5.0),                      # raw weights above 1
     dict(F_=3, H=72, W=96, shift=(0.3, -0.2)),               # large coherent motion: shifted window
@@ -215,12 +217,13 @@ TILED_CASES = [
 ]
 
 
+@pytest.mark.parametrize("tall", [False, True], ids=["tile32x32", "tile32x64"])
 @pytest.mark.parametrize("case", TILED_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
-def test_tiled_scatter_matches_direct_scatter(emu, case):
-    """Serial twin of k_distribute_tiled vs the direct float scatter of k_distribute on the same
-    inputs: identical aligned / weight / intrinsics parts, depth gradient equal up to the float32
-    rounding of the direct path's own cell sums."""
-    (gd0, gw0, k0, _), (gd1, gw1, k1, st) = _tiled_case(emu, **case)
+def test_tiled_scatter_matches_direct_scatter(emu, case, tall):
+    """Serial twin of k_distribute_tiled / k_distribute_tiled64 vs the direct float scatter of
+    k_distribute on the same inputs: identical aligned / weight / intrinsics parts, depth gradient
+    equal up to the float32 rounding of the direct path's own cell sums."""
+    (gd0, gw0, k0, _), (gd1, gw1, k1, st) = _tiled_case(emu, tall=tall, **case)
     assert np.array_equal(gw0, gw1)
     assert np.abs(k0 - k1).max() <= 1e-12 * max(1.0, np.abs(k0).max())
     assert rel_l2(gd1, gd0) <= 5e-7

@@ -1,5 +1,6 @@
-"""A/B of the two Procrustes-adjoint scatters on a B200: global vector REDs (k_distribute,
-FM_SCATTER=red) vs the shared-memory fixed-point window (k_distribute_tiled, FM_SCATTER=tiled).
+"""A/B of the Procrustes-adjoint scatters on a B200: global vector REDs (k_distribute,
+FM_SCATTER=red) vs the shared-memory fixed-point windows (k_distribute_tiled, FM_SCATTER=tiled:
+32 x 32 tiles; k_distribute_tiled64, FM_SCATTER=tiled64: 32 x 64 tiles).
 
 1. same inputs through fm_procrustes_fwd -> fm_flow_loss_fwd_bwd -> fm_procrustes_bwd in both
    modes at several shapes / flow fields: depth, weight and intrinsics gradients must agree;
@@ -23,7 +24,7 @@ from flowmap_b200.types import Batch, Flows, Tracks  # noqa: E402
 
 dev = torch.device("cuda:0")
 P = lambda x: x.data_ptr()  # noqa: E731
-MODES = ("red", "tiled")
+MODES = ("red", "tiled", "tiled64")
 
 
 def set_mode(m):
@@ -90,14 +91,17 @@ def compare(f, h, w, kind, raw_weights=False):
         fwd(); bwd()
         torch.cuda.synchronize()
         res[m] = [o.clone() for o in outs]
-    r = {"shape": [f, h, w], "flows": kind, "raw_weights": raw_weights,
-         "g_depth_rel": rel(res["tiled"][0], res["red"][0]),
-         "g_weights_equal": bool(torch.equal(res["tiled"][1], res["red"][1])),
-         "g_weights_rel": rel(res["tiled"][1], res["red"][1]),
-         "g_k4_rel": rel(res["tiled"][2], res["red"][2]),
-         "finite": bool(torch.isfinite(res["tiled"][0]).all())}
-    # intrinsics sums: float32 per-thread partials over different pixel sets in the two kernels
-    r["ok"] = r["g_depth_rel"] <= 2e-6 and r["g_weights_rel"] <= 1e-7 and r["g_k4_rel"] <= 5e-5 and r["finite"]
+    r = {"shape": [f, h, w], "flows": kind, "raw_weights": raw_weights, "ok": True}
+    for m in MODES[1:]:
+        d = {"g_depth_rel": rel(res[m][0], res["red"][0]),
+             "g_weights_equal": bool(torch.equal(res[m][1], res["red"][1])),
+             "g_weights_rel": rel(res[m][1], res["red"][1]),
+             "g_k4_rel": rel(res[m][2], res["red"][2]),
+             "finite": bool(torch.isfinite(res[m][0]).all())}
+        # intrinsics sums: float32 per-thread partials over different pixel sets in the kernels
+        d["ok"] = d["g_depth_rel"] <= 2e-6 and d["g_weights_rel"] <= 1e-7 and d["g_k4_rel"] <= 5e-5 and d["finite"]
+        r[m] = d
+        r["ok"] = r["ok"] and d["ok"]
     print("compare", json.dumps(r), flush=True)
     return r
 
@@ -153,15 +157,17 @@ def time_steps(steps=40):
         out[m] = {"full_ms": full, "flow_only_ms": flow_only, "loss": loss}
         out[m + "_depth"] = depth
         print(f"fused step {m:6s} full {full:.4f} ms  flow-only {flow_only:.4f} ms  loss after {steps + 5} steps {loss:.6f}", flush=True)
-    out["depth_after_steps_rel"] = rel(out.pop("tiled_depth"), out.pop("red_depth"))
-    print("depth after the optimisation steps, tiled vs red: rel", out["depth_after_steps_rel"], flush=True)
+    red_depth = out.pop("red_depth")
+    for m in MODES[1:]:
+        out[m]["depth_after_steps_rel"] = rel(out.pop(m + "_depth"), red_depth)
+        print(f"depth after the optimisation steps, {m} vs red: rel", out[m]["depth_after_steps_rel"], flush=True)
     return out
 
 
 def main():
     quick = "--quick" in sys.argv
     report = {"compare": [], "bwd_ms": {}, "steps": None}
-    shapes = [(3, 24, 32), (4, 40, 64), (5, 72, 96), (3, 128, 128), (3, 360, 640)]
+    shapes = [(3, 24, 32), (4, 40, 64), (3, 100, 64), (5, 72, 96), (3, 128, 128), (3, 360, 640)]
     for f, h, w in shapes:
         for kind in ("iid", "smooth", "shift", "leave", "outliers"):
             report["compare"].append(compare(f, h, w, kind))
@@ -172,11 +178,9 @@ def main():
     for kind in ("iid", "smooth"):
         report["bwd_ms"][kind] = time_bwd(bench.F_, bench.H_, bench.W_, kind)
     report["tiles_per_cta_ms"] = {}
-    set_mode("tiled")
-    for tpc in (2, 4, 8, 16, 40):
+    for tpc in (2, 4, 8, 16):
         os.environ["FM_TILED_TILES_PER_CTA"] = str(tpc)
-        report["tiles_per_cta_ms"][tpc] = time_bwd(bench.F_, bench.H_, bench.W_, "iid", n=10)["tiled"]
-        print("tiles per CTA", tpc, report["tiles_per_cta_ms"][tpc], flush=True)
+        report["tiles_per_cta_ms"][tpc] = time_bwd(bench.F_, bench.H_, bench.W_, "iid", n=10)
     os.environ.pop("FM_TILED_TILES_PER_CTA")
     if not quick:
         report["steps"] = time_steps()
