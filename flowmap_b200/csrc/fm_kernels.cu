@@ -531,141 +531,6 @@ k_flow_lean(const float* __restrict__ depth, const float* __restrict__ k4, const
   block_accumulate<kFlowLeanVals>(acc, leanacc + (size_t)frame * kFlowAcc, smem);
 }
 
-// ------------------------------------------------------------------------------------------
-// Phase C, staged (opt-in, FM_FLOW_STAGED=1, W % 4 == 0): the same arithmetic as k_flow_lean, but
-// the seven 16-byte operands of a thread's NEXT four pixels (depth, 2 x forward flow, forward
-// mask, 2 x backward flow, backward mask) travel global -> shared memory with cp.async while the
-// current four pixels are processed.  Every thread stages and reads back only its own slots, so
-// no barrier is needed: cp.async.wait_group makes a thread's own copies visible to it.  The
-// default kernel holds 128 registers (2 CTAs/SM = 4 warps per scheduler) and waits on its own
-// loads (51 % issue utilisation, profiles/README.md); shared memory is the only place left to
-// keep a second iteration's operands in flight.  kFlowStages x 7 x 4 KB per block.
-constexpr int kFlowStages = 3;
-constexpr int kFlowOps = 7;
-constexpr size_t kFlowStagedSmem = (size_t)kFlowStages * kFlowOps * kThreads * sizeof(float4);
-
-__device__ __forceinline__ void cp_async16(float4* smem_dst, const float* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <bool HASF, bool HASB, bool FOCAL>
-__device__ __forceinline__ void flow_frame_body_lean_staged(const FlowFrameLean& f, const float* __restrict__ D,
-                                                            const float* __restrict__ ff, const float* __restrict__ mf,
-                                                            const float* __restrict__ fb, const float* __restrict__ mb,
-                                                            float* __restrict__ gd, float g, const RobustCfg& rc,
-                                                            const GridDims& grid, int N, float* acc, float4* stage) {
-  const int W = grid.W;
-  const int stride = gridDim.x * kThreads * 4;
-  int base = (blockIdx.x * kThreads + threadIdx.x) * 4;
-  int r = base / W, c0 = base - r * W;
-  const int dr = stride / W, dc = stride - dr * W;
-  F2 acc2[kFlowLeanVals];
-#pragma unroll
-  for (int k = 0; k < kFlowLeanVals; ++k) acc2[k] = f2s(0.f);
-  // slot of operand `op` in stage `st` for this thread
-  auto slot = [stage](int st, int op) { return stage + ((size_t)(st * kFlowOps + op) * kThreads + threadIdx.x); };
-  auto issue = [&](int st, int b) {  // one commit group per iteration, even an empty one
-    if (b < N) {
-      cp_async16(slot(st, 0), D + b);
-      if (HASF) { cp_async16(slot(st, 1), ff + 2 * b); cp_async16(slot(st, 2), ff + 2 * b + 4); cp_async16(slot(st, 3), mf + b); }
-      if (HASB) { cp_async16(slot(st, 4), fb + 2 * b); cp_async16(slot(st, 5), fb + 2 * b + 4); cp_async16(slot(st, 6), mb + b); }
-    }
-    cp_async_commit();
-  };
-  // prologue: kFlowStages - 1 iterations in flight
-  int ahead = base;
-#pragma unroll
-  for (int k = 0; k < kFlowStages - 1; ++k) { issue(k, ahead); ahead += stride; }
-  int st = 0, st_issue = kFlowStages - 1;
-#pragma unroll 1
-  for (; base < N; base += stride) {
-    issue(st_issue, ahead);
-    ahead += stride;
-    cp_async_wait<kFlowStages - 1>();  // all but the newest kFlowStages - 1 groups: this iteration's is complete
-    const float4 d4 = *slot(st, 0);
-    const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-    float ffv[8], fbv[8], mfv[4], mbv[4], out[4];
-    if (HASF) {
-      const float4 a = *slot(st, 1), b = *slot(st, 2), m = *slot(st, 3);
-      ffv[0] = a.x; ffv[1] = a.y; ffv[2] = a.z; ffv[3] = a.w; ffv[4] = b.x; ffv[5] = b.y; ffv[6] = b.z; ffv[7] = b.w;
-      mfv[0] = m.x; mfv[1] = m.y; mfv[2] = m.z; mfv[3] = m.w;
-    }
-    if (HASB) {
-      const float4 a = *slot(st, 4), b = *slot(st, 5), m = *slot(st, 6);
-      fbv[0] = a.x; fbv[1] = a.y; fbv[2] = a.z; fbv[3] = a.w; fbv[4] = b.x; fbv[5] = b.y; fbv[6] = b.z; fbv[7] = b.w;
-      mbv[0] = m.x; mbv[1] = m.y; mbv[2] = m.z; mbv[3] = m.w;
-    }
-    const float y = pix_coord(r, grid.Hf, grid.invH);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int v = 2 * h;
-      const F2 x = f2(pix_coord(c0 + v, grid.Wf, grid.invW), pix_coord(c0 + v + 1, grid.Wf, grid.invW));
-      const F2 z = f2s(0.f);
-      const F2 o = flow_pixel_lean2<HASF, HASB, FOCAL>(
-          f, x, y, f2(dv[v], dv[v + 1]), HASF ? f2(ffv[2 * v], ffv[2 * v + 2]) : z,
-          HASF ? f2(ffv[2 * v + 1], ffv[2 * v + 3]) : z, HASF ? f2(mfv[v], mfv[v + 1]) : z,
-          HASB ? f2(fbv[2 * v], fbv[2 * v + 2]) : z, HASB ? f2(fbv[2 * v + 1], fbv[2 * v + 3]) : z,
-          HASB ? f2(mbv[v], mbv[v + 1]) : z, g, rc, acc2);
-      out[v] = o.x; out[v + 1] = o.y;
-    }
-    *reinterpret_cast<float4*>(gd + base) = make_float4(out[0], out[1], out[2], out[3]);
-    r += dr; c0 += dc;
-    if (c0 >= W) { c0 -= W; ++r; }
-    st = st + 1 == kFlowStages ? 0 : st + 1;
-    st_issue = st_issue + 1 == kFlowStages ? 0 : st_issue + 1;
-  }
-  cp_async_wait<0>();
-#pragma unroll
-  for (int k = 0; k < kFlowLeanVals; ++k) acc[k] += acc2[k].x + acc2[k].y;
-}
-
-template <bool FOCAL>
-__global__ void __launch_bounds__(kThreads, 2)
-k_flow_lean_staged(const float* __restrict__ depth, const float* __restrict__ k4, const float* __restrict__ rt,
-                   const float* __restrict__ fflow, const float* __restrict__ bflow,
-                   const float* __restrict__ fmask, const float* __restrict__ bmask,
-                   const double* __restrict__ mask_sum, int mapping, float delta, float loss_weight,
-                   float* __restrict__ g_depth, double* __restrict__ leanacc, int F, int H, int W) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  float4* stage = reinterpret_cast<float4*>(dyn_smem);
-  __shared__ double smem[kFlowLeanVals * (kThreads / 32)];
-  const int frame = blockIdx.y;
-  const int bi = frame / F, i = frame - bi * F;
-  const int N = H * W;
-  const bool hasF = i < F - 1, hasB = i > 0;
-  FlowFrameLean f;
-  f.kk = make_cam(load_k4(k4, frame));
-  f.kn = make_cam(load_k4(k4, hasF ? frame + 1 : frame));
-  f.kp = make_cam(load_k4(k4, hasB ? frame - 1 : frame));
-  const int pairF = bi * (F - 1) + i, pairB = pairF - 1;
-  Rt tf, tb;
-  if (hasF) tf = load_rt(rt, pairF);
-  if (hasB) tb = load_rt(rt, pairB);
-  fill_lean(f, hasF ? &tf : nullptr, hasB ? &tb : nullptr);
-  double den = mask_sum ? *mask_sum : 1.0;
-  if (den == 0.0) den = 1.0;  // loss_flow.py:70 "valid_sum or 1"
-  const float g = (float)((double)loss_weight / den);
-  const RobustCfg rc = make_robust(mapping, delta, H, W);
-  const GridDims grid = make_grid(H, W);
-  const float* D = depth + (size_t)frame * N;
-  const float* ff = fflow + (size_t)(hasF ? pairF : 0) * N * 2;
-  const float* mf = fmask + (size_t)(hasF ? pairF : 0) * N;
-  const float* fb = bflow + (size_t)(hasB ? pairB : 0) * N * 2;
-  const float* mb = bmask + (size_t)(hasB ? pairB : 0) * N;
-  float* gd = g_depth + (size_t)frame * N;
-  float acc[kFlowLeanVals];
-#pragma unroll
-  for (int k = 0; k < kFlowLeanVals; ++k) acc[k] = 0.f;
-  if (hasF && hasB) flow_frame_body_lean_staged<true, true, FOCAL>(f, D, ff, mf, fb, mb, gd, g, rc, grid, N, acc, stage);
-  else if (hasF) flow_frame_body_lean_staged<true, false, FOCAL>(f, D, ff, mf, fb, mb, gd, g, rc, grid, N, acc, stage);
-  else flow_frame_body_lean_staged<false, true, FOCAL>(f, D, ff, mf, fb, mb, gd, g, rc, grid, N, acc, stage);
-  block_accumulate<kFlowLeanVals>(acc, leanacc + (size_t)frame * kFlowAcc, smem);
-}
-
 // Rewrites each frame's lean accumulators (slots 0-13) into the standard layout in place.
 __global__ void k_flow_lean_convert(double* __restrict__ flowacc, const float* __restrict__ rt,
                                     const float* __restrict__ k4, int focal_mode, int B, int F, int H, int W) {
@@ -2280,11 +2145,6 @@ int scatter_mode() {
   return 0;
 }
 
-bool flow_staged_enabled() {  // read per call, like FM_SCATTER
-  const char* v = getenv("FM_FLOW_STAGED");
-  return v && !strcmp(v, "1");
-}
-
 int tiles_per_cta64() {  // 32 x 64 tiles: half as many per block for the same pixels per block
   const char* v = getenv("FM_TILED_TILES_PER_CTA");
   const int n = v ? atoi(v) : 0;
@@ -2318,16 +2178,7 @@ int launch_flow(const float* depth, const float* k4, const float* rt, const floa
     return 0;
   }
   const bool focal = intrinsics_mode == 1;
-  if (vec == 4 && flow_staged_enabled()) {  // opt-in experiment (profiles/README.md)
-    static const cudaError_t attr = [] {
-      cudaError_t e = cudaFuncSetAttribute(k_flow_lean_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlowStagedSmem);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_flow_lean_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlowStagedSmem);
-      return e;
-    }();
-    if (attr != cudaSuccess) return fail("k_flow_lean_staged: shared memory attribute", attr);
-    if (focal) k_flow_lean_staged<true><<<grid, kThreads, kFlowStagedSmem, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
-    else k_flow_lean_staged<false><<<grid, kThreads, kFlowStagedSmem, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
-  } else if (vec == 4) {
+  if (vec == 4) {
     if (focal) k_flow_lean<4, true, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
     else k_flow_lean<4, false, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
   } else {
