@@ -201,6 +201,13 @@ __device__ __forceinline__ const float* opaque_ptr(const float* p) {
   return p;
 }
 
+// Same for a 32-bit value (a shared-space base address the compiler would otherwise re-derive from
+// %cluster_ctarank at every use).
+__device__ __forceinline__ unsigned opaque_u32(unsigned v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+
 // Load the 4 (or 1) values a thread owns.
 template <int VEC>
 __device__ __forceinline__ void load_vec(const float* p, float* out) {
@@ -742,6 +749,16 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
   block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
 }
 
+// Native 32-bit integer atomics on a shared-space address (ATOMS.ADD / its no-return form).
+__device__ __forceinline__ unsigned atoms_add_u32(unsigned saddr, unsigned v) {
+  unsigned old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void reds_add_s32(unsigned saddr, int v) {
+  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // Phase D2, tiled (dense path, W % 32 == 0): the bilinear scatter into the EARLIER frame's depth
 // gradient is privatised in shared memory.  A block owns 32 x 32 tiles of the LATER frame; the
@@ -795,6 +812,10 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
   for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
   float bnd_z, bnd_c;  // bound of a tile's contributions = wmax * (bnd_z * max|depth_b| + bnd_c)
   scatter_bound_consts(g, ad, bnd_z, bnd_c);
+  // 32-bit shared-space addresses of the window: the atomics below address it directly instead of
+  // re-deriving a generic address for every tap
+  const unsigned lo_addr = opaque_u32((unsigned)__cvta_generic_to_shared(win_lo));
+  const unsigned hi_addr = lo_addr + (unsigned)((const char*)win_hi - (const char*)win_lo);
   const int tiles_x = W / kTile, tiles_y = (H + kTile - 1) / kTile;
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -856,10 +877,10 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
     const FixScale fs = fix_scale_for(wmax * fmaf(bnd_z, zmax, bnd_c));
     const float inv_scale = fs.inv_scale;
     int* hi_flag = s_hi_used + parity;
-    auto add_u = [](unsigned* p, unsigned v) { return atomicAdd(p, v); };
-    auto add_i = [hi_flag](int* p, int v) { atomicAdd(p, v); *hi_flag = 1; };
+    auto add_u = [lo_addr](int cell, unsigned v) { return atoms_add_u32(lo_addr + 4u * (unsigned)cell, v); };
+    auto add_i = [hi_addr, hi_flag](int cell, int v) { reds_add_s32(hi_addr + 4u * (unsigned)cell, v); *hi_flag = 1; };
     auto scatter = [&](int y0, int x0, float v0, float v1) {
-      if (!window_add(win_lo, win_hi, wx0, wy0, fs.scale, y0, x0, v0, v1, add_u, add_i))
+      if (!window_add(wx0, wy0, fs.scale, y0, x0, v0, v1, add_u, add_i))
         red_pair<true>(gda + y0 * W, x0, W, v0, v1);
     };
     if (row_ok) {
@@ -973,6 +994,10 @@ k_distribute_tiled64(const float* __restrict__ depth, const float* __restrict__ 
   for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
   float bnd_z, bnd_c;
   scatter_bound_consts(g, ad, bnd_z, bnd_c);
+  // 32-bit shared-space addresses of the window: the atomics below address it directly instead of
+  // re-deriving a generic address for every tap
+  const unsigned lo_addr = opaque_u32((unsigned)__cvta_generic_to_shared(win_lo));
+  const unsigned hi_addr = lo_addr + (unsigned)((const char*)win_hi - (const char*)win_lo);
   const int tiles_x = W / kTile, tiles_y = (H + kTile64H - 1) / kTile64H;
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -985,10 +1010,10 @@ k_distribute_tiled64(const float* __restrict__ depth, const float* __restrict__ 
     int wx0 = 0, wy0 = 0;
     float scale = 0.f, inv_scale = 0.f;
     int* hi_flag = s_hi_used + parity;
-    auto add_u = [](unsigned* p, unsigned v) { return atomicAdd(p, v); };
-    auto add_i = [hi_flag](int* p, int v) { atomicAdd(p, v); *hi_flag = 1; };
+    auto add_u = [lo_addr](int cell, unsigned v) { return atoms_add_u32(lo_addr + 4u * (unsigned)cell, v); };
+    auto add_i = [hi_addr, hi_flag](int cell, int v) { reds_add_s32(hi_addr + 4u * (unsigned)cell, v); *hi_flag = 1; };
     auto scatter = [&](int y0, int x0, float v0, float v1) {
-      if (!window_add_t<kWin64H>(win_lo, win_hi, wx0, wy0, scale, y0, x0, v0, v1, add_u, add_i))
+      if (!window_add_t<kWin64H>(wx0, wy0, scale, y0, x0, v0, v1, add_u, add_i))
         red_pair<true>(gda + y0 * W, x0, W, v0, v1);
     };
 #pragma unroll 1

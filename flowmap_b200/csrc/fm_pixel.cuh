@@ -510,8 +510,9 @@ FM_HD void distribute_point(const PairGeom& g, const PairAdjoint& ad, float x, f
 // added to the low word (which starts at 2^31) with one atomic add; the returned old value tells
 // whether that add wrapped, and only then (or for a negative v that did not wrap) a second add
 // adjusts the high word.  (high, low) is an exact integer sum: it cannot overflow and does not
-// depend on the order of the adds (unlike a float RED).  `AtomicAddU` / `AtomicAddI` return the
-// old value / nothing: shared-memory atomics on the device, plain adds in tests/host_emulation.
+// depend on the order of the adds (unlike a float RED).  `add_u(cell, v)` adds to the low word of a
+// cell and returns its old value, `add_i(cell, v)` adds to the high word: shared-memory atomics on
+// 32-bit shared addresses on the device, plain adds in tests/host_emulation.
 // ---------------------------------------------------------------------------------
 constexpr int kTile = 32, kHalo = 16, kWin = kTile + 2 * kHalo;
 constexpr unsigned kFixBias = 0x80000000u;
@@ -529,12 +530,12 @@ FM_HD int fix_round(float scaled) {
 }
 
 template <typename AtomicAddU, typename AtomicAddI>
-FM_HD void fix_add(unsigned* lo, int* hi, int cell, float scaled, AtomicAddU add_u, AtomicAddI add_i) {
+FM_HD void fix_add(int cell, float scaled, AtomicAddU add_u, AtomicAddI add_i) {
   const int v = fix_round(scaled);
-  const unsigned old = add_u(lo + cell, (unsigned)v);
+  const unsigned old = add_u(cell, (unsigned)v);
   const unsigned sum = old + (unsigned)v;
   const int inc = (v >> 31) + (sum < old ? 1 : 0);  // high word of v (0 / -1) + carry of the low add
-  if (inc != 0) add_i(hi + cell, inc);
+  if (inc != 0) add_i(cell, inc);
 }
 
 FM_HD float fix_value(unsigned lo, int hi) {
@@ -619,8 +620,8 @@ FM_HD void tile_window_origin(float sum_flx, float sum_fly, int valid_pixels, in
 // One tap row of a pixel into the window; false = outside the window or too large for the
 // fixed-point range (the caller then adds v0 / v1 to global memory as floats).
 template <int WINH, typename AtomicAddU, typename AtomicAddI>
-FM_HD bool window_add_t(unsigned* lo, int* hi, int wx0, int wy0, float scale, int y0, int x0, float v0,
-                        float v1, AtomicAddU add_u, AtomicAddI add_i) {
+FM_HD bool window_add_t(int wx0, int wy0, float scale, int y0, int x0, float v0, float v1, AtomicAddU add_u,
+                        AtomicAddI add_i) {
   const int ux = x0 - wx0, uy = y0 - wy0;
   const float s0 = v0 * scale, s1 = v1 * scale;
   // NaN compares false: non-finite values take the fallback and propagate like in the float path
@@ -628,14 +629,14 @@ FM_HD bool window_add_t(unsigned* lo, int* hi, int wx0, int wy0, float scale, in
         fabsf(s1) < kFixLimit))
     return false;
   const int cell = uy * kWin + ux;
-  fix_add(lo, hi, cell, s0, add_u, add_i);
-  fix_add(lo, hi, cell + 1, s1, add_u, add_i);
+  fix_add(cell, s0, add_u, add_i);
+  fix_add(cell + 1, s1, add_u, add_i);
   return true;
 }
 template <typename AtomicAddU, typename AtomicAddI>
-FM_HD bool window_add(unsigned* lo, int* hi, int wx0, int wy0, float scale, int y0, int x0, float v0,
-                      float v1, AtomicAddU add_u, AtomicAddI add_i) {
-  return window_add_t<kWin>(lo, hi, wx0, wy0, scale, y0, x0, v0, v1, add_u, add_i);
+FM_HD bool window_add(int wx0, int wy0, float scale, int y0, int x0, float v0, float v1, AtomicAddU add_u,
+                      AtomicAddI add_i) {
+  return window_add_t<kWin>(wx0, wy0, scale, y0, x0, v0, v1, add_u, add_i);
 }
 
 }  // namespace fm

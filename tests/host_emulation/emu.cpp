@@ -43,8 +43,8 @@ static void bwd_tiled_impl(const float* depth, const float* k4, const float* bfl
   std::vector<unsigned> lo(kWin * WINH, kFixBias);
   std::vector<int> hi(kWin * WINH, 0);
   long long hi_adds = 0;
-  auto add_u = [](unsigned* p, unsigned v) { const unsigned old = *p; *p = old + v; return old; };
-  auto add_i = [&hi_adds](int* p, int v) { *p += v; ++hi_adds; };
+  auto add_u = [&lo](int cell, unsigned v) { const unsigned old = lo[cell]; lo[cell] = old + v; return old; };
+  auto add_i = [&hi, &hi_adds](int cell, int v) { hi[cell] += v; ++hi_adds; };
   for (int pair = 0; pair < BP; ++pair) {
     int a;
     PairGeom g = geom(depth, k4, pair, F, H, W, a);
@@ -72,7 +72,7 @@ static void bwd_tiled_impl(const float* depth, const float* k4, const float* bfl
       tile_window_origin_t<WINH>(sx, sy, stat_rows * kTile, X0, Y0, g.grid, wx0, wy0);
       const FixScale fs = fix_scale_for(wmax * fmaf(bnd_z, zmax, bnd_c));
       auto scatter = [&](int y0, int x0, float v0, float v1) {
-        if (window_add_t<WINH>(lo.data(), hi.data(), wx0, wy0, fs.scale, y0, x0, v0, v1, add_u, add_i)) {
+        if (window_add_t<WINH>(wx0, wy0, fs.scale, y0, x0, v0, v1, add_u, add_i)) {
           ++stats[0];
         } else {
           const int ux = x0 - wx0, uy = y0 - wy0;
@@ -275,9 +275,9 @@ void emu_procrustes_bwd_tiled64(const float* depth, const float* k4, const float
 // float the flush would produce.
 void emu_fix_accumulate(const float* scaled, int n, unsigned* lo_out, int* hi_out, float* value_out) {
   unsigned lo = kFixBias; int hi = 0;
-  auto add_u = [](unsigned* p, unsigned v) { const unsigned old = *p; *p = old + v; return old; };
-  auto add_i = [](int* p, int v) { *p += v; };
-  for (int i = 0; i < n; ++i) fix_add(&lo, &hi, 0, scaled[i], add_u, add_i);
+  auto add_u = [&lo](int, unsigned v) { const unsigned old = lo; lo = old + v; return old; };
+  auto add_i = [&hi](int, int v) { hi += v; };
+  for (int i = 0; i < n; ++i) fix_add(0, scaled[i], add_u, add_i);
   *lo_out = lo; *hi_out = hi; *value_out = fix_value(lo, hi);
 }
 
