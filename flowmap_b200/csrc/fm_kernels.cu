@@ -749,6 +749,62 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
   block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
 }
 
+// ---- pieces shared by the two tiled scatter kernels
+// Weight gradient of a thread's four pixels (chain rule of the sigmoid), its store and the fused
+// Adam update of the logits (same operations, same order as in k_distribute / k_adam).
+__device__ __forceinline__ void quad_weight_outputs(float* gwv, const float* wv, float* wraw, float* wt, float* gw,
+                                                    const AdamFuse& adam, long long weight_off, int base, int pair,
+                                                    float wsens) {
+  if (wsens != 0.f) {  // chain rule of the sigmoid: d/d logit = sens * w (1 - w) * d/dw
+#pragma unroll
+    for (int v = 0; v < 4; ++v) gwv[v] *= wsens * wv[v] * (1.0f - wv[v]);
+  }
+  if (gw) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
+  if (adam.on && pair >= adam.first_pair) {  // torch.optim.Adam on the logits (k_adam's order)
+    float4 mm = *reinterpret_cast<float4*>(adam.m + weight_off + base);
+    float4 vv = *reinterpret_cast<float4*>(adam.v + weight_off + base);
+    float* mp = &mm.x; float* vp = &vv.x;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      mp[v] = mp[v] + adam.omb1 * (gwv[v] - mp[v]);
+      vp[v] = vp[v] * adam.beta2 + adam.omb2 * gwv[v] * gwv[v];
+      wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
+    }
+    *reinterpret_cast<float4*>(adam.m + weight_off + base) = mm;
+    *reinterpret_cast<float4*>(adam.v + weight_off + base) = vv;
+    *reinterpret_cast<float4*>(wt + base) = make_float4(wraw[0], wraw[1], wraw[2], wraw[3]);
+  }
+}
+
+// Block-wide tile statistics from per-thread values: sums of the flow components (window origin),
+// max |depth| and max weight (fixed-point scale).  s_red: 4 * (kThreads / 32) floats, 16-byte
+// aligned; contains one barrier.  `reduce_w`: block-uniform, false when the weights are sigmoids
+// (never above 1).
+__device__ __forceinline__ void tile_stats(float sx, float sy, float zm, float wm, bool reduce_w, float* s_red,
+                                           float& mx, float& my, float& zmax, float& wmax) {
+  constexpr int NW = kThreads / 32;
+  static_assert(NW == 8, "two float4 per statistic");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o));
+  }
+  if (reduce_w) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+  }
+  if (lane == 0) { s_red[warp] = sx; s_red[NW + warp] = sy; s_red[2 * NW + warp] = zm; s_red[3 * NW + warp] = wm; }
+  __syncthreads();
+  const float4* r4 = reinterpret_cast<const float4*>(s_red);
+  const float4 a0 = r4[0], a1 = r4[1], b0 = r4[2], b1 = r4[3], z0 = r4[4], z1 = r4[5], w0 = r4[6], w1 = r4[7];
+  mx = ((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w));
+  my = ((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w));
+  zmax = fmaxf(fmaxf(fmaxf(z0.x, z0.y), fmaxf(z0.z, z0.w)), fmaxf(fmaxf(z1.x, z1.y), fmaxf(z1.z, z1.w)));
+  wmax = fmaxf(fmaxf(fmaxf(w0.x, w0.y), fmaxf(w0.z, w0.w)), fmaxf(fmaxf(w1.x, w1.y), fmaxf(w1.z, w1.w)));
+}
+
 // Native 32-bit integer atomics on a shared-space address (ATOMS.ADD / its no-return form).
 __device__ __forceinline__ unsigned atoms_add_u32(unsigned saddr, unsigned v) {
   unsigned old;
@@ -818,7 +874,6 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
   const unsigned hi_addr = lo_addr + (unsigned)((const char*)win_hi - (const char*)win_lo);
   const int tiles_x = W / kTile, tiles_y = (H + kTile - 1) / kTile;
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int parity = 0;
 
   for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x, parity ^= 1) {
@@ -849,29 +904,9 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
       for (int v = 0; v < 8; ++v) fv[v] = 0.f;
     }
     // tile statistics: mean flow (window origin), max |depth| and max weight (fixed-point scale)
-    float sx = (fv[0] + fv[2]) + (fv[4] + fv[6]), sy = (fv[1] + fv[3]) + (fv[5] + fv[7]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      sx += __shfl_xor_sync(0xffffffffu, sx, o);
-      sy += __shfl_xor_sync(0xffffffffu, sy, o);
-      zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o));
-    }
-    if (wsens == 0.f && wt) {  // block-uniform
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-    }
-    if (lane == 0) { s_red[warp] = sx; s_red[NW + warp] = sy; s_red[2 * NW + warp] = zm; s_red[3 * NW + warp] = wm; }
-    __syncthreads();
     float mx, my, zmax, wmax;
-    {
-      static_assert(kThreads / 32 == 8, "two float4 per statistic");
-      const float4* r4 = reinterpret_cast<const float4*>(s_red);
-      const float4 a0 = r4[0], a1 = r4[1], b0 = r4[2], b1 = r4[3], c0_ = r4[4], c1 = r4[5], d0 = r4[6], d1 = r4[7];
-      mx = ((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w));
-      my = ((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w));
-      zmax = fmaxf(fmaxf(fmaxf(c0_.x, c0_.y), fmaxf(c0_.z, c0_.w)), fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w)));
-      wmax = fmaxf(fmaxf(fmaxf(d0.x, d0.y), fmaxf(d0.z, d0.w)), fmaxf(fmaxf(d1.x, d1.y), fmaxf(d1.z, d1.w)));
-    }
+    tile_stats((fv[0] + fv[2]) + (fv[4] + fv[6]), (fv[1] + fv[3]) + (fv[5] + fv[7]), zm, wm, wsens == 0.f && wt, s_red,
+               mx, my, zmax, wmax);
     int wx0, wy0;
     tile_window_origin(mx, my, min(kTile, H - Y0) * kTile, X0, Y0, g.grid, wx0, wy0);
     const FixScale fs = fix_scale_for(wmax * fmaf(bnd_z, zmax, bnd_c));
@@ -890,27 +925,7 @@ k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4
         distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v], fv[2 * v],
                          fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
       red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
-      if (wt) {
-        if (wsens != 0.f) {  // chain rule of the sigmoid: d/d logit = sens * w (1 - w) * d/dw
-#pragma unroll
-          for (int v = 0; v < 4; ++v) gwv[v] *= wsens * wv[v] * (1.0f - wv[v]);
-        }
-        if (gw) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
-        if (adam.on && pair >= adam.first_pair) {  // torch.optim.Adam on the logits (k_adam's order)
-          float4 mm = *reinterpret_cast<float4*>(adam.m + pa.weight + base);
-          float4 vv = *reinterpret_cast<float4*>(adam.v + pa.weight + base);
-          float* mp = &mm.x; float* vp = &vv.x;
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            mp[v] = mp[v] + adam.omb1 * (gwv[v] - mp[v]);
-            vp[v] = vp[v] * adam.beta2 + adam.omb2 * gwv[v] * gwv[v];
-            wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
-          }
-          *reinterpret_cast<float4*>(adam.m + pa.weight + base) = mm;
-          *reinterpret_cast<float4*>(adam.v + pa.weight + base) = vv;
-          *reinterpret_cast<float4*>(wt + base) = make_float4(wraw[0], wraw[1], wraw[2], wraw[3]);
-        }
-      }
+      if (wt) quad_weight_outputs(gwv, wv, wraw, wt, gw, adam, pa.weight, base, pair, wsens);
     }
     __syncthreads();
     // Flush the touched cells (one aligned 16-byte RED per four cells) and reset them.  The high
@@ -1000,7 +1015,6 @@ k_distribute_tiled64(const float* __restrict__ depth, const float* __restrict__ 
   const unsigned hi_addr = lo_addr + (unsigned)((const char*)win_hi - (const char*)win_lo);
   const int tiles_x = W / kTile, tiles_y = (H + kTile64H - 1) / kTile64H;
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int parity = 0;
 
   for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x, parity ^= 1) {
@@ -1043,25 +1057,8 @@ k_distribute_tiled64(const float* __restrict__ depth, const float* __restrict__ 
           sx = (fv[0] + fv[2]) + (fv[4] + fv[6]);
           sy = (fv[1] + fv[3]) + (fv[5] + fv[7]);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          sx += __shfl_xor_sync(0xffffffffu, sx, o);
-          sy += __shfl_xor_sync(0xffffffffu, sy, o);
-          zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o));
-        }
-        if (wsens == 0.f && wt) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-        }
-        if (lane == 0) { s_red[warp] = sx; s_red[NW + warp] = sy; s_red[2 * NW + warp] = zm; s_red[3 * NW + warp] = wm; }
-        __syncthreads();
-        static_assert(kThreads / 32 == 8, "two float4 per statistic");
-        const float4* r4 = reinterpret_cast<const float4*>(s_red);
-        const float4 a0 = r4[0], a1 = r4[1], b0 = r4[2], b1 = r4[3], z0 = r4[4], z1 = r4[5], w0 = r4[6], w1 = r4[7];
-        const float mx = ((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w));
-        const float my = ((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w));
-        const float zmax = fmaxf(fmaxf(fmaxf(z0.x, z0.y), fmaxf(z0.z, z0.w)), fmaxf(fmaxf(z1.x, z1.y), fmaxf(z1.z, z1.w)));
-        const float wmax = fmaxf(fmaxf(fmaxf(w0.x, w0.y), fmaxf(w0.z, w0.w)), fmaxf(fmaxf(w1.x, w1.y), fmaxf(w1.z, w1.w)));
+        float mx, my, zmax, wmax;
+        tile_stats(sx, sy, zm, wm, wsens == 0.f && wt, s_red, mx, my, zmax, wmax);
         tile_window_origin_t<kWin64H>(mx, my, min(kTile, H - Y0) * kTile, X0, Y0, g.grid, wx0, wy0);
         const FixScale fs = fix_scale_for(wmax * fmaf(bnd_z, zmax, bnd_c));
         scale = fs.scale; inv_scale = fs.inv_scale;
@@ -1073,27 +1070,7 @@ k_distribute_tiled64(const float* __restrict__ depth, const float* __restrict__ 
           distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v], fv[2 * v],
                            fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
         red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
-        if (wt) {
-          if (wsens != 0.f) {  // chain rule of the sigmoid: d/d logit = sens * w (1 - w) * d/dw
-#pragma unroll
-            for (int v = 0; v < 4; ++v) gwv[v] *= wsens * wv[v] * (1.0f - wv[v]);
-          }
-          if (gw) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
-          if (adam.on && pair >= adam.first_pair) {  // torch.optim.Adam on the logits (k_adam's order)
-            float4 mm = *reinterpret_cast<float4*>(adam.m + pa.weight + base);
-            float4 vv = *reinterpret_cast<float4*>(adam.v + pa.weight + base);
-            float* mp = &mm.x; float* vp = &vv.x;
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              mp[v] = mp[v] + adam.omb1 * (gwv[v] - mp[v]);
-              vp[v] = vp[v] * adam.beta2 + adam.omb2 * gwv[v] * gwv[v];
-              wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
-            }
-            *reinterpret_cast<float4*>(adam.m + pa.weight + base) = mm;
-            *reinterpret_cast<float4*>(adam.v + pa.weight + base) = vv;
-            *reinterpret_cast<float4*>(wt + base) = make_float4(wraw[0], wraw[1], wraw[2], wraw[3]);
-          }
-        }
+        if (wt) quad_weight_outputs(gwv, wv, wraw, wt, gw, adam, pa.weight, base, pair, wsens);
       }
     }
     __syncthreads();

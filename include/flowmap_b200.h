@@ -107,7 +107,7 @@ int fm_mask_sum(const float* forward_mask, const float* backward_mask, double* o
                 void* stream);
 
 /* loss_flow.py:31-70 LossFlow + projection.py:143-184 compute_{forward,backward}_flow +
- * mapping/*.py, forward and analytic backward in one pass.  Uses the pair-local form of
+ * mapping/<name>.py, forward and analytic backward in one pass.  Uses the pair-local form of
  * SURVEY A.6 (inv(P_i) P_{i+1} == rt_i).  loss_weight is cfg.weight (loss.py:46).
  * mask_sum: device float64 scalar from fm_mask_sum ("or 1" applied inside).
  * intrinsics_mode: FM_K_FULL = per-frame k4, gradient for every entry; FM_K_SHARED_FOCAL =
