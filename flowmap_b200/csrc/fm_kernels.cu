@@ -2310,17 +2310,18 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
   }
   k_adjoint<<<(BP + 63) / 64, 64, 0, s>>>(w.flowacc, w.state, g_rt, include_flow_loss, flow_scale, w.adj, BP, F);
   FM_CHECK_LAUNCH("fm_procrustes_bwd: k_adjoint");
+  const int smode = indices ? 0 : scatter_mode();
   if (indices) {
     dim3 grid(blocks_for_points(num_indices), BP);
     k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
-  } else if (W % kTile == 0 && lay.cand == 1 && scatter_mode() == 2) {  // opt-in experiment, 32 x 64 tiles
+  } else if (W % kTile == 0 && lay.cand == 1 && smode == 2) {  // opt-in experiment, 32 x 64 tiles
     static const cudaError_t attr = cudaFuncSetAttribute(k_distribute_tiled64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiled64Smem);
     if (attr != cudaSuccess) return fail("k_distribute_tiled64: shared memory attribute", attr);
     const int tiles = (W / kTile) * ((H + kTile64H - 1) / kTile64H);
     const int per_cta = tiles_per_cta64();
     dim3 grid((tiles + per_cta - 1) / per_cta, BP);
     k_distribute_tiled64<<<grid, kThreads, kTiled64Smem, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
-  } else if (W % kTile == 0 && lay.cand == 1 && scatter_mode() == 1) {
+  } else if (W % kTile == 0 && lay.cand == 1 && smode == 1) {  // opt-in experiment, 32 x 32 tiles
     const int tiles = (W / kTile) * ((H + kTile - 1) / kTile);
     const int per_cta = tiles_per_cta();
     dim3 grid((tiles + per_cta - 1) / per_cta, BP);
