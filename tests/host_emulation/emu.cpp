@@ -33,7 +33,8 @@ static PairGeom geom(const float* depth, const float* k4, int pair, int F, int H
 // integer cells, flush and float fallback, built from the same inline functions.  stats[0] = tap
 // rows added to a window, [1] = tap rows that took the float fallback because they fell outside the
 // window, [2] = ... because of the fixed-point range, [3] = high-word adds, [4] = flushed groups
-// of four cells, [5] = touched cells outside the image (must stay 0).
+// of four cells, [5] = touched cells outside the image (must stay 0), [6] = largest scaled
+// contribution in millionths of 2^29.
 template <int TH>
 static void bwd_tiled_impl(const float* depth, const float* k4, const float* bflow, const float* weights,
                            const PairState* state, const double* g_rt, float* g_depth, float* g_weights,
@@ -72,6 +73,10 @@ static void bwd_tiled_impl(const float* depth, const float* k4, const float* bfl
       tile_window_origin_t<WINH>(sx, sy, stat_rows * kTile, X0, Y0, g.grid, wx0, wy0);
       const FixScale fs = fix_scale_for(wmax * fmaf(bnd_z, zmax, bnd_c));
       auto scatter = [&](int y0, int x0, float v0, float v1) {
+        // stats[6]: largest |scaled contribution| seen, in millionths of 2^29 (the bound maps to
+        // [2^28, 2^29): values above 1e6 would mean the bound does not hold)
+        const float big = fmaxf(fabsf(v0 * fs.scale), fabsf(v1 * fs.scale));
+        if (big == big) stats[6] = std::max(stats[6], (long long)(big * (1.0e6f / 536870912.0f)));
         if (window_add_t<WINH>(wx0, wy0, fs.scale, y0, x0, v0, v1, add_u, add_i)) {
           ++stats[0];
         } else {
