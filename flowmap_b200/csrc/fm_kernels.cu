@@ -642,7 +642,7 @@ struct AdamFuse {
   int first_pair;  // pairs below this index are left to a later, separate Adam call
 };
 
-template <int VEC>
+template <int VEC, bool FAST_ADAM = false>
 __global__ void __launch_bounds__(kThreads, 3)
 k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
              const float* __restrict__ bflow, float* weights,
@@ -723,7 +723,12 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
           for (int v = 0; v < 4; ++v) {
             mp[v] = mp[v] + adam.omb1 * (gwv[v] - mp[v]);
             vp[v] = vp[v] * adam.beta2 + adam.omb2 * gwv[v] * gwv[v];
-            wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
+            if (FAST_ADAM) {  // opt-in experiment (FM_ADAM=fast): sqrt and the two divisions as single MUFUs
+              const float root = vp[v] * fm_rsqrt(fmaxf(vp[v], 1e-37f));  // sqrt(v); v == 0 -> 0
+              wraw[v] = wraw[v] - adam.step_size * (mp[v] * fm_rcp(fm_fma(root, fm_rcp(adam.bc2_sqrt), adam.eps)));
+            } else {
+              wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
+            }
           }
           *reinterpret_cast<float4*>(adam.m + pa.weight + base) = mm;
           *reinterpret_cast<float4*>(adam.v + pa.weight + base) = vv;
@@ -2147,6 +2152,11 @@ int scatter_mode() {
   return 0;
 }
 
+bool fast_adam_enabled() {  // FM_ADAM=fast: the fused weight-logit Adam with single-MUFU sqrt / divisions
+  const char* v = getenv("FM_ADAM");
+  return v && !strcmp(v, "fast");
+}
+
 int tiles_per_cta64() {  // 32 x 64 tiles: half as many per block for the same pixels per block
   const char* v = getenv("FM_TILED_TILES_PER_CTA");
   const int n = v ? atoi(v) : 0;
@@ -2328,7 +2338,10 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
     k_distribute_tiled<<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
-    k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
+    if (af.on && fast_adam_enabled())  // opt-in experiment
+      k_distribute<4, true><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
+    else
+      k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   } else {
     dim3 grid(blocks_for(H * W, 1), BP);
     k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);

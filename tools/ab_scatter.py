@@ -164,6 +164,41 @@ def time_steps(steps=40):
     return out
 
 
+def time_adam(steps=40):
+    """FM_ADAM=fast (single-MUFU sqrt / divisions in the weight-logit Adam fused into k_distribute)
+    vs the default IEEE forms: fused-step time and the parameters after the same number of steps."""
+    F, H, W = bench.F_, bench.H_, bench.W_
+    inp = bench.synthetic_inputs(F, H, W, seed=0)
+    batch = Batch(torch.zeros(1, 1, 1, 1, 1, device=dev).expand(1, F, 3, H, W), torch.arange(F, device=dev)[None], ["s"], ["d"])
+    flows = Flows(*(inp[k].to(dev) for k in ("fwd", "bwd", "fmask", "bmask")))
+    set_mode("red")
+    out, params = {}, {}
+    for m in ("ieee", "fast"):
+        os.environ["FM_ADAM"] = m
+        o = FusedOverfitter(OverfitCfg(), batch, flows, device=dev)
+        with torch.no_grad():
+            o.model.backbone.depth.copy_(inp["depth"])
+            o.model.backbone.weights.copy_(inp["wparam"])
+        for _ in range(5):
+            o.training_step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            o.training_step()
+        e1.record()
+        torch.cuda.synchronize()
+        out[m] = e0.elapsed_time(e1) / steps
+        params[m] = (o.model.backbone.weights.detach().clone(), o.model.backbone.depth.detach().clone())
+    os.environ.pop("FM_ADAM")
+    w0 = inp["wparam"].to(dev)
+    out["weight_update_rel"] = rel(params["fast"][0] - w0, params["ieee"][0] - w0)
+    out["depth_rel"] = rel(params["fast"][1], params["ieee"][1])
+    print(f"fused flow-only step: IEEE Adam {out['ieee']:.4f} ms  fast Adam {out['fast']:.4f} ms  "
+          f"weight update rel {out['weight_update_rel']:.2e}  depth rel {out['depth_rel']:.2e}", flush=True)
+    return out
+
+
 def main():
     quick = "--quick" in sys.argv
     report = {"compare": [], "bwd_ms": {}, "steps": None}
@@ -184,6 +219,7 @@ def main():
     os.environ.pop("FM_TILED_TILES_PER_CTA")
     if not quick:
         report["steps"] = time_steps()
+        report["adam"] = time_adam()
     out = ROOT / "gpurun_out"
     out.mkdir(exist_ok=True)
     (out / "ab_scatter.json").write_text(json.dumps(report, indent=1))
