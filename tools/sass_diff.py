@@ -29,15 +29,20 @@ def main():
     a = kernels(sys.argv[1])
     b = kernels(sys.argv[2] if len(sys.argv) > 2 else ROOT / "flowmap_b200" / "csrc" / "libflowmap_b200.so")
     same = [k for k in b if k in a and a[k] == b[k]]
+    gone = {a[k]: k for k in a if k not in b}  # (length, hash) -> old name
+    renamed = 0
     for k in sorted(b):
         if k not in a:
-            print(f"new      {b[k][0]:5d}  {k[:110]}")
+            if b[k] in gone:  # same SASS under another (mangled) name, e.g. a new template parameter
+                print(f"renamed  {b[k][0]:5d}  {gone.pop(b[k])[:60]} -> {k[:60]}  (SASS identical)")
+                renamed += 1
+            else:
+                print(f"new      {b[k][0]:5d}  {k[:110]}")
         elif a[k] != b[k]:
             print(f"changed  {a[k][0]:5d} -> {b[k][0]:5d}  {k[:100]}")
-    for k in sorted(a):
-        if k not in b:
-            print(f"removed  {a[k][0]:5d}  {k[:110]}")
-    print(f"{len(same)} kernels identical")
+    for old_name in sorted(gone.values()):
+        print(f"removed  {a[old_name][0]:5d}  {old_name[:110]}")
+    print(f"{len(same) + renamed} kernels identical")
 
 
 if __name__ == "__main__":
