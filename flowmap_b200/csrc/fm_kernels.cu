@@ -272,7 +272,10 @@ __device__ __forceinline__ PairGeom pair_geom(const float* depth, const float* k
   return g;
 }
 
-template <int VEC>
+// TILE2D (opt-in experiment, FM_MAP=tile2d, W % 32 == 0): a block walks 32 x 32 tiles (a warp = 4 rows
+// x 32 pixels) instead of 1024 consecutive pixels of a row strip, so that the jittered taps of a
+// warp fall into ~half as many cache lines and the tap windows of a block overlap in L1.
+template <int VEC, bool TILE2D = false>
 __global__ void __launch_bounds__(kThreads, 3)
 k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
           const float* __restrict__ bflow, const float* __restrict__ weights,
@@ -294,7 +297,37 @@ k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
 #pragma unroll
   for (int i = 0; i < kNumMoments; ++i) acc[i] = 0.f;
 
-  if (indices == nullptr) {
+  if (TILE2D && VEC == 4 && indices == nullptr) {
+    const int tiles_x = W / 32, tiles = tiles_x * ((H + 31) / 32);
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int tyi = tile / tiles_x;
+      const int r = tyi * 32 + ty, c0 = (tile - tyi * tiles_x) * 32 + 4 * tx;
+      if (r >= H) continue;
+      const int base = r * W + c0;
+      float dv[VEC], wv[VEC], fv[2 * VEC];
+      load_vec<VEC>(db + base, dv);
+      load_vec2<VEC>(fl + 2 * base, fv);
+      if (wt) {
+        load_vec<VEC>(wt + base, wv);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) wv[v] = weight_of(wv[v], wsens);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
+      }
+      const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float p[3], q[3];
+        Taps taps;
+        point_pq(g, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], fv[2 * v], fv[2 * v + 1],
+                 load_a, p, q, taps);
+        moments_add(acc, wv[v], p, q);
+      }
+    }
+  } else if (indices == nullptr) {
     const int stride = gridDim.x * kThreads * VEC;
     int base = (blockIdx.x * kThreads + threadIdx.x) * VEC;
     int r = base / W, c0 = base - r * W;
@@ -642,7 +675,7 @@ struct AdamFuse {
   int first_pair;  // pairs below this index are left to a later, separate Adam call
 };
 
-template <int VEC, bool FAST_ADAM = false>
+template <int VEC, bool FAST_ADAM = false, bool TILE2D = false>  // TILE2D: see k_moments
 __global__ void __launch_bounds__(kThreads, 3)
 k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
              const float* __restrict__ bflow, float* weights,
@@ -679,8 +712,18 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
     int base = (blockIdx.x * kThreads + threadIdx.x) * VEC;
     int r = base / W, c0 = base - r * W;
     const int dr = stride / W, dc = stride - dr * W;
+    const int tiles_x = W / 32, tiles = tiles_x * ((H + 31) / 32);  // TILE2D only
+    int tile = blockIdx.x;
 #pragma unroll 1
-    for (; base < N; base += stride) {
+    for (; TILE2D ? tile < tiles : base < N; base += TILE2D ? 0 : stride) {
+      if (TILE2D) {  // this iteration's four pixels: row ty of tile `tile`
+        const int tyi = tile / tiles_x;
+        r = tyi * 32 + (int)(threadIdx.x >> 3);
+        c0 = (tile - tyi * tiles_x) * 32 + 4 * (int)(threadIdx.x & 7);
+        base = r * W + c0;
+        tile += gridDim.x;
+        if (r >= H) continue;
+      }
       float dv[VEC], wv[VEC], wraw[VEC], fv[2 * VEC], gwv[VEC], gdv[VEC];
       load_vec<VEC>(db + base, dv);
       load_vec2<VEC>(fl + 2 * base, fv);
@@ -702,8 +745,10 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
       for (int v = 0; v < VEC; ++v)
         distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v],
                          fv[2 * v], fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
-      r += dr; c0 += dc;
-      if (c0 >= W) { c0 -= W; ++r; }
+      if (!TILE2D) {
+        r += dr; c0 += dc;
+        if (c0 >= W) { c0 -= W; ++r; }
+      }
       if (VEC == 4) red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
       else red_add(gdb + base, gdv[0]);
       if (wt) {
@@ -2152,6 +2197,11 @@ int scatter_mode() {
   return 0;
 }
 
+bool tile2d_enabled() {  // FM_MAP=tile2d: 32 x 32-tile thread -> pixel mapping in the gather kernels
+  const char* v = getenv("FM_MAP");
+  return v && !strcmp(v, "tile2d");
+}
+
 bool fast_adam_enabled() {  // FM_ADAM=fast: the fused weight-logit Adam with single-MUFU sqrt / divisions
   const char* v = getenv("FM_ADAM");
   return v && !strcmp(v, "fast");
@@ -2275,6 +2325,10 @@ static int procrustes_fwd_impl(const float* depth, const float* k4, const float*
   if (indices) {
     dim3 grid(blocks_for_points(num_indices), BP);
     k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.moments, wsens, lay, H, W);
+  } else if (W % 32 == 0 && tile2d_enabled()) {  // opt-in experiment: 2-D thread -> pixel mapping
+    const int tiles = (W / 32) * ((H + 31) / 32);
+    dim3 grid((tiles + 15) / 16, BP);
+    k_moments<4, true><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, lay, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
     k_moments<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, lay, H, W);
@@ -2338,7 +2392,11 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
     k_distribute_tiled<<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
-    if (af.on && fast_adam_enabled())  // opt-in experiment
+    if (W % 32 == 0 && tile2d_enabled()) {  // opt-in experiment: 2-D thread -> pixel mapping
+      const int tiles = (W / 32) * ((H + 31) / 32);
+      dim3 grid2((tiles + 15) / 16, BP);
+      k_distribute<4, false, true><<<grid2, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
+    } else if (af.on && fast_adam_enabled())  // opt-in experiment
       k_distribute<4, true><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
     else
       k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);

@@ -199,6 +199,51 @@ def time_adam(steps=40):
     return out
 
 
+def ab_map(n=20):
+    """FM_MAP=tile2d (32 x 32-tile thread -> pixel mapping in k_moments / k_distribute) vs the default
+    row-strip mapping: poses and gradients must agree; per-launch time of both ops."""
+    set_mode("red")
+    report = {"compare": [], "ok": True}
+
+    def run(c, f, h, w):
+        fwd, bwd, outs = run_ops(c, f, h, w)
+        fwd(); bwd()
+        torch.cuda.synchronize()
+        return [o.clone() for o in outs]
+    for f, h, w in [(3, 24, 32), (3, 100, 64), (5, 72, 96), (3, 360, 640), (2, 720, 1280)]:
+        for kind in ("iid", "smooth", "leave"):
+            c = make_case(f, h, w, kind)
+            res = {}
+            for m in ("strip", "tile2d"):
+                os.environ["FM_MAP"] = m
+                res[m] = run(c, f, h, w)
+            r = {"shape": [f, h, w], "flows": kind, "g_depth_rel": rel(res["tile2d"][0], res["strip"][0]),
+                 "g_weights_rel": rel(res["tile2d"][1], res["strip"][1]), "g_k4_rel": rel(res["tile2d"][2], res["strip"][2])}
+            # the moments are summed in another order (float32 partials per thread): poses differ at the
+            # 1e-7 level and with them every gradient
+            r["ok"] = r["g_depth_rel"] <= 2e-5 and r["g_weights_rel"] <= 2e-5 and r["g_k4_rel"] <= 1e-4
+            report["ok"] = report["ok"] and r["ok"]
+            report["compare"].append(r)
+            print("map", json.dumps(r), flush=True)
+    c = make_case(bench.F_, bench.H_, bench.W_, "iid")
+    for m in ("strip", "tile2d"):
+        os.environ["FM_MAP"] = m
+        fwd, bwd, _ = run_ops(c, bench.F_, bench.H_, bench.W_)
+        for _ in range(3):
+            fwd(); bwd()
+        torch.cuda.synchronize()
+        t_f = t_b = 0.0
+        for _ in range(n):
+            a, b, d = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record(); fwd(); b.record(); bwd(); d.record()
+            torch.cuda.synchronize()
+            t_f += a.elapsed_time(b); t_b += b.elapsed_time(d)
+        report[m] = {"fwd_plus_flow_ms": t_f / n, "bwd_ms": t_b / n}
+        print(f"FM_MAP={m}: procrustes_fwd + flow loss {t_f / n:.4f} ms, procrustes_bwd {t_b / n:.4f} ms", flush=True)
+    os.environ.pop("FM_MAP")
+    return report
+
+
 def main():
     quick = "--quick" in sys.argv
     report = {"compare": [], "bwd_ms": {}, "steps": None}
@@ -217,6 +262,7 @@ def main():
         os.environ["FM_TILED_TILES_PER_CTA"] = str(tpc)
         report["tiles_per_cta_ms"][tpc] = time_bwd(bench.F_, bench.H_, bench.W_, "iid", n=10)
     os.environ.pop("FM_TILED_TILES_PER_CTA")
+    report["map"] = ab_map()
     if not quick:
         report["steps"] = time_steps()
         report["adam"] = time_adam()
