@@ -130,7 +130,97 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": which}
 
 
-# ------------------------------------------------------------------------------ CPU baseline
+# ------------------------------------------------------------------------------ the reference itself
+REF_DIR = ROOT / "baseline" / "_ref"
+
+
+def reference_available():
+    return (REF_DIR / "flowmap" / "model" / "model.py").exists()
+
+
+def reference_runner(device, frames=F_, h=H_, w=W_, seed=0):
+    """The UNMODIFIED reference (baseline/_ref, staged by baseline/install_ref.py) on `device`:
+    flowmap.model.model.Model + flowmap.loss.get_losses driven as model_wrapper_overfit.py:51-73,
+    104-105 does (Lightning / Hydra are not installed: only that shell is restated), with the
+    values of config/overfit.yaml + experiment/ablation_explicit_depth.yaml on the bench workload.
+    Returns step() -> float loss (one full overfit iteration incl. Adam)."""
+    if str(REF_DIR) not in sys.path:
+        sys.path.insert(0, str(REF_DIR))
+    sys.dont_write_bytecode = True
+    from flowmap.dataset.types import Batch as RBatch
+    from flowmap.flow.flow_predictor import Flows as RFlows
+    from flowmap.loss import get_losses as r_get_losses
+    from flowmap.loss.loss_flow import LossFlowCfg as RLossFlowCfg
+    from flowmap.loss.loss_tracking import LossTrackingCfg as RLossTrackingCfg
+    from flowmap.loss.mapping.mapping_huber import MappingHuberCfg as RHuber
+    from flowmap.model.backbone.backbone_explicit_depth import BackboneExplicitDepthCfg as RBackboneCfg
+    from flowmap.model.extrinsics.extrinsics_procrustes import ExtrinsicsProcrustesCfg as RExtrCfg
+    from flowmap.model.intrinsics.intrinsics_softmin import IntrinsicsSoftminCfg as RSoftminCfg
+    from flowmap.model.intrinsics.intrinsics_softmin import RegressionCfg as RRegressionCfg
+    from flowmap.model.model import Model as RModel
+    from flowmap.model.model import ModelCfg as RModelCfg
+    from flowmap.tracking.track_predictor import Tracks as RTracks
+
+    inp = synthetic_inputs(frames, h, w, seed=seed)
+    mcfg = RModelCfg(RBackboneCfg("explicit_depth", 0.1, 100.0),
+                     RSoftminCfg("softmin", 8192, 0.5, 2.0, 60, RRegressionCfg(1000, 100)),
+                     RExtrCfg("procrustes", None, False), True)
+    model = RModel(mcfg, frames, (h, w))
+    with torch.no_grad():
+        model.backbone.depth.copy_(inp["depth"])
+        model.backbone.weights.copy_(inp["wparam"])
+    model.to(device)
+    huber = RHuber("huber", 0.01)
+    losses = r_get_losses([RLossFlowCfg(0, 1000.0, "flow", huber), RLossTrackingCfg(50, 100.0, "tracking", huber)])
+    batch = RBatch(torch.zeros((1, 1, 1, 1, 1), device=device).expand(1, frames, 3, h, w),
+                   torch.arange(frames, device=device)[None], ["synthetic"], ["synthetic"])
+    flows = RFlows(*(inp[k].to(device) for k in ("fwd", "bwd", "fmask", "bmask")))
+    tracks = [RTracks(xy.to(device), vis.to(device), s) for xy, vis, s in synthetic_track_arrays(frames, seed=seed)]
+    opt = torch.optim.Adam(model.parameters(), lr=3e-5)  # model_wrapper_overfit.py:104-105, overfit.yaml:30
+    state = {"step": START_STEP}
+
+    def step():
+        opt.zero_grad()
+        gs = state["step"]
+        out = model(batch, flows, gs)
+        total = sum(l.forward(batch, flows, tracks, out, gs) for l in losses)
+        total.backward()
+        opt.step()
+        state["step"] += 1
+        return float(total.detach())
+    return step
+
+
+def reference_cpu(steps, warmup, budget_s=420.0):
+    """`steps` timed iterations of the full C3 workload through the unmodified reference on the host
+    cores (fixed thread policy: min(cores, 32) ATen threads -- ATen's elementwise kernels stop
+    scaling well below 128 threads); the number of timed steps shrinks (>= 2) only if the first
+    iteration shows that the run would not end within a few minutes."""
+    cores = os.cpu_count() or 1
+    threads = min(cores, 32)
+    torch.set_num_threads(threads)
+    step = reference_runner(torch.device("cpu"))
+    t0 = time.perf_counter()
+    first_loss = step()                       # untimed: first touch of 17 GB of autograd buffers
+    t_first = time.perf_counter() - t0
+    warm_done = 1
+    while warm_done < warmup and (warm_done + 2) * t_first < 0.3 * budget_s:
+        step()
+        warm_done += 1
+    k = max(2, min(steps, int((budget_s - warm_done * t_first) / max(t_first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        last = step()
+    dt = (time.perf_counter() - t0) / k
+    return {"value": 1.0 / dt, "unit": "it/s", "cores": cores, "threads": threads, "kind": "reference",
+            "s_per_iteration": dt, "timed_steps": k, "warmup_steps": warm_done, "first_loss": first_loss,
+            "last_loss": last,
+            "sample": f"the full C3 workload (150 x 360 x 640, softmin + flow + tracking + Adam), {k} timed "
+                      f"iterations after {warm_done} warm-up, unmodified reference modules (baseline/_ref) on "
+                      f"{threads} ATen threads of {cores} host cores"}
+
+
+# ------------------------------------------------------------------------------ CPU baseline (oracle port)
 def cpu_baseline(sample_frames, steps, warmup, full=True):
     """The oracle (CPU restatement of the reference, oracle/flowmap_oracle.py: same op
     sequence on ATen, autograd, torch.optim.Adam) timed on the host cores on the first
@@ -487,6 +577,31 @@ def run_gpu(args):
                         "load latency at 2 CTAs/SM (128 registers), k_moments by L1 gather wavefronts "
                         "(profiles/README.md); HBM is the denominator the task names"}
 
+    # ---- informative: the unmodified reference in its own execution mode, CUDA eager on this same
+    # B200 (flowmap/overfit.py:50,96 hard-code cuda:0) -- what a FlowMap user runs today
+    ref_cuda = None
+    if world == 1 and not pairs_mode and reference_available() and os.environ.get("FM_BENCH_SKIP_CPU") != "1":
+        try:
+            del o
+            torch.cuda.empty_cache()
+            rstep = reference_runner(dev)
+            rstep(); rstep()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_ref = 5
+            for _ in range(n_ref):
+                rl = rstep()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n_ref
+            ref_cuda = {"ms_per_step": round(dt * 1e3, 2), "it_per_s": round(1.0 / dt, 3), "steps": n_ref,
+                        "last_loss": rl, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+                        "what": "unmodified reference modules (baseline/_ref) in PyTorch CUDA eager on this GPU, same "
+                                "workload, wall clock with a synchronize on both sides (loss read back every step)"}
+            del rstep
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001 -- the informative leg must not sink the bench line
+            ref_cuda = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if os.environ.get("FM_BENCH_SKIP_CPU") == "1":  # profiling runs (ncu) only
         cpu = {"value": None, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
                "sample": "skipped (FM_BENCH_SKIP_CPU=1)"}
@@ -532,6 +647,7 @@ def run_gpu(args):
         {"ms_per_step": round(dropin_ms, 4), "it_per_s": round(world * 1000.0 / dropin_ms, 2),
          "what": "same full workload through Model.forward + LossFlow/LossTracking autograd Functions + "
                  "kernel Adam (the install() drop-in surface) instead of the one-call fused step"},
+        "reference_cuda_eager": ref_cuda,
         "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(out))
@@ -542,11 +658,24 @@ def run_gpu(args):
 
 # ------------------------------------------------------------------------------ reference arm
 def run_reference(args):
-    """The reference's own CPU implementation of the path.  The reference is pure Python on
-    ATen (no compiled path, cannot travel to the GPU box), so this times the oracle port of it
-    (same op sequence, torch CPU autograd + Adam, the fastest host thread count) on a bounded
-    sample of the same workload."""
+    """The reference's own CPU implementation of the path: the UNMODIFIED reference modules staged
+    under baseline/_ref (baseline/install_ref.py) on the full C3 workload; if they are missing
+    (a checkout that never ran build() next to /root/reference) the oracle port on a bounded
+    sample, labelled as such."""
     if int(os.environ.get("RANK", 0)) != 0:
+        return
+    if reference_available() and args.mode == "scenes":
+        cpu = reference_cpu(max(2, args.steps), max(1, args.warmup))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": round(cpu["value"], 6), "unit": "it/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": cpu["timed_steps"], "warmup": cpu["warmup_steps"],
+            "requested_steps": args.steps, "ms_per_step": round(1000.0 * cpu["s_per_iteration"], 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames": F_, "height": H_, "width": W_},
+            "cpu_baseline": cpu,
+            "e2e": {"value": round(cpu["value"], 6), "unit": "it/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
         return
     # exactly K timed steps; the sample shrinks with K so that the run stays within minutes
     frames = max(3, min(12, 60 // max(1, args.steps) + 2))

@@ -34,6 +34,13 @@ SIGNATURES = {
     "fm_procrustes_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "fm_procrustes_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P, _P,
                                   c_int, c_int, c_int, c_int, _P]),
+    "fm_splat_plan_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "fm_splat_plan_build": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
+    "fm_splat_plan_info": (c_int, [_P, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_uint),
+                                   ctypes.POINTER(ctypes.c_ulonglong), _P]),
+    "fm_procrustes_fwd_planned": (c_int, [_P, _P, _P, _P, c_float, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "fm_procrustes_bwd_planned": (c_int, [_P, _P, _P, _P, c_float, _P, ctypes.c_uint, _P, c_int, _P, _P, _P, _P,
+                                          c_int, c_int, c_int, _P]),
     "fm_mask_sum": (c_int, [_P, _P, _P, c_size_t, _P]),
     "fm_flow_loss_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_float, c_float, c_int,
                                      _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
@@ -92,7 +99,7 @@ class OverfitStepArgs(ctypes.Structure):
                 ("extrinsics", _P), ("g_extrinsics", _P), ("g_rt", _P), ("track_g_k4", _P),
                 ("track_loss", _P),
                 ("ws", _P), ("track_ws", _P), ("focal_step", c_int), ("defer_adam", c_int),
-                ("phase", c_int)]
+                ("phase", c_int), ("splat_plan", _P), ("splat_overflow_max", ctypes.c_uint)]
 
 
 SIGNATURES["fm_overfit_step"] = (c_int, [ctypes.POINTER(OverfitStepArgs), _P])

@@ -272,10 +272,7 @@ __device__ __forceinline__ PairGeom pair_geom(const float* depth, const float* k
   return g;
 }
 
-// TILE2D (opt-in experiment, FM_MAP=tile2d, W % 32 == 0): a block walks 32 x 32 tiles (a warp = 4 rows
-// x 32 pixels) instead of 1024 consecutive pixels of a row strip, so that the jittered taps of a
-// warp fall into ~half as many cache lines and the tap windows of a block overlap in L1.
-template <int VEC, bool TILE2D = false>
+template <int VEC>
 __global__ void __launch_bounds__(kThreads, 3)
 k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
           const float* __restrict__ bflow, const float* __restrict__ weights,
@@ -297,37 +294,7 @@ k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
 #pragma unroll
   for (int i = 0; i < kNumMoments; ++i) acc[i] = 0.f;
 
-  if (TILE2D && VEC == 4 && indices == nullptr) {
-    const int tiles_x = W / 32, tiles = tiles_x * ((H + 31) / 32);
-    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-#pragma unroll 1
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int tyi = tile / tiles_x;
-      const int r = tyi * 32 + ty, c0 = (tile - tyi * tiles_x) * 32 + 4 * tx;
-      if (r >= H) continue;
-      const int base = r * W + c0;
-      float dv[VEC], wv[VEC], fv[2 * VEC];
-      load_vec<VEC>(db + base, dv);
-      load_vec2<VEC>(fl + 2 * base, fv);
-      if (wt) {
-        load_vec<VEC>(wt + base, wv);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) wv[v] = weight_of(wv[v], wsens);
-      } else {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
-      }
-      const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        float p[3], q[3];
-        Taps taps;
-        point_pq(g, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], fv[2 * v], fv[2 * v + 1],
-                 load_a, p, q, taps);
-        moments_add(acc, wv[v], p, q);
-      }
-    }
-  } else if (indices == nullptr) {
+  if (indices == nullptr) {
     const int stride = gridDim.x * kThreads * VEC;
     int base = (blockIdx.x * kThreads + threadIdx.x) * VEC;
     int r = base / W, c0 = base - r * W;
@@ -645,10 +612,15 @@ __global__ void k_flow_finalize(const double* __restrict__ flowacc, const float*
 }
 
 // ================================================================== phase D1: adjoint solve
+// focal_moments != NULL (tiled path, all frames share one focal length): the pair's Procrustes part
+// of d loss / d focal is taken from the moment sums (fm_procrustes.cuh) and booked as the
+// equivalent d/dfx of the pair's earlier frame in k4acc -- the per-pixel kernels carry no
+// intrinsics accumulators at all.
 __global__ void k_adjoint(const double* __restrict__ flowacc, const PairState* __restrict__ state,
                           const float* __restrict__ g_rt, int include_flow,
                           const float* __restrict__ flow_scale, PairAdjoint* __restrict__ adj, int BP,
-                          int F) {
+                          int F, const double* __restrict__ focal_moments = nullptr,
+                          const float* __restrict__ k4 = nullptr, double* __restrict__ k4acc = nullptr) {
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
   if (pair >= BP) return;
   double g[12];
@@ -660,7 +632,15 @@ __global__ void k_adjoint(const double* __restrict__ flowacc, const PairState* _
   }
   if (g_rt) for (int k = 0; k < 12; ++k) g[k] += (double)g_rt[(size_t)pair * 12 + k];
   PairAdjoint out;
-  procrustes_adjoint(state[pair], g, out);
+  if (focal_moments) {
+    double dbl[15];
+    procrustes_adjoint(state[pair], g, out, dbl);
+    const int bi = pair / (F - 1), a = bi * F + (pair - bi * (F - 1));
+    const double fdf = procrustes_focal_log_grad(state[pair], focal_moments + (size_t)pair * kNumMoments, dbl);
+    k4acc[(size_t)a * 4] = fdf / (double)k4[(size_t)a * 4];  // f dL/df = fx dL/dfx
+  } else {
+    procrustes_adjoint(state[pair], g, out);
+  }
   adj[pair] = out;
 }
 
@@ -675,7 +655,7 @@ struct AdamFuse {
   int first_pair;  // pairs below this index are left to a later, separate Adam call
 };
 
-template <int VEC, bool FAST_ADAM = false, bool TILE2D = false>  // TILE2D: see k_moments
+template <int VEC>
 __global__ void __launch_bounds__(kThreads, 3)
 k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
              const float* __restrict__ bflow, float* weights,
@@ -712,18 +692,8 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
     int base = (blockIdx.x * kThreads + threadIdx.x) * VEC;
     int r = base / W, c0 = base - r * W;
     const int dr = stride / W, dc = stride - dr * W;
-    const int tiles_x = W / 32, tiles = tiles_x * ((H + 31) / 32);  // TILE2D only
-    int tile = blockIdx.x;
 #pragma unroll 1
-    for (; TILE2D ? tile < tiles : base < N; base += TILE2D ? 0 : stride) {
-      if (TILE2D) {  // this iteration's four pixels: row ty of tile `tile`
-        const int tyi = tile / tiles_x;
-        r = tyi * 32 + (int)(threadIdx.x >> 3);
-        c0 = (tile - tyi * tiles_x) * 32 + 4 * (int)(threadIdx.x & 7);
-        base = r * W + c0;
-        tile += gridDim.x;
-        if (r >= H) continue;
-      }
+    for (; base < N; base += stride) {
       float dv[VEC], wv[VEC], wraw[VEC], fv[2 * VEC], gwv[VEC], gdv[VEC];
       load_vec<VEC>(db + base, dv);
       load_vec2<VEC>(fl + 2 * base, fv);
@@ -745,10 +715,8 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
       for (int v = 0; v < VEC; ++v)
         distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v],
                          fv[2 * v], fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
-      if (!TILE2D) {
-        r += dr; c0 += dc;
-        if (c0 >= W) { c0 -= W; ++r; }
-      }
+      r += dr; c0 += dc;
+      if (c0 >= W) { c0 -= W; ++r; }
       if (VEC == 4) red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
       else red_add(gdb + base, gdv[0]);
       if (wt) {
@@ -768,12 +736,7 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
           for (int v = 0; v < 4; ++v) {
             mp[v] = mp[v] + adam.omb1 * (gwv[v] - mp[v]);
             vp[v] = vp[v] * adam.beta2 + adam.omb2 * gwv[v] * gwv[v];
-            if (FAST_ADAM) {  // opt-in experiment (FM_ADAM=fast): sqrt and the two divisions as single MUFUs
-              const float root = vp[v] * fm_rsqrt(fmaxf(vp[v], 1e-37f));  // sqrt(v); v == 0 -> 0
-              wraw[v] = wraw[v] - adam.step_size * (mp[v] * fm_rcp(fm_fma(root, fm_rcp(adam.bc2_sqrt), adam.eps)));
-            } else {
-              wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
-            }
+            wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
           }
           *reinterpret_cast<float4*>(adam.m + pa.weight + base) = mm;
           *reinterpret_cast<float4*>(adam.v + pa.weight + base) = vv;
@@ -799,365 +762,7 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
   block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
 }
 
-// ---- pieces shared by the two tiled scatter kernels
-// Weight gradient of a thread's four pixels (chain rule of the sigmoid), its store and the fused
-// Adam update of the logits (same operations, same order as in k_distribute / k_adam).
-__device__ __forceinline__ void quad_weight_outputs(float* gwv, const float* wv, float* wraw, float* wt, float* gw,
-                                                    const AdamFuse& adam, long long weight_off, int base, int pair,
-                                                    float wsens) {
-  if (wsens != 0.f) {  // chain rule of the sigmoid: d/d logit = sens * w (1 - w) * d/dw
-#pragma unroll
-    for (int v = 0; v < 4; ++v) gwv[v] *= wsens * wv[v] * (1.0f - wv[v]);
-  }
-  if (gw) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
-  if (adam.on && pair >= adam.first_pair) {  // torch.optim.Adam on the logits (k_adam's order)
-    float4 mm = *reinterpret_cast<float4*>(adam.m + weight_off + base);
-    float4 vv = *reinterpret_cast<float4*>(adam.v + weight_off + base);
-    float* mp = &mm.x; float* vp = &vv.x;
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      mp[v] = mp[v] + adam.omb1 * (gwv[v] - mp[v]);
-      vp[v] = vp[v] * adam.beta2 + adam.omb2 * gwv[v] * gwv[v];
-      wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
-    }
-    *reinterpret_cast<float4*>(adam.m + weight_off + base) = mm;
-    *reinterpret_cast<float4*>(adam.v + weight_off + base) = vv;
-    *reinterpret_cast<float4*>(wt + base) = make_float4(wraw[0], wraw[1], wraw[2], wraw[3]);
-  }
-}
-
-// Block-wide tile statistics from per-thread values: sums of the flow components (window origin),
-// max |depth| and max weight (fixed-point scale).  s_red: 4 * (kThreads / 32) floats, 16-byte
-// aligned; contains one barrier.  `reduce_w`: block-uniform, false when the weights are sigmoids
-// (never above 1).
-__device__ __forceinline__ void tile_stats(float sx, float sy, float zm, float wm, bool reduce_w, float* s_red,
-                                           float& mx, float& my, float& zmax, float& wmax) {
-  constexpr int NW = kThreads / 32;
-  static_assert(NW == 8, "two float4 per statistic");
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sx += __shfl_xor_sync(0xffffffffu, sx, o);
-    sy += __shfl_xor_sync(0xffffffffu, sy, o);
-    zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o));
-  }
-  if (reduce_w) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-  }
-  if (lane == 0) { s_red[warp] = sx; s_red[NW + warp] = sy; s_red[2 * NW + warp] = zm; s_red[3 * NW + warp] = wm; }
-  __syncthreads();
-  const float4* r4 = reinterpret_cast<const float4*>(s_red);
-  const float4 a0 = r4[0], a1 = r4[1], b0 = r4[2], b1 = r4[3], z0 = r4[4], z1 = r4[5], w0 = r4[6], w1 = r4[7];
-  mx = ((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w));
-  my = ((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w));
-  zmax = fmaxf(fmaxf(fmaxf(z0.x, z0.y), fmaxf(z0.z, z0.w)), fmaxf(fmaxf(z1.x, z1.y), fmaxf(z1.z, z1.w)));
-  wmax = fmaxf(fmaxf(fmaxf(w0.x, w0.y), fmaxf(w0.z, w0.w)), fmaxf(fmaxf(w1.x, w1.y), fmaxf(w1.z, w1.w)));
-}
-
-// Native 32-bit integer atomics on a shared-space address (ATOMS.ADD / its no-return form).
-__device__ __forceinline__ unsigned atoms_add_u32(unsigned saddr, unsigned v) {
-  unsigned old;
-  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(v) : "memory");
-  return old;
-}
-__device__ __forceinline__ void reds_add_s32(unsigned saddr, int v) {
-  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
-
-// ------------------------------------------------------------------------------------------
-// Phase D2, tiled (dense path, W % 32 == 0): the bilinear scatter into the EARLIER frame's depth
-// gradient is privatised in shared memory.  A block owns 32 x 32 tiles of the LATER frame; the
-// taps of a tile land in a 64 x 64 window (tile + 16 px halo, shifted by the tile's mean backward
-// flow so that smooth real flows stay inside); taps outside fall back to global vector REDs.
-//
-// Shared-memory float atomics are CAS loops on sm_100a (measured slower than the global REDs,
-// profiles/README.md), so the window accumulates in fixed point on the native 32-bit integer
-// ATOMS.ADD: an exact (high, low) 64-bit integer per cell with a per-tile power-of-two scale
-// derived from a bound of the tile's contributions (fm_pixel.cuh: fix_add, fix_scale_for,
-// scatter_bound_consts).  Values too large for the fixed-point range (raw weights > 1,
-// non-finite input) take the global float RED, so correctness never depends on the bound.  The
-// flush converts each touched cell once and adds four cells with one aligned 16-byte RED.
-__global__ void __launch_bounds__(kThreads, 3)
-k_distribute_tiled(const float* __restrict__ depth, const float* __restrict__ k4,
-                   const float* __restrict__ bflow, float* weights,
-                   const PairAdjoint* __restrict__ adj, float* __restrict__ g_depth,
-                   float* __restrict__ g_weights, double* __restrict__ k4acc, float wsens,
-                   PairLayout lay, AdamFuse adam, int H, int W) {
-  constexpr int NW = kThreads / 32;
-  __shared__ double smem[8 * NW];
-  __shared__ PairAdjoint s_adj;
-  __shared__ __align__(16) unsigned win_lo[kWin * kWin];
-  __shared__ __align__(16) int win_hi[kWin * kWin];
-  __shared__ __align__(16) float s_red[4 * NW];  // per-warp tile statistics: sum flx, sum fly, max |depth|, max weight
-  __shared__ int s_hi_used[2];                   // did any add of this tile (parity) touch a high word?
-  const int pair = blockIdx.y;
-  const int N = H * W;
-  if (threadIdx.x < sizeof(PairAdjoint) / 4)
-    reinterpret_cast<float*>(&s_adj)[threadIdx.x] = reinterpret_cast<const float*>(adj + pair)[threadIdx.x];
-  for (int i = threadIdx.x; i < kWin * kWin / 4; i += kThreads) {
-    reinterpret_cast<uint4*>(win_lo)[i] = make_uint4(kFixBias, kFixBias, kFixBias, kFixBias);
-    reinterpret_cast<int4*>(win_hi)[i] = make_int4(0, 0, 0, 0);
-  }
-  if (threadIdx.x < 2) s_hi_used[threadIdx.x] = 0;
-  __syncthreads();
-  const PairAdjoint ad = s_adj;
-  const PairAddr pa = pair_addr(lay, pair, N);
-  const PairGeom g = pair_geom(depth, k4, pa, H, W);
-  const int a = pa.k4_frame_a;
-  const float* da = opaque_ptr(depth + pa.depth_a);
-  const float* db = da + N;
-  const float* fl = bflow + pa.flow;
-  float* wt = weights ? weights + pa.weight : nullptr;
-  float* gda = g_depth + pa.depth_a;
-  float* gdb = gda + N;
-  float* gw = g_weights ? g_weights + pa.weight : nullptr;
-  auto load_a = [da](int o) { return __ldg(da + o); };
-  float kacc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
-  float bnd_z, bnd_c;  // bound of a tile's contributions = wmax * (bnd_z * max|depth_b| + bnd_c)
-  scatter_bound_consts(g, ad, bnd_z, bnd_c);
-  // 32-bit shared-space addresses of the window: the atomics below address it directly instead of
-  // re-deriving a generic address for every tap
-  const unsigned lo_addr = opaque_u32((unsigned)__cvta_generic_to_shared(win_lo));
-  const unsigned hi_addr = lo_addr + (unsigned)((const char*)win_hi - (const char*)win_lo);
-  const int tiles_x = W / kTile, tiles_y = (H + kTile - 1) / kTile;
-  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-  int parity = 0;
-
-  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x, parity ^= 1) {
-    const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
-    const int X0 = txi * kTile, Y0 = tyi * kTile;
-    const int r = Y0 + ty, c0 = X0 + 4 * tx;
-    const bool row_ok = r < H;
-    const int base = r * W + c0;
-    float dv[4], wv[4], wraw[4], fv[8], gwv[4], gdv[4];
-    float zm = 0.f, wm = 1.f;
-    if (row_ok) {
-      load_vec<4>(db + base, dv);
-      load_vec2<4>(fl + 2 * base, fv);
-      if (wt) {  // plain (coherent) load: the logits may be updated in place below
-        const float4 w4 = *reinterpret_cast<const float4*>(wt + base);
-        wraw[0] = w4.x; wraw[1] = w4.y; wraw[2] = w4.z; wraw[3] = w4.w;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) wv[v] = weight_of(wraw[v], wsens);
-        // a sigmoid never exceeds 1; raw weights (wsens == 0) may
-        if (wsens == 0.f) wm = fmaxf(fmaxf(fabsf(wv[0]), fabsf(wv[1])), fmaxf(fabsf(wv[2]), fabsf(wv[3])));
-      } else {
-#pragma unroll
-        for (int v = 0; v < 4; ++v) wv[v] = 1.f;
-      }
-      zm = fmaxf(fmaxf(fabsf(dv[0]), fabsf(dv[1])), fmaxf(fabsf(dv[2]), fabsf(dv[3])));
-    } else {
-#pragma unroll
-      for (int v = 0; v < 8; ++v) fv[v] = 0.f;
-    }
-    // tile statistics: mean flow (window origin), max |depth| and max weight (fixed-point scale)
-    float mx, my, zmax, wmax;
-    tile_stats((fv[0] + fv[2]) + (fv[4] + fv[6]), (fv[1] + fv[3]) + (fv[5] + fv[7]), zm, wm, wsens == 0.f && wt, s_red,
-               mx, my, zmax, wmax);
-    int wx0, wy0;
-    tile_window_origin(mx, my, min(kTile, H - Y0) * kTile, X0, Y0, g.grid, wx0, wy0);
-    const FixScale fs = fix_scale_for(wmax * fmaf(bnd_z, zmax, bnd_c));
-    const float inv_scale = fs.inv_scale;
-    int* hi_flag = s_hi_used + parity;
-    auto add_u = [lo_addr](int cell, unsigned v) { return atoms_add_u32(lo_addr + 4u * (unsigned)cell, v); };
-    auto add_i = [hi_addr, hi_flag](int cell, int v) { reds_add_s32(hi_addr + 4u * (unsigned)cell, v); *hi_flag = 1; };
-    auto scatter = [&](int y0, int x0, float v0, float v1) {
-      if (!window_add(wx0, wy0, fs.scale, y0, x0, v0, v1, add_u, add_i))
-        red_pair<true>(gda + y0 * W, x0, W, v0, v1);
-    };
-    if (row_ok) {
-      const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
-#pragma unroll
-      for (int v = 0; v < 4; ++v)
-        distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v], fv[2 * v],
-                         fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
-      red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
-      if (wt) quad_weight_outputs(gwv, wv, wraw, wt, gw, adam, pa.weight, base, pair, wsens);
-    }
-    __syncthreads();
-    // Flush the touched cells (one aligned 16-byte RED per four cells) and reset them.  The high
-    // words are only looked at when some add of this tile touched one (rare).  The other parity's
-    // flag is cleared here: its last readers passed the previous trailing barrier, its next
-    // writers start after this tile's.
-    const bool any_hi = *hi_flag != 0;
-    if (threadIdx.x == 0) s_hi_used[parity ^ 1] = 0;
-    for (int i = threadIdx.x; i < kWin * kWin / 4; i += kThreads) {
-      const uint4 l4 = reinterpret_cast<uint4*>(win_lo)[i];
-      int4 h4 = make_int4(0, 0, 0, 0);
-      if (any_hi) h4 = reinterpret_cast<int4*>(win_hi)[i];
-      const unsigned dirty = ((l4.x ^ kFixBias) | (l4.y ^ kFixBias)) | ((l4.z ^ kFixBias) | (l4.w ^ kFixBias)) |
-                             (unsigned)((h4.x | h4.y) | (h4.z | h4.w));
-      if (dirty == 0) continue;
-      const int uy = i >> 4, ux = (i & 15) << 2;  // kWin / 4 == 16 groups per window row
-      const int gy = wy0 + uy, gx = wx0 + ux;
-      // taps are clamped into the image, so a touched cell is always inside it
-      if (gy >= 0 && gy < H && gx >= 0 && gx + 3 < W)
-        red_add4(gda + gy * W + gx, fix_value(l4.x, h4.x) * inv_scale, fix_value(l4.y, h4.y) * inv_scale,
-                 fix_value(l4.z, h4.z) * inv_scale, fix_value(l4.w, h4.w) * inv_scale);
-      reinterpret_cast<uint4*>(win_lo)[i] = make_uint4(kFixBias, kFixBias, kFixBias, kFixBias);
-      if (any_hi) reinterpret_cast<int4*>(win_hi)[i] = make_int4(0, 0, 0, 0);
-    }
-    __syncthreads();
-  }
-  block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
-}
-
-// ------------------------------------------------------------------------------------------
-// Phase D2, tiled, 32 x 64 tiles (opt-in, FM_SCATTER=tiled64): k_distribute_tiled spends a third
-// of its 392 instructions per pixel on per-tile work (statistics, two barriers, the flush of 4
-// window cells per pixel).  Here a block owns 32 x 64 tiles -- every thread processes two groups of
-// four pixels, 32 rows apart, against ONE 64 x 96 window (3 cells per pixel): the tile statistics
-// (window origin, fixed-point scale) come from the upper 32 rows only -- they are only a
-// placement / scaling heuristic, correctness never depends on them (fm_pixel.cuh) -- and the
-// flush reads the high words only if some add of the tile touched one.  48 KB of dynamic shared
-// memory for the window.
-constexpr int kTile64H = 64, kWin64H = kTile64H + 2 * kHalo;
-constexpr size_t kTiled64Smem = (size_t)kWin * kWin64H * (sizeof(unsigned) + sizeof(int));
-
-__global__ void __launch_bounds__(kThreads, 3)
-k_distribute_tiled64(const float* __restrict__ depth, const float* __restrict__ k4,
-                     const float* __restrict__ bflow, float* weights,
-                     const PairAdjoint* __restrict__ adj, float* __restrict__ g_depth,
-                     float* __restrict__ g_weights, double* __restrict__ k4acc, float wsens,
-                     PairLayout lay, AdamFuse adam, int H, int W) {
-  constexpr int NW = kThreads / 32;
-  constexpr int kCells = kWin * kWin64H;
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  unsigned* win_lo = reinterpret_cast<unsigned*>(dyn_smem);
-  int* win_hi = reinterpret_cast<int*>(dyn_smem + (size_t)kCells * sizeof(unsigned));
-  __shared__ double smem[8 * NW];
-  __shared__ PairAdjoint s_adj;
-  __shared__ __align__(16) float s_red[4 * NW];
-  __shared__ int s_hi_used[2];
-  const int pair = blockIdx.y;
-  const int N = H * W;
-  if (threadIdx.x < sizeof(PairAdjoint) / 4)
-    reinterpret_cast<float*>(&s_adj)[threadIdx.x] = reinterpret_cast<const float*>(adj + pair)[threadIdx.x];
-  for (int i = threadIdx.x; i < kCells / 4; i += kThreads) {
-    reinterpret_cast<uint4*>(win_lo)[i] = make_uint4(kFixBias, kFixBias, kFixBias, kFixBias);
-    reinterpret_cast<int4*>(win_hi)[i] = make_int4(0, 0, 0, 0);
-  }
-  if (threadIdx.x < 2) s_hi_used[threadIdx.x] = 0;
-  __syncthreads();
-  const PairAdjoint ad = s_adj;
-  const PairAddr pa = pair_addr(lay, pair, N);
-  const PairGeom g = pair_geom(depth, k4, pa, H, W);
-  const int a = pa.k4_frame_a;
-  const float* da = opaque_ptr(depth + pa.depth_a);
-  const float* db = da + N;
-  const float* fl = bflow + pa.flow;
-  float* wt = weights ? weights + pa.weight : nullptr;
-  float* gda = g_depth + pa.depth_a;
-  float* gdb = gda + N;
-  float* gw = g_weights ? g_weights + pa.weight : nullptr;
-  auto load_a = [da](int o) { return __ldg(da + o); };
-  float kacc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
-  float bnd_z, bnd_c;
-  scatter_bound_consts(g, ad, bnd_z, bnd_c);
-  // 32-bit shared-space addresses of the window: the atomics below address it directly instead of
-  // re-deriving a generic address for every tap
-  const unsigned lo_addr = opaque_u32((unsigned)__cvta_generic_to_shared(win_lo));
-  const unsigned hi_addr = lo_addr + (unsigned)((const char*)win_hi - (const char*)win_lo);
-  const int tiles_x = W / kTile, tiles_y = (H + kTile64H - 1) / kTile64H;
-  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-  int parity = 0;
-
-  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x, parity ^= 1) {
-    const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
-    const int X0 = txi * kTile, Y0 = tyi * kTile64H;
-    const int c0 = X0 + 4 * tx;
-    int wx0 = 0, wy0 = 0;
-    float scale = 0.f, inv_scale = 0.f;
-    int* hi_flag = s_hi_used + parity;
-    auto add_u = [lo_addr](int cell, unsigned v) { return atoms_add_u32(lo_addr + 4u * (unsigned)cell, v); };
-    auto add_i = [hi_addr, hi_flag](int cell, int v) { reds_add_s32(hi_addr + 4u * (unsigned)cell, v); *hi_flag = 1; };
-    auto scatter = [&](int y0, int x0, float v0, float v1) {
-      if (!window_add_t<kWin64H>(wx0, wy0, scale, y0, x0, v0, v1, add_u, add_i))
-        red_pair<true>(gda + y0 * W, x0, W, v0, v1);
-    };
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      const int r = Y0 + ty + 32 * half;
-      const bool row_ok = r < H;
-      const int base = r * W + c0;
-      float dv[4], wv[4], wraw[4], fv[8], gwv[4], gdv[4];
-      if (row_ok) {
-        load_vec<4>(db + base, dv);
-        load_vec2<4>(fl + 2 * base, fv);
-        if (wt) {  // plain (coherent) load: the logits may be updated in place below
-          const float4 w4 = *reinterpret_cast<const float4*>(wt + base);
-          wraw[0] = w4.x; wraw[1] = w4.y; wraw[2] = w4.z; wraw[3] = w4.w;
-#pragma unroll
-          for (int v = 0; v < 4; ++v) wv[v] = weight_of(wraw[v], wsens);
-        } else {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) wv[v] = 1.f;
-        }
-      }
-      if (half == 0) {  // block-uniform: tile statistics from the upper 32 rows
-        float zm = 0.f, wm = 1.f, sx = 0.f, sy = 0.f;
-        if (row_ok) {
-          zm = fmaxf(fmaxf(fabsf(dv[0]), fabsf(dv[1])), fmaxf(fabsf(dv[2]), fabsf(dv[3])));
-          if (wt && wsens == 0.f) wm = fmaxf(fmaxf(fabsf(wv[0]), fabsf(wv[1])), fmaxf(fabsf(wv[2]), fabsf(wv[3])));
-          sx = (fv[0] + fv[2]) + (fv[4] + fv[6]);
-          sy = (fv[1] + fv[3]) + (fv[5] + fv[7]);
-        }
-        float mx, my, zmax, wmax;
-        tile_stats(sx, sy, zm, wm, wsens == 0.f && wt, s_red, mx, my, zmax, wmax);
-        tile_window_origin_t<kWin64H>(mx, my, min(kTile, H - Y0) * kTile, X0, Y0, g.grid, wx0, wy0);
-        const FixScale fs = fix_scale_for(wmax * fmaf(bnd_z, zmax, bnd_c));
-        scale = fs.scale; inv_scale = fs.inv_scale;
-      }
-      if (row_ok) {
-        const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v], fv[2 * v],
-                           fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
-        red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
-        if (wt) quad_weight_outputs(gwv, wv, wraw, wt, gw, adam, pa.weight, base, pair, wsens);
-      }
-    }
-    __syncthreads();
-    // flush (see k_distribute_tiled); the two cases of the block-uniform any_hi are separate loops
-    // so that the common one carries no 64-bit conversion code at all
-    const bool any_hi = *hi_flag != 0;
-    if (threadIdx.x == 0) s_hi_used[parity ^ 1] = 0;
-    if (!any_hi) {
-      for (int i = threadIdx.x; i < kCells / 4; i += kThreads) {
-        const uint4 l4 = reinterpret_cast<uint4*>(win_lo)[i];
-        const unsigned dx = l4.x ^ kFixBias, dy = l4.y ^ kFixBias, dz = l4.z ^ kFixBias, dw = l4.w ^ kFixBias;
-        if (((dx | dy) | (dz | dw)) == 0) continue;
-        const int gy = wy0 + (i >> 4), gx = wx0 + ((i & 15) << 2);
-        if (gy < H && gx + 3 < W)  // wx0, wy0 >= 0: the window was clamped onto the image
-          red_add4(gda + gy * W + gx, (float)(int)dx * inv_scale, (float)(int)dy * inv_scale,
-                   (float)(int)dz * inv_scale, (float)(int)dw * inv_scale);
-        reinterpret_cast<uint4*>(win_lo)[i] = make_uint4(kFixBias, kFixBias, kFixBias, kFixBias);
-      }
-    } else {
-      for (int i = threadIdx.x; i < kCells / 4; i += kThreads) {
-        const uint4 l4 = reinterpret_cast<uint4*>(win_lo)[i];
-        const int4 h4 = reinterpret_cast<int4*>(win_hi)[i];
-        const unsigned dirty = ((l4.x ^ kFixBias) | (l4.y ^ kFixBias)) | ((l4.z ^ kFixBias) | (l4.w ^ kFixBias)) |
-                               (unsigned)((h4.x | h4.y) | (h4.z | h4.w));
-        if (dirty == 0) continue;
-        const int gy = wy0 + (i >> 4), gx = wx0 + ((i & 15) << 2);
-        if (gy < H && gx + 3 < W)
-          red_add4(gda + gy * W + gx, fix_value(l4.x, h4.x) * inv_scale, fix_value(l4.y, h4.y) * inv_scale,
-                   fix_value(l4.z, h4.z) * inv_scale, fix_value(l4.w, h4.w) * inv_scale);
-        reinterpret_cast<uint4*>(win_lo)[i] = make_uint4(kFixBias, kFixBias, kFixBias, kFixBias);
-        reinterpret_cast<int4*>(win_hi)[i] = make_int4(0, 0, 0, 0);
-      }
-    }
-    __syncthreads();
-  }
-  block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
-}
+#include "fm_tiled.cuh"
 
 __global__ void k_k4_finalize(const double* __restrict__ k4acc, const double* __restrict__ flowacc,
                               int include_flow, const float* __restrict__ flow_scale,
@@ -2186,39 +1791,6 @@ int blocks_for_points(int n) {
   return nb < 1 ? 1 : nb;
 }
 
-// Procrustes-adjoint scatter: FM_SCATTER=tiled / tiled64 select the shared-memory fixed-point
-// windows (k_distribute_tiled / k_distribute_tiled64), anything else the global vector REDs
-// (k_distribute).  Read per call (a getenv): tests and tools flip it inside one process.
-int scatter_mode() {
-  const char* v = getenv("FM_SCATTER");
-  if (!v) return 0;
-  if (!strcmp(v, "tiled")) return 1;
-  if (!strcmp(v, "tiled64")) return 2;
-  return 0;
-}
-
-bool tile2d_enabled() {  // FM_MAP=tile2d: 32 x 32-tile thread -> pixel mapping in the gather kernels
-  const char* v = getenv("FM_MAP");
-  return v && !strcmp(v, "tile2d");
-}
-
-bool fast_adam_enabled() {  // FM_ADAM=fast: the fused weight-logit Adam with single-MUFU sqrt / divisions
-  const char* v = getenv("FM_ADAM");
-  return v && !strcmp(v, "fast");
-}
-
-int tiles_per_cta64() {  // 32 x 64 tiles: half as many per block for the same pixels per block
-  const char* v = getenv("FM_TILED_TILES_PER_CTA");
-  const int n = v ? atoi(v) : 0;
-  return n >= 1 && n <= 1024 ? n : 4;
-}
-
-int tiles_per_cta() {  // tuning knob of tools/ab_scatter.py (a block walks this many 32 x 32 tiles)
-  const char* v = getenv("FM_TILED_TILES_PER_CTA");
-  const int n = v ? atoi(v) : 0;
-  return n >= 1 && n <= 1024 ? n : 8;
-}
-
 bool bad_dims(int B, int F, int H, int W) { return B < 1 || F < 2 || H < 1 || W < 1 || (long long)H * W > (1ll << 30); }
 
 }  // namespace
@@ -2250,6 +1822,110 @@ int launch_flow(const float* depth, const float* k4, const float* rt, const floa
   FM_CHECK_LAUNCH("k_flow_lean");
   k_flow_lean_convert<<<(BF + 63) / 64, 64, 0, s>>>(flowacc, rt, k4, focal ? 1 : 0, B, F, H, W);
   FM_CHECK_LAUNCH("k_flow_lean_convert");
+  return 0;
+}
+}  // namespace
+
+// ---------------------------------------------------------------- tiled path: host side
+namespace {
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder() {
+  static const TensorMapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (TensorMapEncodeFn)p;
+  }();
+  return fn;
+}
+
+// (W, H, frames) float32 tensor, box = one (kWX x kWY x 1) window; out-of-range parts read as 0.
+int make_window_map(CUtensorMap* m, const float* base, int W, int H, int frames) {
+  const TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) return fail_msg("tiled path: cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 4ull, (cuuint64_t)W * (cuuint64_t)H * 4ull};
+  const cuuint32_t box[3] = {(cuuint32_t)tiled::kWX, (cuuint32_t)tiled::kWY, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[128];
+    snprintf(msg, sizeof(msg), "tiled path: cuTensorMapEncodeTiled failed (CUresult %d) for %d x %d x %d", (int)r, W, H, frames);
+    return fail_msg(msg);
+  }
+  return 0;
+}
+
+int sm_count() {
+  static const int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1)
+      v = 148;
+    return v;
+  }();
+  return n;
+}
+
+bool tiled_shape_ok(int F, int H, int W) { return F >= 2 && W % 4 == 0 && H >= 1 && W < 32768 && H < 32768; }
+
+// Phase A through the plan: moments of all pairs (+ the step's correspondence weights into the
+// plan's scratch for phase D), then the solve.
+int launch_moments_tiled(const float* depth, const float* k4, const float* bflow, const float* weights, float wsens,
+                         const tiled::Plan& pl, double* moments, int F, int H, int W, cudaStream_t s) {
+  CUtensorMap tm;
+  int rc = make_window_map(&tm, depth, W, H, F);
+  if (rc) return rc;
+  tiled::MomArgs b;
+  b.depth = depth; b.k4 = k4; b.bflow = bflow; b.weights = weights; b.wscratch = pl.wscratch; b.moments = moments;
+  b.tinfo = pl.tiles; b.wsens = wsens; b.F = F; b.H = H; b.W = W; b.tiles_x = pl.tiles_x;
+  b.tiles = pl.tiles_x * pl.tiles_y; b.n_items = (F - 1) * b.tiles;
+  int grid = sm_count() * 3;
+  if (grid > b.n_items) grid = b.n_items;
+  static const cudaError_t at1 = cudaFuncSetAttribute(tiled::k_moments_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled::kMomSmem);
+  static const cudaError_t at0 = cudaFuncSetAttribute(tiled::k_moments_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled::kMomSmem);
+  if (at1 != cudaSuccess || at0 != cudaSuccess) return fail("k_moments_tiled: shared memory attribute", at1 != cudaSuccess ? at1 : at0);
+  if (weights) tiled::k_moments_tiled<true><<<grid, tiled::kT, tiled::kMomSmem, s>>>(tm, b);
+  else tiled::k_moments_tiled<false><<<grid, tiled::kT, tiled::kMomSmem, s>>>(tm, b);
+  FM_CHECK_LAUNCH("k_moments_tiled");
+  return 0;
+}
+
+// Phase D2 through the plan: transposed (gather-form) bilinear splat + per-pixel adjoints + final depth
+// gradient in one pass; flow outliers afterwards as REDs.
+int launch_backward_tiled(const float* depth, const float* k4, const float* bflow, float* weights, float wsens,
+                          const tiled::Plan& pl, unsigned ovf_max, const PairAdjoint* adj, float* g_depth,
+                          float* g_weights, const AdamFuse& af, int F, int H, int W, cudaStream_t s) {
+  CUtensorMap tm_d, tm_w;
+  int rc = make_window_map(&tm_d, depth, W, H, F);
+  if (rc) return rc;
+  if ((rc = make_window_map(&tm_w, pl.wscratch, W, H, F - 1))) return rc;
+  tiled::BwdArgs b;
+  b.depth = depth; b.k4 = k4; b.bflow = bflow; b.weights = weights; b.adj = adj; b.tinfo = pl.tiles;
+  b.perm = pl.perm; b.entries = pl.entries; b.g_depth = g_depth; b.g_weights = g_weights; b.adam = af;
+  b.wsens = wsens; b.F = F; b.H = H; b.W = W; b.tiles_x = pl.tiles_x; b.tiles = pl.tiles_x * pl.tiles_y;
+  b.n_items = F * b.tiles;
+  int grid = sm_count() * 2;
+  if (grid > b.n_items) grid = b.n_items;
+  static const cudaError_t at1 = cudaFuncSetAttribute(tiled::k_backward_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled::kBwdSmem);
+  static const cudaError_t at0 = cudaFuncSetAttribute(tiled::k_backward_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled::kBwdSmem);
+  if (at1 != cudaSuccess || at0 != cudaSuccess) return fail("k_backward_tiled: shared memory attribute", at1 != cudaSuccess ? at1 : at0);
+  if (weights) tiled::k_backward_tiled<true><<<grid, tiled::kT, tiled::kBwdSmem, s>>>(tm_d, tm_w, b);
+  else tiled::k_backward_tiled<false><<<grid, tiled::kT, tiled::kBwdSmem, s>>>(tm_d, tm_w, b);
+  FM_CHECK_LAUNCH("k_backward_tiled");
+  if (ovf_max > 0u) {
+    const unsigned n = ovf_max < (unsigned)pl.ovf_cap ? ovf_max : (unsigned)pl.ovf_cap;
+    dim3 g2((n + 255u) / 256u, F - 1);
+    tiled::k_backward_overflow<<<g2, 256, 0, s>>>(depth, k4, weights ? pl.wscratch : nullptr, adj, pl.ovf_count, pl.ovf,
+                                                  pl.ovf_cap, g_depth, H, W);
+    FM_CHECK_LAUNCH("k_backward_overflow");
+  }
   return 0;
 }
 }  // namespace
@@ -2312,23 +1988,25 @@ int fm_reproject(const float* xyz, const float* rt, const float* k4, float* xy, 
 static int procrustes_fwd_impl(const float* depth, const float* k4, const float* backward_flow,
                                const float* weights, float wsens, const int64_t* indices,
                                int num_indices, float* rt, void* ws, int B, int F, int H, int W,
-                               void* stream, const PairLayout* layout = nullptr) {
+                               void* stream, const PairLayout* layout = nullptr, void* plan = nullptr) {
   const PairLayout lay = layout ? *layout : dense_layout(F, H, W);
   if (!depth || !k4 || !backward_flow || !rt || !ws || bad_dims(B, F, H, W))
     return fail_msg("fm_procrustes_fwd: bad arguments");
+  if (plan && (B != 1 || indices || layout || !tiled_shape_ok(F, H, W)))
+    return fail_msg("fm_procrustes_fwd: the splat plan serves the dense single-video path with W % 4 == 0");
   if (indices && num_indices < 1) return fail_msg("fm_procrustes_fwd: empty index set");
   cudaStream_t s = (cudaStream_t)stream;
   Workspace w = carve(ws, B, F);
   const int BP = B * (F - 1);
   cudaError_t e = cudaMemsetAsync(w.moments, 0, (size_t)BP * kNumMoments * sizeof(double), s);
   if (e != cudaSuccess) return fail("fm_procrustes_fwd: memset", e);
-  if (indices) {
+  if (plan) {
+    const tiled::Plan pl = tiled::plan_carve(plan, F, H, W);
+    const int rc = launch_moments_tiled(depth, k4, backward_flow, weights, wsens, pl, w.moments, F, H, W, s);
+    if (rc) return rc;
+  } else if (indices) {
     dim3 grid(blocks_for_points(num_indices), BP);
     k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.moments, wsens, lay, H, W);
-  } else if (W % 32 == 0 && tile2d_enabled()) {  // opt-in experiment: 2-D thread -> pixel mapping
-    const int tiles = (W / 32) * ((H + 31) / 32);
-    dim3 grid((tiles + 15) / 16, BP);
-    k_moments<4, true><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, lay, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
     k_moments<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, lay, H, W);
@@ -2336,7 +2014,7 @@ static int procrustes_fwd_impl(const float* depth, const float* k4, const float*
     dim3 grid(blocks_for(H * W, 1), BP);
     k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, lay, H, W);
   }
-  FM_CHECK_LAUNCH("fm_procrustes_fwd: k_moments");
+  if (!plan) FM_CHECK_LAUNCH("fm_procrustes_fwd: k_moments");
   k_solve<<<(BP + 63) / 64, 64, 0, s>>>(w.moments, depth, rt, w.state, BP, lay, H, W);
   FM_CHECK_LAUNCH("fm_procrustes_fwd: k_solve");
   return 0;
@@ -2354,8 +2032,11 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
                                int num_indices, const float* g_rt, int include_flow_loss,
                                const float* flow_scale, float* g_depth, float* g_weights, float* g_k4,
                                void* ws, int B, int F, int H, int W, void* stream,
-                               const PairLayout* layout = nullptr, const AdamFuse* adam = nullptr) {
+                               const PairLayout* layout = nullptr, const AdamFuse* adam = nullptr,
+                               void* plan = nullptr, unsigned plan_ovf_max = 0u) {
   const PairLayout lay = layout ? *layout : dense_layout(F, H, W);
+  if (plan && (B != 1 || indices || layout || !tiled_shape_ok(F, H, W)))
+    return fail_msg("fm_procrustes_bwd: the splat plan serves the dense single-video path with W % 4 == 0");
   if (!depth || !k4 || !backward_flow || !g_depth || !g_k4 || !ws || bad_dims(B, F, H, W))
     return fail_msg("fm_procrustes_bwd: bad arguments");
   if (!g_rt && !include_flow_loss) return fail_msg("fm_procrustes_bwd: no pose gradient given");
@@ -2372,34 +2053,28 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
     k_scale_inplace<<<148 * 4, kThreads, 0, s>>>(g_depth, flow_scale, (size_t)BF * H * W);
     FM_CHECK_LAUNCH("fm_procrustes_bwd: k_scale_inplace");
   }
+  if (plan) {
+    // one focal length shared by all frames (or constant intrinsics): the Procrustes part of the
+    // intrinsics gradient comes from the moment sums, the pixel kernel carries no K accumulators
+    k_adjoint<<<(BP + 63) / 64, 64, 0, s>>>(w.flowacc, w.state, g_rt, include_flow_loss, flow_scale, w.adj, BP, F,
+                                            w.moments, k4, w.k4acc);
+    FM_CHECK_LAUNCH("fm_procrustes_bwd: k_adjoint");
+    const tiled::Plan pl = tiled::plan_carve(plan, F, H, W);
+    const int rc = launch_backward_tiled(depth, k4, backward_flow, weights_rw, wsens, pl, plan_ovf_max, w.adj, g_depth,
+                                         g_weights, af, F, H, W, s);
+    if (rc) return rc;
+    k_k4_finalize<<<(BF + 127) / 128, 128, 0, s>>>(w.k4acc, w.flowacc, include_flow_loss, flow_scale, g_k4, B, F);
+    FM_CHECK_LAUNCH("fm_procrustes_bwd: k_k4_finalize");
+    return 0;
+  }
   k_adjoint<<<(BP + 63) / 64, 64, 0, s>>>(w.flowacc, w.state, g_rt, include_flow_loss, flow_scale, w.adj, BP, F);
   FM_CHECK_LAUNCH("fm_procrustes_bwd: k_adjoint");
-  const int smode = indices ? 0 : scatter_mode();
   if (indices) {
     dim3 grid(blocks_for_points(num_indices), BP);
     k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
-  } else if (W % kTile == 0 && lay.cand == 1 && smode == 2) {  // opt-in experiment, 32 x 64 tiles
-    static const cudaError_t attr = cudaFuncSetAttribute(k_distribute_tiled64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTiled64Smem);
-    if (attr != cudaSuccess) return fail("k_distribute_tiled64: shared memory attribute", attr);
-    const int tiles = (W / kTile) * ((H + kTile64H - 1) / kTile64H);
-    const int per_cta = tiles_per_cta64();
-    dim3 grid((tiles + per_cta - 1) / per_cta, BP);
-    k_distribute_tiled64<<<grid, kThreads, kTiled64Smem, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
-  } else if (W % kTile == 0 && lay.cand == 1 && smode == 1) {  // opt-in experiment, 32 x 32 tiles
-    const int tiles = (W / kTile) * ((H + kTile - 1) / kTile);
-    const int per_cta = tiles_per_cta();
-    dim3 grid((tiles + per_cta - 1) / per_cta, BP);
-    k_distribute_tiled<<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   } else if (W % 4 == 0) {
     dim3 grid(blocks_for(H * W, 4), BP);
-    if (W % 32 == 0 && tile2d_enabled()) {  // opt-in experiment: 2-D thread -> pixel mapping
-      const int tiles = (W / 32) * ((H + 31) / 32);
-      dim3 grid2((tiles + 15) / 16, BP);
-      k_distribute<4, false, true><<<grid2, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
-    } else if (af.on && fast_adam_enabled())  // opt-in experiment
-      k_distribute<4, true><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
-    else
-      k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
+    k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   } else {
     dim3 grid(blocks_for(H * W, 1), BP);
     k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
@@ -2418,6 +2093,78 @@ int fm_procrustes_bwd(const float* depth, const float* k4, const float* backward
   return procrustes_bwd_impl(depth, k4, backward_flow, weights, 0.f, indices, num_indices, g_rt,
                              include_flow_loss, flow_scale, g_depth, g_weights, g_k4, ws, B, F, H, W,
                              stream);
+}
+
+size_t fm_splat_plan_bytes(int F, int H, int W) {
+  if (!tiled_shape_ok(F, H, W) || (long long)H * W > (1ll << 30)) return 0;
+  return tiled::plan_carve(nullptr, F, H, W).bytes;
+}
+
+int fm_splat_plan_build(const float* backward_flow, void* plan, int F, int H, int W, void* stream) {
+  if (!backward_flow || !plan || !tiled_shape_ok(F, H, W) || bad_dims(1, F, H, W))
+    return fail_msg("fm_splat_plan_build: bad arguments (needs F >= 2 and W % 4 == 0)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const tiled::Plan pl = tiled::plan_carve(plan, F, H, W);
+  const int P = F - 1, tiles = pl.tiles_x * pl.tiles_y;
+  const size_t N = (size_t)H * W;
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(pl.count, 0, (size_t)P * N * sizeof(unsigned), s)) != cudaSuccess ||
+      (e = cudaMemsetAsync(pl.tile_sum, 0, (size_t)P * tiles * sizeof(int4), s)) != cudaSuccess ||
+      (e = cudaMemsetAsync(pl.ovf_count, 0, (size_t)P * sizeof(unsigned), s)) != cudaSuccess)
+    return fail("fm_splat_plan_build: memset", e);
+  tiled::k_plan_init<<<1, 1, 0, s>>>(pl.hdr, F, H, W, pl.tiles_x, pl.tiles_y, pl.ovf_cap, (unsigned long long)pl.entry_capacity);
+  FM_CHECK_LAUNCH("k_plan_init");
+  int nb = (int)((N + 255) / 256);
+  if (nb > 1024) nb = 1024;
+  tiled::k_plan_count<<<dim3(nb, P), 256, 0, s>>>(backward_flow, pl.count, pl.tile_sum, H, W, pl.tiles_x, tiles);
+  FM_CHECK_LAUNCH("k_plan_count");
+  tiled::k_plan_sort<<<dim3(tiles, P), tiled::kT, 0, s>>>(backward_flow, pl.count, pl.tile_sum, pl.tiles, pl.perm, pl.slot_of,
+                                                           pl.tile_total, pl.hdr, H, W, pl.tiles_x, tiles);
+  FM_CHECK_LAUNCH("k_plan_sort");
+  tiled::k_plan_scan<<<1, 1024, 0, s>>>(pl.tile_total, pl.tiles, pl.hdr, P * tiles, (unsigned long long)pl.entry_capacity);
+  FM_CHECK_LAUNCH("k_plan_scan");
+  if ((e = cudaMemsetAsync(pl.count, 0, (size_t)P * N * sizeof(unsigned), s)) != cudaSuccess)
+    return fail("fm_splat_plan_build: memset", e);
+  tiled::k_plan_fill<<<dim3(nb, P), 256, 0, s>>>(backward_flow, pl.tiles, pl.slot_of, pl.count, pl.entries, pl.ovf_count, pl.ovf,
+                                                 pl.hdr, H, W, pl.tiles_x, tiles, (unsigned long long)pl.entry_capacity, pl.ovf_cap);
+  FM_CHECK_LAUNCH("k_plan_fill");
+  const size_t slots = (size_t)P * tiles * tiled::kCells;
+  tiled::k_plan_canon<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(pl.tiles, pl.perm, pl.count, pl.entries, pl.ovf_count, pl.hdr,
+                                                                     H, W, pl.tiles_x, tiles, P, (unsigned long long)pl.entry_capacity);
+  FM_CHECK_LAUNCH("k_plan_canon");
+  return 0;
+}
+
+int fm_splat_plan_info(const void* plan, int* status, unsigned* overflow_max, unsigned long long* total_entries,
+                       void* stream) {
+  if (!plan) return fail_msg("fm_splat_plan_info: bad arguments");
+  tiled::PlanHeader h;
+  cudaError_t e = cudaMemcpyAsync(&h, plan, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) return fail("fm_splat_plan_info", e);
+  if (h.magic != tiled::kPlanMagic) return fail_msg("fm_splat_plan_info: not a splat plan");
+  if (status) *status = h.status;
+  if (overflow_max) *overflow_max = h.ovf_max;
+  if (total_entries) *total_entries = h.total_entries;
+  return 0;
+}
+
+int fm_procrustes_fwd_planned(const float* depth, const float* k4, const float* backward_flow, const float* weights,
+                              float weight_sensitivity, void* plan, float* rt, void* ws, int F, int H, int W,
+                              void* stream) {
+  if (!plan) return fail_msg("fm_procrustes_fwd_planned: plan missing");
+  return procrustes_fwd_impl(depth, k4, backward_flow, weights, weight_sensitivity, nullptr, 0, rt, ws, 1, F, H, W,
+                             stream, nullptr, plan);
+}
+
+int fm_procrustes_bwd_planned(const float* depth, const float* k4, const float* backward_flow, const float* weights,
+                              float weight_sensitivity, void* plan, unsigned plan_overflow_max, const float* g_rt,
+                              int include_flow_loss, float* g_depth, float* g_weights, float* g_k4, void* ws, int F,
+                              int H, int W, void* stream) {
+  if (!plan) return fail_msg("fm_procrustes_bwd_planned: plan missing");
+  return procrustes_bwd_impl(depth, k4, backward_flow, weights, weight_sensitivity, nullptr, 0, g_rt, include_flow_loss,
+                             nullptr, g_depth, g_weights, g_k4, ws, 1, F, H, W, stream, nullptr, nullptr, plan,
+                             plan_overflow_max);
 }
 
 int fm_mask_sum(const float* forward_mask, const float* backward_mask, double* out, size_t count, void* stream) {
@@ -2810,6 +2557,8 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
   if (a->phase < FM_STEP_ALL || a->phase > FM_STEP_BACKWARD) return fail_msg("fm_overfit_step: unknown phase");
   if (a->phase != FM_STEP_ALL && a->tracks)
     return fail_msg("fm_overfit_step: a split step takes the tracking gradient through g_rt / track_g_k4");
+  // the splat plan of this video's backward flows serves the dense path (all-pixel Procrustes)
+  void* plan = (a->splat_plan && !a->indices && tiled_shape_ok(F, H, W)) ? a->splat_plan : nullptr;
   // intrinsics from the focal parameter (regressed stage) or as given
   float* k4 = a->k4;
   if (a->phase != FM_STEP_BACKWARD) {
@@ -2819,7 +2568,7 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
     }
     // Model.forward: Procrustes poses (model.py:54-90)
     if ((rc = procrustes_fwd_impl(a->depth, k4, a->bflow, a->weight_logits, a->weight_sensitivity,
-                                  a->indices, a->num_indices, a->rt, a->ws, 1, F, H, W, stream)))
+                                  a->indices, a->num_indices, a->rt, a->ws, 1, F, H, W, stream, nullptr, plan)))
       return rc;
     // LossFlow forward + direct gradients (loss_flow.py:31-70)
     e = cudaMemsetAsync(w.flowacc, 0, (size_t)F * kFlowAcc * sizeof(double), s);
@@ -2872,7 +2621,8 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
   }
   if ((rc = procrustes_bwd_impl(a->depth, k4, a->bflow, a->weight_logits, a->weight_sensitivity,
                                 a->indices, a->num_indices, g_rt, 1, nullptr, a->g_depth, a->g_weights,
-                                a->g_k4, a->ws, 1, F, H, W, stream, nullptr, fuse_w ? &af : nullptr)))
+                                a->g_k4, a->ws, 1, F, H, W, stream, nullptr, fuse_w ? &af : nullptr, plan,
+                                a->splat_overflow_max)))
     return rc;
   // Adam (model_wrapper_overfit.py:104-105)
   if (a->step > 0 && !defer) {

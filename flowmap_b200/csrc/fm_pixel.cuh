@@ -501,144 +501,6 @@ FM_HD void distribute_point(const PairGeom& g, const PairAdjoint& ad, float x, f
   kacc[3] -= ea1 * qz_true;
 }
 
-// ---------------------------------------------------------------------------------
-// Fixed-point window of the tiled Procrustes-adjoint scatter (k_distribute_tiled).
-//
-// sm_100a has no native float add on shared memory (float atomicAdd compiles to an LDS + FADD +
-// ATOMS.CAST.SPIN loop), only 32-bit integer ATOMS.ADD.  A window cell is therefore a 64-bit
-// integer kept as two 32-bit words: a contribution c becomes v = rint(c * 2^k), |v| < 2^30, and is
-// added to the low word (which starts at 2^31) with one atomic add; the returned old value tells
-// whether that add wrapped, and only then (or for a negative v that did not wrap) a second add
-// adjusts the high word.  (high, low) is an exact integer sum: it cannot overflow and does not
-// depend on the order of the adds (unlike a float RED).  `add_u(cell, v)` adds to the low word of a
-// cell and returns its old value, `add_i(cell, v)` adds to the high word: shared-memory atomics on
-// 32-bit shared addresses on the device, plain adds in tests/host_emulation.
-// ---------------------------------------------------------------------------------
-constexpr int kTile = 32, kHalo = 16, kWin = kTile + 2 * kHalo;
-constexpr unsigned kFixBias = 0x80000000u;
-constexpr float kFixLimit = 1073741824.0f;  // 2^30: larger scaled values take the float fallback
-
-FM_HD int min_i(int a, int b) { return a < b ? a : b; }
-FM_HD int max_i(int a, int b) { return a > b ? a : b; }
-
-FM_HD int fix_round(float scaled) {
-#if defined(__CUDA_ARCH__)
-  return __float2int_rn(scaled);
-#else
-  return (int)lrintf(scaled);
-#endif
-}
-
-template <typename AtomicAddU, typename AtomicAddI>
-FM_HD void fix_add(int cell, float scaled, AtomicAddU add_u, AtomicAddI add_i) {
-  const int v = fix_round(scaled);
-  const unsigned old = add_u(cell, (unsigned)v);
-  const unsigned sum = old + (unsigned)v;
-  const int inc = (v >> 31) + (sum < old ? 1 : 0);  // high word of v (0 / -1) + carry of the low add
-  if (inc != 0) add_i(cell, inc);
-}
-
-FM_HD float fix_value(unsigned lo, int hi) {
-  if (hi == 0) return (float)(int)(lo ^ kFixBias);
-  const long long total = (long long)hi * 4294967296ll + (long long)lo - 2147483648ll;
-#if defined(__CUDA_ARCH__)
-  return __ll2float_rn(total);
-#else
-  return (float)total;
-#endif
-}
-
-FM_HD float max_ray_norm(const Cam& k) {
-  const float mx = fmaxf(fabsf(k.cx), fabsf(1.0f - k.cx)) * fabsf(k.ifx);
-  const float my = fmaxf(fabsf(k.cy), fabsf(1.0f - k.cy)) * fabsf(k.ify);
-  return sqrtf(1.0f + mx * mx + my * my);
-}
-
-// Bound of the scattered values of a tile (distribute_point: c = tap weight * qb . ray_a with
-// qb = w (Cbar dp + ad.qb), dp = p' - pbar, |p'| <= |depth_b| |ray_b| + |z0|):
-//   |c| <= wmax * (bnd_z * max|depth_b| + bnd_c).
-FM_HD void scatter_bound_consts(const PairGeom& g, const PairAdjoint& ad, float& bnd_z, float& bnd_c) {
-  float c2 = 0.f;
-  for (int k = 0; k < 9; ++k) c2 += ad.cbar[k] * ad.cbar[k];
-  const float cn = sqrtf(c2);
-  const float off = sqrtf(ad.pbar[0] * ad.pbar[0] + ad.pbar[1] * ad.pbar[1] + ad.pbar[2] * ad.pbar[2]) + fabsf(g.z0);
-  const float qn = sqrtf(ad.qb[0] * ad.qb[0] + ad.qb[1] * ad.qb[1] + ad.qb[2] * ad.qb[2]);
-  const float ra = max_ray_norm(g.ka), rb = max_ray_norm(g.kb);
-  bnd_z = cn * rb * ra;
-  bnd_c = (cn * off + qn) * ra;
-}
-
-// Power-of-two scale that maps `bound` into [2^28, 2^29): bound < 2^(e - 126) for its biased
-// exponent e, so scale = 2^(155 - e) (exact in float32, as is its inverse).  A zero / tiny /
-// non-finite bound is clamped: correctness never depends on the bound, values that still
-// reach 2^30 after scaling take the float fallback.
-struct FixScale { float scale, inv_scale; };
-FM_HD FixScale fix_scale_for(float bound) {
-  int bits;
-#if defined(__CUDA_ARCH__)
-  bits = __float_as_int(bound);
-#else
-  memcpy(&bits, &bound, 4);
-#endif
-  int e = (bits >> 23) & 0xff;
-  e = e < 40 ? 40 : (e > 240 ? 240 : e);
-  const int sb = (282 - e) << 23, ib = (e - 28) << 23;
-  FixScale f;
-#if defined(__CUDA_ARCH__)
-  f.scale = __int_as_float(sb);
-  f.inv_scale = __int_as_float(ib);
-#else
-  memcpy(&f.scale, &sb, 4);
-  memcpy(&f.inv_scale, &ib, 4);
-#endif
-  return f;
-}
-
-// Window origin of a tile: tile origin - halo, shifted by the tile's mean backward flow (x to a
-// multiple of 4 so that the flush stays 16-byte aligned; W is a multiple of kTile).  fmaxf / fminf
-// also map a NaN mean to a finite origin: any origin is correct, taps are clamped into the image
-// and far ones fall back.  WINH: rows of the window (kWin for 32-row tiles, kWin + 32 for the
-// 64-row tiles of k_distribute_tiled64); the window is always kWin columns wide.
-template <int WINH>
-FM_HD void tile_window_origin_t(float sum_flx, float sum_fly, int valid_pixels, int X0, int Y0,
-                                const GridDims& grid, int& wx0, int& wy0) {
-  const float inv_cnt = 1.0f / (float)valid_pixels;
-  const float mx = fminf(fmaxf(sum_flx * inv_cnt, -4.0f), 4.0f);
-  const float my = fminf(fmaxf(sum_fly * inv_cnt, -4.0f), 4.0f);
-  wx0 = X0 - kHalo + ((int)rintf(mx * grid.Wf * 0.25f)) * 4;
-  wy0 = Y0 - kHalo + (int)rintf(my * grid.Hf);
-  // keep the window on the image (taps are clamped into it: flows that leave the frame pile up
-  // on the border rows / columns, which a window hanging over the edge would miss)
-  wx0 = max_i(min_i(wx0, grid.W - kWin), 0);
-  wy0 = max_i(min_i(wy0, grid.H - WINH), 0);
-}
-FM_HD void tile_window_origin(float sum_flx, float sum_fly, int valid_pixels, int X0, int Y0,
-                              const GridDims& grid, int& wx0, int& wy0) {
-  tile_window_origin_t<kWin>(sum_flx, sum_fly, valid_pixels, X0, Y0, grid, wx0, wy0);
-}
-
-// One tap row of a pixel into the window; false = outside the window or too large for the
-// fixed-point range (the caller then adds v0 / v1 to global memory as floats).
-template <int WINH, typename AtomicAddU, typename AtomicAddI>
-FM_HD bool window_add_t(int wx0, int wy0, float scale, int y0, int x0, float v0, float v1, AtomicAddU add_u,
-                        AtomicAddI add_i) {
-  const int ux = x0 - wx0, uy = y0 - wy0;
-  const float s0 = v0 * scale, s1 = v1 * scale;
-  // NaN compares false: non-finite values take the fallback and propagate like in the float path
-  if (!((unsigned)ux < (unsigned)(kWin - 1) && (unsigned)uy < (unsigned)WINH && fabsf(s0) < kFixLimit &&
-        fabsf(s1) < kFixLimit))
-    return false;
-  const int cell = uy * kWin + ux;
-  fix_add(cell, s0, add_u, add_i);
-  fix_add(cell + 1, s1, add_u, add_i);
-  return true;
-}
-template <typename AtomicAddU, typename AtomicAddI>
-FM_HD bool window_add(int wx0, int wy0, float scale, int y0, int x0, float v0, float v1, AtomicAddU add_u,
-                      AtomicAddI add_i) {
-  return window_add_t<kWin>(wx0, wy0, scale, y0, x0, v0, v1, add_u, add_i);
-}
-
 }  // namespace fm
 
 // ---------------------------------------------------------------------------------

@@ -129,14 +129,30 @@ class FusedOverfitter(Overfitter):
     regressed focal length, flow [+ tracking] loss, Adam) but each step is ONE C-ABI call,
     fm_overfit_step: no autograd graph, no intermediate tensors, the sigmoid of the weight
     logits and its chain rule evaluated inside the kernels, gradients accumulated into a
-    single buffer per parameter."""
+    single buffer per parameter.
 
-    def __init__(self, cfg: OverfitCfg, batch: Batch, flows: Flows, tracks=None, device="cuda"):
+    use_splat_plan=True selects the DETERMINISTIC backward (ops.SplatPlan, csrc/fm_tiled.cuh): the
+    bilinear scatter of the Procrustes adjoint is transposed once per Flows into a static plan and
+    evaluated as a gather with TMA-staged windows -- no atomics, bit-reproducible gradients.  It is
+    parity-green but measured ~10 % slower per backward than the default global-RED kernel on
+    B200 (profiles/README.md), hence opt-in."""
+
+    def __init__(self, cfg: OverfitCfg, batch: Batch, flows: Flows, tracks=None, device="cuda",
+                 use_splat_plan: bool = False):
         super().__init__(cfg, batch, flows, tracks, device)
         from ._lib import OverfitStepArgs, PackedTracksC, lib
         import ctypes
+        if batch.videos.shape[0] != 1:
+            raise ValueError("flowmap_b200: the fused step optimises one video (batch size 1), as "
+                             "flowmap/overfit.py does")
+        # the kernels read raw pointers: canonical (contiguous float32) copies, kept alive here
+        # (FlowPredictor.rescale_flow returns a permuted view, flow_predictor.py:40-49)
+        self.flows = Flows(*(ops._canon(getattr(self.flows, n), n)
+                             for n in ("forward", "backward", "forward_mask", "backward_mask")))
         dev = self.flows.forward.device
         _, f, _, h, w = batch.videos.shape
+        self._use_plan = use_splat_plan and cfg.procrustes_points is None and not cfg.procrustes_randomize
+        self._plan = ops.SplatPlan(self.flows.backward) if self._use_plan else None
         bb = self.model.backbone
         self._depth, self._wlog = bb.depth.data, bb.weights.data
         self._softmin = cfg.intrinsics == "softmin"
@@ -189,6 +205,7 @@ class FusedOverfitter(Overfitter):
         a.g_depth, a.g_weights, a.g_focal, a.g_k4 = P(self._g_depth), P(self._g_w), \
             P(self._g_focal), P(self._g_k4)
         a.rt, a.loss, a.ws = P(self.rt), P(self._loss), P(self._ws)
+        self._set_plan_args(a)
         self._packed = None
         if cfg.use_tracking:
             assert self.tracks is not None
@@ -208,20 +225,31 @@ class FusedOverfitter(Overfitter):
         self._args, self._ctypes = a, ctypes
         self._lib = lib()
 
+    def _set_plan_args(self, a):
+        pl = self._plan
+        a.splat_plan = pl.ptr if pl is not None else None
+        a.splat_overflow_max = pl.overflow_max if (pl is not None and pl.ok) else 0
+
     def set_flows(self, flows: Flows, mask_sum: Optional[Tensor] = None):
         """Point the step at another device-resident Flows of the same shape (the next batch of a
         prefetching loader) without rebuilding parameters or optimiser state.  `mask_sum` is the
         flow-loss normaliser (loss_flow.py:70) if the caller already has it."""
         old = self.flows
+        canon = {}
         for name in ("forward", "backward", "forward_mask", "backward_mask"):
             t = ops._canon(getattr(flows, name), name)
             if t.shape != getattr(old, name).shape or t.device != getattr(old, name).device:
                 raise ValueError(f"flowmap_b200: `{name}` does not match the optimiser's shapes / device")
-        self.flows = flows
+            canon[name] = t
+        flows = Flows(canon["forward"], canon["backward"], canon["forward_mask"], canon["backward_mask"])
+        self.flows = flows  # the canonical tensors stay referenced while the kernels hold their pointers
         a = self._args
         a.fflow, a.bflow = flows.forward.data_ptr(), flows.backward.data_ptr()
         a.fmask, a.bmask = flows.forward_mask.data_ptr(), flows.backward_mask.data_ptr()
         self._msum.copy_(self._mask_sum(flows) if mask_sum is None else mask_sum)
+        if self._plan is not None:  # new backward flows: new transpose
+            self._plan.rebuild(flows.backward)
+            self._set_plan_args(a)
 
     def _mask_sum(self, flows: Flows) -> Tensor:
         return ops.mask_sum(flows.forward_mask, flows.backward_mask)

@@ -28,94 +28,6 @@ static PairGeom geom(const float* depth, const float* k4, int pair, int F, int H
   return g;
 }
 
-// Serial twin of k_distribute_tiled / k_distribute_tiled64 (fm_kernels.cu): same tiles (32 x TH),
-// window origin and per-tile fixed-point scale (from the upper 32 rows of a tile), (high, low)
-// integer cells, flush and float fallback, built from the same inline functions.  stats[0] = tap
-// rows added to a window, [1] = tap rows that took the float fallback because they fell outside the
-// window, [2] = ... because of the fixed-point range, [3] = high-word adds, [4] = flushed groups
-// of four cells, [5] = touched cells outside the image (must stay 0), [6] = largest scaled
-// contribution in millionths of 2^29.
-template <int TH>
-static void bwd_tiled_impl(const float* depth, const float* k4, const float* bflow, const float* weights,
-                           const PairState* state, const double* g_rt, float* g_depth, float* g_weights,
-                           double* k4acc, long long* stats, int B, int F, int H, int W) {
-  constexpr int WINH = TH + 2 * kHalo;
-  const int N = H * W, BP = B * (F - 1);
-  std::vector<unsigned> lo(kWin * WINH, kFixBias);
-  std::vector<int> hi(kWin * WINH, 0);
-  long long hi_adds = 0;
-  auto add_u = [&lo](int cell, unsigned v) { const unsigned old = lo[cell]; lo[cell] = old + v; return old; };
-  auto add_i = [&hi, &hi_adds](int cell, int v) { hi[cell] += v; ++hi_adds; };
-  for (int pair = 0; pair < BP; ++pair) {
-    int a;
-    PairGeom g = geom(depth, k4, pair, F, H, W, a);
-    PairAdjoint ad;
-    procrustes_adjoint(state[pair], g_rt + (size_t)pair * 12, ad);
-    const float* da = depth + (size_t)a * N; const float* db = da + N;
-    float* gda = g_depth + (size_t)a * N; float* gdb = gda + N;
-    const float* fl = bflow + (size_t)pair * N * 2;
-    const float* wt = weights ? weights + (size_t)pair * N : nullptr;
-    float bnd_z, bnd_c;
-    scatter_bound_consts(g, ad, bnd_z, bnd_c);
-    const int tiles_x = W / kTile, tiles_y = (H + TH - 1) / TH;
-    for (int tile = 0; tile < tiles_x * tiles_y; ++tile) {
-      const int X0 = (tile % tiles_x) * kTile, Y0 = (tile / tiles_x) * TH;
-      const int rows = std::min(TH, H - Y0), stat_rows = std::min(kTile, H - Y0);
-      float sx = 0.f, sy = 0.f, zmax = 0.f, wmax = 1.f;
-      for (int r = Y0; r < Y0 + stat_rows; ++r)
-        for (int c = X0; c < X0 + kTile; ++c) {
-          const int j = r * W + c;
-          sx += fl[2 * j]; sy += fl[2 * j + 1];
-          zmax = fmaxf(zmax, fabsf(db[j]));
-          wmax = fmaxf(wmax, fabsf(wt ? wt[j] : 1.f));
-        }
-      int wx0, wy0;
-      tile_window_origin_t<WINH>(sx, sy, stat_rows * kTile, X0, Y0, g.grid, wx0, wy0);
-      const FixScale fs = fix_scale_for(wmax * fmaf(bnd_z, zmax, bnd_c));
-      auto scatter = [&](int y0, int x0, float v0, float v1) {
-        // stats[6]: largest |scaled contribution| seen, in millionths of 2^29 (the bound maps to
-        // [2^28, 2^29): values above 1e6 would mean the bound does not hold)
-        const float big = fmaxf(fabsf(v0 * fs.scale), fabsf(v1 * fs.scale));
-        if (big == big) stats[6] = std::max(stats[6], (long long)(big * (1.0e6f / 536870912.0f)));
-        if (window_add_t<WINH>(wx0, wy0, fs.scale, y0, x0, v0, v1, add_u, add_i)) {
-          ++stats[0];
-        } else {
-          const int ux = x0 - wx0, uy = y0 - wy0;
-          ++stats[((unsigned)ux < (unsigned)(kWin - 1) && (unsigned)uy < (unsigned)WINH) ? 2 : 1];
-          gda[y0 * W + x0] += v0;
-          if (x0 + 1 < W) gda[y0 * W + x0 + 1] += v1;
-        }
-      };
-      for (int r = Y0; r < Y0 + rows; ++r)
-        for (int c = X0; c < X0 + kTile; ++c) {
-          const int j = r * W + c;
-          float kacc[8] = {0}; float gdj, gwj;
-          distribute_point(g, ad, pix_coord(c, g.grid.Wf, g.grid.invW), pix_coord(r, g.grid.Hf, g.grid.invH), db[j],
-                           wt ? wt[j] : 1.f, fl[2 * j], fl[2 * j + 1],
-                           [da](int o) { return da[o]; }, scatter, gdj, gwj, kacc);
-          gdb[j] += gdj;
-          if (g_weights) g_weights[(size_t)pair * N + j] += gwj;
-          for (int k = 0; k < 8; ++k) k4acc[(size_t)a * 4 + k] += kacc[k];
-        }
-      for (int i = 0; i < kWin * WINH / 4; ++i) {
-        bool clean = true;
-        for (int k = 0; k < 4; ++k) clean = clean && lo[i * 4 + k] == kFixBias && hi[i * 4 + k] == 0;
-        if (clean) continue;
-        const int uy = (i * 4) / kWin, ux = (i * 4) - uy * kWin;
-        const int gy = wy0 + uy, gx = wx0 + ux;
-        if (gy >= 0 && gy < H && gx >= 0 && gx + 3 < W) {
-          for (int k = 0; k < 4; ++k) gda[gy * W + gx + k] += fix_value(lo[i * 4 + k], hi[i * 4 + k]) * fs.inv_scale;
-          ++stats[4];
-        } else {
-          stats[5] += 1;
-        }
-        for (int k = 0; k < 4; ++k) { lo[i * 4 + k] = kFixBias; hi[i * 4 + k] = 0; }
-      }
-    }
-  }
-  stats[3] = hi_adds;
-}
-
 extern "C" {
 
 size_t emu_state_bytes() { return sizeof(PairState); }
@@ -262,32 +174,5 @@ void emu_procrustes_bwd(const float* depth, const float* k4, const float* bflow,
     }
   }
 }
-void emu_procrustes_bwd_tiled(const float* depth, const float* k4, const float* bflow, const float* weights,
-                              const PairState* state, const double* g_rt, float* g_depth,
-                              float* g_weights, double* k4acc, long long* stats, int B, int F, int H,
-                              int W) {
-  bwd_tiled_impl<32>(depth, k4, bflow, weights, state, g_rt, g_depth, g_weights, k4acc, stats, B, F, H, W);
 }
 
-void emu_procrustes_bwd_tiled64(const float* depth, const float* k4, const float* bflow, const float* weights,
-                                const PairState* state, const double* g_rt, float* g_depth,
-                                float* g_weights, double* k4acc, long long* stats, int B, int F, int H,
-                                int W) {
-  bwd_tiled_impl<64>(depth, k4, bflow, weights, state, g_rt, g_depth, g_weights, k4acc, stats, B, F, H, W);
-}
-
-// fix_add / fix_value on ONE cell: adds the n scaled values, returns the (high, low) words and the
-// float the flush would produce.
-void emu_fix_accumulate(const float* scaled, int n, unsigned* lo_out, int* hi_out, float* value_out) {
-  unsigned lo = kFixBias; int hi = 0;
-  auto add_u = [&lo](int, unsigned v) { const unsigned old = lo; lo = old + v; return old; };
-  auto add_i = [&hi](int, int v) { hi += v; };
-  for (int i = 0; i < n; ++i) fix_add(0, scaled[i], add_u, add_i);
-  *lo_out = lo; *hi_out = hi; *value_out = fix_value(lo, hi);
-}
-
-void emu_fix_scale(float bound, float* scale, float* inv_scale) {
-  const FixScale f = fix_scale_for(bound);
-  *scale = f.scale; *inv_scale = f.inv_scale;
-}
-}

@@ -132,109 +132,3 @@ def test_emulated_step_matches_reference(emu, name, mapping, focal, npts, lean):
     assert rel_l2(r["g_depth"], g64["g_depth"]) <= max(1e-4, 3 * ref_noise_d)
     assert rel_l2(r["g_wparam"], g64["g_wparam"]) <= max(1e-4, 3 * ref_noise_w)
     assert abs(r["g_focal"] - float(g64["g_focal"])) <= 1e-4 * abs(float(g64["g_focal"]))
-
-
-# ------------------------------------------------------------------------------------------
-# Tiled Procrustes-adjoint scatter (k_distribute_tiled): fixed-point shared-memory window.
-# ------------------------------------------------------------------------------------------
-def test_fixed_point_cell_is_an_exact_integer_sum(emu):
-    """(high, low) words of a window cell = the exact integer sum of the rounded contributions,
-    whatever their sign pattern and however often the low word wraps (fm_pixel.cuh: fix_add)."""
-    rng = np.random.default_rng(0)
-    lim = 2.0 ** 30
-    cases = [rng.uniform(-lim, lim, 4000), rng.uniform(0.9 * lim, lim, 3000) * 0.999,
-             -rng.uniform(0.9 * lim, lim, 3000) * 0.999, rng.uniform(-3, 3, 1000), np.zeros(5),
-             np.array([-1.0]), np.array([-0.4, 0.4, -0.5, 0.5, 1.5, 2.5])]
-    for vals in cases:
-        v = np.ascontiguousarray(vals, dtype=np.float32)
-        v = v[np.abs(v) < lim]
-        lo, hi, out = ctypes.c_uint(), ctypes.c_int(), ctypes.c_float()
-        emu.emu_fix_accumulate(_p(v), len(v), ctypes.byref(lo), ctypes.byref(hi), ctypes.byref(out))
-        exact = int(sum(int(np.rint(x)) for x in v.astype(np.float64)))  # rint: ties to even, like cvt.rni
-        assert hi.value * 2 ** 32 + lo.value - 2 ** 31 == exact
-        assert out.value == np.float32(exact)
-
-
-def test_fixed_point_scale_maps_the_bound_below_2_pow_29(emu):
-    for bound in [1e-25, 3e-7, 0.999, 1.0, 1.0001, 777.0, 6e12, 1e30]:
-        s, i = ctypes.c_float(), ctypes.c_float()
-        emu.emu_fix_scale(ctypes.c_float(bound), ctypes.byref(s), ctypes.byref(i))
-        assert 2.0 ** 28 <= np.float32(bound) * np.float32(s.value) < 2.0 ** 29
-        assert s.value * i.value == 1.0 and np.log2(s.value) == np.rint(np.log2(s.value))
-    for bound in [0.0, float("nan"), float("inf"), 1e-45, 1e-30]:  # clamped, still an exact power of two
-        s, i = ctypes.c_float(), ctypes.c_float()
-        emu.emu_fix_scale(ctypes.c_float(bound), ctypes.byref(s), ctypes.byref(i))
-        assert np.isfinite(s.value) and s.value > 0 and s.value * i.value == 1.0
-        assert not bound * s.value >= 2.0 ** 29 or not np.isfinite(bound)
-
-
-def _tiled_case(emu, F_, H, W, seed=0, sigma=0.01, outliers=0.0, wscale=1.0, shift=(0.0, 0.0),
-                depth_scale=1.0, grt_scale=1.0, tall=False):
-    rng = np.random.default_rng(seed)
-    _, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
-    depth = (depth_scale * (1.0 + 0.5 * rng.random((F_, H, W)) + 0.3 * np.sin(xx / 17.0)[None])).astype(np.float32)
-    fb = (sigma * rng.standard_normal((F_ - 1, H, W, 2))).astype(np.float32)
-    fb[..., 0] += shift[0]
-    fb[..., 1] += shift[1]
-    if outliers > 0:
-        m = rng.random((F_ - 1, H, W)) < outliers
-        fb[m] = (0.5 * rng.standard_normal((int(m.sum()), 2))).astype(np.float32)
-    w = (wscale * rng.random((F_ - 1, H, W))).astype(np.float32)
-    s = (H * W) ** 0.5
-    k4 = np.tile(np.array([0.85 * s / W, 0.85 * s / H, 0.5, 0.5], dtype=np.float32), (F_, 1))
-    BP = F_ - 1
-    rt = np.zeros((BP, 12), dtype=np.float32)
-    state = np.zeros(BP * emu.emu_state_bytes(), dtype=np.uint8)
-    emu.emu_procrustes_fwd(_p(depth), _p(k4), _p(fb), _p(w), None, 0, _p(rt), _p(state), 1, F_, H, W)
-    g_rt = (grt_scale * rng.standard_normal((BP, 12))).astype(np.float64)
-    res = []
-    for tiled in (False, True):
-        gd, gw, k4acc = np.zeros_like(depth), np.zeros_like(w), np.zeros((F_, 4))
-        stats = np.zeros(8, dtype=np.int64)
-        if tiled:
-            (emu.emu_procrustes_bwd_tiled64 if tall else emu.emu_procrustes_bwd_tiled)(_p(depth), _p(k4), _p(fb), _p(w), _p(state), _p(g_rt), _p(gd), _p(gw),
-                                         _p(k4acc), _p(stats), 1, F_, H, W)
-        else:
-            emu.emu_procrustes_bwd(_p(depth), _p(k4), _p(fb), _p(w), None, 0, _p(state), _p(g_rt), _p(gd),
-                                   _p(gw), _p(k4acc), 1, F_, H, W)
-        res.append((gd, gw, k4acc, stats))
-    return res
-
-
-TILED_CASES = [
-    dict(F_=3, H=72, W=96),                                  # iid +-6 px jitter (the bench's flows)
-    dict(F_=3, H=40, W=64),                                  # partial last tile row
-    dict(F_=3, H=24, W=32),                                  # image smaller than the window
-    dict(F_=3, H=100, W=64),                                 # second half of the last 64-row tile partly outside
-    dict(F_=2, H=136, W=96, shift=(0.0, 0.08)),              # vertical motion across several tile rows
-    dict(F_=3, H=72, W=96, outliers=0.05),                   # far taps: float fallback
-    dict(F_=3, H=72, W=96, wscale=5.0),                      # raw weights above 1
-    dict(F_=3, H=72, W=96, shift=(0.3, -0.2)),               # large coherent motion: shifted window
-    dict(F_=3, H=72, W=96, shift=(2.0, 0.0)),                # everything leaves the frame: border pile-up
-    dict(F_=3, H=72, W=96, depth_scale=1e3),
-    dict(F_=3, H=72, W=96, depth_scale=1e-3, grt_scale=1e-6),
-    dict(F_=3, H=72, W=96, grt_scale=1e8),
-]
-
-
-@pytest.mark.parametrize("tall", [False, True], ids=["tile32x32", "tile32x64"])
-@pytest.mark.parametrize("case", TILED_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
-def test_tiled_scatter_matches_direct_scatter(emu, case, tall):
-    """Serial twin of k_distribute_tiled / k_distribute_tiled64 vs the direct float scatter of
-    k_distribute on the same inputs: identical aligned / weight / intrinsics parts, depth gradient
-    equal up to the float32 rounding of the direct path's own cell sums."""
-    (gd0, gw0, k0, _), (gd1, gw1, k1, st) = _tiled_case(emu, tall=tall, **case)
-    assert np.array_equal(gw0, gw1)
-    assert np.abs(k0 - k1).max() <= 1e-12 * max(1.0, np.abs(k0).max())
-    assert rel_l2(gd1, gd0) <= 5e-7
-    assert st[5] == 0                       # no touched cell outside the image
-    assert st[2] == 0 or case.get("wscale", 1.0) > 1.0   # the bound holds: no range fallback
-    taps = st[0] + st[1] + st[2]
-    assert taps == 2 * (case["F_"] - 1) * case["H"] * case["W"]
-    if not case.get("outliers"):
-        assert st[1] <= 0.01 * taps          # windows follow the flow
-    assert st[3] <= 0.01 * taps              # high-word adds are rare
-    if case.get("wscale", 1.0) <= 1.0:
-        # the bound of scatter_bound_consts holds (scaled values stay below 2^29) and is not
-        # wastefully loose (the largest one uses at least 1/2000 of the range: >= 18 bits left)
-        assert 500 <= st[6] <= 1_000_000
