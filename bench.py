@@ -321,6 +321,148 @@ def cpu_baseline(sample_frames, steps, warmup, full=True):
             **parts}
 
 
+# ------------------------------------------------------------------------------ ncu evidence
+NCU_SUMMARY = ROOT / "profiles" / "r2_path_ncu_summary.txt"  # tools/ncu_summary.py output, committed
+
+
+def ncu_traffic_from_profiles(path=NCU_SUMMARY):
+    """{op: dram bytes per launch} for the three pixel kernels from the committed ncu summary."""
+    names = {"k_moments": "procrustes_fwd(k_moments)", "k_flow_lean": "flow_loss_fwd_bwd(k_flow_lean)",
+             "k_distribute": "procrustes_bwd(k_distribute)"}
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    out, cur = {}, None
+    if not Path(path).exists():
+        return {}, None
+    for line in Path(path).read_text().splitlines():
+        if line.startswith("====="):
+            cur = next((v for k, v in names.items() if f"::{k}<" in line or f"::{k}(" in line), None)
+        elif cur and ("dram__bytes_read.sum " in line or "dram__bytes_write.sum " in line):
+            parts = line.split()
+            out[cur] = out.get(cur, 0.0) + float(parts[1]) * unit.get(parts[2], 1.0)
+    return out, str(Path(path).relative_to(ROOT))
+
+
+# ------------------------------------------------------------------------------ pair sharding
+def device_shard_inputs(f, h, w, pair_lo, pair_hi, dev):
+    """The frames [pair_lo, pair_hi] / pairs [pair_lo, pair_hi) of one synthetic video, generated on
+    the device with per-frame / per-pair seeds: every rank builds exactly its shard of the SAME
+    video whatever the world size (same distributions as synthetic_inputs)."""
+    def gen(seed):
+        return torch.Generator(device=dev).manual_seed(seed)
+    nf = pair_hi - pair_lo + 1
+    depth = torch.empty(nf, h, w, device=dev)
+    for i in range(nf):
+        depth[i] = 0.1 + 0.05 * torch.rand(h, w, device=dev, generator=gen(10_000 + pair_lo + i))
+    npair = pair_hi - pair_lo
+    wparam = torch.empty(npair, h, w, device=dev)
+    fwd, bwd = torch.empty(1, npair, h, w, 2, device=dev), torch.empty(1, npair, h, w, 2, device=dev)
+    fm, bm = torch.empty(1, npair, h, w, device=dev), torch.empty(1, npair, h, w, device=dev)
+    for i in range(npair):
+        g = gen(20_000 + pair_lo + i)
+        wparam[i] = 0.01 * torch.randn(h, w, device=dev, generator=g)
+        fwd[0, i] = 0.01 * torch.randn(h, w, 2, device=dev, generator=g)
+        bwd[0, i] = 0.01 * torch.randn(h, w, 2, device=dev, generator=g)
+        fm[0, i] = torch.rand(h, w, device=dev, generator=g)
+        bm[0, i] = torch.rand(h, w, device=dev, generator=g)
+    return depth, wparam, (fwd, bwd, fm, bm)
+
+
+def sharded_record(f, h, w, full, rank, world, dev, steps, barrier, max_over_ranks):
+    """Strong scaling of ONE f x h x w video over the ranks of this run: ms/step with its pairs
+    split over `world` ranks, the same video on one rank (rank 0) alongside, bytes sent per rank per
+    step and the device time inside the exchange (CUDA events around StepReducer.reduce /
+    _tracking_exchange on the step's stream; includes waiting for the slowest neighbour)."""
+    from flowmap_b200 import parallel
+    from flowmap_b200.overfit import OverfitCfg, ShardedFusedOverfitter
+    from flowmap_b200.types import Batch, Flows, Tracks
+
+    def build(plan, group=None):
+        a, b = plan.pair_range
+        depth, wparam, fl = device_shard_inputs(f, h, w, a, b, dev)
+        nf = b - a + 1
+        batch = Batch(torch.zeros(1, 1, 1, 1, 1, device=dev).expand(1, nf, 3, h, w),
+                      torch.arange(nf, device=dev)[None], ["synthetic"], ["synthetic"])
+        cfg = OverfitCfg(intrinsics="softmin", use_tracking=True) if full else OverfitCfg()
+        tracks = [Tracks(xy, vis, s) for xy, vis, s in synthetic_track_arrays(f, seed=0)] if full else None
+        o = ShardedFusedOverfitter(cfg, batch, Flows(*fl), plan, tracks=tracks, device=dev, group=group)
+        with torch.no_grad():
+            o.model.backbone.depth.copy_(depth)
+            o.model.backbone.weights.copy_(wparam)
+        o.global_step = START_STEP
+        return o
+
+    def timed(o, n):
+        for _ in range(3):
+            o.training_step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            o.training_step()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / n
+
+    plan = parallel.make_plan(f - 1, rank, world)
+    o = build(plan)
+    ms_n = max_over_ranks(timed(o, steps))
+    # time inside the exchange: events around the collectives of a few extra steps
+    spans = []
+    real_reduce, real_track = o.reducer.reduce, getattr(o, "_tracking_exchange", None)
+
+    def wrap(fn):
+        def inner(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            spans.append((e0, e1))
+            return out
+        return inner
+    o.reducer.reduce = wrap(real_reduce)
+    if full:
+        o._tracking_exchange = wrap(real_track)
+    n_probe = 5
+    barrier()
+    for _ in range(n_probe):
+        o.training_step()
+    torch.cuda.synchronize()
+    comm_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in spans) / n_probe)
+    sent = o.reducer.bytes_per_step()
+    del o
+    torch.cuda.empty_cache()
+    ms_1 = None
+    if world == 1:
+        ms_1 = ms_n
+    else:  # the same video unsharded, on rank 0 alone (the others wait at the barrier)
+        g0 = torch.distributed.new_group([0])  # collective: every rank creates the one-rank group
+        if rank == 0:
+            solo = build(parallel.ShardPlan(0, 1, (0, f - 1), f - 1), group=g0)
+            for _ in range(3):
+                solo.training_step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                solo.training_step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_1 = e0.elapsed_time(e1) / steps
+            del solo
+        t = torch.tensor([ms_1 if ms_1 is not None else 0.0], device=dev, dtype=torch.float64)
+        torch.distributed.broadcast(t, src=0)
+        ms_1 = float(t)
+    return {"frames": f, "height": h, "width": w, "pairs": f - 1, "n_gpus": world,
+            "what": ("full loop (softmin sweep on rank 0, tracking sharded by source frame)" if full
+                     else "flow loss only, regressed focal (BASELINE configs[3])"),
+            "ms_per_step": round(ms_n, 4), "ms_per_step_one_gpu": round(ms_1, 4),
+            "speedup": round(ms_1 / ms_n, 3), "strong_scaling_efficiency": round(ms_1 / ms_n / world, 4),
+            "it_per_s": round(1000.0 / ms_n, 2), "bytes_sent_per_rank_per_step": int(sent),
+            "ms_in_exchange_per_step": round(comm_ms, 4),
+            "exchange": "one 2-float all-reduce + one boundary depth-gradient frame swapped with each neighbour"
+                        + (" + pose gather, tracking-sum all-reduce (F x 10 doubles), focal broadcast" if full else "")}
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     from flowmap_b200 import ops, parallel
@@ -396,6 +538,24 @@ def run_gpu(args):
         barrier()
         clocks.window(t0, time.time())
         return max_over_ranks(e0.elapsed_time(e1) / steps), out
+
+    # ---- parity gate: the first step of THIS workload (seed 0) against the value the unmodified
+    # reference produced for it (tests/golden/big_c3.npz, generated by tests/golden/make_golden_big.py
+    # with the same softmin point indices); a fast step that computes something else is worthless
+    loss_check = None
+    fixture = ROOT / "tests" / "golden" / "big_c3.npz"
+    if not pairs_mode and rank == 0 and fixture.exists():
+        import numpy as np
+        with np.load(fixture) as z:
+            ref_loss, ref_idx = float(z["loss"][0]), torch.as_tensor(z["softmin_indices"])
+        o.injected_indices = ref_idx.to(dev)
+        got = float(o.training_step(update=False)[0])
+        o.injected_indices = None
+        rel_err = abs(got - ref_loss) / abs(ref_loss)
+        loss_check = {"step0_loss": got, "reference_step0_loss": ref_loss, "rel_err": rel_err, "tolerance": 1e-4,
+                      "source": "tests/golden/big_c3.npz (unmodified reference, float32, CPU)"}
+        if not rel_err <= 1e-4:
+            raise SystemExit(f"bench.py: step-0 loss {got} differs from the reference's {ref_loss} (rel {rel_err:.2e})")
 
     # ---- device-resident timing (value)
     clocks = ClockSampler(local)
@@ -489,6 +649,23 @@ def run_gpu(args):
         flows_dev.forward.copy_(flows_host.forward, non_blocking=True)   # o.flows shares these buffers
         flows_dev.backward.copy_(flows_host.backward, non_blocking=True)
 
+    # ---- pair-sharded strong scaling, measured in the same run (BASELINE configs[3]):
+    # ONE video, its frame pairs split over the N ranks; per step one 2-float all-reduce and one
+    # boundary depth-gradient frame swapped with each neighbour (NCCL over NVLink).
+    pair_sharded = None
+    if not pairs_mode and os.environ.get("FM_BENCH_SKIP_SHARDED") != "1":
+        pair_sharded = {}
+        for name, (pf, ph, pw, full) in {"config4_flow_only": (150, 720, 1280, False),
+                                         "config3_full_loop": (F_, H_, W_, True)}.items():
+            if name == "config3_full_loop" and world == 1:
+                continue  # at N = 1 this is the headline `value` itself
+            try:
+                pair_sharded[name] = sharded_record(pf, ph, pw, full, rank, world, dev, max(5, min(args.steps, 30)),
+                                                    barrier, max_over_ranks)
+            except Exception as exc:  # noqa: BLE001 -- keep the bench line
+                pair_sharded[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             torch.distributed.barrier()  # rank 0 still runs its per-op timing / CPU baseline
@@ -559,14 +736,14 @@ def run_gpu(args):
     path_ms = t_fwd + t_flow + t_bwd
     path_gbs = algorithmic_bytes(F_, H_, W_) / (path_ms * 1e-3) / 1e9
     dom_gbs = ops_bytes[dom] / (times[dom] * 1e-3) / 1e9
-    # DRAM bytes per launch from the committed ncu --set full capture of these kernels at this
-    # shape (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1_v12_ncu_summary.txt)
-    ncu_traffic = {"procrustes_fwd(k_moments)": 557.4e6, "flow_loss_fwd_bwd(k_flow_lean)": 1118.0e6,
-                   "procrustes_bwd(k_distribute)": 943.9e6}
+    # DRAM bytes per launch: parsed from the committed `ncu --set full` summary of these kernels at
+    # this shape (dram__bytes_read.sum + dram__bytes_write.sum); None if the file is missing
+    ncu_traffic, traffic_file = ncu_traffic_from_profiles()
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(dom_gbs, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(dom_gbs / peak, 4), "traffic": ncu_traffic[dom],
+                "unit": "GB/s", "frac": round(dom_gbs / peak, 4), "traffic": ncu_traffic.get(dom),
                 "algorithmic_bytes": ops_bytes[dom],
-                "traffic_source": "ncu --set full capture of this kernel at this shape (profiles/)",
+                "traffic_source": f"ncu --set full capture of this kernel at this shape ({traffic_file})",
+                "path_traffic": (sum(ncu_traffic.values()) if len(ncu_traffic) == 3 else None),
                 "peak_source": peak_src,
                 "path": {"what": "unproject->Procrustes->reproject->loss+grad (3 ops, summed)",
                          "algorithmic_bytes": algorithmic_bytes(F_, H_, W_),
@@ -636,7 +813,7 @@ def run_gpu(args):
                 "what": "Flows (flow fwd/bwd + masks) copied from pinned host memory every step "
                         "(double-buffered: step k+1 uploads while step k computes), loss read back "
                         "every step"},
-        "gpu_launches": int(launches), "final_loss": final_loss,
+        "gpu_launches": int(launches), "final_loss": final_loss, "loss_check": loss_check,
         "flow_only": None if flow_only_ms is None else
         {"ms_per_step": round(flow_only_ms, 4), "it_per_s": round(world * 1000.0 / flow_only_ms, 2),
          "what": "same step without tracking loss / softmin sweep (regressed focal)",
@@ -647,6 +824,7 @@ def run_gpu(args):
         {"ms_per_step": round(dropin_ms, 4), "it_per_s": round(world * 1000.0 / dropin_ms, 2),
          "what": "same full workload through Model.forward + LossFlow/LossTracking autograd Functions + "
                  "kernel Adam (the install() drop-in surface) instead of the one-call fused step"},
+        "pair_sharded": pair_sharded,
         "reference_cuda_eager": ref_cuda,
         "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
     }

@@ -11,8 +11,13 @@ def install() -> dict:
 
       * ``flowmap.model.model.Model``      -> flowmap_b200.model.Model (same cfg / forward)
       * ``flowmap.loss.LOSSES["flow"|"tracking"]`` -> flowmap_b200.loss.LossFlow / LossTracking
-      * ``flowmap.model.intrinsics.INTRINSICS`` / ``...extrinsics.EXTRINSICS["procrustes"]``
-        entries of the pieces that exist here,
+      * ``flowmap.model.intrinsics.INTRINSICS`` / ``flowmap.model.extrinsics.EXTRINSICS`` entries
+        (``regressed`` / ``softmin`` / ``ground_truth``; ``procrustes`` / ``regressed``),
+      * ``flowmap.model.projection.{sample_image_grid, unproject, project, reproject_points,
+        compute_forward_flow, compute_backward_flow, get_extrinsics, align_surfaces}`` and
+        ``flowmap.model.procrustes.align_rigid`` (module attributes; also re-bound in the reference
+        modules that imported them by name: model.model, intrinsics.intrinsics_softmin, export.colmap,
+        visualization.visualizer_summary when importable),
       * ``flowmap.flow.flow_predictor.FlowPredictor.rescale_flow / rescale_mask /
         compute_consistency_mask`` (static methods; the RAFT / GMFlow subclasses inherit them,
         so ``compute_bidirectional_flow`` runs on the kernels with the reference's predictor),
@@ -39,6 +44,30 @@ def install() -> dict:
     for key, cls in my_model.INTRINSICS.items():
         replaced[f"flowmap.model.intrinsics.INTRINSICS[{key}]"] = ref_intr.INTRINSICS.get(key)
         ref_intr.INTRINSICS[key] = cls
+    ref_extr = importlib.import_module("flowmap.model.extrinsics")
+    for key, cls in my_model.EXTRINSICS.items():
+        replaced[f"flowmap.model.extrinsics.EXTRINSICS[{key}]"] = ref_extr.EXTRINSICS.get(key)
+        ref_extr.EXTRINSICS[key] = cls
+    from . import procrustes as my_procrustes
+    from . import projection as my_projection
+    ref_proj = importlib.import_module("flowmap.model.projection")
+    proj_names = ("sample_image_grid", "unproject", "project", "reproject_points", "compute_forward_flow",
+                  "compute_backward_flow", "get_extrinsics", "align_surfaces")
+    users = [ref_proj]
+    for mod in ("flowmap.model.model", "flowmap.model.intrinsics.intrinsics_softmin", "flowmap.export.colmap",
+                "flowmap.visualization.visualizer_summary", "flowmap.model.extrinsics.extrinsics_regressed"):
+        try:
+            users.append(importlib.import_module(mod))
+        except ImportError:
+            pass
+    for name in proj_names:
+        replaced[f"flowmap.model.projection.{name}"] = getattr(ref_proj, name)
+        for mod in users:  # `from ..projection import name` made a copy of the binding there
+            if mod is ref_proj or hasattr(mod, name):
+                setattr(mod, name, getattr(my_projection, name))
+    ref_procrustes = importlib.import_module("flowmap.model.procrustes")
+    replaced["flowmap.model.procrustes.align_rigid"] = ref_procrustes.align_rigid
+    ref_procrustes.align_rigid = my_procrustes.align_rigid
     from . import export as my_export
     from . import flow as my_flow
     try:

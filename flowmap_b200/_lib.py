@@ -99,7 +99,8 @@ class OverfitStepArgs(ctypes.Structure):
                 ("extrinsics", _P), ("g_extrinsics", _P), ("g_rt", _P), ("track_g_k4", _P),
                 ("track_loss", _P),
                 ("ws", _P), ("track_ws", _P), ("focal_step", c_int), ("defer_adam", c_int),
-                ("phase", c_int), ("splat_plan", _P), ("splat_overflow_max", ctypes.c_uint)]
+                ("phase", c_int), ("splat_plan", _P), ("splat_overflow_max", ctypes.c_uint),
+                ("flow_grad_scale", _P), ("track_grad_scale", _P)]
 
 
 SIGNATURES["fm_overfit_step"] = (c_int, [ctypes.POINTER(OverfitStepArgs), _P])

@@ -1755,13 +1755,14 @@ __global__ void k_k4_from_focal(const float* __restrict__ focal, float* __restri
 // d loss / d focal from the per-frame k4 gradients (flow-loss part + Procrustes part).
 __global__ void k_focal_grad(const double* __restrict__ k4acc, const double* __restrict__ flowacc,
                              const float* __restrict__ extra_g_k4, float* __restrict__ g_focal, int B,
-                             int F, int H, int W) {
+                             int F, int H, int W, const float* __restrict__ flow_scale = nullptr) {
   double sx = 0.0, sy = 0.0;
+  const double fs = flow_scale ? (double)*flow_scale : 1.0;  // d total / d flow loss (the Procrustes part in k4acc carries it already)
   for (int t = threadIdx.x; t < B * F; t += blockDim.x) {
     double g[4];
     flow_k4_grad(flowacc, t, F, g);
-    sx += g[0] + k4acc[(size_t)t * 4 + 0] + (extra_g_k4 ? (double)extra_g_k4[t * 4 + 0] : 0.0);
-    sy += g[1] + k4acc[(size_t)t * 4 + 1] + (extra_g_k4 ? (double)extra_g_k4[t * 4 + 1] : 0.0);
+    sx += fs * g[0] + k4acc[(size_t)t * 4 + 0] + (extra_g_k4 ? (double)extra_g_k4[t * 4 + 0] : 0.0);
+    sy += fs * g[1] + k4acc[(size_t)t * 4 + 1] + (extra_g_k4 ? (double)extra_g_k4[t * 4 + 1] : 0.0);
   }
   __shared__ double sm[2][32];
   sx = warp_sum(sx); sy = warp_sum(sy);
@@ -2033,7 +2034,7 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
                                const float* flow_scale, float* g_depth, float* g_weights, float* g_k4,
                                void* ws, int B, int F, int H, int W, void* stream,
                                const PairLayout* layout = nullptr, const AdamFuse* adam = nullptr,
-                               void* plan = nullptr, unsigned plan_ovf_max = 0u) {
+                               void* plan = nullptr, unsigned plan_ovf_max = 0u, bool depth_prescaled = false) {
   const PairLayout lay = layout ? *layout : dense_layout(F, H, W);
   if (plan && (B != 1 || indices || layout || !tiled_shape_ok(F, H, W)))
     return fail_msg("fm_procrustes_bwd: the splat plan serves the dense single-video path with W % 4 == 0");
@@ -2048,7 +2049,7 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
   AdamFuse af;
   if (adam) af = *adam; else memset(&af, 0, sizeof(af));
   float* weights_rw = const_cast<float*>(weights);
-  if (include_flow_loss && flow_scale) {
+  if (include_flow_loss && flow_scale && !depth_prescaled) {
     // the direct depth gradient already sitting in g_depth was computed for scale 1
     k_scale_inplace<<<148 * 4, kThreads, 0, s>>>(g_depth, flow_scale, (size_t)BF * H * W);
     FM_CHECK_LAUNCH("fm_procrustes_bwd: k_scale_inplace");
@@ -2555,8 +2556,6 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
   int rc;
   cudaError_t e;
   if (a->phase < FM_STEP_ALL || a->phase > FM_STEP_BACKWARD) return fail_msg("fm_overfit_step: unknown phase");
-  if (a->phase != FM_STEP_ALL && a->tracks)
-    return fail_msg("fm_overfit_step: a split step takes the tracking gradient through g_rt / track_g_k4");
   // the splat plan of this video's backward flows serves the dense path (all-pixel Procrustes)
   void* plan = (a->splat_plan && !a->indices && tiled_shape_ok(F, H, W)) ? a->splat_plan : nullptr;
   // intrinsics from the focal parameter (regressed stage) or as given
@@ -2579,12 +2578,10 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
       return rc;
     k_flow_finalize<<<(F + 127) / 128, 128, 0, s>>>(w.flowacc, a->rt, a->loss, nullptr, nullptr, 1, F);
     FM_CHECK_LAUNCH("fm_overfit_step: k_flow_finalize");
-    if (a->phase == FM_STEP_FORWARD) return 0;
   }
-  // LossTracking (loss_tracking.py:28-61) on the chained poses, gradients into g_depth / g_rt
-  const float* g_rt = a->phase == FM_STEP_BACKWARD ? a->g_rt : nullptr;           // the caller's
-  const float* track_g_k4 = a->phase == FM_STEP_BACKWARD ? a->track_g_k4 : nullptr;  // tracking part
-  if (a->tracks) {
+  // LossTracking (loss_tracking.py:28-61) on the chained poses: the forward sweep belongs to the
+  // forward half of a split step, its scaling / scatter to the backward half
+  if (a->tracks && a->phase != FM_STEP_BACKWARD) {
     const fm_packed_tracks* t = a->tracks;
     if ((rc = fm_pose_chain(a->rt, a->extrinsics, 1, F, stream))) return rc;
     // one focal length (or constant intrinsics) for all frames: only the summed K gradient is used
@@ -2593,9 +2590,23 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
                                         a->track_weight, a->track_loss, a->track_ws, F, H, W, 0, 0, F, 1,
                                         stream)))
       return rc;
+  }
+  if (a->phase == FM_STEP_FORWARD) return 0;
+  // d total / d (flow loss) and d total / d (tracking loss) of a split step (device scalars, NULL = 1)
+  const float* fscale = a->phase == FM_STEP_BACKWARD ? a->flow_grad_scale : nullptr;
+  const float* tscale = a->phase == FM_STEP_BACKWARD ? a->track_grad_scale : nullptr;
+  if (fscale) {  // the direct flow-loss gradient in g_depth was computed for scale 1; scale it before
+    // the tracking loss adds its own (differently scaled) part
+    k_scale_inplace<<<148 * 4, kThreads, 0, s>>>(a->g_depth, fscale, (size_t)F * N);
+    FM_CHECK_LAUNCH("fm_overfit_step: k_scale_inplace");
+  }
+  const float* g_rt = a->phase == FM_STEP_BACKWARD ? a->g_rt : nullptr;           // the caller's
+  const float* track_g_k4 = a->phase == FM_STEP_BACKWARD ? a->track_g_k4 : nullptr;  // tracking part
+  if (a->tracks) {
+    const fm_packed_tracks* t = a->tracks;
     if ((rc = fm_track_loss_bwd(a->depth, k4, a->extrinsics, t->segments, t->num_segments, t->max_rows,
                                 t->max_points, t->xy, t->vis, t->total_samples, a->mapping, a->delta,
-                                a->track_weight, nullptr, a->g_depth, a->g_extrinsics, a->track_g_k4,
+                                a->track_weight, tscale, a->g_depth, a->g_extrinsics, a->track_g_k4,
                                 a->track_ws, F, H, W, stream)))
       return rc;
     if ((rc = fm_pose_chain_bwd(a->rt, a->extrinsics, a->g_extrinsics, a->g_rt, 1, F, stream))) return rc;
@@ -2620,9 +2631,9 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
     af.bc2_sqrt = (float)sqrt(1.0 - pow(a->beta2, (double)a->step));
   }
   if ((rc = procrustes_bwd_impl(a->depth, k4, a->bflow, a->weight_logits, a->weight_sensitivity,
-                                a->indices, a->num_indices, g_rt, 1, nullptr, a->g_depth, a->g_weights,
+                                a->indices, a->num_indices, g_rt, 1, fscale, a->g_depth, a->g_weights,
                                 a->g_k4, a->ws, 1, F, H, W, stream, nullptr, fuse_w ? &af : nullptr, plan,
-                                a->splat_overflow_max)))
+                                a->splat_overflow_max, /*depth_prescaled=*/fscale != nullptr)))
     return rc;
   // Adam (model_wrapper_overfit.py:104-105)
   if (a->step > 0 && !defer) {
@@ -2634,14 +2645,14 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
                            a->lr, a->beta1, a->beta2, a->eps, a->step, stream)))
       return rc;
     if (a->focal) {
-      k_focal_grad<<<1, 256, 0, s>>>(w.k4acc, w.flowacc, track_g_k4, a->g_focal, 1, F, H, W);
+      k_focal_grad<<<1, 256, 0, s>>>(w.k4acc, w.flowacc, track_g_k4, a->g_focal, 1, F, H, W, fscale);
       FM_CHECK_LAUNCH("fm_overfit_step: k_focal_grad");
       if ((rc = fm_adam_step(a->focal, a->g_focal, a->m_focal, a->v_focal, 1, a->lr, a->beta1, a->beta2,
                              a->eps, a->focal_step > 0 ? a->focal_step : a->step, stream)))
         return rc;
     }
   } else if (a->focal) {
-    k_focal_grad<<<1, 256, 0, s>>>(w.k4acc, w.flowacc, track_g_k4, a->g_focal, 1, F, H, W);
+    k_focal_grad<<<1, 256, 0, s>>>(w.k4acc, w.flowacc, track_g_k4, a->g_focal, 1, F, H, W, fscale);
     FM_CHECK_LAUNCH("fm_overfit_step: k_focal_grad");
   }
   if (defer && a->step > 0 && a->weight_logits && !fuse_w) return fail_msg("fm_overfit_step: defer_adam needs the fused weight update");

@@ -56,8 +56,16 @@ def compute_consistency_mask(videos: Tensor, flow: Tensor, reverse: bool = False
         raise ValueError("flowmap_b200: consistency mask shape mismatch")
     mask = torch.empty((b, f - 1, h, w), dtype=torch.float32, device=videos.device)
     with torch.cuda.device(videos.device):
-        check(lib().fm_consistency_mask(_ptr(videos), _ptr(flow), _ptr(mask), b, f, h, w, int(reverse),
-                                        _stream()), "fm_consistency_mask")
+        if b * (f - 1) <= 65535:  # the y grid dimension carries the (batch, pair) items
+            check(lib().fm_consistency_mask(_ptr(videos), _ptr(flow), _ptr(mask), b, f, h, w, int(reverse),
+                                            _stream()), "fm_consistency_mask")
+        else:  # very long / heavily batched videos: one batch element (and <= 65535 pairs) per launch
+            for bi in range(b):
+                for lo in range(0, f - 1, 65535):
+                    hi = min(f - 1, lo + 65535)
+                    check(lib().fm_consistency_mask(_ptr(videos[bi, lo:hi + 1]), _ptr(flow[bi, lo:hi]),
+                                                    _ptr(mask[bi, lo:hi]), 1, hi - lo + 1, h, w, int(reverse),
+                                                    _stream()), "fm_consistency_mask")
     return mask
 
 

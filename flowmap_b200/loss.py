@@ -100,6 +100,11 @@ class LossFlow(Loss):
 
     def compute_weighted_loss(self, batch, flows, tracks, model_output, global_step):
         out = model_output
+        fused = out.__dict__.get("_fused")  # flowmap_b200.fused.LazyModelOutput
+        if fused is not None:
+            value = fused.flow_loss(self, tracks)
+            if value is not None:
+                return value
         k4 = getattr(out, "k4", None)
         if k4 is None:
             k4 = ops.intrinsics_to_k4(out.intrinsics)
@@ -132,6 +137,11 @@ class LossTracking(Loss):
     def compute_weighted_loss(self, batch, flows, tracks, model_output, global_step):
         assert tracks is not None  # loss_tracking.py:37
         out = model_output
+        fused = out.__dict__.get("_fused")
+        if fused is not None:
+            value = fused.track_loss(self, tracks)
+            if value is not None:
+                return value
         k4 = getattr(out, "k4", None)
         if k4 is None:
             k4 = ops.intrinsics_to_k4(out.intrinsics)

@@ -203,12 +203,46 @@ class ExtrinsicsProcrustes(nn.Module):
         return ops.pose_chain(rt), rt
 
 
-EXTRINSICS = {"procrustes": ExtrinsicsProcrustes}
+@dataclass
+class ExtrinsicsRegressedCfg:
+    name: Literal["regressed"]
+
+
+class ExtrinsicsRegressed(nn.Module):
+    """flowmap/model/extrinsics/extrinsics_regressed.py:47-83, the free-pose ablation (no Procrustes:
+    nothing for the moment kernels to do).  Per-pair translations and quaternions (parameter names
+    and the scipy (i, j, k, r) order kept so that reference checkpoints load); plain ATen arithmetic
+    for the 3 x 3 matrices, the chain on the scan kernel.  The flow / tracking kernels take its
+    relative poses like the Procrustes ones."""
+
+    def __init__(self, cfg, num_frames):
+        super().__init__()
+        assert num_frames >= 2
+        self.cfg, self.num_frames = cfg, num_frames
+        self.translations = nn.Parameter(torch.zeros((num_frames - 1, 3), dtype=torch.float32))
+        rotations = torch.zeros((num_frames - 1, 4), dtype=torch.float32)
+        rotations[:, -1] = 1
+        self.rotations = nn.Parameter(rotations)
+
+    @staticmethod
+    def quaternion_to_matrix(q: Tensor, eps: float = 1e-8) -> Tensor:
+        i, j, k, r = q.unbind(-1)
+        s = 2 / ((q * q).sum(-1) + eps)
+        rows = (1 - s * (j * j + k * k), s * (i * j - k * r), s * (i * k + j * r),
+                s * (i * j + k * r), 1 - s * (i * i + k * k), s * (j * k - i * r),
+                s * (i * k - j * r), s * (j * k + i * r), 1 - s * (i * i + j * j))
+        return torch.stack(rows, -1).reshape(*q.shape[:-1], 3, 3)
+
+    def forward(self, batch, flows, backbone_output, k4=None, indices=None):
+        assert backbone_output.depths.shape[0] == 1  # extrinsics_regressed.py:75-76
+        rt = torch.cat((self.quaternion_to_matrix(self.rotations), self.translations[..., None]), dim=-1)[None]
+        return ops.pose_chain(rt.contiguous()), rt
+
+
+EXTRINSICS = {"procrustes": ExtrinsicsProcrustes, "regressed": ExtrinsicsRegressed}
 
 
 def get_extrinsics(cfg, num_frames):
-    if cfg.name not in EXTRINSICS:
-        raise NotImplementedError(f"extrinsics '{cfg.name}' is an ablation outside the hot path")
     return EXTRINSICS[cfg.name](cfg, num_frames)
 
 
@@ -231,7 +265,70 @@ class Model(nn.Module):
         self.intrinsics = get_intrinsics(cfg.intrinsics)
         self.extrinsics = get_extrinsics(cfg.extrinsics, num_frames)
 
+    # ---- fused evaluation (flowmap_b200.fused): Model.forward launches nothing, the losses run the
+    # two halves of the fused step
+    fused_enabled = True  # class-wide switch (tests compare the two evaluation orders)
+
+    def _fusable(self, batch: Batch, flows: Flows) -> bool:
+        return (self.fused_enabled and torch.is_grad_enabled() and self.training and
+                isinstance(self.backbone, BackboneExplicitDepth) and
+                isinstance(self.extrinsics, ExtrinsicsProcrustes) and
+                isinstance(self.intrinsics, (IntrinsicsRegressed, IntrinsicsSoftmin)) and
+                batch.videos.shape[0] == 1 and self.backbone.depth.is_cuda and flows.forward.is_cuda)
+
+    def _fused_params(self, global_step: int):
+        """Parameters that receive a gradient from the fused step, in the order of FusedStep's buffers."""
+        params = [self.backbone.depth]
+        if self.cfg.use_correspondence_weights:
+            params.append(self.backbone.weights)
+        intr = self.intrinsics
+        if isinstance(intr, IntrinsicsRegressed):
+            params.append(intr.focal_length)
+        elif intr.cfg.regression is not None and global_step >= intr.cfg.regression.after_step:
+            params.append(intr.intrinsics_regressed.focal_length)
+        return params
+
+    def _fused_engine(self, batch: Batch, flows: Flows, tracks, flow_loss):
+        """The FusedOverfitter bound to this model's parameters for (flows, tracks); built on first
+        use, re-pointed when the Flows tensors change, None if the configuration is not covered."""
+        from .overfit import FusedOverfitter, OverfitCfg
+        mc, bc, ic, ec = self.cfg, self.cfg.backbone, self.cfg.intrinsics, self.cfg.extrinsics
+        lm = flow_loss.cfg.mapping
+        key = (tuple(batch.videos.shape), None if tracks is None else tuple(id(t) for t in tracks),
+               lm.name, getattr(lm, "delta", 0.01))
+        eng = getattr(self, "_engine", None)
+        if eng is None or self._engine_key != key:
+            soft = isinstance(self.intrinsics, IntrinsicsSoftmin)
+            reg = ic.regression if soft else None
+            cfg = OverfitCfg(
+                initial_depth=bc.initial_depth, weight_sensitivity=bc.weight_sensitivity,
+                use_correspondence_weights=mc.use_correspondence_weights, procrustes_points=ec.num_points,
+                procrustes_randomize=ec.randomize_points, intrinsics="softmin" if soft else "regressed",
+                softmin_points=ic.num_procrustes_points if soft else 8192,
+                softmin_min=ic.min_focal_length if soft else 0.5, softmin_max=ic.max_focal_length if soft else 2.0,
+                softmin_candidates=ic.num_candidates if soft else 60,
+                regression_after=reg.after_step if reg is not None else None,
+                regression_window=reg.window if reg is not None else 100,
+                flow_weight=flow_loss.cfg.weight, flow_enable_after=flow_loss.cfg.enable_after,
+                use_tracking=tracks is not None, tracking_enable_after=0, mapping=lm.name,
+                delta=getattr(lm, "delta", 0.01))
+            eng = FusedOverfitter(cfg, batch, flows, tracks, device=self.backbone.depth.device, model=self)
+            object.__setattr__(self, "_engine", eng)
+            object.__setattr__(self, "_engine_key", key)
+            object.__setattr__(self, "_engine_flows", None)
+        cur = (flows.forward, flows.backward, flows.forward_mask, flows.backward_mask)
+        if self._engine_flows is None or any(a is not b for a, b in zip(cur, self._engine_flows)):
+            eng.set_flows(flows, mask_sum=flow_loss._mask_total(flows))
+            object.__setattr__(self, "_engine_flows", cur)
+        return eng
+
     def forward(self, batch: Batch, flows: Flows, global_step: int) -> ModelOutput:
+        if self._fusable(batch, flows):
+            from .fused import LazyModelOutput
+            return LazyModelOutput(self, batch, flows, global_step)
+        return self._forward_materialized(batch, flows, global_step)
+
+    def _forward_materialized(self, batch: Batch, flows: Flows, global_step: int) -> ModelOutput:
         backbone_out = self.backbone.forward(batch, flows)
         if not self.cfg.use_correspondence_weights:  # model.py:67-68
             backbone_out.weights = torch.ones_like(backbone_out.weights)
@@ -240,11 +337,11 @@ class Model(nn.Module):
         extrinsics, rt = self.extrinsics.forward(batch, flows, backbone_out, k4)
         k_mode = {IntrinsicsRegressed: "shared_focal", IntrinsicsSoftmin: "shared_focal",
                   IntrinsicsGroundTruth: "const"}.get(type(self.intrinsics), "full")
-        return ModelOutput(backbone_out.depths, intrinsics, extrinsics, backbone_out.weights,
+        return ModelOutput(backbone_out.depths, None, intrinsics, extrinsics, backbone_out.weights,
                            relative=rt, k4=k4, k_mode=k_mode)
 
     @torch.no_grad()
     def export(self, batch: Batch, flows: Flows, global_step: int) -> ModelExports:
         assert batch.videos.shape[0] == 1  # model.py:100-101
-        out = self.forward(batch, flows, global_step)
+        out = self._forward_materialized(batch, flows, global_step)
         return ModelExports(out.extrinsics, out.intrinsics, batch.videos, out.depths)

@@ -100,15 +100,23 @@ class Overfitter:
     (model_wrapper_overfit.py:24-73)."""
 
     def __init__(self, cfg: OverfitCfg, batch: Batch, flows: Flows, tracks=None,
-                 device="cuda"):
+                 device="cuda", model=None):
         self.cfg = cfg
         self.batch, self.flows = batch.to(device), flows.to(device)
         self.tracks = None if tracks is None else [t.to(device) for t in tracks]
         _, f, _, h, w = batch.videos.shape
-        self.model, self.losses = build_model_and_losses(cfg, f, (h, w))
-        self.model.to(device)
-        self.optimizer = FusedAdam(self.model.parameters(), cfg.lr)
+        if model is None:
+            self.model, self.losses = build_model_and_losses(cfg, f, (h, w))
+            self.model.to(device)
+            self.optimizer = FusedAdam(self.model.parameters(), cfg.lr)
+        else:  # bound to a caller's Model (the autograd drop-in surface, flowmap_b200.fused)
+            self.model, self.losses, self.optimizer = model, None, None
         self.global_step = 0
+        # torch.optim.Adam counts the updates each parameter has received, not the trainer's
+        # global_step (they differ when a run starts at global_step > 0 with a fresh optimiser, and
+        # for the focal length, which sees its first gradient at the softmin -> regressed hand-over)
+        self.optimizer_steps = 0
+        self.focal_steps = 0
 
     def training_step(self):
         """Returns (total loss tensor (device), ModelOutput); no host sync."""
@@ -138,8 +146,8 @@ class FusedOverfitter(Overfitter):
     B200 (profiles/README.md), hence opt-in."""
 
     def __init__(self, cfg: OverfitCfg, batch: Batch, flows: Flows, tracks=None, device="cuda",
-                 use_splat_plan: bool = False):
-        super().__init__(cfg, batch, flows, tracks, device)
+                 use_splat_plan: bool = False, model=None):
+        super().__init__(cfg, batch, flows, tracks, device, model=model)
         from ._lib import OverfitStepArgs, PackedTracksC, lib
         import ctypes
         if batch.videos.shape[0] != 1:
@@ -286,7 +294,7 @@ class FusedOverfitter(Overfitter):
             # gradient is final there); depth and pair 0 wait for the sweep's backward
             fuse = update and c.use_correspondence_weights and self._indices is None and w % 4 == 0
             a.focal = P(self._sw_focal)
-            a.step = self.global_step + 1 if fuse else 0
+            a.step = self.optimizer_steps + 1 if fuse else 0
             a.defer_adam = 1 if fuse else 0
             check(L.fm_overfit_step(self._ctypes.byref(a), st), "fm_overfit_step")
             a.defer_adam = 0
@@ -299,7 +307,7 @@ class FusedOverfitter(Overfitter):
                                          P(self._g_w) if wl else None, P(self._sw_ws), 1, f, h, w, st),
                   "fm_softmin_sweep_bwd")
         if update:
-            s_ = self.global_step + 1
+            s_ = self.optimizer_steps + 1
             ops.adam_step(self._depth, self._g_depth, self._state[0], self._state[1], s_, c.lr)
             if c.use_correspondence_weights:
                 k = 1 if fuse else self._wlog.shape[0]  # pair 0 only when the rest was fused
@@ -308,6 +316,111 @@ class FusedOverfitter(Overfitter):
             if c.regression_after is not None and \
                     self.global_step >= c.regression_after - c.regression_window:
                 self.window.append(self._sw_focal[0].clone())
+
+    # ---- split step: the two halves of one iteration WITHOUT the parameter update, for callers that
+    # need the loss values before they decide on the backward (torch.autograd: flowmap_b200.fused)
+    def _window(self):
+        """The hand-over window of the softmin stage (intrinsics_softmin.py:133-139): the bound
+        model's own list when there is one (drop-in surface), else this optimiser's."""
+        intr = self.model.intrinsics
+        return intr.window if hasattr(intr, "window") and self.optimizer is None else self.window
+
+    def forward_phase(self, global_step: int, training: bool = True):
+        """Poses + flow loss with its direct gradients (fm_overfit_step, FM_STEP_FORWARD; the
+        candidate sweep first in the softmin stage).  Returns the weighted flow loss (device scalar,
+        a buffer that the next call overwrites)."""
+        from ._lib import check
+        c, a, L = self.cfg, self._args, self._lib
+        _, f, _, h, w = self.batch.videos.shape
+        dev = self.rt.device
+        st = torch.cuda.current_stream().cuda_stream
+        P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        self.global_step = global_step
+        if c.procrustes_randomize:
+            self._indices = self.model.extrinsics.select_indices(h, w, dev)
+        a.indices = None if self._indices is None else self._indices.data_ptr()
+        a.num_indices = 0 if self._indices is None else self._indices.numel()
+        a.flow_weight = c.flow_weight if global_step >= c.flow_enable_after else 0.0
+        a.tracks, a.step, a.defer_adam = None, 0, 0
+        self._sweep_idx = None
+        with torch.cuda.device(dev):
+            if self._softmin_stage():
+                idx = self.injected_indices
+                if idx is None:
+                    idx = getattr(self.model.intrinsics, "injected_indices", None)
+                if idx is None:
+                    idx = ops.random_subset(h * w, min(c.softmin_points, h * w), dev)
+                self._sweep_idx = idx = idx.contiguous()
+                n = c.softmin_candidates
+                wl = P(self._wlog) if c.use_correspondence_weights else None
+                sens = c.weight_sensitivity if c.use_correspondence_weights else 0.0
+                check(L.fm_softmin_sweep_fwd(P(self._depth), wl, sens, P(self.flows.backward), P(idx),
+                                             idx.numel(), P(self._cand_k4), n, P(self._sw_err),
+                                             P(self._sw_rt), P(self._sw_ws), 1, f, h, w, st),
+                      "fm_softmin_sweep_fwd")
+                check(L.fm_softmin_focal(P(self._sw_err), P(self._cand_f), n, 1, P(self._sw_sm),
+                                         P(self._sw_focal), st), "fm_softmin_focal")
+                a.focal = P(self._sw_focal)
+                if training and c.regression_after is not None and \
+                        global_step >= c.regression_after - c.regression_window:
+                    self._window().append(self._sw_focal[0].clone())
+            else:
+                if self._softmin and global_step == c.regression_after and training:
+                    self._focal.copy_(torch.stack(self._window()).mean())
+                a.focal = self._focal.data_ptr()
+            a.phase = 1  # FM_STEP_FORWARD
+            try:
+                check(L.fm_overfit_step(self._ctypes.byref(a), st), "fm_overfit_step (forward)")
+            finally:
+                a.phase = 0
+        return self._loss
+
+    def tracking_forward_phase(self):
+        """Chained poses + tracking loss of the step begun by forward_phase (loss_tracking.py:28-61).
+        Returns the weighted tracking loss (device scalar buffer)."""
+        from ._lib import check
+        c, a, L, pk = self.cfg, self._args, self._lib, self._packed
+        _, f, _, h, w = self.batch.videos.shape
+        P = lambda t: t.data_ptr()  # noqa: E731
+        st = torch.cuda.current_stream().cuda_stream
+        with torch.cuda.device(self.rt.device):
+            check(L.fm_pose_chain(P(self.rt), P(self._ext), 1, f, st), "fm_pose_chain")
+            check(L.fm_track_loss_fwd_sharded(
+                P(self._depth), P(self._k4), P(self._ext), P(pk.seg), pk.num_segments, pk.max_rows,
+                pk.max_points, P(pk.xy), P(pk.vis), pk.total, ops.MAPPINGS[c.mapping], c.delta,
+                c.tracking_weight, P(self._track_loss), P(self._tws), f, h, w, 0, 0, f, 1, st),
+                "fm_track_loss_fwd")
+        return self._track_loss
+
+    def backward_phase(self, flow_scale=None, track_scale=None, with_tracking: bool = False):
+        """Second half: [tracking backward,] Procrustes backward, focal gradient[, the sweep's
+        backward].  flow_scale / track_scale: device float scalars d total / d loss (None = 1).
+        Leaves the gradients in gradients()."""
+        from ._lib import check
+        c, a, L = self.cfg, self._args, self._lib
+        _, f, _, h, w = self.batch.videos.shape
+        st = torch.cuda.current_stream().cuda_stream
+        P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        a.tracks = self._ctypes.pointer(self._pk_c) if with_tracking else None
+        a.flow_grad_scale, a.track_grad_scale = P(flow_scale), P(track_scale)
+        a.phase, a.step, a.defer_adam = 2, 0, 0  # FM_STEP_BACKWARD
+        with torch.cuda.device(self.rt.device):
+            try:
+                check(L.fm_overfit_step(self._ctypes.byref(a), st), "fm_overfit_step (backward)")
+            finally:
+                a.phase, a.tracks, a.flow_grad_scale, a.track_grad_scale = 0, None, None, None
+            if self._sweep_idx is not None:
+                idx, n = self._sweep_idx, c.softmin_candidates
+                wl = P(self._wlog) if c.use_correspondence_weights else None
+                sens = c.weight_sensitivity if c.use_correspondence_weights else 0.0
+                check(L.fm_softmin_focal_bwd(P(self._sw_sm), P(self._cand_f), P(self._sw_focal),
+                                             P(self._g_focal), n, 1, P(self._sw_gerr), st),
+                      "fm_softmin_focal_bwd")
+                check(L.fm_softmin_sweep_bwd(P(self._depth), wl, sens, P(self.flows.backward), P(idx),
+                                             idx.numel(), P(self._cand_k4), n, P(self._sw_rt),
+                                             P(self._sw_gerr), P(self._g_depth),
+                                             P(self._g_w) if wl else None, P(self._sw_ws), 1, f, h, w, st),
+                      "fm_softmin_sweep_bwd")
 
     def training_step(self, update: bool = True):
         """Returns (total loss (device tensor), relative poses rt (1, F-1, 3, 4))."""
@@ -325,17 +438,19 @@ class FusedOverfitter(Overfitter):
             self._step_softmin(update)
         else:
             a.focal = self._focal.data_ptr()
-            a.step = self.global_step + 1 if update else 0
-            if self._softmin:  # hand-over: seed the regressed focal length once, own Adam clock
-                if self.global_step == c.regression_after and update:
-                    self._focal.copy_(torch.stack(self.window).mean())
-                a.focal_step = self.global_step - c.regression_after + 1 if update else 0
+            a.step = self.optimizer_steps + 1 if update else 0
+            if self._softmin and self.global_step == c.regression_after and update:
+                self._focal.copy_(torch.stack(self.window).mean())  # hand-over: seed the regressed focal length once
+            a.focal_step = self.focal_steps + 1 if update else 0  # the focal length's own Adam clock
+            if update:
+                self.focal_steps += 1
             with torch.cuda.device(self.rt.device):
                 check(self._lib.fm_overfit_step(self._ctypes.byref(a),
                                                 torch.cuda.current_stream().cuda_stream),
                       "fm_overfit_step")
         if update:
             self.global_step += 1
+            self.optimizer_steps += 1
         total = self._loss + self._track_loss if track_on else self._loss.clone()
         return total, self.rt
 
@@ -475,7 +590,7 @@ class ShardedFusedOverfitter(FusedOverfitter):
         # focal length wait for the exchange below
         fuse_w = update and c.use_correspondence_weights and self._indices is None and w % 4 == 0
         a.tracks = None
-        a.step = self.global_step + 1 if fuse_w else 0
+        a.step = self.optimizer_steps + 1 if fuse_w else 0
         a.defer_adam = (1 if own_sweep else 2) if fuse_w else 0
         if sweep:
             n = c.softmin_candidates
@@ -530,7 +645,7 @@ class ShardedFusedOverfitter(FusedOverfitter):
                                              P(self._g_w) if wl else None, P(self._sw_ws), 1, f_local, h, w, st),
                       "fm_softmin_sweep_bwd")
         if update:
-            s_ = self.global_step + 1
+            s_ = self.optimizer_steps + 1
             stt = self._state
             ops.adam_step(self._depth, self._g_depth, stt[0], stt[1], s_, c.lr)
             if c.use_correspondence_weights and (not fuse_w or own_sweep):
@@ -540,10 +655,11 @@ class ShardedFusedOverfitter(FusedOverfitter):
                 if c.regression_after is not None and self.global_step >= c.regression_after - c.regression_window:
                     self.window.append(self._sw_focal[0].clone())
             else:
-                fstep = s_ - c.regression_after if self._softmin else s_
+                self.focal_steps += 1
                 ops.adam_step(self._focal.reshape(1), self._g_focal.reshape(1), stt[4].reshape(1),
-                              stt[5].reshape(1), fstep, c.lr)
+                              stt[5].reshape(1), self.focal_steps, c.lr)
             self.global_step += 1
+            self.optimizer_steps += 1
         total = red[0] + self._track_loss if track_on else red[0]
         return total, self.rt
 

@@ -91,7 +91,8 @@ def global_mask_sum(local_sum: Tensor, group=None) -> Tensor:
     """The loss normaliser is global (loss_flow.py:70 sums the masks of ALL pairs): all-reduce
     the local mask sums once; the result is loop-invariant."""
     total = local_sum.clone()
-    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    if dist.is_available() and dist.is_initialized():  # a single process without a group: nothing to add
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     return total
 
 

@@ -1,6 +1,12 @@
 """Function-level mirror of flowmap/model/projection.py for callers outside the fused hot
-path (visualiser, COLMAP export, custom losses).  Same names and argument meaning; every
-body is a kernel call through flowmap_b200.ops (CUDA float32 tensors only).
+path (visualiser, COLMAP export, custom losses).  Same names and argument meaning; the bodies
+are kernel calls through flowmap_b200.ops (CUDA float32 tensors only).
+
+Differentiability: `unproject`, `get_extrinsics` and `align_surfaces` are differentiable through
+the kernels' own backward passes.  `project`, `reproject_points` and `compute_{forward,backward}_
+flow` have forward-only kernels (the differentiable uses live inside the fused loss kernels): when
+an input requires grad under autograd they evaluate the same formulas with ATen ops instead, so a
+custom loss built on them after `install()` still trains depth and poses.
 
 Broadcasting: the reference accepts arbitrary `*#batch` shapes.  Supported here are the
 shapes its own callers use: intrinsics / extrinsics / transformations carry the leading
@@ -70,8 +76,26 @@ def _rigid_inverse(ext: Tensor) -> Tensor:
     return torch.cat((rt_, -rt_ @ t), dim=-1)
 
 
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(t, Tensor) and t.requires_grad for t in tensors)
+
+
+def _project_camera_space_torch(points: Tensor, intrinsics: Tensor, epsilon: float = 1e-5) -> Tensor:
+    """projection.py:49-58 with ATen ops (autograd fall-back of the forward-only kernel)."""
+    u = points / (points[..., -1:] + epsilon)
+    u = u.nan_to_num(posinf=1e8, neginf=-1e8)
+    return (intrinsics @ u[..., None])[..., :2, 0]
+
+
+def _transform_torch(xyz: Tensor, transformation: Tensor) -> Tensor:
+    """(T [x; 1])[:3] with (*#batch, 4, 4) transformations (projection.py:27-46)."""
+    return (transformation[..., :3, :3] @ xyz[..., None])[..., 0] + transformation[..., :3, 3]
+
+
 def reproject_points(xyz: Tensor, relative_transformations: Tensor, intrinsics: Tensor) -> Tensor:
-    """projection.py:116-134 (forward only)."""
+    """projection.py:116-134."""
+    if _needs_grad(xyz, relative_transformations, intrinsics):
+        return _project_camera_space_torch(_transform_torch(xyz, relative_transformations), intrinsics)
     batch = tuple(xyz.shape[:-1])
     k = max(_split(relative_transformations, batch, 2), _split(intrinsics, batch, 2))
     items = 1
@@ -86,7 +110,10 @@ def reproject_points(xyz: Tensor, relative_transformations: Tensor, intrinsics: 
 
 
 def project(points: Tensor, extrinsics: Tensor, intrinsics: Tensor, epsilon: float = 1e-5):
-    """projection.py:61-73: world points -> (xy, in_front_of_camera); forward only."""
+    """projection.py:61-73: world points -> (xy, in_front_of_camera)."""
+    if _needs_grad(points, extrinsics, intrinsics):
+        cam = _transform_torch(points, torch.linalg.inv(extrinsics))
+        return _project_camera_space_torch(cam, intrinsics, epsilon), cam[..., -1] >= 0
     if abs(epsilon - 1e-5) > 1e-12:
         raise ValueError("flowmap_b200.projection.project: epsilon is fixed at the reference default 1e-5")
     batch = tuple(points.shape[:-1])
@@ -108,7 +135,7 @@ later = lambda x: x[:, 1:]  # noqa: E731
 
 
 def compute_forward_flow(surfaces: Tensor, extrinsics: Tensor, intrinsics: Tensor) -> Tensor:
-    """projection.py:143-162: positions of frame-i points in frame i+1 (forward only)."""
+    """projection.py:143-162: positions of frame-i points in frame i+1."""
     rel = torch.cat((_rigid_inverse(later(extrinsics)),
                      torch.tensor([0., 0., 0., 1.], device=extrinsics.device).expand(
                          *later(extrinsics).shape[:-2], 1, 4)), dim=-2) @ earlier(extrinsics)
@@ -119,7 +146,7 @@ def compute_forward_flow(surfaces: Tensor, extrinsics: Tensor, intrinsics: Tenso
 
 
 def compute_backward_flow(surfaces: Tensor, extrinsics: Tensor, intrinsics: Tensor) -> Tensor:
-    """projection.py:165-184: positions of frame-(i+1) points in frame i (forward only)."""
+    """projection.py:165-184: positions of frame-(i+1) points in frame i."""
     rel = torch.cat((_rigid_inverse(earlier(extrinsics)),
                      torch.tensor([0., 0., 0., 1.], device=extrinsics.device).expand(
                          *earlier(extrinsics).shape[:-2], 1, 4)), dim=-2) @ later(extrinsics)
@@ -136,10 +163,32 @@ def get_extrinsics(inverse_relative_transformations: Tensor) -> Tensor:
     return ops.pose_chain(rt).reshape(*batch, p + 1, 4, 4)
 
 
-def align_surfaces(depths: Tensor, intrinsics: Tensor, backward_flows: Tensor,
-                   backward_weights: Tensor, indices: Tensor | None = None) -> Tensor:
-    """projection.py:213-252 from depths + intrinsics (the point cloud is formed inside the
-    kernel; the reference's variant takes the materialised surfaces): extrinsics (b, f, 4, 4)."""
+def align_surfaces(*args) -> Tensor:
+    """projection.py:213-252 -> extrinsics (b, f, 4, 4).  Two call forms:
+
+      align_surfaces(surfaces, backward_flows, backward_weights, indices)   # the reference's signature
+      align_surfaces(depths, intrinsics, backward_flows, backward_weights[, indices])
+
+    The second forms the point cloud inside the moment kernel (no (b, f, h, w, 3) tensor).  The first
+    accepts ANY xyz image, so it follows the reference's own steps: gather the later points, sample
+    the earlier surface at xy + flow (F.grid_sample, bilinear / border / align_corners=False) and
+    solve with the align_rigid kernel (closed-form SVD adjoint); differentiable in both forms."""
+    if args[0].dim() == 5 and args[0].shape[-1] == 3 and len(args) == 4:
+        from .procrustes import align_rigid
+        surfaces, backward_flows, backward_weights, indices = args
+        b, f, h, w, _ = surfaces.shape
+        xy, _ = sample_image_grid((h, w), device=surfaces.device)
+        xyz_later = later(surfaces).reshape(b, f - 1, h * w, 3)[:, :, indices]
+        xy_earlier = (xy + backward_flows).reshape(b, f - 1, h * w, 2)[:, :, indices]
+        sampled = torch.nn.functional.grid_sample(
+            earlier(surfaces).reshape(b * (f - 1), h, w, 3).permute(0, 3, 1, 2),
+            (xy_earlier * 2 - 1).reshape(b * (f - 1), -1, 1, 2), mode="bilinear", padding_mode="border",
+            align_corners=False)
+        xyz_earlier = sampled[..., 0].permute(0, 2, 1).reshape(b, f - 1, -1, 3)
+        weights = backward_weights.reshape(b, f - 1, h * w)[..., indices]
+        return get_extrinsics(align_rigid(xyz_later.contiguous(), xyz_earlier.contiguous(), weights.contiguous()))
+    depths, intrinsics, backward_flows, backward_weights = args[:4]
+    indices = args[4] if len(args) > 4 else None
     rt = ops.procrustes_poses(depths, backward_weights, ops.intrinsics_to_k4(intrinsics),
                               backward_flows, indices)
     return ops.pose_chain(rt)

@@ -58,8 +58,10 @@ class ModelOutput:
     150x360x640) is never needed by the fused kernels, so it is materialised on first
     access only (by the unprojection kernel, differentiable)."""
 
-    def __init__(self, depths, intrinsics, extrinsics, backward_correspondence_weights,
-                 surfaces=None, relative=None, k4=None, k_mode="full"):
+    def __init__(self, depths, surfaces, intrinsics, extrinsics, backward_correspondence_weights, *,
+                 relative=None, k4=None, k_mode="full"):
+        # positional order = the reference's dataclass (model.py:24-30); `surfaces` may be None
+        # (materialised on first access); the extra fields are keyword-only
         self.depths = depths
         self.intrinsics = intrinsics
         self.extrinsics = extrinsics

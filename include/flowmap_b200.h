@@ -306,15 +306,20 @@ typedef struct {
                                    and on pair 0's logits afterwards.  2 (pair sharding): the weight logits
                                    of ALL pairs are updated here (their gradient is rank-local and final),
                                    depth and focal length wait for the caller's collective */
-  int phase;                    /* FM_STEP_ALL, or a split step for pair sharding with a tracking loss:
-                                   FM_STEP_FORWARD stops after the flow loss (rt, loss, direct depth
-                                   gradient, pose-gradient sums in ws); FM_STEP_BACKWARD resumes at the
-                                   Procrustes backward with the caller's extra pose gradient g_rt (F-1,3,4)
-                                   and intrinsics gradient track_g_k4 (F,4) (either may be NULL); tracks
-                                   must be NULL in both */
+  int phase;                    /* FM_STEP_ALL, or a split step (pair sharding with a tracking loss; the
+                                   autograd drop-in surface, where the losses' values are needed before
+                                   backward() runs): FM_STEP_FORWARD computes rt, the flow loss with its
+                                   direct depth gradient and pose-gradient sums in ws and -- with tracks --
+                                   the chained poses and the tracking loss; FM_STEP_BACKWARD resumes with
+                                   the tracking backward (with tracks) or the caller's extra pose gradient
+                                   g_rt (F-1,3,4) / intrinsics gradient track_g_k4 (F,4) (tracks == NULL,
+                                   either may be NULL), then the Procrustes backward; step must be 0 in
+                                   the two halves' common use (no parameter may change in between) */
   void* splat_plan;             /* fm_splat_plan_build of `bflow` with status 1, or NULL (global-RED path);
                                    used when indices == NULL */
   unsigned splat_overflow_max;  /* overflow_max of fm_splat_plan_info */
+  const float* flow_grad_scale;  /* FM_STEP_BACKWARD only: device scalars d total / d flow loss and     */
+  const float* track_grad_scale; /* d total / d tracking loss (autograd's grad_output), or NULL (= 1) */
 } fm_overfit_step_args;
 #define FM_STEP_ALL 0
 #define FM_STEP_FORWARD 1
