@@ -370,8 +370,9 @@ def device_shard_inputs(f, h, w, pair_lo, pair_hi, dev):
 def sharded_record(f, h, w, full, rank, world, dev, steps, barrier, max_over_ranks):
     """Strong scaling of ONE f x h x w video over the ranks of this run: ms/step with its pairs
     split over `world` ranks, the same video on one rank (rank 0) alongside, bytes sent per rank per
-    step and the device time inside the exchange (CUDA events around StepReducer.reduce /
-    _tracking_exchange on the step's stream; includes waiting for the slowest neighbour)."""
+    step and the device time inside the exchange (CUDA events around every collective / the two
+    halves of StepReducer on the step's stream, eager steps; includes waiting for the slowest
+    neighbour; in the flow-only step Adam on the interior frames runs between the two halves)."""
     from flowmap_b200 import parallel
     from flowmap_b200.overfit import OverfitCfg, ShardedFusedOverfitter
     from flowmap_b200.types import Batch, Flows, Tracks
@@ -385,6 +386,7 @@ def sharded_record(f, h, w, full, rank, world, dev, steps, barrier, max_over_ran
         cfg = OverfitCfg(intrinsics="softmin", use_tracking=True) if full else OverfitCfg()
         tracks = [Tracks(xy, vis, s) for xy, vis, s in synthetic_track_arrays(f, seed=0)] if full else None
         o = ShardedFusedOverfitter(cfg, batch, Flows(*fl), plan, tracks=tracks, device=dev, group=group)
+        o.use_cuda_graph = os.environ.get("FM_BENCH_NO_GRAPH") != "1"
         with torch.no_grad():
             o.model.backbone.depth.copy_(depth)
             o.model.backbone.weights.copy_(wparam)
@@ -406,29 +408,42 @@ def sharded_record(f, h, w, full, rank, world, dev, steps, barrier, max_over_ran
     plan = parallel.make_plan(f - 1, rank, world)
     o = build(plan)
     ms_n = max_over_ranks(timed(o, steps))
-    # time inside the exchange: events around the collectives of a few extra steps
-    spans = []
-    real_reduce, real_track = o.reducer.reduce, getattr(o, "_tracking_exchange", None)
+    # time inside the exchange: CUDA events around every collective of a few extra steps (the
+    # blocking collectives make the step's stream wait for the NCCL stream, so the events bracket
+    # them; StepReducer.reduce is bracketed as a whole: grouped send/recv + all-reduce + the two adds)
+    import torch.distributed as dist
+    spans, depth = [], {"n": 0}
 
     def wrap(fn):
         def inner(*a, **k):
+            if depth["n"] > 0:  # a collective inside an already bracketed exchange
+                return fn(*a, **k)
+            depth["n"] += 1
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = fn(*a, **k)
-            e1.record()
-            spans.append((e0, e1))
-            return out
+            try:
+                return fn(*a, **k)
+            finally:
+                e1.record()
+                spans.append((e0, e1))
+                depth["n"] -= 1
         return inner
-    o.reducer.reduce = wrap(real_reduce)
-    if full:
-        o._tracking_exchange = wrap(real_track)
+    real = (o.reducer.reduce, o.reducer.start, o.reducer.finish, dist.all_reduce, dist.broadcast)
+    (o.reducer.reduce, o.reducer.start, o.reducer.finish, dist.all_reduce, dist.broadcast) = (wrap(f) for f in real)
     n_probe = 5
-    barrier()
-    for _ in range(n_probe):
-        o.training_step()
-    torch.cuda.synchronize()
+    graph_was = o.use_cuda_graph
+    o.use_cuda_graph = False  # the probes are host-side wrappers: run these steps eagerly
+    try:
+        barrier()
+        for _ in range(n_probe):
+            o.training_step()
+        torch.cuda.synchronize()
+    finally:
+        o.reducer.reduce, o.reducer.start, o.reducer.finish, dist.all_reduce, dist.broadcast = real
+        o.use_cuda_graph = graph_was
     comm_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in spans) / n_probe)
     sent = o.reducer.bytes_per_step()
+    o_graph = bool(o._graphs)
     del o
     torch.cuda.empty_cache()
     ms_1 = None
@@ -458,7 +473,7 @@ def sharded_record(f, h, w, full, rank, world, dev, steps, barrier, max_over_ran
             "ms_per_step": round(ms_n, 4), "ms_per_step_one_gpu": round(ms_1, 4),
             "speedup": round(ms_1 / ms_n, 3), "strong_scaling_efficiency": round(ms_1 / ms_n / world, 4),
             "it_per_s": round(1000.0 / ms_n, 2), "bytes_sent_per_rank_per_step": int(sent),
-            "ms_in_exchange_per_step": round(comm_ms, 4),
+            "ms_in_exchange_per_step": round(comm_ms, 4), "cuda_graph": bool(o_graph),
             "exchange": "one 2-float all-reduce + one boundary depth-gradient frame swapped with each neighbour"
                         + (" + pose gather, tracking-sum all-reduce (F x 10 doubles), focal broadcast" if full else "")}
 
@@ -515,6 +530,7 @@ def run_gpu(args):
         tracks = [Tracks(xy, vis, s) for xy, vis, s in synthetic_track_arrays(F_, seed=rank)]
         o = init_params(FusedOverfitter(OverfitCfg(intrinsics="softmin", use_tracking=True), batch,
                                         flows_dev, tracks, device=dev))
+        o.use_cuda_graph = os.environ.get("FM_BENCH_NO_GRAPH") != "1"  # the step replayed as one CUDA graph
 
     def barrier():
         if world > 1:
@@ -561,11 +577,17 @@ def run_gpu(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    for _ in range(args.warmup):
+    l0 = lib().fm_launch_count()
+    o.training_step()  # the first warm-up step runs eagerly: its launches are the step's kernel list
+    launches_per_step = lib().fm_launch_count() - l0
+    for _ in range(max(args.warmup, 4) - 1):  # (the graph is captured on the third step)
         o.training_step()
     l0 = lib().fm_launch_count()
     ms, last = time_steps(o.training_step, args.steps)
     launches = lib().fm_launch_count() - l0
+    graph_replay = bool(getattr(o, "_graphs", None))
+    if graph_replay:  # replayed graph nodes are not host launches: count the kernels they contain
+        launches = launches_per_step * args.steps
     final_loss = float(last[0])
 
     # ---- end-to-end: the step's Flows arrive in pinned host memory every step (the
@@ -813,7 +835,8 @@ def run_gpu(args):
                 "what": "Flows (flow fwd/bwd + masks) copied from pinned host memory every step "
                         "(double-buffered: step k+1 uploads while step k computes), loss read back "
                         "every step"},
-        "gpu_launches": int(launches), "final_loss": final_loss, "loss_check": loss_check,
+        "gpu_launches": int(launches), "launches_per_step": int(launches_per_step),
+        "cuda_graph": graph_replay, "final_loss": final_loss, "loss_check": loss_check,
         "flow_only": None if flow_only_ms is None else
         {"ms_per_step": round(flow_only_ms, 4), "it_per_s": round(world * 1000.0 / flow_only_ms, 2),
          "what": "same step without tracking loss / softmin sweep (regressed focal)",

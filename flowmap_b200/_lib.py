@@ -73,6 +73,9 @@ SIGNATURES = {
     "fm_world_points": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "fm_adam_step": (c_int, [_P, _P, _P, _P, c_size_t, c_double, c_double, c_double, c_double,
                              c_int, _P]),
+    "fm_step_clock_tick": (c_int, [_P, c_double, c_double, c_double, ctypes.c_ulonglong, c_int, _P]),
+    "fm_adam_step_clock": (c_int, [_P, _P, _P, _P, c_size_t, _P, c_int, c_double, c_double, c_double, _P]),
+    "fm_random_subset_clock": (c_int, [_P, ctypes.c_longlong, c_int, _P, _P]),
 }
 
 
@@ -100,7 +103,7 @@ class OverfitStepArgs(ctypes.Structure):
                 ("track_loss", _P),
                 ("ws", _P), ("track_ws", _P), ("focal_step", c_int), ("defer_adam", c_int),
                 ("phase", c_int), ("splat_plan", _P), ("splat_overflow_max", ctypes.c_uint),
-                ("flow_grad_scale", _P), ("track_grad_scale", _P)]
+                ("flow_grad_scale", _P), ("track_grad_scale", _P), ("clock", _P)]
 
 
 SIGNATURES["fm_overfit_step"] = (c_int, [ctypes.POINTER(OverfitStepArgs), _P])

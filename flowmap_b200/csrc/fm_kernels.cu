@@ -231,6 +231,20 @@ __device__ __forceinline__ void load_vec2(const float* p, float* out) {  // 2 * 
   }
 }
 
+// Work decomposition of the dense (all-pixel) kernels: an item is one chunk of kThreads * VEC
+// consecutive pixels of one unit (a frame pair, or a frame); ONE 1-D grid of SMs x CTAs-per-SM blocks,
+// each taking a contiguous range of items.  No partial last wave (the 2-D grids of round 1 ended in a
+// 9 %..70 % full one), and a block's per-unit constants change at most a couple of times.
+struct ItemRange { int i0, i1; };
+__device__ __forceinline__ ItemRange block_item_range(long long total) {
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  long long i0 = (long long)blockIdx.x * per, i1 = i0 + per;
+  if (i0 > total) i0 = total;
+  if (i1 > total) i1 = total;
+  ItemRange r; r.i0 = (int)i0; r.i1 = (int)i1;
+  return r;
+}
+
 // ================================================================== phase A: moments
 // Where the data of (virtual) pair `pair` lives.  Normally item == batch element and the
 // strides are the dense ones; the focal-length sweep (intrinsics_softmin.py:84-109) runs
@@ -294,37 +308,7 @@ k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
 #pragma unroll
   for (int i = 0; i < kNumMoments; ++i) acc[i] = 0.f;
 
-  if (indices == nullptr) {
-    const int stride = gridDim.x * kThreads * VEC;
-    int base = (blockIdx.x * kThreads + threadIdx.x) * VEC;
-    int r = base / W, c0 = base - r * W;
-    const int dr = stride / W, dc = stride - dr * W;
-#pragma unroll 1
-    for (; base < N; base += stride) {
-      float dv[VEC], wv[VEC], fv[2 * VEC];
-      load_vec<VEC>(db + base, dv);
-      load_vec2<VEC>(fl + 2 * base, fv);
-      if (wt) {
-        load_vec<VEC>(wt + base, wv);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) wv[v] = weight_of(wv[v], wsens);
-      } else {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
-      }
-      const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        float p[3], q[3];
-        Taps taps;
-        point_pq(g, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], fv[2 * v], fv[2 * v + 1],
-                 load_a, p, q, taps);
-        moments_add(acc, wv[v], p, q);
-      }
-      r += dr; c0 += dc;
-      if (c0 >= W) { c0 -= W; ++r; }
-    }
-  } else {
+  {  // index mode only (subsampled Procrustes, the focal sweep); all pixels: k_moments_dense
     for (int t = blockIdx.x * kThreads + threadIdx.x; t < num_indices; t += gridDim.x * kThreads) {
       const int j = (int)indices[t];
       const int r = j / W, c = j - r * W;
@@ -336,6 +320,65 @@ k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
     }
   }
   block_accumulate<kNumMoments>(acc, moments + (size_t)pair * kNumMoments, smem);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads, 3)
+k_moments_dense(const float* __restrict__ depth, const float* __restrict__ k4,
+                const float* __restrict__ bflow, const float* __restrict__ weights,
+                double* __restrict__ moments, float wsens, PairLayout lay, int H, int W, int BP) {
+  __shared__ double smem[kNumMoments * (kThreads / 32)];
+  const int N = H * W;
+  constexpr int kChunk = kThreads * VEC;
+  const int chunks = (N + kChunk - 1) / kChunk;
+  const ItemRange range = block_item_range((long long)BP * chunks);
+  const int dr = kChunk / W, dc = kChunk - dr * W;
+#pragma unroll 1
+  for (int i = range.i0; i < range.i1;) {
+    const int pair = i / chunks, cb = i - pair * chunks;
+    const int ce = (cb + (range.i1 - i) < chunks) ? cb + (range.i1 - i) : chunks;
+    const PairAddr pa = pair_addr(lay, pair, N);
+    const PairGeom g = pair_geom(depth, k4, pa, H, W);
+    const float* da = opaque_ptr(depth + pa.depth_a);
+    const float* db = da + N;
+    const float* fl = bflow + pa.flow;
+    const float* wt = weights ? weights + pa.weight : nullptr;
+    auto load_a = [da](int o) { return __ldg(da + o); };
+    float acc[kNumMoments];
+#pragma unroll
+    for (int k = 0; k < kNumMoments; ++k) acc[k] = 0.f;
+    int base = (cb * kThreads + (int)threadIdx.x) * VEC;
+    int r = base / W, c0 = base - r * W;
+#pragma unroll 1
+    for (int c = cb; c < ce; ++c, base += kChunk) {
+      if (base < N) {
+        float dv[VEC], wv[VEC], fv[2 * VEC];
+        load_vec<VEC>(db + base, dv);
+        load_vec2<VEC>(fl + 2 * base, fv);
+        if (wt) {
+          load_vec<VEC>(wt + base, wv);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) wv[v] = weight_of(wv[v], wsens);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
+        }
+        const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          float p[3], q[3];
+          Taps taps;
+          point_pq(g, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], fv[2 * v], fv[2 * v + 1],
+                   load_a, p, q, taps);
+          moments_add(acc, wv[v], p, q);
+        }
+      }
+      r += dr; c0 += dc;
+      if (c0 >= W) { c0 -= W; ++r; }
+    }
+    block_accumulate<kNumMoments>(acc, moments + (size_t)pair * kNumMoments, smem);
+    i += ce - cb;
+  }
 }
 
 // ================================================================== phase B: solve
@@ -449,10 +492,11 @@ __device__ __forceinline__ void flow_frame_body_lean(const FlowFrameLean& f, con
                                                      const float* __restrict__ ff, const float* __restrict__ mf,
                                                      const float* __restrict__ fb, const float* __restrict__ mb,
                                                      float* __restrict__ gd, float g, const RobustCfg& rc,
-                                                     const GridDims& grid, int N, float* acc) {
+                                                     const GridDims& grid, int N, float* acc, int chunk_begin,
+                                                     int chunk_end) {
   const int W = grid.W;
-  const int stride = gridDim.x * kThreads * VEC;
-  int base = (blockIdx.x * kThreads + threadIdx.x) * VEC;
+  constexpr int stride = kThreads * VEC;  // one chunk per iteration (see block_item_range)
+  int base = (chunk_begin * kThreads + (int)threadIdx.x) * VEC;
   int r = base / W, c0 = base - r * W;
   const int dr = stride / W, dc = stride - dr * W;
   F2 acc2[kFlowLeanVals];
@@ -460,8 +504,9 @@ __device__ __forceinline__ void flow_frame_body_lean(const FlowFrameLean& f, con
 #pragma unroll
     for (int k = 0; k < kFlowLeanVals; ++k) acc2[k] = f2s(0.f);
   }
+  const int end = chunk_end * stride < N ? chunk_end * stride : N;
 #pragma unroll 1
-  for (; base < N; base += stride) {
+  for (; base < end; base += stride) {
     float dv[VEC], ffv[2 * VEC], fbv[2 * VEC], mfv[VEC], mbv[VEC], out[VEC];
     load_vec<VEC>(D + base, dv);
     if (HASF) { load_vec2<VEC>(ff + 2 * base, ffv); load_vec<VEC>(mf + base, mfv); }
@@ -502,40 +547,48 @@ k_flow_lean(const float* __restrict__ depth, const float* __restrict__ k4, const
             const float* __restrict__ fflow, const float* __restrict__ bflow,
             const float* __restrict__ fmask, const float* __restrict__ bmask,
             const double* __restrict__ mask_sum, int mapping, float delta, float loss_weight,
-            float* __restrict__ g_depth, double* __restrict__ leanacc, int F, int H, int W) {
+            float* __restrict__ g_depth, double* __restrict__ leanacc, int F, int H, int W, int BF) {
   __shared__ double smem[kFlowLeanVals * (kThreads / 32)];
-  const int frame = blockIdx.y;
-  const int bi = frame / F, i = frame - bi * F;
   const int N = H * W;
-  const bool hasF = i < F - 1, hasB = i > 0;
-  FlowFrameLean f;
-  f.kk = make_cam(load_k4(k4, frame));
-  f.kn = make_cam(load_k4(k4, hasF ? frame + 1 : frame));
-  f.kp = make_cam(load_k4(k4, hasB ? frame - 1 : frame));
-  const int pairF = bi * (F - 1) + i, pairB = pairF - 1;
-  Rt tf, tb;
-  if (hasF) tf = load_rt(rt, pairF);
-  if (hasB) tb = load_rt(rt, pairB);
-  fill_lean(f, hasF ? &tf : nullptr, hasB ? &tb : nullptr);
+  constexpr int kChunk = kThreads * VEC;
+  const int chunks = (N + kChunk - 1) / kChunk;
+  const ItemRange range = block_item_range((long long)BF * chunks);
   double den = mask_sum ? *mask_sum : 1.0;
   if (den == 0.0) den = 1.0;  // loss_flow.py:70 "valid_sum or 1"
   const float g = (float)((double)loss_weight / den);
   const RobustCfg rc = make_robust(mapping, delta, H, W);
   const GridDims grid = make_grid(H, W);
-  const float* D = depth + (size_t)frame * N;
-  const float* ff = fflow + (size_t)(hasF ? pairF : 0) * N * 2;
-  const float* mf = fmask + (size_t)(hasF ? pairF : 0) * N;
-  const float* fb = bflow + (size_t)(hasB ? pairB : 0) * N * 2;
-  const float* mb = bmask + (size_t)(hasB ? pairB : 0) * N;
-  float* gd = g_depth + (size_t)frame * N;
-  float acc[kFlowLeanVals];
+#pragma unroll 1
+  for (int it = range.i0; it < range.i1;) {
+    const int frame = it / chunks, cb = it - frame * chunks;
+    const int ce = (cb + (range.i1 - it) < chunks) ? cb + (range.i1 - it) : chunks;
+    const int bi = frame / F, i = frame - bi * F;
+    const bool hasF = i < F - 1, hasB = i > 0;
+    FlowFrameLean f;
+    f.kk = make_cam(load_k4(k4, frame));
+    f.kn = make_cam(load_k4(k4, hasF ? frame + 1 : frame));
+    f.kp = make_cam(load_k4(k4, hasB ? frame - 1 : frame));
+    const int pairF = bi * (F - 1) + i, pairB = pairF - 1;
+    Rt tf, tb;
+    if (hasF) tf = load_rt(rt, pairF);
+    if (hasB) tb = load_rt(rt, pairB);
+    fill_lean(f, hasF ? &tf : nullptr, hasB ? &tb : nullptr);
+    const float* D = depth + (size_t)frame * N;
+    const float* ff = fflow + (size_t)(hasF ? pairF : 0) * N * 2;
+    const float* mf = fmask + (size_t)(hasF ? pairF : 0) * N;
+    const float* fb = bflow + (size_t)(hasB ? pairB : 0) * N * 2;
+    const float* mb = bmask + (size_t)(hasB ? pairB : 0) * N;
+    float* gd = g_depth + (size_t)frame * N;
+    float acc[kFlowLeanVals];
 #pragma unroll
-  for (int k = 0; k < kFlowLeanVals; ++k) acc[k] = 0.f;
-  if (hasF && hasB) flow_frame_body_lean<VEC, true, true, FOCAL>(f, D, ff, mf, fb, mb, gd, g, rc, grid, N, acc);
-  else if (hasF) flow_frame_body_lean<VEC, true, false, FOCAL>(f, D, ff, mf, fb, mb, gd, g, rc, grid, N, acc);
-  else flow_frame_body_lean<VEC, false, true, FOCAL>(f, D, ff, mf, fb, mb, gd, g, rc, grid, N, acc);
-  // lean slots live in the upper half of the frame's accumulator row until k_flow_lean_convert
-  block_accumulate<kFlowLeanVals>(acc, leanacc + (size_t)frame * kFlowAcc, smem);
+    for (int k = 0; k < kFlowLeanVals; ++k) acc[k] = 0.f;
+    if (hasF && hasB) flow_frame_body_lean<VEC, true, true, FOCAL>(f, D, ff, mf, fb, mb, gd, g, rc, grid, N, acc, cb, ce);
+    else if (hasF) flow_frame_body_lean<VEC, true, false, FOCAL>(f, D, ff, mf, fb, mb, gd, g, rc, grid, N, acc, cb, ce);
+    else flow_frame_body_lean<VEC, false, true, FOCAL>(f, D, ff, mf, fb, mb, gd, g, rc, grid, N, acc, cb, ce);
+    // lean slots live in the upper half of the frame's accumulator row until k_flow_lean_convert
+    block_accumulate<kFlowLeanVals>(acc, leanacc + (size_t)frame * kFlowAcc, smem);
+    it += ce - cb;
+  }
 }
 
 // Rewrites each frame's lean accumulators (slots 0-13) into the standard layout in place.
@@ -653,6 +706,7 @@ struct AdamFuse {
   float beta1, beta2, omb1, omb2, eps, step_size, bc2_sqrt;
   int on;
   int first_pair;  // pairs below this index are left to a later, separate Adam call
+  const float* consts;  // device {step_size, bc2_sqrt} of a step clock (CUDA-graph replays), or NULL
 };
 
 template <int VEC>
@@ -674,6 +728,7 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
   const PairAddr pa = pair_addr(lay, pair, N);
   const PairGeom g = pair_geom(depth, k4, pa, H, W);
   const int a = pa.k4_frame_a;
+  if (adam.on && adam.consts) { adam.step_size = __ldg(adam.consts); adam.bc2_sqrt = __ldg(adam.consts + 1); }
   const float* da = opaque_ptr(depth + pa.depth_a);
   const float* db = da + N;
   const float* fl = bflow + pa.flow;
@@ -687,64 +742,7 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
 #pragma unroll
   for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
 
-  if (indices == nullptr) {
-    const int stride = gridDim.x * kThreads * VEC;
-    int base = (blockIdx.x * kThreads + threadIdx.x) * VEC;
-    int r = base / W, c0 = base - r * W;
-    const int dr = stride / W, dc = stride - dr * W;
-#pragma unroll 1
-    for (; base < N; base += stride) {
-      float dv[VEC], wv[VEC], wraw[VEC], fv[2 * VEC], gwv[VEC], gdv[VEC];
-      load_vec<VEC>(db + base, dv);
-      load_vec2<VEC>(fl + 2 * base, fv);
-      if (wt) {
-        if (VEC == 4) {  // plain (coherent) load: the logits may be updated in place below
-          const float4 w4 = *reinterpret_cast<const float4*>(wt + base);
-          wraw[0] = w4.x; wraw[1] = w4.y; wraw[2] = w4.z; wraw[3] = w4.w;
-        } else {
-          wraw[0] = wt[base];
-        }
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) wv[v] = weight_of(wraw[v], wsens);
-      } else {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
-      }
-      const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
-#pragma unroll
-      for (int v = 0; v < VEC; ++v)
-        distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v],
-                         fv[2 * v], fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
-      r += dr; c0 += dc;
-      if (c0 >= W) { c0 -= W; ++r; }
-      if (VEC == 4) red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
-      else red_add(gdb + base, gdv[0]);
-      if (wt) {
-        if (wsens != 0.f) {  // chain rule of the sigmoid: d/d logit = sens * w (1 - w) * d/dw
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) gwv[v] *= wsens * wv[v] * (1.0f - wv[v]);
-        }
-        if (gw) {
-          if (VEC == 4) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
-          else gw[base] = gwv[0];
-        }
-        if (VEC == 4 && adam.on && pair >= adam.first_pair) {  // torch.optim.Adam on the logits (k_adam's order)
-          float4 mm = *reinterpret_cast<float4*>(adam.m + pa.weight + base);
-          float4 vv = *reinterpret_cast<float4*>(adam.v + pa.weight + base);
-          float* mp = &mm.x; float* vp = &vv.x;
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            mp[v] = mp[v] + adam.omb1 * (gwv[v] - mp[v]);
-            vp[v] = vp[v] * adam.beta2 + adam.omb2 * gwv[v] * gwv[v];
-            wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
-          }
-          *reinterpret_cast<float4*>(adam.m + pa.weight + base) = mm;
-          *reinterpret_cast<float4*>(adam.v + pa.weight + base) = vv;
-          *reinterpret_cast<float4*>(wt + base) = make_float4(wraw[0], wraw[1], wraw[2], wraw[3]);
-        }
-      }
-    }
-  } else {
+  {  // index mode only; all pixels: k_distribute_dense
     for (int t = blockIdx.x * kThreads + threadIdx.x; t < num_indices; t += gridDim.x * kThreads) {
       const int j = (int)indices[t];
       const int r = j / W, c = j - r * W;
@@ -760,6 +758,108 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
   }
   // kacc[0..3] -> frame a, kacc[4..7] -> frame b = a + 1: contiguous in k4acc
   block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
+}
+
+// Dense (all-pixel) phase D2 on the item decomposition of block_item_range: same per-pixel work as
+// k_distribute's dense branch, per-pair constants re-staged when a block moves on to its next pair.
+template <int VEC>
+__global__ void __launch_bounds__(kThreads, 3)
+k_distribute_dense(const float* __restrict__ depth, const float* __restrict__ k4,
+                   const float* __restrict__ bflow, float* weights, const PairAdjoint* __restrict__ adj,
+                   float* __restrict__ g_depth, float* __restrict__ g_weights, double* __restrict__ k4acc,
+                   float wsens, PairLayout lay, AdamFuse adam, int H, int W, int BP) {
+  __shared__ double smem[8 * (kThreads / 32)];
+  __shared__ PairAdjoint s_adj;
+  const int N = H * W;
+  constexpr int kChunk = kThreads * VEC;
+  const int chunks = (N + kChunk - 1) / kChunk;
+  const ItemRange range = block_item_range((long long)BP * chunks);
+  const int dr = kChunk / W, dc = kChunk - dr * W;
+  if (adam.on && adam.consts) { adam.step_size = __ldg(adam.consts); adam.bc2_sqrt = __ldg(adam.consts + 1); }
+#pragma unroll 1
+  for (int i = range.i0; i < range.i1;) {
+    const int pair = i / chunks, cb = i - pair * chunks;
+    const int ce = (cb + (range.i1 - i) < chunks) ? cb + (range.i1 - i) : chunks;
+    __syncthreads();  // the previous pair's s_adj is no longer read
+    if (threadIdx.x < sizeof(PairAdjoint) / 4)
+      reinterpret_cast<float*>(&s_adj)[threadIdx.x] = reinterpret_cast<const float*>(adj + pair)[threadIdx.x];
+    __syncthreads();
+    const PairAdjoint ad = s_adj;
+    const PairAddr pa = pair_addr(lay, pair, N);
+    const PairGeom g = pair_geom(depth, k4, pa, H, W);
+    const int a = pa.k4_frame_a;
+    const float* da = opaque_ptr(depth + pa.depth_a);
+    const float* db = da + N;
+    const float* fl = bflow + pa.flow;
+    float* wt = weights ? weights + pa.weight : nullptr;
+    float* gda = g_depth + pa.depth_a;
+    auto load_a = [da](int o) { return __ldg(da + o); };
+    auto scatter = [gda, W](int y0, int x0, float v0, float v1) { red_pair<VEC == 4>(gda + y0 * W, x0, W, v0, v1); };
+    float* gdb = gda + N;
+    float* gw = g_weights ? g_weights + pa.weight : nullptr;
+    float kacc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
+    int base = (cb * kThreads + (int)threadIdx.x) * VEC;
+    int r = base / W, c0 = base - r * W;
+#pragma unroll 1
+    for (int c = cb; c < ce; ++c, base += kChunk) {
+      if (base < N) {
+        float dv[VEC], wv[VEC], wraw[VEC], fv[2 * VEC], gwv[VEC], gdv[VEC];
+        load_vec<VEC>(db + base, dv);
+        load_vec2<VEC>(fl + 2 * base, fv);
+        if (wt) {
+          if (VEC == 4) {  // plain (coherent) load: the logits may be updated in place below
+            const float4 w4 = *reinterpret_cast<const float4*>(wt + base);
+            wraw[0] = w4.x; wraw[1] = w4.y; wraw[2] = w4.z; wraw[3] = w4.w;
+          } else {
+            wraw[0] = wt[base];
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) wv[v] = weight_of(wraw[v], wsens);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) wv[v] = 1.f;
+        }
+        const float y = pix_coord(r, g.grid.Hf, g.grid.invH);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          distribute_point(g, ad, pix_coord(c0 + v, g.grid.Wf, g.grid.invW), y, dv[v], wv[v],
+                           fv[2 * v], fv[2 * v + 1], load_a, scatter, gdv[v], gwv[v], kacc);
+        if (VEC == 4) red_add4(gdb + base, gdv[0], gdv[1], gdv[2], gdv[3]);
+        else red_add(gdb + base, gdv[0]);
+        if (wt) {
+          if (wsens != 0.f) {  // chain rule of the sigmoid: d/d logit = sens * w (1 - w) * d/dw
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) gwv[v] *= wsens * wv[v] * (1.0f - wv[v]);
+          }
+          if (gw) {
+            if (VEC == 4) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
+            else gw[base] = gwv[0];
+          }
+          if (VEC == 4 && adam.on && pair >= adam.first_pair) {  // torch.optim.Adam on the logits (k_adam's order)
+            float4 mm = *reinterpret_cast<float4*>(adam.m + pa.weight + base);
+            float4 vv = *reinterpret_cast<float4*>(adam.v + pa.weight + base);
+            float* mp = &mm.x; float* vp = &vv.x;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              mp[v] = mp[v] + adam.omb1 * (gwv[v] - mp[v]);
+              vp[v] = vp[v] * adam.beta2 + adam.omb2 * gwv[v] * gwv[v];
+              wraw[v] = wraw[v] - adam.step_size * (mp[v] / (sqrtf(vp[v]) / adam.bc2_sqrt + adam.eps));
+            }
+            *reinterpret_cast<float4*>(adam.m + pa.weight + base) = mm;
+            *reinterpret_cast<float4*>(adam.v + pa.weight + base) = vv;
+            *reinterpret_cast<float4*>(wt + base) = make_float4(wraw[0], wraw[1], wraw[2], wraw[3]);
+          }
+        }
+      }
+      r += dr; c0 += dc;
+      if (c0 >= W) { c0 -= W; ++r; }
+    }
+    // kacc[0..3] -> frame a, kacc[4..7] -> frame b = a + 1: contiguous in k4acc
+    block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
+    i += ce - cb;
+  }
 }
 
 #include "fm_tiled.cuh"
@@ -1046,7 +1146,8 @@ k_pose_chain_bwd(const float* __restrict__ rt, const float* __restrict__ ext,
 __global__ void __launch_bounds__(kThreads)
 k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
        size_t n, float beta1, float beta2, float omb1, float omb2, float eps, float step_size,
-       float bc2_sqrt) {
+       float bc2_sqrt, const float* __restrict__ consts = nullptr) {
+  if (consts) { step_size = __ldg(consts); bc2_sqrt = __ldg(consts + 1); }  // device step clock
   const size_t n4 = n / 4;
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kThreads) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -1719,9 +1820,11 @@ __device__ __forceinline__ unsigned feistel_hash(unsigned v, unsigned key) {
   v ^= key; v *= 0x9E3779B1u; v ^= v >> 15; v *= 0x85EBCA77u; v ^= v >> 13; v *= 0xC2B2AE3Du; v ^= v >> 16;
   return v;
 }
-__global__ void k_random_subset(unsigned long long seed, long long N, int n, int64_t* __restrict__ out) {
+__global__ void k_random_subset(unsigned long long seed, long long N, int n, int64_t* __restrict__ out,
+                                const unsigned long long* __restrict__ seed_dev = nullptr) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
+  if (seed_dev) seed = *seed_dev;  // the step clock's per-step seed (CUDA-graph replays)
   int bits = 2;
   while ((1ll << bits) < N) bits += 2;  // even number of bits: two equal halves
   const int half = bits / 2;
@@ -1738,6 +1841,38 @@ __global__ void k_random_subset(unsigned long long seed, long long N, int n, int
     x = ((unsigned long long)l << half) | r;
   } while ((long long)x >= N);
   out[t] = (int64_t)x;
+}
+
+// ================================================================== step clock
+// Everything that changes from one optimisation step to the next OUTSIDE the parameters -- Adam's
+// bias corrections (model_wrapper_overfit.py:104-105, torch.optim.Adam's per-parameter step count)
+// and the seed of the softmin point sample (intrinsics_softmin.py:90) -- kept in device memory and
+// advanced by a one-thread kernel, so that a whole step is a fixed sequence of launches with fixed
+// arguments: capturable in a CUDA graph and replayable.
+struct StepClock {
+  unsigned step, focal_step;
+  float step_size, bc2_sqrt;              // lr / (1 - beta1^step), sqrt(1 - beta2^step)
+  float focal_step_size, focal_bc2_sqrt;  // the same on the focal length's own count
+  unsigned long long seed;
+};
+static_assert(sizeof(StepClock) == 32, "StepClock layout (FM_STEP_CLOCK_BYTES)");
+
+__global__ void k_clock_tick(StepClock* c, double lr, double b1, double b2, unsigned long long base_seed,
+                             int tick_focal) {
+  const unsigned t = c->step + 1u;
+  c->step = t;
+  c->step_size = (float)(lr / (1.0 - pow(b1, (double)t)));
+  c->bc2_sqrt = (float)sqrt(1.0 - pow(b2, (double)t));
+  const unsigned tf = c->focal_step + (tick_focal ? 1u : 0u);
+  c->focal_step = tf;
+  if (tf > 0u) {
+    c->focal_step_size = (float)(lr / (1.0 - pow(b1, (double)tf)));
+    c->focal_bc2_sqrt = (float)sqrt(1.0 - pow(b2, (double)tf));
+  }
+  unsigned long long z = base_seed + 0x9E3779B97F4A7C15ull * (unsigned long long)t;  // splitmix64
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  c->seed = z ^ (z >> 31);
 }
 
 // ================================================================== fused overfit step helpers
@@ -1785,6 +1920,22 @@ int blocks_for(int n_items_per_row, int vec) {
   return nb < 1 ? 1 : nb;
 }
 
+// 1-D grid of the dense kernels (block_item_range): every SM holds `ctas_per_sm` blocks for the whole
+// launch.
+int sm_count_cached() {
+  static const int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1)
+      v = 148;
+    return v;
+  }();
+  return n;
+}
+int persistent_grid(int ctas_per_sm, long long items) {
+  const long long g = (long long)sm_count_cached() * ctas_per_sm;
+  return (int)(items < g ? (items < 1 ? 1 : items) : g);
+}
+
 // Index-mode launches (subsampled Procrustes, the focal sweep): few points, dependent gathers ->
 // one point per thread so that the latency is covered by parallelism, not by a per-thread loop.
 int blocks_for_points(int n) {
@@ -1813,12 +1964,13 @@ int launch_flow(const float* depth, const float* k4, const float* rt, const floa
     return 0;
   }
   const bool focal = intrinsics_mode == 1;
+  const int pg = persistent_grid(2, (long long)BF * ((H * W + kThreads * vec - 1) / (kThreads * vec)));
   if (vec == 4) {
-    if (focal) k_flow_lean<4, true, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
-    else k_flow_lean<4, false, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
+    if (focal) k_flow_lean<4, true, 2><<<pg, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W, BF);
+    else k_flow_lean<4, false, 2><<<pg, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W, BF);
   } else {
-    if (focal) k_flow_lean<1, true, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
-    else k_flow_lean<1, false, 2><<<grid, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W);
+    if (focal) k_flow_lean<1, true, 2><<<pg, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W, BF);
+    else k_flow_lean<1, false, 2><<<pg, kThreads, 0, s>>>(depth, k4, rt, ff, fb, mf, mb, mask_sum, mapping, delta, loss_weight, g_depth, flowacc, F, H, W, BF);
   }
   FM_CHECK_LAUNCH("k_flow_lean");
   k_flow_lean_convert<<<(BF + 63) / 64, 64, 0, s>>>(flowacc, rt, k4, focal ? 1 : 0, B, F, H, W);
@@ -2009,11 +2161,11 @@ static int procrustes_fwd_impl(const float* depth, const float* k4, const float*
     dim3 grid(blocks_for_points(num_indices), BP);
     k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.moments, wsens, lay, H, W);
   } else if (W % 4 == 0) {
-    dim3 grid(blocks_for(H * W, 4), BP);
-    k_moments<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, lay, H, W);
+    const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4)));
+    k_moments_dense<4><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP);
   } else {
-    dim3 grid(blocks_for(H * W, 1), BP);
-    k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, nullptr, 0, w.moments, wsens, lay, H, W);
+    const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads - 1) / kThreads));
+    k_moments_dense<1><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP);
   }
   if (!plan) FM_CHECK_LAUNCH("fm_procrustes_fwd: k_moments");
   k_solve<<<(BP + 63) / 64, 64, 0, s>>>(w.moments, depth, rt, w.state, BP, lay, H, W);
@@ -2074,11 +2226,11 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
     dim3 grid(blocks_for_points(num_indices), BP);
     k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   } else if (W % 4 == 0) {
-    dim3 grid(blocks_for(H * W, 4), BP);
-    k_distribute<4><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
+    const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4)));
+    k_distribute_dense<4><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W, BP);
   } else {
-    dim3 grid(blocks_for(H * W, 1), BP);
-    k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, nullptr, 0, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
+    const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads - 1) / kThreads));
+    k_distribute_dense<1><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W, BP);
   }
   FM_CHECK_LAUNCH("fm_procrustes_bwd: k_distribute");
   k_k4_finalize<<<(BF + 127) / 128, 128, 0, s>>>(w.k4acc, w.flowacc, include_flow_loss, flow_scale, g_k4, B, F);
@@ -2219,6 +2371,37 @@ int fm_pose_chain_bwd(const float* rt, const float* extrinsics, const float* g_e
   if (!rt || !extrinsics || !g_extrinsics || !g_rt || B < 1 || F < 2) return fail_msg("fm_pose_chain_bwd: bad arguments");
   k_pose_chain_bwd<<<B, kChainThreads, 0, (cudaStream_t)stream>>>(rt, extrinsics, g_extrinsics, g_rt, B, F);
   FM_CHECK_LAUNCH("fm_pose_chain_bwd");
+  return 0;
+}
+
+int fm_step_clock_tick(void* clock, double lr, double beta1, double beta2, unsigned long long base_seed,
+                       int tick_focal, void* stream) {
+  if (!clock) return fail_msg("fm_step_clock_tick: bad arguments");
+  k_clock_tick<<<1, 1, 0, (cudaStream_t)stream>>>((StepClock*)clock, lr, beta1, beta2, base_seed, tick_focal);
+  FM_CHECK_LAUNCH("fm_step_clock_tick");
+  return 0;
+}
+
+int fm_adam_step_clock(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count,
+                       const void* clock, int focal_clock, double beta1_d, double beta2_d, double eps_d,
+                       void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !clock) return fail_msg("fm_adam_step_clock: bad arguments");
+  if (count == 0) return 0;
+  size_t nb = (count / 4 + kThreads * 2 - 1) / (kThreads * 2);
+  if (nb < 1) nb = 1;
+  if (nb > 148 * 16) nb = 148 * 16;
+  const StepClock* c = (const StepClock*)clock;
+  k_adam<<<(unsigned)nb, kThreads, 0, (cudaStream_t)stream>>>(
+      param, grad, exp_avg, exp_avg_sq, count, (float)beta1_d, (float)beta2_d, (float)(1.0 - beta1_d),
+      (float)(1.0 - beta2_d), (float)eps_d, 0.f, 1.f, focal_clock ? &c->focal_step_size : &c->step_size);
+  FM_CHECK_LAUNCH("fm_adam_step_clock");
+  return 0;
+}
+
+int fm_random_subset_clock(const void* clock, long long N, int n, int64_t* out, void* stream) {
+  if (!clock || N < 1 || n < 1 || n > N || !out) return fail_msg("fm_random_subset_clock: bad arguments");
+  k_random_subset<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(0ull, N, n, out, &((const StepClock*)clock)->seed);
+  FM_CHECK_LAUNCH("fm_random_subset_clock");
   return 0;
 }
 
@@ -2622,7 +2805,9 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
   memset(&af, 0, sizeof(af));
   const bool defer = a->defer_adam != 0;  // softmin stage: the sweep's backward still adds gradients
   const bool fuse_w = a->step > 0 && a->weight_logits && !a->indices && W % 4 == 0;
+  const StepClock* clock = (const StepClock*)a->clock;
   if (fuse_w) {  // the weight gradient is final inside k_distribute: update the logits there
+    af.consts = clock ? &clock->step_size : nullptr;
     af.on = 1; af.m = a->m_weights; af.v = a->v_weights;
     af.first_pair = a->defer_adam == 1 ? 1 : 0;  // 1: the sweep still touches pair 0; 2: every pair is final
     af.beta1 = (float)a->beta1; af.beta2 = (float)a->beta2;
@@ -2637,18 +2822,18 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
     return rc;
   // Adam (model_wrapper_overfit.py:104-105)
   if (a->step > 0 && !defer) {
-    if ((rc = fm_adam_step(a->depth, a->g_depth, a->m_depth, a->v_depth, (size_t)F * N, a->lr, a->beta1,
-                           a->beta2, a->eps, a->step, stream)))
-      return rc;
+    auto adam = [&](float* p, const float* g, float* m, float* v, size_t n, int step, int focal_clock) -> int {
+      return clock ? fm_adam_step_clock(p, g, m, v, n, clock, focal_clock, a->beta1, a->beta2, a->eps, stream)
+                   : fm_adam_step(p, g, m, v, n, a->lr, a->beta1, a->beta2, a->eps, step, stream);
+    };
+    if ((rc = adam(a->depth, a->g_depth, a->m_depth, a->v_depth, (size_t)F * N, a->step, 0))) return rc;
     if (a->weight_logits && !fuse_w &&
-        (rc = fm_adam_step(a->weight_logits, a->g_weights, a->m_weights, a->v_weights, (size_t)BP * N,
-                           a->lr, a->beta1, a->beta2, a->eps, a->step, stream)))
+        (rc = adam(a->weight_logits, a->g_weights, a->m_weights, a->v_weights, (size_t)BP * N, a->step, 0)))
       return rc;
     if (a->focal) {
       k_focal_grad<<<1, 256, 0, s>>>(w.k4acc, w.flowacc, track_g_k4, a->g_focal, 1, F, H, W, fscale);
       FM_CHECK_LAUNCH("fm_overfit_step: k_focal_grad");
-      if ((rc = fm_adam_step(a->focal, a->g_focal, a->m_focal, a->v_focal, 1, a->lr, a->beta1, a->beta2,
-                             a->eps, a->focal_step > 0 ? a->focal_step : a->step, stream)))
+      if ((rc = adam(a->focal, a->g_focal, a->m_focal, a->v_focal, 1, a->focal_step > 0 ? a->focal_step : a->step, 1)))
         return rc;
     }
   } else if (a->focal) {

@@ -704,6 +704,9 @@ k_backward_tiled(const __grid_constant__ CUtensorMap tm_depth, const __grid_cons
   }
   unsigned phWD = 0u, phQ = 0u;
   int ib = 0;
+  // Adam's step-dependent scalars: by value, or from the device step clock (CUDA-graph replays)
+  const float adam_step_size = (a.adam.on && a.adam.consts) ? __ldg(a.adam.consts) : a.adam.step_size;
+  const float adam_bc2_sqrt = (a.adam.on && a.adam.consts) ? __ldg(a.adam.consts + 1) : a.adam.bc2_sqrt;
 #pragma unroll 1
   for (int i = i0; i < i1; ++i, ib ^= 1) {
     const ItemInfo& me = info[ib];
@@ -906,13 +909,13 @@ k_backward_tiled(const __grid_constant__ CUtensorMap tm_depth, const __grid_cons
             float4 mm = *reinterpret_cast<float4*>(am);
             float4 vv = *reinterpret_cast<float4*>(av);
             float* mp = &mm.x; float* vp = &vv.x;
-            const float inv_bc2 = fm_rcp(a.adam.bc2_sqrt);
+            const float inv_bc2 = fm_rcp(adam_bc2_sqrt);
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
               mp[v] = mp[v] + a.adam.omb1 * (gwv[v] - mp[v]);
               vp[v] = vp[v] * a.adam.beta2 + a.adam.omb2 * gwv[v] * gwv[v];
               const float root = vp[v] * fm_rsqrt(fmaxf(vp[v], 1e-37f));
-              wraw[v] = wraw[v] - a.adam.step_size * (mp[v] * fm_rcp(fm_fma(root, inv_bc2, a.adam.eps)));
+              wraw[v] = wraw[v] - adam_step_size * (mp[v] * fm_rcp(fm_fma(root, inv_bc2, a.adam.eps)));
             }
             *reinterpret_cast<float4*>(am) = mm;
             *reinterpret_cast<float4*>(av) = vv;

@@ -348,6 +348,55 @@ def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, 
               "fm_adam_step")
 
 
+class StepClock:
+    """Device-resident step state (fm_step_clock_tick): Adam's bias-correction scalars on the
+    optimiser's own step counts and a per-step seed.  With it every optimisation step is the same
+    sequence of launches with the same arguments -- the precondition for replaying it as a CUDA graph."""
+
+    def __init__(self, device, lr: float, betas=(0.9, 0.999), base_seed: int | None = None):
+        self.buf = torch.zeros(32, dtype=torch.uint8, device=device)  # FM_STEP_CLOCK_BYTES
+        self.lr, self.betas = lr, betas
+        self.base_seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if base_seed is None else base_seed
+        self.steps = self.focal_steps = 0  # host mirror of the device counters
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr()
+
+    def set(self, steps: int, focal_steps: int) -> None:
+        """Counts of completed updates (the next tick makes them steps + 1)."""
+        if (steps, focal_steps) != (self.steps, self.focal_steps):
+            self.buf.view(torch.int32)[:2].copy_(torch.tensor([steps, focal_steps], dtype=torch.int32))
+            self.steps, self.focal_steps = steps, focal_steps
+
+    def tick(self, tick_focal: bool) -> None:
+        with torch.cuda.device(self.buf.device):
+            check(lib().fm_step_clock_tick(self.ptr, self.lr, self.betas[0], self.betas[1], self.base_seed,
+                                           int(tick_focal), _stream()), "fm_step_clock_tick")
+        self.steps += 1
+        self.focal_steps += int(tick_focal)
+
+
+def adam_step_clock(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, clock: StepClock,
+                    focal_clock: bool = False, eps: float = 1e-8) -> None:
+    """adam_step with the bias corrections of the current tick of `clock`."""
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("flowmap_b200: adam_step needs contiguous CUDA float32 tensors")
+    with torch.cuda.device(param.device):
+        check(lib().fm_adam_step_clock(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(),
+                                       clock.ptr, int(focal_clock), clock.betas[0], clock.betas[1], eps, _stream()),
+              "fm_adam_step_clock")
+
+
+def random_subset_clock(clock: StepClock, num_items: int, out: Tensor) -> Tensor:
+    """random_subset seeded by the current tick of `clock`, into the caller's int64 buffer."""
+    with torch.cuda.device(out.device):
+        check(lib().fm_random_subset_clock(clock.ptr, num_items, out.numel(), _ptr(out), _stream()),
+              "fm_random_subset_clock")
+    return out
+
+
 class PackedTracks:
     """All segments of a list[Tracks] in the flat layout fm_track_loss_* expects."""
 

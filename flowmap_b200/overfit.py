@@ -213,6 +213,14 @@ class FusedOverfitter(Overfitter):
         a.g_depth, a.g_weights, a.g_focal, a.g_k4 = P(self._g_depth), P(self._g_w), \
             P(self._g_focal), P(self._g_k4)
         a.rt, a.loss, a.ws = P(self.rt), P(self._loss), P(self._ws)
+        # step-dependent scalars live in device memory: every step is the same launch sequence
+        self._clock = ops.StepClock(dev, cfg.lr)
+        a.clock = self._clock.ptr
+        self._total = torch.zeros((), device=dev)
+        self._idx_buf = torch.empty(min(cfg.softmin_points, h * w), dtype=torch.int64, device=dev) \
+            if self._softmin else None
+        self.use_cuda_graph = False  # opt-in: replay the update step as ONE CUDA graph launch
+        self._graphs, self._eager_runs = {}, {}
         self._set_plan_args(a)
         self._packed = None
         if cfg.use_tracking:
@@ -258,6 +266,8 @@ class FusedOverfitter(Overfitter):
         if self._plan is not None:  # new backward flows: new transpose
             self._plan.rebuild(flows.backward)
             self._set_plan_args(a)
+        self._graphs.clear()  # captured launches hold the old pointers
+        self._eager_runs.clear()
 
     def _mask_sum(self, flows: Flows) -> Tensor:
         return ops.mask_sum(flows.forward_mask, flows.backward_mask)
@@ -278,7 +288,10 @@ class FusedOverfitter(Overfitter):
         P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         idx = self.injected_indices
         if idx is None:
-            idx = ops.random_subset(h * w, min(c.softmin_points, h * w), dev)
+            if update:  # seeded by the step clock (replayable); intrinsics_softmin.py:90
+                idx = ops.random_subset_clock(self._clock, h * w, self._idx_buf)
+            else:
+                idx = ops.random_subset(h * w, min(c.softmin_points, h * w), dev)
         idx = idx.contiguous()
         n = c.softmin_candidates
         wl = P(self._wlog) if c.use_correspondence_weights else None
@@ -294,7 +307,7 @@ class FusedOverfitter(Overfitter):
             # gradient is final there); depth and pair 0 wait for the sweep's backward
             fuse = update and c.use_correspondence_weights and self._indices is None and w % 4 == 0
             a.focal = P(self._sw_focal)
-            a.step = self.optimizer_steps + 1 if fuse else 0
+            a.step = 1 if fuse else 0  # on / off: the bias corrections come from the step clock
             a.defer_adam = 1 if fuse else 0
             check(L.fm_overfit_step(self._ctypes.byref(a), st), "fm_overfit_step")
             a.defer_adam = 0
@@ -307,15 +320,11 @@ class FusedOverfitter(Overfitter):
                                          P(self._g_w) if wl else None, P(self._sw_ws), 1, f, h, w, st),
                   "fm_softmin_sweep_bwd")
         if update:
-            s_ = self.optimizer_steps + 1
-            ops.adam_step(self._depth, self._g_depth, self._state[0], self._state[1], s_, c.lr)
+            ops.adam_step_clock(self._depth, self._g_depth, self._state[0], self._state[1], self._clock)
             if c.use_correspondence_weights:
                 k = 1 if fuse else self._wlog.shape[0]  # pair 0 only when the rest was fused
-                ops.adam_step(self._wlog[:k], self._g_w[:k], self._state[2][:k], self._state[3][:k],
-                              s_, c.lr)
-            if c.regression_after is not None and \
-                    self.global_step >= c.regression_after - c.regression_window:
-                self.window.append(self._sw_focal[0].clone())
+                ops.adam_step_clock(self._wlog[:k], self._g_w[:k], self._state[2][:k], self._state[3][:k],
+                                    self._clock)
 
     # ---- split step: the two halves of one iteration WITHOUT the parameter update, for callers that
     # need the loss values before they decide on the backward (torch.autograd: flowmap_b200.fused)
@@ -422,9 +431,51 @@ class FusedOverfitter(Overfitter):
                                              P(self._g_w) if wl else None, P(self._sw_ws), 1, f, h, w, st),
                       "fm_softmin_sweep_bwd")
 
+    def _step_body(self, update: bool, track_on: bool, sweep: bool):
+        """One step as a fixed launch sequence (no host-side step numbers: see ops.StepClock)."""
+        from ._lib import check
+        c, a = self.cfg, self._args
+        if update:
+            self._clock.tick(tick_focal=not sweep)
+        a.tracks = self._ctypes.pointer(self._pk_c) if track_on else None
+        a.flow_weight = c.flow_weight if self.global_step >= c.flow_enable_after else 0.0
+        if sweep:
+            self._step_softmin(update)
+        else:
+            a.focal = self._focal.data_ptr()
+            a.step = a.focal_step = 1 if update else 0  # on / off: the step clock carries the counts
+            with torch.cuda.device(self.rt.device):
+                check(self._lib.fm_overfit_step(self._ctypes.byref(a),
+                                                torch.cuda.current_stream().cuda_stream),
+                      "fm_overfit_step")
+        if track_on:
+            torch.add(self._loss, self._track_loss, out=self._total)
+        else:
+            self._total.copy_(self._loss)
+
+    def _run_body(self, key, graphable: bool, body, ticks_focal: bool):
+        """Run one step body: eagerly, or -- from its third run on -- as a replay of its CUDA graph
+        (the body must tick the step clock first and be a fixed launch sequence)."""
+        if graphable and self._eager_runs.get(key, 0) >= 2:
+            g = self._graphs.get(key)
+            if g is None:  # capture records the launches without running them: replayed right below
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    body()
+                self._graphs[key] = g
+                self._clock.steps -= 1  # the capture's host-side tick was not executed
+                self._clock.focal_steps -= int(ticks_focal)
+            g.replay()
+            self._clock.steps += 1
+            self._clock.focal_steps += int(ticks_focal)
+        else:
+            body()
+            if graphable:
+                self._eager_runs[key] = self._eager_runs.get(key, 0) + 1
+
     def training_step(self, update: bool = True):
         """Returns (total loss (device tensor), relative poses rt (1, F-1, 3, 4))."""
-        from ._lib import check
         c, a = self.cfg, self._args
         if c.procrustes_randomize:
             _, _, _, h, w = self.batch.videos.shape
@@ -432,27 +483,24 @@ class FusedOverfitter(Overfitter):
         a.indices = None if self._indices is None else self._indices.data_ptr()
         a.num_indices = 0 if self._indices is None else self._indices.numel()
         track_on = c.use_tracking and self.global_step >= c.tracking_enable_after
-        a.tracks = self._ctypes.pointer(self._pk_c) if track_on else None
-        a.flow_weight = c.flow_weight if self.global_step >= c.flow_enable_after else 0.0
-        if self._softmin_stage():
-            self._step_softmin(update)
-        else:
-            a.focal = self._focal.data_ptr()
-            a.step = self.optimizer_steps + 1 if update else 0
-            if self._softmin and self.global_step == c.regression_after and update:
-                self._focal.copy_(torch.stack(self.window).mean())  # hand-over: seed the regressed focal length once
-            a.focal_step = self.focal_steps + 1 if update else 0  # the focal length's own Adam clock
-            if update:
-                self.focal_steps += 1
-            with torch.cuda.device(self.rt.device):
-                check(self._lib.fm_overfit_step(self._ctypes.byref(a),
-                                                torch.cuda.current_stream().cuda_stream),
-                      "fm_overfit_step")
+        sweep = self._softmin_stage()
         if update:
+            self._clock.set(self.optimizer_steps, self.focal_steps)
+            if self._softmin and not sweep and self.global_step == c.regression_after:
+                self._focal.copy_(torch.stack(self.window).mean())  # hand-over: seed the regressed focal length once
+        window_on = sweep and c.regression_after is not None and \
+            self.global_step >= c.regression_after - c.regression_window
+        key = (track_on, sweep, self.global_step >= c.flow_enable_after)
+        graphable = (update and self.use_cuda_graph and not c.procrustes_randomize and not window_on and
+                     getattr(self, "injected_indices", None) is None)
+        self._run_body(key, graphable, lambda upd=update: self._step_body(upd, track_on, sweep), not sweep)
+        if update:
+            if window_on:
+                self.window.append(self._sw_focal[0].clone())
             self.global_step += 1
             self.optimizer_steps += 1
-        total = self._loss + self._track_loss if track_on else self._loss.clone()
-        return total, self.rt
+            self.focal_steps += int(not sweep)
+        return self._total.clone(), self.rt
 
     def extrinsics(self) -> Tensor:
         """Camera-to-world poses of the last step (projection.py:187-210)."""
@@ -493,6 +541,7 @@ class ShardedFusedOverfitter(FusedOverfitter):
         super().__init__(replace(cfg, use_tracking=False), batch, flows, None, device)
         self.cfg = cfg
         self.plan, self.group = plan, group
+        self._args.clock = None  # this driver passes Adam's step numbers by value
         _, f_local, _, h, w = batch.videos.shape
         if f_local != plan.num_local_frames:
             raise ValueError("flowmap_b200: batch does not match the shard plan")
@@ -569,10 +618,57 @@ class ShardedFusedOverfitter(FusedOverfitter):
         return (self._tg_k4_all[:, 0].double().sum() * (scale / w) +
                 self._tg_k4_all[:, 1].double().sum() * (scale / h)).float()
 
+    def _flow_only_body(self):
+        """Flow loss with a regressed focal length, update step, as a fixed launch sequence: the step
+        (weight-logit Adam fused in), the exchange started, Adam on the interior depth frames WHILE the
+        boundary frames and the two scalars travel, then the boundary frames and the focal length."""
+        from ._lib import check
+        c, a, p, r = self.cfg, self._args, self.plan, self.reducer
+        P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        clk = self._clock
+        clk.tick(tick_focal=True)
+        a.clock, a.tracks, a.step, a.focal_step, a.defer_adam, a.phase = clk.ptr, None, 1, 1, 2, 0
+        a.focal = P(self._focal)
+        try:
+            with torch.cuda.device(self.rt.device):
+                check(self._lib.fm_overfit_step(self._ctypes.byref(a), torch.cuda.current_stream().cuda_stream),
+                      "fm_overfit_step")
+        finally:
+            a.clock, a.step, a.focal_step, a.defer_adam = None, 0, 0, 0
+        r.scal[0].copy_(self._loss.reshape(()))
+        r.scal[1].copy_(self._g_focal.reshape(()))
+        reqs = r.start(self._g_depth)
+        stt, n = self._state, self._depth.shape[0]
+        lo, hi = int(p.has_left and p.world > 1), n - int(p.has_right and p.world > 1)
+        if hi > lo:
+            ops.adam_step_clock(self._depth[lo:hi], self._g_depth[lo:hi], stt[0][lo:hi], stt[1][lo:hi], clk)
+        red = r.finish(reqs, self._g_depth)
+        if lo > 0:
+            ops.adam_step_clock(self._depth[:1], self._g_depth[:1], stt[0][:1], stt[1][:1], clk)
+        if hi < n:
+            ops.adam_step_clock(self._depth[n - 1:], self._g_depth[n - 1:], stt[0][n - 1:], stt[1][n - 1:], clk)
+        self._g_focal.copy_(red[1])
+        ops.adam_step_clock(self._focal.reshape(1), self._g_focal.reshape(1), stt[4].reshape(1),
+                            stt[5].reshape(1), clk, focal_clock=True)
+        self._total.copy_(red[0])
+
     def training_step(self, update: bool = True):
         import torch.distributed as dist
         from ._lib import check
         c, a, p, L = self.cfg, self._args, self.plan, self._lib
+        _, _, _, h_, w_ = self.batch.videos.shape
+        if (update and not self._softmin and not c.procrustes_randomize and self._indices is None and
+                c.use_correspondence_weights and w_ % 4 == 0 and
+                not (c.use_tracking and self.global_step >= c.tracking_enable_after)):
+            a.indices, a.num_indices = None, 0
+            a.flow_weight = c.flow_weight if self.global_step >= c.flow_enable_after else 0.0
+            self._clock.set(self.optimizer_steps, self.focal_steps)
+            self._run_body(("flow", self.global_step >= c.flow_enable_after), self.use_cuda_graph,
+                           self._flow_only_body, True)
+            self.global_step += 1
+            self.optimizer_steps += 1
+            self.focal_steps += 1
+            return self._total.clone(), self.rt
         _, _, _, h, w = self.batch.videos.shape
         P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         st = torch.cuda.current_stream().cuda_stream

@@ -169,6 +169,41 @@ class StepReducer:
             depth_grad[-1].add_(self.from_right)
         return self.scal.clone()
 
+    # ---- the same exchange in two halves, so that work that does not depend on it (Adam on the
+    # interior frames) runs between them while the boundary frames travel over NVLink
+    @torch.no_grad()
+    def start(self, depth_grad: Tensor):
+        """Begin the exchange of `self.scal` (filled by the caller) and the boundary frames of
+        depth_grad; returns the pending requests for finish()."""
+        p = self.plan
+        if p.world == 1:
+            return []
+        ops = []
+        if p.has_left:
+            self.to_left.copy_(depth_grad[0])
+            ops += [dist.P2POp(dist.isend, self.to_left, self._peer(-1), self.group),
+                    dist.P2POp(dist.irecv, self.from_left, self._peer(-1), self.group)]
+        if p.has_right:
+            self.to_right.copy_(depth_grad[-1])
+            ops += [dist.P2POp(dist.isend, self.to_right, self._peer(+1), self.group),
+                    dist.P2POp(dist.irecv, self.from_right, self._peer(+1), self.group)]
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        reqs.append(dist.all_reduce(self.scal, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        return reqs
+
+    @torch.no_grad()
+    def finish(self, reqs, depth_grad: Tensor) -> Tensor:
+        """Wait for start()'s requests and add the neighbours' boundary partials (both owners end up
+        with the same sum).  Returns self.scal (globally summed, a persistent buffer)."""
+        for r in reqs:
+            r.wait()
+        if self.plan.world > 1:
+            if self.plan.has_left:
+                depth_grad[0].add_(self.from_left)
+            if self.plan.has_right:
+                depth_grad[-1].add_(self.from_right)
+        return self.scal
+
     def bytes_per_step(self) -> int:
         """Bytes this rank sends per step (scalars + one frame per neighbour)."""
         return 4 * self.nscal + 4 * self.h * self.w * (int(self.plan.has_left) + int(self.plan.has_right))

@@ -224,6 +224,19 @@ int fm_track_loss_bwd_sharded(const float* depth, const float* k4, const float* 
 int fm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count,
                  double lr, double beta1, double beta2, double eps, int step, void* stream);
 
+/* ---- step clock: the step-dependent scalars in device memory (CUDA-graph capture of whole steps) --
+ * FM_STEP_CLOCK_BYTES of zero-initialised device memory = {u32 step, u32 focal_step, f32 step_size,
+ * bc2_sqrt, focal_step_size, focal_bc2_sqrt, u64 seed}.  fm_step_clock_tick advances `step` (and
+ * `focal_step` when tick_focal != 0) by one and refreshes torch.optim.Adam's bias-correction scalars
+ * lr / (1 - beta1^t), sqrt(1 - beta2^t) (model_wrapper_overfit.py:104-105) and a per-step seed
+ * (splitmix64 of base_seed and step) for fm_random_subset_clock (intrinsics_softmin.py:90). */
+#define FM_STEP_CLOCK_BYTES 32
+int fm_step_clock_tick(void* clock, double lr, double beta1, double beta2, unsigned long long base_seed,
+                       int tick_focal, void* stream);
+int fm_adam_step_clock(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count,
+                       const void* clock, int focal_clock, double beta1, double beta2, double eps, void* stream);
+int fm_random_subset_clock(const void* clock, long long N, int n, int64_t* out, void* stream);
+
 /* intrinsics_softmin.py:84-131, the candidate sweep on the first frame pair.  For each of
  * the num_candidates intrinsics in cand_k4 (B*num_candidates, 2, 4: one k4 row per virtual
  * frame) run Procrustes at the `indices` points (depth frames 0/1, backward flow and weights
@@ -320,6 +333,10 @@ typedef struct {
   unsigned splat_overflow_max;  /* overflow_max of fm_splat_plan_info */
   const float* flow_grad_scale;  /* FM_STEP_BACKWARD only: device scalars d total / d flow loss and     */
   const float* track_grad_scale; /* d total / d tracking loss (autograd's grad_output), or NULL (= 1) */
+  const void* clock;             /* device step clock (fm_step_clock_tick) or NULL.  With a clock the Adam
+                                    bias corrections come from it instead of `step` / `focal_step`
+                                    (which then only switch the update on), so that consecutive steps
+                                    are launches with identical arguments: a CUDA graph can replay them */
 } fm_overfit_step_args;
 #define FM_STEP_ALL 0
 #define FM_STEP_FORWARD 1

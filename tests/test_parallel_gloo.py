@@ -58,6 +58,15 @@ def _worker(rank, world, port, f, h, w, out_dir):
         red = parallel.StepReducer(plan, (h, w), "cpu", 2)
         g_depth = st.depth.grad.float().clone()
         scal = red.reduce(torch.stack((loss.detach().float(), st.focal.grad.float())), g_depth)
+        # the same exchange in its two halves (start ... independent work ... finish)
+        red2 = parallel.StepReducer(plan, (h, w), "cpu", 2)
+        g_depth2 = st.depth.grad.float().clone()
+        red2.scal.copy_(torch.stack((loss.detach().float(), st.focal.grad.float())))
+        reqs = red2.start(g_depth2)
+        interior_untouched = g_depth2[1:-1].clone()
+        scal2 = red2.finish(reqs, g_depth2)
+        assert torch.equal(scal2, scal) and torch.equal(g_depth2, g_depth)
+        assert torch.equal(g_depth2[1:-1], interior_untouched)
         torch.save({"range": plan.pair_range, "g_depth": g_depth, "g_w": st.weights.grad.float(),
                     "scalars": scal, "bytes": red.bytes_per_step()}, f"{out_dir}/r{rank}.pt")
     finally:

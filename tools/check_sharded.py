@@ -60,10 +60,13 @@ CASES = {
                                                               intrinsics="softmin", softmin_points=512,
                                                               regression_after=3, regression_window=2),
 }
+CASES["flow only, regressed focal, replayed as a CUDA graph (exchange captured)"] = OverfitCfg(lr=1e-3)
 for name, cfg in CASES.items():
-    steps = 5 if cfg.intrinsics == "softmin" else STEPS
+    graph = "CUDA graph" in name
+    steps = 6 if graph else (5 if cfg.intrinsics == "softmin" else STEPS)
     trk = tracks if cfg.use_tracking else None
     sh = make(ShardedFusedOverfitter, cfg, d_l, w_l, fl_l, plan, tracks=trk)
+    sh.use_cuda_graph = graph
     losses = [float(sh.training_step()[0]) for _ in range(steps)]
     full = make(FusedOverfitter, cfg, depth, wparam, flows, trk)
     ref_losses = [float(full.training_step()[0]) for _ in range(steps)]
@@ -76,5 +79,9 @@ for name, cfg in CASES.items():
     print(f"[{name}] rank {rank}/{world} pairs {plan.pair_range}: loss rel err {e_l:.2e}, depth {e_d:.2e}, "
           f"weight-update {e_w:.2e}, focal {e_f:.2e}, collective {sh.reducer.bytes_per_step()} B/step", flush=True)
     assert e_l < 1e-4 and e_d < 1e-5 and e_w < 2e-2 and e_f < 1e-5, name
+    assert not graph or len(sh._graphs) == 1, "the step was not captured"
+    sh._graphs.clear()  # a graph that captured NCCL kernels must go before the communicator does
+    del sh, full
+    torch.cuda.synchronize()
     dist.barrier()
 dist.destroy_process_group()
