@@ -327,8 +327,8 @@ NCU_SUMMARY = ROOT / "profiles" / "r2_path_ncu_summary.txt"  # tools/ncu_summary
 
 def ncu_traffic_from_profiles(path=NCU_SUMMARY):
     """{op: dram bytes per launch} for the three pixel kernels from the committed ncu summary."""
-    names = {"k_moments": "procrustes_fwd(k_moments)", "k_flow_lean": "flow_loss_fwd_bwd(k_flow_lean)",
-             "k_distribute": "procrustes_bwd(k_distribute)"}
+    names = {"k_moments_dense": "procrustes_fwd(k_moments)", "k_flow_lean": "flow_loss_fwd_bwd(k_flow_lean)",
+             "k_distribute_dense": "procrustes_bwd(k_distribute)"}
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     out, cur = {}, None
     if not Path(path).exists():
