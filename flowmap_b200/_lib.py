@@ -113,6 +113,16 @@ class FlowmapLibraryError(RuntimeError):
     pass
 
 
+def load_library(path) -> ctypes.CDLL:
+    """dlopen one build of the library and type every entry point of include/flowmap_b200.h."""
+    handle = ctypes.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return handle
+
+
 def lib() -> ctypes.CDLL:
     """Load (once) and return the shared library; raises if it has not been built."""
     global _lib
@@ -121,12 +131,7 @@ def lib() -> ctypes.CDLL:
             raise FlowmapLibraryError(
                 f"{SO_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
                 "g.build()'` (nvcc, sm_100a).  flowmap_b200 has no CPU or PyTorch fallback.")
-        handle = ctypes.CDLL(str(SO_PATH))
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(handle, name)  # AttributeError if the symbol is missing
-            fn.restype = res
-            fn.argtypes = args
-        _lib = handle
+        _lib = load_library(SO_PATH)
     return _lib
 
 
