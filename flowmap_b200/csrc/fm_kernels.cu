@@ -208,6 +208,10 @@ __device__ __forceinline__ unsigned opaque_u32(unsigned v) {
   return v;
 }
 
+// Software prefetch into L2 (no register, no scoreboard): streaming operands are requested a couple
+// of chunks ahead so that the demand loads find them on chip.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // Load the 4 (or 1) values a thread owns.
 template <int VEC>
 __device__ __forceinline__ void load_vec(const float* p, float* out) {
@@ -243,6 +247,32 @@ __device__ __forceinline__ ItemRange block_item_range(long long total) {
   if (i1 > total) i1 = total;
   ItemRange r; r.i0 = (int)i0; r.i1 = (int)i1;
   return r;
+}
+
+// Thread -> pixel mapping inside a chunk of kThreads * 4 pixels of the dense Procrustes kernels; a
+// thread always owns 4 consecutive pixels of a row (128-bit streaming loads / stores).
+//   LX == 0 (strip): a warp is a 128-pixel strip of one row (linear order).
+//   LX  > 0 (patch): a chunk is 8 warp tiles of (4 LX) x (32 / LX) pixels: LX lanes side by side,
+//                    32 / LX rows.  The flow-displaced taps of one gather / RED instruction then fall
+//                    into fewer distinct 128-byte lines.  Needs W % (4 LX) == 0 and H % (32 / LX) == 0.
+template <int LX>
+struct PatchSite {
+  int base;     // linear index of the thread's first pixel
+  int r, c0;    // its row / column
+  bool inside;  // the warp tile exists (the last chunk of a frame may be partial)
+};
+template <int LX>
+__device__ __forceinline__ PatchSite<LX> patch_site(int chunk, int W, int tiles_x, int tiles) {
+  constexpr int kRows = 32 / LX;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wt = chunk * (kThreads / 32) + warp;
+  const int band = wt / tiles_x, tx = wt - band * tiles_x;
+  PatchSite<LX> s;
+  s.inside = wt < tiles;
+  s.r = band * kRows + lane / LX;
+  s.c0 = tx * (4 * LX) + 4 * (lane % LX);
+  s.base = s.r * W + s.c0;
+  return s;
 }
 
 // ================================================================== phase A: moments
@@ -322,7 +352,7 @@ k_moments(const float* __restrict__ depth, const float* __restrict__ k4,
   block_accumulate<kNumMoments>(acc, moments + (size_t)pair * kNumMoments, smem);
 }
 
-template <int VEC>
+template <int VEC, int LX>
 __global__ void __launch_bounds__(kThreads, 3)
 k_moments_dense(const float* __restrict__ depth, const float* __restrict__ k4,
                 const float* __restrict__ bflow, const float* __restrict__ weights,
@@ -333,6 +363,7 @@ k_moments_dense(const float* __restrict__ depth, const float* __restrict__ k4,
   const int chunks = (N + kChunk - 1) / kChunk;
   const ItemRange range = block_item_range((long long)BP * chunks);
   const int dr = kChunk / W, dc = kChunk - dr * W;
+  const int tiles_x = LX > 0 ? W / (4 * LX) : 1, tiles = N / 128;
 #pragma unroll 1
   for (int i = range.i0; i < range.i1;) {
     const int pair = i / chunks, cb = i - pair * chunks;
@@ -351,7 +382,12 @@ k_moments_dense(const float* __restrict__ depth, const float* __restrict__ k4,
     int r = base / W, c0 = base - r * W;
 #pragma unroll 1
     for (int c = cb; c < ce; ++c, base += kChunk) {
-      if (base < N) {
+      bool inside = base < N;
+      if constexpr (LX > 0) {
+        const PatchSite<LX> ps = patch_site<LX>(c, W, tiles_x, tiles);
+        base = ps.base; r = ps.r; c0 = ps.c0; inside = ps.inside;
+      }
+      if (inside) {
         float dv[VEC], wv[VEC], fv[2 * VEC];
         load_vec<VEC>(db + base, dv);
         load_vec2<VEC>(fl + 2 * base, fv);
@@ -485,6 +521,9 @@ k_flow(const float* __restrict__ depth, const float* __restrict__ k4, const floa
   block_accumulate<kFlowVals>(acc, flowacc + (size_t)frame * kFlowAcc, smem);
 }
 
+// Chunks ahead whose streaming operands k_flow_lean requests into L2 (measured on B200: 0.274 ms
+// without, 0.255 / 0.253 / 0.261 / 0.307 ms at distance 1 / 2 / 4 / 8).
+constexpr int kFlowPrefetchChunks = 2;
 // Lean phase C (constant intrinsics or one shared focal length): see fm_pixel.cuh.  The vector
 // instantiation processes its 4 pixels as two packed float32x2 pairs (FFMA2 / FMUL2 / FADD2).
 template <int VEC, bool HASF, bool HASB, bool FOCAL>
@@ -511,6 +550,14 @@ __device__ __forceinline__ void flow_frame_body_lean(const FlowFrameLean& f, con
     load_vec<VEC>(D + base, dv);
     if (HASF) { load_vec2<VEC>(ff + 2 * base, ffv); load_vec<VEC>(mf + base, mfv); }
     if (HASB) { load_vec2<VEC>(fb + 2 * base, fbv); load_vec<VEC>(mb + base, mbv); }
+    {
+      const int pb = base + kFlowPrefetchChunks * stride;
+      if (pb < N) {
+        prefetch_l2(D + pb);
+        if (HASF) { prefetch_l2(ff + 2 * pb); prefetch_l2(mf + pb); }
+        if (HASB) { prefetch_l2(fb + 2 * pb); prefetch_l2(mb + pb); }
+      }
+    }
     const float y = pix_coord(r, grid.Hf, grid.invH);
     if (VEC == 4) {
 #pragma unroll
@@ -762,7 +809,7 @@ k_distribute(const float* __restrict__ depth, const float* __restrict__ k4,
 
 // Dense (all-pixel) phase D2 on the item decomposition of block_item_range: same per-pixel work as
 // k_distribute's dense branch, per-pair constants re-staged when a block moves on to its next pair.
-template <int VEC>
+template <int VEC, int LX>
 __global__ void __launch_bounds__(kThreads, 3)
 k_distribute_dense(const float* __restrict__ depth, const float* __restrict__ k4,
                    const float* __restrict__ bflow, float* weights, const PairAdjoint* __restrict__ adj,
@@ -775,6 +822,7 @@ k_distribute_dense(const float* __restrict__ depth, const float* __restrict__ k4
   const int chunks = (N + kChunk - 1) / kChunk;
   const ItemRange range = block_item_range((long long)BP * chunks);
   const int dr = kChunk / W, dc = kChunk - dr * W;
+  const int tiles_x = LX > 0 ? W / (4 * LX) : 1, tiles = N / 128;
   if (adam.on && adam.consts) { adam.step_size = __ldg(adam.consts); adam.bc2_sqrt = __ldg(adam.consts + 1); }
 #pragma unroll 1
   for (int i = range.i0; i < range.i1;) {
@@ -797,6 +845,7 @@ k_distribute_dense(const float* __restrict__ depth, const float* __restrict__ k4
     auto scatter = [gda, W](int y0, int x0, float v0, float v1) { red_pair<VEC == 4>(gda + y0 * W, x0, W, v0, v1); };
     float* gdb = gda + N;
     float* gw = g_weights ? g_weights + pa.weight : nullptr;
+    const bool fuse_adam = VEC == 4 && adam.on && pair >= adam.first_pair;
     float kacc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) kacc[k] = 0.f;
@@ -804,7 +853,12 @@ k_distribute_dense(const float* __restrict__ depth, const float* __restrict__ k4
     int r = base / W, c0 = base - r * W;
 #pragma unroll 1
     for (int c = cb; c < ce; ++c, base += kChunk) {
-      if (base < N) {
+      bool inside = base < N;
+      if constexpr (LX > 0) {
+        const PatchSite<LX> ps = patch_site<LX>(c, W, tiles_x, tiles);
+        base = ps.base; r = ps.r; c0 = ps.c0; inside = ps.inside;
+      }
+      if (inside) {
         float dv[VEC], wv[VEC], wraw[VEC], fv[2 * VEC], gwv[VEC], gdv[VEC];
         load_vec<VEC>(db + base, dv);
         load_vec2<VEC>(fl + 2 * base, fv);
@@ -837,7 +891,7 @@ k_distribute_dense(const float* __restrict__ depth, const float* __restrict__ k4
             if (VEC == 4) *reinterpret_cast<float4*>(gw + base) = make_float4(gwv[0], gwv[1], gwv[2], gwv[3]);
             else gw[base] = gwv[0];
           }
-          if (VEC == 4 && adam.on && pair >= adam.first_pair) {  // torch.optim.Adam on the logits (k_adam's order)
+          if (fuse_adam) {  // torch.optim.Adam on the logits (k_adam's order)
             float4 mm = *reinterpret_cast<float4*>(adam.m + pa.weight + base);
             float4 vv = *reinterpret_cast<float4*>(adam.v + pa.weight + base);
             float* mp = &mm.x; float* vp = &vv.x;
@@ -1920,6 +1974,12 @@ int blocks_for(int n_items_per_row, int vec) {
   return nb < 1 ? 1 : nb;
 }
 
+// Lanes per row of the warp patch of the dense Procrustes kernels (PatchSite).  Measured on B200 at
+// 150 x 360 x 640, iid flows, fwd / bwd op in ms: strips 0.231 / 0.592, 4 lanes x 8 rows 0.222 / 0.611,
+// 8 x 4 0.227 / 0.564, 16 x 2 0.224 / 0.590 (profiles/README.md).
+constexpr int kPatchLanes = 8;
+static bool patch_shape_ok(int H, int W) { return W % (4 * kPatchLanes) == 0 && H % (32 / kPatchLanes) == 0; }
+
 // 1-D grid of the dense kernels (block_item_range): every SM holds `ctas_per_sm` blocks for the whole
 // launch.
 int sm_count_cached() {
@@ -2160,12 +2220,15 @@ static int procrustes_fwd_impl(const float* depth, const float* k4, const float*
   } else if (indices) {
     dim3 grid(blocks_for_points(num_indices), BP);
     k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.moments, wsens, lay, H, W);
+  } else if (patch_shape_ok(H, W)) {
+    const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4)));
+    k_moments_dense<4, kPatchLanes><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP);
   } else if (W % 4 == 0) {
     const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4)));
-    k_moments_dense<4><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP);
+    k_moments_dense<4, 0><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP);
   } else {
     const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads - 1) / kThreads));
-    k_moments_dense<1><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP);
+    k_moments_dense<1, 0><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP);
   }
   if (!plan) FM_CHECK_LAUNCH("fm_procrustes_fwd: k_moments");
   k_solve<<<(BP + 63) / 64, 64, 0, s>>>(w.moments, depth, rt, w.state, BP, lay, H, W);
@@ -2225,12 +2288,15 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
   if (indices) {
     dim3 grid(blocks_for_points(num_indices), BP);
     k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
+  } else if (patch_shape_ok(H, W)) {
+    const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4)));
+    k_distribute_dense<4, kPatchLanes><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W, BP);
   } else if (W % 4 == 0) {
     const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4)));
-    k_distribute_dense<4><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W, BP);
+    k_distribute_dense<4, 0><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W, BP);
   } else {
     const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads - 1) / kThreads));
-    k_distribute_dense<1><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W, BP);
+    k_distribute_dense<1, 0><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W, BP);
   }
   FM_CHECK_LAUNCH("fm_procrustes_bwd: k_distribute");
   k_k4_finalize<<<(BF + 127) / 128, 128, 0, s>>>(w.k4acc, w.flowacc, include_flow_loss, flow_scale, g_k4, B, F);
@@ -2505,6 +2571,30 @@ int fm_track_loss_value(const void* ws, float loss_weight, float* loss, void* st
   return 0;
 }
 
+// The depth scatter of the tracking loss (k_track_apply, REDs into g_depth) and the pose / intrinsics
+// gradients (k_track_finalize) are independent: `apply_stream` may differ from `s`.
+static int track_bwd_impl(const float* k4, const float* extrinsics, const int* segments, int num_segments,
+                          int max_rows, int max_points, const float* track_xy, long long total_samples,
+                          float loss_weight, const float* grad_out, float* g_depth, float* g_extrinsics,
+                          float* g_k4, void* ws, int F, int H, int W, int depth_frame0, int src_frame_lo,
+                          int src_frame_hi, cudaStream_t s, cudaStream_t apply_stream) {
+  if (!k4 || !extrinsics || !segments || !track_xy || !g_depth || !g_extrinsics || !g_k4 || !ws ||
+      num_segments < 1 || max_rows < 1 || max_points < 1 || F < 1)
+    return fail_msg("fm_track_loss_bwd: bad arguments");
+  if (depth_frame0 < 0 || src_frame_lo < depth_frame0 || src_frame_hi > F || src_frame_lo > src_frame_hi)
+    return fail_msg("fm_track_loss_bwd: bad source-frame range");
+  TrackWs w = carve_track(ws, F, total_samples);
+  dim3 grid((max_points + kThreads - 1) / kThreads, max_rows, num_segments);
+  const TrackShard sh = {depth_frame0, src_frame_lo, src_frame_hi};
+  k_track_apply<<<grid, kThreads, 0, apply_stream>>>(k4, segments, track_xy, w.flag, w.dq, w.sums, loss_weight,
+                                                    grad_out, g_depth, H, W, sh);
+  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_apply");
+  k_track_finalize<<<(F + 63) / 64, 64, 0, s>>>(w.acc, w.sums, loss_weight, grad_out, extrinsics, g_extrinsics,
+                                               g_k4, F);
+  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_finalize");
+  return 0;
+}
+
 int fm_track_loss_bwd_sharded(const float* depth, const float* k4, const float* extrinsics, const int* segments,
                               int num_segments, int max_rows, int max_points, const float* track_xy,
                               const unsigned char* track_vis, long long total_samples, int mapping, float delta,
@@ -2512,22 +2602,9 @@ int fm_track_loss_bwd_sharded(const float* depth, const float* k4, const float* 
                               float* g_k4, void* ws, int F, int H, int W, int depth_frame0, int src_frame_lo,
                               int src_frame_hi, void* stream) {
   (void)depth; (void)track_vis; (void)mapping; (void)delta;
-  if (!k4 || !extrinsics || !segments || !track_xy || !g_depth || !g_extrinsics || !g_k4 || !ws ||
-      num_segments < 1 || max_rows < 1 || max_points < 1 || F < 1)
-    return fail_msg("fm_track_loss_bwd: bad arguments");
-  if (depth_frame0 < 0 || src_frame_lo < depth_frame0 || src_frame_hi > F || src_frame_lo > src_frame_hi)
-    return fail_msg("fm_track_loss_bwd: bad source-frame range");
-  cudaStream_t s = (cudaStream_t)stream;
-  TrackWs w = carve_track(ws, F, total_samples);
-  dim3 grid((max_points + kThreads - 1) / kThreads, max_rows, num_segments);
-  const TrackShard sh = {depth_frame0, src_frame_lo, src_frame_hi};
-  k_track_apply<<<grid, kThreads, 0, s>>>(k4, segments, track_xy, w.flag, w.dq, w.sums, loss_weight, grad_out,
-                                         g_depth, H, W, sh);
-  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_apply");
-  k_track_finalize<<<(F + 63) / 64, 64, 0, s>>>(w.acc, w.sums, loss_weight, grad_out, extrinsics, g_extrinsics,
-                                               g_k4, F);
-  FM_CHECK_LAUNCH("fm_track_loss_bwd: k_track_finalize");
-  return 0;
+  return track_bwd_impl(k4, extrinsics, segments, num_segments, max_rows, max_points, track_xy, total_samples,
+                        loss_weight, grad_out, g_depth, g_extrinsics, g_k4, ws, F, H, W, depth_frame0,
+                        src_frame_lo, src_frame_hi, (cudaStream_t)stream, (cudaStream_t)stream);
 }
 
 int fm_track_loss_bwd(const float* depth, const float* k4, const float* extrinsics, const int* segments,
@@ -2725,6 +2802,25 @@ int fm_softmin_focal_bwd(const float* softmin, const float* cand_focal, const fl
   return 0;
 }
 
+// A second stream (per device) for work that only has to be finished when the step ends: forked
+// from / joined to the caller's stream with events, so it is captured into the caller's CUDA graph as
+// a parallel branch.
+struct SideLane { cudaStream_t stream; cudaEvent_t fork, join; int state; };  // state 0 new, 1 ready, -1 unavailable
+static SideLane* side_lane() {
+  static SideLane lanes[64];
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideLane& l = lanes[dev];
+  if (l.state == 0) {
+    const bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) == cudaSuccess;
+    l.state = ok ? 1 : -1;
+    if (!ok) (void)cudaGetLastError();
+  }
+  return l.state == 1 ? &l : nullptr;
+}
+
 int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
   if (!a || !a->depth || !a->fflow || !a->bflow || !a->fmask || !a->bmask || !a->mask_sum ||
       !a->g_depth || !a->rt || !a->loss || !a->ws || !a->k4 || bad_dims(1, a->F, a->H, a->W))
@@ -2752,6 +2848,15 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
     if ((rc = procrustes_fwd_impl(a->depth, k4, a->bflow, a->weight_logits, a->weight_sensitivity,
                                   a->indices, a->num_indices, a->rt, a->ws, 1, F, H, W, stream, nullptr, plan)))
       return rc;
+    // The flow loss and the tracking sweep both need only the poses: with tracking on they run as
+    // two branches of the step (the tracking sweep is issue-bound, the flow kernel waits on memory:
+    // where blocks of both share an SM they fill each other's idle slots; measured 1.889 -> 1.846 ms per
+    // full step on B200, limiting the flow kernel to one block per SM to force the sharing 1.922).
+    SideLane* fwd_lane = a->tracks ? side_lane() : nullptr;
+    if (fwd_lane) {
+      if ((e = cudaEventRecord(fwd_lane->fork, s)) != cudaSuccess) return fail("fm_overfit_step: fork", e);
+      if ((e = cudaStreamWaitEvent(fwd_lane->stream, fwd_lane->fork, 0)) != cudaSuccess) return fail("fm_overfit_step: fork", e);
+    }
     // LossFlow forward + direct gradients (loss_flow.py:31-70)
     e = cudaMemsetAsync(w.flowacc, 0, (size_t)F * kFlowAcc * sizeof(double), s);
     if (e != cudaSuccess) return fail("fm_overfit_step: memset", e);
@@ -2761,18 +2866,22 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
       return rc;
     k_flow_finalize<<<(F + 127) / 128, 128, 0, s>>>(w.flowacc, a->rt, a->loss, nullptr, nullptr, 1, F);
     FM_CHECK_LAUNCH("fm_overfit_step: k_flow_finalize");
-  }
-  // LossTracking (loss_tracking.py:28-61) on the chained poses: the forward sweep belongs to the
-  // forward half of a split step, its scaling / scatter to the backward half
-  if (a->tracks && a->phase != FM_STEP_BACKWARD) {
-    const fm_packed_tracks* t = a->tracks;
-    if ((rc = fm_pose_chain(a->rt, a->extrinsics, 1, F, stream))) return rc;
-    // one focal length (or constant intrinsics) for all frames: only the summed K gradient is used
-    if ((rc = fm_track_loss_fwd_sharded(a->depth, k4, a->extrinsics, t->segments, t->num_segments, t->max_rows,
-                                        t->max_points, t->xy, t->vis, t->total_samples, a->mapping, a->delta,
-                                        a->track_weight, a->track_loss, a->track_ws, F, H, W, 0, 0, F, 1,
-                                        stream)))
-      return rc;
+    // LossTracking (loss_tracking.py:28-61) on the chained poses: the forward sweep belongs to the
+    // forward half of a split step, its scaling / scatter to the backward half
+    if (a->tracks) {
+      const fm_packed_tracks* t = a->tracks;
+      void* ts = fwd_lane ? (void*)fwd_lane->stream : stream;
+      if ((rc = fm_pose_chain(a->rt, a->extrinsics, 1, F, ts))) return rc;
+      // one focal length (or constant intrinsics) for all frames: only the summed K gradient is used
+      if ((rc = fm_track_loss_fwd_sharded(a->depth, k4, a->extrinsics, t->segments, t->num_segments, t->max_rows,
+                                          t->max_points, t->xy, t->vis, t->total_samples, a->mapping, a->delta,
+                                          a->track_weight, a->track_loss, a->track_ws, F, H, W, 0, 0, F, 1, ts)))
+        return rc;
+      if (fwd_lane) {
+        if ((e = cudaEventRecord(fwd_lane->join, fwd_lane->stream)) != cudaSuccess) return fail("fm_overfit_step: join", e);
+        if ((e = cudaStreamWaitEvent(s, fwd_lane->join, 0)) != cudaSuccess) return fail("fm_overfit_step: join", e);
+      }
+    }
   }
   if (a->phase == FM_STEP_FORWARD) return 0;
   // d total / d (flow loss) and d total / d (tracking loss) of a split step (device scalars, NULL = 1)
@@ -2785,13 +2894,23 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
   }
   const float* g_rt = a->phase == FM_STEP_BACKWARD ? a->g_rt : nullptr;           // the caller's
   const float* track_g_k4 = a->phase == FM_STEP_BACKWARD ? a->track_g_k4 : nullptr;  // tracking part
+  SideLane* lane = nullptr;  // carries the tracking loss's depth scatter while the Procrustes backward runs
   if (a->tracks) {
     const fm_packed_tracks* t = a->tracks;
-    if ((rc = fm_track_loss_bwd(a->depth, k4, a->extrinsics, t->segments, t->num_segments, t->max_rows,
-                                t->max_points, t->xy, t->vis, t->total_samples, a->mapping, a->delta,
-                                a->track_weight, tscale, a->g_depth, a->g_extrinsics, a->track_g_k4,
-                                a->track_ws, F, H, W, stream)))
+    // REDs into g_depth commute with those of k_distribute; the splat-plan backward instead rewrites
+    // g_depth with plain stores, so there the scatter stays in stream order
+    if (!plan) lane = side_lane();
+    cudaStream_t apply_stream = s;
+    if (lane) {
+      if ((e = cudaEventRecord(lane->fork, s)) != cudaSuccess) return fail("fm_overfit_step: fork", e);
+      if ((e = cudaStreamWaitEvent(lane->stream, lane->fork, 0)) != cudaSuccess) return fail("fm_overfit_step: fork", e);
+      apply_stream = lane->stream;
+    }
+    if ((rc = track_bwd_impl(k4, a->extrinsics, t->segments, t->num_segments, t->max_rows, t->max_points, t->xy,
+                             t->total_samples, a->track_weight, tscale, a->g_depth, a->g_extrinsics, a->track_g_k4,
+                             a->track_ws, F, H, W, 0, 0, F, s, apply_stream)))
       return rc;
+    if (lane && (e = cudaEventRecord(lane->join, lane->stream)) != cudaSuccess) return fail("fm_overfit_step: join", e);
     if ((rc = fm_pose_chain_bwd(a->rt, a->extrinsics, a->g_extrinsics, a->g_rt, 1, F, stream))) return rc;
     g_rt = a->g_rt;
     track_g_k4 = a->track_g_k4;
@@ -2820,6 +2939,7 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
                                 a->g_k4, a->ws, 1, F, H, W, stream, nullptr, fuse_w ? &af : nullptr, plan,
                                 a->splat_overflow_max, /*depth_prescaled=*/fscale != nullptr)))
     return rc;
+  if (lane && (e = cudaStreamWaitEvent(s, lane->join, 0)) != cudaSuccess) return fail("fm_overfit_step: join", e);
   // Adam (model_wrapper_overfit.py:104-105)
   if (a->step > 0 && !defer) {
     auto adam = [&](float* p, const float* g, float* m, float* v, size_t n, int step, int focal_clock) -> int {

@@ -215,6 +215,7 @@ class FusedOverfitter(Overfitter):
         a.rt, a.loss, a.ws = P(self.rt), P(self._loss), P(self._ws)
         # step-dependent scalars live in device memory: every step is the same launch sequence
         self._clock = ops.StepClock(dev, cfg.lr)
+        self._side_stream = torch.cuda.Stream(device=dev)  # parallel branch of the step (see _step_softmin)
         a.clock = self._clock.ptr
         self._total = torch.zeros((), device=dev)
         self._idx_buf = torch.empty(min(cfg.softmin_points, h * w), dtype=torch.int64, device=dev) \
@@ -311,6 +312,16 @@ class FusedOverfitter(Overfitter):
             a.defer_adam = 1 if fuse else 0
             check(L.fm_overfit_step(self._ctypes.byref(a), st), "fm_overfit_step")
             a.defer_adam = 0
+            # The sweep's backward only touches the gradients of frames 0 / 1 (the candidate Procrustes
+            # runs on the first pair): the depth update of every other frame runs beside it on a second
+            # stream (a parallel branch of the captured step), frames 0 / 1 follow the sweep.
+            side, cur = None, torch.cuda.current_stream()
+            if update and f > 2:
+                side = self._side_stream
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    ops.adam_step_clock(self._depth[2:], self._g_depth[2:], self._state[0][2:], self._state[1][2:],
+                                        self._clock)
             check(L.fm_softmin_focal_bwd(P(self._sw_sm), P(self._cand_f), P(self._sw_focal),
                                          P(self._g_focal), n, 1, P(self._sw_gerr), st),
                   "fm_softmin_focal_bwd")
@@ -320,11 +331,14 @@ class FusedOverfitter(Overfitter):
                                          P(self._g_w) if wl else None, P(self._sw_ws), 1, f, h, w, st),
                   "fm_softmin_sweep_bwd")
         if update:
-            ops.adam_step_clock(self._depth, self._g_depth, self._state[0], self._state[1], self._clock)
+            ops.adam_step_clock(self._depth[:2], self._g_depth[:2], self._state[0][:2], self._state[1][:2],
+                                self._clock)
             if c.use_correspondence_weights:
                 k = 1 if fuse else self._wlog.shape[0]  # pair 0 only when the rest was fused
                 ops.adam_step_clock(self._wlog[:k], self._g_w[:k], self._state[2][:k], self._state[3][:k],
                                     self._clock)
+            if side is not None:
+                cur.wait_stream(side)
 
     # ---- split step: the two halves of one iteration WITHOUT the parameter update, for callers that
     # need the loss values before they decide on the backward (torch.autograd: flowmap_b200.fused)
@@ -629,14 +643,16 @@ class ShardedFusedOverfitter(FusedOverfitter):
         clk.tick(tick_focal=True)
         a.clock, a.tracks, a.step, a.focal_step, a.defer_adam, a.phase = clk.ptr, None, 1, 1, 2, 0
         a.focal = P(self._focal)
+        # the step writes its two scalars (loss, d focal) straight into the all-reduce buffer
+        loss_ptr, gf_ptr = a.loss, a.g_focal
+        a.loss, a.g_focal = r.scal[0:1].data_ptr(), r.scal[1:2].data_ptr()
         try:
             with torch.cuda.device(self.rt.device):
                 check(self._lib.fm_overfit_step(self._ctypes.byref(a), torch.cuda.current_stream().cuda_stream),
                       "fm_overfit_step")
         finally:
             a.clock, a.step, a.focal_step, a.defer_adam = None, 0, 0, 0
-        r.scal[0].copy_(self._loss.reshape(()))
-        r.scal[1].copy_(self._g_focal.reshape(()))
+            a.loss, a.g_focal = loss_ptr, gf_ptr
         reqs = r.start(self._g_depth)
         stt, n = self._state, self._depth.shape[0]
         lo, hi = int(p.has_left and p.world > 1), n - int(p.has_right and p.world > 1)
@@ -647,9 +663,8 @@ class ShardedFusedOverfitter(FusedOverfitter):
             ops.adam_step_clock(self._depth[:1], self._g_depth[:1], stt[0][:1], stt[1][:1], clk)
         if hi < n:
             ops.adam_step_clock(self._depth[n - 1:], self._g_depth[n - 1:], stt[0][n - 1:], stt[1][n - 1:], clk)
-        self._g_focal.copy_(red[1])
-        ops.adam_step_clock(self._focal.reshape(1), self._g_focal.reshape(1), stt[4].reshape(1),
-                            stt[5].reshape(1), clk, focal_clock=True)
+        ops.adam_step_clock(self._focal.reshape(1), red[1:2], stt[4].reshape(1), stt[5].reshape(1), clk,
+                            focal_clock=True)
         self._total.copy_(red[0])
 
     def training_step(self, update: bool = True):

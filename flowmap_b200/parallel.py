@@ -179,13 +179,13 @@ class StepReducer:
         if p.world == 1:
             return []
         ops = []
+        # the boundary frames are sent from where they lie (contiguous rows of depth_grad; nothing
+        # writes them before finish() has waited for the sends)
         if p.has_left:
-            self.to_left.copy_(depth_grad[0])
-            ops += [dist.P2POp(dist.isend, self.to_left, self._peer(-1), self.group),
+            ops += [dist.P2POp(dist.isend, depth_grad[0], self._peer(-1), self.group),
                     dist.P2POp(dist.irecv, self.from_left, self._peer(-1), self.group)]
         if p.has_right:
-            self.to_right.copy_(depth_grad[-1])
-            ops += [dist.P2POp(dist.isend, self.to_right, self._peer(+1), self.group),
+            ops += [dist.P2POp(dist.isend, depth_grad[-1], self._peer(+1), self.group),
                     dist.P2POp(dist.irecv, self.from_right, self._peer(+1), self.group)]
         reqs = dist.batch_isend_irecv(ops) if ops else []
         reqs.append(dist.all_reduce(self.scal, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
