@@ -248,6 +248,25 @@ __device__ __forceinline__ ItemRange block_item_range(long long total) {
   ItemRange r; r.i0 = (int)i0; r.i1 = (int)i1;
   return r;
 }
+// The same decomposition applied to each of `rounds` consecutive slices of the item list (all blocks
+// share slice 0, then slice 1, ...).  The gathers / REDs of the Procrustes kernels touch a band of rows
+// around a block's position; with one round the resident blocks sit in as many different places as there
+// are blocks, and at 720p those bands (grid x band x row bytes x 2 arrays) no longer fit the 126 MB L2
+// (k_distribute 2.4 -> 4.5 ms at 150 x 720 x 1280).  With more rounds the blocks advance together through
+// a few frame pairs and share their bands.  Blocks are rotated between rounds so that the odd chunk of
+// an uneven split does not always land on the same block.
+__device__ __forceinline__ ItemRange block_item_range(long long total, int rounds, int round) {
+  const long long len = (total + rounds - 1) / rounds;
+  long long s0 = len * round, s1 = s0 + len;
+  if (s0 > total) s0 = total;
+  if (s1 > total) s1 = total;
+  const long long g = gridDim.x;
+  const long long b = ((long long)blockIdx.x + ((long long)round * g) / rounds) % g;
+  ItemRange r;
+  r.i0 = (int)(s0 + ((s1 - s0) * b) / g);
+  r.i1 = (int)(s0 + ((s1 - s0) * (b + 1)) / g);
+  return r;
+}
 
 // Thread -> pixel mapping inside a chunk of kThreads * 4 pixels of the dense Procrustes kernels; a
 // thread always owns 4 consecutive pixels of a row (128-bit streaming loads / stores).
@@ -356,14 +375,16 @@ template <int VEC, int LX>
 __global__ void __launch_bounds__(kThreads, 3)
 k_moments_dense(const float* __restrict__ depth, const float* __restrict__ k4,
                 const float* __restrict__ bflow, const float* __restrict__ weights,
-                double* __restrict__ moments, float wsens, PairLayout lay, int H, int W, int BP) {
+                double* __restrict__ moments, float wsens, PairLayout lay, int H, int W, int BP, int rounds) {
   __shared__ double smem[kNumMoments * (kThreads / 32)];
   const int N = H * W;
   constexpr int kChunk = kThreads * VEC;
   const int chunks = (N + kChunk - 1) / kChunk;
-  const ItemRange range = block_item_range((long long)BP * chunks);
   const int dr = kChunk / W, dc = kChunk - dr * W;
   const int tiles_x = LX > 0 ? W / (4 * LX) : 1, tiles = N / 128;
+#pragma unroll 1
+  for (int round = 0; round < rounds; ++round) {
+  const ItemRange range = block_item_range((long long)BP * chunks, rounds, round);
 #pragma unroll 1
   for (int i = range.i0; i < range.i1;) {
     const int pair = i / chunks, cb = i - pair * chunks;
@@ -414,6 +435,7 @@ k_moments_dense(const float* __restrict__ depth, const float* __restrict__ k4,
     }
     block_accumulate<kNumMoments>(acc, moments + (size_t)pair * kNumMoments, smem);
     i += ce - cb;
+  }
   }
 }
 
@@ -814,16 +836,18 @@ __global__ void __launch_bounds__(kThreads, 3)
 k_distribute_dense(const float* __restrict__ depth, const float* __restrict__ k4,
                    const float* __restrict__ bflow, float* weights, const PairAdjoint* __restrict__ adj,
                    float* __restrict__ g_depth, float* __restrict__ g_weights, double* __restrict__ k4acc,
-                   float wsens, PairLayout lay, AdamFuse adam, int H, int W, int BP) {
+                   float wsens, PairLayout lay, AdamFuse adam, int H, int W, int BP, int rounds) {
   __shared__ double smem[8 * (kThreads / 32)];
   __shared__ PairAdjoint s_adj;
   const int N = H * W;
   constexpr int kChunk = kThreads * VEC;
   const int chunks = (N + kChunk - 1) / kChunk;
-  const ItemRange range = block_item_range((long long)BP * chunks);
   const int dr = kChunk / W, dc = kChunk - dr * W;
   const int tiles_x = LX > 0 ? W / (4 * LX) : 1, tiles = N / 128;
   if (adam.on && adam.consts) { adam.step_size = __ldg(adam.consts); adam.bc2_sqrt = __ldg(adam.consts + 1); }
+#pragma unroll 1
+  for (int round = 0; round < rounds; ++round) {
+  const ItemRange range = block_item_range((long long)BP * chunks, rounds, round);
 #pragma unroll 1
   for (int i = range.i0; i < range.i1;) {
     const int pair = i / chunks, cb = i - pair * chunks;
@@ -913,6 +937,7 @@ k_distribute_dense(const float* __restrict__ depth, const float* __restrict__ k4
     // kacc[0..3] -> frame a, kacc[4..7] -> frame b = a + 1: contiguous in k4acc
     block_accumulate<8>(kacc, k4acc + (size_t)a * 4, smem);
     i += ce - cb;
+  }
   }
 }
 
@@ -1977,8 +2002,14 @@ int blocks_for(int n_items_per_row, int vec) {
 // Lanes per row of the warp patch of the dense Procrustes kernels (PatchSite).  Measured on B200 at
 // 150 x 360 x 640, iid flows, fwd / bwd op in ms: strips 0.231 / 0.592, 4 lanes x 8 rows 0.222 / 0.611,
 // 8 x 4 0.227 / 0.564, 16 x 2 0.224 / 0.590 (profiles/README.md).
-constexpr int kPatchLanes = 8;
-static bool patch_shape_ok(int H, int W) { return W % (4 * kPatchLanes) == 0 && H % (32 / kPatchLanes) == 0; }
+#ifndef FM_PATCH_LANES  // build-time knob for tools/ab_libs.py (0 = strips only)
+#define FM_PATCH_LANES 8
+#endif
+constexpr int kPatchLanes = FM_PATCH_LANES;
+static bool patch_shape_ok(int H, int W) {
+  constexpr int lx = kPatchLanes > 0 ? kPatchLanes : 1;
+  return kPatchLanes > 0 && W % (4 * lx) == 0 && H % (32 / lx) == 0;
+}
 
 // 1-D grid of the dense kernels (block_item_range): every SM holds `ctas_per_sm` blocks for the whole
 // launch.
@@ -1994,6 +2025,29 @@ int sm_count_cached() {
 int persistent_grid(int ctas_per_sm, long long items) {
   const long long g = (long long)sm_count_cached() * ctas_per_sm;
   return (int)(items < g ? (items < 1 ? 1 : items) : g);
+}
+
+// Rounds of the dense Procrustes kernels (block_item_range): runs of about kRunChunks chunks per block
+// and round.  Measured on B200 (tools/ab_libs.py): k_distribute_dense (REDs + the fused Adam streams)
+// gains at every shape -- 150 x 720 x 1280: 4.32 ms in one round, 2.47 / 2.44 / 2.69 / 3.73 ms with runs
+// of 4 / 8 / 16 / 32 chunks; 150 x 360 x 640: 0.565 -> 0.553 ms.  k_moments_dense (read-only gathers)
+// gains only once the resident blocks' row bands (sized for flows of a few percent of the image) stop
+// fitting in L2: 1.04 -> 0.95 ms at 720p, but 0.223 -> 0.239 ms at 360 x 640, so it keeps one round there.
+constexpr int kRunChunks = 8;
+int procrustes_rounds(int H, int W, long long items, int grid, bool gathers_only) {
+  if (gathers_only) {
+    static const double l2_bytes = [] {
+      int dev = 0, v = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev) != cudaSuccess || v < 1)
+        v = 126 << 20;
+      return (double)v;
+    }();
+    const double band_rows = 0.07 * H + 6.0;
+    if ((double)grid * band_rows * W * 4.0 <= 0.35 * l2_bytes) return 1;
+  }
+  const long long per_block = (items + grid - 1) / grid;
+  const long long rounds = per_block / kRunChunks;
+  return (int)(rounds < 1 ? 1 : rounds);
 }
 
 // Index-mode launches (subsampled Procrustes, the focal sweep): few points, dependent gathers ->
@@ -2221,14 +2275,17 @@ static int procrustes_fwd_impl(const float* depth, const float* k4, const float*
     dim3 grid(blocks_for_points(num_indices), BP);
     k_moments<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights, indices, num_indices, w.moments, wsens, lay, H, W);
   } else if (patch_shape_ok(H, W)) {
-    const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4)));
-    k_moments_dense<4, kPatchLanes><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP);
+    const long long items = (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4));
+    const int pg = persistent_grid(3, items);
+    k_moments_dense<4, kPatchLanes><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP, procrustes_rounds(H, W, items, pg, true));
   } else if (W % 4 == 0) {
-    const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4)));
-    k_moments_dense<4, 0><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP);
+    const long long items = (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4));
+    const int pg = persistent_grid(3, items);
+    k_moments_dense<4, 0><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP, procrustes_rounds(H, W, items, pg, true));
   } else {
-    const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads - 1) / kThreads));
-    k_moments_dense<1, 0><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP);
+    const long long items = (long long)BP * ((H * W + kThreads - 1) / kThreads);
+    const int pg = persistent_grid(3, items);
+    k_moments_dense<1, 0><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP, procrustes_rounds(H, W, items / 4, pg, true));
   }
   if (!plan) FM_CHECK_LAUNCH("fm_procrustes_fwd: k_moments");
   k_solve<<<(BP + 63) / 64, 64, 0, s>>>(w.moments, depth, rt, w.state, BP, lay, H, W);
@@ -2289,14 +2346,17 @@ static int procrustes_bwd_impl(const float* depth, const float* k4, const float*
     dim3 grid(blocks_for_points(num_indices), BP);
     k_distribute<1><<<grid, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, indices, num_indices, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W);
   } else if (patch_shape_ok(H, W)) {
-    const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4)));
-    k_distribute_dense<4, kPatchLanes><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W, BP);
+    const long long items = (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4));
+    const int pg = persistent_grid(3, items);
+    k_distribute_dense<4, kPatchLanes><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W, BP, procrustes_rounds(H, W, items, pg, false));
   } else if (W % 4 == 0) {
-    const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4)));
-    k_distribute_dense<4, 0><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W, BP);
+    const long long items = (long long)BP * ((H * W + kThreads * 4 - 1) / (kThreads * 4));
+    const int pg = persistent_grid(3, items);
+    k_distribute_dense<4, 0><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W, BP, procrustes_rounds(H, W, items, pg, false));
   } else {
-    const int pg = persistent_grid(3, (long long)BP * ((H * W + kThreads - 1) / kThreads));
-    k_distribute_dense<1, 0><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W, BP);
+    const long long items = (long long)BP * ((H * W + kThreads - 1) / kThreads);
+    const int pg = persistent_grid(3, items);
+    k_distribute_dense<1, 0><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights_rw, w.adj, g_depth, g_weights, w.k4acc, wsens, lay, af, H, W, BP, procrustes_rounds(H, W, items / 4, pg, false));
   }
   FM_CHECK_LAUNCH("fm_procrustes_bwd: k_distribute");
   k_k4_finalize<<<(BF + 127) / 128, 128, 0, s>>>(w.k4acc, w.flowacc, include_flow_loss, flow_scale, g_k4, B, F);

@@ -128,13 +128,18 @@ def fused(f, h, w, steps, full):
 
 
 def main():
-    paths = [a for a in sys.argv[1:] if not a.startswith("--")]
+    paths = [a for a in sys.argv[1:] if not a.startswith("--") and not a.isdigit()]
     with_step = "--no-step" not in sys.argv
     libs = [(Path(p).stem, libmod.load_library(ROOT / p)) for p in paths]
     out = {}
     ref = {}
     small = [(4, 36, 48, "iid"), (3, 100, 64, "leave"), (5, 72, 96, "leave"), (3, 100, 64, "smooth")]
     big = [(150, 360, 640, "iid"), (150, 360, 640, "smooth")]
+    if "--shape" in sys.argv:  # e.g. --shape 150 720 1280: time the ops at another shape instead
+        i = sys.argv.index("--shape")
+        f_, h_, w_ = (int(x) for x in sys.argv[i + 1:i + 4])
+        big = [(f_, h_, w_, "iid")]
+
     cases = {key: OpsCase(*key) for key in small + big}
     for name, L in libs:
         rec = out[name] = {"parity": [], "times": {}}
@@ -161,9 +166,9 @@ def main():
         base = {}
         for name, L in libs:
             libmod._lib = L  # the package's ops / fused step now run on this build
-            for full in (False, True):
+            for full in ((False,) if "--shape" in sys.argv else (False, True)):
                 small_run = fused(8, 72, 96, 3, full)
-                r = fused(150, 360, 640, 30, full)
+                r = fused(*big[0][:3], 30, full)
                 key = "full" if full else "flow_only"
                 if name == libs[0][0]:
                     base[key] = (small_run, r)
