@@ -118,17 +118,17 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 // Per-thread partials cover at most a few dozen pixels, so the float32 warp tree adds no
 // visible error; the cross-warp and cross-block sums run in float64.
 // smem must hold NV * (kThreads / 32) doubles.
-template <int NV>
+template <int NV, int NT = kThreads>
 __device__ __forceinline__ void block_accumulate(const float* vals, double* dst, double* smem) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = kThreads / 32;
+  constexpr int NW = NT / 32;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const float s = warp_sum_f(vals[i]);
     if (lane == 0) smem[i * NW + warp] = (double)s;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < NV; i += kThreads) {
+  for (int i = threadIdx.x; i < NV; i += NT) {
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) s += smem[i * NW + w];
@@ -1291,39 +1291,49 @@ __device__ __forceinline__ SegInfo load_seg(const int* seg, int s) {
 }
 
 // Per-frame record: R (9, row-major, camera-to-world), t (3), c = -R^T t (3), fx fy cx cy ifx ify,
-// 3 pad.
+// 3 pad -- every value stored TWICE in a row (2 * kTrackRec floats per frame), so that an 8-byte
+// shared-memory load yields the (v, v) register pair a packed float32x2 instruction takes as its
+// broadcast operand (rec2), no register moves.  rec1 reads one copy.
 __device__ __forceinline__ void load_segment_frames(float* sm, const float* ext, const float* k4,
                                                     const SegInfo& si) {
   for (int row = threadIdx.x; row < si.rows; row += blockDim.x) {
     const float* P = ext + (size_t)(si.start_frame + row) * 16;
-    float* o = sm + row * kTrackRec;
-    float R[9], t[3];
+    float* o = sm + row * 2 * kTrackRec;
+    float v[kTrackRec];
+    float* R = v;
+    float* t = v + 9;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       R[i * 3 + 0] = __ldg(P + i * 4 + 0); R[i * 3 + 1] = __ldg(P + i * 4 + 1); R[i * 3 + 2] = __ldg(P + i * 4 + 2);
       t[i] = __ldg(P + i * 4 + 3);
     }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) o[i] = R[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      o[9 + i] = t[i];
-      o[12 + i] = -(R[0 * 3 + i] * t[0] + R[1 * 3 + i] * t[1] + R[2 * 3 + i] * t[2]);
-    }
+    for (int i = 0; i < 3; ++i)
+      v[12 + i] = -(R[0 * 3 + i] * t[0] + R[1 * 3 + i] * t[1] + R[2 * 3 + i] * t[2]);
     const float4 k = __ldg(reinterpret_cast<const float4*>(k4) + si.start_frame + row);
-    o[15] = k.x; o[16] = k.y; o[17] = k.z; o[18] = k.w; o[19] = 1.0f / k.x; o[20] = 1.0f / k.y;
+    v[15] = k.x; v[16] = k.y; v[17] = k.z; v[18] = k.w; v[19] = 1.0f / k.x; v[20] = 1.0f / k.y;
+    v[21] = v[22] = v[23] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kTrackRec; ++i) reinterpret_cast<float2*>(o)[i] = make_float2(v[i], v[i]);
   }
   __syncthreads();
 }
+__device__ __forceinline__ float rec1(const float* rec, int i) { return rec[2 * i]; }
+__device__ __forceinline__ F2 rec2(const float* rec, int i) {
+  const float2 v = reinterpret_cast<const float2*>(rec)[i];
+  return f2(v.x, v.y);
+}
 __device__ __forceinline__ Cam sm_cam(const float* rec) {
   Cam c;
-  c.fx = rec[15]; c.fy = rec[16]; c.cx = rec[17]; c.cy = rec[18]; c.ifx = rec[19]; c.ify = rec[20];
+  c.fx = rec1(rec, 15); c.fy = rec1(rec, 16); c.cx = rec1(rec, 17); c.cy = rec1(rec, 18);
+  c.ifx = rec1(rec, 19); c.ify = rec1(rec, 20);
   return c;
 }
 
 // Block-level stream compaction: every thread offers (valid, value); afterwards list[0..count)
 // holds the values of the valid threads in thread order.  Keeps whole warps idle instead of
 // 30 % of the lanes of every warp (track visibility is ~70 %).
+template <int NT = kThreads>
 __device__ __forceinline__ int block_compact(bool valid, int value, int* list, int* warp_base) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned m = __ballot_sync(0xffffffffu, valid);
@@ -1331,7 +1341,7 @@ __device__ __forceinline__ int block_compact(bool valid, int value, int* list, i
   __syncthreads();
   int base = 0, total = 0;
 #pragma unroll
-  for (int w = 0; w < kThreads / 32; ++w) {
+  for (int w = 0; w < NT / 32; ++w) {
     const int c = warp_base[w];
     if (w < warp) base += c;
     total += c;
@@ -1339,22 +1349,6 @@ __device__ __forceinline__ int block_compact(bool valid, int value, int* list, i
   if (valid) list[base + __popc(m & ((1u << lane) - 1u))] = value;
   __syncthreads();
   return total;
-}
-
-// One (world point, target frame) term: Y = R_t^T Xw + c_t, project, validity, robust loss and
-// the unscaled adjoint.  Returns false (and leaves outputs unspecified) when invalid.
-__device__ __forceinline__ bool track_term_lean(const float* rec, const float* Xw, float gtx, float gty,
-                                                const RobustCfg& rc, LeanTerm& t, float* g) {
-  const float dir0 = fm_fma(rec[0], Xw[0], fm_fma(rec[3], Xw[1], rec[6] * Xw[2]));
-  const float dir1 = fm_fma(rec[1], Xw[0], fm_fma(rec[4], Xw[1], rec[7] * Xw[2]));
-  const float dir2 = fm_fma(rec[2], Xw[0], fm_fma(rec[5], Xw[1], rec[8] * Xw[2]));
-  t = lean_term(1.0f, dir0, dir1, dir2, rec[12], rec[13], rec[14], sm_cam(rec), gtx, gty, 0.f, 0.f, 1.0f, rc);
-  if (!in_unit_square(t.uvx, t.uvy)) return false;  // projection.py:294-296 (predicted target)
-  // world-space gradient g = R_t dY
-  g[0] = fm_fma(rec[0], t.d0, fm_fma(rec[1], t.d1, rec[2] * t.d2));
-  g[1] = fm_fma(rec[3], t.d0, fm_fma(rec[4], t.d1, rec[5] * t.d2));
-  g[2] = fm_fma(rec[6], t.d0, fm_fma(rec[7], t.d1, rec[8] * t.d2));
-  return true;
 }
 
 // Warp sum of N per-lane values by recursive halving (N = 10: 12 shuffles instead of 50; N = 6:
@@ -1418,132 +1412,185 @@ __device__ __forceinline__ float warp_sum_n(float* v, int lane) {
   return v[0];
 }
 
-// One sweep over the (source row, target row, point) triples.  A block owns (segment, source
-// row, 256 points): every thread keeps the source-side sums of its point in registers; the
-// target-side sums (pose twist and K of the TARGET frame) of one loop iteration belong to one
-// frame for the whole block, so each warp reduces them with warp_sum_n into its own
-// [target row][10] slice of shared memory, folded into the per-frame accumulators at the end.
+// One sweep over the (source row, target row, point) triples.  A block of kTrackThreads threads owns
+// (segment, source row, kTrackPoints = 2 * kTrackThreads points): every thread keeps TWO usable source
+// points in registers and evaluates their terms against one target row as ONE packed float32x2
+// computation (FFMA2 / FMUL2 / FADD2: the two points share every target-frame constant; lean_term2 of
+// fm_pixel.cuh is the two-pixel form of the flow kernel's term).  The source-side sums stay in
+// registers; the target-side sums (pose twist and K of the TARGET frame) of one loop iteration belong
+// to one frame for the whole block, so the two points' contributions are added and each warp reduces
+// them with warp_sum_n into its own [target row][10] slice of shared memory -- one reduction per 64
+// terms -- folded into the per-frame accumulators at the end.
 // SHARED_K: every frame has the same intrinsics (one focal length, or constants), so only the SUM
 // over frames of the intrinsics gradient matters: the target-frame terms are then added to the
 // thread's own (source-frame) accumulators and only the 6 pose values go through the reduction.
+constexpr int kTrackThreads = 128;
+constexpr int kTrackPoints = 2 * kTrackThreads;
+
 template <bool SHARED_K>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kTrackThreads, 5)  // 96 registers: 5 blocks per SM (122 unbounded: 4; 80: spills)
 k_track_src(const float* __restrict__ depth, const float* __restrict__ k4, const float* __restrict__ ext,
             const int* __restrict__ seg, const float* __restrict__ txy,
             const unsigned char* __restrict__ tvis, int mapping, float delta, double* __restrict__ sums,
             unsigned char* __restrict__ flag, float* __restrict__ dq_out,
             double* __restrict__ trackacc, int H, int W, TrackShard sh) {
   extern __shared__ float sm[];
-  __shared__ double red[kTrackAcc * (kThreads / 32)];
+  constexpr int NW = kTrackThreads / 32;
+  __shared__ double red[kTrackAcc * NW];
   const SegInfo si = load_seg(seg, blockIdx.z);
   const int row = blockIdx.y;
   if (row >= si.rows || !sh.owns(si.start_frame + row)) return;
   load_segment_frames(sm, ext, k4, si);
-  float* s_tgt = sm + (size_t)gridDim.y * kTrackRec;  // [warp][target row][kTrackAcc]
-  __shared__ int s_list[kThreads];
-  __shared__ int s_wbase[kThreads / 32];
+  float* s_tgt = sm + (size_t)gridDim.y * 2 * kTrackRec;  // [warp][target row][kTrackAcc]
+  __shared__ int s_list[kTrackPoints];
+  __shared__ int s_wbase[NW];
   const GridDims grid = make_grid(H, W);
   const RobustCfg rc = make_robust(mapping, delta, H, W);
   const int frame = si.start_frame + row;
   const float* D = depth + (size_t)(frame - sh.depth_frame0) * H * W;
-  const float* rs = sm + row * kTrackRec;
-  const Cam ks = sm_cam(rs);
+  const float* rsrec = sm + row * 2 * kTrackRec;
+  float rs[12];  // source pose: R (9), t (3)
+#pragma unroll
+  for (int i = 0; i < 12; ++i) rs[i] = rec1(rsrec, i);
+  const Cam ks = sm_cam(rsrec);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float acc[kTrackAcc], lc[2] = {0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < kTrackAcc; ++i) acc[i] = 0.f;
-  // which of this block's points are usable sources (visible and inside [0,1)^2)?
-  const int p_own = blockIdx.x * kThreads + threadIdx.x;
-  bool ok_own = false;
-  if (p_own < si.n) {
-    const size_t sidx = (size_t)si.sample_start + (size_t)row * si.n + p_own;
-    const float2 sxy = __ldg(reinterpret_cast<const float2*>(txy) + sidx);
-    ok_own = tvis[sidx] && in_unit_square(sxy.x, sxy.y);
-    flag[sidx] = ok_own ? 1 : 0;
-  }
-  const int count = block_compact(ok_own, p_own, s_list, s_wbase);
-  const bool live = (int)threadIdx.x < count;
-  if (warp * 32 < count) {  // warp-uniform: the shuffles below need all 32 lanes
-    const int p = live ? s_list[threadIdx.x] : 0;
-    const size_t sidx = (size_t)si.sample_start + (size_t)row * si.n + p;
-    float q[3] = {0.f, 0.f, 0.f}, Xw[3] = {0.f, 0.f, 0.f};
-    if (live) {
+  // which of this block's points are usable sources (visible and inside [0,1)^2)?  Two offers per
+  // thread, compacted one after the other into one list.
+  int count = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p_own = blockIdx.x * kTrackPoints + h * kTrackThreads + (int)threadIdx.x;
+    bool ok_own = false;
+    if (p_own < si.n) {
+      const size_t sidx = (size_t)si.sample_start + (size_t)row * si.n + p_own;
       const float2 sxy = __ldg(reinterpret_cast<const float2*>(txy) + sidx);
+      ok_own = tvis[sidx] && in_unit_square(sxy.x, sxy.y);
+      flag[sidx] = ok_own ? 1 : 0;
+    }
+    count += block_compact<kTrackThreads>(ok_own, p_own, s_list + count, s_wbase);
+  }
+  const int half = (count + 1) >> 1;  // thread t works on list[t] and list[t + half]
+  const bool live_a = (int)threadIdx.x < half, live_b = (int)threadIdx.x + half < count;
+  if (warp * 32 < half) {  // warp-uniform: the shuffles below need all 32 lanes
+    const int pa = live_a ? s_list[threadIdx.x] : 0, pb = live_b ? s_list[threadIdx.x + half] : 0;
+    const size_t row0 = (size_t)si.sample_start + (size_t)row * si.n;
+    float qa[3] = {0.f, 0.f, 0.f}, qb[3] = {0.f, 0.f, 0.f};
+    F2 Xw[3] = {f2s(0.f), f2s(0.f), f2s(0.f)};
+    auto lift = [&](int p, float* q, float* X) {
+      const float2 sxy = __ldg(reinterpret_cast<const float2*>(txy) + row0 + p);
       const Taps t = bilinear_taps(sxy.x, sxy.y, grid);
       sample_surface(t, grid, ks, [D](int o) { return __ldg(D + o); }, q[0], q[1], q[2]);
 #pragma unroll
       for (int i = 0; i < 3; ++i)
-        Xw[i] = fm_fma(rs[i * 3 + 0], q[0], fm_fma(rs[i * 3 + 1], q[1], fm_fma(rs[i * 3 + 2], q[2], rs[9 + i])));
-    }
-    float G[3] = {0.f, 0.f, 0.f};
-    float kt[4] = {0.f, 0.f, 0.f, 0.f};  // SHARED_K: intrinsics terms of the targets
+        X[i] = fm_fma(rs[i * 3 + 0], q[0], fm_fma(rs[i * 3 + 1], q[1], fm_fma(rs[i * 3 + 2], q[2], rs[9 + i])));
+    };
+    if (live_a) { float X[3]; lift(pa, qa, X); Xw[0].x = X[0]; Xw[1].x = X[1]; Xw[2].x = X[2]; }
+    if (live_b) { float X[3]; lift(pb, qb, X); Xw[0].y = X[0]; Xw[1].y = X[1]; Xw[2].y = X[2]; }
+    F2 G[3] = {f2s(0.f), f2s(0.f), f2s(0.f)}, lc2[2] = {f2s(0.f), f2s(0.f)};
+    F2 kt[4] = {f2s(0.f), f2s(0.f), f2s(0.f), f2s(0.f)};  // SHARED_K: intrinsics terms of the targets
     constexpr int NRED = SHARED_K ? 6 : kTrackAcc;
     constexpr int SLOT0 = kTrackAcc - NRED;  // twist values live in slots 4..9 either way
     const TrackSlot slot = track_slot<NRED>(lane);
     float* tgt = s_tgt + (size_t)warp * si.rows * kTrackAcc;
     // the next target row's visibility / position is fetched while the current one is processed
-    size_t tidx_n = (size_t)si.sample_start + p;
-    unsigned char vis_n = live ? tvis[tidx_n] : 0;
-    float2 gxy_n = live ? __ldg(reinterpret_cast<const float2*>(txy) + tidx_n) : make_float2(0.f, 0.f);
+    size_t ia = (size_t)si.sample_start + pa, ib = (size_t)si.sample_start + pb;
+    unsigned char va_n = live_a ? tvis[ia] : 0, vb_n = live_b ? tvis[ib] : 0;
+    float2 ga_n = live_a ? __ldg(reinterpret_cast<const float2*>(txy) + ia) : make_float2(0.f, 0.f);
+    float2 gb_n = live_b ? __ldg(reinterpret_cast<const float2*>(txy) + ib) : make_float2(0.f, 0.f);
     for (int ft = 0; ft < si.rows; ++ft) {
-      const unsigned char vis_t = vis_n;
-      const float2 gxy = gxy_n;
-      if (ft + 1 < si.rows && live) {
-        tidx_n += si.n;
-        vis_n = tvis[tidx_n];
-        gxy_n = __ldg(reinterpret_cast<const float2*>(txy) + tidx_n);
+      const unsigned char vis_a = va_n, vis_b = vb_n;
+      const float2 ga = ga_n, gb = gb_n;
+      if (ft + 1 < si.rows) {
+        if (live_a) { ia += si.n; va_n = tvis[ia]; ga_n = __ldg(reinterpret_cast<const float2*>(txy) + ia); }
+        if (live_b) { ib += si.n; vb_n = tvis[ib]; gb_n = __ldg(reinterpret_cast<const float2*>(txy) + ib); }
       }
       float c[NRED];
 #pragma unroll
       for (int i = 0; i < NRED; ++i) c[i] = 0.f;
       bool ok = false;
-      if (vis_t) {
-        const float* rec = sm + ft * kTrackRec;
-        LeanTerm lt;
-        float g[3];
-        if (track_term_lean(rec, Xw, gxy.x, gxy.y, rc, lt, g)) {
+      if (vis_a | vis_b) {
+        const float* rec = sm + ft * 2 * kTrackRec;
+        F2 R[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = rec2(rec, i);
+        // Y = R_t^T Xw + c_t for both points
+        const F2 dir0 = f2_fma(R[0], Xw[0], f2_fma(R[3], Xw[1], f2_mul(R[6], Xw[2])));
+        const F2 dir1 = f2_fma(R[1], Xw[0], f2_fma(R[4], Xw[1], f2_mul(R[7], Xw[2])));
+        const F2 dir2 = f2_fma(R[2], Xw[0], f2_fma(R[5], Xw[1], f2_mul(R[8], Xw[2])));
+        Cam2 kc;
+        kc.fx = rec2(rec, 15); kc.fy = rec2(rec, 16); kc.cx = rec2(rec, 17); kc.cy = rec2(rec, 18);
+        const LeanTerm2 lt = lean_term2(f2s(1.0f), dir0, dir1, dir2, rec2(rec, 12), rec2(rec, 13), rec2(rec, 14), kc,
+                                        f2(ga.x, gb.x), f2(ga.y, gb.y), f2s(0.f), f2s(0.f), f2s(1.0f), rc);
+        // projection.py:294-296: the PREDICTED target position decides
+        const bool oa = vis_a && in_unit_square(lt.uvx.x, lt.uvy.x);
+        const bool ob = vis_b && in_unit_square(lt.uvx.y, lt.uvy.y);
+        if (oa | ob) {
           ok = true;
-          lc[0] += lt.loss;
-          lc[1] += 1.f;
-          G[0] += g[0]; G[1] += g[1]; G[2] += g[2];
+          // an invalid point contributes nothing (selects, not products: its adjoint may hold inf / nan;
+          // the camera-space point P itself is always finite)
+          const F2 d0 = f2(oa ? lt.d0.x : 0.f, ob ? lt.d0.y : 0.f);
+          const F2 d1 = f2(oa ? lt.d1.x : 0.f, ob ? lt.d1.y : 0.f);
+          const F2 d2 = f2(oa ? lt.d2.x : 0.f, ob ? lt.d2.y : 0.f);
+          lc2[0] = f2_add(lc2[0], f2(oa ? lt.loss.x : 0.f, ob ? lt.loss.y : 0.f));
+          lc2[1] = f2_add(lc2[1], f2(oa ? 1.f : 0.f, ob ? 1.f : 0.f));
+          // world-space gradient g = R_t dY
+          const F2 g0 = f2_fma(R[0], d0, f2_fma(R[1], d1, f2_mul(R[2], d2)));
+          const F2 g1 = f2_fma(R[3], d0, f2_fma(R[4], d1, f2_mul(R[5], d2)));
+          const F2 g2 = f2_fma(R[6], d0, f2_fma(R[7], d1, f2_mul(R[8], d2)));
+          G[0] = f2_add(G[0], g0); G[1] = f2_add(G[1], g1); G[2] = f2_add(G[2], g2);
           // target-frame K gradient: duv = d (P_z + eps) / f and uv - c = f P / (P_z + eps)
-          const float ex = lt.d0 * rec[19], ey = lt.d1 * rec[20];
-          float* kd = SHARED_K ? kt : c;
-          if (SHARED_K) { kd[0] = fm_fma(ex, lt.P0, kd[0]); kd[1] = fm_fma(ey, lt.P1, kd[1]); kd[2] = fm_fma(ex, lt.P2, kd[2]); kd[3] = fm_fma(ey, lt.P2, kd[3]); }
-          else { kd[0] = ex * lt.P0; kd[1] = ey * lt.P1; kd[2] = ex * lt.P2; kd[3] = ey * lt.P2; }
+          const F2 ex = f2_mul(d0, rec2(rec, 19)), ey = f2_mul(d1, rec2(rec, 20));
+          if (SHARED_K) {
+            kt[0] = f2_fma(ex, lt.P0, kt[0]); kt[1] = f2_fma(ey, lt.P1, kt[1]);
+            kt[2] = f2_fma(ex, lt.P2, kt[2]); kt[3] = f2_fma(ey, lt.P2, kt[3]);
+          } else {
+            const F2 k0 = f2_mul(ex, lt.P0), k1 = f2_mul(ey, lt.P1), k2 = f2_mul(ex, lt.P2), k3 = f2_mul(ey, lt.P2);
+            c[0] = k0.x + k0.y; c[1] = k1.x + k1.y; c[2] = k2.x + k2.y; c[3] = k3.x + k3.y;
+          }
+          // twist of the target pose: (Xw - t) x g, -g (an invalid point has g = 0)
+          const F2 e0 = f2_sub(Xw[0], rec2(rec, 9)), e1 = f2_sub(Xw[1], rec2(rec, 10)), e2 = f2_sub(Xw[2], rec2(rec, 11));
+          const F2 t0 = f2_fma(e2, g1, f2_neg(f2_mul(e1, g2)));
+          const F2 t1 = f2_fma(e0, g2, f2_neg(f2_mul(e2, g0)));
+          const F2 t2 = f2_fma(e1, g0, f2_neg(f2_mul(e0, g1)));
           float* tw = c + (SHARED_K ? 0 : 4);
-          const float d0 = Xw[0] - rec[9], d1 = Xw[1] - rec[10], d2 = Xw[2] - rec[11];
-          tw[0] = d2 * g[1] - d1 * g[2];
-          tw[1] = d0 * g[2] - d2 * g[0];
-          tw[2] = d1 * g[0] - d0 * g[1];
-          tw[3] = -g[0]; tw[4] = -g[1]; tw[5] = -g[2];
+          tw[0] = t0.x + t0.y; tw[1] = t1.x + t1.y; tw[2] = t2.x + t2.y;
+          tw[3] = -(g0.x + g0.y); tw[4] = -(g1.x + g1.y); tw[5] = -(g2.x + g2.y);
         }
       }
       float total = 0.f;
       if (__ballot_sync(0xffffffffu, ok)) total = warp_sum_n<NRED>(c, lane);
       if (slot.owner) tgt[ft * kTrackAcc + SLOT0 + slot.slot] = total;
     }
-    if (live) {
-      // camera-space adjoint of the sampled point (unscaled), source K / twist sums
-      const float dq0 = fm_fma(rs[0], G[0], fm_fma(rs[3], G[1], rs[6] * G[2]));
-      const float dq1 = fm_fma(rs[1], G[0], fm_fma(rs[4], G[1], rs[7] * G[2]));
-      const float dq2 = fm_fma(rs[2], G[0], fm_fma(rs[5], G[1], rs[8] * G[2]));
+    lc[0] = lc2[0].x + lc2[0].y;
+    lc[1] = lc2[1].x + lc2[1].y;
+    // camera-space adjoint of the sampled points (unscaled), source K / twist sums
+    auto finish = [&](int p, const float* q, float X0, float X1, float X2, float G0, float G1, float G2, float k0,
+                      float k1, float k2, float k3) {
+      const size_t sidx = row0 + p;
+      const float dq0 = fm_fma(rs[0], G0, fm_fma(rs[3], G1, rs[6] * G2));
+      const float dq1 = fm_fma(rs[1], G0, fm_fma(rs[4], G1, rs[7] * G2));
+      const float dq2 = fm_fma(rs[2], G0, fm_fma(rs[5], G1, rs[8] * G2));
       dq_out[sidx * 3 + 0] = dq0; dq_out[sidx * 3 + 1] = dq1; dq_out[sidx * 3 + 2] = dq2;
       const float e0 = dq0 * ks.ifx, e1 = dq1 * ks.ify;
-      acc[0] = kt[0] - e0 * q[0]; acc[1] = kt[1] - e1 * q[1]; acc[2] = kt[2] - e0 * q[2]; acc[3] = kt[3] - e1 * q[2];
-      const float c0 = Xw[0] - rs[9], c1 = Xw[1] - rs[10], c2 = Xw[2] - rs[11];
-      acc[4] = c1 * G[2] - c2 * G[1];
-      acc[5] = c2 * G[0] - c0 * G[2];
-      acc[6] = c0 * G[1] - c1 * G[0];
-      acc[7] = G[0]; acc[8] = G[1]; acc[9] = G[2];
-    }
+      acc[0] += k0 - e0 * q[0]; acc[1] += k1 - e1 * q[1]; acc[2] += k2 - e0 * q[2]; acc[3] += k3 - e1 * q[2];
+      const float c0 = X0 - rs[9], c1 = X1 - rs[10], c2 = X2 - rs[11];
+      acc[4] += c1 * G2 - c2 * G1;
+      acc[5] += c2 * G0 - c0 * G2;
+      acc[6] += c0 * G1 - c1 * G0;
+      acc[7] += G0; acc[8] += G1; acc[9] += G2;
+    };
+    if (live_a) finish(pa, qa, Xw[0].x, Xw[1].x, Xw[2].x, G[0].x, G[1].x, G[2].x, kt[0].x, kt[1].x, kt[2].x, kt[3].x);
+    if (live_b) finish(pb, qb, Xw[0].y, Xw[1].y, Xw[2].y, G[0].y, G[1].y, G[2].y, kt[0].y, kt[1].y, kt[2].y, kt[3].y);
   }
-  block_accumulate<2>(lc, sums, red);
-  block_accumulate<kTrackAcc>(acc, trackacc + (size_t)frame * kTrackAcc, red);
+  block_accumulate<2, kTrackThreads>(lc, sums, red);
+  block_accumulate<kTrackAcc, kTrackThreads>(acc, trackacc + (size_t)frame * kTrackAcc, red);
   // fold the warps' target-side slices into the per-frame accumulators (block_accumulate ended
   // with a barrier, so every slice is complete)
-  const int live_warps = (count + 31) >> 5;
-  for (int i = threadIdx.x; i < si.rows * kTrackAcc; i += kThreads) {
+  const int live_warps = (half + 31) >> 5;
+  for (int i = threadIdx.x; i < si.rows * kTrackAcc; i += kTrackThreads) {
     if (SHARED_K && i % kTrackAcc < 4) continue;  // those slots are not written in this mode
     double t = 0.0;
     for (int w = 0; w < live_warps; ++w) t += (double)s_tgt[(size_t)w * si.rows * kTrackAcc + i];
@@ -2590,8 +2637,8 @@ int fm_track_loss_fwd_sharded(const float* depth, const float* k4, const float* 
   TrackWs w = carve_track(ws, F, total_samples);
   cudaError_t e = cudaMemsetAsync(w.sums, 0, (char*)w.dq - (char*)w.sums, s);  // sums + accumulators
   if (e != cudaSuccess) return fail("fm_track_loss_fwd: memset", e);
-  dim3 grid((max_points + kThreads - 1) / kThreads, max_rows, num_segments);
-  const size_t smem = (size_t)max_rows * (kTrackRec + (kThreads / 32) * kTrackAcc) * sizeof(float);
+  dim3 grid((max_points + kTrackPoints - 1) / kTrackPoints, max_rows, num_segments);
+  const size_t smem = (size_t)max_rows * (2 * kTrackRec + (kTrackThreads / 32) * kTrackAcc) * sizeof(float);
   if (smem > 200 * 1024) return fail_msg("fm_track_loss_fwd: segment too long for shared memory");
   if (smem > 48 * 1024) {
     cudaError_t ea = shared_intrinsics
@@ -2601,10 +2648,10 @@ int fm_track_loss_fwd_sharded(const float* depth, const float* k4, const float* 
   }
   const TrackShard sh = {depth_frame0, src_frame_lo, src_frame_hi};
   if (shared_intrinsics)
-    k_track_src<true><<<grid, kThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis, mapping,
+    k_track_src<true><<<grid, kTrackThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis, mapping,
                                                   delta, w.sums, w.flag, w.dq, w.acc, H, W, sh);
   else
-    k_track_src<false><<<grid, kThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis, mapping,
+    k_track_src<false><<<grid, kTrackThreads, smem, s>>>(depth, k4, extrinsics, segments, track_xy, track_vis, mapping,
                                                    delta, w.sums, w.flag, w.dq, w.acc, H, W, sh);
   FM_CHECK_LAUNCH("fm_track_loss_fwd: k_track_src");
   if (loss) {

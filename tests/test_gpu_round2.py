@@ -71,7 +71,8 @@ def test_step_clock_adam_equals_by_value_adam():
 @pytest.mark.parametrize("full", [False, True], ids=["flow_only", "softmin_tracking"])
 def test_cuda_graph_replay_equals_eager_steps(full):
     """The update step replayed as one CUDA graph (from its third run on) follows the eager
-    trajectory: exactly for the flow-only step, to atomics noise with the tracking scatter."""
+    trajectory to the noise of the float atomics (the order of the REDs into the depth gradient is
+    not fixed from run to run)."""
     import bench
     from flowmap_b200.overfit import FusedOverfitter, OverfitCfg
     from flowmap_b200.types import Batch, Flows, Tracks
@@ -98,6 +99,6 @@ def test_cuda_graph_replay_equals_eager_steps(full):
     la, da, wa, _ = run(False)
     lb, db, wb, ngraphs = run(True)
     assert ngraphs == 1
-    tol = 1e-5 if full else 0.0
+    tol = 1e-5 if full else 1e-7
     assert max(abs(x - y) for x, y in zip(la, lb)) <= tol * abs(la[0])
-    assert rel_l2(db, da) <= tol and float((wb - wa).abs().max()) <= 1e-5 * (1.0 if full else 0.0)
+    assert rel_l2(db, da) <= tol and float((wb - wa).abs().max()) <= (1e-5 if full else 1e-6)
