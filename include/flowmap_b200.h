@@ -341,6 +341,12 @@ typedef struct {
 #define FM_STEP_ALL 0
 #define FM_STEP_FORWARD 1
 #define FM_STEP_BACKWARD 2
+/* Stream semantics: everything is ordered after the work already in `stream` and is complete, in
+ * stream order, when later work of `stream` runs.  With `tracks` the call internally forks part of
+ * its launches onto a second, library-owned stream (the tracking sweep beside the flow-loss kernel,
+ * the tracking loss's depth scatter beside the Procrustes backward) and joins it again with events
+ * before it returns; under stream capture (cudaStreamCaptureModeThreadLocal / Relaxed) these become
+ * parallel branches of the caller's graph. */
 int fm_overfit_step(const fm_overfit_step_args* args, void* stream);
 
 /* ---- stages either side of the hot path ---------------------------- */
