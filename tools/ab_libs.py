@@ -3,6 +3,13 @@ files, e.g. with -D knobs, instead of living behind run-time switches in the pro
 
   python tools/ab_libs.py flowmap_b200/csrc/ab/base.so flowmap_b200/csrc/ab/x.so ... [--no-step]
 
+Building a variant (the knobs are `#ifndef` defaults in csrc/fm_kernels.cu, e.g. FM_PATCH_LANES):
+
+  cd flowmap_b200/csrc && mkdir -p ab && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 \
+      --expt-extended-lambda -Xcompiler -fPIC -shared -DFM_PATCH_LANES=4 -o ab/lanes4.so fm_kernels.cu fm_io.cu
+
+(`git stash` + a normal build gives the committed state as the first, reference build.)
+
 For every build: results of the three path ops at a small and at the benchmark shape against the
 FIRST build (poses, loss, depth / weight / intrinsics gradients), CUDA-event times of the three ops
 at 150 x 360 x 640 on iid and on smooth flows, and the fused full / flow-only step (trajectory
