@@ -2913,8 +2913,11 @@ int fm_softmin_focal_bwd(const float* softmin, const float* cand_focal, const fl
 // from / joined to the caller's stream with events, so it is captured into the caller's CUDA graph as
 // a parallel branch.
 struct SideLane { cudaStream_t stream; cudaEvent_t fork, join; int state; };  // state 0 new, 1 ready, -1 unavailable
+// One lane per (host thread, device): a thread's calls are sequential, so its events are never
+// re-recorded while a wait on them is still to be issued; other threads have their own.  The lane is
+// created on the first call with tracks (an eager warm-up step, not inside a capture).
 static SideLane* side_lane() {
-  static SideLane lanes[64];
+  static thread_local SideLane lanes[64];
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   SideLane& l = lanes[dev];
