@@ -41,6 +41,7 @@ SIGNATURES = {
     "fm_procrustes_fwd_planned": (c_int, [_P, _P, _P, _P, c_float, _P, _P, _P, c_int, c_int, c_int, _P]),
     "fm_procrustes_bwd_planned": (c_int, [_P, _P, _P, _P, c_float, _P, ctypes.c_uint, _P, c_int, _P, _P, _P, _P,
                                           c_int, c_int, c_int, _P]),
+    "fm_procrustes_moments": (c_int, [_P, _P, _P, _P, c_float, _P, c_int, c_int, c_int, _P]),
     "fm_mask_sum": (c_int, [_P, _P, _P, c_size_t, _P]),
     "fm_flow_loss_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_float, c_float, c_int,
                                      _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
@@ -103,7 +104,7 @@ class OverfitStepArgs(ctypes.Structure):
                 ("track_loss", _P),
                 ("ws", _P), ("track_ws", _P), ("focal_step", c_int), ("defer_adam", c_int),
                 ("phase", c_int), ("splat_plan", _P), ("splat_overflow_max", ctypes.c_uint),
-                ("flow_grad_scale", _P), ("track_grad_scale", _P), ("clock", _P)]
+                ("flow_grad_scale", _P), ("track_grad_scale", _P), ("clock", _P), ("moments_k4", _P)]
 
 
 SIGNATURES["fm_overfit_step"] = (c_int, [ctypes.POINTER(OverfitStepArgs), _P])

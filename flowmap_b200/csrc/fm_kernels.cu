@@ -440,15 +440,31 @@ k_moments_dense(const float* __restrict__ depth, const float* __restrict__ k4,
 }
 
 // ================================================================== phase B: solve
-__global__ void k_solve(const double* __restrict__ moments, const float* __restrict__ depth,
+// moments_k4 != NULL: the sums were accumulated with the intrinsics moments_k4 (same principal points,
+// other focal lengths) before the step's own K was known.  Points scale per axis with the focal
+// ratio (p = S_b p', q = S_a q', S = diag(fx'/fx, fy'/fy, 1); the conditioning shift is along z), so
+// the 16 sums are rescaled exactly here -- and written back for later readers of the workspace.
+__global__ void k_solve(double* __restrict__ moments, const float* __restrict__ depth,
                         float* __restrict__ rt, PairState* __restrict__ state, int BP, PairLayout lay,
-                        int H, int W) {
+                        int H, int W, const float* __restrict__ moments_k4 = nullptr,
+                        const float* __restrict__ k4 = nullptr) {
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
   if (pair >= BP) return;
   const PairAddr pa = pair_addr(lay, pair, H * W);
   const double z0 = (double)__ldg(depth + pa.depth_a + (size_t)H * W + (size_t)(H / 2) * W + W / 2);
   double m[kNumMoments];
   for (int k = 0; k < kNumMoments; ++k) m[k] = moments[(size_t)pair * kNumMoments + k];
+  if (moments_k4) {
+    const int fa = pa.k4_frame_a, fb = fa + 1;
+    const double sa[3] = {(double)moments_k4[fa * 4 + 0] / (double)k4[fa * 4 + 0],
+                          (double)moments_k4[fa * 4 + 1] / (double)k4[fa * 4 + 1], 1.0};
+    const double sb[3] = {(double)moments_k4[fb * 4 + 0] / (double)k4[fb * 4 + 0],
+                          (double)moments_k4[fb * 4 + 1] / (double)k4[fb * 4 + 1], 1.0};
+    for (int i = 0; i < 3; ++i) { m[1 + i] *= sb[i]; m[4 + i] *= sa[i]; }
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) m[7 + a * 3 + c] *= sa[a] * sb[c];
+    for (int k = 0; k < kNumMoments; ++k) moments[(size_t)pair * kNumMoments + k] = m[k];
+  }
   const double shift[3] = {0.0, 0.0, z0};
   PairState st;
   float out[12];
@@ -2302,9 +2318,10 @@ int fm_reproject(const float* xyz, const float* rt, const float* k4, float* xy, 
 static int procrustes_fwd_impl(const float* depth, const float* k4, const float* backward_flow,
                                const float* weights, float wsens, const int64_t* indices,
                                int num_indices, float* rt, void* ws, int B, int F, int H, int W,
-                               void* stream, const PairLayout* layout = nullptr, void* plan = nullptr) {
+                               void* stream, const PairLayout* layout = nullptr, void* plan = nullptr,
+                               const float* moments_k4 = nullptr, bool solve = true) {
   const PairLayout lay = layout ? *layout : dense_layout(F, H, W);
-  if (!depth || !k4 || !backward_flow || !rt || !ws || bad_dims(B, F, H, W))
+  if (!depth || !k4 || !backward_flow || (!rt && solve) || !ws || bad_dims(B, F, H, W))
     return fail_msg("fm_procrustes_fwd: bad arguments");
   if (plan && (B != 1 || indices || layout || !tiled_shape_ok(F, H, W)))
     return fail_msg("fm_procrustes_fwd: the splat plan serves the dense single-video path with W % 4 == 0");
@@ -2312,6 +2329,13 @@ static int procrustes_fwd_impl(const float* depth, const float* k4, const float*
   cudaStream_t s = (cudaStream_t)stream;
   Workspace w = carve(ws, B, F);
   const int BP = B * (F - 1);
+  if (moments_k4) {  // fm_procrustes_moments already ran with those intrinsics
+    if (plan || indices || layout) return fail_msg("fm_procrustes_fwd: precomputed moments serve the dense path");
+    if (!solve) return 0;
+    k_solve<<<(BP + 63) / 64, 64, 0, s>>>(w.moments, depth, rt, w.state, BP, lay, H, W, moments_k4, k4);
+    FM_CHECK_LAUNCH("fm_procrustes_fwd: k_solve");
+    return 0;
+  }
   cudaError_t e = cudaMemsetAsync(w.moments, 0, (size_t)BP * kNumMoments * sizeof(double), s);
   if (e != cudaSuccess) return fail("fm_procrustes_fwd: memset", e);
   if (plan) {
@@ -2335,6 +2359,7 @@ static int procrustes_fwd_impl(const float* depth, const float* k4, const float*
     k_moments_dense<1, 0><<<pg, kThreads, 0, s>>>(depth, k4, backward_flow, weights, w.moments, wsens, lay, H, W, BP, procrustes_rounds(H, W, items / 4, pg, true));
   }
   if (!plan) FM_CHECK_LAUNCH("fm_procrustes_fwd: k_moments");
+  if (!solve) return 0;
   k_solve<<<(BP + 63) / 64, 64, 0, s>>>(w.moments, depth, rt, w.state, BP, lay, H, W);
   FM_CHECK_LAUNCH("fm_procrustes_fwd: k_solve");
   return 0;
@@ -2345,6 +2370,13 @@ int fm_procrustes_fwd(const float* depth, const float* k4, const float* backward
                       void* ws, int B, int F, int H, int W, void* stream) {
   return procrustes_fwd_impl(depth, k4, backward_flow, weights, 0.f, indices, num_indices, rt, ws, B, F,
                              H, W, stream);
+}
+
+int fm_procrustes_moments(const float* depth, const float* k4, const float* backward_flow,
+                          const float* weights, float weight_sensitivity, void* ws, int F, int H, int W,
+                          void* stream) {
+  return procrustes_fwd_impl(depth, k4, backward_flow, weights, weight_sensitivity, nullptr, 0, nullptr, ws, 1, F,
+                             H, W, stream, nullptr, nullptr, nullptr, /*solve=*/false);
 }
 
 static int procrustes_bwd_impl(const float* depth, const float* k4, const float* backward_flow,
@@ -2956,7 +2988,8 @@ int fm_overfit_step(const fm_overfit_step_args* a, void* stream) {
     }
     // Model.forward: Procrustes poses (model.py:54-90)
     if ((rc = procrustes_fwd_impl(a->depth, k4, a->bflow, a->weight_logits, a->weight_sensitivity,
-                                  a->indices, a->num_indices, a->rt, a->ws, 1, F, H, W, stream, nullptr, plan)))
+                                  a->indices, a->num_indices, a->rt, a->ws, 1, F, H, W, stream, nullptr, plan,
+                                  (a->indices || plan) ? nullptr : a->moments_k4)))
       return rc;
     // The flow loss and the tracking sweep both need only the poses: with tracking on they run as
     // two branches of the step (the tracking sweep is issue-bound, the flow kernel waits on memory:

@@ -178,6 +178,8 @@ class FusedOverfitter(Overfitter):
             self._sw_focal = torch.zeros(1, device=dev)
             self._sw_ws = torch.empty(lib().fm_softmin_workspace_bytes(1, n), dtype=torch.uint8,
                                       device=dev)
+            # candidate 0's intrinsics for every frame: what the early moment pass of a sweep step uses
+            self._k4_base = self._cand_k4.reshape(-1, 4)[0].expand(f, 4).contiguous()
             self.window = []
             self.injected_indices = None
         else:
@@ -287,30 +289,47 @@ class FusedOverfitter(Overfitter):
         dev = self.rt.device
         st = torch.cuda.current_stream().cuda_stream
         P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
-        idx = self.injected_indices
-        if idx is None:
-            if update:  # seeded by the step clock (replayable); intrinsics_softmin.py:90
-                idx = ops.random_subset_clock(self._clock, h * w, self._idx_buf)
-            else:
-                idx = ops.random_subset(h * w, min(c.softmin_points, h * w), dev)
-        idx = idx.contiguous()
         n = c.softmin_candidates
         wl = P(self._wlog) if c.use_correspondence_weights else None
         sens = c.weight_sensitivity if c.use_correspondence_weights else 0.0
+        # All-pixel Procrustes: the moment pass of the step does not have to wait for the focal length
+        # the sweep is about to produce -- the sums for one K follow exactly from the sums for another
+        # (fm_overfit_step_args.moments_k4) -- so it runs beside the sweep, on the candidate-0 intrinsics.
+        early_moments = update and self._indices is None and self._plan is None
+        cur = torch.cuda.current_stream()
         with torch.cuda.device(dev):
-            check(L.fm_softmin_sweep_fwd(P(self._depth), wl, sens, P(self.flows.backward), P(idx),
-                                         idx.numel(), P(self._cand_k4), n, P(self._sw_err),
-                                         P(self._sw_rt), P(self._sw_ws), 1, f, h, w, st),
-                  "fm_softmin_sweep_fwd")
-            check(L.fm_softmin_focal(P(self._sw_err), P(self._cand_f), n, 1, P(self._sw_sm),
-                                     P(self._sw_focal), st), "fm_softmin_focal")
+            if early_moments:
+                self._side_stream.wait_stream(cur)
+                check(L.fm_procrustes_moments(P(self._depth), P(self._k4_base), P(self.flows.backward), wl, sens,
+                                              P(self._ws), f, h, w, st), "fm_procrustes_moments")
+            with torch.cuda.stream(self._side_stream if early_moments else cur):
+                sst = torch.cuda.current_stream().cuda_stream
+                idx = self.injected_indices
+                if idx is None:
+                    if update:  # seeded by the step clock (replayable); intrinsics_softmin.py:90
+                        idx = ops.random_subset_clock(self._clock, h * w, self._idx_buf)
+                    else:
+                        idx = ops.random_subset(h * w, min(c.softmin_points, h * w), dev)
+                idx = idx.contiguous()
+                check(L.fm_softmin_sweep_fwd(P(self._depth), wl, sens, P(self.flows.backward), P(idx),
+                                             idx.numel(), P(self._cand_k4), n, P(self._sw_err),
+                                             P(self._sw_rt), P(self._sw_ws), 1, f, h, w, sst),
+                      "fm_softmin_sweep_fwd")
+                check(L.fm_softmin_focal(P(self._sw_err), P(self._cand_f), n, 1, P(self._sw_sm),
+                                         P(self._sw_focal), sst), "fm_softmin_focal")
+            if early_moments:
+                cur.wait_stream(self._side_stream)
+            a.moments_k4 = P(self._k4_base) if early_moments else None
             # all-pixel dense path: the logits of pairs >= 1 are updated inside the step (their
             # gradient is final there); depth and pair 0 wait for the sweep's backward
             fuse = update and c.use_correspondence_weights and self._indices is None and w % 4 == 0
             a.focal = P(self._sw_focal)
             a.step = 1 if fuse else 0  # on / off: the bias corrections come from the step clock
             a.defer_adam = 1 if fuse else 0
-            check(L.fm_overfit_step(self._ctypes.byref(a), st), "fm_overfit_step")
+            try:
+                check(L.fm_overfit_step(self._ctypes.byref(a), st), "fm_overfit_step")
+            finally:
+                a.moments_k4 = None
             a.defer_adam = 0
             # The sweep's backward only touches the gradients of frames 0 / 1 (the candidate Procrustes
             # runs on the first pair): the depth update of every other frame runs beside it on a second

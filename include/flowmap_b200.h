@@ -337,6 +337,11 @@ typedef struct {
                                     bias corrections come from it instead of `step` / `focal_step`
                                     (which then only switch the update on), so that consecutive steps
                                     are launches with identical arguments: a CUDA graph can replay them */
+  const float* moments_k4;       /* NULL, or the intrinsics (F,4) with which fm_procrustes_moments has ALREADY
+                                    accumulated this step's moment sums into `ws` (all-pixel Procrustes only;
+                                    same principal points as k4, any focal lengths): the step then starts at the
+                                    pose solve and rescales the sums to its own K.  Lets the caller run the
+                                    moment pass beside the work that produces the focal length (the softmin sweep). */
 } fm_overfit_step_args;
 #define FM_STEP_ALL 0
 #define FM_STEP_FORWARD 1
@@ -348,6 +353,14 @@ typedef struct {
  * before it returns; under stream capture (cudaStreamCaptureModeThreadLocal / Relaxed) these become
  * parallel branches of the caller's graph. */
 int fm_overfit_step(const fm_overfit_step_args* args, void* stream);
+
+/* Phase A alone (all pixels, one video): the 16 weighted moment sums of every frame pair into `ws`,
+ * for intrinsics `k4` (F,4); `weights` are plain weights (weight_sensitivity == 0) or logits.  See
+ * fm_overfit_step_args.moments_k4.  (Model.forward's first reduction, model.py:75-90 with
+ * projection.py:222-242.) */
+int fm_procrustes_moments(const float* depth, const float* k4, const float* backward_flow,
+                          const float* weights, float weight_sensitivity, void* ws, int F, int H, int W,
+                          void* stream);
 
 /* ---- stages either side of the hot path ---------------------------- */
 

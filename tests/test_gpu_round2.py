@@ -102,3 +102,31 @@ def test_cuda_graph_replay_equals_eager_steps(full):
     tol = 1e-5 if full else 1e-7
     assert max(abs(x - y) for x, y in zip(la, lb)) <= tol * abs(la[0])
     assert rel_l2(db, da) <= tol and float((wb - wa).abs().max()) <= (1e-5 if full else 1e-6)
+
+
+def test_early_moment_pass_of_a_sweep_step_matches_the_sequential_order():
+    """An update step of the softmin stage accumulates the Procrustes moments beside the sweep, on the
+    candidate-0 intrinsics, and rescales them to the focal length the sweep produced
+    (fm_procrustes_moments + fm_overfit_step_args.moments_k4).  An evaluation step of the same state
+    runs the moment pass after the sweep with the final intrinsics: same loss, same poses."""
+    import bench
+    from flowmap_b200.overfit import FusedOverfitter, OverfitCfg
+    from flowmap_b200.types import Batch, Flows, Tracks
+    dev = torch.device("cuda:0")
+    f, h, w = 10, 72, 96
+    inp = bench.synthetic_inputs(f, h, w, seed=3)
+    batch = Batch(torch.zeros(1, f, 3, h, w, device=dev), torch.arange(f, device=dev)[None], ["s"], ["d"])
+    flows = Flows(*(inp[k].to(dev) for k in ("fwd", "bwd", "fmask", "bmask")))
+    tracks = [Tracks(xy, vis, s) for xy, vis, s in bench.synthetic_track_arrays(f, n_points=64, interval=3, radius=2)]
+    o = FusedOverfitter(OverfitCfg(intrinsics="softmin", use_tracking=True, tracking_enable_after=0), batch, flows,
+                        tracks, device=dev)
+    with torch.no_grad():
+        o.model.backbone.depth.copy_(1.0 + inp["depth"])
+        o.model.backbone.weights.copy_(inp["wparam"])
+    o.injected_indices = torch.randperm(h * w, generator=torch.Generator().manual_seed(5))[:512].to(dev)
+    o.use_cuda_graph = False
+    loss_eval, rt_eval = o.training_step(update=False)
+    loss_eval, rt_eval = float(loss_eval), rt_eval.clone()
+    loss_upd, rt_upd = o.training_step(update=True)
+    assert abs(float(loss_upd) - loss_eval) <= 2e-6 * abs(loss_eval)
+    assert float((rt_upd - rt_eval).abs().max()) <= 2e-6
