@@ -130,3 +130,42 @@ def test_early_moment_pass_of_a_sweep_step_matches_the_sequential_order():
     loss_upd, rt_upd = o.training_step(update=True)
     assert abs(float(loss_upd) - loss_eval) <= 2e-6 * abs(loss_eval)
     assert float((rt_upd - rt_eval).abs().max()) <= 2e-6
+
+
+def test_tracking_sweep_sharded_by_source_frame_adds_up():
+    """fm_track_loss_fwd_sharded restricted to source frames [lo, hi): the head of the tracking
+    workspace (loss sum, valid count, per-frame accumulators; what the ranks all-reduce) of two
+    complementary shards adds up to the unsharded sweep's, with a shard whose depth pointer starts
+    at its first source frame."""
+    from flowmap_b200 import ops
+    from flowmap_b200._lib import check, lib
+    from flowmap_b200.types import Tracks
+    dev = torch.device("cuda:0")
+    f, h, w = 9, 24, 32
+    g = torch.Generator().manual_seed(21)
+    depth = (1.0 + 0.5 * torch.rand(1, f, h, w, generator=g)).to(dev)
+    ext = torch.eye(4).repeat(1, f, 1, 1)
+    ext[0, :, :3, 3] = 0.05 * torch.randn(f, 3, generator=g)
+    ext = ext.to(dev).contiguous()
+    s = (h * w) ** 0.5
+    k4 = torch.tensor([0.9 * s / w, 0.9 * s / h, 0.5, 0.5]).expand(1, f, 4).contiguous().to(dev)
+    tracks = [Tracks(torch.rand(1, f, 300, 2, generator=g).to(dev), (torch.rand(1, f, 300, generator=g) < 0.7).to(dev), 0),
+              Tracks(torch.rand(1, 4, 70, 2, generator=g).to(dev), (torch.rand(1, 4, 70, generator=g) < 0.7).to(dev), 3)]
+    pk = ops.PackedTracks(tracks, dev)
+    L = lib()
+    P = lambda t: t.data_ptr()  # noqa: E731
+    st = torch.cuda.current_stream().cuda_stream
+    head = L.fm_track_reduce_bytes(f) // 8
+
+    def sweep(lo, hi, frame0):
+        ws = torch.zeros(L.fm_track_workspace_bytes(f, pk.total), dtype=torch.uint8, device=dev)
+        check(L.fm_track_loss_fwd_sharded(P(depth[:, frame0:]), P(k4), P(ext), P(pk.seg), pk.num_segments, pk.max_rows,
+                                          pk.max_points, P(pk.xy), P(pk.vis), pk.total, 0, 0.01, 100.0, None, P(ws),
+                                          f, h, w, frame0, lo, hi, 1, st), "fm_track_loss_fwd_sharded")
+        torch.cuda.synchronize()
+        return ws[:head * 8].view(torch.float64).clone()
+
+    full = sweep(0, f, 0)
+    parts = sweep(0, 4, 0) + sweep(4, f, 4)
+    assert float(full[1]) > 100  # enough valid terms for the comparison to mean something
+    assert float((parts - full).abs().max()) <= 1e-5 * float(full.abs().max())
