@@ -256,15 +256,10 @@ __device__ __forceinline__ ItemRange block_item_range(long long total) {
 // a few frame pairs and share their bands.  Blocks are rotated between rounds so that the odd chunk of
 // an uneven split does not always land on the same block.
 __device__ __forceinline__ ItemRange block_item_range(long long total, int rounds, int round) {
-  const long long len = (total + rounds - 1) / rounds;
-  long long s0 = len * round, s1 = s0 + len;
-  if (s0 > total) s0 = total;
-  if (s1 > total) s1 = total;
-  const long long g = gridDim.x;
-  const long long b = ((long long)blockIdx.x + ((long long)round * g) / rounds) % g;
+  const ItemSpan sp = item_span(total, rounds, round, (int)blockIdx.x, (int)gridDim.x);
   ItemRange r;
-  r.i0 = (int)(s0 + ((s1 - s0) * b) / g);
-  r.i1 = (int)(s0 + ((s1 - s0) * (b + 1)) / g);
+  r.i0 = (int)sp.i0;
+  r.i1 = (int)sp.i1;
   return r;
 }
 

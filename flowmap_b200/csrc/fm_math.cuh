@@ -139,6 +139,27 @@ FM_HD void ray_of(float x, float y, const Cam& k, float& rx, float& ry) {
 // unnormalise -> clip -> floor sequence.  Out-of-range taps get weight 0 and a clamped
 // (in-bounds) index, so callers may load unconditionally.
 // ---------------------------------------------------------------------------------
+// Work decomposition of the persistent dense kernels (see block_item_range in fm_kernels.cu):
+// `total` items, walked in `rounds` consecutive slices; a slice is cut into `grid` contiguous parts
+// of q or q + 1 items.  The parts with the extra item are handed out round-robin ACROSS the rounds
+// (round r starts where round r - 1 stopped), so that over all rounds the blocks' totals differ by
+// at most two items.  Every item belongs to exactly one (round, block).
+struct ItemSpan { long long i0, i1; };
+FM_HD ItemSpan item_span(long long total, int rounds, int round, int block, int grid) {
+  const long long len = (total + rounds - 1) / rounds;
+  long long s0 = len * round, s1 = s0 + len;
+  if (s0 > total) s0 = total;
+  if (s1 > total) s1 = total;
+  const long long g = grid;
+  const long long first = ((long long)round * (len % g)) % g;  // block that takes part 0 of this slice
+  const long long part = ((long long)block - first + g) % g;
+  const long long q = (s1 - s0) / g, extra = (s1 - s0) % g;
+  ItemSpan r;
+  r.i0 = s0 + part * q + (part < extra ? part : extra);
+  r.i1 = r.i0 + q + (part < extra ? 1 : 0);
+  return r;
+}
+
 struct Taps {
   int x0, y0, x1, y1;      // clamped tap coordinates
   float fx0, fy0;          // x0 / y0 as floats (they fall out of the floor computation)

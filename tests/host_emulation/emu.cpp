@@ -32,6 +32,20 @@ extern "C" {
 
 size_t emu_state_bytes() { return sizeof(PairState); }
 
+// item_span (fm_math.cuh): how often every item is covered by the (round, block) spans, and the
+// largest / smallest number of items one block receives over all rounds.
+void emu_item_cover(long long total, int rounds, int grid, int* cover, long long* per_block_minmax) {
+  std::vector<long long> per(grid, 0);
+  for (int r = 0; r < rounds; ++r)
+    for (int b = 0; b < grid; ++b) {
+      const ItemSpan sp = item_span(total, rounds, r, b, grid);
+      for (long long i = sp.i0; i < sp.i1; ++i) cover[i] += 1;
+      per[b] += sp.i1 - sp.i0;
+    }
+  per_block_minmax[0] = *std::min_element(per.begin(), per.end());
+  per_block_minmax[1] = *std::max_element(per.begin(), per.end());
+}
+
 void emu_procrustes_fwd(const float* depth, const float* k4, const float* bflow, const float* weights,
                         const int64_t* indices, int n_idx, float* rt, PairState* state, int B, int F,
                         int H, int W) {

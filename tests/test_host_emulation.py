@@ -132,3 +132,20 @@ def test_emulated_step_matches_reference(emu, name, mapping, focal, npts, lean):
     assert rel_l2(r["g_depth"], g64["g_depth"]) <= max(1e-4, 3 * ref_noise_d)
     assert rel_l2(r["g_wparam"], g64["g_wparam"]) <= max(1e-4, 3 * ref_noise_w)
     assert abs(r["g_focal"] - float(g64["g_focal"])) <= 1e-4 * abs(float(g64["g_focal"]))
+
+
+@pytest.mark.parametrize("total,rounds,grid", [
+    (33525, 1, 444), (33525, 9, 444), (134100, 37, 444),   # 149 pairs of 360x640 / 720x1280, B200 grid
+    (16762, 4, 444),                                        # one rank of an 8-way split at 720p
+    (7, 3, 5), (5, 8, 444), (1000, 1, 1), (4096, 16, 3), (0, 2, 4),
+])
+def test_item_decomposition_covers_every_item_once_and_is_balanced(emu, total, rounds, grid):
+    """block_item_range of the persistent dense kernels (item_span in fm_math.cuh): the (round, block)
+    spans tile the item list exactly, and the rotation between rounds keeps the blocks' totals within
+    a couple of items of each other (one odd item per round, moved around)."""
+    cover = np.zeros(max(total, 1), dtype=np.int32)
+    minmax = np.zeros(2, dtype=np.int64)
+    emu.emu_item_cover(ctypes.c_longlong(total), rounds, grid, _p(cover), _p(minmax))
+    assert (cover[:total] == 1).all()
+    if total >= grid * rounds:
+        assert minmax[1] - minmax[0] <= 2
