@@ -241,11 +241,10 @@ __device__ __forceinline__ void load_vec2(const float* p, float* out) {  // 2 * 
 // 9 %..70 % full one), and a block's per-unit constants change at most a couple of times.
 struct ItemRange { int i0, i1; };
 __device__ __forceinline__ ItemRange block_item_range(long long total) {
-  const long long per = (total + gridDim.x - 1) / gridDim.x;
-  long long i0 = (long long)blockIdx.x * per, i1 = i0 + per;
-  if (i0 > total) i0 = total;
-  if (i1 > total) i1 = total;
-  ItemRange r; r.i0 = (int)i0; r.i1 = (int)i1;
+  const ItemSpan sp = item_span(total, 1, 0, (int)blockIdx.x, (int)gridDim.x);
+  ItemRange r;
+  r.i0 = (int)sp.i0;
+  r.i1 = (int)sp.i1;
   return r;
 }
 // The same decomposition applied to each of `rounds` consecutive slices of the item list (all blocks
