@@ -32,6 +32,28 @@ extern "C" {
 
 size_t emu_state_bytes() { return sizeof(PairState); }
 
+// lean_term (one point) against lean_term2 (two points packed as float32x2, the form k_flow_lean and
+// k_track_src evaluate): out[0..1] = 7 values per point from the scalar form, out2 the same from the
+// packed form.  dir / off: camera-space direction and offset (P = D * dir + off), k4: intrinsics,
+// xy: reference position, fl: flow, mapping / delta: robust map.
+void emu_lean_terms(const float* D, const float* dir, const float* off, const float* k4, const float* xy,
+                    const float* fl, int mapping, float delta, int H, int W, float* out, float* out2) {
+  const RobustCfg rc = make_robust(mapping, delta, H, W);
+  K4 kk; kk.fx = k4[0]; kk.fy = k4[1]; kk.cx = k4[2]; kk.cy = k4[3];
+  const Cam cam = make_cam(kk);
+  for (int i = 0; i < 2; ++i) {
+    const LeanTerm t = lean_term(D[i], dir[i * 3 + 0], dir[i * 3 + 1], dir[i * 3 + 2], off[0], off[1], off[2], cam,
+                                 xy[i * 2 + 0], xy[i * 2 + 1], fl[i * 2 + 0], fl[i * 2 + 1], 1.0f, rc);
+    const float v[7] = {t.loss, t.d0, t.d1, t.d2, t.uvx, t.uvy, t.su};
+    for (int k = 0; k < 7; ++k) out[i * 7 + k] = v[k];
+  }
+  const LeanTerm2 t2 = lean_term2(f2(D[0], D[1]), f2(dir[0], dir[3]), f2(dir[1], dir[4]), f2(dir[2], dir[5]),
+                                  f2s(off[0]), f2s(off[1]), f2s(off[2]), cam2(cam, cam), f2(xy[0], xy[2]),
+                                  f2(xy[1], xy[3]), f2(fl[0], fl[2]), f2(fl[1], fl[3]), f2s(1.0f), rc);
+  const F2 v2[7] = {t2.loss, t2.d0, t2.d1, t2.d2, t2.uvx, t2.uvy, t2.su};
+  for (int k = 0; k < 7; ++k) { out2[k] = v2[k].x; out2[7 + k] = v2[k].y; }
+}
+
 // item_span (fm_math.cuh): how often every item is covered by the (round, block) spans, and the
 // largest / smallest number of items one block receives over all rounds.
 void emu_item_cover(long long total, int rounds, int grid, int* cover, long long* per_block_minmax) {

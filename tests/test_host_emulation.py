@@ -149,3 +149,28 @@ def test_item_decomposition_covers_every_item_once_and_is_balanced(emu, total, r
     assert (cover[:total] == 1).all()
     if total >= grid * rounds:
         assert minmax[1] - minmax[0] <= 2
+
+
+@pytest.mark.parametrize("mapping", [0, 1, 2], ids=["huber", "l1", "l2"])
+def test_packed_two_point_term_equals_the_scalar_term(emu, mapping):
+    """lean_term2 (two points as one float32x2 computation: k_flow_lean's pixel pairs, k_track_src's
+    point pairs) against lean_term on each point, incl. a point behind the camera plane
+    (z + eps == 0: the nan_to_num branch of projection.py:56) next to an ordinary one."""
+    rng = np.random.default_rng(7)
+    for case in range(200):
+        D = rng.uniform(0.5, 2.0, 2).astype(np.float32)
+        dirs = rng.normal(0, 0.3, (2, 3)).astype(np.float32)
+        dirs[:, 2] = rng.uniform(0.7, 1.3, 2)
+        off = rng.normal(0, 0.05, 3).astype(np.float32)
+        if case % 10 == 0:  # first point exactly on the plane z + eps = 0
+            dirs[0, 2] = 0.0
+            off[2] = np.float32(-1e-5)
+        k4 = np.array([0.9, 1.2, 0.5, 0.5], dtype=np.float32)
+        xy = rng.uniform(0, 1, (2, 2)).astype(np.float32)
+        fl = rng.normal(0, 0.01, (2, 2)).astype(np.float32)
+        out, out2 = np.zeros(14, np.float32), np.zeros(14, np.float32)
+        emu.emu_lean_terms(_p(D), _p(dirs), _p(off), _p(k4), _p(xy), _p(fl), mapping, ctypes.c_float(0.01), 36, 48,
+                           _p(out), _p(out2))
+        ok = np.isfinite(out)
+        assert (np.isfinite(out2) == ok).all()
+        assert np.allclose(out2[ok], out[ok], rtol=2e-6, atol=1e-7), (case, out, out2)
